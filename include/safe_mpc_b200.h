@@ -1,0 +1,196 @@
+/*
+ * safe_mpc_b200.h -- C ABI of the B200-native batched RTI-MPC engine.
+ *
+ * This is the drop-in boundary for the hot path of idra-lab/safe-mpc: everything the
+ * reference delegates to `acados_template.AcadosOcpSolver` + CasADi/adam/L4CasADi generated
+ * code (reference call sites: src/safe_mpc/controller.py:141-164,193,208-209,247) plus the
+ * per-problem control logic wrapped around it (controller.py:169-184,226-231,274-284,
+ * 375-388,448-498; env_model.py:192-206; scripts/mpc.py:102-291), batched over B
+ * independent problems that live on one GPU.
+ *
+ * Conventions
+ *   - plain C, no torch types; every array argument is a caller-owned pointer.
+ *   - `mem` says where the caller's arrays live: SMPC_HOST (pageable or pinned host memory;
+ *     the library does the H2D/D2H copies on its own stream) or SMPC_DEVICE (device pointers,
+ *     e.g. torch tensor .data_ptr(); no copies, no sync).
+ *   - caller-side layout is batch-major row-major: x[B][nx], xg[B][N+1][nx], ug[B][N][nu].
+ *     (Internally the engine keeps a 32-problem-wide AoSoA layout; see DESIGN.md.)
+ *   - every function returns 0 on success, <0 on API/CUDA error (text via smpc_last_error).
+ *     Per-problem solver status uses the acados codes the reference consumes
+ *     (controller.py:166,279,379,489): 0 ok, 1 NaN, 2 max-iter, 3 min-step, 4 QP failure.
+ *   - one handle per (GPU, controller type, N, batch); not re-entrant; no global state.
+ *   - there is NO CPU fallback: without a CUDA device smpc_create fails with SMPC_ERR_CUDA.
+ */
+#ifndef SAFE_MPC_B200_H
+#define SAFE_MPC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMPC_NQ 5            /* config.yaml:10 n_dofs (compile-time in this build)     */
+#define SMPC_NX (2 * SMPC_NQ)
+#define SMPC_NU SMPC_NQ
+#define SMPC_NPAIR 6         /* config.yaml:205-216 collision_pairs (capsule-capsule)  */
+#define SMPC_MAX_POINTS 8    /* moving points: [0]=EE, then capsule end points          */
+#define SMPC_HID 256         /* config.yaml:66 network_size hidden width                */
+#define SMPC_NN_NPARAM (SMPC_HID * SMPC_NX + SMPC_HID + 2 * (SMPC_HID * SMPC_HID + SMPC_HID) + SMPC_HID + 1)
+
+/* memory space of caller arrays */
+#define SMPC_HOST 0
+#define SMPC_DEVICE 1
+
+/* error codes */
+#define SMPC_OK 0
+#define SMPC_ERR_ARG (-1)
+#define SMPC_ERR_CUDA (-2)
+#define SMPC_ERR_UNSUPPORTED (-3)
+
+/* controller state machines (reference utils.py:64-75 + classes in controller.py) */
+enum {
+  SMPC_CTRL_NAIVE = 0,          /* NaiveController            controller.py:251-284 */
+  SMPC_CTRL_ZEROVEL = 1,        /* TerminalZeroVelocity       controller.py:295-317 */
+  SMPC_CTRL_ST = 2,             /* STController               controller.py:319-361 */
+  SMPC_CTRL_STWA = 3,           /* STWAController             controller.py:364-393 */
+  SMPC_CTRL_HTWA = 4,           /* HTWAController             controller.py:396-401 */
+  SMPC_CTRL_RECEDING = 5,       /* RecedingController         controller.py:404-502 */
+  SMPC_CTRL_REAL_RECEDING = 6,  /* RealReceding               controller.py:504-565 */
+  SMPC_CTRL_EVERYWHERE = 7,     /* ControllerSafeSetEverywhere controller.py:646-689 */
+  SMPC_CTRL_BACKUP = 8          /* SafeBackupController       controller.py:692-712 */
+};
+
+/* which stages carry the viability-network row (safe_set.py:82-104) */
+enum {
+  SMPC_NN_NONE = 0,
+  SMPC_NN_TERMINAL = 1,         /* ST / STWA / HTWA / RealReceding                  */
+  SMPC_NN_RECEDING = 2,         /* stages 1..N-1 gated by p[4], terminal always on */
+  SMPC_NN_EVERYWHERE = 3        /* stages 1..N, never gated                        */
+};
+
+enum { SMPC_COST_ZERO = 0, SMPC_COST_EXT = 1, SMPC_COST_NLS = 2 };
+
+/*
+ * Static description of one OCP family (shared by all B problems of a handle).
+ * Filled by the host layer from config.yaml + URDF exactly as the reference's
+ * Parameters / AdamModel / AbstractController.__init__ do (parser.py:60-221,
+ * env_model.py:18-165, controller.py:12-125).
+ */
+typedef struct smpc_problem {
+  /* ---- dimensions and modes ---- */
+  int32_t nq;                    /* must equal SMPC_NQ                                            */
+  int32_t N;                     /* horizon (config.yaml:5, --horizon)                            */
+  int32_t n_pairs;               /* must equal SMPC_NPAIR                                         */
+  int32_t n_points;              /* <= SMPC_MAX_POINTS                                            */
+  int32_t controller;            /* SMPC_CTRL_*                                                   */
+  int32_t nn_rows;               /* SMPC_NN_*                                                     */
+  int32_t nn_terminal_soft;      /* terminal NN row has an L1 slack (controller.py:348-354)       */
+  int32_t stage0_collision_rows; /* 0 when --noise > 0 (controller.py:68-75), else 1              */
+  int32_t cost_type;             /* SMPC_COST_*                                                   */
+  int32_t abort_flag;            /* config.yaml:58                                                */
+  int32_t qp_iter_max;           /* config.yaml:18 qp_max_iter                                    */
+  int32_t reserved_i[5];
+  /* ---- scalars ---- */
+  double dt;                     /* config.yaml:7                                                 */
+  double q_weight, r_weight;     /* config.yaml:35,39                                             */
+  double lm;                     /* levenberg_marquardt, config.yaml:21                           */
+  double alpha;                  /* safety margin in percent, p[3]                                */
+  double eps;                    /* config.yaml:48                                                */
+  double slack_penalty_e;        /* zl_e = zu_e of the soft terminal row (ws_r for ST, ws_t for receding) */
+  double tol_x, tol_tau, tol_obs, tol_safe, tol_conv; /* config.yaml:42-49                       */
+  double qp_mu0, qp_tol_stat, qp_tol_eq, qp_tol_ineq, qp_tol_comp, qp_alpha_min, qp_reg_prim;
+  double gravity[3];             /* world-frame gravity acceleration, (0,0,-9.80665)              */
+  double reserved_d[8];
+  /* ---- serial chain (lumped over locked/fixed joints, see host/robot_model.py) ---- */
+  double joint_R[SMPC_NQ][9];    /* row-major rotation parent-body <- joint frame at q=0          */
+  double joint_p[SMPC_NQ][3];    /* joint-frame origin in the parent body frame                   */
+  double joint_axis[SMPC_NQ][3]; /* unit axis in the joint's own frame                            */
+  double inertial[SMPC_NQ][10];  /* nominal: m, c[3], Ixx,Iyy,Izz,Ixy,Iyz,Ixz about the CoM       */
+  /* ---- bounds ---- */
+  double x_min[SMPC_NX], x_max[SMPC_NX];     /* model bounds widened by q_margin (env_model.py:115-121) */
+  double lbx[SMPC_NX], ubx[SMPC_NX];         /* OCP box, stages 1..N-1 (controller.py:49-51)            */
+  double lbx_e[SMPC_NX], ubx_e[SMPC_NX];     /* OCP box, stage N (controller.py:53-55,300-306,701-707)  */
+  double tau_min[SMPC_NU], tau_max[SMPC_NU]; /* env_model.py:113-114                                    */
+  double ee_ref[3];                          /* config.yaml:73                                          */
+  /* ---- points rigidly attached to bodies; point 0 is the end effector ---- */
+  int32_t point_body[SMPC_MAX_POINTS];
+  double point_local[SMPC_MAX_POINTS][3];
+  /* ---- capsule-capsule pairs: moving segment (points pa,pb) vs fixed world segment (C,D) ---- */
+  int32_t pair_pa[SMPC_NPAIR], pair_pb[SMPC_NPAIR];
+  double pair_C[SMPC_NPAIR][3], pair_D[SMPC_NPAIR][3];
+  double pair_lo_ocp[SMPC_NPAIR];  /* (r1+r2+2*margin)^2            env_model.py:266 */
+  double pair_lo_chk[SMPC_NPAIR];  /* (r1+r2)^2 - tol_obs           env_model.py:268 */
+  double pair_hi;                  /* 1e6                           env_model.py:266 */
+  /* ---- viability network (safe_set.py:26-43,82-87) ---- */
+  double nn_mean[SMPC_NQ], nn_std[SMPC_NQ];
+  const float* nn_weights;         /* host pointer, SMPC_NN_NPARAM floats:
+                                      W1[HID][NX] b1[HID] W2[HID][HID] b2[HID] W3[HID][HID] b3[HID] W4[HID] b4[1]
+                                      (row-major, torch nn.Linear convention y = W x + b); may be NULL if nn_rows==0 */
+} smpc_problem_t;
+
+typedef struct smpc_handle smpc_handle_t;
+
+/* --- life cycle (replaces AcadosOcpSolver(ocp, json_file, generate, build), controller.py:247) --- */
+int smpc_create(const smpc_problem_t* prob, int32_t batch, int32_t device, smpc_handle_t** out);
+void smpc_destroy(smpc_handle_t* h);
+const char* smpc_last_error(const smpc_handle_t* h);
+const char* smpc_version(void);
+
+/* --- per-problem plant data --- */
+/* perturbed inertial parameters of the simulated plant, [B][NQ][10]
+ * (replaces update_randomized_dynamics + the z1_randomized*.urdf files, env_model.py:321-328) */
+int smpc_set_plant_inertial(smpc_handle_t* h, const double* inertial, int32_t mem);
+/* additive torque noise drawn by the host with default_rng(seed=i) (mpc.py:126, env_model.py:196), [B][NU] */
+int smpc_set_torque_noise(smpc_handle_t* h, const double* tau_noise, int32_t mem);
+
+/* --- warm start (controller.py:195-200,390-393) --- */
+int smpc_set_guess(smpc_handle_t* h, const double* xg, const double* ug, int32_t mem);
+int smpc_get_guess(smpc_handle_t* h, double* xg, double* ug, int32_t mem);
+int smpc_get_temp(smpc_handle_t* h, double* x_temp, double* u_temp, int32_t mem);
+/* reset_controller(): fails=0, r=N, current_step=0 (controller.py:234-238,359-361,444-446) */
+int smpc_reset_controller(smpc_handle_t* h);
+
+/* --- one RTI iteration = AbstractController.solve(x0) (controller.py:136-167) ---
+ * uses the stored guess; writes x_temp/u_temp (fetch with smpc_get_temp) and status[B]. */
+int smpc_rti_solve(smpc_handle_t* h, const double* x0, int32_t* status, int32_t mem);
+
+/* --- controller.step(x) -> (u, abort_flag) for every problem (controller.py:274-284 etc.) ---
+ * active[B] (may be NULL = all active): problems with active==0 are left untouched. */
+int smpc_controller_step(smpc_handle_t* h, const double* x, const uint8_t* active,
+                         double* u, uint8_t* abort_flag, int32_t mem);
+
+/* --- plant step = AdamModel.integrate(x,u) (env_model.py:192-206) --- */
+int smpc_plant_step(smpc_handle_t* h, const double* x, const double* u,
+                    double* x_next, double* a_applied, int32_t mem);
+
+/* --- pieces exposed for parity tests and for the host-side mirror of AdamModel --- */
+/* tau_fun(x,u) (env_model.py:80-83), n rows */
+int smpc_tau(smpc_handle_t* h, int32_t n, const double* x, const double* u, double* tau, int32_t mem);
+/* ee_fun(x) (env_model.py:91-95) and the 6 collision-constraint values (env_model.py:263-271), n rows */
+int smpc_kinematics(smpc_handle_t* h, int32_t n, const double* x, double* ee, double* dist, int32_t mem);
+/* nn_func_x(x): c(x) with the handle's alpha (safe_set.py:100-102) and its gradient [n][NX] (grad may be NULL) */
+int smpc_nn_constraint(smpc_handle_t* h, int32_t n, const double* x, double* c, double* grad, int32_t mem);
+/* linearisation of one stage class at n points: see DESIGN.md "stage record" for the field order */
+int smpc_linearize(smpc_handle_t* h, double* lin /*[B][N+1][SMPC_LIN_FIELDS]*/, int32_t mem);
+#define SMPC_LIN_FIELDS 162
+
+/* --- per-problem controller state (controller.py attrs fails, r, last_status, x_viable) --- */
+enum { SMPC_STATE_FAILS = 0, SMPC_STATE_R = 1, SMPC_STATE_STATUS = 2, SMPC_STATE_QP_ITER = 3, SMPC_STATE_QP_STATUS = 4 };
+int smpc_get_state_i32(smpc_handle_t* h, int32_t field, int32_t* out, int32_t mem);
+int smpc_set_state_i32(smpc_handle_t* h, int32_t field, const int32_t* in, int32_t mem);
+int smpc_get_x_viable(smpc_handle_t* h, double* x_viable, int32_t mem);
+
+/* --- timing of the last call, milliseconds, CUDA events (replaces get_stats, controller.py:192-193) ---
+ * out[0]=time_lin out[1]=time_sim out[2]=time_qp out[3]=time_qp_solver_call out[4]=time_glob out[5]=time_reg out[6]=time_tot */
+int smpc_get_times(smpc_handle_t* h, double* out7);
+/* number of kernels this handle has launched so far (bench.py "gpu_launches") */
+int64_t smpc_launch_count(const smpc_handle_t* h);
+/* the CUDA stream the handle launches on (cudaStream_t as void*) */
+void* smpc_stream(smpc_handle_t* h);
+int smpc_sync(smpc_handle_t* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SAFE_MPC_B200_H */

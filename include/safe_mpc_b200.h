@@ -11,10 +11,9 @@
  * Conventions
  *   - plain C, no torch types; every array argument is a caller-owned pointer.
  *   - `mem` says where the caller's arrays live: SMPC_HOST (pageable or pinned host memory;
- *     the library does the H2D/D2H copies on its own stream) or SMPC_DEVICE (device pointers,
- *     e.g. torch tensor .data_ptr(); no copies, no sync).
+ *     the library does the H2D/D2H copies on its own stream and returns after they complete)
+ *     or SMPC_DEVICE (device pointers, e.g. torch tensor .data_ptr(); no copies, no sync).
  *   - caller-side layout is batch-major row-major: x[B][nx], xg[B][N+1][nx], ug[B][N][nu].
- *     (Internally the engine keeps a 32-problem-wide AoSoA layout; see DESIGN.md.)
  *   - every function returns 0 on success, <0 on API/CUDA error (text via smpc_last_error).
  *     Per-problem solver status uses the acados codes the reference consumes
  *     (controller.py:166,279,379,489): 0 ok, 1 NaN, 2 max-iter, 3 min-step, 4 QP failure.
@@ -33,10 +32,12 @@ extern "C" {
 #define SMPC_NQ 5            /* config.yaml:10 n_dofs (compile-time in this build)     */
 #define SMPC_NX (2 * SMPC_NQ)
 #define SMPC_NU SMPC_NQ
+#define SMPC_NZ (SMPC_NX + SMPC_NU)
 #define SMPC_NPAIR 6         /* config.yaml:205-216 collision_pairs (capsule-capsule)  */
 #define SMPC_MAX_POINTS 8    /* moving points: [0]=EE, then capsule end points          */
 #define SMPC_HID 256         /* config.yaml:66 network_size hidden width                */
 #define SMPC_NN_NPARAM (SMPC_HID * SMPC_NX + SMPC_HID + 2 * (SMPC_HID * SMPC_HID + SMPC_HID) + SMPC_HID + 1)
+#define SMPC_MAX_N 128       /* longest supported horizon                               */
 
 /* memory space of caller arrays */
 #define SMPC_HOST 0
@@ -72,6 +73,36 @@ enum {
 enum { SMPC_COST_ZERO = 0, SMPC_COST_EXT = 1, SMPC_COST_NLS = 2 };
 
 /*
+ * Stage record: the linearisation of one stage of one problem, SMPC_REC doubles.
+ * Written by the linearisation kernel, consumed by the QP kernel, readable through
+ * smpc_get_lin() for parity tests.  QP variable order is z = [du(5); dq(5); dv(5)].
+ */
+#define SMPC_REC 192
+#define SMPC_REC_U 0        /* 5   u_guess[k] (zeros at k=N)                                     */
+#define SMPC_REC_X 5        /* 10  x_guess[k]                                                    */
+#define SMPC_REC_G 15       /* 15  cost gradient, [u q v], scaled by the stage weight            */
+#define SMPC_REC_HQQ 30     /* 15  q-block of the cost Hessian, lower triangle row-major, scaled */
+#define SMPC_REC_TAU 45     /* 5   tau(x,u)                                                      */
+#define SMPC_REC_JTAU 50    /* 75  d tau / d [u q v], row-major 5x15                             */
+#define SMPC_REC_DIST 125   /* 6   squared capsule distances                                     */
+#define SMPC_REC_JDIST 131  /* 30  d dist / dq, row-major 6x5                                    */
+#define SMPC_REC_NN 161     /* 1   viability row value (5e5 when gated off)                      */
+#define SMPC_REC_JNN 162    /* 10  d c / d [q v]                                                 */
+#define SMPC_REC_B 172      /* 10  dynamics offset  A x_k + B u_k - x_{k+1}  (zeros at k=N)      */
+#define SMPC_REC_HU 182     /* 1   diagonal of the u-block of the Hessian incl. Levenberg-Marquardt */
+#define SMPC_REC_HV 183     /* 1   diagonal of the v-block incl. LM                              */
+#define SMPC_REC_HQ 184     /* 1   LM term added to the diagonal of the q-block                  */
+#define SMPC_REC_NNROW 185  /* 1   1.0 if the stage has a viability row                          */
+#define SMPC_REC_SOFT 186   /* 1   L1 penalty of the soft viability row, <0: hard                */
+#define SMPC_REC_NTAU 187   /* 1   number of torque rows (5, or 0 at k=N)                        */
+#define SMPC_REC_NDIST 188  /* 1   number of capsule rows (6, or 0 at stage 0 when noise>0)      */
+
+/* QP constraint slots of one stage (lam/t layout of smpc_get_qp): rows are
+ * [box x (10)] [tau (5)] [dist (6)] [nn (1)], slot = side*SMPC_QP_NR + row, then the two slacks */
+#define SMPC_QP_NR 22
+#define SMPC_QP_NC (2 * SMPC_QP_NR + 2)
+
+/*
  * Static description of one OCP family (shared by all B problems of a handle).
  * Filled by the host layer from config.yaml + URDF exactly as the reference's
  * Parameters / AdamModel / AbstractController.__init__ do (parser.py:60-221,
@@ -90,7 +121,10 @@ typedef struct smpc_problem {
   int32_t cost_type;             /* SMPC_COST_*                                                   */
   int32_t abort_flag;            /* config.yaml:58                                                */
   int32_t qp_iter_max;           /* config.yaml:18 qp_max_iter                                    */
-  int32_t reserved_i[5];
+  int32_t lm_scale_dt;           /* 1: LM term is scaled by the stage time step for k<N (acados
+                                    ocp_nlp_approximate_qp_matrices convention)    */
+  int32_t qp_cond_pred_corr;     /* HPIPM BALANCE: 1                                              */
+  int32_t reserved_i[3];
   /* ---- scalars ---- */
   double dt;                     /* config.yaml:7                                                 */
   double q_weight, r_weight;     /* config.yaml:35,39                                             */
@@ -130,10 +164,12 @@ typedef struct smpc_problem {
 } smpc_problem_t;
 
 typedef struct smpc_handle smpc_handle_t;
+typedef struct smpc_sim smpc_sim_t;
 
 /* --- life cycle (replaces AcadosOcpSolver(ocp, json_file, generate, build), controller.py:247) --- */
 int smpc_create(const smpc_problem_t* prob, int32_t batch, int32_t device, smpc_handle_t** out);
 void smpc_destroy(smpc_handle_t* h);
+/* text of the last error of this handle (h may be NULL: last error of smpc_create on this thread) */
 const char* smpc_last_error(const smpc_handle_t* h);
 const char* smpc_version(void);
 
@@ -152,11 +188,12 @@ int smpc_get_temp(smpc_handle_t* h, double* x_temp, double* u_temp, int32_t mem)
 int smpc_reset_controller(smpc_handle_t* h);
 
 /* --- one RTI iteration = AbstractController.solve(x0) (controller.py:136-167) ---
- * uses the stored guess; writes x_temp/u_temp (fetch with smpc_get_temp) and status[B]. */
-int smpc_rti_solve(smpc_handle_t* h, const double* x0, int32_t* status, int32_t mem);
+ * uses the stored guess; writes x_temp/u_temp (fetch with smpc_get_temp) and status[B].
+ * active[B] (may be NULL = all): problems with active==0 are skipped and keep their state;
+ * status may be NULL. */
+int smpc_rti_solve(smpc_handle_t* h, const double* x0, const uint8_t* active, int32_t* status, int32_t mem);
 
-/* --- controller.step(x) -> (u, abort_flag) for every problem (controller.py:274-284 etc.) ---
- * active[B] (may be NULL = all active): problems with active==0 are left untouched. */
+/* --- controller.step(x) -> (u, abort_flag) for every problem (controller.py:274-284 etc.) --- */
 int smpc_controller_step(smpc_handle_t* h, const double* x, const uint8_t* active,
                          double* u, uint8_t* abort_flag, int32_t mem);
 
@@ -167,13 +204,15 @@ int smpc_plant_step(smpc_handle_t* h, const double* x, const double* u,
 /* --- pieces exposed for parity tests and for the host-side mirror of AdamModel --- */
 /* tau_fun(x,u) (env_model.py:80-83), n rows */
 int smpc_tau(smpc_handle_t* h, int32_t n, const double* x, const double* u, double* tau, int32_t mem);
-/* ee_fun(x) (env_model.py:91-95) and the 6 collision-constraint values (env_model.py:263-271), n rows */
+/* ee_fun(x) (env_model.py:91-95) [n][3] and the 6 collision-constraint values (env_model.py:263-271) [n][6] */
 int smpc_kinematics(smpc_handle_t* h, int32_t n, const double* x, double* ee, double* dist, int32_t mem);
 /* nn_func_x(x): c(x) with the handle's alpha (safe_set.py:100-102) and its gradient [n][NX] (grad may be NULL) */
 int smpc_nn_constraint(smpc_handle_t* h, int32_t n, const double* x, double* c, double* grad, int32_t mem);
-/* linearisation of one stage class at n points: see DESIGN.md "stage record" for the field order */
-int smpc_linearize(smpc_handle_t* h, double* lin /*[B][N+1][SMPC_LIN_FIELDS]*/, int32_t mem);
-#define SMPC_LIN_FIELDS 162
+/* stage records of the last smpc_rti_solve, [B][N+1][SMPC_REC] */
+int smpc_get_lin(smpc_handle_t* h, double* lin, int32_t mem);
+/* QP solution of the last smpc_rti_solve: dz[B][N+1][15] ([du;dx]; terminal stage: dx in the first 10),
+ * pi[B][N][10], lam/t[B][N+1][SMPC_QP_NC]; any pointer may be NULL */
+int smpc_get_qp(smpc_handle_t* h, double* dz, double* pi, double* lam, double* t, int32_t mem);
 
 /* --- per-problem controller state (controller.py attrs fails, r, last_status, x_viable) --- */
 enum { SMPC_STATE_FAILS = 0, SMPC_STATE_R = 1, SMPC_STATE_STATUS = 2, SMPC_STATE_QP_ITER = 3, SMPC_STATE_QP_STATUS = 4 };
@@ -181,7 +220,30 @@ int smpc_get_state_i32(smpc_handle_t* h, int32_t field, int32_t* out, int32_t me
 int smpc_set_state_i32(smpc_handle_t* h, int32_t field, const int32_t* in, int32_t mem);
 int smpc_get_x_viable(smpc_handle_t* h, double* x_viable, int32_t mem);
 
-/* --- timing of the last call, milliseconds, CUDA events (replaces get_stats, controller.py:192-193) ---
+/* --- closed loop = the per-test body of scripts/mpc.py:102-291, batched ---
+ * `backup` is a handle created with controller = SMPC_CTRL_BACKUP and N = back_hor (mpc.py:54-73),
+ * same batch.  One smpc_sim_step advances every live problem by one control step: abort following /
+ * PD hold / controller.step, backup solve on abort, plant step, bounds and collision checks.
+ * No host synchronisation inside. */
+int smpc_sim_create(smpc_handle_t* main_ctrl, smpc_handle_t* backup, int32_t n_steps, smpc_sim_t** out);
+void smpc_sim_destroy(smpc_sim_t* s);
+int smpc_sim_reset(smpc_sim_t* s, const double* x_init, int32_t mem);
+int smpc_sim_step(smpc_sim_t* s);
+int smpc_sim_run(smpc_sim_t* s, int32_t n_steps);
+/* outcome bits after n_steps: see SMPC_OUT_*; runs the convergence test of mpc.py:273 first */
+#define SMPC_OUT_CONVERGED 1  /* conv_idx        */
+#define SMPC_OUT_COLLIDED 2   /* collisions_idx  */
+#define SMPC_OUT_ABORTED 4    /* was added to viable_idx at least once (before the final filtering) */
+int smpc_sim_get_outcome(smpc_sim_t* s, int32_t* outcome, int32_t mem);
+/* logs: x[B][n_steps+1][NX], u[B][n_steps][NU], NaN after termination (mpc.py:114-116) */
+int smpc_sim_get_log(smpc_sim_t* s, double* x, double* u, int32_t mem);
+/* x_viable of the first abort of each problem [B][NX] (NaN if none) */
+int smpc_sim_get_x_viable(smpc_sim_t* s, double* xv, int32_t mem);
+/* out[0] = RTI solves of the main controller, out[1] = backup solves, out[2] = problem-steps simulated,
+ * out[3] = total IPM iterations */
+int smpc_sim_get_counters(smpc_sim_t* s, int64_t* out4);
+
+/* --- timing of the last rti_solve/controller_step, milliseconds, CUDA events (replaces get_stats, controller.py:192-193) ---
  * out[0]=time_lin out[1]=time_sim out[2]=time_qp out[3]=time_qp_solver_call out[4]=time_glob out[5]=time_reg out[6]=time_tot */
 int smpc_get_times(smpc_handle_t* h, double* out7);
 /* number of kernels this handle has launched so far (bench.py "gpu_launches") */

@@ -176,51 +176,55 @@ struct MlpView {
     W1 = w; b1 = W1 + H * I; W2 = b1 + H; b2 = W2 + H * H; W3 = b2 + H; b3 = W3 + H * H; W4 = b3 + H; b4 = W4 + H;
   }
 };
-inline float gelu_tanh(float x, float* dgelu) {
-  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
-  float x2 = x * x;
-  float inner = k0 * (x + k1 * x * x2);
-  float t = std::tanh(inner);
-  *dgelu = 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * k0 * (1.0f + 3.0f * k1 * x2);
-  return 0.5f * x * (1.0f + t);
+template <class F>
+inline F gelu_tanh(F x, F* dgelu) {
+  const F k0 = (F)0.7978845608028654, k1 = (F)0.044715;
+  F x2 = x * x;
+  F inner = k0 * (x + k1 * x * x2);
+  F t = std::tanh(inner);
+  *dgelu = (F)0.5 * ((F)1.0 + t) + (F)0.5 * x * ((F)1.0 - t * t) * k0 * ((F)1.0 + (F)3.0 * k1 * x2);
+  return (F)0.5 * x * ((F)1.0 + t);
 }
-// y = NN(in) and dy/din, all in fp32 like the libtorch evaluation behind L4CasADi
-inline float mlp_value_grad(const MlpView& W, const float* in, float* grad) {
+// y = NN(in) and dy/din.  F = float: everything in fp32 like the libtorch evaluation behind L4CasADi
+// (SURVEY Appendix C); F = double: the same fp32 weights, fp64 arithmetic (deterministic across summation orders;
+// differs from the fp32 evaluation by less than the fp32 rounding of the reference itself).
+template <class F>
+inline F mlp_value_grad(const MlpView& W, const F* in, F* grad) {
   const int H = ORC_HID, I = ORC_NX;
-  float a1[ORC_HID], a2[ORC_HID], a3[ORC_HID], d1[ORC_HID], d2[ORC_HID], d3[ORC_HID];
+  F a1[ORC_HID], a2[ORC_HID], a3[ORC_HID], d1[ORC_HID], d2[ORC_HID], d3[ORC_HID];
   for (int j = 0; j < H; ++j) {
-    float s = W.b1[j];
-    for (int k = 0; k < I; ++k) s += W.W1[j * I + k] * in[k];
-    a1[j] = gelu_tanh(s, &d1[j]);
+    F s = W.b1[j];
+    for (int k = 0; k < I; ++k) s += (F)W.W1[j * I + k] * in[k];
+    a1[j] = gelu_tanh<F>(s, &d1[j]);
   }
   for (int j = 0; j < H; ++j) {
-    float s = W.b2[j];
-    for (int k = 0; k < H; ++k) s += W.W2[j * H + k] * a1[k];
-    a2[j] = gelu_tanh(s, &d2[j]);
+    F s = W.b2[j];
+    for (int k = 0; k < H; ++k) s += (F)W.W2[j * H + k] * a1[k];
+    a2[j] = gelu_tanh<F>(s, &d2[j]);
   }
   for (int j = 0; j < H; ++j) {
-    float s = W.b3[j];
-    for (int k = 0; k < H; ++k) s += W.W3[j * H + k] * a2[k];
-    a3[j] = gelu_tanh(s, &d3[j]);
+    F s = W.b3[j];
+    for (int k = 0; k < H; ++k) s += (F)W.W3[j * H + k] * a2[k];
+    a3[j] = gelu_tanh<F>(s, &d3[j]);
   }
-  float y = W.b4[0];
-  for (int k = 0; k < H; ++k) y += W.W4[k] * a3[k];
+  F y = W.b4[0];
+  for (int k = 0; k < H; ++k) y += (F)W.W4[k] * a3[k];
   if (grad) {
-    float g3[ORC_HID], g2[ORC_HID], g1[ORC_HID];
-    for (int k = 0; k < H; ++k) g3[k] = W.W4[k] * d3[k];
+    F g3[ORC_HID], g2[ORC_HID], g1[ORC_HID];
+    for (int k = 0; k < H; ++k) g3[k] = (F)W.W4[k] * d3[k];
     for (int k = 0; k < H; ++k) {
-      float s = 0.f;
-      for (int j = 0; j < H; ++j) s += W.W3[j * H + k] * g3[j];
+      F s = 0;
+      for (int j = 0; j < H; ++j) s += (F)W.W3[j * H + k] * g3[j];
       g2[k] = s * d2[k];
     }
     for (int k = 0; k < H; ++k) {
-      float s = 0.f;
-      for (int j = 0; j < H; ++j) s += W.W2[j * H + k] * g2[j];
+      F s = 0;
+      for (int j = 0; j < H; ++j) s += (F)W.W2[j * H + k] * g2[j];
       g1[k] = s * d1[k];
     }
     for (int k = 0; k < I; ++k) {
-      float s = 0.f;
-      for (int j = 0; j < H; ++j) s += W.W1[j * I + k] * g1[j];
+      F s = 0;
+      for (int j = 0; j < H; ++j) s += (F)W.W1[j * I + k] * g1[j];
       grad[k] = s;
     }
   }
@@ -229,6 +233,7 @@ inline float mlp_value_grad(const MlpView& W, const float* in, float* grad) {
 
 // c(x) = NN(psi(x)) * (100 - alpha)/100 - ||v||, psi = [(q-mean)/std ; v/||v||], v = qdot with v[0] += eps
 // (reference safe_set.py:82-94).  grad = dc/dx (may be null).
+template <class F>
 inline double nn_constraint(const orc_problem_t& P, const double* x, double alpha, double* grad) {
   constexpr int n = ORC_NQ;
   double v[n], nrm2 = 0.0;
@@ -236,15 +241,15 @@ inline double nn_constraint(const orc_problem_t& P, const double* x, double alph
   v[0] += P.eps;
   for (int i = 0; i < n; ++i) nrm2 += v[i] * v[i];
   double nrm = std::sqrt(nrm2);
-  float in[ORC_NX], g[ORC_NX];
+  F in[ORC_NX], g[ORC_NX];
   double dir[n];
   for (int i = 0; i < n; ++i) {
-    in[i] = (float)((x[i] - P.nn_mean[i]) / P.nn_std[i]);
+    in[i] = (F)((x[i] - P.nn_mean[i]) / P.nn_std[i]);
     dir[i] = v[i] / nrm;
-    in[n + i] = (float)dir[i];
+    in[n + i] = (F)dir[i];
   }
   MlpView W(P.nn_weights);
-  float y = mlp_value_grad(W, in, grad ? g : nullptr);
+  F y = mlp_value_grad<F>(W, in, grad ? g : nullptr);
   double s = (100.0 - alpha) / 100.0;
   if (grad) {
     double gd = 0.0;

@@ -1,0 +1,64 @@
+"""ORACLE -- test infrastructure only.  ctypes wrapper of oracle/liboracle.so (CPU restatement of the
+reference hot path, see oracle.h).  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs may import this module; the product package never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from safe_mpc_b200 import abi
+from safe_mpc_b200.binding import EngineBase, SimBase
+
+_DIR = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build(force=False):
+    so = os.path.join(_DIR, 'liboracle.so')
+    srcs = [os.path.join(_DIR, f) for f in ('oracle.cpp', 'oracle.h', 'model.hpp', 'qp.hpp', 'dual.hpp')]
+    srcs.append(os.path.join(_DIR, '..', 'include', 'safe_mpc_b200.h'))
+    stale = force or not os.path.isfile(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs if os.path.isfile(s))
+    if stale and os.path.isfile(srcs[0]):
+        subprocess.run(['make', '-C', _DIR, '-s'], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+    return _LIB
+
+
+class Oracle(EngineBase):
+    prefix = 'orc_'
+    has_mem = False
+
+    def __init__(self, prob: abi.Problem, batch: int, threads: int = 0):
+        super().__init__(lib(), prob, batch, threads)
+
+    def num_threads(self):
+        return int(self.lib.orc_num_threads(self.h))
+
+    def set_mlp_fp32(self, on):
+        self._call('set_mlp_fp32', C.c_int32(int(on)))
+
+    def mass_bias(self, b, x, nominal=True):
+        M = np.empty((abi.NQ, abi.NQ)); h = np.empty(abi.NQ)
+        xx = np.ascontiguousarray(x, dtype=np.float64)
+        self._call('mass_bias', C.c_int32(b), C.c_int32(int(nominal)), C.c_void_p(xx.ctypes.data),
+                   C.c_void_p(M.ctypes.data), C.c_void_p(h.ctypes.data))
+        return M, h
+
+    def qp_info(self, b):
+        res = (C.c_double * 4)(); mu = C.c_double(); it = C.c_int32(); st = C.c_int32()
+        self._call('qp_info', C.c_int32(b), res, C.byref(mu), C.byref(it), C.byref(st))
+        return np.array(res[:]), mu.value, it.value, st.value
+
+
+class OracleSim(SimBase):
+    pass

@@ -16,7 +16,14 @@ NPAIR = 6
 MAX_POINTS = 8
 HID = 256
 NN_NPARAM = HID * NX + HID + 2 * (HID * HID + HID) + HID + 1
-LIN_FIELDS = 162
+REC = 192
+MAX_N = 128
+QP_NR = 22
+QP_NC = 2 * QP_NR + 2
+# stage-record offsets (include/safe_mpc_b200.h SMPC_REC_*)
+REC_U, REC_X, REC_G, REC_HQQ, REC_TAU, REC_JTAU, REC_DIST, REC_JDIST, REC_NN, REC_JNN, REC_B = 0, 5, 15, 30, 45, 50, 125, 131, 161, 162, 172
+REC_HU, REC_HV, REC_HQ, REC_NNROW, REC_SOFT, REC_NTAU, REC_NDIST = 182, 183, 184, 185, 186, 187, 188
+OUT_CONVERGED, OUT_COLLIDED, OUT_ABORTED = 1, 2, 4
 
 HOST, DEVICE = 0, 1
 
@@ -32,7 +39,8 @@ class Problem(C.Structure):
         ('nq', C.c_int32), ('N', C.c_int32), ('n_pairs', C.c_int32), ('n_points', C.c_int32),
         ('controller', C.c_int32), ('nn_rows', C.c_int32), ('nn_terminal_soft', C.c_int32),
         ('stage0_collision_rows', C.c_int32), ('cost_type', C.c_int32), ('abort_flag', C.c_int32),
-        ('qp_iter_max', C.c_int32), ('reserved_i', C.c_int32 * 5),
+        ('qp_iter_max', C.c_int32), ('lm_scale_dt', C.c_int32), ('qp_cond_pred_corr', C.c_int32),
+        ('reserved_i', C.c_int32 * 3),
         ('dt', C.c_double), ('q_weight', C.c_double), ('r_weight', C.c_double), ('lm', C.c_double),
         ('alpha', C.c_double), ('eps', C.c_double), ('slack_penalty_e', C.c_double),
         ('tol_x', C.c_double), ('tol_tau', C.c_double), ('tol_obs', C.c_double), ('tol_safe', C.c_double),

@@ -1,0 +1,172 @@
+"""OCP description -> ``struct smpc_problem``.
+
+This is the engine-side equivalent of what the reference assembles with ``AdamModel.__init__``
+(env_model.py:18-165: chain, limits, capsule kinematics, NL-constraint lists) and
+``AbstractController.__init__`` + the per-controller ``additionalSetting`` (controller.py:12-125,
+300-306,332-357,400-401,439-442,514-515,687-689,696-712): bounds, which stages carry which rows, which
+rows are soft, the solver options.  Nothing is code-generated; the result is a flat struct of numbers.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+from . import abi, synthetic
+from .robot_model import build_chain, capsule_local_points, point_on_link, GRAVITY
+
+# CLI / class name -> (engine state machine, where the viability rows are, soft terminal row?)
+CONTROLLERS = {
+    'naive': (abi.CTRL['naive'], abi.NN_NONE, False),
+    'zerovel': (abi.CTRL['zerovel'], abi.NN_NONE, False),
+    'st': (abi.CTRL['st'], abi.NN_TERMINAL, True),
+    'stwa': (abi.CTRL['stwa'], abi.NN_TERMINAL, True),
+    'htwa': (abi.CTRL['htwa'], abi.NN_TERMINAL, False),
+    'receding': (abi.CTRL['receding'], abi.NN_RECEDING, True),
+    'real_receding': (abi.CTRL['real_receding'], abi.NN_TERMINAL, False),
+    'constraint_everywhere': (abi.CTRL['constraint_everywhere'], abi.NN_EVERYWHERE, False),
+    'backup': (abi.CTRL['backup'], abi.NN_NONE, False),
+}
+
+COSTS = {'zero': abi.COST_ZERO, 'ext': abi.COST_EXT, 'nls': abi.COST_NLS}
+
+
+def load_network(params):
+    """Weights / normalisation of the viability network in the reference's file format
+    (safe_set.py:76-85: ``torch.load`` of {'model', 'mean', 'std'}); written by synthetic.py if absent."""
+    path = params.net_path
+    if not os.path.isabs(path):
+        path = os.path.normpath(os.path.join(params.NN_DIR, os.path.basename(path)))
+    if not os.path.isfile(path):
+        synthetic.write_synthetic_net(path, nq=params.nq, hidden=int(params.net_size[1]))
+    import torch
+    data = torch.load(path, map_location='cpu', weights_only=True)
+    sd = data['model']
+    ws = [sd[f'linear_stack.{i}.weight'].numpy() for i in (0, 2, 4, 6)]
+    bs = [sd[f'linear_stack.{i}.bias'].numpy() for i in (0, 2, 4, 6)]
+    mean = np.broadcast_to(np.asarray(data['mean'], dtype=np.float64).ravel(), (params.nq,)) \
+        if np.asarray(data['mean']).size in (1, params.nq) else np.asarray(data['mean'], dtype=np.float64).ravel()[:params.nq]
+    std = np.broadcast_to(np.asarray(data['std'], dtype=np.float64).ravel(), (params.nq,)) \
+        if np.asarray(data['std']).size in (1, params.nq) else np.asarray(data['std'], dtype=np.float64).ravel()[:params.nq]
+    return ws, bs, np.array(mean, dtype=np.float64), np.array(std, dtype=np.float64)
+
+
+class ModelData:
+    """Numbers the reference's AdamModel derives from URDF + config (env_model.py:23-40,106-121,131-165,263-271)."""
+
+    def __init__(self, params):
+        self.params = params
+        nq = params.nq
+        if nq != abi.NQ:
+            raise NotImplementedError(f'this build of the engine is compiled for n_dofs={abi.NQ} (config.yaml n_dofs={nq})')
+        self.chain, self.nominal_links = build_chain(params.robot_descr, nq)
+        c = self.chain
+        self.inertial = c.lump(self.nominal_links['mass'], self.nominal_links['com'], self.nominal_links['inertia6'],
+                               self.nominal_links['rpy'])
+        # joint limits, widened by q_margin (env_model.py:106-121)
+        self.tau_min, self.tau_max = -c.effort.copy(), c.effort.copy()
+        x_min = np.hstack([c.lower, -c.velocity])
+        x_max = np.hstack([c.upper, c.velocity])
+        self.bounds_diff = np.abs(x_max - x_min)
+        self.x_min = x_min - self.bounds_diff * (params.q_margin / 100)
+        self.x_max = x_max + self.bounds_diff * (params.q_margin / 100)
+        # moving points: 0 = end effector (env_model.py:91-95), then capsule end points (:131-147)
+        bodies, locals_ = [], []
+        b, p = point_on_link(c, params.frame_name, np.append(params.ee_pos, 1.0))
+        bodies.append(b); locals_.append(p)
+        self.capsule_points = {}
+        for cap in params.robot_capsules:
+            idx = []
+            for lp in capsule_local_points(cap):
+                b, p = point_on_link(c, cap['link_name'], lp)
+                idx.append(len(bodies)); bodies.append(b); locals_.append(p)
+            self.capsule_points[cap['name']] = idx
+        used = {0}
+        self.pairs = []
+        for pair in params.collisions_pairs:
+            if pair['type'] != 'capsule-capsule':
+                raise NotImplementedError(f"collision pair type {pair['type']} is outside the engine's scope "
+                                          '(config.yaml ships capsule-capsule pairs only)')
+            mov, fix = pair['elements']
+            if mov.get('type') != 'moving_capsule' or fix.get('type') != 'fixed_capsule':
+                raise NotImplementedError('capsule pairs must be (robot capsule, obstacle capsule)')
+            ia, ib = self.capsule_points[mov['name']]
+            used.update((ia, ib))
+            rsum = mov['radius'] + fix['radius']
+            self.pairs.append(dict(pa=ia, pb=ib, C=np.asarray(fix['end_points'][0], dtype=np.float64),
+                                   D=np.asarray(fix['end_points'][1], dtype=np.float64),
+                                   lo_ocp=(rsum + params.collision_margin * 2) ** 2,
+                                   lo_chk=rsum ** 2 - params.tol_obs, name=(mov['name'], fix['name'])))
+        if len(self.pairs) != abi.NPAIR:
+            raise NotImplementedError(f'this build expects {abi.NPAIR} capsule-capsule pairs, config has {len(self.pairs)}')
+        # compact the point list to the ones in use
+        order = sorted(used)
+        if len(order) > abi.MAX_POINTS:
+            raise NotImplementedError('too many moving points')
+        remap = {old: new for new, old in enumerate(order)}
+        self.point_body = np.full(abi.MAX_POINTS, -1, dtype=np.int32)
+        self.point_local = np.zeros((abi.MAX_POINTS, 3))
+        for old in order:
+            self.point_body[remap[old]] = bodies[old]
+            self.point_local[remap[old]] = locals_[old]
+        for pr in self.pairs:
+            pr['pa'], pr['pb'] = remap[pr['pa']], remap[pr['pb']]
+        self.n_points = len(order)
+
+
+def build_problem(params, controller: str, cost: str = 'ext', N: int | None = None, model: ModelData | None = None):
+    """-> (abi.Problem, keepalive).  ``keepalive`` owns the weight buffer the struct points to."""
+    if controller not in CONTROLLERS:
+        raise ValueError(f'Controller {controller} not available')
+    ctrl, nn_rows, soft = CONTROLLERS[controller]
+    md = model or ModelData(params)
+    N = int(params.N if N is None else N)
+    if not 2 <= N <= abi.MAX_N:
+        raise ValueError(f'horizon {N} outside [2, {abi.MAX_N}]')
+    p = abi.Problem()
+    q_m = params.q_margin / 100
+    lbx = md.x_min + q_m * md.bounds_diff          # controller.py:49-55: re-narrow by the same margin
+    ubx = md.x_max - q_m * md.bounds_diff
+    lbx_e, ubx_e = lbx.copy(), ubx.copy()
+    nq = params.nq
+    if controller == 'zerovel':                    # controller.py:300-306
+        lbx_e[nq:] = 0.0; ubx_e[nq:] = 0.0
+    if controller == 'backup':                     # controller.py:701-707 (uses the model bounds)
+        lbx_e = np.hstack([md.x_min[:nq], np.zeros(nq)]); ubx_e = np.hstack([md.x_max[:nq], np.zeros(nq)])
+    keep = None
+    if nn_rows != abi.NN_NONE:
+        if not params.use_net:
+            raise NotImplementedError('the analytic safe set is out of scope (config.yaml use_net: true)')
+        ws, bs, mean, std = load_network(params)
+        keep = abi.pack_nn_weights(ws, bs)
+    else:
+        mean, std = np.zeros(nq), np.ones(nq)
+    if controller == 'receding':
+        penalty = params.ws_t                      # controller.py:461-462 (runtime cost_set wins over zl_e)
+    else:
+        penalty = params.ws_r                      # controller.py:351-354
+    abi.fill(
+        p, nq=nq, N=N, n_pairs=abi.NPAIR, n_points=md.n_points, controller=ctrl, nn_rows=nn_rows,
+        nn_terminal_soft=int(soft), stage0_collision_rows=int(not params.noise > 0), cost_type=COSTS[cost],
+        abort_flag=int(params.abort_flag), qp_iter_max=int(params.qp_max_iter), lm_scale_dt=1, qp_cond_pred_corr=1,
+        dt=params.dt, q_weight=params.Q_weight, r_weight=params.R_weight, lm=params.levenberg_marquardt,
+        alpha=params.alpha, eps=params.eps, slack_penalty_e=penalty,
+        tol_x=params.tol_x, tol_tau=params.tol_tau, tol_obs=params.tol_obs, tol_safe=params.tol_safe_set,
+        tol_conv=params.tol_conv,
+        # HPIPM BALANCE defaults (UNVERIFIED offline)
+        qp_mu0=1e1, qp_tol_stat=1e-6, qp_tol_eq=1e-8, qp_tol_ineq=1e-8, qp_tol_comp=1e-8, qp_alpha_min=1e-12,
+        qp_reg_prim=1e-15,
+        gravity=[0.0, 0.0, -GRAVITY],
+        joint_R=md.chain.joint_R, joint_p=md.chain.joint_p, joint_axis=md.chain.joint_axis, inertial=md.inertial,
+        x_min=md.x_min, x_max=md.x_max, lbx=lbx, ubx=ubx, lbx_e=lbx_e, ubx_e=ubx_e,
+        tau_min=md.tau_min, tau_max=md.tau_max, ee_ref=params.ee_ref,
+        point_body=md.point_body, point_local=md.point_local,
+        pair_pa=[pr['pa'] for pr in md.pairs], pair_pb=[pr['pb'] for pr in md.pairs],
+        pair_C=[pr['C'] for pr in md.pairs], pair_D=[pr['D'] for pr in md.pairs],
+        pair_lo_ocp=[pr['lo_ocp'] for pr in md.pairs], pair_lo_chk=[pr['lo_chk'] for pr in md.pairs],
+        pair_hi=1e6, nn_mean=mean, nn_std=std,
+    )
+    if keep is not None:
+        import ctypes as C
+        p.nn_weights = keep.ctypes.data_as(C.POINTER(C.c_float))
+    return p, keep

@@ -1,0 +1,473 @@
+// Rigid-body / geometry device functions of the batched RTI engine (sm_100a).
+//
+// Hand-derived recursions for the quantities the reference obtains from CasADi's AD of the adam expression
+// graphs (reference env_model.py:80-95,131-151; utils.py:94-113; cost_definition.py:69-96):
+//   * recursive Newton-Euler inverse dynamics of the fixed-base serial chain, tau = M(q) u + h(q, v),
+//   * its analytic first derivatives d tau / d(q, v, u) by sparse tangent recursions (one direction at a time:
+//     forward from the perturbed joint to the tip, backward to the base),
+//   * world kinematics of points attached to bodies with geometric Jacobians z_j x (P - o_j) and the
+//     second-order terms z_j x (z_k x (P - o_k)) needed by the exact cost Hessian,
+//   * squared capsule segment distance (clamped closest-point parameters, utils.py:94-113) with a
+//     hand-written reverse sweep for its gradient.
+// Everything is SMPC_HD so that the same source can be compiled for the host by the emulation harness in
+// tests/emu (kernel-logic tests without a GPU); the product only ever runs the device instantiation.
+#pragma once
+#include <math.h>
+
+#include "../../include/safe_mpc_b200.h"
+
+#if defined(__CUDACC__)
+#define SMPC_HD __host__ __device__ __forceinline__
+#else
+#define SMPC_HD inline
+#endif
+
+namespace smpc {
+
+constexpr int NQ = SMPC_NQ, NX = SMPC_NX, NU = SMPC_NU, NZ = SMPC_NZ, NPAIR = SMPC_NPAIR, REC = SMPC_REC;
+
+struct V3 {
+  double x, y, z;
+};
+SMPC_HD V3 v3(double x, double y, double z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+SMPC_HD V3 v3(const double* p) { return v3(p[0], p[1], p[2]); }
+SMPC_HD V3 operator+(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
+SMPC_HD V3 operator-(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+SMPC_HD V3 operator*(double s, V3 a) { return v3(s * a.x, s * a.y, s * a.z); }
+SMPC_HD double dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+SMPC_HD V3 cross(V3 a, V3 b) { return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+
+struct M3 {
+  double m[9];   // row-major
+};
+SMPC_HD V3 mul(const M3& R, V3 a) {
+  return v3(R.m[0] * a.x + R.m[1] * a.y + R.m[2] * a.z, R.m[3] * a.x + R.m[4] * a.y + R.m[5] * a.z,
+            R.m[6] * a.x + R.m[7] * a.y + R.m[8] * a.z);
+}
+SMPC_HD V3 mulT(const M3& R, V3 a) {
+  return v3(R.m[0] * a.x + R.m[3] * a.y + R.m[6] * a.z, R.m[1] * a.x + R.m[4] * a.y + R.m[7] * a.z,
+            R.m[2] * a.x + R.m[5] * a.y + R.m[8] * a.z);
+}
+SMPC_HD M3 matmul(const M3& A, const M3& B) {
+  M3 C;
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) C.m[3 * r + c] = A.m[3 * r] * B.m[c] + A.m[3 * r + 1] * B.m[3 + c] + A.m[3 * r + 2] * B.m[6 + c];
+  return C;
+}
+
+// rotation parent-body <- body i:  joint_R[i] * exp([axis]x q)
+SMPC_HD M3 joint_rot(const smpc_problem_t& P, int i, double q) {
+  const double* a = P.joint_axis[i];
+  double s, c;
+  sincos(q, &s, &c);
+  const double oc = 1.0 - c;
+  M3 E;
+  E.m[0] = c + oc * (a[0] * a[0]);        E.m[1] = oc * (a[0] * a[1]) - s * a[2]; E.m[2] = oc * (a[0] * a[2]) + s * a[1];
+  E.m[3] = oc * (a[1] * a[0]) + s * a[2]; E.m[4] = c + oc * (a[1] * a[1]);        E.m[5] = oc * (a[1] * a[2]) - s * a[0];
+  E.m[6] = oc * (a[2] * a[0]) - s * a[1]; E.m[7] = oc * (a[2] * a[1]) + s * a[0]; E.m[8] = c + oc * (a[2] * a[2]);
+  M3 F;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) F.m[k] = P.joint_R[i][k];
+  return matmul(F, E);
+}
+
+SMPC_HD V3 inertia_mul(const double* I10, V3 w) {   // I10 = m, c[3], Ixx,Iyy,Izz,Ixy,Iyz,Ixz
+  const double Ixx = I10[4], Iyy = I10[5], Izz = I10[6], Ixy = I10[7], Iyz = I10[8], Ixz = I10[9];
+  return v3(Ixx * w.x + Ixy * w.y + Ixz * w.z, Ixy * w.x + Iyy * w.y + Iyz * w.z, Ixz * w.x + Iyz * w.y + Izz * w.z);
+}
+
+// ------------------------------------------------------------------------------------------------ RNEA
+struct Rnea {
+  M3 R[NQ];                 // parent <- body
+  V3 w[NQ], wd[NQ], vd[NQ]; // body angular velocity / acceleration, linear acceleration of the frame origin
+  V3 f[NQ], n[NQ];          // accumulated wrench transmitted through joint i, body frame i
+};
+
+// tau = M(q) a + h(q, v) of the chain with inertial parameters `I` ([NQ][10]); fills `S` for the tangent passes
+SMPC_HD void rnea(const smpc_problem_t& P, const double (*I)[10], const double* q, const double* v, const double* a,
+                  Rnea& S, double* tau) {
+  V3 w = v3(0, 0, 0), wd = v3(0, 0, 0), vd = v3(-P.gravity[0], -P.gravity[1], -P.gravity[2]);
+#pragma unroll
+  for (int i = 0; i < NQ; ++i) {
+    S.R[i] = joint_rot(P, i, q[i]);
+    const V3 ax = v3(P.joint_axis[i]), p = v3(P.joint_p[i]);
+    const V3 acc = vd + cross(wd, p) + cross(w, cross(w, p));
+    vd = mulT(S.R[i], acc);
+    const V3 av = v[i] * ax;
+    w = mulT(S.R[i], w) + av;
+    wd = mulT(S.R[i], wd) + a[i] * ax + cross(w, av);
+    S.w[i] = w; S.wd[i] = wd; S.vd[i] = vd;
+    const V3 c = v3(&I[i][1]);
+    const V3 F = I[i][0] * (vd + cross(wd, c) + cross(w, cross(w, c)));
+    const V3 Nn = inertia_mul(I[i], wd) + cross(w, inertia_mul(I[i], w)) + cross(c, F);
+    S.f[i] = F; S.n[i] = Nn;
+  }
+#pragma unroll
+  for (int i = NQ - 1; i >= 0; --i) {
+    tau[i] = dot(v3(P.joint_axis[i]), S.n[i]);
+    if (i > 0) {
+      const V3 fp = mul(S.R[i], S.f[i]);
+      S.f[i - 1] = S.f[i - 1] + fp;
+      S.n[i - 1] = S.n[i - 1] + mul(S.R[i], S.n[i]) + cross(v3(P.joint_p[i]), fp);
+    }
+  }
+}
+
+enum { TAN_Q = 0, TAN_V = 1, TAN_U = 2 };
+
+// d tau / d (q_j | v_j | u_j) given the nominal pass `S` (v: joint velocities, u: joint accelerations)
+template <int MODE>
+SMPC_HD void rnea_tangent(const smpc_problem_t& P, const double (*I)[10], const Rnea& S, const double* v, const double* u,
+                          int j, double* dtau) {
+  V3 dF[NQ], dN[NQ];
+  V3 dw, dwd, dvd;
+  const V3 aj = v3(P.joint_axis[j]);
+  if (MODE == TAN_Q) {
+    dw = cross(S.w[j], aj);
+    const V3 rwd = S.wd[j] - u[j] * aj - cross(S.w[j], v[j] * aj);   // R_j^T wd_{j-1}
+    dwd = cross(rwd, aj) + cross(dw, v[j] * aj);
+    dvd = cross(S.vd[j], aj);
+  } else if (MODE == TAN_V) {
+    dw = aj; dwd = cross(S.w[j], aj); dvd = v3(0, 0, 0);
+  } else {
+    dw = v3(0, 0, 0); dwd = aj; dvd = v3(0, 0, 0);
+  }
+#pragma unroll
+  for (int i = 0; i < NQ; ++i) {
+    if (i < j) { dF[i] = v3(0, 0, 0); dN[i] = v3(0, 0, 0); continue; }
+    if (i > j) {
+      const V3 p = v3(P.joint_p[i]);
+      const V3 wp = S.w[i - 1];
+      V3 t = dvd + cross(dwd, p);
+      if (MODE != TAN_U) t = t + cross(dw, cross(wp, p)) + cross(wp, cross(dw, p));
+      dvd = mulT(S.R[i], t);
+      dwd = mulT(S.R[i], dwd);
+      if (MODE != TAN_U) { dw = mulT(S.R[i], dw); dwd = dwd + cross(dw, v[i] * v3(P.joint_axis[i])); }
+    }
+    const V3 c = v3(&I[i][1]);
+    const V3 w = S.w[i];
+    V3 t = dvd + cross(dwd, c);
+    if (MODE != TAN_U) t = t + cross(dw, cross(w, c)) + cross(w, cross(dw, c));
+    dF[i] = I[i][0] * t;
+    V3 nn = inertia_mul(I[i], dwd) + cross(c, dF[i]);
+    if (MODE != TAN_U) nn = nn + cross(dw, inertia_mul(I[i], w)) + cross(w, inertia_mul(I[i], dw));
+    dN[i] = nn;
+  }
+  V3 cf = v3(0, 0, 0), cn = v3(0, 0, 0);
+#pragma unroll
+  for (int i = NQ - 1; i >= 0; --i) {
+    V3 fi = dF[i] + cf, ni = dN[i] + cn;
+    dtau[i] = dot(v3(P.joint_axis[i]), ni);
+    if (i > 0) {
+      if (MODE == TAN_Q && i == j) {
+        // nominal accumulated wrench of body j is S.f[j], S.n[j]
+        fi = fi + cross(aj, S.f[j]);
+        ni = ni + cross(aj, S.n[j]);
+      }
+      cf = mul(S.R[i], fi);
+      cn = mul(S.R[i], ni) + cross(v3(P.joint_p[i]), cf);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ kinematics
+struct Fk {
+  M3 Rw[NQ];      // world <- body
+  V3 o[NQ];       // body-frame origins (= joint origins) in the world
+  V3 z[NQ];       // joint axes in the world
+};
+
+SMPC_HD void fk(const smpc_problem_t& P, const double* q, Fk& K) {
+  M3 Rc;
+  Rc.m[0] = 1; Rc.m[1] = 0; Rc.m[2] = 0; Rc.m[3] = 0; Rc.m[4] = 1; Rc.m[5] = 0; Rc.m[6] = 0; Rc.m[7] = 0; Rc.m[8] = 1;
+  V3 oc = v3(0, 0, 0);
+#pragma unroll
+  for (int i = 0; i < NQ; ++i) {
+    oc = oc + mul(Rc, v3(P.joint_p[i]));
+    Rc = matmul(Rc, joint_rot(P, i, q[i]));
+    K.Rw[i] = Rc; K.o[i] = oc; K.z[i] = mul(Rc, v3(P.joint_axis[i]));
+  }
+}
+
+SMPC_HD V3 point_world(const smpc_problem_t& P, const Fk& K, int p) {
+  const int b = P.point_body[p];
+  const V3 l = v3(P.point_local[p]);
+  if (b < 0) return l;
+  V3 r = l;
+#pragma unroll
+  for (int i = 0; i < NQ; ++i) if (i == b) r = K.o[i] + mul(K.Rw[i], l);
+  return r;
+}
+
+// J[:, j] = z_j x (Pw - o_j) for j <= body, else 0
+SMPC_HD void point_jacobian(const smpc_problem_t& P, const Fk& K, int p, V3 Pw, V3* J) {
+  const int b = P.point_body[p];
+#pragma unroll
+  for (int j = 0; j < NQ; ++j) J[j] = (j <= b) ? cross(K.z[j], Pw - K.o[j]) : v3(0, 0, 0);
+}
+
+// --------------------------------------------------------------------------- capsule segment distance
+// d = |(B-A) t - (D-C) u - (C-A)|^2 with the reference's clamped closest-point parameters (utils.py:94-113);
+// gA, gB = d(d)/dA, d(d)/dB by a reverse sweep through the three clamps.
+SMPC_HD double clamp01(double y, bool& free) {
+  if (y > 1.0) { free = false; return 1.0; }      // fmin(y,1) then fmax(.,0)
+  if (y < 0.0) { free = false; return 0.0; }
+  free = true;
+  return y;
+}
+SMPC_HD double segment_dist_grad(V3 A, V3 B, V3 C, V3 D, V3* gA, V3* gB) {
+  const V3 ab = B - A, dc = D - C, ca = C - A;
+  const double R = dot(ab, dc), S1 = dot(ab, ca), D1 = dot(ab, ab), S2 = dot(ca, dc), D2 = dot(dc, dc);
+  const double den = D1 * D2 - (R * R + 1e-5);
+  const double num = S1 * D2 - S2 * R;
+  const double y1 = num / den;
+  bool f1, f2, f3;
+  const double t1 = clamp01(y1, f1);
+  const double y2 = (t1 * R - S2) / D2;
+  const double u = clamp01(y2, f2);
+  const double y3 = (u * R + S1) / D1;
+  const double t = clamp01(y3, f3);
+  const V3 r = t * ab - u * dc - ca;
+  const double d = dot(r, r);
+  if (gA) {
+    const V3 rb = 2.0 * r;
+    V3 abb = t * rb;
+    V3 cab = -1.0 * rb;
+    const double tb = dot(rb, ab);
+    double ub = -dot(rb, dc);
+    double Rb = 0.0, S1b = 0.0, D1b = 0.0, S2b = 0.0;
+    if (f3) { const double yb = tb; ub += yb * R / D1; Rb += yb * u / D1; S1b += yb / D1; D1b -= yb * y3 / D1; }
+    double t1b = 0.0;
+    if (f2) { const double yb = ub; t1b = yb * R / D2; Rb += yb * t1 / D2; S2b -= yb / D2; }
+    if (f1) {
+      const double yb = t1b;
+      const double numb = yb / den, denb = -yb * y1 / den;
+      S1b += numb * D2; S2b -= numb * R; Rb -= numb * S2;
+      D1b += denb * D2; Rb -= denb * 2.0 * R;
+    }
+    abb = abb + Rb * dc + S1b * ca + (2.0 * D1b) * ab;
+    cab = cab + S1b * ab + S2b * dc;
+    *gB = abb;
+    *gA = -1.0 * (abb + cab);
+  }
+  return d;
+}
+
+// ----------------------------------------------------------------------------------- viability network
+// psi(x) = [(q - mean)/std ; v/|v|] with v = qdot, v[0] += eps (safe_set.py:82-87)
+SMPC_HD void nn_input(const smpc_problem_t& P, const double* x, double* in, double* nrm_out) {
+  double v[NQ], n2 = 0.0;
+#pragma unroll
+  for (int i = 0; i < NQ; ++i) v[i] = x[NQ + i];
+  v[0] += P.eps;
+#pragma unroll
+  for (int i = 0; i < NQ; ++i) n2 += v[i] * v[i];
+  const double nrm = sqrt(n2);
+#pragma unroll
+  for (int i = 0; i < NQ; ++i) { in[i] = (x[i] - P.nn_mean[i]) / P.nn_std[i]; in[NQ + i] = v[i] / nrm; }
+  *nrm_out = nrm;
+}
+// c = y (100 - alpha)/100 - |v| and dc/dx from the network output y and its input gradient g
+SMPC_HD double nn_output(const smpc_problem_t& P, const double* in, double nrm, double y, const double* g, double* grad) {
+  const double s = (100.0 - P.alpha) / 100.0;
+  if (grad) {
+    double gd = 0.0;
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) gd += g[NQ + i] * in[NQ + i];
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) {
+      grad[i] = s * g[i] / P.nn_std[i];
+      grad[NQ + i] = s * (g[NQ + i] - gd * in[NQ + i]) / nrm - in[NQ + i];
+    }
+  }
+  return y * s - nrm;
+}
+
+SMPC_HD double gelu_tanh(double x, double* d) {
+  const double k0 = 0.7978845608028654, k1 = 0.044715;
+  const double x2 = x * x;
+  const double t = tanh(k0 * (x + k1 * x * x2));
+  *d = 0.5 * (1.0 + t) + 0.5 * x * (1.0 - t * t) * k0 * (1.0 + 3.0 * k1 * x2);
+  return 0.5 * x * (1.0 + t);
+}
+
+// ------------------------------------------------------------------------------------------ dynamics
+SMPC_HD void f_disc(double dt, const double* x, const double* u, double* xn) {   // env_model.py:63-71
+#pragma unroll
+  for (int i = 0; i < NQ; ++i) {
+    xn[i] = x[i] + dt * x[NQ + i] + 0.5 * dt * dt * u[i];
+    xn[NQ + i] = x[NQ + i] + dt * u[i];
+  }
+}
+
+SMPC_HD bool state_in_bounds(const smpc_problem_t& P, const double* x) {        // env_model.py:175-177
+  bool ok = true;
+#pragma unroll
+  for (int i = 0; i < NX; ++i) ok = ok && (x[i] >= P.x_min[i] - P.tol_x) && (x[i] <= P.x_max[i] + P.tol_x);
+  return ok;
+}
+
+SMPC_HD void distances(const smpc_problem_t& P, const double* q, double* ee, double* dist) {
+  Fk K;
+  fk(P, q, K);
+  if (ee) { const V3 e = point_world(P, K, 0); ee[0] = e.x; ee[1] = e.y; ee[2] = e.z; }
+  if (dist)
+    for (int p = 0; p < NPAIR; ++p)
+      dist[p] = segment_dist_grad(point_world(P, K, P.pair_pa[p]), point_world(P, K, P.pair_pb[p]), v3(P.pair_C[p]), v3(P.pair_D[p]), nullptr, nullptr);
+}
+
+SMPC_HD bool collision_free(const smpc_problem_t& P, const double* x) {         // env_model.py:236-243
+  double d[NPAIR];
+  distances(P, x, nullptr, d);
+  bool ok = true;
+  for (int p = 0; p < NPAIR; ++p) ok = ok && (P.pair_lo_chk[p] <= d[p]) && (d[p] <= P.pair_hi + P.tol_obs);
+  return ok;
+}
+
+// one stage of the linearisation -> stage record (viability row value/gradient are supplied by the MLP kernel)
+SMPC_HD void linearize_stage(const smpc_problem_t& P, int k, const double* x, const double* u, const double* xnext,
+                             bool has_nn, bool gate_on, const double* nn11, double* rec) {
+  const int N = P.N;
+  const bool term = (k == N);
+  const double s = term ? 1.0 : P.dt;
+  for (int i = 0; i < REC; ++i) rec[i] = 0.0;
+#pragma unroll
+  for (int i = 0; i < NX; ++i) rec[SMPC_REC_X + i] = x[i];
+  if (!term)
+#pragma unroll
+    for (int i = 0; i < NU; ++i) rec[SMPC_REC_U + i] = u[i];
+  const double* q = x;
+  const double* v = x + NQ;
+  Fk K;
+  fk(P, q, K);
+  // ---- cost ----
+  double hu = 0.0;
+  if (P.cost_type != SMPC_COST_ZERO) {
+    const V3 Pw = point_world(P, K, 0);
+    V3 J[NQ];
+    point_jacobian(P, K, 0, Pw, J);
+    const V3 e = Pw - v3(P.ee_ref);
+    const bool ext = P.cost_type == SMPC_COST_EXT;
+    const double wq = (ext ? 2.0 : 1.0) * P.q_weight * s;
+    const int be = P.point_body[0];
+    int o = 0;
+    for (int i = 0; i < NQ; ++i) {
+      rec[SMPC_REC_G + NU + i] = wq * dot(J[i], e);
+      for (int j = 0; j <= i; ++j) {
+        double h = dot(J[i], J[j]);
+        if (ext && i <= be) h += dot(e, cross(K.z[j], cross(K.z[i], Pw - K.o[i])));   // j <= i: d2P/dq_j dq_i
+        rec[SMPC_REC_HQQ + o++] = wq * h;
+      }
+    }
+    if (!term) {
+      const double wr = (ext ? 2.0 : 1.0) * P.r_weight * s;
+#pragma unroll
+      for (int i = 0; i < NU; ++i) rec[SMPC_REC_G + i] = wr * u[i];
+      hu = wr;
+    }
+  }
+  const double lmk = P.lm * ((P.lm_scale_dt && !term) ? P.dt : 1.0);
+  rec[SMPC_REC_HU] = term ? 0.0 : hu + lmk;
+  rec[SMPC_REC_HV] = lmk;
+  rec[SMPC_REC_HQ] = lmk;
+  // ---- torque rows ----
+  if (!term) {
+    Rnea S;
+    double tau[NQ], d[NQ];
+    rnea(P, P.inertial, q, v, u, S, tau);
+#pragma unroll
+    for (int i = 0; i < NU; ++i) rec[SMPC_REC_TAU + i] = tau[i];
+    for (int j = 0; j < NQ; ++j) {
+      rnea_tangent<TAN_U>(P, P.inertial, S, v, u, j, d);
+      for (int i = 0; i < NU; ++i) rec[SMPC_REC_JTAU + i * 15 + j] = d[i];
+      rnea_tangent<TAN_Q>(P, P.inertial, S, v, u, j, d);
+      for (int i = 0; i < NU; ++i) rec[SMPC_REC_JTAU + i * 15 + NU + j] = d[i];
+      rnea_tangent<TAN_V>(P, P.inertial, S, v, u, j, d);
+      for (int i = 0; i < NU; ++i) rec[SMPC_REC_JTAU + i * 15 + NU + NQ + j] = d[i];
+    }
+    rec[SMPC_REC_NTAU] = NU;
+  }
+  // ---- capsule rows ----
+  if (k > 0 || P.stage0_collision_rows) {
+    for (int p = 0; p < NPAIR; ++p) {
+      const V3 A = point_world(P, K, P.pair_pa[p]), Bp = point_world(P, K, P.pair_pb[p]);
+      V3 gA, gB, JA[NQ], JB[NQ];
+      const double d = segment_dist_grad(A, Bp, v3(P.pair_C[p]), v3(P.pair_D[p]), &gA, &gB);
+      point_jacobian(P, K, P.pair_pa[p], A, JA);
+      point_jacobian(P, K, P.pair_pb[p], Bp, JB);
+      rec[SMPC_REC_DIST + p] = d;
+      for (int j = 0; j < NQ; ++j) rec[SMPC_REC_JDIST + p * NQ + j] = dot(gA, JA[j]) + dot(gB, JB[j]);
+    }
+    rec[SMPC_REC_NDIST] = NPAIR;
+  }
+  // ---- viability row ----
+  rec[SMPC_REC_SOFT] = -1.0;
+  if (has_nn) {
+    rec[SMPC_REC_NNROW] = 1.0;
+    if (gate_on) {
+      rec[SMPC_REC_NN] = nn11[0];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) rec[SMPC_REC_JNN + i] = nn11[1 + i];
+    } else {
+      rec[SMPC_REC_NN] = 5e5;
+    }
+    if (term && P.nn_terminal_soft) rec[SMPC_REC_SOFT] = P.slack_penalty_e;
+  }
+  // ---- dynamics offset ----
+  if (!term) {
+    double xn[NX];
+    f_disc(P.dt, x, u, xn);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) rec[SMPC_REC_B + i] = xn[i] - xnext[i];
+  }
+}
+
+SMPC_HD bool stage_has_nn(const smpc_problem_t& P, int k) {
+  return (P.nn_rows == SMPC_NN_TERMINAL && k == P.N) || ((P.nn_rows == SMPC_NN_RECEDING || P.nn_rows == SMPC_NN_EVERYWHERE) && k >= 1);
+}
+
+// M(q) (row-major 5x5) and h(q, v) of the chain with inertial parameters I
+SMPC_HD void mass_bias(const smpc_problem_t& P, const double (*I)[10], const double* x, double* M, double* h) {
+  Rnea S;
+  const double zero[NQ] = {0, 0, 0, 0, 0};
+  rnea(P, I, x, x + NQ, zero, S, h);
+  double d[NQ];
+  for (int j = 0; j < NQ; ++j) {
+    rnea_tangent<TAN_U>(P, I, S, x + NQ, zero, j, d);
+    for (int i = 0; i < NQ; ++i) M[i * NQ + j] = d[i];
+  }
+}
+
+// AdamModel.integrate (env_model.py:192-206): nominal torque + noise, clip, forward dynamics on the perturbed plant
+SMPC_HD void plant_step(const smpc_problem_t& P, const double (*Iplant)[10], const double* noise, const double* x,
+                        const double* u, double* xn, double* a) {
+  Rnea S;
+  double tau[NQ];
+  rnea(P, P.inertial, x, x + NQ, u, S, tau);
+  double M[NQ * NQ], h[NQ], L[NQ * NQ], y[NQ];
+  mass_bias(P, Iplant, x, M, h);
+#pragma unroll
+  for (int i = 0; i < NQ; ++i) {
+    double t = tau[i] + noise[i];
+    t = fmin(fmax(t, P.tau_min[i]), P.tau_max[i]);
+    tau[i] = t - h[i];
+  }
+  for (int i = 0; i < NQ * NQ; ++i) L[i] = 0.0;
+  for (int j = 0; j < NQ; ++j) {
+    double d = M[j * NQ + j];
+    for (int k = 0; k < j; ++k) d -= L[j * NQ + k] * L[j * NQ + k];
+    L[j * NQ + j] = sqrt(d);
+    for (int i = j + 1; i < NQ; ++i) {
+      double s = M[i * NQ + j];
+      for (int k = 0; k < j; ++k) s -= L[i * NQ + k] * L[j * NQ + k];
+      L[i * NQ + j] = s / L[j * NQ + j];
+    }
+  }
+  for (int i = 0; i < NQ; ++i) { double s = tau[i]; for (int k = 0; k < i; ++k) s -= L[i * NQ + k] * y[k]; y[i] = s / L[i * NQ + i]; }
+  for (int i = NQ - 1; i >= 0; --i) { double s = y[i]; for (int k = i + 1; k < NQ; ++k) s -= L[k * NQ + i] * a[k]; a[i] = s / L[i * NQ + i]; }
+  f_disc(P.dt, x, a, xn);
+}
+
+}  // namespace smpc

@@ -1,0 +1,521 @@
+// C ABI of the engine (include/safe_mpc_b200.h).  Host-side orchestration only: buffers, streams, kernel sequencing.
+// There is no CPU compute path in this library: every entry point that produces numbers launches kernels.
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "engine.cuh"
+
+using namespace smpc;
+
+namespace {
+thread_local std::string g_create_error;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+}  // namespace
+
+struct smpc_handle {
+  smpc_problem_t P;
+  smpc_problem_t* dP = nullptr;
+  int B = 0, N = 0, device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  int64_t launches = 0;
+  std::string err;
+  std::vector<void*> allocs;
+  // network
+  float* dW = nullptr;
+  MlpWeights w{};
+  // state
+  double *xg = nullptr, *ug = nullptr, *xt = nullptr, *ut = nullptr, *lin = nullptr, *plant_inertial = nullptr, *tau_noise = nullptr,
+         *x_viable = nullptr, *nn11 = nullptr, *scan11 = nullptr, *qpbuf = nullptr, *qp_res = nullptr, *x_in = nullptr, *u_out = nullptr;
+  int32_t *fails = nullptr, *r = nullptr, *status = nullptr, *qp_iter = nullptr, *qp_status = nullptr, *cur_step = nullptr;
+  uint8_t *act = nullptr, *need_scan = nullptr, *abort_flag = nullptr;
+  // staging for host callers
+  void* stage = nullptr;
+  size_t stage_bytes = 0;
+  double times[7] = {0, 0, 0, 0, 0, 0, 0};
+  bool timed = false;
+  LaunchCtx ctx() { return LaunchCtx{stream, &launches}; }
+};
+
+struct smpc_sim {
+  smpc_handle* c;
+  smpc_handle* bk;
+  SimDev d;
+  int j = 0;
+  int32_t* outcome_tmp = nullptr;
+};
+
+namespace {
+
+int fail(smpc_handle* h, int code, const char* what, cudaError_t e = cudaSuccess) {
+  char buf[512];
+  if (e != cudaSuccess) snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
+  else snprintf(buf, sizeof buf, "%s", what);
+  if (h) h->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define CK(h, call)                                                         \
+  do {                                                                      \
+    cudaError_t e__ = (call);                                               \
+    if (e__ != cudaSuccess) return fail(h, SMPC_ERR_CUDA, #call, e__);      \
+  } while (0)
+
+template <class T>
+cudaError_t dalloc(smpc_handle* h, T** p, size_t n) {
+  cudaError_t e = cudaMalloc((void**)p, n * sizeof(T));
+  if (e == cudaSuccess) { h->allocs.push_back(*p); e = cudaMemsetAsync(*p, 0, n * sizeof(T), h->stream); }
+  return e;
+}
+
+// caller array -> device pointer (copy through the staging area when the caller is on the host)
+struct In {
+  const void* dev = nullptr;
+};
+int stage_reserve(smpc_handle* h, size_t bytes) {
+  if (bytes <= h->stage_bytes) return 0;
+  if (h->stage) cudaFree(h->stage);
+  h->stage = nullptr; h->stage_bytes = 0;
+  CK(h, cudaMalloc(&h->stage, bytes));
+  h->stage_bytes = bytes;
+  return 0;
+}
+
+int copy_in(smpc_handle* h, void* dst, const void* src, size_t bytes, int mem) {
+  CK(h, cudaMemcpyAsync(dst, src, bytes, mem == SMPC_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, h->stream));
+  if (mem == SMPC_HOST) CK(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+int copy_out(smpc_handle* h, void* dst, const void* src, size_t bytes, int mem) {
+  if (!dst) return 0;
+  CK(h, cudaMemcpyAsync(dst, src, bytes, mem == SMPC_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, h->stream));
+  if (mem == SMPC_HOST) CK(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int check_launch(smpc_handle* h, const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(h, SMPC_ERR_CUDA, what, e);
+  return 0;
+}
+
+// mask pointer: NULL stays NULL (= all problems)
+int mask_in(smpc_handle* h, const uint8_t* active, int mem, const uint8_t** out) {
+  if (!active) { *out = nullptr; return 0; }
+  if (mem == SMPC_DEVICE) { *out = active; return 0; }
+  int rc = copy_in(h, h->act, active, (size_t)h->B, SMPC_HOST);
+  *out = h->act;
+  return rc;
+}
+
+// linearise + QP for the problems in `act` at the stored guess: AbstractController.solve (controller.py:136-167)
+int solve_pipeline(smpc_handle* h, const double* x0_dev, const uint8_t* act) {
+  LaunchCtx c = h->ctx();
+  const int B = h->B, N = h->N;
+  if (h->timed) cudaEventRecord(h->ev[0], h->stream);
+  if (h->P.nn_rows != SMPC_NN_NONE) {
+    const int mode = h->P.nn_rows == SMPC_NN_TERMINAL ? ROWS_TERMINAL : (h->P.nn_rows == SMPC_NN_EVERYWHERE ? ROWS_ALL : ROWS_RECEDING);
+    launch_mlp(c, h->dP, h->w, B, N, mode, 0, h->xg, h->r, act, nullptr, h->nn11, true);
+  }
+  launch_linearize(c, h->dP, B, N, h->xg, h->ug, h->r, act, h->nn11, h->lin);
+  if (h->timed) cudaEventRecord(h->ev[1], h->stream);
+  launch_qp(c, h->dP, B, N, h->lin, x0_dev, h->r, act, h->qpbuf, h->xt, h->ut, h->status, h->qp_iter, h->qp_status, h->qp_res);
+  if (h->timed) cudaEventRecord(h->ev[2], h->stream);
+  return check_launch(h, "solve pipeline");
+}
+
+// controller.step for the problems in `act` (device pointers)
+int step_pipeline(smpc_handle* h, const double* x_dev, const uint8_t* act, double* u_dev, uint8_t* abort_dev) {
+  LaunchCtx c = h->ctx();
+  const int B = h->B, N = h->N;
+  launch_prep(c, h->dP, B, N, h->xg, h->ug, act, h->P.controller != SMPC_CTRL_REAL_RECEDING);
+  int rc = solve_pipeline(h, x_dev, act);
+  if (rc) return rc;
+  launch_ctrl_post1(c, h->dP, B, N, act, h->xg, h->ug, h->xt, h->status, h->fails, h->r, h->x_viable, h->need_scan, abort_dev, u_dev);
+  if (h->P.controller == SMPC_CTRL_RECEDING || h->P.controller == SMPC_CTRL_REAL_RECEDING)
+    launch_mlp(c, h->dP, h->w, B, N, ROWS_ALL, 0, h->xt, h->r, act, h->need_scan, h->scan11, false);
+  launch_ctrl_post2(c, h->dP, B, N, act, h->xg, h->ug, h->xt, h->ut, h->fails, h->r, h->cur_step, h->need_scan, h->scan11, abort_dev, u_dev);
+  if (h->timed) cudaEventRecord(h->ev[3], h->stream);
+  return check_launch(h, "controller step pipeline");
+}
+
+void collect_times(smpc_handle* h, bool with_post) {
+  float lin = 0, qp = 0, post = 0;
+  cudaEventElapsedTime(&lin, h->ev[0], h->ev[1]);
+  cudaEventElapsedTime(&qp, h->ev[1], h->ev[2]);
+  if (with_post) cudaEventElapsedTime(&post, h->ev[2], h->ev[3]);
+  h->times[0] = lin; h->times[1] = 0.0; h->times[2] = qp; h->times[3] = qp; h->times[4] = post; h->times[5] = 0.0;
+  h->times[6] = lin + qp + post;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* smpc_version(void) { return "safe_mpc_b200 0.1.0 (sm_100a)"; }
+
+const char* smpc_last_error(const smpc_handle_t* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int smpc_create(const smpc_problem_t* prob, int32_t batch, int32_t device, smpc_handle_t** out) {
+  if (!prob || !out || batch <= 0) return fail(nullptr, SMPC_ERR_ARG, "smpc_create: bad arguments");
+  if (prob->nq != SMPC_NQ || prob->n_pairs != SMPC_NPAIR || prob->N < 2 || prob->N > SMPC_MAX_N || prob->n_points > SMPC_MAX_POINTS)
+    return fail(nullptr, SMPC_ERR_UNSUPPORTED, "smpc_create: unsupported dimensions (this build: nq=5, 6 capsule pairs, 2<=N<=128)");
+  if (prob->nn_rows != SMPC_NN_NONE && !prob->nn_weights) return fail(nullptr, SMPC_ERR_ARG, "smpc_create: nn_rows set but nn_weights is NULL");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) return fail(nullptr, SMPC_ERR_CUDA, "smpc_create: no CUDA device (this engine has no CPU fallback)", e);
+  if (device < 0 || device >= ndev) return fail(nullptr, SMPC_ERR_ARG, "smpc_create: bad device index");
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) return fail(nullptr, SMPC_ERR_CUDA, "cudaSetDevice", e);
+  smpc_handle* h = new smpc_handle;
+  h->P = *prob;
+  h->B = batch; h->N = prob->N; h->device = device;
+  const int B = batch, N = prob->N;
+#define CKC(call)                                                                                     \
+  do {                                                                                                \
+    cudaError_t e__ = (call);                                                                         \
+    if (e__ != cudaSuccess) { fail(nullptr, SMPC_ERR_CUDA, #call, e__); smpc_destroy(h); return SMPC_ERR_CUDA; } \
+  } while (0)
+  CKC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  for (auto& ev : h->ev) CKC(cudaEventCreate(&ev));
+  // network weights: original + transposed copies of the two square layers
+  if (prob->nn_weights) {
+    const size_t np = SMPC_NN_NPARAM, sq = (size_t)SMPC_HID * SMPC_HID;
+    CKC(dalloc(h, &h->dW, np + 2 * sq));
+    std::vector<float> host(np + 2 * sq);
+    std::memcpy(host.data(), prob->nn_weights, np * sizeof(float));
+    const float* W1 = host.data();
+    const float* b1 = W1 + SMPC_HID * SMPC_NX;
+    const float* W2 = b1 + SMPC_HID;
+    const float* b2 = W2 + sq;
+    const float* W3 = b2 + SMPC_HID;
+    float* W2t = host.data() + np;
+    float* W3t = W2t + sq;
+    for (int i = 0; i < SMPC_HID; ++i)
+      for (int j = 0; j < SMPC_HID; ++j) { W2t[(size_t)j * SMPC_HID + i] = W2[(size_t)i * SMPC_HID + j]; W3t[(size_t)j * SMPC_HID + i] = W3[(size_t)i * SMPC_HID + j]; }
+    CKC(cudaMemcpyAsync(h->dW, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    CKC(cudaStreamSynchronize(h->stream));
+    float* d = h->dW;
+    h->w.W1 = d; d += SMPC_HID * SMPC_NX; h->w.b1 = d; d += SMPC_HID;
+    h->w.W2 = d; d += sq; h->w.b2 = d; d += SMPC_HID;
+    h->w.W3 = d; d += sq; h->w.b3 = d; d += SMPC_HID;
+    h->w.W4 = d; d += SMPC_HID; h->w.b4 = d; d += 1;
+    h->w.W2t = d; d += sq; h->w.W3t = d;
+  }
+  CKC(dalloc(h, &h->dP, 1));
+  {
+    smpc_problem_t tmp = *prob;
+    tmp.nn_weights = h->dW;
+    CKC(cudaMemcpyAsync(h->dP, &tmp, sizeof tmp, cudaMemcpyHostToDevice, h->stream));
+    CKC(cudaStreamSynchronize(h->stream));
+  }
+  const size_t nx = (size_t)B * (N + 1) * NX, nu = (size_t)B * N * NU, nst = (size_t)B * (N + 1);
+  CKC(dalloc(h, &h->xg, nx)); CKC(dalloc(h, &h->ug, nu)); CKC(dalloc(h, &h->xt, nx)); CKC(dalloc(h, &h->ut, nu));
+  CKC(dalloc(h, &h->lin, nst * REC));
+  CKC(dalloc(h, &h->plant_inertial, (size_t)B * NQ * 10)); CKC(dalloc(h, &h->tau_noise, (size_t)B * NU));
+  CKC(dalloc(h, &h->x_viable, (size_t)B * NX));
+  CKC(dalloc(h, &h->nn11, nst * NN_OUT));
+  if (prob->controller == SMPC_CTRL_RECEDING || prob->controller == SMPC_CTRL_REAL_RECEDING) CKC(dalloc(h, &h->scan11, nst * NN_OUT));
+  CKC(dalloc(h, &h->qpbuf, (size_t)B * qp_stride_doubles(N)));
+  CKC(dalloc(h, &h->qp_res, (size_t)B * 5));
+  CKC(dalloc(h, &h->x_in, (size_t)B * NX)); CKC(dalloc(h, &h->u_out, (size_t)B * NU));
+  CKC(dalloc(h, &h->fails, (size_t)B)); CKC(dalloc(h, &h->r, (size_t)B)); CKC(dalloc(h, &h->status, (size_t)B));
+  CKC(dalloc(h, &h->qp_iter, (size_t)B)); CKC(dalloc(h, &h->qp_status, (size_t)B)); CKC(dalloc(h, &h->cur_step, (size_t)B));
+  CKC(dalloc(h, &h->act, (size_t)B)); CKC(dalloc(h, &h->need_scan, (size_t)B)); CKC(dalloc(h, &h->abort_flag, (size_t)B));
+  // defaults: plant = nominal model, r = N, status = 4 (controller.py:125)
+  {
+    std::vector<double> pin((size_t)B * NQ * 10);
+    for (int b = 0; b < B; ++b) std::memcpy(&pin[(size_t)b * NQ * 10], prob->inertial, sizeof(double) * NQ * 10);
+    CKC(cudaMemcpyAsync(h->plant_inertial, pin.data(), pin.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CKC(cudaStreamSynchronize(h->stream));
+  }
+  LaunchCtx c = h->ctx();
+  launch_fill_i32(c, h->r, B, N);
+  launch_fill_i32(c, h->status, B, 4);
+  CKC(cudaStreamSynchronize(h->stream));
+  CKC(cudaGetLastError());
+#undef CKC
+  *out = h;
+  return SMPC_OK;
+}
+
+void smpc_destroy(smpc_handle_t* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (void* p : h->allocs) cudaFree(p);
+  if (h->stage) cudaFree(h->stage);
+  for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int smpc_set_plant_inertial(smpc_handle_t* h, const double* v, int32_t mem) { return copy_in(h, h->plant_inertial, v, sizeof(double) * h->B * NQ * 10, mem); }
+int smpc_set_torque_noise(smpc_handle_t* h, const double* v, int32_t mem) { return copy_in(h, h->tau_noise, v, sizeof(double) * h->B * NU, mem); }
+
+int smpc_set_guess(smpc_handle_t* h, const double* xg, const double* ug, int32_t mem) {
+  int rc = copy_in(h, h->xg, xg, sizeof(double) * h->B * (h->N + 1) * NX, mem);
+  if (rc) return rc;
+  rc = copy_in(h, h->ug, ug, sizeof(double) * h->B * h->N * NU, mem);
+  if (rc) return rc;
+  launch_set_xviable_from_guess(h->ctx(), h->B, h->N, h->xg, h->x_viable);
+  return check_launch(h, "set_guess");
+}
+int smpc_get_guess(smpc_handle_t* h, double* xg, double* ug, int32_t mem) {
+  int rc = copy_out(h, xg, h->xg, sizeof(double) * h->B * (h->N + 1) * NX, mem);
+  return rc ? rc : copy_out(h, ug, h->ug, sizeof(double) * h->B * h->N * NU, mem);
+}
+int smpc_get_temp(smpc_handle_t* h, double* xt, double* ut, int32_t mem) {
+  int rc = copy_out(h, xt, h->xt, sizeof(double) * h->B * (h->N + 1) * NX, mem);
+  return rc ? rc : copy_out(h, ut, h->ut, sizeof(double) * h->B * h->N * NU, mem);
+}
+int smpc_reset_controller(smpc_handle_t* h) {
+  LaunchCtx c = h->ctx();
+  launch_fill_i32(c, h->fails, h->B, 0);
+  launch_fill_i32(c, h->r, h->B, h->N);
+  launch_fill_i32(c, h->cur_step, h->B, 0);
+  return check_launch(h, "reset_controller");
+}
+
+int smpc_rti_solve(smpc_handle_t* h, const double* x0, const uint8_t* active, int32_t* status, int32_t mem) {
+  if (!x0) return fail(h, SMPC_ERR_ARG, "smpc_rti_solve: x0 is NULL");
+  const uint8_t* act = nullptr;
+  int rc = mask_in(h, active, mem, &act);
+  if (rc) return rc;
+  const double* xd = x0;
+  if (mem == SMPC_HOST) { rc = copy_in(h, h->x_in, x0, sizeof(double) * h->B * NX, mem); if (rc) return rc; xd = h->x_in; }
+  h->timed = true;
+  rc = solve_pipeline(h, xd, act);
+  if (rc) return rc;
+  if (mem == SMPC_HOST) { CK(h, cudaStreamSynchronize(h->stream)); collect_times(h, false); }
+  return copy_out(h, status, h->status, sizeof(int32_t) * h->B, mem);
+}
+
+int smpc_controller_step(smpc_handle_t* h, const double* x, const uint8_t* active, double* u, uint8_t* abort_flag, int32_t mem) {
+  if (!x || !u) return fail(h, SMPC_ERR_ARG, "smpc_controller_step: x or u is NULL");
+  const uint8_t* act = nullptr;
+  int rc = mask_in(h, active, mem, &act);
+  if (rc) return rc;
+  const double* xd = x;
+  double* ud = u;
+  uint8_t* ad = abort_flag;
+  if (mem == SMPC_HOST) {
+    rc = copy_in(h, h->x_in, x, sizeof(double) * h->B * NX, mem); if (rc) return rc;
+    rc = copy_in(h, h->u_out, u, sizeof(double) * h->B * NU, mem); if (rc) return rc;   // inactive problems keep the caller's values
+    xd = h->x_in; ud = h->u_out; ad = h->abort_flag;
+  } else if (!ad) ad = h->abort_flag;
+  h->timed = true;
+  rc = step_pipeline(h, xd, act, ud, ad);
+  if (rc) return rc;
+  if (mem == SMPC_HOST) {
+    CK(h, cudaStreamSynchronize(h->stream));
+    collect_times(h, true);
+    rc = copy_out(h, u, h->u_out, sizeof(double) * h->B * NU, mem); if (rc) return rc;
+    rc = copy_out(h, abort_flag, h->abort_flag, (size_t)h->B, mem);
+  }
+  return rc;
+}
+
+int smpc_plant_step(smpc_handle_t* h, const double* x, const double* u, double* xn, double* a, int32_t mem) {
+  const size_t bx = sizeof(double) * h->B * NX, bu = sizeof(double) * h->B * NU;
+  if (mem == SMPC_DEVICE) {
+    launch_plant(h->ctx(), h->dP, h->B, h->plant_inertial, h->tau_noise, x, u, nullptr, xn, a);
+    return check_launch(h, "plant_step");
+  }
+  int rc = stage_reserve(h, 2 * bx + 2 * bu); if (rc) return rc;
+  char* s = (char*)h->stage;
+  double *dx = (double*)s, *du = (double*)(s + bx), *dxn = (double*)(s + bx + bu), *da = (double*)(s + 2 * bx + bu);
+  rc = copy_in(h, dx, x, bx, mem); if (rc) return rc;
+  rc = copy_in(h, du, u, bu, mem); if (rc) return rc;
+  launch_plant(h->ctx(), h->dP, h->B, h->plant_inertial, h->tau_noise, dx, du, nullptr, dxn, da);
+  rc = check_launch(h, "plant_step"); if (rc) return rc;
+  rc = copy_out(h, xn, dxn, bx, mem); if (rc) return rc;
+  return copy_out(h, a, da, bu, mem);
+}
+
+int smpc_tau(smpc_handle_t* h, int32_t n, const double* x, const double* u, double* tau, int32_t mem) {
+  if (n <= 0) return SMPC_OK;
+  const size_t bx = sizeof(double) * n * NX, bu = sizeof(double) * n * NU;
+  if (mem == SMPC_DEVICE) { launch_tau(h->ctx(), h->dP, n, x, u, tau); return check_launch(h, "tau"); }
+  int rc = stage_reserve(h, bx + 2 * bu); if (rc) return rc;
+  char* s = (char*)h->stage;
+  rc = copy_in(h, s, x, bx, mem); if (rc) return rc;
+  rc = copy_in(h, s + bx, u, bu, mem); if (rc) return rc;
+  launch_tau(h->ctx(), h->dP, n, (double*)s, (double*)(s + bx), (double*)(s + bx + bu));
+  rc = check_launch(h, "tau"); if (rc) return rc;
+  return copy_out(h, tau, s + bx + bu, bu, mem);
+}
+
+int smpc_kinematics(smpc_handle_t* h, int32_t n, const double* x, double* ee, double* dist, int32_t mem) {
+  if (n <= 0) return SMPC_OK;
+  const size_t bx = sizeof(double) * n * NX, be = sizeof(double) * n * 3, bd = sizeof(double) * n * NPAIR;
+  if (mem == SMPC_DEVICE) { launch_kin(h->ctx(), h->dP, n, x, ee, dist); return check_launch(h, "kinematics"); }
+  int rc = stage_reserve(h, bx + be + bd); if (rc) return rc;
+  char* s = (char*)h->stage;
+  rc = copy_in(h, s, x, bx, mem); if (rc) return rc;
+  launch_kin(h->ctx(), h->dP, n, (double*)s, (double*)(s + bx), (double*)(s + bx + be));
+  rc = check_launch(h, "kinematics"); if (rc) return rc;
+  rc = copy_out(h, ee, s + bx, be, mem); if (rc) return rc;
+  return copy_out(h, dist, s + bx + be, bd, mem);
+}
+
+int smpc_nn_constraint(smpc_handle_t* h, int32_t n, const double* x, double* cval, double* grad, int32_t mem) {
+  if (!h->dW) return fail(h, SMPC_ERR_ARG, "smpc_nn_constraint: this handle has no viability network");
+  if (n <= 0) return SMPC_OK;
+  const size_t bx = sizeof(double) * n * NX, bo = sizeof(double) * n * NN_OUT;
+  int rc = stage_reserve(h, bx + bo + sizeof(double) * n * (NX + 1)); if (rc) return rc;
+  char* s = (char*)h->stage;
+  const double* xd = x;
+  if (mem == SMPC_HOST) { rc = copy_in(h, s, x, bx, mem); if (rc) return rc; xd = (double*)s; }
+  double* o11 = (double*)(s + bx);
+  launch_mlp(h->ctx(), h->dP, h->w, n, 0, ROWS_FLAT, n, xd, nullptr, nullptr, nullptr, o11, true);
+  rc = check_launch(h, "nn_constraint"); if (rc) return rc;
+  // de-interleave [n][11] -> c[n], grad[n][10]
+  double* dc = (double*)(s + bx + bo);
+  double* dg = dc + n;
+  CK(h, cudaMemcpy2DAsync(dc, sizeof(double), o11, sizeof(double) * NN_OUT, sizeof(double), n, cudaMemcpyDeviceToDevice, h->stream));
+  CK(h, cudaMemcpy2DAsync(dg, sizeof(double) * NX, o11 + 1, sizeof(double) * NN_OUT, sizeof(double) * NX, n, cudaMemcpyDeviceToDevice, h->stream));
+  rc = copy_out(h, cval, dc, sizeof(double) * n, mem); if (rc) return rc;
+  return copy_out(h, grad, dg, sizeof(double) * n * NX, mem);
+}
+
+int smpc_get_lin(smpc_handle_t* h, double* lin, int32_t mem) { return copy_out(h, lin, h->lin, sizeof(double) * h->B * (h->N + 1) * REC, mem); }
+
+int smpc_get_qp(smpc_handle_t* h, double* dz, double* pi, double* lam, double* t, int32_t mem) {
+  const size_t nst = (size_t)h->B * (h->N + 1);
+  const size_t b1 = sizeof(double) * nst * 15, b2 = sizeof(double) * h->B * h->N * 10, b3 = sizeof(double) * nst * SMPC_QP_NC;
+  int rc = stage_reserve(h, b1 + b2 + 2 * b3); if (rc) return rc;
+  char* s = (char*)h->stage;
+  launch_dump_qp(h->ctx(), h->B, h->N, h->qpbuf, qp_stride_doubles(h->N), h->lin, (double*)s, (double*)(s + b1), (double*)(s + b1 + b2), (double*)(s + b1 + b2 + b3));
+  rc = check_launch(h, "get_qp"); if (rc) return rc;
+  rc = copy_out(h, dz, s, b1, mem); if (rc) return rc;
+  rc = copy_out(h, pi, s + b1, b2, mem); if (rc) return rc;
+  rc = copy_out(h, lam, s + b1 + b2, b3, mem); if (rc) return rc;
+  return copy_out(h, t, s + b1 + b2 + b3, b3, mem);
+}
+
+static int32_t* state_ptr(smpc_handle_t* h, int32_t f) {
+  switch (f) {
+    case SMPC_STATE_FAILS: return h->fails;
+    case SMPC_STATE_R: return h->r;
+    case SMPC_STATE_STATUS: return h->status;
+    case SMPC_STATE_QP_ITER: return h->qp_iter;
+    case SMPC_STATE_QP_STATUS: return h->qp_status;
+  }
+  return nullptr;
+}
+int smpc_get_state_i32(smpc_handle_t* h, int32_t f, int32_t* out, int32_t mem) {
+  int32_t* p = state_ptr(h, f);
+  if (!p) return fail(h, SMPC_ERR_ARG, "smpc_get_state_i32: unknown field");
+  return copy_out(h, out, p, sizeof(int32_t) * h->B, mem);
+}
+int smpc_set_state_i32(smpc_handle_t* h, int32_t f, const int32_t* in, int32_t mem) {
+  int32_t* p = state_ptr(h, f);
+  if (!p) return fail(h, SMPC_ERR_ARG, "smpc_set_state_i32: unknown field");
+  return copy_in(h, p, in, sizeof(int32_t) * h->B, mem);
+}
+int smpc_get_x_viable(smpc_handle_t* h, double* xv, int32_t mem) { return copy_out(h, xv, h->x_viable, sizeof(double) * h->B * NX, mem); }
+
+int smpc_get_times(smpc_handle_t* h, double* out7) { for (int i = 0; i < 7; ++i) out7[i] = h->times[i]; return SMPC_OK; }
+int64_t smpc_launch_count(const smpc_handle_t* h) { return h->launches; }
+void* smpc_stream(smpc_handle_t* h) { return (void*)h->stream; }
+int smpc_sync(smpc_handle_t* h) { CK(h, cudaStreamSynchronize(h->stream)); return check_launch(h, "sync"); }
+
+// ------------------------------------------------------------------------------------------------ closed loop
+int smpc_sim_create(smpc_handle_t* c, smpc_handle_t* bk, int32_t n_steps, smpc_sim_t** out) {
+  if (!c || !bk || !out || n_steps <= 0 || c->B != bk->B || c->device != bk->device) return fail(c, SMPC_ERR_ARG, "smpc_sim_create: bad arguments");
+  smpc_sim* s = new smpc_sim;
+  s->c = c; s->bk = bk;
+  SimDev& d = s->d;
+  const int B = c->B, Nb = bk->N;
+  d.B = B; d.N = c->N; d.Nb = Nb; d.n_steps = n_steps;
+#define CKS(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { fail(c, SMPC_ERR_CUDA, #call, e__); delete s; return SMPC_ERR_CUDA; } } while (0)
+  CKS(dalloc(c, &d.x, (size_t)B * NX));
+  CKS(dalloc(c, &d.xlog, (size_t)B * (n_steps + 1) * NX));
+  CKS(dalloc(c, &d.ulog, (size_t)B * n_steps * NU));
+  CKS(dalloc(c, &d.x_abort, (size_t)B * (Nb + 1) * NX));
+  CKS(dalloc(c, &d.u_abort, (size_t)B * Nb * NU));
+  CKS(dalloc(c, &d.xv_first, (size_t)B * NX));
+  CKS(dalloc(c, &d.u_ctrl, (size_t)B * NU));
+  CKS(dalloc(c, &d.u, (size_t)B * NU));
+  CKS(dalloc(c, &d.mode, (size_t)B)); CKS(dalloc(c, &d.ja, (size_t)B)); CKS(dalloc(c, &d.outcome, (size_t)B));
+  CKS(dalloc(c, &d.need_ctrl, (size_t)B)); CKS(dalloc(c, &d.need_backup, (size_t)B)); CKS(dalloc(c, &d.abort_flag, (size_t)B));
+  CKS(dalloc(c, &d.live, (size_t)B));
+  CKS(dalloc(c, &d.counters, (size_t)4));
+  CKS(dalloc(c, &s->outcome_tmp, (size_t)B));
+#undef CKS
+  *out = s;
+  return SMPC_OK;
+}
+void smpc_sim_destroy(smpc_sim_t* s) { delete s; }   // device buffers are owned (and freed) by the main handle
+
+int smpc_sim_reset(smpc_sim_t* s, const double* x_init, int32_t mem) {
+  smpc_handle* c = s->c;
+  SimDev& d = s->d;
+  const int B = d.B;
+  const double nan = __builtin_nan("");
+  LaunchCtx lc = c->ctx();
+  launch_fill_f64(lc, d.xlog, (size_t)B * (d.n_steps + 1) * NX, nan);
+  launch_fill_f64(lc, d.ulog, (size_t)B * d.n_steps * NU, nan);
+  launch_fill_f64(lc, d.xv_first, (size_t)B * NX, nan);
+  launch_fill_i32(lc, d.mode, B, 0); launch_fill_i32(lc, d.ja, B, 0); launch_fill_i32(lc, d.outcome, B, 0);
+  CK(c, cudaMemsetAsync(d.counters, 0, 4 * sizeof(unsigned long long), c->stream));
+  int rc = copy_in(c, d.x, x_init, sizeof(double) * B * NX, mem); if (rc) return rc;
+  CK(c, cudaMemcpy2DAsync(d.xlog, sizeof(double) * (d.n_steps + 1) * NX, d.x, sizeof(double) * NX, sizeof(double) * NX, B, cudaMemcpyDeviceToDevice, c->stream));
+  s->j = 0;
+  return check_launch(c, "sim_reset");
+}
+
+int smpc_sim_step(smpc_sim_t* s) {
+  smpc_handle* c = s->c;
+  smpc_handle* bk = s->bk;
+  SimDev& d = s->d;
+  if (s->j >= d.n_steps) return fail(c, SMPC_ERR_ARG, "smpc_sim_step: past n_steps");
+  // both handles launch on the main controller's stream so that the step is one ordered sequence
+  LaunchCtx lc = c->ctx();
+  cudaStream_t bk_stream = bk->stream;
+  bk->stream = c->stream;
+  launch_sim_pre(lc, d, c->dP, s->j);
+  c->timed = false; bk->timed = false;
+  int rc = step_pipeline(c, d.x, d.need_ctrl, d.u_ctrl, d.abort_flag);
+  if (!rc) {
+    launch_sim_mid(lc, d, c->x_viable, bk->xg, bk->ug, c->qp_iter);
+    rc = solve_pipeline(bk, c->x_viable, d.need_backup);     // safe_ocp.solve(x_viable), one RTI (mpc.py:177)
+  }
+  if (!rc) {
+    launch_sim_post(lc, d, c->dP, s->j, bk->status, bk->xt, bk->ut, c->plant_inertial, c->tau_noise, bk->qp_iter);
+    rc = check_launch(c, "sim_step");
+  }
+  bk->stream = bk_stream;
+  c->launches += 0;
+  s->j += 1;
+  return rc;
+}
+int smpc_sim_run(smpc_sim_t* s, int32_t n) {
+  for (int i = 0; i < n; ++i) { int rc = smpc_sim_step(s); if (rc) return rc; }
+  return SMPC_OK;
+}
+int smpc_sim_get_outcome(smpc_sim_t* s, int32_t* out, int32_t mem) {
+  launch_sim_outcome(s->c->ctx(), s->d, s->c->dP, s->outcome_tmp);
+  int rc = check_launch(s->c, "sim_outcome"); if (rc) return rc;
+  return copy_out(s->c, out, s->outcome_tmp, sizeof(int32_t) * s->d.B, mem);
+}
+int smpc_sim_get_log(smpc_sim_t* s, double* x, double* u, int32_t mem) {
+  int rc = copy_out(s->c, x, s->d.xlog, sizeof(double) * s->d.B * (s->d.n_steps + 1) * NX, mem);
+  return rc ? rc : copy_out(s->c, u, s->d.ulog, sizeof(double) * s->d.B * s->d.n_steps * NU, mem);
+}
+int smpc_sim_get_x_viable(smpc_sim_t* s, double* xv, int32_t mem) { return copy_out(s->c, xv, s->d.xv_first, sizeof(double) * s->d.B * NX, mem); }
+int smpc_sim_get_counters(smpc_sim_t* s, int64_t* out4) {
+  unsigned long long v[4];
+  CK(s->c, cudaMemcpyAsync(v, s->d.counters, sizeof v, cudaMemcpyDeviceToHost, s->c->stream));
+  CK(s->c, cudaStreamSynchronize(s->c->stream));
+  for (int i = 0; i < 4; ++i) out4[i] = (int64_t)v[i];
+  return SMPC_OK;
+}
+
+}  // extern "C"

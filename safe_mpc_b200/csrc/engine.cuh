@@ -1,0 +1,69 @@
+// Internal declarations of the CUDA engine behind include/safe_mpc_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/safe_mpc_b200.h"
+#include "qp_lanes.cuh"
+
+namespace smpc {
+
+constexpr int NN_OUT = 11;   // viability row value + 10 gradient entries
+
+struct MlpWeights {
+  // fp32 weights of the reference architecture 10 -> 256 -> 256 -> 256 -> 1 (safe_set.py:26-43)
+  const float *W1, *b1, *W2, *b2, *W3, *b3, *W4, *b4;   // row-major [out][in]
+  const float *W2t, *W3t;                               // transposed copies [in][out] for the forward sweep
+};
+
+// which (problem, stage) rows the viability network is evaluated on
+enum { ROWS_TERMINAL = 0, ROWS_ALL = 1, ROWS_RECEDING = 2, ROWS_FLAT = 3 };
+
+struct LaunchCtx {
+  cudaStream_t stream;
+  int64_t* launches;
+};
+
+// kernels.cu
+void launch_prep(const LaunchCtx& c, const smpc_problem_t* dP, int B, int N, double* xg, const double* ug, const uint8_t* act, bool correct);
+void launch_mlp(const LaunchCtx& c, const smpc_problem_t* dP, const MlpWeights& w, int B, int N, int rows_mode, int n_flat,
+                const double* xsrc, const int32_t* r, const uint8_t* act, const uint8_t* need, double* out11, bool want_grad);
+void launch_linearize(const LaunchCtx& c, const smpc_problem_t* dP, int B, int N, const double* xg, const double* ug,
+                      const int32_t* r, const uint8_t* act, const double* nn11, double* lin);
+void launch_ctrl_post1(const LaunchCtx& c, const smpc_problem_t* dP, int B, int N, const uint8_t* act, const double* xg, const double* ug,
+                       const double* xt, int32_t* status, int32_t* fails, int32_t* r, double* x_viable, uint8_t* need_scan,
+                       uint8_t* abort_flag, double* u_out);
+void launch_ctrl_post2(const LaunchCtx& c, const smpc_problem_t* dP, int B, int N, const uint8_t* act, double* xg, double* ug,
+                       const double* xt, const double* ut, const int32_t* fails, int32_t* r, int32_t* cur_step,
+                       const uint8_t* need_scan, const double* scan11, const uint8_t* abort_flag, double* u_out);
+void launch_plant(const LaunchCtx& c, const smpc_problem_t* dP, int B, const double* inertial, const double* noise, const double* x,
+                  const double* u, const uint8_t* act, double* xn, double* a);
+void launch_tau(const LaunchCtx& c, const smpc_problem_t* dP, int n, const double* x, const double* u, double* tau);
+void launch_kin(const LaunchCtx& c, const smpc_problem_t* dP, int n, const double* x, double* ee, double* dist);
+void launch_fill_i32(const LaunchCtx& c, int32_t* p, int n, int32_t v);
+void launch_fill_f64(const LaunchCtx& c, double* p, size_t n, double v);
+void launch_set_xviable_from_guess(const LaunchCtx& c, int B, int N, const double* xg, double* xv);
+void launch_dump_qp(const LaunchCtx& c, int B, int N, const double* qpbuf, size_t stride, const double* lin, double* dz, double* pi, double* lam, double* t);
+
+// sim kernels
+struct SimDev {
+  int B, N, Nb, n_steps;
+  double *x, *xlog, *ulog, *x_abort, *u_abort, *xv_first, *u_ctrl, *u;
+  int32_t *mode, *ja, *outcome;
+  uint8_t *need_ctrl, *need_backup, *abort_flag, *live;
+  unsigned long long* counters;   // [4]
+};
+void launch_sim_pre(const LaunchCtx& c, const SimDev& s, const smpc_problem_t* dP, int j);
+void launch_sim_mid(const LaunchCtx& c, const SimDev& s, const double* x_viable, double* bk_xg, double* bk_ug, const int32_t* qp_iter_main);
+void launch_sim_post(const LaunchCtx& c, const SimDev& s, const smpc_problem_t* dP, int j, const int32_t* bk_status, const double* bk_xt,
+                     const double* bk_ut, const double* inertial, const double* noise, const int32_t* qp_iter_bk);
+void launch_sim_outcome(const LaunchCtx& c, const SimDev& s, const smpc_problem_t* dP, int32_t* out);
+
+// qp.cu
+size_t qp_stride_doubles(int N);
+void launch_qp(const LaunchCtx& c, const smpc_problem_t* dP, int B, int N, const double* lin, const double* x0, const int32_t* r,
+               const uint8_t* act, double* qpbuf, double* xt, double* ut, int32_t* status, int32_t* qp_iter, int32_t* qp_status, double* qp_res);
+
+}  // namespace smpc

@@ -1,0 +1,75 @@
+"""Product binding: the CUDA engine behind include/safe_mpc_b200.h.
+
+``Engine`` = one batched OCP solver handle on one GPU (what ``AcadosOcpSolver`` is to the reference's
+controllers, controller.py:247, but for B problems at once); ``Sim`` = the closed loop of scripts/mpc.py over the
+batch.  Arrays are numpy (host; the library copies) or torch CUDA tensors (device pointers, zero copy).
+There is no CPU path: a missing library or a missing GPU raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import abi
+from .binding import EngineBase, SimBase, _is_torch
+
+_LIB = None
+
+
+def library_path():
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), 'csrc', 'libsafe_mpc_b200.so')
+
+
+def load_library():
+    """dlopen the in-tree CUDA library; fail loudly when it has not been built."""
+    global _LIB
+    if _LIB is None:
+        path = library_path()
+        if not os.path.isfile(path):
+            raise RuntimeError(f'{path} is missing: build it with `python -m safe_mpc_b200.build` '
+                               '(or __graft_entry__.build()); the engine has no CPU fallback')
+        lib = C.CDLL(path)
+        lib.smpc_version.restype = C.c_char_p
+        lib.smpc_last_error.restype = C.c_char_p
+        lib.smpc_launch_count.restype = C.c_int64
+        lib.smpc_launch_count.argtypes = [C.c_void_p]
+        lib.smpc_stream.restype = C.c_void_p
+        lib.smpc_stream.argtypes = [C.c_void_p]
+        _LIB = lib
+    return _LIB
+
+
+class Engine(EngineBase):
+    prefix = 'smpc_'
+    has_mem = True
+
+    def __init__(self, prob: abi.Problem, batch: int, device: int = 0):
+        super().__init__(load_library(), prob, batch, device)
+        self.device = device
+
+    def _in(self, a, dtype, shape=None):
+        # torch tensors live on torch's stream; the engine has its own -> order them
+        if a is not None and _is_torch(a) and a.is_cuda:
+            import torch
+            torch.cuda.current_stream(a.device).synchronize()
+        return super()._in(a, dtype, shape)
+
+    def sync(self):
+        self._call('sync')
+
+    def launch_count(self) -> int:
+        return int(self.lib.smpc_launch_count(self.h))
+
+    def stream(self) -> int:
+        return int(self.lib.smpc_stream(self.h) or 0)
+
+    def times(self):
+        out = (C.c_double * 7)()
+        self._call('get_times', out)
+        fields = ['time_lin', 'time_sim', 'time_qp', 'time_qp_solver_call', 'time_glob', 'time_reg', 'time_tot']
+        return dict(zip(fields, [v * 1e-3 for v in out]))     # seconds, like acados get_stats
+
+
+class Sim(SimBase):
+    def sync(self):
+        self.main.sync()

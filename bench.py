@@ -1,0 +1,304 @@
+#!/usr/bin/env python
+"""Headline benchmark: RTI iterations/s of the batched closed-loop MPC (BASELINE.json metric).
+
+A step = one closed-loop control step of every problem of the batch (controller.step = RTI solve, backup solve
+on abort, plant step; scripts/mpc.py:125-264).  Workload at 1 GPU = BASELINE.json configs[1]: Z1(-like) ST
+controller with the viability-network terminal constraint, N=45, dt=5 ms, batch 10 000 per GPU (weak scaling).
+
+  python bench.py [--gpus N --steps K --warmup W]          this engine (one process per GPU under torchrun)
+  python bench.py --impl reference ...                      the CPU path (oracle port of the acados RTI path,
+                                                            all host threads, bounded sample of the same workload)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from safe_mpc_b200 import abi, distributed as D  # noqa: E402
+from safe_mpc_b200.parser import Parameters, default_args  # noqa: E402
+from safe_mpc_b200.problem import ModelData, build_problem  # noqa: E402
+
+METRIC = 'rti_iterations_per_sec'
+UNIT = 'RTI iterations/s'
+Q0 = np.array([-0.3, 0.8, -1.65, 0.658, 0.0])
+
+
+def workload(controller, N, noise, seed, lo, hi):
+    """Synthetic inputs of problems [lo, hi): initial states around the shipped IC, perturbed plants, torque noise."""
+    args = default_args(controller=controller, horizon=N, noise=noise)
+    params = Parameters(args, 'z1', rti=True)
+    params.N = N
+    md = ModelData(params)
+    B = hi - lo
+    x0 = np.zeros((B, abi.NX)); pin = np.zeros((B, abi.NQ, 10))
+    for i, gi in enumerate(range(lo, hi)):          # per-problem streams -> independent of the sharding
+        rng = np.random.default_rng([seed, gi])
+        x0[i, :abi.NQ] = Q0 + 0.15 * rng.uniform(-1, 1, abi.NQ)
+        x0[i, abi.NQ:] = 0.2 * rng.uniform(-1, 1, abi.NQ)
+        pin[i] = md.inertial * (1 + noise / 100 * rng.uniform(-1, 1, (abi.NQ, 10)))
+    return params, md, x0, pin
+
+
+def make_handles(E, params, md, controller, B, arg):
+    prob, keep = build_problem(params, controller, cost='ext', model=md)
+    bprob, bkeep = build_problem(params, 'backup', cost='zero', N=params.back_hor, model=md)
+    main, bk = E(prob, B, arg), E(bprob, B, arg)
+    main._keepalive = (prob, keep); bk._keepalive = (bprob, bkeep)
+    return main, bk, prob
+
+
+def warm_guess(main, x0, N, iters):
+    """Warm start: a few full-step SQP iterations from the constant guess (x0 repeated, u = 0), untimed."""
+    xg = np.repeat(x0[:, None, :], N + 1, axis=1).copy()
+    ug = np.zeros((x0.shape[0], N, abi.NU))
+    main.set_guess(xg, ug)
+    for _ in range(iters):
+        main.rti_solve(x0)
+        xt, ut = main.get_temp()
+        main.set_guess(xt, ut)
+    main.reset_controller()
+
+
+class ClockSampler:
+    QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--id={gpu_index}', f'--query-gpu={self.QUERY}', '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            pass
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill(); out, _ = self.proc.communicate()
+        sm, smax, reasons = [], [], set()
+        for line in out.splitlines():
+            f = [s.strip() for s in line.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(smax) if smax else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def time_oracle(controller, N, noise, seed, n_problems, steps, warmup, sqp_iters):
+    """The CPU path (oracle port of the reference's acados RTI path) on a bounded sample of the workload."""
+    from oracle.oracle import Oracle, OracleSim
+    params, md, x0, pin = workload(controller, N, noise, seed, 0, n_problems)
+    main, bk, prob = make_handles(Oracle, params, md, controller, n_problems, 0)
+    main.set_plant_inertial(pin)
+    warm_guess(main, x0, N, sqp_iters)
+    sim = OracleSim(main, bk, warmup + steps)
+    sim.reset(x0)
+    sim.run(warmup)
+    c0 = sim.counters()
+    t0 = time.perf_counter()
+    sim.run(steps)
+    dt = time.perf_counter() - t0
+    c1 = sim.counters()
+    solves = (c1['rti_solves'] - c0['rti_solves']) + (c1['backup_solves'] - c0['backup_solves'])
+    return {'value': solves / dt, 'seconds': dt, 'solves': solves, 'cores': main.num_threads(),
+            'ipm_per_solve': (c1['ipm_iterations'] - c0['ipm_iterations']) / max(1, solves),
+            'sample': f'{n_problems} problems x {steps} closed-loop steps of the same workload ({controller}, N={N})',
+            'outcome': D.outcome_counts(sim.outcome())}
+
+
+def run_reference(a):
+    rank, _, world = D.env_world()
+    if rank != 0:
+        return
+    n = a.ref_problems
+    r = time_oracle(a.controller, a.horizon, a.noise, a.seed, n, a.steps, a.warmup, a.sqp_iters)
+    line = {'metric': METRIC, 'value': r['value'], 'unit': UNIT, 'impl': 'reference', 'n_gpus': a.gpus, 'steps': a.steps, 'warmup': a.warmup,
+            'ms_per_step': 1e3 * r['seconds'] / a.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+            'data': 'synthetic',
+            'config': {'workload': f'closed-loop RTI MPC, controller={a.controller}, N={a.horizon}, dt=5ms, synthetic Z1-like 5-DOF chain + random-init viability MLP',
+                       'batch': n, 'note': 'CPU path: oracle port of the acados SQP_RTI/HPIPM path (acados, CasADi, adam, l4casadi are not installable offline)'},
+            'cpu_baseline': {'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': 'port', 'sample': r['sample']},
+            'e2e': {'value': r['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'ipm_iterations_per_solve': r['ipm_per_solve'], 'outcome': r['outcome']}
+    print(json.dumps(line), flush=True)
+
+
+def run_engine(a):
+    import torch
+    from safe_mpc_b200.engine import Engine, Sim
+    rank, local_rank, world = D.init('nccl')
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device; this engine has no CPU fallback (use --impl reference for the CPU path)')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    B = a.batch                                   # per GPU (weak scaling)
+    lo, hi = rank * B, (rank + 1) * B
+    params, md, x0, pin = workload(a.controller, a.horizon, a.noise, a.seed, lo, hi)
+    N = a.horizon
+    main, bk, prob = make_handles(Engine, params, md, a.controller, B, local_rank)
+    main.set_plant_inertial(pin)
+    warm_guess(main, x0, N, a.sqp_iters)
+    total_steps = a.warmup + a.steps
+    sim = Sim(main, bk, total_steps)
+    sim.reset(x0)
+    stream = torch.cuda.ExternalStream(main.stream(), device=dev)
+    sim.run(a.warmup)
+    main.sync()
+    c0 = sim.counters(); l0 = main.launch_count() + bk.launch_count()
+    D.barrier(); torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps + 1)]
+    evs[0].record(stream)
+    for i in range(a.steps):
+        sim.step()
+        evs[i + 1].record(stream)
+    main.sync(); torch.cuda.synchronize()
+    D.barrier()
+    clocks = sampler.stop() if sampler else None
+    ms = evs[0].elapsed_time(evs[-1])
+    lat = np.array([evs[i].elapsed_time(evs[i + 1]) for i in range(a.steps)])
+    c1 = sim.counters(); l1 = main.launch_count() + bk.launch_count()
+    solves = (c1['rti_solves'] - c0['rti_solves']) + (c1['backup_solves'] - c0['backup_solves'])
+    ipm = c1['ipm_iterations'] - c0['ipm_iterations']
+
+    # ---- dominant kernel (QP) timed alone on this stream, for the roofline ----
+    xs = torch.tensor(x0, device=dev)
+    main.rti_solve(xs); main.sync()
+    tq = []
+    for _ in range(3):
+        main.rti_solve(xs); main.sync()
+        t = main_times(main)
+        tq.append(t)
+    qp_ms = float(np.median([t['time_qp'] for t in tq]) * 1e3)
+    lin_ms = float(np.median([t['time_lin'] for t in tq]) * 1e3)
+    it_qp = float(main.get_state(abi.STATE_QP_ITER).mean())
+
+    # ---- end to end through the C ABI with host buffers (H2D / D2H inside the timed region) ----
+    e2e = None
+    if not a.no_e2e:
+        warm_guess(main, x0, N, 0)
+        main.set_guess(*[np.ascontiguousarray(v) for v in guess_copy(main)])
+        xh = torch.tensor(x0).pin_memory().numpy() if hasattr(torch.Tensor, 'pin_memory') else x0.copy()
+        x_cur = xh.copy()
+        for _ in range(max(1, a.warmup // 2)):
+            u, ab = main.controller_step(x_cur); x_cur, _ = main.plant_step(x_cur, u)
+        D.barrier()
+        t0 = time.perf_counter()
+        n_e2e = max(3, a.steps // 2)
+        for _ in range(n_e2e):
+            u, ab = main.controller_step(x_cur)
+            x_cur, _ = main.plant_step(x_cur, u)
+        main.sync()
+        e2e_s = time.perf_counter() - t0
+        e2e = {'steps': n_e2e, 'seconds': e2e_s, 'solves': n_e2e * B,
+               'h2d': B * (abi.NX * 8 + abi.NU * 8) + B * (abi.NX + abi.NU) * 8, 'd2h': B * (abi.NU * 8 + 1) + B * (abi.NX + abi.NU) * 8}
+
+    # ---- aggregate over ranks ----
+    vec = [ms, solves, ipm, l1 - l0, (e2e['seconds'] if e2e else 0.0), (e2e['solves'] if e2e else 0.0)]
+    allv = D.all_gather_vector(vec, device=dev)
+    ms_max = max(v[0] for v in allv)
+    solves_all = sum(v[1] for v in allv)
+    outcome = D.gather_outcomes(sim.outcome(), device=dev)
+    if rank != 0:
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+    peak_src = 'measured (MEASURED_PEAKS.json hbm_gbs)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s (B200_PROFILING.md)'
+    # algorithmic bytes of one QP launch: stage records in, x_temp/u_temp + status out
+    alg_bytes = B * ((N + 1) * abi.REC * 8 + ((N + 1) * abi.NX + N * abi.NU) * 8 + abi.NX * 8 + 12)
+    achieved = alg_bytes / (qp_ms * 1e-3) / 1e9
+    value = solves_all / (ms_max * 1e-3)
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
+        'ms_per_step': ms_max / a.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+        'data': 'synthetic',
+        'config': {'workload': f'closed-loop RTI MPC, controller={a.controller} (viability-network terminal constraint), N={N}, dt=5ms, '
+                               f'synthetic Z1-like 5-DOF chain + random-init viability MLP 10-256-256-256-1',
+                   'batch_per_gpu': B, 'global_batch': B * world, 'parallelism': f'dp{world} (problem sharding, no hot-path collective)',
+                   'l2': f'working set {B * (main_qp_bytes(N)) / 1e9:.2f} GB per GPU > 126 MB L2 (no flush needed)',
+                   'noise_percent': a.noise, 'sqp_warm_start_iters': a.sqp_iters},
+        'p50_step_ms': float(np.percentile(lat, 50)), 'p99_step_ms': float(np.percentile(lat, 99)),
+        'ipm_iterations_per_solve': ipm / max(1, solves),
+        'gpu_launches': int(sum(v[3] for v in allv)),
+        'clocks': clocks,
+        'roofline': {'kernel': 'qp_kernel', 'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak,
+                     'traffic': None, 'peak_source': peak_src, 'algorithmic_bytes_per_launch': alg_bytes, 'launch_ms': qp_ms,
+                     'ipm_iterations': it_qp, 'linearize_ms': lin_ms},
+        'outcome': D.outcome_counts(outcome),
+    }
+    if e2e:
+        e2e_s = max(v[4] for v in allv)
+        line['e2e'] = {'value': sum(v[5] for v in allv) / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': e2e['h2d'], 'd2h_bytes_per_step': e2e['d2h'],
+                       'api': 'smpc_controller_step + smpc_plant_step with host buffers'}
+    if world == 1 and not a.no_cpu:
+        r = time_oracle(a.controller, N, a.noise, a.seed, a.cpu_problems, a.cpu_steps, 1, a.sqp_iters)
+        line['cpu_baseline'] = {'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': 'port', 'sample': r['sample'],
+                                'ipm_iterations_per_solve': r['ipm_per_solve']}
+    print(json.dumps(line), flush=True)
+
+
+def main_times(main):
+    return main.times()
+
+
+def guess_copy(main):
+    return main.get_guess()
+
+
+def main_qp_bytes(N):
+    per_stage = 16 * (1 + 1 + 4 + 4 + 1 + 5 + 10 + 1 + 1 + 1 + 1 + 4 + 1 + 1 + 4 + 4)
+    return ((N + 1) * (per_stage + abi.REC) + 320) * 8
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='engine', choices=['engine', 'reference'])
+    ap.add_argument('--controller', default='st')
+    ap.add_argument('--horizon', type=int, default=45)
+    ap.add_argument('--batch', type=int, default=10000, help='problems per GPU')
+    ap.add_argument('--noise', type=float, default=0.0)
+    ap.add_argument('--seed', type=int, default=0)
+    ap.add_argument('--sqp-iters', type=int, default=5, dest='sqp_iters')
+    ap.add_argument('--ref-problems', type=int, default=256, dest='ref_problems')
+    ap.add_argument('--cpu-problems', type=int, default=256, dest='cpu_problems')
+    ap.add_argument('--cpu-steps', type=int, default=8, dest='cpu_steps')
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-cpu', action='store_true')
+    a = ap.parse_args()
+    if a.warmup < 3 and a.impl == 'engine':
+        a.warmup = 3
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_engine(a)
+
+
+if __name__ == '__main__':
+    main()

@@ -270,8 +270,7 @@ def guess_copy(main):
 
 
 def main_qp_bytes(N):
-    per_stage = 16 * (1 + 1 + 4 + 4 + 1 + 5 + 10 + 1 + 1 + 1 + 1 + 4 + 1 + 1 + 4 + 4)
-    return ((N + 1) * (per_stage + abi.REC) + 320) * 8
+    return ((N + 1) * (736 + abi.REC) + 320) * 8     # stage blocks (qp_lanes.cuh QP_ST) + stage records
 
 
 def main():

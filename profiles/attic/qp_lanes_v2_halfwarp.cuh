@@ -9,10 +9,15 @@
 //   * the Cholesky elimination of the 5 control columns is a sequence of shuffle broadcasts + rank-1 updates on the lane
 //     columns; each lane keeps its row of the factor for the vector-only re-solves (corrector / centering);
 //   * inequality rows are owned by lanes: lanes 0-4 a torque row, lanes 5-14 the box row of their state, lanes 5-10 also
-//     a capsule row, lane 11 the viability row (+ its slacks);  lam/t live in global memory as [slot][lane];
-//   * the stage record (linearisation, 192 doubles) is staged through shared memory once per sweep and stage.
-// The code is written against a small `Lanes` policy (lane id, shuffle, group barrier, scratch pointer) so that the
-// same source runs on the device (LanesDev, qp.cu) and, for kernel-logic tests without a GPU, on the host
+//     a capsule row, lane 11 the viability row (+ its slacks);
+//   * all per-stage data of a problem (iterate, multipliers, factor, step) is ONE contiguous block per stage in global
+//     memory; every sweep streams the stage record + the sub-range of the block it needs into shared memory with a
+//     double-buffered asynchronous bulk copy (TMA 1-D, mbarrier completion) issued one stage ahead, so the
+//     sequential stage recursion never waits on HBM latency; results are stored straight from registers;
+//   * the primal-dual update of iteration i is fused into the factorisation sweep of iteration i+1 (both walk the
+//     stages backwards), which removes one full pass over the data per iteration.
+// The code is written against a small `Lanes` policy (lane id, shuffle, group barrier, scratch, async stage fetch) so
+// that the same source runs on the device (LanesDev, qp.cu) and, for kernel-logic tests without a GPU, on the host
 // (tests/emu: 16 threads and a barrier).  The product only ever instantiates the device policy.
 #pragma once
 #include "dev_model.cuh"
@@ -21,34 +26,42 @@ namespace smpc {
 
 constexpr int QL = 16;            // lanes per problem
 constexpr int NSLOT = 4;          // constraint slots per lane: rowA lower/upper, rowB lower/upper
-constexpr int QP_SCRATCH = REC + 96;   // doubles of group scratch: stage record + replicated vectors
 
-// per-problem global-memory views (all double; [..][16] arrays are indexed by lane)
+// ---- per-stage block in global memory (doubles); [..16] arrays are indexed by lane, [..64] by slot*16+lane ----
+enum {
+  O_DZ = 0,      // 16  step: primal
+  O_DPI = 16,    // 16  step: multipliers of the dynamics k -> k+1 (lanes 5..14)
+  O_DPIM = 32,   // 16  step: multipliers of the dynamics k-1 -> k (copy kept with stage k)
+  O_DLAM = 48,   // 64
+  O_DTT = 112,   // 64
+  O_Z = 176,     // 16  iterate
+  O_PI = 192,    // 16
+  O_PIM = 208,   // 16  pi_{k-1}
+  O_LAM = 224,   // 64
+  O_T = 288,     // 64
+  O_AUX = 352,   // 16  slacks of the soft row: s_l s_u lam_sl lam_su t_sl t_su ds_l ds_u dlam_sl dlam_su dt_sl dt_su prod_sl prod_su
+  O_PROD = 368,  // 64  dlam_aff * dt_aff
+  O_GB = 432,    // 16  res_g
+  O_WV = 448,    // 16  P_{k+1} res_b_k
+  O_RB = 464,    // 16  res_b_k
+  O_PV = 480,    // 16  l (lanes 0..4) and p (lanes 5..14) of the current solve
+  O_FAC = 496,   // 80  rows of [Lr; Ls]: fac[j*16 + lane] = L[lane][j]
+  O_PM = 576,    // 160 Riccati matrix: Pm[r*16 + lane] = P[r][lane-5]
+  QP_ST = 736
+};
+constexpr int QP_L0 = 320;                    // stage-0 state factor (columns, rows), after the stage blocks
+constexpr int QP_STATE_MAX = QP_ST - O_Z;     // largest state range a sweep fetches (560 doubles)
+constexpr int QP_BUF = REC + QP_STATE_MAX;    // one staging buffer: stage record + state range
+constexpr int QP_VEC = 96;                    // replicated-vector scratch
+constexpr int QP_SMEM_PER_GROUP = 2 * QP_BUF + QP_VEC;   // doubles
+
 struct QpMem {
   const double* rec;   // [N+1][REC]
   const double* x0;    // [10]
-  double* z;           // [N+1][16]   primal iterate  (lane c: z_c)
-  double* pi;          // [N+1][16]   multipliers of the dynamics k -> k+1 (lanes 5..14)
-  double* lam;         // [N+1][4][16]
-  double* t;           // [N+1][4][16]
-  double* aux;         // [N+1][16]   slack data of the soft row: s_l s_u lam_sl lam_su t_sl t_su ds_l ds_u dlam_sl dlam_su dt_sl dt_su prod_sl prod_su
-  double* fac;         // [N+1][5][16]  rows of the factor [Lr; Ls]: fac[j][lane] = L[lane][j]
-  double* Pm;          // [N+1][10][16] Riccati matrix: Pm[r][lane] = P[r][lane-5]
-  double* pv;          // [N+1][16]   l (lanes 0..4) and p (lanes 5..14) of the current solve
-  double* wv;          // [N+1][16]   P_{k+1} res_b_k
-  double* rb;          // [N+1][16]   res_b_k
-  double* gb;          // [N+1][16]   res_g_k
-  double* prod;        // [N+1][4][16] dlam_aff * dt_aff
-  double* dz;          // [N+1][16]
-  double* dpi;         // [N+1][16]
-  double* dlam;        // [N+1][4][16]
-  double* dtt;         // [N+1][4][16]
-  double* L0;          // [2][10][16]  stage-0 state factor: columns then rows
+  double* st;          // [N+1][QP_ST] + [QP_L0]
   int r;               // receding index of the problem (RealReceding box override)
 };
-
-constexpr size_t qp_doubles_per_stage() { return 16 * (1 + 1 + 4 + 4 + 1 + 5 + 10 + 1 + 1 + 1 + 1 + 4 + 1 + 1 + 4 + 4); }
-constexpr size_t qp_doubles_fixed() { return 2 * 10 * 16; }
+constexpr size_t qp_doubles_per_problem(int N) { return (size_t)(N + 1) * QP_ST + QP_L0; }
 
 struct QpResult {
   int iter, status;          // status: 0 success, 1 max iter, 2 min step, 3 NaN
@@ -61,12 +74,14 @@ struct QpSolver {
   const smpc_problem_t& P;
   const QpMem& M;
   const int N, lane;
-  double* S;          // scratch: [0, REC) stage record, then replicated vectors
-  double* V;          // S + REC: 96 doubles
+  double* V;          // replicated-vector scratch (QP_VEC doubles)
+  const double* S;    // current stage record (in the staging buffer)
+  const double* T;    // current state range, biased so that T[O_xxx + i] addresses field O_xxx
   int nc;
   double dt, hdt2;
 
-  SMPC_HD QpSolver(L& l, const smpc_problem_t& p, const QpMem& m) : ln(l), P(p), M(m), N(p.N), lane(l.lane()), S(l.scratch()), V(l.scratch() + REC), nc(0), dt(p.dt), hdt2(0.5 * p.dt * p.dt) {}
+  SMPC_HD QpSolver(L& l, const smpc_problem_t& p, const QpMem& m)
+      : ln(l), P(p), M(m), N(p.N), lane(l.lane()), V(l.scratch()), S(nullptr), T(nullptr), nc(0), dt(p.dt), hdt2(0.5 * p.dt * p.dt) {}
 
   // ---- small group helpers ----
   SMPC_HD double gsum(double v) { for (int o = 8; o > 0; o >>= 1) v += ln.shfl_xor(v, o); return v; }
@@ -78,22 +93,20 @@ struct QpSolver {
   // replicate a lane-distributed 16-vector into scratch slot `off` (V[off + c] = value of lane c)
   SMPC_HD void publish(int off, double v) { ln.sync(); V[off + lane] = v; ln.sync(); }
 
-  SMPC_HD void load_rec(int k) {
-    ln.sync();
-    const double* src = M.rec + (size_t)k * REC;
-    for (int i = lane; i < REC; i += QL) S[i] = src[i];
-    ln.sync();
-  }
+  // ---- stage streaming ----
+  SMPC_HD double* gst(int k) const { return M.st + (size_t)k * QP_ST; }
+  SMPC_HD void fetch(int k, int buf, int lo, int cnt) { ln.fetch(buf, M.rec + (size_t)k * REC, gst(k) + lo, cnt); }
+  SMPC_HD void acquire(int buf, int lo) { ln.wait(buf); S = ln.buffer(buf); T = S + REC - lo; }
 
   // ---- row ownership ----
-  SMPC_HD bool hasA(int k) const { return lane < 5 ? (S[SMPC_REC_NTAU] > 0.5) : (lane < 15); }
-  SMPC_HD bool hasB(int k) const { return (lane >= 5 && lane <= 10) ? (S[SMPC_REC_NDIST] > 0.5) : (lane == 11 ? S[SMPC_REC_NNROW] > 0.5 : false); }
+  SMPC_HD bool hasA() const { return lane < 5 ? (S[SMPC_REC_NTAU] > 0.5) : (lane < 15); }
+  SMPC_HD bool hasB() const { return (lane >= 5 && lane <= 10) ? (S[SMPC_REC_NDIST] > 0.5) : (lane == 11 ? S[SMPC_REC_NNROW] > 0.5 : false); }
   SMPC_HD bool softB() const { return lane == 11 && S[SMPC_REC_NNROW] > 0.5 && S[SMPC_REC_SOFT] >= 0.0; }
   // canonical row id (box 0-9, tau 10-14, dist 15-20, nn 21)
   SMPC_HD int idA() const { return lane < 5 ? 10 + lane : lane - 5; }
   SMPC_HD int idB() const { return lane == 11 ? 21 : 15 + (lane - 5); }
 
-  // a_rowA . y and a_rowB . y for a replicated 15-vector y (scratch offset `yo`, [u q v] order)
+  // a_rowA . y and a_rowB . y for a replicated 15-vector y ([u q v] order)
   SMPC_HD double dotA(const double* y) const {
     if (lane < 5) {
       double r = 0.0;
@@ -142,40 +155,41 @@ struct QpSolver {
     double lam[NSLOT], t[NSLOT], r[NSLOT];   // r = res_d
     double sl, su, lsl, lsu, tsl, tsu, rsl, rsu, rgsl, rgsu;   // slack data (lane 11, soft only)
     double aA, aB;                            // row products with z
-    double loA, hiA, loB, hiB;
   };
 
-  // loads lam/t, evaluates res_d of the own slots for the replicated iterate zr
-  SMPC_HD void load_slots(int k, const double* zr, Slots& s) {
-    s.pa = hasA(k); s.pb = hasB(k); s.soft = softB();
-    const double* lam = M.lam + (size_t)k * 64;
-    const double* t = M.t + (size_t)k * 64;
-#pragma unroll
-    for (int i = 0; i < NSLOT; ++i) { s.lam[i] = lam[i * 16 + lane]; s.t[i] = t[i * 16 + lane]; s.r[i] = 0.0; }
+  // res_d of the own slots for the replicated iterate zr, given lam/t (and the slack entries) already in `s`
+  SMPC_HD void eval_slots(int k, const double* zr, Slots& s) {
     s.aA = dotA(zr); s.aB = dotB(zr);
-    s.loA = s.hiA = s.loB = s.hiB = 0.0;
-    s.sl = s.su = 0.0;
+#pragma unroll
+    for (int i = 0; i < NSLOT; ++i) s.r[i] = 0.0;
     if (s.soft) {
-      const double* a = M.aux + (size_t)k * 16;
-      s.sl = a[0]; s.su = a[1]; s.lsl = a[2]; s.lsu = a[3]; s.tsl = a[4]; s.tsu = a[5];
       s.rsl = s.tsl - s.sl; s.rsu = s.tsu - s.su;
       s.rgsl = S[SMPC_REC_SOFT] - s.lam[2] - s.lsl;
       s.rgsu = S[SMPC_REC_SOFT] - s.lam[3] - s.lsu;
     }
-    if (s.pa) { boundsA(k, s.loA, s.hiA); s.r[0] = s.t[0] - (s.aA - s.loA); s.r[1] = s.t[1] - (s.hiA - s.aA); }
-    if (s.pb) { boundsB(s.loB, s.hiB); s.r[2] = s.t[2] - (s.aB + s.sl - s.loB); s.r[3] = s.t[3] - (s.hiB - s.aB + s.su); }
+    if (s.pa) { double lo, hi; boundsA(k, lo, hi); s.r[0] = s.t[0] - (s.aA - lo); s.r[1] = s.t[1] - (hi - s.aA); }
+    if (s.pb) { double lo, hi; boundsB(lo, hi); s.r[2] = s.t[2] - (s.aB + s.sl - lo); s.r[3] = s.t[3] - (hi - s.aB + s.su); }
+  }
+  // loads lam/t from the staged block, then eval_slots
+  SMPC_HD void load_slots(int k, const double* zr, Slots& s) {
+    s.pa = hasA(); s.pb = hasB(); s.soft = softB();
+#pragma unroll
+    for (int i = 0; i < NSLOT; ++i) { s.lam[i] = T[O_LAM + i * 16 + lane]; s.t[i] = T[O_T + i * 16 + lane]; }
+    s.sl = s.su = 0.0;
+    if (s.soft) { const double* a = T + O_AUX; s.sl = a[0]; s.su = a[1]; s.lsl = a[2]; s.lsu = a[3]; s.tsl = a[4]; s.tsu = a[5]; }
+    eval_slots(k, zr, s);
   }
 
-  // complementarity right-hand side of slot i:  mode 0 affine, 1 corrector, 2 centering
+  // complementarity right-hand side:  mode 0 affine, 1 corrector, 2 centering
   SMPC_HD double rm_of(int mode, double lam, double t, double prod, double sigmu) const {
     return mode == 0 ? lam * t : (mode == 1 ? lam * t + prod - sigmu : lam * t - sigmu);
   }
 
   // per-row condensation terms (Gamma, gamma) and nu = lam_hi - lam_lo of the own rows
   struct RowT { double GA, gA, nA, GB, gB, nB; };
-  SMPC_HD RowT row_terms(int k, const Slots& s, int mode, double sigmu) {
+  SMPC_HD RowT row_terms(const Slots& s, int mode, double sigmu) {
     RowT o; o.GA = o.gA = o.nA = o.GB = o.gB = o.nB = 0.0;
-    const double* prod = M.prod + (size_t)k * 64;
+    const double* prod = T + O_PROD;     // only dereferenced in corrector mode (then part of the staged range)
     if (s.pa) {
       const double rl = rm_of(mode, s.lam[0], s.t[0], mode == 1 ? prod[0 * 16 + lane] : 0.0, sigmu);
       const double ru = rm_of(mode, s.lam[1], s.t[1], mode == 1 ? prod[1 * 16 + lane] : 0.0, sigmu);
@@ -190,7 +204,7 @@ struct QpSolver {
       double cl = (rl - s.lam[2] * s.r[2]) / s.t[2], cu = (ru - s.lam[3] * s.r[3]) / s.t[3];
       double Gl = s.lam[2] / s.t[2], Gu = s.lam[3] / s.t[3];
       if (s.soft) {
-        const double* a = M.aux + (size_t)k * 16;
+        const double* a = T + O_AUX;
         const double rsl = rm_of(mode, s.lsl, s.tsl, mode == 1 ? a[12] : 0.0, sigmu);
         const double rsu = rm_of(mode, s.lsu, s.tsu, mode == 1 ? a[13] : 0.0, sigmu);
         const double Gsl = s.lsl / s.tsl, Gsu = s.lsu / s.tsu;
@@ -257,12 +271,14 @@ struct QpSolver {
   }
 
   // ------------------------------------------------------------------------------------ S0: cold start
-  SMPC_HD void init(QpResult& R, double mu0, double thr0) {
-    double nb = 0.0, nd = 0.0, nm = 0.0, musum = 0.0;
+  // writes the iterate block (z, pi, pim, lam, t, aux) and a zero step block; counts the constraints
+  SMPC_HD void init(double mu0, double thr0) {
     int cnt = 0;
-    double zxn = 0.0;   // z of stage k+1, own lane
+    int buf = 0;
+    fetch(N, buf, O_Z, 0);
     for (int k = N; k >= 0; --k) {
-      load_rec(k);
+      if (k > 0) fetch(k - 1, buf ^ 1, O_Z, 0);
+      acquire(buf, O_Z);
       // box rows: move the primal inside (lanes 5..14)
       double zc = 0.0, tl = 0.0, tu = 0.0, loA = 0, hiA = 0;
       if (lane >= 5 && lane < 15) {
@@ -275,75 +291,104 @@ struct QpSolver {
       }
       publish(0, zc);
       const double* zr = V;
-      const bool pa = hasA(k), pb = hasB(k), soft = softB();
-      double lam[NSLOT] = {0, 0, 0, 0}, t[NSLOT] = {0, 0, 0, 0};
+      const bool pa = hasA(), pb = hasB(), soft = softB();
+      double t[NSLOT] = {0, 0, 0, 0};
       if (lane < 5 && pa) {
         boundsA(k, loA, hiA);
         const double v = dotA(zr);
         tl = fmax(thr0, v - loA); tu = fmax(thr0, hiA - v);
       }
       if (pa) { t[0] = tl; t[1] = tu; }
-      double rdB0 = 0.0, rdB1 = 0.0;
       if (pb) {
         double lo, hi; boundsB(lo, hi);
         const double v = dotB(zr);
         t[2] = fmax(thr0, v - lo); t[3] = fmax(thr0, hi - v);
-        const double sl = soft ? thr0 : 0.0;
-        rdB0 = t[2] - (v + sl - lo); rdB1 = t[3] - (hi - v + sl);
       }
-      double rdA0 = 0.0, rdA1 = 0.0;
-      if (pa) { const double v = dotA(zr); rdA0 = t[0] - (v - loA); rdA1 = t[1] - (hiA - v); }
+      double* g = gst(k);
 #pragma unroll
       for (int i = 0; i < NSLOT; ++i) {
         const bool p = i < 2 ? pa : pb;
-        lam[i] = p ? mu0 / t[i] : 0.0;
-        M.lam[(size_t)k * 64 + i * 16 + lane] = lam[i];
-        M.t[(size_t)k * 64 + i * 16 + lane] = t[i];
-        if (p) { ++cnt; musum += lam[i] * t[i]; nm = fmax(nm, fabs(lam[i] * t[i])); }
+        g[O_LAM + i * 16 + lane] = p ? mu0 / t[i] : 0.0;
+        g[O_T + i * 16 + lane] = t[i];
+        g[O_DLAM + i * 16 + lane] = 0.0;
+        g[O_DTT + i * 16 + lane] = 0.0;
+        if (p) ++cnt;
       }
-      nd = fmax(nd, fmax(fmax(fabs(rdA0), fabs(rdA1)), fmax(fabs(rdB0), fabs(rdB1))));
-      if (lane == 11) {
-        double* a = M.aux + (size_t)k * 16;
-        for (int i = 0; i < 16; ++i) a[i] = 0.0;
-        if (soft) {
-          a[0] = a[1] = thr0; a[4] = a[5] = thr0; a[2] = a[3] = mu0 / thr0;
-          cnt += 2; musum += 2.0 * mu0; nm = fmax(nm, mu0);
-        }
-      }
-      M.z[(size_t)k * 16 + lane] = zc;
-      M.pi[(size_t)k * 16 + lane] = 0.0;
-      // res_b_k = A zx_k + B zu_k + b_k - zx_{k+1}   (zu = 0)
-      if (k < N && lane >= 5 && lane < 15) {
-        const int i = lane - 5;
-        const double y = i < 5 ? zr[5 + i] + dt * zr[10 + i] : zr[5 + i];
-        nb = fmax(nb, fabs(y + S[SMPC_REC_B + i] - zxn));
-      }
-      zxn = zc;
+      double av = 0.0;
+      if (soft) { av = (lane == 0 || lane == 1 || lane == 4 || lane == 5) ? thr0 : ((lane == 2 || lane == 3) ? mu0 / thr0 : 0.0); }
+      // aux is indexed by field, not by lane: lane i writes field i (soft flag is a lane-11 property -> broadcast it)
+      const bool stage_soft = ln.shfl(soft ? 1.0 : 0.0, 11) > 0.5;
+      av = stage_soft ? ((lane == 0 || lane == 1 || lane == 4 || lane == 5) ? thr0 : ((lane == 2 || lane == 3) ? mu0 / thr0 : 0.0)) : 0.0;
+      g[O_AUX + lane] = av;
+      if (stage_soft && lane == 11) cnt += 2;
+      g[O_Z + lane] = zc; g[O_PI + lane] = 0.0; g[O_PIM + lane] = 0.0;
+      g[O_DZ + lane] = 0.0; g[O_DPI + lane] = 0.0; g[O_DPIM + lane] = 0.0;
+      ln.sync();
+      buf ^= 1;
     }
     nc = (int)(gsum((double)cnt) + 0.5);
-    R.res[1] = gmax_nan(nb); R.res[2] = gmax_nan(nd); R.res[3] = gmax_nan(nm);
-    R.mu = gsum(musum) / nc;
-    R.res[0] = 0.0;
+    ln.flush();
   }
 
-  // -------------------------------------------------------------- S1: factorisation + affine gradient
-  // returns the max-norm of the stationarity residual; leaves dx_0 (affine) replicated at V[64..74)
-  SMPC_HD double factorize(double reg) {
-    double ng = 0.0;
+  // ------------------------------------------------- S1: (update of the previous step) + factorisation + affine gradient
+  // Applies  w <- w + a*dw  (a = 0 right after init), evaluates all residual norms and mu of the new iterate, factorises.
+  // Leaves dx_0 (affine) replicated at V[64+5 .. 64+15).
+  SMPC_HD void update_factorize(double a, double lam_min, double t_min, double reg, QpResult& R) {
+    double ng = 0.0, nb = 0.0, nd = 0.0, nm = 0.0, musum = 0.0;
     double pp[10];            // column (lane-5) of P_{k+1}   (lanes 5..14)
     double pcur = 0.0;        // p_{k+1}[lane-5]
     double zxn[10];           // z_x of stage k+1, replicated
 #pragma unroll
     for (int i = 0; i < 10; ++i) { pp[i] = 0.0; zxn[i] = 0.0; }
+    int buf = 0;
+    fetch(N, buf, 0, O_PROD);
     for (int k = N; k >= 0; --k) {
-      load_rec(k);
-      publish(0, M.z[(size_t)k * 16 + lane]);                 // V[0..15) = z_k
+      if (k > 0) fetch(k - 1, buf ^ 1, 0, O_PROD);
+      acquire(buf, 0);
+      double* g = gst(k);
+      // ---- primal-dual update of this stage ----
+      const double znew = T[O_Z + lane] + a * T[O_DZ + lane];
+      const double pinew = T[O_PI + lane] + a * T[O_DPI + lane];
+      const double pimnew = T[O_PIM + lane] + a * T[O_DPIM + lane];
+      g[O_Z + lane] = znew; g[O_PI + lane] = pinew; g[O_PIM + lane] = pimnew;
+      publish(0, znew);                                        // V[0..15) = z_k
       double zr[15];
 #pragma unroll
       for (int i = 0; i < 15; ++i) zr[i] = V[i];
       Slots s;
-      load_slots(k, zr, s);
-      const RowT rt = row_terms(k, s, 0, 0.0);
+      s.pa = hasA(); s.pb = hasB(); s.soft = softB();
+#pragma unroll
+      for (int i = 0; i < NSLOT; ++i) {
+        const bool p = i < 2 ? s.pa : s.pb;
+        s.lam[i] = 0.0; s.t[i] = 0.0;
+        if (p) {
+          s.lam[i] = fmax(T[O_LAM + i * 16 + lane] + a * T[O_DLAM + i * 16 + lane], lam_min);
+          s.t[i] = fmax(T[O_T + i * 16 + lane] + a * T[O_DTT + i * 16 + lane], t_min);
+          g[O_LAM + i * 16 + lane] = s.lam[i]; g[O_T + i * 16 + lane] = s.t[i];
+          const double c = s.lam[i] * s.t[i];
+          musum += c;
+          nm = (c != c) ? c : fmax(nm, fabs(c));
+        }
+      }
+      s.sl = s.su = 0.0;
+      if (s.soft) {
+        const double* aw = T + O_AUX;
+        s.sl = aw[0] + a * aw[6]; s.su = aw[1] + a * aw[7];
+        s.lsl = fmax(aw[2] + a * aw[8], lam_min); s.lsu = fmax(aw[3] + a * aw[9], lam_min);
+        s.tsl = fmax(aw[4] + a * aw[10], t_min); s.tsu = fmax(aw[5] + a * aw[11], t_min);
+        g[O_AUX + 0] = s.sl; g[O_AUX + 1] = s.su; g[O_AUX + 2] = s.lsl; g[O_AUX + 3] = s.lsu; g[O_AUX + 4] = s.tsl; g[O_AUX + 5] = s.tsu;
+        musum += s.lsl * s.tsl + s.lsu * s.tsu;
+        nm = fmax(nm, fmax(fabs(s.lsl * s.tsl), fabs(s.lsu * s.tsu)));
+        nd = fmax(nd, fmax(fabs(s.tsl - s.sl), fabs(s.tsu - s.su)));
+      }
+      eval_slots(k, zr, s);
+      {
+        const double rd = fmax(fmax(fabs(s.r[0]), fabs(s.r[1])), fmax(fabs(s.r[2]), fabs(s.r[3])));
+        const double chk = s.r[0] + s.r[1] + s.r[2] + s.r[3];
+        nd = (chk != chk) ? chk : fmax(nd, rd);
+      }
+      // ---- condensation terms (affine rhs: rm = lam * t) ----
+      const RowT rt = row_terms(s, 0, 0.0);
       publish_rows(16, s.pa, rt.GA, s.pb, rt.GB);              // V[16..38) Gamma
       const double GamBox = (lane >= 5 && lane < 15) ? rt.GA : 0.0;
       // ---- column of the condensed matrix ----
@@ -354,33 +399,33 @@ struct QpSolver {
       else if (lane < 10) {
         const int i = lane - 5;
 #pragma unroll
-        for (int j = 0; j < 5; ++j) { const int a = i > j ? i : j, b = i > j ? j : i; m[5 + j] = S[SMPC_REC_HQQ + a * (a + 1) / 2 + b]; }
+        for (int j = 0; j < 5; ++j) { const int aa = i > j ? i : j, bb = i > j ? j : i; m[5 + j] = S[SMPC_REC_HQQ + aa * (aa + 1) / 2 + bb]; }
         m[lane] += S[SMPC_REC_HQ] + reg + GamBox;
       } else if (lane < 15) { m[lane] = S[SMPC_REC_HV] + reg + GamBox; }
       if (lane < 15) {
         if (S[SMPC_REC_NTAU] > 0.5) {
 #pragma unroll
           for (int r = 0; r < 5; ++r) {
-            const double* a = S + SMPC_REC_JTAU + r * 15;
-            const double coef = V[16 + 10 + r] * a[lane];
+            const double* ar = S + SMPC_REC_JTAU + r * 15;
+            const double coef = V[16 + 10 + r] * ar[lane];
 #pragma unroll
-            for (int i = 0; i < 15; ++i) m[i] += coef * a[i];
+            for (int i = 0; i < 15; ++i) m[i] += coef * ar[i];
           }
         }
         if (lane >= 5 && lane < 10 && S[SMPC_REC_NDIST] > 0.5) {
 #pragma unroll
           for (int p = 0; p < 6; ++p) {
-            const double* a = S + SMPC_REC_JDIST + p * 5;
-            const double coef = V[16 + 15 + p] * a[lane - 5];
+            const double* ar = S + SMPC_REC_JDIST + p * 5;
+            const double coef = V[16 + 15 + p] * ar[lane - 5];
 #pragma unroll
-            for (int i = 0; i < 5; ++i) m[5 + i] += coef * a[i];
+            for (int i = 0; i < 5; ++i) m[5 + i] += coef * ar[i];
           }
         }
         if (lane >= 5 && S[SMPC_REC_NNROW] > 0.5) {
-          const double* a = S + SMPC_REC_JNN;
-          const double coef = V[16 + 21] * a[lane - 5];
+          const double* ar = S + SMPC_REC_JNN;
+          const double coef = V[16 + 21] * ar[lane - 5];
 #pragma unroll
-          for (int i = 0; i < 10; ++i) m[5 + i] += coef * a[i];
+          for (int i = 0; i < 10; ++i) m[5 + i] += coef * ar[i];
         }
       }
       // ---- stationarity residual and affine gradient ----
@@ -388,15 +433,14 @@ struct QpSolver {
       double rg = cost_grad(k, zr) + rowsT(40);
       publish_rows(40, s.pa, rt.gA, s.pb, rt.gB);              // V[40..62) gamma
       double gv = rowsT(40);
-      // dynamics terms
       if (k < N) {
-        publish(64, M.pi[(size_t)k * 16 + lane]);              // V[64+5 .. 64+15) = pi_k
+        publish(64, pinew);                                    // V[64+5 .. 64+15) = pi_k
         rg += dynT(V + 64 + 5);
       }
-      if (k > 0) { if (lane >= 5 && lane < 15) rg -= M.pi[(size_t)(k - 1) * 16 + lane]; }
+      if (k > 0 && lane >= 5 && lane < 15) rg -= pimnew;
       if (k == N && lane < 5) rg = 0.0;
       ng = (rg != rg) ? rg : fmax(ng, fabs(rg));
-      M.gb[(size_t)k * 16 + lane] = rg;
+      g[O_GB + lane] = rg;
       gv += rg;
       if (k < N) {
         // res_b_k (replicated) and w = P_{k+1} res_b_k
@@ -410,9 +454,15 @@ struct QpSolver {
         if (lane >= 5 && lane < 15) {
 #pragma unroll
           for (int r = 0; r < 10; ++r) w += pp[r] * rb[r];
-          M.rb[(size_t)k * 16 + lane] = rb[lane - 5];
-          M.wv[(size_t)k * 16 + lane] = w;
+          const double mine = rb[0];   // placeholder, replaced below
+          (void)mine;
         }
+        double rbl = 0.0;
+#pragma unroll
+        for (int i = 0; i < 10; ++i) if (i == lane - 5) rbl = rb[i];
+        if (lane >= 5 && lane < 15) { nb = (rbl != rbl) ? rbl : fmax(nb, fabs(rbl)); }
+        g[O_RB + lane] = rbl;
+        g[O_WV + lane] = w;
         publish(80, w + pcur);                                 // V[80+5..80+15) = P rb + p_{k+1}
         gv += dynT(V + 80 + 5);
         // M += [B A]' P_{k+1} [B A]
@@ -472,24 +522,31 @@ struct QpSolver {
       }
       // ---- store the factor ----
 #pragma unroll
-      for (int j = 0; j < 5; ++j) M.fac[((size_t)k * 5 + j) * 16 + lane] = lrow[j];
-      M.pv[(size_t)k * 16 + lane] = m[15];
+      for (int j = 0; j < 5; ++j) g[O_FAC + j * 16 + lane] = lrow[j];
+      g[O_PV + lane] = m[15];
       if (k > 0) {
         if (lane >= 5 && lane < 15) {
 #pragma unroll
-          for (int r = 0; r < 10; ++r) { pp[r] = m[5 + r]; M.Pm[((size_t)k * 10 + r) * 16 + lane] = pp[r]; }
+          for (int r = 0; r < 10; ++r) pp[r] = m[5 + r];
           pcur = m[15];
         }
+#pragma unroll
+        for (int r = 0; r < 10; ++r) g[O_PM + r * 16 + lane] = (lane >= 5 && lane < 15) ? m[5 + r] : 0.0;
 #pragma unroll
         for (int i = 0; i < 10; ++i) zxn[i] = zr[5 + i];
       } else {
         // stage 0: keep the state factor (columns and rows) and solve for dx_0
+        double* L0 = M.st + (size_t)(N + 1) * QP_ST;
 #pragma unroll
-        for (int r = 0; r < 10; ++r) { M.L0[(size_t)r * 16 + lane] = m[5 + r]; M.L0[(size_t)(10 + r) * 16 + lane] = l0row[r]; }
+        for (int r = 0; r < 10; ++r) { L0[r * 16 + lane] = m[5 + r]; L0[(10 + r) * 16 + lane] = l0row[r]; }
         solve_dx0(m, m[15]);
       }
+      ln.sync();
+      buf ^= 1;
     }
-    return gmax_nan(ng);
+    R.res[0] = gmax_nan(ng); R.res[1] = gmax_nan(nb); R.res[2] = gmax_nan(nd); R.res[3] = gmax_nan(nm);
+    R.mu = gsum(musum) / nc;
+    ln.flush();
   }
 
   // back substitution with the stage-0 state factor held column-wise in mcol[5..15): dx_0 -> V[64+5 .. 64+15), replicated
@@ -497,11 +554,10 @@ struct QpSolver {
     double acc = -lx;
     double mine = 0.0;
     for (int r = 14; r >= 5; --r) {
-      double dr = 0.0, lrr = 0.0, lrc = 0.0;
+      double dr = 0.0, lrc = 0.0;
 #pragma unroll
       for (int i = 5; i < 15; ++i) if (i == r) lrc = mcol[i];     // L0[r][lane] (valid for r >= lane)
-      lrr = lrc;
-      if (lane == r) dr = lrr > 0.0 ? acc / lrr : 0.0;
+      if (lane == r) dr = lrc > 0.0 ? acc / lrc : 0.0;
       dr = ln.shfl(dr, r);
       if (lane == r) mine = dr;
       if (lane >= 5 && lane < r) acc -= lrc * dr;
@@ -512,19 +568,24 @@ struct QpSolver {
   // ------------------------------------------------- S3: vector-only backward recursion (corrector / centering)
   SMPC_HD void resolve_backward(int mode, double sigmu) {
     double pcur = 0.0;
+    int buf = 0;
+    const int cnt = O_PM - O_Z;
+    fetch(N, buf, O_Z, cnt);
     for (int k = N; k >= 0; --k) {
-      load_rec(k);
-      publish(0, M.z[(size_t)k * 16 + lane]);
+      if (k > 0) fetch(k - 1, buf ^ 1, O_Z, cnt);
+      acquire(buf, O_Z);
+      double* g = gst(k);
+      publish(0, T[O_Z + lane]);
       double zr[15];
 #pragma unroll
       for (int i = 0; i < 15; ++i) zr[i] = V[i];
       Slots s;
       load_slots(k, zr, s);
-      const RowT rt = row_terms(k, s, mode, sigmu);
+      const RowT rt = row_terms(s, mode, sigmu);
       publish_rows(40, s.pa, rt.gA, s.pb, rt.gB);
-      double gv = M.gb[(size_t)k * 16 + lane] + rowsT(40);
+      double gv = T[O_GB + lane] + rowsT(40);
       if (k < N) {
-        const double w = (lane >= 5 && lane < 15) ? M.wv[(size_t)k * 16 + lane] : 0.0;
+        const double w = (lane >= 5 && lane < 15) ? T[O_WV + lane] : 0.0;
         publish(80, w + pcur);
         gv += dynT(V + 80 + 5);
       }
@@ -533,7 +594,7 @@ struct QpSolver {
       // forward elimination with the stored rows of [Lr; Ls]
       double lrow[5];
 #pragma unroll
-      for (int j = 0; j < 5; ++j) lrow[j] = M.fac[((size_t)k * 5 + j) * 16 + lane];
+      for (int j = 0; j < 5; ++j) lrow[j] = T[O_FAC + j * 16 + lane];
 #pragma unroll
       for (int j = 0; j < 5; ++j) {
         double lj = 0.0;
@@ -541,13 +602,14 @@ struct QpSolver {
         lj = ln.shfl(lj, j);
         if (lane > j && lane < 15) gv -= lrow[j] * lj;
       }
-      M.pv[(size_t)k * 16 + lane] = gv;
+      g[O_PV + lane] = gv;
       if (k > 0) { pcur = (lane >= 5 && lane < 15) ? gv : 0.0; }
       else {
         // stage 0: forward then backward substitution with the state factor
+        const double* L0 = M.st + (size_t)(N + 1) * QP_ST;
         double l0row[10], mcol[16];
 #pragma unroll
-        for (int r = 0; r < 10; ++r) { mcol[5 + r] = M.L0[(size_t)r * 16 + lane]; l0row[r] = M.L0[(size_t)(10 + r) * 16 + lane]; }
+        for (int r = 0; r < 10; ++r) { mcol[5 + r] = L0[r * 16 + lane]; l0row[r] = L0[(10 + r) * 16 + lane]; }
 #pragma unroll
         for (int i = 0; i < 5; ++i) mcol[i] = 0.0;
         mcol[15] = 0.0;
@@ -561,32 +623,58 @@ struct QpSolver {
         }
         solve_dx0(mcol, gv);
       }
+      ln.sync();
+      buf ^= 1;
     }
+    ln.flush();
   }
 
   // ------------------------------------------------------------------------- S2 / S4: forward substitution
   struct StepStats { double alpha, s_lin, s_quad; };
-  // mode: complementarity rhs as in rm_of; store_prod: keep dlam*dt (affine pass); final: store dlam, dt, dpi
+  // mode: complementarity rhs as in rm_of; store_prod: keep dlam*dt (affine pass); final: store the step (dz, dpi, dlam, dt)
   SMPC_HD StepStats forward(int mode, double sigmu, bool store_prod, bool final) {
     double alpha = 1.0, s_lin = 0.0, s_quad = 0.0;
     double dx[10];
 #pragma unroll
     for (int i = 0; i < 10; ++i) dx[i] = V[64 + 5 + i];
     ln.sync();
+    int buf = 0;
+    const int cnt = (final ? QP_ST : O_PM) - O_Z;
+    fetch(0, buf, O_Z, cnt);
     for (int k = 0; k <= N; ++k) {
-      load_rec(k);
+      if (k < N) fetch(k + 1, buf ^ 1, O_Z, cnt);
+      acquire(buf, O_Z);
+      double* g = gst(k);
+      // multiplier step of the dynamics k-1 -> k:  dpi_{k-1} = P_k dx_k + p_k   (stored with both stages)
+      if (final && k > 0) {
+        double dp = 0.0;
+        if (lane >= 5 && lane < 15) {
+          dp = T[O_PV + lane];
+#pragma unroll
+          for (int r = 0; r < 10; ++r) dp += T[O_PM + r * 16 + lane] * dx[r];
+        }
+        g[O_DPIM + lane] = dp;
+        gst(k - 1)[O_DPI + lane] = dp;
+      }
+      if (final && k == 0) g[O_DPIM + lane] = 0.0;
+      if (final && k == N) g[O_DPI + lane] = 0.0;
       // ---- du_k ----
       double du[5] = {0, 0, 0, 0, 0};
-      double lrow[5];
-#pragma unroll
-      for (int j = 0; j < 5; ++j) lrow[j] = M.fac[((size_t)k * 5 + j) * 16 + lane];
       if (k < N) {
-        const double lp = M.pv[(size_t)k * 16 + lane];
+        double lrow[5];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) lrow[j] = T[O_FAC + j * 16 + lane];
+        const double lp = T[O_PV + lane];
         double sj[5];
 #pragma unroll
         for (int j = 0; j < 5; ++j) {
           double term = 0.0;
-          if (lane >= 5 && lane < 15) term = lrow[j] * dx[lane - 5];
+          if (lane >= 5 && lane < 15) {
+            double dxl = 0.0;
+#pragma unroll
+            for (int i = 0; i < 10; ++i) if (i == lane - 5) dxl = dx[i];
+            term = lrow[j] * dxl;
+          }
           if (lane == j) term = lp;
           sj[j] = gsum(term);
         }
@@ -618,22 +706,22 @@ struct QpSolver {
 #pragma unroll
       for (int i = 0; i < 15; ++i) if (i == lane) mydz = dzr[i];
       // ---- own slots ----
-      publish(0, M.z[(size_t)k * 16 + lane]);
+      publish(0, T[O_Z + lane]);
       double zr[15];
 #pragma unroll
       for (int i = 0; i < 15; ++i) zr[i] = V[i];
       Slots s;
       load_slots(k, zr, s);
       const double adA = dotA(dzr), adB = dotB(dzr);
-      const double* prod = M.prod + (size_t)k * 64;
+      const double* prod = T + O_PROD;
       double dlam[NSLOT] = {0, 0, 0, 0}, dtt[NSLOT] = {0, 0, 0, 0};
       double dsl = 0.0, dsu = 0.0;
       if (s.soft) {
-        const double* a = M.aux + (size_t)k * 16;
+        const double* aw = T + O_AUX;
         const double rl = rm_of(mode, s.lam[2], s.t[2], mode == 1 ? prod[2 * 16 + lane] : 0.0, sigmu);
         const double ru = rm_of(mode, s.lam[3], s.t[3], mode == 1 ? prod[3 * 16 + lane] : 0.0, sigmu);
-        const double rsl = rm_of(mode, s.lsl, s.tsl, mode == 1 ? a[12] : 0.0, sigmu);
-        const double rsu = rm_of(mode, s.lsu, s.tsu, mode == 1 ? a[13] : 0.0, sigmu);
+        const double rsl = rm_of(mode, s.lsl, s.tsl, mode == 1 ? aw[12] : 0.0, sigmu);
+        const double rsu = rm_of(mode, s.lsu, s.tsu, mode == 1 ? aw[13] : 0.0, sigmu);
         const double Gl = s.lam[2] / s.t[2], Gu = s.lam[3] / s.t[3], Gsl = s.lsl / s.tsl, Gsu = s.lsu / s.tsu;
         const double cl = (rl - s.lam[2] * s.r[2]) / s.t[2], cu = (ru - s.lam[3] * s.r[3]) / s.t[3];
         const double csl = (rsl - s.lsl * s.rsl) / s.tsl, csu = (rsu - s.lsu * s.rsu) / s.tsu;
@@ -647,9 +735,8 @@ struct QpSolver {
         if (dtsu < 0.0) alpha = fmin(alpha, -s.tsu / dtsu);
         s_lin += s.lsl * dtsl + s.tsl * dlsl + s.lsu * dtsu + s.tsu * dlsu;
         s_quad += dlsl * dtsl + dlsu * dtsu;
-        double* aw = M.aux + (size_t)k * 16;
-        if (store_prod) { aw[12] = dlsl * dtsl; aw[13] = dlsu * dtsu; }
-        if (final) { aw[6] = dsl; aw[7] = dsu; aw[8] = dlsl; aw[9] = dlsu; aw[10] = dtsl; aw[11] = dtsu; }
+        if (store_prod) { g[O_AUX + 12] = dlsl * dtsl; g[O_AUX + 13] = dlsu * dtsu; }
+        if (final) { g[O_AUX + 6] = dsl; g[O_AUX + 7] = dsu; g[O_AUX + 8] = dlsl; g[O_AUX + 9] = dlsu; g[O_AUX + 10] = dtsl; g[O_AUX + 11] = dtsu; }
       }
       if (s.pa) { dtt[0] = adA - s.r[0]; dtt[1] = -adA - s.r[1]; }
       if (s.pb) { dtt[2] = adB + dsl - s.r[2]; dtt[3] = -adB + dsu - s.r[3]; }
@@ -667,105 +754,33 @@ struct QpSolver {
       }
       if (store_prod) {
 #pragma unroll
-        for (int i = 0; i < NSLOT; ++i) M.prod[(size_t)k * 64 + i * 16 + lane] = dlam[i] * dtt[i];
+        for (int i = 0; i < NSLOT; ++i) g[O_PROD + i * 16 + lane] = dlam[i] * dtt[i];
       }
       if (final) {
 #pragma unroll
-        for (int i = 0; i < NSLOT; ++i) { M.dlam[(size_t)k * 64 + i * 16 + lane] = dlam[i]; M.dtt[(size_t)k * 64 + i * 16 + lane] = dtt[i]; }
-        M.dz[(size_t)k * 16 + lane] = mydz;
+        for (int i = 0; i < NSLOT; ++i) { g[O_DLAM + i * 16 + lane] = dlam[i]; g[O_DTT + i * 16 + lane] = dtt[i]; }
+        g[O_DZ + lane] = mydz;
       }
       // ---- next state ----
       if (k < N) {
         double dxn[10];
-        ln.sync();
-        V[80 + lane] = M.rb[(size_t)k * 16 + lane];
-        ln.sync();
 #pragma unroll
         for (int i = 0; i < 5; ++i) {
-          dxn[i] = dx[i] + dt * dx[5 + i] + hdt2 * du[i] + V[80 + 5 + i];
-          dxn[5 + i] = dx[5 + i] + dt * du[i] + V[80 + 10 + i];
-        }
-        if (final) {
-          double dp = 0.0;
-          if (lane >= 5 && lane < 15) {
-            dp = M.pv[(size_t)(k + 1) * 16 + lane];
-#pragma unroll
-            for (int r = 0; r < 10; ++r) dp += M.Pm[((size_t)(k + 1) * 10 + r) * 16 + lane] * dxn[r];
-          }
-          M.dpi[(size_t)k * 16 + lane] = dp;
+          dxn[i] = dx[i] + dt * dx[5 + i] + hdt2 * du[i] + T[O_RB + 5 + i];
+          dxn[5 + i] = dx[5 + i] + dt * du[i] + T[O_RB + 10 + i];
         }
 #pragma unroll
         for (int i = 0; i < 10; ++i) dx[i] = dxn[i];
       }
+      ln.sync();
+      buf ^= 1;
     }
     StepStats o;
     o.alpha = gmin(alpha);
     o.s_lin = gsum(s_lin);
     o.s_quad = gsum(s_quad);
+    ln.flush();
     return o;
-  }
-
-  // --------------------------------------------------------------------------------------- S5: update
-  SMPC_HD void update(double a, double lam_min, double t_min, QpResult& R) {
-    double nb = 0.0, nd = 0.0, nm = 0.0, musum = 0.0;
-    double zprev[15];   // updated z of stage k-1 (replicated)
-#pragma unroll
-    for (int i = 0; i < 15; ++i) zprev[i] = 0.0;
-    double bprev = 0.0;  // b_{k-1}[lane-5]
-    for (int k = 0; k <= N; ++k) {
-      load_rec(k);
-      const double znew = M.z[(size_t)k * 16 + lane] + a * M.dz[(size_t)k * 16 + lane];
-      M.z[(size_t)k * 16 + lane] = znew;
-      if (k < N) M.pi[(size_t)k * 16 + lane] += a * M.dpi[(size_t)k * 16 + lane];
-      publish(0, znew);
-      double zr[15];
-#pragma unroll
-      for (int i = 0; i < 15; ++i) zr[i] = V[i];
-      // res_b_{k-1}
-      if (k > 0 && lane >= 5 && lane < 15) {
-        const int i = lane - 5;
-        const double y = i < 5 ? zprev[5 + i] + dt * zprev[10 + i] + hdt2 * zprev[i] : zprev[5 + i] + dt * zprev[i - 5];
-        const double rbv = y + bprev - znew;
-        nb = (rbv != rbv) ? rbv : fmax(nb, fabs(rbv));
-      }
-      bprev = (lane >= 5 && lane < 15) ? S[SMPC_REC_B + lane - 5] : 0.0;
-#pragma unroll
-      for (int i = 0; i < 15; ++i) zprev[i] = zr[i];
-      // slots
-      const bool pa = hasA(k), pb = hasB(k), soft = softB();
-      double sl = 0.0, su = 0.0;
-      if (soft) {
-        double* aw = M.aux + (size_t)k * 16;
-        sl = aw[0] + a * aw[6]; su = aw[1] + a * aw[7];
-        const double lsl = fmax(aw[2] + a * aw[8], lam_min), lsu = fmax(aw[3] + a * aw[9], lam_min);
-        const double tsl = fmax(aw[4] + a * aw[10], t_min), tsu = fmax(aw[5] + a * aw[11], t_min);
-        aw[0] = sl; aw[1] = su; aw[2] = lsl; aw[3] = lsu; aw[4] = tsl; aw[5] = tsu;
-        musum += lsl * tsl + lsu * tsu;
-        nm = fmax(nm, fmax(fabs(lsl * tsl), fabs(lsu * tsu)));
-        nd = fmax(nd, fmax(fabs(tsl - sl), fabs(tsu - su)));
-      }
-      double lam[NSLOT], t[NSLOT];
-#pragma unroll
-      for (int i = 0; i < NSLOT; ++i) {
-        const bool p = i < 2 ? pa : pb;
-        const size_t o = (size_t)k * 64 + i * 16 + lane;
-        lam[i] = 0.0; t[i] = 0.0;
-        if (p) {
-          lam[i] = fmax(M.lam[o] + a * M.dlam[o], lam_min);
-          t[i] = fmax(M.t[o] + a * M.dtt[o], t_min);
-          M.lam[o] = lam[i]; M.t[o] = t[i];
-          const double c = lam[i] * t[i];
-          musum += c;
-          nm = (c != c) ? c : fmax(nm, fabs(c));
-        }
-      }
-      double rd = 0.0;
-      if (pa) { double lo, hi; boundsA(k, lo, hi); const double v = dotA(zr); rd = fmax(fabs(t[0] - (v - lo)), fabs(t[1] - (hi - v))); }
-      if (pb) { double lo, hi; boundsB(lo, hi); const double v = dotB(zr); rd = fmax(rd, fmax(fabs(t[2] - (v + sl - lo)), fabs(t[3] - (hi - v + su)))); }
-      nd = (rd != rd) ? rd : fmax(nd, rd);
-    }
-    R.res[1] = gmax_nan(nb); R.res[2] = gmax_nan(nd); R.res[3] = gmax_nan(nm);
-    R.mu = gsum(musum) / nc;
   }
 
   // --------------------------------------------------------------------------------------- driver
@@ -773,12 +788,13 @@ struct QpSolver {
     QpResult R;
     R.iter = 0; R.status = 0;
     const double thr0 = 1e-1, lam_min = 1e-16, t_min = 1e-16;
-    init(R, P.qp_mu0, thr0);
+    init(P.qp_mu0, thr0);
     double alpha = 1.0;
+    double step = 0.0;      // step length still to be applied to the stored direction
     int kk = 0;
     bool nan = false;
     for (;; ++kk) {
-      R.res[0] = factorize(P.qp_reg_prim);
+      update_factorize(step, lam_min, t_min, P.qp_reg_prim, R);
       nan = (R.res[0] != R.res[0]) || (R.res[1] != R.res[1]) || (R.res[2] != R.res[2]) || (R.res[3] != R.res[3]);
       if (nan && kk > 0) break;
       const bool unconv = (R.res[0] > P.qp_tol_stat) || (R.res[1] > P.qp_tol_eq) || (R.res[2] > P.qp_tol_ineq) || (R.res[3] > P.qp_tol_comp);
@@ -802,7 +818,7 @@ struct QpSolver {
           alpha = cor.alpha;
         }
       }
-      update(0.995 * alpha, lam_min, t_min, R);
+      step = 0.995 * alpha;
     }
     R.iter = kk;
     const bool unconv = (R.res[0] > P.qp_tol_stat) || (R.res[1] > P.qp_tol_eq) || (R.res[2] > P.qp_tol_ineq) || (R.res[3] > P.qp_tol_comp);

@@ -216,12 +216,13 @@ int smpc_create(const smpc_problem_t* prob, int32_t batch, int32_t device, smpc_
   }
   const size_t nx = (size_t)B * (N + 1) * NX, nu = (size_t)B * N * NU, nst = (size_t)B * (N + 1);
   CKC(dalloc(h, &h->xg, nx)); CKC(dalloc(h, &h->ug, nu)); CKC(dalloc(h, &h->xt, nx)); CKC(dalloc(h, &h->ut, nu));
-  CKC(dalloc(h, &h->lin, nst * REC));
+  const size_t Bt = ((size_t)(B + 31) / 32) * 32;   // tiles of 32 problems
+  CKC(dalloc(h, &h->lin, Bt * (N + 1) * REC));
   CKC(dalloc(h, &h->plant_inertial, (size_t)B * NQ * 10)); CKC(dalloc(h, &h->tau_noise, (size_t)B * NU));
   CKC(dalloc(h, &h->x_viable, (size_t)B * NX));
   CKC(dalloc(h, &h->nn11, nst * NN_OUT));
   if (prob->controller == SMPC_CTRL_RECEDING || prob->controller == SMPC_CTRL_REAL_RECEDING) CKC(dalloc(h, &h->scan11, nst * NN_OUT));
-  CKC(dalloc(h, &h->qpbuf, (size_t)B * qp_stride_doubles(N)));
+  CKC(dalloc(h, &h->qpbuf, Bt * qp_stride_doubles(N)));
   CKC(dalloc(h, &h->qp_res, (size_t)B * 5));
   CKC(dalloc(h, &h->x_in, (size_t)B * NX)); CKC(dalloc(h, &h->u_out, (size_t)B * NU));
   CKC(dalloc(h, &h->fails, (size_t)B)); CKC(dalloc(h, &h->r, (size_t)B)); CKC(dalloc(h, &h->status, (size_t)B));
@@ -384,7 +385,14 @@ int smpc_nn_constraint(smpc_handle_t* h, int32_t n, const double* x, double* cva
   return copy_out(h, grad, dg, sizeof(double) * n * NX, mem);
 }
 
-int smpc_get_lin(smpc_handle_t* h, double* lin, int32_t mem) { return copy_out(h, lin, h->lin, sizeof(double) * h->B * (h->N + 1) * REC, mem); }
+int smpc_get_lin(smpc_handle_t* h, double* lin, int32_t mem) {
+  const size_t bytes = sizeof(double) * h->B * (h->N + 1) * REC;
+  if (mem == SMPC_DEVICE) { launch_dump_lin(h->ctx(), h->B, h->N, h->lin, lin); return check_launch(h, "get_lin"); }
+  int rc = stage_reserve(h, bytes); if (rc) return rc;
+  launch_dump_lin(h->ctx(), h->B, h->N, h->lin, (double*)h->stage);
+  rc = check_launch(h, "get_lin"); if (rc) return rc;
+  return copy_out(h, lin, h->stage, bytes, mem);
+}
 
 int smpc_get_qp(smpc_handle_t* h, double* dz, double* pi, double* lam, double* t, int32_t mem) {
   const size_t nst = (size_t)h->B * (h->N + 1);

@@ -326,18 +326,19 @@ SMPC_HD bool collision_free(const smpc_problem_t& P, const double* x) {         
   return ok;
 }
 
-// one stage of the linearisation -> stage record (viability row value/gradient are supplied by the MLP kernel)
+// one stage of the linearisation -> stage record (viability row value/gradient are supplied by the MLP kernel);
+// `rs` = stride between consecutive record fields (32 in the device layout [tile][stage][field][32 problems])
 SMPC_HD void linearize_stage(const smpc_problem_t& P, int k, const double* x, const double* u, const double* xnext,
-                             bool has_nn, bool gate_on, const double* nn11, double* rec) {
+                             bool has_nn, bool gate_on, const double* nn11, double* rec, int rs = 1) {
   const int N = P.N;
   const bool term = (k == N);
   const double s = term ? 1.0 : P.dt;
-  for (int i = 0; i < REC; ++i) rec[i] = 0.0;
+  for (int i = 0; i < REC; ++i) rec[(size_t)rs * (i)] = 0.0;
 #pragma unroll
-  for (int i = 0; i < NX; ++i) rec[SMPC_REC_X + i] = x[i];
+  for (int i = 0; i < NX; ++i) rec[(size_t)rs * (SMPC_REC_X + i)] = x[i];
   if (!term)
 #pragma unroll
-    for (int i = 0; i < NU; ++i) rec[SMPC_REC_U + i] = u[i];
+    for (int i = 0; i < NU; ++i) rec[(size_t)rs * (SMPC_REC_U + i)] = u[i];
   const double* q = x;
   const double* v = x + NQ;
   Fk K;
@@ -354,40 +355,40 @@ SMPC_HD void linearize_stage(const smpc_problem_t& P, int k, const double* x, co
     const int be = P.point_body[0];
     int o = 0;
     for (int i = 0; i < NQ; ++i) {
-      rec[SMPC_REC_G + NU + i] = wq * dot(J[i], e);
+      rec[(size_t)rs * (SMPC_REC_G + NU + i)] = wq * dot(J[i], e);
       for (int j = 0; j <= i; ++j) {
         double h = dot(J[i], J[j]);
         if (ext && i <= be) h += dot(e, cross(K.z[j], cross(K.z[i], Pw - K.o[i])));   // j <= i: d2P/dq_j dq_i
-        rec[SMPC_REC_HQQ + o++] = wq * h;
+        rec[(size_t)rs * (SMPC_REC_HQQ + o++)] = wq * h;
       }
     }
     if (!term) {
       const double wr = (ext ? 2.0 : 1.0) * P.r_weight * s;
 #pragma unroll
-      for (int i = 0; i < NU; ++i) rec[SMPC_REC_G + i] = wr * u[i];
+      for (int i = 0; i < NU; ++i) rec[(size_t)rs * (SMPC_REC_G + i)] = wr * u[i];
       hu = wr;
     }
   }
   const double lmk = P.lm * ((P.lm_scale_dt && !term) ? P.dt : 1.0);
-  rec[SMPC_REC_HU] = term ? 0.0 : hu + lmk;
-  rec[SMPC_REC_HV] = lmk;
-  rec[SMPC_REC_HQ] = lmk;
+  rec[(size_t)rs * (SMPC_REC_HU)] = term ? 0.0 : hu + lmk;
+  rec[(size_t)rs * (SMPC_REC_HV)] = lmk;
+  rec[(size_t)rs * (SMPC_REC_HQ)] = lmk;
   // ---- torque rows ----
   if (!term) {
     Rnea S;
     double tau[NQ], d[NQ];
     rnea(P, P.inertial, q, v, u, S, tau);
 #pragma unroll
-    for (int i = 0; i < NU; ++i) rec[SMPC_REC_TAU + i] = tau[i];
+    for (int i = 0; i < NU; ++i) rec[(size_t)rs * (SMPC_REC_TAU + i)] = tau[i];
     for (int j = 0; j < NQ; ++j) {
       rnea_tangent<TAN_U>(P, P.inertial, S, v, u, j, d);
-      for (int i = 0; i < NU; ++i) rec[SMPC_REC_JTAU + i * 15 + j] = d[i];
+      for (int i = 0; i < NU; ++i) rec[(size_t)rs * (SMPC_REC_JTAU + i * 15 + j)] = d[i];
       rnea_tangent<TAN_Q>(P, P.inertial, S, v, u, j, d);
-      for (int i = 0; i < NU; ++i) rec[SMPC_REC_JTAU + i * 15 + NU + j] = d[i];
+      for (int i = 0; i < NU; ++i) rec[(size_t)rs * (SMPC_REC_JTAU + i * 15 + NU + j)] = d[i];
       rnea_tangent<TAN_V>(P, P.inertial, S, v, u, j, d);
-      for (int i = 0; i < NU; ++i) rec[SMPC_REC_JTAU + i * 15 + NU + NQ + j] = d[i];
+      for (int i = 0; i < NU; ++i) rec[(size_t)rs * (SMPC_REC_JTAU + i * 15 + NU + NQ + j)] = d[i];
     }
-    rec[SMPC_REC_NTAU] = NU;
+    rec[(size_t)rs * (SMPC_REC_NTAU)] = NU;
   }
   // ---- capsule rows ----
   if (k > 0 || P.stage0_collision_rows) {
@@ -397,30 +398,30 @@ SMPC_HD void linearize_stage(const smpc_problem_t& P, int k, const double* x, co
       const double d = segment_dist_grad(A, Bp, v3(P.pair_C[p]), v3(P.pair_D[p]), &gA, &gB);
       point_jacobian(P, K, P.pair_pa[p], A, JA);
       point_jacobian(P, K, P.pair_pb[p], Bp, JB);
-      rec[SMPC_REC_DIST + p] = d;
-      for (int j = 0; j < NQ; ++j) rec[SMPC_REC_JDIST + p * NQ + j] = dot(gA, JA[j]) + dot(gB, JB[j]);
+      rec[(size_t)rs * (SMPC_REC_DIST + p)] = d;
+      for (int j = 0; j < NQ; ++j) rec[(size_t)rs * (SMPC_REC_JDIST + p * NQ + j)] = dot(gA, JA[j]) + dot(gB, JB[j]);
     }
-    rec[SMPC_REC_NDIST] = NPAIR;
+    rec[(size_t)rs * (SMPC_REC_NDIST)] = NPAIR;
   }
   // ---- viability row ----
-  rec[SMPC_REC_SOFT] = -1.0;
+  rec[(size_t)rs * (SMPC_REC_SOFT)] = -1.0;
   if (has_nn) {
-    rec[SMPC_REC_NNROW] = 1.0;
+    rec[(size_t)rs * (SMPC_REC_NNROW)] = 1.0;
     if (gate_on) {
-      rec[SMPC_REC_NN] = nn11[0];
+      rec[(size_t)rs * (SMPC_REC_NN)] = nn11[0];
 #pragma unroll
-      for (int i = 0; i < NX; ++i) rec[SMPC_REC_JNN + i] = nn11[1 + i];
+      for (int i = 0; i < NX; ++i) rec[(size_t)rs * (SMPC_REC_JNN + i)] = nn11[1 + i];
     } else {
-      rec[SMPC_REC_NN] = 5e5;
+      rec[(size_t)rs * (SMPC_REC_NN)] = 5e5;
     }
-    if (term && P.nn_terminal_soft) rec[SMPC_REC_SOFT] = P.slack_penalty_e;
+    if (term && P.nn_terminal_soft) rec[(size_t)rs * (SMPC_REC_SOFT)] = P.slack_penalty_e;
   }
   // ---- dynamics offset ----
   if (!term) {
     double xn[NX];
     f_disc(P.dt, x, u, xn);
 #pragma unroll
-    for (int i = 0; i < NX; ++i) rec[SMPC_REC_B + i] = xn[i] - xnext[i];
+    for (int i = 0; i < NX; ++i) rec[(size_t)rs * (SMPC_REC_B + i)] = xn[i] - xnext[i];
   }
 }
 

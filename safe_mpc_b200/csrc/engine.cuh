@@ -6,7 +6,7 @@
 #include <string>
 
 #include "../../include/safe_mpc_b200.h"
-#include "qp_lanes.cuh"
+#include "qp_scalar.cuh"
 
 namespace smpc {
 
@@ -45,6 +45,7 @@ void launch_kin(const LaunchCtx& c, const smpc_problem_t* dP, int n, const doubl
 void launch_fill_i32(const LaunchCtx& c, int32_t* p, int n, int32_t v);
 void launch_fill_f64(const LaunchCtx& c, double* p, size_t n, double v);
 void launch_set_xviable_from_guess(const LaunchCtx& c, int B, int N, const double* xg, double* xv);
+void launch_dump_lin(const LaunchCtx& c, int B, int N, const double* lin, double* out);
 void launch_dump_qp(const LaunchCtx& c, int B, int N, const double* qpbuf, size_t stride, const double* lin, double* dz, double* pi, double* lam, double* t);
 
 // sim kernels

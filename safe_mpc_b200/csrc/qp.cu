@@ -1,147 +1,119 @@
-// QP kernel: one RTI quadratic program per half warp (see qp_lanes.cuh for the algorithm and data layout).
+// QP kernel: one RTI quadratic program per thread, 32 problems per warp (see qp_scalar.cuh for the algorithm).
 // Replaces the HPIPM solve inside AcadosOcpSolver.solve() (reference controller.py:158) and the full-step update /
 // status mapping that acados' SQP_RTI performs around it (controller.py:161-167).
+//
+// Global layout (both the stage records written by the linearisation kernel and the solver state):
+//   [tile = problem / 32][stage][field][problem % 32]  -> a warp's access to one field is one 256-byte row.
 #include "engine.cuh"
 
 namespace smpc {
 
-struct LanesDev {
-  int lane_;
-  int base_;
-  unsigned mask_;
-  double* scr_;
-  __device__ __forceinline__ int lane() const { return lane_; }
-  __device__ __forceinline__ double shfl(double v, int src) { return __shfl_sync(mask_, v, base_ + (src & 15)); }
-  __device__ __forceinline__ double shfl_xor(double v, int o) { return __shfl_xor_sync(mask_, v, o); }
-  __device__ __forceinline__ void sync() { __syncwarp(mask_); }
-  __device__ __forceinline__ double* scratch() { return scr_; }
+struct AccDev {
+  const double* recb;   // stage records of this problem's tile, offset by the lane
+  double* stb;          // solver state of this problem's tile, offset by the lane
+  double* l0b;
+  __device__ __forceinline__ double rec(int k, int f) const { return __ldg(recb + ((size_t)k * REC + f) * 32); }
+  __device__ __forceinline__ double ld(int k, int f) const { return stb[((size_t)k * QS_ST + f) * 32]; }
+  __device__ __forceinline__ void sd(int k, int f, double v) { stb[((size_t)k * QS_ST + f) * 32] = v; }
+  __device__ __forceinline__ double ll0(int i) const { return l0b[(size_t)i * 32]; }
+  __device__ __forceinline__ void sl0(int i, double v) { l0b[(size_t)i * 32] = v; }
 };
 
-size_t qp_stride_doubles(int N) { return (size_t)(N + 1) * qp_doubles_per_stage() + qp_doubles_fixed(); }
+size_t qp_stride_doubles(int N) { return qs_doubles_per_problem(N); }
 
-__device__ __forceinline__ QpMem qp_views(double* base, int N) {
-  QpMem M;
-  double* p = base;
-  const size_t n1 = (size_t)(N + 1);
-  M.z = p; p += 16 * n1;
-  M.pi = p; p += 16 * n1;
-  M.lam = p; p += 64 * n1;
-  M.t = p; p += 64 * n1;
-  M.aux = p; p += 16 * n1;
-  M.fac = p; p += 80 * n1;
-  M.Pm = p; p += 160 * n1;
-  M.pv = p; p += 16 * n1;
-  M.wv = p; p += 16 * n1;
-  M.rb = p; p += 16 * n1;
-  M.gb = p; p += 16 * n1;
-  M.prod = p; p += 64 * n1;
-  M.dz = p; p += 16 * n1;
-  M.dpi = p; p += 16 * n1;
-  M.dlam = p; p += 64 * n1;
-  M.dtt = p; p += 64 * n1;
-  M.L0 = p;
-  return M;
-}
-
-constexpr int QP_THREADS = 128;                 // 4 warps = 8 problems per CTA
-constexpr int QP_PROBLEMS_PER_CTA = QP_THREADS / QL;
+constexpr int QP_THREADS = 32;
 
 __global__ void __launch_bounds__(QP_THREADS)
 qp_kernel(const smpc_problem_t* __restrict__ dP, int B, int N, const double* __restrict__ lin, const double* __restrict__ x0,
-          const int32_t* __restrict__ r, const uint8_t* __restrict__ act, double* qpbuf, size_t stride, double* xt, double* ut,
+          const int32_t* __restrict__ r, const uint8_t* __restrict__ act, double* qpbuf, double* xt, double* ut,
           int32_t* status, int32_t* qp_iter, int32_t* qp_status, double* qp_res) {
-  extern __shared__ double smem[];
-  const int g = threadIdx.x / QL;                       // group within the CTA
-  const int b = blockIdx.x * QP_PROBLEMS_PER_CTA + g;   // problem
+  const int b = blockIdx.x * QP_THREADS + threadIdx.x;
   if (b >= B) return;
   if (act && !act[b]) return;
   const smpc_problem_t& P = *dP;
-  LanesDev ln;
-  ln.lane_ = threadIdx.x & 15;
-  ln.base_ = (threadIdx.x & 31) & 16;
-  ln.mask_ = 0xffffu << ln.base_;
-  ln.scr_ = smem + (size_t)g * QP_SCRATCH;
-  QpMem M = qp_views(qpbuf + (size_t)b * stride, N);
-  M.rec = lin + (size_t)b * (N + 1) * REC;
-  M.x0 = x0 + (size_t)b * NX;
-  M.r = r[b];
-  QpSolver<LanesDev> solver(ln, P, M);
+  const int tile = b >> 5, lane = b & 31;
+  AccDev acc;
+  acc.recb = lin + (size_t)tile * (N + 1) * REC * 32 + lane;
+  acc.stb = qpbuf + (size_t)tile * qs_doubles_per_problem(N) * 32 + lane;
+  acc.l0b = acc.stb + (size_t)(N + 1) * QS_ST * 32;
+  double x0l[NX];
+#pragma unroll
+  for (int i = 0; i < NX; ++i) x0l[i] = x0[(size_t)b * NX + i];
+  QpScalar<AccDev> solver(P, acc, x0l, r[b]);
   const QpResult R = solver.solve();
   // ---- full step and status mapping (acados SQP_RTI: QP success / max-iter -> step taken, else QP failure) ----
-  const int lane = ln.lane_;
   const bool ok = (R.status == 0 || R.status == 1);
   bool nan = false;
   double* xtb = xt + (size_t)b * (N + 1) * NX;
   double* utb = ut + (size_t)b * N * NU;
   for (int k = 0; k <= N; ++k) {
-    const double* rec = M.rec + (size_t)k * REC;
-    const double z = ok ? M.z[(size_t)k * 16 + lane] : 0.0;
-    if (lane < 5) { if (k < N) { utb[k * NU + lane] = rec[SMPC_REC_U + lane] + z; nan |= (z != z); } }
-    else if (lane < 15) { xtb[k * NX + lane - 5] = rec[SMPC_REC_X + lane - 5] + z; nan |= (z != z); }
+    if (k < N)
+      for (int i = 0; i < NU; ++i) { const double z = ok ? acc.ld(k, F_Z + i) : 0.0; utb[k * NU + i] = acc.rec(k, SMPC_REC_U + i) + z; nan |= (z != z); }
+    for (int i = 0; i < NX; ++i) { const double z = ok ? acc.ld(k, F_Z + 5 + i) : 0.0; xtb[k * NX + i] = acc.rec(k, SMPC_REC_X + i) + z; nan |= (z != z); }
   }
-  const unsigned any_nan = __ballot_sync(ln.mask_, nan) & ln.mask_;
-  if (lane == 0) {
-    status[b] = ok ? (any_nan ? 1 : 0) : 4;
-    qp_iter[b] = R.iter;
-    qp_status[b] = R.status;
-    for (int i = 0; i < 4; ++i) qp_res[(size_t)b * 5 + i] = R.res[i];
-    qp_res[(size_t)b * 5 + 4] = R.mu;
-  }
+  status[b] = ok ? (nan ? 1 : 0) : 4;
+  qp_iter[b] = R.iter;
+  qp_status[b] = R.status;
+  for (int i = 0; i < 4; ++i) qp_res[(size_t)b * 5 + i] = R.res[i];
+  qp_res[(size_t)b * 5 + 4] = R.mu;
 }
 
 void launch_qp(const LaunchCtx& c, const smpc_problem_t* dP, int B, int N, const double* lin, const double* x0, const int32_t* r,
                const uint8_t* act, double* qpbuf, double* xt, double* ut, int32_t* status, int32_t* qp_iter, int32_t* qp_status,
                double* qp_res) {
-  const int grid = (B + QP_PROBLEMS_PER_CTA - 1) / QP_PROBLEMS_PER_CTA;
-  const size_t smem = (size_t)QP_PROBLEMS_PER_CTA * QP_SCRATCH * sizeof(double);
-  qp_kernel<<<grid, QP_THREADS, smem, c.stream>>>(dP, B, N, lin, x0, r, act, qpbuf, qp_stride_doubles(N), xt, ut, status, qp_iter,
-                                                  qp_status, qp_res);
+  const int grid = (B + QP_THREADS - 1) / QP_THREADS;
+  qp_kernel<<<grid, QP_THREADS, 0, c.stream>>>(dP, B, N, lin, x0, r, act, qpbuf, xt, ut, status, qp_iter, qp_status, qp_res);
+  ++*c.launches;
+}
+
+// stage records [tile][stage][field][32] -> caller layout [B][N+1][REC]   (smpc_get_lin)
+__global__ void dump_lin_kernel(int B, int N, const double* lin, double* out) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)B * (N + 1) * REC;
+  if (idx >= total) return;
+  const int f = idx % REC;
+  const int k = (idx / REC) % (N + 1);
+  const int b = idx / ((size_t)REC * (N + 1));
+  out[idx] = lin[(((size_t)(b >> 5) * (N + 1) + k) * REC + f) * 32 + (b & 31)];
+}
+void launch_dump_lin(const LaunchCtx& c, int B, int N, const double* lin, double* out) {
+  const size_t total = (size_t)B * (N + 1) * REC;
+  dump_lin_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c.stream>>>(B, N, lin, out);
   ++*c.launches;
 }
 
 // canonical dump of the QP solution for parity tests (layout of smpc_get_qp)
-__global__ void dump_qp_kernel(int B, int N, const double* qpbuf, size_t stride, const double* lin, double* dz, double* pi, double* lam, double* t) {
+__global__ void dump_qp_kernel(int B, int N, const double* qpbuf, const double* lin, double* dz, double* pi, double* lam, double* t) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * (N + 1)) return;
   const int b = idx / (N + 1), k = idx % (N + 1);
-  QpMem M = qp_views(const_cast<double*>(qpbuf) + (size_t)b * stride, N);
-  const double* rec = lin + ((size_t)b * (N + 1) + k) * REC;
+  const double* st = qpbuf + (size_t)(b >> 5) * qs_doubles_per_problem(N) * 32 + (b & 31) + (size_t)k * QS_ST * 32;
+  const double* rec = lin + ((size_t)(b >> 5) * (N + 1) + k) * REC * 32 + (b & 31);
+  auto S = [&](int f) { return st[(size_t)f * 32]; };
+  auto R = [&](int f) { return rec[(size_t)f * 32]; };
   if (dz) {
     double* o = dz + (size_t)idx * 15;
-    if (k < N) for (int i = 0; i < 15; ++i) o[i] = M.z[(size_t)k * 16 + i];
-    else { for (int i = 0; i < 10; ++i) o[i] = M.z[(size_t)k * 16 + 5 + i]; for (int i = 10; i < 15; ++i) o[i] = 0.0; }
+    if (k < N) for (int i = 0; i < 15; ++i) o[i] = S(F_Z + i);
+    else { for (int i = 0; i < 10; ++i) o[i] = S(F_Z + 5 + i); for (int i = 10; i < 15; ++i) o[i] = 0.0; }
   }
-  if (pi && k < N) for (int i = 0; i < 10; ++i) pi[((size_t)b * N + k) * 10 + i] = M.pi[(size_t)k * 16 + 5 + i];
+  if (pi && k < N) for (int i = 0; i < 10; ++i) pi[((size_t)b * N + k) * 10 + i] = S(F_PI + i);
   if (lam && t) {
     double* ol = lam + (size_t)idx * SMPC_QP_NC;
     double* ot = t + (size_t)idx * SMPC_QP_NC;
-    for (int i = 0; i < SMPC_QP_NC; ++i) { ol[i] = 0.0; ot[i] = 0.0; }
-    const bool ntau = rec[SMPC_REC_NTAU] > 0.5, ndist = rec[SMPC_REC_NDIST] > 0.5, nn = rec[SMPC_REC_NNROW] > 0.5;
-    for (int lane = 0; lane < 15; ++lane) {
-      const bool pa = lane < 5 ? ntau : true;
-      const int ida = lane < 5 ? 10 + lane : lane - 5;
-      if (pa) for (int s = 0; s < 2; ++s) {
-        ol[s * SMPC_QP_NR + ida] = M.lam[(size_t)k * 64 + s * 16 + lane];
-        ot[s * SMPC_QP_NR + ida] = M.t[(size_t)k * 64 + s * 16 + lane];
-      }
-      const bool pb = (lane >= 5 && lane <= 10) ? ndist : (lane == 11 ? nn : false);
-      const int idb = lane == 11 ? 21 : 15 + lane - 5;
-      if (pb) for (int s = 0; s < 2; ++s) {
-        ol[s * SMPC_QP_NR + idb] = M.lam[(size_t)k * 64 + (2 + s) * 16 + lane];
-        ot[s * SMPC_QP_NR + idb] = M.t[(size_t)k * 64 + (2 + s) * 16 + lane];
-      }
+    const bool ntau = R(SMPC_REC_NTAU) > 0.5, ndist = R(SMPC_REC_NDIST) > 0.5, nn = R(SMPC_REC_NNROW) > 0.5;
+    for (int j = 0; j < QNR; ++j) {
+      const bool p = j < 10 ? true : (j < 15 ? ntau : (j < 21 ? ndist : nn));
+      for (int s = 0; s < 2; ++s) { ol[s * QNR + j] = p ? S(F_LAM + s * QNR + j) : 0.0; ot[s * QNR + j] = p ? S(F_T + s * QNR + j) : 0.0; }
     }
-    if (nn && rec[SMPC_REC_SOFT] >= 0.0) {
-      const double* a = M.aux + (size_t)k * 16;
-      ol[2 * SMPC_QP_NR] = a[2]; ol[2 * SMPC_QP_NR + 1] = a[3];
-      ot[2 * SMPC_QP_NR] = a[4]; ot[2 * SMPC_QP_NR + 1] = a[5];
-    }
+    const bool soft = nn && R(SMPC_REC_SOFT) >= 0.0;
+    ol[2 * QNR] = soft ? S(F_SLK + 2) : 0.0; ol[2 * QNR + 1] = soft ? S(F_SLK + 3) : 0.0;
+    ot[2 * QNR] = soft ? S(F_SLK + 4) : 0.0; ot[2 * QNR + 1] = soft ? S(F_SLK + 5) : 0.0;
   }
 }
 
 void launch_dump_qp(const LaunchCtx& c, int B, int N, const double* qpbuf, size_t stride, const double* lin, double* dz, double* pi, double* lam, double* t) {
   const int n = B * (N + 1);
-  dump_qp_kernel<<<(n + 127) / 128, 128, 0, c.stream>>>(B, N, qpbuf, stride, lin, dz, pi, lam, t);
+  dump_qp_kernel<<<(n + 127) / 128, 128, 0, c.stream>>>(B, N, qpbuf, lin, dz, pi, lam, t);
   ++*c.launches;
 }
 

@@ -6,7 +6,7 @@
 
 #include "../../safe_mpc_b200/csrc/dev_model.cuh"
 #ifdef EMU_QP
-#include "../../safe_mpc_b200/csrc/qp_lanes.cuh"
+#include "../../safe_mpc_b200/csrc/qp_scalar.cuh"
 #endif
 
 using namespace smpc;
@@ -39,52 +39,38 @@ int emu_checks(const smpc_problem_t* P, int n, const double* x, int* in_bounds, 
 }  // extern "C"
 
 #ifdef EMU_QP
-#include <barrier>
-#include <thread>
-
 namespace {
-struct Group {
-  std::barrier<> bar{QL};
-  double x[QL];
-  double scratch[QP_SCRATCH];
-};
-struct LanesHost {
-  int lane_;
-  Group* g;
-  int lane() const { return lane_; }
-  double shfl(double v, int src) { g->x[lane_] = v; g->bar.arrive_and_wait(); double r = g->x[src & 15]; g->bar.arrive_and_wait(); return r; }
-  double shfl_xor(double v, int o) { return shfl(v, lane_ ^ o); }
-  void sync() { g->bar.arrive_and_wait(); }
-  double* scratch() { return g->scratch; }
+// host stand-in of the device accessor: plain (stride-1) arrays of one problem
+struct AccHost {
+  const double* recb;
+  double* stb;
+  double* l0b;
+  double rec(int k, int f) const { return recb[(size_t)k * REC + f]; }
+  double ld(int k, int f) const { return stb[(size_t)k * QS_ST + f]; }
+  void sd(int k, int f, double v) { stb[(size_t)k * QS_ST + f] = v; }
+  double ll0(int i) const { return l0b[i]; }
+  void sl0(int i, double v) { l0b[i] = v; }
 };
 }  // namespace
 
-extern "C" int emu_qp_solve(const smpc_problem_t* P, const double* rec, const double* x0, int r, double* z16, double* pi16,
-                            double* lam64, double* t64, int* iter, int* status, double* res5) {
+// z: [N+1][15], pi: [N][10], lam/t: [N+1][44]
+extern "C" int emu_qp_solve(const smpc_problem_t* P, const double* rec, const double* x0, int r, double* z, double* pi,
+                            double* lam, double* t, int* iter, int* status, double* res5) {
   const int N = P->N;
-  std::vector<double> buf((size_t)(N + 1) * qp_doubles_per_stage() + qp_doubles_fixed(), 0.0);
-  QpMem M;
-  double* p = buf.data();
-  auto take = [&](size_t per_stage) { double* q = p; p += per_stage * (N + 1); return q; };
-  M.rec = rec; M.x0 = x0; M.r = r;
-  M.z = z16; M.pi = pi16; M.lam = lam64; M.t = t64;
-  take(16); take(16); take(64); take(64);   // (caller-provided above; keep the arithmetic of the size formula)
-  M.aux = take(16); M.fac = take(80); M.Pm = take(160); M.pv = take(16); M.wv = take(16); M.rb = take(16); M.gb = take(16);
-  M.prod = take(64); M.dz = take(16); M.dpi = take(16); M.dlam = take(64); M.dtt = take(64);
-  M.L0 = p;
-  Group g;
-  QpResult R[QL];
-  std::vector<std::thread> th;
-  for (int l = 0; l < QL; ++l)
-    th.emplace_back([&, l]() {
-      LanesHost ln{l, &g};
-      QpSolver<LanesHost> s(ln, *P, M);
-      R[l] = s.solve();
-    });
-  for (auto& t : th) t.join();
-  *iter = R[0].iter; *status = R[0].status;
-  for (int i = 0; i < 4; ++i) res5[i] = R[0].res[i];
-  res5[4] = R[0].mu;
+  std::vector<double> st(qs_doubles_per_problem(N), 0.0);
+  AccHost acc{rec, st.data(), st.data() + (size_t)(N + 1) * QS_ST};
+  QpScalar<AccHost> solver(*P, acc, x0, r);
+  const QpResult R = solver.solve();
+  for (int k = 0; k <= N; ++k) {
+    const double* b = st.data() + (size_t)k * QS_ST;
+    std::memcpy(z + k * 15, b + F_Z, 15 * sizeof(double));
+    if (k < N) std::memcpy(pi + k * 10, b + F_PI, 10 * sizeof(double));
+    std::memcpy(lam + k * 44, b + F_LAM, 44 * sizeof(double));
+    std::memcpy(t + k * 44, b + F_T, 44 * sizeof(double));
+  }
+  *iter = R.iter; *status = R.status;
+  for (int i = 0; i < 4; ++i) res5[i] = R.res[i];
+  res5[4] = R.mu;
   return 0;
 }
 #endif

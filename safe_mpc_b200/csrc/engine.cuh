@@ -6,7 +6,7 @@
 #include <string>
 
 #include "../../include/safe_mpc_b200.h"
-#include "qp_scalar.cuh"
+#include "qp_warp.cuh"
 
 namespace smpc {
 
@@ -45,8 +45,7 @@ void launch_kin(const LaunchCtx& c, const smpc_problem_t* dP, int n, const doubl
 void launch_fill_i32(const LaunchCtx& c, int32_t* p, int n, int32_t v);
 void launch_fill_f64(const LaunchCtx& c, double* p, size_t n, double v);
 void launch_set_xviable_from_guess(const LaunchCtx& c, int B, int N, const double* xg, double* xv);
-void launch_dump_lin(const LaunchCtx& c, int B, int N, const double* lin, double* out);
-void launch_dump_qp(const LaunchCtx& c, int B, int N, const double* qpbuf, size_t stride, const double* lin, double* dz, double* pi, double* lam, double* t);
+void launch_dump_qp(const LaunchCtx& c, int B, int N, const double* ws, const double* lin, double* dz, double* pi, double* lam, double* t);
 
 // sim kernels
 struct SimDev {
@@ -63,8 +62,13 @@ void launch_sim_post(const LaunchCtx& c, const SimDev& s, const smpc_problem_t* 
 void launch_sim_outcome(const LaunchCtx& c, const SimDev& s, const smpc_problem_t* dP, int32_t* out);
 
 // qp.cu
-size_t qp_stride_doubles(int N);
-void launch_qp(const LaunchCtx& c, const smpc_problem_t* dP, int B, int N, const double* lin, const double* x0, const int32_t* r,
-               const uint8_t* act, double* qpbuf, double* xt, double* ut, int32_t* status, int32_t* qp_iter, int32_t* qp_status, double* qp_res);
+size_t qp_ws_doubles(int N);          // workspace of one warp (slot)
+size_t qp_smem_bytes();
+int qp_grid(int B);                   // number of persistent one-warp CTAs (= workspace slots) for a batch of B; sets kernel attributes
+// queue != nullptr: `grid` persistent warps pull problems from the atomic queue; queue == nullptr: CTA b solves problem b
+// in workspace slot b (grid must equal B; used when the caller wants the per-problem QP solution back)
+void launch_qp(const LaunchCtx& c, const smpc_problem_t* dP, int B, int N, int grid, const double* lin, const double* x0, const int32_t* r,
+               const uint8_t* act, double* ws, int* queue, double* xt, double* ut, int32_t* status, int32_t* qp_iter, int32_t* qp_status,
+               double* qp_res);
 
 }  // namespace smpc

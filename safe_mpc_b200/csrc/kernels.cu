@@ -195,13 +195,10 @@ void launch_mlp(const LaunchCtx& c, const smpc_problem_t* dP, const MlpWeights& 
 __global__ void __launch_bounds__(128)
 linearize_kernel(const smpc_problem_t* __restrict__ dP, int B, int N, const double* __restrict__ xg, const double* __restrict__ ug,
                  const int32_t* __restrict__ r, const uint8_t* __restrict__ act, const double* __restrict__ nn11, double* lin) {
-  // consecutive threads = consecutive problems of the same stage: the record stores of a warp are 256-byte rows of the
-  // [tile][stage][field][32] layout the QP kernel reads
-  const int Bt = ((B + 31) >> 5) << 5;
+  // one contiguous record per (problem, stage), [B][N+1][REC]: the QP kernel streams whole records with bulk copies
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= Bt * (N + 1)) return;
-  const int b = idx % Bt, k = idx / Bt;
-  if (b >= B) return;
+  if (idx >= B * (N + 1)) return;
+  const int b = idx / (N + 1), k = idx % (N + 1);
   if (act && !act[b]) return;
   const smpc_problem_t& P = *dP;
   double x[NX], u[NU], xn[NX];
@@ -213,12 +210,12 @@ linearize_kernel(const smpc_problem_t* __restrict__ dP, int B, int N, const doub
   const bool has_nn = stage_has_nn(P, k);
   bool gate = true;
   if (P.nn_rows == SMPC_NN_RECEDING && k < N) gate = (k == r[b]);      // controller.py:452-469
-  double* rec = lin + (((size_t)(b >> 5) * (N + 1) + k) * REC) * 32 + (b & 31);
-  linearize_stage(P, k, x, u, xn, has_nn, gate, nn11 + ((size_t)b * (N + 1) + k) * NN_OUT, rec, 32);
+  double* rec = lin + (size_t)idx * REC;
+  linearize_stage(P, k, x, u, xn, has_nn, gate, nn11 + (size_t)idx * NN_OUT, rec, 1);
 }
 void launch_linearize(const LaunchCtx& c, const smpc_problem_t* dP, int B, int N, const double* xg, const double* ug, const int32_t* r,
                       const uint8_t* act, const double* nn11, double* lin) {
-  const int n = (((B + 31) >> 5) << 5) * (N + 1);
+  const int n = B * (N + 1);
   linearize_kernel<<<GRID1D(n, 128), 128, 0, c.stream>>>(dP, B, N, xg, ug, r, act, nn11, lin);
   ++*c.launches;
 }

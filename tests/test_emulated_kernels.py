@@ -1,4 +1,4 @@
-"""Kernel-logic tests without a GPU: the engine's device sources (safe_mpc_b200/csrc/dev_model.cuh, qp_lanes.cuh)
+"""Kernel-logic tests without a GPU: the engine's device sources (safe_mpc_b200/csrc/dev_model.cuh, qp_warp.cuh)
 compiled for the host by tests/emu and compared with the oracle.
 This is a test harness, not a fallback: the product never loads it."""
 import ctypes as C
@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 @pytest.fixture(scope='module')
 def emu():
     so = os.path.join(HERE, 'emu', 'libsmpc_emu.so')
-    srcs = [os.path.join(HERE, 'emu', 'emu.cpp')] + [os.path.join(HERE, '..', 'safe_mpc_b200', 'csrc', f) for f in ('dev_model.cuh', 'qp_scalar.cuh')]
+    srcs = [os.path.join(HERE, 'emu', 'emu.cpp')] + [os.path.join(HERE, '..', 'safe_mpc_b200', 'csrc', f) for f in ('dev_model.cuh', 'qp_warp.cuh')]
     if not os.path.isfile(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.run(['g++', '-O2', '-std=c++17', '-DEMU_QP', '-fPIC', '-shared', '-o', so, srcs[0]], check=True)
     return C.CDLL(so)
@@ -55,7 +55,8 @@ def test_analytic_linearisation_matches_ad_oracle(emu):
 
 @pytest.mark.parametrize('controller,cost', [('naive', 'ext'), ('st', 'ext'), ('htwa', 'ext'), ('receding', 'ext'),
                                              ('real_receding', 'ext'), ('zerovel', 'ext'), ('backup', 'zero')])
-def test_qp_kernel_source_matches_oracle(emu, controller, cost):
+@pytest.mark.parametrize('lazy', [0, 1])
+def test_qp_kernel_source_matches_oracle(emu, controller, cost, lazy):
     N, B = 10, 3
     prob, params, md = make_problem(controller, cost=cost, N=N)
     o = Oracle(prob, B, 1)
@@ -70,7 +71,7 @@ def test_qp_kernel_source_matches_oracle(emu, controller, cost):
         z = np.zeros((N + 1, 15)); pi_e = np.zeros((N, 10)); lam_e = np.zeros((N + 1, 44)); t_e = np.zeros((N + 1, 44))
         it = C.c_int(); st = C.c_int(); res = np.zeros(5)
         x0b = (x0[b] + 1e-3).copy()
-        emu.emu_qp_solve(C.byref(prob), _p(np.ascontiguousarray(lin[b])), _p(x0b), C.c_int(rset), _p(z), _p(pi_e), _p(lam_e), _p(t_e),
+        emu.emu_qp_solve(C.byref(prob), _p(np.ascontiguousarray(lin[b])), _p(x0b), C.c_int(rset), C.c_int(lazy), _p(z), _p(pi_e), _p(lam_e), _p(t_e),
                          C.byref(it), C.byref(st), _p(res))
         _, _, oit, ost = o.qp_info(b)
         assert (it.value, st.value) == (oit, ost)

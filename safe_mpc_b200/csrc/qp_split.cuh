@@ -1,0 +1,985 @@
+// Stage-structured interior-point QP solve of one RTI iteration -- split formulation (v6).
+//
+// Replaces the HPIPM call inside AcadosOcpSolver.solve() (reference controller.py:158; options :97-110,208-209;
+// algorithm: Frison & Diehl, HPIPM, IFAC 2020 -- Mehrotra predictor-corrector IPM, inequality rows condensed into
+// the stage Hessian, backward Riccati factorisation / forward substitution) and the full-step update / status
+// mapping acados' SQP_RTI performs around it (controller.py:161-167).
+//
+// Decomposition.  Only the Riccati recursion is sequential in the stage index k; the primal-dual update, the
+// residuals, the condensation of the inequality rows, the recovery of (dlam, dt, dslack) and the step length are
+// independent per (problem, stage).  One IPM iteration is therefore a short sequence of small kernels:
+//   prep   (thread per (problem, stage))  update iterate, residuals, condensed stage matrix / gradient
+//   ctl    (thread per problem)           reduce residual norms, convergence / failure logic, write result when done
+//   ric1   (thread per problem)           backward factorisation + forward substitution of the affine direction
+//   step0  (thread per (problem, stage))  affine (dlam, dt), step-length partials, dlam*dt products, corrector terms
+//   ric2   (thread per problem)           sigma; vector-only backward + forward sweep of the corrector direction
+//   step1  (thread per (problem, stage))  corrector (dlam, dt, dslack), step-length partials
+//   red    (thread per problem)           step length; conditional predictor-corrector decision
+//   ric2 / step1 / red in mode 2          pure centering re-solve for the problems that asked for it
+// Every lane owns a whole problem (or a whole stage of one): no shuffles, no barriers, no padding, 32 useful
+// operations per instruction, and each kernel body is a few KB of code (the monolithic v5 kernel was bound by
+// instruction fetch, profiles/r01_qp_v5_warp_per_problem.md).
+//
+// Layout.  Problems are grouped in tiles of TL = 32; every per-(problem, stage) array is stored
+// [tile][stage][field][lane], every per-problem array [tile][field][lane]: lane l of a warp works on problem
+// 32 tile + l and any field access of the warp is one coalesced 256-byte transaction, in the stage-parallel
+// kernels (warp = one stage of a tile) and in the Riccati kernels (warp = one tile walking the stages) alike.
+//
+// QP variable order per stage: z = [du(5); dq(5); dv(5)].  The constant double-integrator A, B
+// (env_model.py:63-71) are never stored: [B A]' P [B A] is formed in closed form from the 5x5 blocks of P.
+// Rows per stage: box 0-9 (state j), torque 10-14, capsule 15-20, viability 21; slot = side * 22 + row,
+// side 0 = lower, 1 = upper.  The viability row may be soft (one slack per side, L1 penalty).
+//
+// The functions are SMPC_HD so that tests/emu can run the very same source on the host against the oracle.
+#pragma once
+#include "dev_model.cuh"
+
+namespace smpc {
+
+constexpr int TL = 32;             // problems per tile
+constexpr int QNR = 22;            // two-sided rows per stage
+SMPC_HD constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }   // packed lower triangle, i >= j
+SMPC_HD constexpr int trs(int i, int j) { return i >= j ? tri(i, j) : tri(j, i); }
+
+// iterate block (also the layout of the step block)
+enum { I_Z = 0, I_PIM = 15, I_LAM = 25, I_T = 69, I_SLK = 113, NIT = 120 };   // I_SLK: s_l s_u lam_sl lam_su t_sl t_su
+// condensed stage block (prep -> ric1 / ric2)
+enum { H_M = 0, H_GA = 120, H_RB = 135, NHC = 145 };
+// corrector terms (step0 -> ric2): v1 = C'(dlam_aff dt_aff / t), v2 = C'(1 / t)
+enum { V_1 = 0, V_2 = 15, NV = 30 };
+// Riccati factors (ric1 -> ric2): T[15][5] elimination multipliers (T[j][j] = 1/d_j), P packed 10x10, l~(5) p(10), P_{k+1} res_b
+enum { F_T = 0, F_P = 75, F_LP = 130, F_WV = 145, NFAC = 155 };
+enum { NPROD = 46 };               // dlam_aff * dt_aff per slot (44) + the two slack slots
+enum { R_NG = 0, R_NB = 1, R_ND = 2, R_NM = 3, R_MU = 4, R_CHK = 5, R_CNT = 6, NRES = 8 };
+enum { S_ALPHA = 0, S_LIN = 1, S_QUAD = 2, NSTP = 4 };
+// per-problem doubles
+enum { D_X0 = 0, D_T0 = 10, D_MU = 65, D_MUAFF = 66, D_SIGMU = 67, D_ALPHA = 68, D_STEP = 69, D_RES = 70, NPD = 74 };
+// per-problem ints
+enum { J_ACT = 0, J_ITER = 1, J_QST = 2, J_REDO = 3, J_NC = 4, J_ITBUF = 5, J_R = 6, J_B = 7, NPI = 8 };
+
+struct QsBufs {
+  const double* rec;     // [T][N+1][REC][TL]   stage records (linearisation)
+  double* it[2];         // [T][N+1][NIT][TL]   iterate, ping-pong
+  double* st;            // [T][N+1][NIT][TL]   step
+  double* hc;            // [T][N+1][NHC][TL]
+  double* v;             // [T][N+1][NV][TL]
+  double* fac;           // [T][N+1][NFAC][TL]
+  double* prod;          // [T][N+1][NPROD][TL]
+  double* res;           // [T][N+1][NRES][TL]
+  double* stp;           // [T][N+1][NSTP][TL]
+  double* pd;            // [T][NPD][TL]
+  int32_t* pi;           // [T][NPI][TL]
+  int N;
+};
+
+#define QF(p, f) (p)[(size_t)(f) * TL]
+
+SMPC_HD size_t qs_blk(int tile, int N, int k, int nf, int lane) { return ((size_t)(tile * (N + 1) + k) * nf) * TL + lane; }
+SMPC_HD size_t qs_pb(int tile, int nf, int lane) { return (size_t)tile * nf * TL + lane; }
+
+struct StageFlags {
+  bool tau, dist, nn, soft;
+  double zpen;
+};
+SMPC_HD StageFlags qs_flags(const smpc_problem_t& P, int k) {
+  StageFlags f;
+  f.tau = k < P.N;
+  f.dist = (k > 0) || P.stage0_collision_rows;
+  f.nn = stage_has_nn(P, k);
+  f.soft = f.nn && k == P.N && P.nn_terminal_soft;
+  f.zpen = f.soft ? P.slack_penalty_e : -1.0;
+  return f;
+}
+
+// box of dx_j at stage k (controller.py:49-55,144-145,300-306,530-536,701-707)
+SMPC_HD void qs_box(const smpc_problem_t& P, const QsBufs& q, int tile, int lane, int k, int j, double x0j, int rrec, double& lo, double& hi) {
+  const int N = q.N;
+  const double xk = QF(q.rec + qs_blk(tile, N, k, REC, lane), SMPC_REC_X + j);
+  if (k == 0) { lo = x0j - xk; hi = lo; }
+  else if (k == N) { lo = P.lbx_e[j] - xk; hi = P.ubx_e[j] - xk; }
+  else if (P.controller == SMPC_CTRL_REAL_RECEDING) {
+    if (k == rrec) { const double c = QF(q.rec + qs_blk(tile, N, k + 1, REC, lane), SMPC_REC_X + j); lo = c - 1e-3 - xk; hi = c + 1e-3 - xk; }
+    else { lo = P.x_min[j] - xk; hi = P.x_max[j] - xk; }
+  } else { lo = P.lbx[j] - xk; hi = P.ubx[j] - xk; }
+}
+// cold start of a box row: primal moved inside, slacks >= thr0
+SMPC_HD double qs_zinit(double lo, double hi, double& tl, double& tu) {
+  const double thr0 = 1e-1;
+  double zc = 0.0;
+  tl = zc - lo; tu = hi - zc;
+  if (tl < thr0) {
+    if (tu < thr0) { zc = 0.5 * (lo + hi); tl = thr0; tu = thr0; }
+    else { tl = thr0; zc = lo + thr0; }
+  } else if (tu < thr0) { tu = thr0; zc = hi - thr0; }
+  return zc;
+}
+
+SMPC_HD double qs_rm(int mode, double lamt, double prod, double sigmu) {
+  return mode == 0 ? lamt : (mode == 1 ? lamt + prod - sigmu : lamt - sigmu);
+}
+
+struct QsNorms {
+  double ng, nb, nd, nm, mu, chk;
+  int cnt;
+};
+
+// ================================================================================================================
+// prep: (cold start | primal-dual update) + residuals + condensation.   thread = (problem, stage)
+// ================================================================================================================
+SMPC_HD void qs_prep(const smpc_problem_t& P, const QsBufs& q, int tile, int lane, int k, int kk) {
+  const int N = q.N;
+  const int32_t* pi = q.pi + qs_pb(tile, NPI, lane);
+  if (!QF(pi, J_ACT)) return;
+  const double* pd = q.pd + qs_pb(tile, NPD, lane);
+  const bool first = kk == 0;
+  const double a = first ? 0.0 : QF(pd, D_STEP);
+  const int rrec = QF(pi, J_R);
+  const double* rec = q.rec + qs_blk(tile, N, k, REC, lane);
+  double* ito = q.it[kk & 1] + qs_blk(tile, N, k, NIT, lane);
+  const double* iti = q.it[(kk & 1) ^ 1] + qs_blk(tile, N, k, NIT, lane);
+  const double* st = q.st + qs_blk(tile, N, k, NIT, lane);
+  double* hc = q.hc + qs_blk(tile, N, k, NHC, lane);
+  const StageFlags F = qs_flags(P, k);
+  const double lam_min = 1e-16, t_min = 1e-16, thr0 = 1e-1, mu0 = P.qp_mu0, reg = P.qp_reg_prim;
+  const double dt = P.dt, a2 = 0.5 * P.dt * P.dt;
+  QsNorms nr;
+  nr.ng = nr.nb = nr.nd = nr.nm = nr.mu = nr.chk = 0.0; nr.cnt = 0;
+
+  // ---- iterate of this stage ----
+  double z[15], blo[10], bhi[10];
+#pragma unroll
+  for (int j = 0; j < 10; ++j) qs_box(P, q, tile, lane, k, j, QF(pd, D_X0 + j), rrec, blo[j], bhi[j]);
+  if (first) {
+#pragma unroll
+    for (int i = 0; i < 5; ++i) z[i] = 0.0;
+#pragma unroll
+    for (int j = 0; j < 10; ++j) { double tl, tu; z[5 + j] = qs_zinit(blo[j], bhi[j], tl, tu); }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 15; ++i) z[i] = QF(iti, I_Z + i) + a * QF(st, I_Z + i);
+  }
+  if (k == N) {
+#pragma unroll
+    for (int i = 0; i < 5; ++i) z[i] = 0.0;
+  }
+#pragma unroll
+  for (int i = 0; i < 15; ++i) QF(ito, I_Z + i) = z[i];
+
+  // ---- stationarity residual: H z + g + [B A]' pi_{k+1} - pi_k  (inequality multipliers are added row by row below) ----
+  double rg[15], gd[15];
+#pragma unroll
+  for (int i = 0; i < 15; ++i) gd[i] = 0.0;
+  {
+    const double hu = QF(rec, SMPC_REC_HU), hq = QF(rec, SMPC_REC_HQ), hv = QF(rec, SMPC_REC_HV);
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      rg[i] = (k == N) ? 0.0 : hu * z[i] + QF(rec, SMPC_REC_G + i);
+      double s = QF(rec, SMPC_REC_G + 5 + i) + hq * z[5 + i];
+#pragma unroll
+      for (int j = 0; j < 5; ++j) s += QF(rec, SMPC_REC_HQQ + trs(i, j)) * z[5 + j];
+      rg[5 + i] = s;
+      rg[10 + i] = QF(rec, SMPC_REC_G + 10 + i) + hv * z[10 + i];
+    }
+  }
+  // multipliers of the dynamics: pi_k (link k-1 -> k, stored with stage k), pi_{k+1}
+#pragma unroll
+  for (int j = 0; j < 10; ++j) {
+    const double pim = (first || k == 0) ? 0.0 : QF(iti, I_PIM + j) + a * QF(st, I_PIM + j);
+    QF(ito, I_PIM + j) = pim;
+    rg[5 + j] -= pim;
+  }
+  if (k < N) {
+    const double* itn = q.it[(kk & 1) ^ 1] + qs_blk(tile, N, k + 1, NIT, lane);
+    const double* stn = q.st + qs_blk(tile, N, k + 1, NIT, lane);
+    double rb[10];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      rb[j] = z[5 + j] + dt * z[10 + j] + a2 * z[j] + QF(rec, SMPC_REC_B + j);
+      rb[5 + j] = z[10 + j] + dt * z[j] + QF(rec, SMPC_REC_B + 5 + j);
+    }
+    if (first) {
+#pragma unroll
+      for (int j = 0; j < 10; ++j) {
+        double lo, hi, tl, tu;
+        qs_box(P, q, tile, lane, k + 1, j, 0.0, rrec, lo, hi);
+        rb[j] -= qs_zinit(lo, hi, tl, tu);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        const double pq = QF(itn, I_PIM + j) + a * QF(stn, I_PIM + j);
+        const double pv = QF(itn, I_PIM + 5 + j) + a * QF(stn, I_PIM + 5 + j);
+        if (k < N) { rg[j] += a2 * pq + dt * pv; }
+        rg[5 + j] += pq;
+        rg[10 + j] += dt * pq + pv;
+        rb[j] -= QF(itn, I_Z + 5 + j) + a * QF(stn, I_Z + 5 + j);
+        rb[5 + j] -= QF(itn, I_Z + 10 + j) + a * QF(stn, I_Z + 10 + j);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 10; ++j) { QF(hc, H_RB + j) = rb[j]; nr.nb = fmax(nr.nb, fabs(rb[j])); nr.chk += rb[j]; }
+  }
+
+  // ---- rows: (lam, t) update or cold start, residuals, condensation terms ----
+  // one side of a row; returns G = lam/t and c = (lam t - lam r)/t  (mode-0 right-hand side)
+  auto side = [&](int slot, double sgn, double az, double bnd, double slack, double tinit, double& lam, double& G, double& c) {
+    double t;
+    if (first) { t = tinit; lam = mu0 / t; }
+    else {
+      lam = fmax(QF(iti, I_LAM + slot) + a * QF(st, I_LAM + slot), lam_min);
+      t = fmax(QF(iti, I_T + slot) + a * QF(st, I_T + slot), t_min);
+    }
+    QF(ito, I_LAM + slot) = lam; QF(ito, I_T + slot) = t;
+    const double r = t - (sgn * (az - bnd) + slack);
+    const double rm = lam * t;
+    const double it_ = 1.0 / t;
+    G = lam * it_;
+    c = (rm - lam * r) * it_;
+    nr.mu += rm; nr.chk += rm + r; nr.nm = fmax(nr.nm, fabs(rm)); nr.nd = fmax(nr.nd, fabs(r)); nr.cnt += 1;
+  };
+  double Gb[10], Gg[12];
+  // box rows
+#pragma unroll
+  for (int j = 0; j < 10; ++j) {
+    double tl = 0.0, tu = 0.0;
+    if (first) qs_zinit(blo[j], bhi[j], tl, tu);
+    double ll, lu, Gl, Gu, cl, cu;
+    side(j, 1.0, z[5 + j], blo[j], 0.0, tl, ll, Gl, cl);
+    side(QNR + j, -1.0, z[5 + j], bhi[j], 0.0, tu, lu, Gu, cu);
+    Gb[j] = Gl + Gu;
+    rg[5 + j] += lu - ll;
+    gd[5 + j] += cl - cu;
+  }
+  // torque rows
+#pragma unroll
+  for (int r = 0; r < 5; ++r) Gg[r] = 0.0;
+  if (F.tau) {
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {
+      double az = 0.0;
+#pragma unroll
+      for (int c = 0; c < 15; ++c) az += QF(rec, SMPC_REC_JTAU + r * 15 + c) * z[c];
+      const double v = QF(rec, SMPC_REC_TAU + r);
+      const double lo = P.tau_min[r] - v, hi = P.tau_max[r] - v;
+      double ll, lu, Gl, Gu, cl, cu;
+      side(10 + r, 1.0, az, lo, 0.0, fmax(thr0, az - lo), ll, Gl, cl);
+      side(QNR + 10 + r, -1.0, az, hi, 0.0, fmax(thr0, hi - az), lu, Gu, cu);
+      Gg[r] = Gl + Gu;
+      const double nu = lu - ll, gam = cl - cu;
+#pragma unroll
+      for (int c = 0; c < 15; ++c) { const double jv = QF(rec, SMPC_REC_JTAU + r * 15 + c); rg[c] += jv * nu; gd[c] += jv * gam; }
+    }
+  }
+  // capsule rows
+#pragma unroll
+  for (int p = 0; p < 6; ++p) Gg[5 + p] = 0.0;
+  if (F.dist) {
+#pragma unroll
+    for (int p = 0; p < 6; ++p) {
+      double az = 0.0;
+#pragma unroll
+      for (int c = 0; c < 5; ++c) az += QF(rec, SMPC_REC_JDIST + p * 5 + c) * z[5 + c];
+      const double v = QF(rec, SMPC_REC_DIST + p);
+      const double lo = P.pair_lo_ocp[p] - v, hi = P.pair_hi - v;
+      double ll, lu, Gl, Gu, cl, cu;
+      side(15 + p, 1.0, az, lo, 0.0, fmax(thr0, az - lo), ll, Gl, cl);
+      side(QNR + 15 + p, -1.0, az, hi, 0.0, fmax(thr0, hi - az), lu, Gu, cu);
+      Gg[5 + p] = Gl + Gu;
+      const double nu = lu - ll, gam = cl - cu;
+#pragma unroll
+      for (int c = 0; c < 5; ++c) { const double jv = QF(rec, SMPC_REC_JDIST + p * 5 + c); rg[5 + c] += jv * nu; gd[5 + c] += jv * gam; }
+    }
+  }
+  // viability row (may be soft)
+  Gg[11] = 0.0;
+  if (F.nn) {
+    double az = 0.0;
+#pragma unroll
+    for (int c = 0; c < 10; ++c) az += QF(rec, SMPC_REC_JNN + c) * z[5 + c];
+    const double v = QF(rec, SMPC_REC_NN);
+    const double lo = 0.0 - v, hi = 1e6 - v;
+    double sl[2] = {0.0, 0.0}, ls[2] = {0.0, 0.0}, ts[2] = {0.0, 0.0};
+    if (F.soft) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (first) { sl[h] = thr0; ls[h] = mu0 / thr0; ts[h] = thr0; }
+        else {
+          sl[h] = QF(iti, I_SLK + h) + a * QF(st, I_SLK + h);
+          ls[h] = fmax(QF(iti, I_SLK + 2 + h) + a * QF(st, I_SLK + 2 + h), lam_min);
+          ts[h] = fmax(QF(iti, I_SLK + 4 + h) + a * QF(st, I_SLK + 4 + h), t_min);
+        }
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) { QF(ito, I_SLK + h) = sl[h]; QF(ito, I_SLK + 2 + h) = ls[h]; QF(ito, I_SLK + 4 + h) = ts[h]; }
+    double ll, lu, Gl, Gu, cl, cu;
+    side(21, 1.0, az, lo, sl[0], fmax(thr0, az - lo), ll, Gl, cl);
+    side(QNR + 21, -1.0, az, hi, sl[1], fmax(thr0, hi - az), lu, Gu, cu);
+    if (F.soft) {
+      const double lam2[2] = {ll, lu};
+      double G2[2] = {Gl, Gu}, c2[2] = {cl, cu};
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const double rsl = ts[h] - sl[h];
+        const double rgs = F.zpen - lam2[h] - ls[h];
+        const double rms = ls[h] * ts[h];
+        const double its = 1.0 / ts[h];
+        const double Gs = ls[h] * its;
+        const double cs = (rms - ls[h] * rsl) * its;
+        const double Wl = 1.0 / (G2[h] + Gs);
+        c2[h] = c2[h] - G2[h] * Wl * (rgs + c2[h] + cs);
+        G2[h] = G2[h] * Gs * Wl;
+        nr.mu += rms; nr.chk += rms + rsl + rgs;
+        nr.nm = fmax(nr.nm, fabs(rms)); nr.nd = fmax(nr.nd, fabs(rsl)); nr.ng = fmax(nr.ng, fabs(rgs));
+        nr.cnt += 1;
+      }
+      Gl = G2[0]; Gu = G2[1]; cl = c2[0]; cu = c2[1];
+    }
+    Gg[11] = Gl + Gu;
+    const double nu = lu - ll, gam = cl - cu;
+#pragma unroll
+    for (int c = 0; c < 10; ++c) { const double jv = QF(rec, SMPC_REC_JNN + c); rg[5 + c] += jv * nu; gd[5 + c] += jv * gam; }
+  } else {
+#pragma unroll
+    for (int h = 0; h < 6; ++h) QF(ito, I_SLK + h) = 0.0;
+  }
+  if (k == N) {
+#pragma unroll
+    for (int i = 0; i < 5; ++i) { rg[i] = 0.0; gd[i] = 0.0; }
+  }
+#pragma unroll
+  for (int i = 0; i < 15; ++i) { nr.ng = fmax(nr.ng, fabs(rg[i])); nr.chk += rg[i]; QF(hc, H_GA + i) = rg[i] + gd[i]; }
+
+  // ---- condensed stage matrix  H + reg + C' Gam C  (packed lower triangle) ----
+  {
+    const double hu = (k == N) ? 1.0 : QF(rec, SMPC_REC_HU) + reg;
+    const double hq = QF(rec, SMPC_REC_HQ) + reg, hv = QF(rec, SMPC_REC_HV) + reg;
+#pragma unroll
+    for (int i = 0; i < 15; ++i) {
+      double acc[15];
+#pragma unroll
+      for (int c = 0; c <= i; ++c) {
+        double v = 0.0;
+        if (c == i) v = i < 5 ? hu : ((i < 10 ? hq : hv) + Gb[i >= 5 ? i - 5 : 0]);
+        if (i >= 5 && i < 10 && c >= 5) v += QF(rec, SMPC_REC_HQQ + tri(i - 5, c - 5));
+        acc[c] = v;
+      }
+      if (F.tau) {
+#pragma unroll
+        for (int r = 0; r < 5; ++r) {
+          const double w = Gg[r] * QF(rec, SMPC_REC_JTAU + r * 15 + i);
+#pragma unroll
+          for (int c = 0; c <= i; ++c) acc[c] += w * QF(rec, SMPC_REC_JTAU + r * 15 + c);
+        }
+      }
+      if (F.dist && i >= 5 && i < 10) {
+#pragma unroll
+        for (int p = 0; p < 6; ++p) {
+          const double w = Gg[5 + p] * QF(rec, SMPC_REC_JDIST + p * 5 + i - 5);
+#pragma unroll
+          for (int c = 5; c <= i; ++c) acc[c] += w * QF(rec, SMPC_REC_JDIST + p * 5 + c - 5);
+        }
+      }
+      if (F.nn && i >= 5) {
+        const double w = Gg[11] * QF(rec, SMPC_REC_JNN + i - 5);
+#pragma unroll
+        for (int c = 5; c <= i; ++c) acc[c] += w * QF(rec, SMPC_REC_JNN + c - 5);
+      }
+#pragma unroll
+      for (int c = 0; c <= i; ++c) QF(hc, H_M + tri(i, c)) = acc[c];
+    }
+  }
+  double* res = q.res + qs_blk(tile, N, k, NRES, lane);
+  QF(res, R_NG) = nr.ng; QF(res, R_NB) = nr.nb; QF(res, R_ND) = nr.nd; QF(res, R_NM) = nr.nm;
+  QF(res, R_MU) = nr.mu; QF(res, R_CHK) = nr.chk; QF(res, R_CNT) = (double)nr.cnt;
+}
+
+// ================================================================================================================
+// ctl: residual norms of the new iterate, exit tests (same control flow as the oracle's QpIpm::solve), result.
+// thread = problem.  Returns true when the problem stays active.
+// ================================================================================================================
+SMPC_HD bool qs_ctl(const smpc_problem_t& P, const QsBufs& q, int tile, int lane, int kk, double* xt, double* ut, int32_t* status,
+                    int32_t* qp_iter, int32_t* qp_status, double* qp_res) {
+  const int N = q.N;
+  int32_t* pi = q.pi + qs_pb(tile, NPI, lane);
+  if (!QF(pi, J_ACT)) return false;
+  double* pd = q.pd + qs_pb(tile, NPD, lane);
+  double ng = 0.0, nb = 0.0, nd = 0.0, nm = 0.0, mu = 0.0, chk = 0.0, cnt = 0.0;
+  for (int k = 0; k <= N; ++k) {
+    const double* res = q.res + qs_blk(tile, N, k, NRES, lane);
+    ng = fmax(ng, QF(res, R_NG)); nb = fmax(nb, QF(res, R_NB)); nd = fmax(nd, QF(res, R_ND)); nm = fmax(nm, QF(res, R_NM));
+    mu += QF(res, R_MU); chk += QF(res, R_CHK); cnt += QF(res, R_CNT);
+  }
+  if (kk == 0) QF(pi, J_NC) = (int)(cnt + 0.5);
+  const int nc = QF(pi, J_NC);
+  const double r0 = (chk != chk) ? chk : ng;
+  mu = mu / nc;
+  QF(pd, D_RES + 0) = r0; QF(pd, D_RES + 1) = nb; QF(pd, D_RES + 2) = nd; QF(pd, D_RES + 3) = nm; QF(pd, D_MU) = mu;
+  const bool nan = (r0 != r0) || (nb != nb) || (nd != nd) || (nm != nm);
+  const bool unconv = (r0 > P.qp_tol_stat) || (nb > P.qp_tol_eq) || (nd > P.qp_tol_ineq) || (nm > P.qp_tol_comp);
+  bool done = false;
+  if (nan && kk > 0) done = true;
+  else if (!unconv && !nan) done = true;
+  else if (kk >= P.qp_iter_max) done = true;
+  else if (!(QF(pd, D_ALPHA) > P.qp_alpha_min)) done = true;
+  if (!done) return true;
+  int qst;
+  if (nan) qst = 3; else if (!unconv) qst = 0; else if (kk >= P.qp_iter_max) qst = 1; else qst = 2;
+  QF(pi, J_ACT) = 0; QF(pi, J_ITER) = kk; QF(pi, J_QST) = qst; QF(pi, J_ITBUF) = kk & 1;
+  // ---- full step and status mapping (acados SQP_RTI: QP success / max-iter -> step taken, else QP failure) ----
+  const int b = QF(pi, J_B);
+  const bool ok = (qst == 0 || qst == 1);
+  bool znan = false;
+  double* xtb = xt + (size_t)b * (N + 1) * NX;
+  double* utb = ut + (size_t)b * N * NU;
+  for (int k = 0; k <= N; ++k) {
+    const double* it = q.it[kk & 1] + qs_blk(tile, N, k, NIT, lane);
+    const double* rec = q.rec + qs_blk(tile, N, k, REC, lane);
+    for (int j = 0; j < NZ; ++j) {
+      if (j < NU && k == N) continue;
+      const double z = ok ? QF(it, I_Z + j) : 0.0;
+      znan |= (z != z);
+      if (j < NU) utb[k * NU + j] = QF(rec, SMPC_REC_U + j) + z;
+      else xtb[k * NX + j - NU] = QF(rec, SMPC_REC_X + j - NU) + z;
+    }
+  }
+  status[b] = ok ? (znan ? 1 : 0) : 4;
+  qp_iter[b] = kk;
+  qp_status[b] = qst;
+  for (int c = 0; c < 4; ++c) qp_res[(size_t)b * 5 + c] = QF(pd, D_RES + c);
+  qp_res[(size_t)b * 5 + 4] = mu;
+  return false;
+}
+
+// ================================================================================================================
+// Riccati sweeps.   thread = problem, walking the stages.
+// Y = [B A]' P [B A] entry (i, c) of the 15x15 matrix, from the packed 10x10 P (rows/cols: q 0-4, v 5-9).
+// ================================================================================================================
+template <class PF>
+SMPC_HD double qs_y(int i, int c, double dt, double a2, PF Pn) {
+  const int gi = i / 5, gc = c / 5, ii = i % 5, ic = c % 5;
+  // coefficient of q+ / v+ for the variable groups u, q, v
+  const double aqi = gi == 0 ? a2 : (gi == 1 ? 1.0 : dt), avi = gi == 0 ? dt : (gi == 1 ? 0.0 : 1.0);
+  const double aqc = gc == 0 ? a2 : (gc == 1 ? 1.0 : dt), avc = gc == 0 ? dt : (gc == 1 ? 0.0 : 1.0);
+  double y = 0.0;
+  y += (aqi * aqc) * Pn(trs(ii, ic));               // Pqq
+  if (gc != 1) y += (aqi * avc) * Pn(tri(5 + ic, ii));   // Pqv[ii][ic] = P[ii][5+ic]
+  if (gi != 1) y += (avi * aqc) * Pn(tri(5 + ii, ic));   // Pvq[ii][ic] = P[5+ii][ic]
+  if (gi != 1 && gc != 1) y += (avi * avc) * Pn(trs(5 + ii, 5 + ic));
+  return y;
+}
+
+// ric1: backward factorisation with the affine gradient, stage-0 solve, forward substitution of the affine direction.
+// psm: scratch for two packed P matrices + p, [2][65][TL] doubles, indexed like every other block (lane already added).
+SMPC_HD void qs_ric1(const smpc_problem_t& P, const QsBufs& q, int tile, int lane, double* psm) {
+  const int N = q.N;
+  const int32_t* pi = q.pi + qs_pb(tile, NPI, lane);
+  if (!QF(pi, J_ACT)) return;
+  double* pd = q.pd + qs_pb(tile, NPD, lane);
+  const double dt = P.dt, a2 = 0.5 * P.dt * P.dt;
+  double dx[10];
+  for (int k = N; k >= 0; --k) {
+    const double* hc = q.hc + qs_blk(tile, N, k, NHC, lane);
+    double* fac = q.fac + qs_blk(tile, N, k, NFAC, lane);
+    double* pcur = psm + (size_t)(k & 1) * 65 * TL;            // P_k, p_k
+    const double* pnx = psm + (size_t)((k & 1) ^ 1) * 65 * TL; // P_{k+1}, p_{k+1}
+    auto Pn = [&](int idx) { return QF(pnx, idx); };
+    // gradient: g = ga + [B A]' (P_{k+1} rb + p_{k+1})
+    double g[15];
+#pragma unroll
+    for (int i = 0; i < 15; ++i) g[i] = QF(hc, H_GA + i);
+    if (k < N) {
+      double rb[10], y[10];
+#pragma unroll
+      for (int j = 0; j < 10; ++j) rb[j] = QF(hc, H_RB + j);
+#pragma unroll
+      for (int i = 0; i < 10; ++i) {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < 10; ++j) s += Pn(trs(i, j)) * rb[j];
+        QF(fac, F_WV + i) = s;
+        y[i] = s + QF(pnx, 55 + i);
+      }
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        g[j] += a2 * y[j] + dt * y[5 + j];
+        g[5 + j] += y[j];
+        g[10 + j] += dt * y[j] + y[5 + j];
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 5; ++i) g[i] = 0.0;
+    }
+    // panel: columns 0..4 of the stage matrix, rows 0..14 (lower part)
+    double pan[15][5];
+#pragma unroll
+    for (int i = 0; i < 15; ++i)
+#pragma unroll
+      for (int j = 0; j < 5; ++j)
+        if (j <= i) pan[i][j] = QF(hc, H_M + tri(i, j)) + (k < N ? qs_y(i, j, dt, a2, Pn) : 0.0);
+    // eliminate the control columns in place (LDL' form; a non-positive pivot zeroes the column, as BLASFEO dpotrf and
+    // the oracle).  Rows are walked downwards-to-upwards so that the un-scaled column entries pan[c][j] of the rows
+    // above are still available; afterwards pan[i][j] holds the multiplier t_ij (i > j) and pan[j][j] = 1/d_j.
+    double dd[5];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      const double d = pan[j][j];
+      const double invd = d > 0.0 ? 1.0 / d : 0.0;
+      dd[j] = d > 0.0 ? d : 0.0;
+#pragma unroll
+      for (int i = 14; i > j; --i) {
+        const double t = pan[i][j] * invd;
+        g[i] -= t * g[j];
+#pragma unroll
+        for (int c = j + 1; c < 5; ++c)
+          if (c <= i) pan[i][c] -= t * pan[c][j];
+        pan[i][j] = t;
+      }
+      pan[j][j] = invd;
+    }
+#pragma unroll
+    for (int i = 0; i < 15; ++i)
+#pragma unroll
+      for (int j = 0; j < 5; ++j)
+        if (j <= i) QF(fac, F_T + i * 5 + j) = pan[i][j];
+#pragma unroll
+    for (int i = 0; i < 15; ++i) QF(fac, F_LP + i) = g[i];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) QF(pcur, 55 + i) = g[5 + i];
+    // P_k = trailing block - T_x D T_x'
+#pragma unroll
+    for (int i = 5; i < 15; ++i) {
+      double sd[5];
+#pragma unroll
+      for (int j = 0; j < 5; ++j) sd[j] = pan[i][j] * dd[j];
+#pragma unroll
+      for (int c = 5; c <= i; ++c) {
+        double v = QF(hc, H_M + tri(i, c)) + (k < N ? qs_y(i, c, dt, a2, Pn) : 0.0);
+#pragma unroll
+        for (int j = 0; j < 5; ++j) v -= sd[j] * pan[c][j];
+        QF(pcur, tri(i - 5, c - 5)) = v;
+        QF(fac, F_P + tri(i - 5, c - 5)) = v;
+      }
+    }
+    if (k == 0) {
+      // factorise P_0 (kept per problem for the re-solves) and solve P_0 dx_0 = -p_0
+      double m[10][10], gg[10];
+#pragma unroll
+      for (int i = 0; i < 10; ++i) {
+        gg[i] = g[5 + i];
+#pragma unroll
+        for (int c = 0; c <= i; ++c) m[i][c] = QF(pcur, tri(i, c));
+      }
+#pragma unroll
+      for (int j = 0; j < 10; ++j) {
+        const double d = m[j][j];
+        const double invd = d > 0.0 ? 1.0 / d : 0.0;
+        QF(pd, D_T0 + tri(j, j)) = invd;
+        m[j][j] = invd;
+#pragma unroll
+        for (int i = 9; i > j; --i) {       // bottom-up: the rows above still hold their un-scaled column entries
+          const double t = m[i][j] * invd;
+          gg[i] -= t * gg[j];
+#pragma unroll
+          for (int c = j + 1; c <= i; ++c) m[i][c] -= t * m[c][j];
+          m[i][j] = t;
+          QF(pd, D_T0 + tri(i, j)) = t;
+        }
+      }
+#pragma unroll
+      for (int i = 9; i >= 0; --i) {
+        double acc = m[i][i] * gg[i];
+#pragma unroll
+        for (int c = i + 1; c < 10; ++c) acc += m[c][i] * dx[c];
+        dx[i] = m[i][i] > 0.0 ? -acc : 0.0;
+      }
+    }
+  }
+  // forward substitution (affine direction)
+  for (int k = 0; k <= N; ++k) {
+    const double* fac = q.fac + qs_blk(tile, N, k, NFAC, lane);
+    const double* hc = q.hc + qs_blk(tile, N, k, NHC, lane);
+    double* st = q.st + qs_blk(tile, N, k, NIT, lane);
+    double du[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) du[i] = 0.0;
+    if (k < N) {
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        double w = QF(fac, F_T + i * 5 + i) * QF(fac, F_LP + i);
+#pragma unroll
+        for (int r = 0; r < 10; ++r) w += QF(fac, F_T + (5 + r) * 5 + i) * dx[r];
+        du[i] = -w;
+      }
+#pragma unroll
+      for (int c = 4; c >= 1; --c)
+#pragma unroll
+        for (int i = 0; i < c; ++i) du[i] -= QF(fac, F_T + c * 5 + i) * du[c];
+    }
+#pragma unroll
+    for (int i = 0; i < 5; ++i) QF(st, I_Z + i) = du[i];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) QF(st, I_Z + 5 + i) = dx[i];
+    if (k < N) {
+      double nx[10];
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        nx[j] = dx[j] + dt * dx[5 + j] + a2 * du[j] + QF(hc, H_RB + j);
+        nx[5 + j] = dx[5 + j] + dt * du[j] + QF(hc, H_RB + 5 + j);
+      }
+#pragma unroll
+      for (int j = 0; j < 10; ++j) dx[j] = nx[j];
+    }
+  }
+}
+
+// reduction of the step-length partials of one problem
+SMPC_HD void qs_reduce_step(const QsBufs& q, int tile, int lane, double& alpha, double& s_lin, double& s_quad) {
+  const int N = q.N;
+  alpha = 1.0; s_lin = 0.0; s_quad = 0.0;
+  for (int k = 0; k <= N; ++k) {
+    const double* stp = q.stp + qs_blk(tile, N, k, NSTP, lane);
+    alpha = fmin(alpha, QF(stp, S_ALPHA)); s_lin += QF(stp, S_LIN); s_quad += QF(stp, S_QUAD);
+  }
+}
+
+// ric2: vector-only backward sweep for the corrector (mode 1) / centering (mode 2) right-hand side, stage-0 solve,
+// forward substitution with the multiplier steps.  In mode 1 the prologue turns the affine step statistics into sigma.
+SMPC_HD void qs_ric2(const smpc_problem_t& P, const QsBufs& q, int tile, int lane, int mode) {
+  const int N = q.N;
+  const int32_t* pi = q.pi + qs_pb(tile, NPI, lane);
+  if (!QF(pi, J_ACT)) return;
+  if (mode == 2 && !QF(pi, J_REDO)) return;
+  double* pd = q.pd + qs_pb(tile, NPD, lane);
+  const double dt = P.dt, a2 = 0.5 * P.dt * P.dt;
+  double sigmu;
+  if (mode == 1) {
+    double alpha, s_lin, s_quad;
+    qs_reduce_step(q, tile, lane, alpha, s_lin, s_quad);
+    const double mu = QF(pd, D_MU);
+    const double mu_aff = mu + (alpha * s_lin + alpha * alpha * s_quad) / QF(pi, J_NC);
+    double sigma = mu_aff / mu; sigma = sigma * sigma * sigma;
+    sigmu = sigma * mu;
+    QF(pd, D_MUAFF) = mu_aff; QF(pd, D_SIGMU) = sigmu;
+  } else sigmu = QF(pd, D_SIGMU);
+  double pn[10], dx[10];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) pn[i] = 0.0;
+  for (int k = N; k >= 0; --k) {
+    const double* hc = q.hc + qs_blk(tile, N, k, NHC, lane);
+    const double* vv = q.v + qs_blk(tile, N, k, NV, lane);
+    double* fac = q.fac + qs_blk(tile, N, k, NFAC, lane);
+    double g[15];
+#pragma unroll
+    for (int i = 0; i < 15; ++i) g[i] = QF(hc, H_GA + i) + (mode == 1 ? QF(vv, V_1 + i) : 0.0) - sigmu * QF(vv, V_2 + i);
+    if (k < N) {
+      double y[10];
+#pragma unroll
+      for (int i = 0; i < 10; ++i) y[i] = QF(fac, F_WV + i) + pn[i];
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        g[j] += a2 * y[j] + dt * y[5 + j];
+        g[5 + j] += y[j];
+        g[10 + j] += dt * y[j] + y[5 + j];
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 5; ++i) g[i] = 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < 5; ++j)
+#pragma unroll
+      for (int i = j + 1; i < 15; ++i) g[i] -= QF(fac, F_T + i * 5 + j) * g[j];
+#pragma unroll
+    for (int i = 0; i < 15; ++i) QF(fac, F_LP + i) = g[i];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) pn[i] = g[5 + i];
+    if (k == 0) {
+#pragma unroll
+      for (int j = 0; j < 10; ++j)
+#pragma unroll
+        for (int i = j + 1; i < 10; ++i) pn[i] -= QF(pd, D_T0 + tri(i, j)) * pn[j];
+#pragma unroll
+      for (int i = 9; i >= 0; --i) {
+        const double invd = QF(pd, D_T0 + tri(i, i));
+        double acc = invd * pn[i];
+#pragma unroll
+        for (int c = i + 1; c < 10; ++c) acc += QF(pd, D_T0 + tri(c, i)) * dx[c];
+        dx[i] = invd > 0.0 ? -acc : 0.0;
+      }
+    }
+  }
+  for (int k = 0; k <= N; ++k) {
+    const double* fac = q.fac + qs_blk(tile, N, k, NFAC, lane);
+    const double* hc = q.hc + qs_blk(tile, N, k, NHC, lane);
+    double* st = q.st + qs_blk(tile, N, k, NIT, lane);
+    // multiplier step of the link k-1 -> k:  dpi = P_k dx_k + p_k
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+      double s = 0.0;
+      if (k > 0) {
+        s = QF(fac, F_LP + 5 + i);
+#pragma unroll
+        for (int j = 0; j < 10; ++j) s += QF(fac, F_P + trs(i, j)) * dx[j];
+      }
+      QF(st, I_PIM + i) = s;
+    }
+    double du[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) du[i] = 0.0;
+    if (k < N) {
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        double w = QF(fac, F_T + i * 5 + i) * QF(fac, F_LP + i);
+#pragma unroll
+        for (int r = 0; r < 10; ++r) w += QF(fac, F_T + (5 + r) * 5 + i) * dx[r];
+        du[i] = -w;
+      }
+#pragma unroll
+      for (int c = 4; c >= 1; --c)
+#pragma unroll
+        for (int i = 0; i < c; ++i) du[i] -= QF(fac, F_T + c * 5 + i) * du[c];
+    }
+#pragma unroll
+    for (int i = 0; i < 5; ++i) QF(st, I_Z + i) = du[i];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) QF(st, I_Z + 5 + i) = dx[i];
+    if (k < N) {
+      double nx[10];
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        nx[j] = dx[j] + dt * dx[5 + j] + a2 * du[j] + QF(hc, H_RB + j);
+        nx[5 + j] = dx[5 + j] + dt * du[j] + QF(hc, H_RB + 5 + j);
+      }
+#pragma unroll
+      for (int j = 0; j < 10; ++j) dx[j] = nx[j];
+    }
+  }
+}
+
+// ================================================================================================================
+// step: recover (dlam, dt, dslack) of every row from dz, step-length partials.   thread = (problem, stage)
+//   mode 0 (affine): stores dlam*dt per slot and the corrector gradient terms v1, v2
+//   mode 1 / 2 (corrector / centering): stores the step
+// ================================================================================================================
+SMPC_HD void qs_step(const smpc_problem_t& P, const QsBufs& q, int tile, int lane, int k, int kk, int mode) {
+  const int N = q.N;
+  const int32_t* pi = q.pi + qs_pb(tile, NPI, lane);
+  if (!QF(pi, J_ACT)) return;
+  if (mode == 2 && !QF(pi, J_REDO)) return;
+  const double* pd = q.pd + qs_pb(tile, NPD, lane);
+  const int rrec = QF(pi, J_R);
+  const double sigmu = mode == 0 ? 0.0 : QF(pd, D_SIGMU);
+  const double* rec = q.rec + qs_blk(tile, N, k, REC, lane);
+  const double* it = q.it[kk & 1] + qs_blk(tile, N, k, NIT, lane);
+  double* st = q.st + qs_blk(tile, N, k, NIT, lane);
+  double* prod = q.prod + qs_blk(tile, N, k, NPROD, lane);
+  const StageFlags F = qs_flags(P, k);
+  double z[15], dz[15];
+#pragma unroll
+  for (int i = 0; i < 15; ++i) { z[i] = QF(it, I_Z + i); dz[i] = QF(st, I_Z + i); }
+  double alpha = 1.0, s_lin = 0.0, s_quad = 0.0;
+  double v1[15], v2[15];
+#pragma unroll
+  for (int i = 0; i < 15; ++i) { v1[i] = 0.0; v2[i] = 0.0; }
+
+  // one side of a hard row.  e1 / e2: this side's contribution to the corrector terms (signed)
+  auto side = [&](int slot, double sgn, double az, double adz, double bnd, double& e1, double& e2) {
+    const double lam = QF(it, I_LAM + slot), t = QF(it, I_T + slot);
+    const double r = t - sgn * (az - bnd);
+    const double pr = mode == 1 ? QF(prod, slot) : 0.0;
+    const double rm = qs_rm(mode, lam * t, pr, sigmu);
+    const double it_ = 1.0 / t;
+    const double dtt = sgn * adz - r;
+    const double dl = -(rm + lam * dtt) * it_;
+    if (dl < 0.0) alpha = fmin(alpha, -lam / dl);
+    if (dtt < 0.0) alpha = fmin(alpha, -t / dtt);
+    s_lin += lam * dtt + t * dl; s_quad += dl * dtt;
+    if (mode == 0) { const double pp = dl * dtt; QF(prod, slot) = pp; e1 += sgn * pp * it_; e2 += sgn * it_; }
+    else { QF(st, I_LAM + slot) = dl; QF(st, I_T + slot) = dtt; }
+  };
+  // box rows
+#pragma unroll
+  for (int j = 0; j < 10; ++j) {
+    double lo, hi;
+    qs_box(P, q, tile, lane, k, j, QF(pd, D_X0 + j), rrec, lo, hi);
+    double e1 = 0.0, e2 = 0.0;
+    side(j, 1.0, z[5 + j], dz[5 + j], lo, e1, e2);
+    side(QNR + j, -1.0, z[5 + j], dz[5 + j], hi, e1, e2);
+    v1[5 + j] += e1; v2[5 + j] += e2;
+  }
+  if (F.tau) {
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {
+      double az = 0.0, adz = 0.0;
+#pragma unroll
+      for (int c = 0; c < 15; ++c) { const double jv = QF(rec, SMPC_REC_JTAU + r * 15 + c); az += jv * z[c]; adz += jv * dz[c]; }
+      const double v = QF(rec, SMPC_REC_TAU + r);
+      double e1 = 0.0, e2 = 0.0;
+      side(10 + r, 1.0, az, adz, P.tau_min[r] - v, e1, e2);
+      side(QNR + 10 + r, -1.0, az, adz, P.tau_max[r] - v, e1, e2);
+      if (mode == 0) {
+#pragma unroll
+        for (int c = 0; c < 15; ++c) { const double jv = QF(rec, SMPC_REC_JTAU + r * 15 + c); v1[c] += jv * e1; v2[c] += jv * e2; }
+      }
+    }
+  } else if (mode != 0) {
+#pragma unroll
+    for (int r = 0; r < 5; ++r) { QF(st, I_LAM + 10 + r) = 0.0; QF(st, I_T + 10 + r) = 0.0; QF(st, I_LAM + QNR + 10 + r) = 0.0; QF(st, I_T + QNR + 10 + r) = 0.0; }
+  }
+  if (F.dist) {
+#pragma unroll
+    for (int p = 0; p < 6; ++p) {
+      double az = 0.0, adz = 0.0;
+#pragma unroll
+      for (int c = 0; c < 5; ++c) { const double jv = QF(rec, SMPC_REC_JDIST + p * 5 + c); az += jv * z[5 + c]; adz += jv * dz[5 + c]; }
+      const double v = QF(rec, SMPC_REC_DIST + p);
+      double e1 = 0.0, e2 = 0.0;
+      side(15 + p, 1.0, az, adz, P.pair_lo_ocp[p] - v, e1, e2);
+      side(QNR + 15 + p, -1.0, az, adz, P.pair_hi - v, e1, e2);
+      if (mode == 0) {
+#pragma unroll
+        for (int c = 0; c < 5; ++c) { const double jv = QF(rec, SMPC_REC_JDIST + p * 5 + c); v1[5 + c] += jv * e1; v2[5 + c] += jv * e2; }
+      }
+    }
+  } else if (mode != 0) {
+#pragma unroll
+    for (int p = 0; p < 6; ++p) { QF(st, I_LAM + 15 + p) = 0.0; QF(st, I_T + 15 + p) = 0.0; QF(st, I_LAM + QNR + 15 + p) = 0.0; QF(st, I_T + QNR + 15 + p) = 0.0; }
+  }
+  if (F.nn) {
+    double az = 0.0, adz = 0.0;
+#pragma unroll
+    for (int c = 0; c < 10; ++c) { const double jv = QF(rec, SMPC_REC_JNN + c); az += jv * z[5 + c]; adz += jv * dz[5 + c]; }
+    const double v = QF(rec, SMPC_REC_NN);
+    double e1 = 0.0, e2 = 0.0;
+    if (!F.soft) {
+      side(21, 1.0, az, adz, 0.0 - v, e1, e2);
+      side(QNR + 21, -1.0, az, adz, 1e6 - v, e1, e2);
+      if (mode != 0) {
+#pragma unroll
+        for (int h = 0; h < 6; ++h) QF(st, I_SLK + h) = 0.0;
+      }
+    } else {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int slot = h * QNR + 21;
+        const double sgn = h ? -1.0 : 1.0, bnd = h ? 1e6 - v : 0.0 - v;
+        const double lam = QF(it, I_LAM + slot), t = QF(it, I_T + slot);
+        const double sl = QF(it, I_SLK + h), ls = QF(it, I_SLK + 2 + h), ts = QF(it, I_SLK + 4 + h);
+        const double r = t - (sgn * (az - bnd) + sl);
+        const double pr = mode == 1 ? QF(prod, slot) : 0.0, spr = mode == 1 ? QF(prod, 44 + h) : 0.0;
+        const double rm = qs_rm(mode, lam * t, pr, sigmu);
+        const double it_ = 1.0 / t;
+        const double G = lam * it_;
+        const double c = (rm - lam * r) * it_;
+        const double rsl = ts - sl;
+        const double rgs = F.zpen - lam - ls;
+        const double rms = qs_rm(mode, ls * ts, spr, sigmu);
+        const double its = 1.0 / ts;
+        const double Gs = ls * its;
+        const double cs = (rms - ls * rsl) * its;
+        const double W = 1.0 / (G + Gs);
+        const double ds = -(rgs + c + cs + sgn * G * adz) * W;
+        const double dts = ds - rsl;
+        const double dls = -(rms + ls * dts) * its;
+        if (dls < 0.0) alpha = fmin(alpha, -ls / dls);
+        if (dts < 0.0) alpha = fmin(alpha, -ts / dts);
+        s_lin += ls * dts + ts * dls; s_quad += dls * dts;
+        const double dtt = sgn * adz + ds - r;
+        const double dl = -(rm + lam * dtt) * it_;
+        if (dl < 0.0) alpha = fmin(alpha, -lam / dl);
+        if (dtt < 0.0) alpha = fmin(alpha, -t / dtt);
+        s_lin += lam * dtt + t * dl; s_quad += dl * dtt;
+        if (mode == 0) {
+          const double pp = dl * dtt, sp = dls * dts;
+          QF(prod, slot) = pp; QF(prod, 44 + h) = sp;
+          // d cc = (1 - G W) d c - G W d cs  with  d c = (pp - sigmu)/t,  d cs = (sp - sigmu)/ts
+          const double gw = G * W;
+          e1 += sgn * ((1.0 - gw) * pp * it_ - gw * sp * its);
+          e2 += sgn * ((1.0 - gw) * it_ - gw * its);
+        } else {
+          QF(st, I_LAM + slot) = dl; QF(st, I_T + slot) = dtt;
+          QF(st, I_SLK + h) = ds; QF(st, I_SLK + 2 + h) = dls; QF(st, I_SLK + 4 + h) = dts;
+        }
+      }
+    }
+    if (mode == 0) {
+#pragma unroll
+      for (int c = 0; c < 10; ++c) { const double jv = QF(rec, SMPC_REC_JNN + c); v1[5 + c] += jv * e1; v2[5 + c] += jv * e2; }
+    }
+  } else if (mode != 0) {
+    QF(st, I_LAM + 21) = 0.0; QF(st, I_T + 21) = 0.0; QF(st, I_LAM + QNR + 21) = 0.0; QF(st, I_T + QNR + 21) = 0.0;
+#pragma unroll
+    for (int h = 0; h < 6; ++h) QF(st, I_SLK + h) = 0.0;
+  }
+  if (mode == 0) {
+    double* vv = q.v + qs_blk(tile, N, k, NV, lane);
+    if (k == N) {
+#pragma unroll
+      for (int i = 0; i < 5; ++i) { v1[i] = 0.0; v2[i] = 0.0; }
+    }
+#pragma unroll
+    for (int i = 0; i < 15; ++i) { QF(vv, V_1 + i) = v1[i]; QF(vv, V_2 + i) = v2[i]; }
+  }
+  double* stp = q.stp + qs_blk(tile, N, k, NSTP, lane);
+  QF(stp, S_ALPHA) = alpha; QF(stp, S_LIN) = s_lin; QF(stp, S_QUAD) = s_quad;
+}
+
+// ================================================================================================================
+// red: step length of the corrector; conditional predictor-corrector (fall back to pure centering when the corrected
+// step would more than double mu_aff).   thread = problem.   after_redo: second call, for the problems that re-solved.
+// ================================================================================================================
+SMPC_HD void qs_red(const smpc_problem_t& P, const QsBufs& q, int tile, int lane, bool after_redo) {
+  int32_t* pi = q.pi + qs_pb(tile, NPI, lane);
+  if (!QF(pi, J_ACT)) return;
+  if (after_redo && !QF(pi, J_REDO)) return;
+  double* pd = q.pd + qs_pb(tile, NPD, lane);
+  double alpha, s_lin, s_quad;
+  qs_reduce_step(q, tile, lane, alpha, s_lin, s_quad);
+  int redo = 0;
+  if (!after_redo && P.qp_cond_pred_corr) {
+    const double mu_corr = QF(pd, D_MU) + (alpha * s_lin + alpha * alpha * s_quad) / QF(pi, J_NC);
+    if (mu_corr > 2.0 * QF(pd, D_MUAFF)) redo = 1;
+  }
+  QF(pi, J_REDO) = redo;
+  QF(pd, D_ALPHA) = alpha;
+  QF(pd, D_STEP) = 0.995 * alpha;
+}
+
+// per-problem initialisation of one solve.   thread = problem (lane of a tile; b = 32 tile + lane may be >= B: padding)
+SMPC_HD void qs_init(const QsBufs& q, int tile, int lane, int B, const double* x0, const int32_t* r, const uint8_t* act) {
+  const int b = tile * TL + lane;
+  int32_t* pi = q.pi + qs_pb(tile, NPI, lane);
+  double* pd = q.pd + qs_pb(tile, NPD, lane);
+  const bool on = b < B && (!act || act[b]);
+  QF(pi, J_ACT) = on ? 1 : 0; QF(pi, J_ITER) = 0; QF(pi, J_QST) = 0; QF(pi, J_REDO) = 0; QF(pi, J_NC) = 1; QF(pi, J_ITBUF) = 0;
+  QF(pi, J_R) = b < B ? r[b] : 0; QF(pi, J_B) = b;
+  for (int j = 0; j < NX; ++j) QF(pd, D_X0 + j) = b < B ? x0[(size_t)b * NX + j] : 0.0;
+  QF(pd, D_MU) = 0.0; QF(pd, D_MUAFF) = 0.0; QF(pd, D_SIGMU) = 0.0; QF(pd, D_ALPHA) = 1.0; QF(pd, D_STEP) = 0.0;
+}
+
+// Host-side sequencing of one batched solve; BK launches the phases (CUDA kernels in qp.cu, plain loops in tests/emu).
+// sync(n_active, n_redo) is the one host round trip per IPM iteration.
+template <class BK>
+int qs_drive(BK& bk) {
+  bk.init();
+  int kk = 0;
+  bk.prep(0);
+  for (;;) {
+    bk.ctl(kk);
+    bk.ric1();
+    bk.step(kk, 0);
+    bk.ric2(1);
+    bk.step(kk, 1);
+    bk.red(false);
+    int n_active = 0, n_redo = 0;
+    bk.sync(n_active, n_redo);
+    if (n_active == 0) break;
+    if (n_redo > 0) { bk.ric2(2); bk.step(kk, 2); bk.red(true); }
+    ++kk;
+    bk.prep(kk);
+  }
+  return kk;
+}
+
+}  // namespace smpc

@@ -6,13 +6,10 @@
 
 #include "../../safe_mpc_b200/csrc/dev_model.cuh"
 #ifdef EMU_QP
-#include <ucontext.h>
-
 #include <cstdio>
 #include <cstdlib>
-#include <deque>
 
-#include "../../safe_mpc_b200/csrc/qp_warp.cuh"
+#include "../../safe_mpc_b200/csrc/qp_split.cuh"
 #endif
 
 using namespace smpc;
@@ -47,146 +44,90 @@ int emu_checks(const smpc_problem_t* P, int n, const double* x, int* in_bounds, 
 #ifdef EMU_QP
 namespace {
 // ----------------------------------------------------------------------------------------------------------------
-// Host stand-in of a warp: 32 cooperative fibers (ucontext) and a barrier.  Every warp primitive of the device policy
-// (shuffles, __syncwarp, staged bulk copies) is emulated with exchanges through a shared array between barriers.
-// Copy timing is adversarial on purpose: with lazy = 1 a staged load lands only when it is waited for and a staged
-// store leaves only when it is retired, with lazy = 0 loads land at issue -- so both premature reads of a staging
-// buffer and premature reuse of a buffer show up as wrong numbers in the parity test.
+// Host stand-in of the kernel launches of qp.cu: every phase of the split IPM (qp_split.cuh) is run as plain loops
+// over (tile, stage, lane) in a caller-chosen order (ascending / descending), so that a phase that reads what
+// another work item of the same phase writes shows up as an order-dependent result in the parity test.
 // ----------------------------------------------------------------------------------------------------------------
-struct FiberWarp;
-struct Shared {
-  ucontext_t main_ctx, ctx[32];
-  std::vector<char> stacks;
-  int cur = 0, arrived = 0, done = 0;
-  unsigned gen = 0;
-  double xd[32];
-  int xi[32];
-  std::vector<double> smem;
-  struct Copy { double* dst; const double* src; int n; };
-  std::vector<Copy> pend_load[2];
-  std::deque<Copy> pend_store;
-  int lazy = 0;
-  bool finished[32];
-  void (*body)(FiberWarp&) = nullptr;
-  void* user = nullptr;
-};
-
-struct FiberWarp {
-  Shared* sh;
-  int ln;
-  int lane() const { return ln; }
-  double* scratch() { return sh->smem.data() + 2 * QW_IN + 2 * QW_OUT; }
-  double* inbuf(int b) { return sh->smem.data() + b * QW_IN; }
-  double* outbuf(int b) { return sh->smem.data() + 2 * QW_IN + b * QW_OUT; }
-  void yield() {
-    int nxt = sh->cur;
-    for (int n = 0; n < 32; ++n) { nxt = (nxt + 1) & 31; if (!sh->finished[nxt]) break; }
-    if (nxt == sh->cur) return;
-    const int me = sh->cur;
-    sh->cur = nxt;
-    swapcontext(&sh->ctx[me], &sh->ctx[nxt]);
+struct HostBackend {
+  const smpc_problem_t& P;
+  QsBufs q;
+  int B, T, N, order;
+  const double* x0; const int32_t* r; const uint8_t* act;
+  double *xt, *ut; int32_t *status, *qp_iter, *qp_status; double* qp_res;
+  std::vector<double> psm;
+  int n_active = 0;
+  template <class F> void each_stage(F f) {
+    for (int t = 0; t < T; ++t)
+      for (int kx = 0; kx <= N; ++kx) {
+        const int k = order ? N - kx : kx;
+        for (int lx = 0; lx < TL; ++lx) f(t, order ? TL - 1 - lx : lx, k);
+      }
   }
-  void sync() {
-    const unsigned g = sh->gen;
-    if (++sh->arrived == 32 - sh->done) { sh->arrived = 0; ++sh->gen; return; }
-    long spins = 0;
-    while (sh->gen == g) { yield(); if (++spins > 100000000L) { fprintf(stderr, "emu: barrier deadlock (divergent barrier)\n"); abort(); } }
+  template <class F> void each_problem(F f) {
+    for (int t = 0; t < T; ++t) for (int lx = 0; lx < TL; ++lx) f(t, order ? TL - 1 - lx : lx);
   }
-  double shfl(double v, int src) { sh->xd[ln] = v; sync(); const double r = sh->xd[src & 31]; sync(); return r; }
-  double shfl_xor(double v, int mask) { return shfl(v, ln ^ mask); }
-  int shfl_xor_i(int v, int mask) { sh->xi[ln] = v; sync(); const int r = sh->xi[(ln ^ mask) & 31]; sync(); return r; }
-  void load_begin(int buf, int bytes) { (void)buf; (void)bytes; }
-  void load(int buf, double* dst, const double* src, int n) {
-    if (ln != 0) return;
-    if (sh->lazy) sh->pend_load[buf].push_back({dst, src, n});
-    else std::memcpy(dst, src, sizeof(double) * n);
+  void init() { each_problem([&](int t, int l) { qs_init(q, t, l, B, x0, r, act); }); }
+  void prep(int kk) { each_stage([&](int t, int l, int k) { qs_prep(P, q, t, l, k, kk); }); }
+  void ctl(int kk) {
+    n_active = 0;
+    each_problem([&](int t, int l) { if (qs_ctl(P, q, t, l, kk, xt, ut, status, qp_iter, qp_status, qp_res)) ++n_active; });
   }
-  void load_wait(int buf) {
-    sync();
-    if (ln == 0) { for (auto& c : sh->pend_load[buf]) std::memcpy(c.dst, c.src, sizeof(double) * c.n); sh->pend_load[buf].clear(); }
-    sync();
-  }
-  void store(double* gdst, const double* ssrc, int n) {
-    sync();
-    if (ln == 0) {
-      if (sh->lazy) sh->pend_store.push_back({gdst, ssrc, n});
-      else std::memcpy(gdst, ssrc, sizeof(double) * n);
-    }
-  }
-  void store_wait(int keep) {
-    if (ln == 0)
-      while ((int)sh->pend_store.size() > keep) { auto c = sh->pend_store.front(); sh->pend_store.pop_front(); std::memcpy(c.dst, c.src, sizeof(double) * c.n); }
-    sync();
+  void ric1() { each_problem([&](int t, int l) { qs_ric1(P, q, t, l, psm.data() + l); }); }
+  void ric2(int mode) { each_problem([&](int t, int l) { qs_ric2(P, q, t, l, mode); }); }
+  void step(int kk, int mode) { each_stage([&](int t, int l, int k) { qs_step(P, q, t, l, k, kk, mode); }); }
+  void red(bool after) { each_problem([&](int t, int l) { qs_red(P, q, t, l, after); }); }
+  void sync(int& na, int& nr) {
+    na = n_active; nr = 0;
+    each_problem([&](int t, int l) { const int32_t* pi = q.pi + qs_pb(t, NPI, l); if (QF(pi, J_ACT) && QF(pi, J_REDO)) ++nr; });
   }
 };
-
-Shared* g_sh = nullptr;
-void fiber_entry(int ln) {
-  Shared* sh = g_sh;
-  FiberWarp w{sh, ln};
-  sh->body(w);
-  sh->finished[ln] = true;
-  ++sh->done;
-  // a finished lane must not be waited for any more
-  if (sh->arrived == 32 - sh->done && sh->done < 32) { sh->arrived = 0; ++sh->gen; }
-  if (sh->done == 32) { swapcontext(&sh->ctx[ln], &sh->main_ctx); return; }
-  int nxt = ln;
-  for (int n = 0; n < 32; ++n) { nxt = (nxt + 1) & 31; if (!sh->finished[nxt]) break; }
-  sh->cur = nxt;
-  swapcontext(&sh->ctx[ln], &sh->ctx[nxt]);
-}
-
-void run_warp(Shared& sh) {
-  const size_t stk = 1 << 20;
-  sh.stacks.assign(32 * stk, 0);
-  g_sh = &sh;
-  for (int l = 0; l < 32; ++l) {
-    sh.finished[l] = false;
-    getcontext(&sh.ctx[l]);
-    sh.ctx[l].uc_stack.ss_sp = sh.stacks.data() + l * stk;
-    sh.ctx[l].uc_stack.ss_size = stk;
-    sh.ctx[l].uc_link = &sh.main_ctx;
-    makecontext(&sh.ctx[l], (void (*)())fiber_entry, 1, l);
-  }
-  sh.cur = 0; sh.arrived = 0; sh.done = 0; sh.gen = 0;
-  swapcontext(&sh.main_ctx, &sh.ctx[0]);
-}
-
-struct QpJob {
-  const smpc_problem_t* P; const double* rec; const double* x0; int r; double* ws;
-  double* xt; double* ut; QpResult R;
-};
-
-void qp_body(FiberWarp& w) {
-  QpJob* J = (QpJob*)w.sh->user;
-  QpWarp<FiberWarp> solver(w, *J->P, J->rec, J->ws, J->x0, J->r);
-  const QpResult R = solver.solve();
-  if (w.lane() == 0) J->R = R;
-}
 }  // namespace
 
-// z: [N+1][15], pi: [N][10] (multiplier of the link k -> k+1), lam/t: [N+1][44]
-extern "C" int emu_qp_solve(const smpc_problem_t* P, const double* rec, const double* x0, int r, int lazy, double* z, double* pi,
-                            double* lam, double* t, int* iter, int* status, double* res5) {
-  const int N = P->N;
-  std::vector<double> ws(qw_ws_doubles(N), 0.0);
-  Shared sh;
-  sh.smem.assign(QW_SMEM_DOUBLES, 0.0);
-  sh.lazy = lazy;
-  QpJob job{P, rec, x0, r, ws.data(), nullptr, nullptr, {}};
-  sh.user = &job;
-  sh.body = qp_body;
-  run_warp(sh);
-  for (int k = 0; k <= N; ++k) {
-    const double* b = ws.data() + (size_t)k * WS;
-    std::memcpy(z + k * 15, b + A_Z, 15 * sizeof(double));
-    if (k > 0) std::memcpy(pi + (k - 1) * 10, b + A_PIM, 10 * sizeof(double));
-    std::memcpy(lam + k * 44, b + A_LAM, 44 * sizeof(double));
-    std::memcpy(t + k * 44, b + A_T, 44 * sizeof(double));
+// Batched QP solve with the engine's kernel sources.  rec: [B][N+1][REC] (caller layout), x0: [B][10], r: [B].
+// Outputs in the layout of smpc_get_qp: z [B][N+1][15] ([du;dx], terminal stage: dx first), pi [B][N][10],
+// lam / t [B][N+1][SMPC_QP_NC]; plus x_temp / u_temp / status as smpc_rti_solve produces them.
+extern "C" int emu_qp_solve(const smpc_problem_t* P, int B, const double* rec, const double* x0, const int32_t* r, const uint8_t* act,
+                            int order, double* z, double* pi, double* lam, double* t, double* xt, double* ut, int32_t* status,
+                            int32_t* qp_iter, int32_t* qp_status, double* qp_res, int* n_redo_total) {
+  const int N = P->N, T = (B + TL - 1) / TL;
+  const size_t S = (size_t)T * (N + 1) * TL;
+  std::vector<double> vrec(S * REC, 0.0), it0(S * NIT, 0.0), it1(S * NIT, 0.0), st(S * NIT, 0.0), hc(S * NHC, 0.0), vv(S * NV, 0.0),
+      fac(S * NFAC, 0.0), prod(S * NPROD, 0.0), res(S * NRES, 0.0), stp(S * NSTP, 0.0), pd((size_t)T * NPD * TL, 0.0);
+  std::vector<int32_t> pi32((size_t)T * NPI * TL, 0);
+  for (int b = 0; b < B; ++b)
+    for (int k = 0; k <= N; ++k)
+      for (int f = 0; f < REC; ++f)
+        vrec[qs_blk(b / TL, N, k, REC, b % TL) + (size_t)f * TL] = rec[((size_t)b * (N + 1) + k) * REC + f];
+  QsBufs q{vrec.data(), {it0.data(), it1.data()}, st.data(), hc.data(), vv.data(), fac.data(), prod.data(), res.data(), stp.data(),
+           pd.data(), pi32.data(), N};
+  HostBackend bk{*P, q, B, T, N, order, x0, r, act, xt, ut, status, qp_iter, qp_status, qp_res, std::vector<double>(2 * 65 * TL, 0.0)};
+  struct Counting : HostBackend {
+    int redo = 0;
+    void sync(int& na, int& nr) { HostBackend::sync(na, nr); redo += nr; }
+  };
+  Counting cb{bk};
+  qs_drive(cb);
+  if (n_redo_total) *n_redo_total = cb.redo;
+  for (int b = 0; b < B; ++b) {
+    const int tile = b / TL, lane = b % TL;
+    const int buf = QF(pi32.data() + qs_pb(tile, NPI, lane), J_ITBUF);
+    for (int k = 0; k <= N; ++k) {
+      const double* it = q.it[buf] + qs_blk(tile, N, k, NIT, lane);
+      const StageFlags F = qs_flags(*P, k);
+      double* zo = z + ((size_t)b * (N + 1) + k) * 15;
+      if (k < N) for (int i = 0; i < 15; ++i) zo[i] = QF(it, I_Z + i);
+      else { for (int i = 0; i < 10; ++i) zo[i] = QF(it, I_Z + 5 + i); for (int i = 10; i < 15; ++i) zo[i] = 0.0; }
+      if (k > 0) for (int i = 0; i < 10; ++i) pi[((size_t)b * N + k - 1) * 10 + i] = QF(it, I_PIM + i);
+      double* ol = lam + ((size_t)b * (N + 1) + k) * SMPC_QP_NC;
+      double* ot = t + ((size_t)b * (N + 1) + k) * SMPC_QP_NC;
+      for (int j = 0; j < QNR; ++j) {
+        const bool p = j < 10 ? true : (j < 15 ? F.tau : (j < 21 ? F.dist : F.nn));
+        for (int s = 0; s < 2; ++s) { ol[s * QNR + j] = p ? QF(it, I_LAM + s * QNR + j) : 0.0; ot[s * QNR + j] = p ? QF(it, I_T + s * QNR + j) : 0.0; }
+      }
+      ol[2 * QNR] = F.soft ? QF(it, I_SLK + 2) : 0.0; ol[2 * QNR + 1] = F.soft ? QF(it, I_SLK + 3) : 0.0;
+      ot[2 * QNR] = F.soft ? QF(it, I_SLK + 4) : 0.0; ot[2 * QNR + 1] = F.soft ? QF(it, I_SLK + 5) : 0.0;
+    }
   }
-  *iter = job.R.iter; *status = job.R.status;
-  for (int i = 0; i < 4; ++i) res5[i] = job.R.res[i];
-  res5[4] = job.R.mu;
   return 0;
 }
 #endif

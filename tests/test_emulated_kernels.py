@@ -1,4 +1,4 @@
-"""Kernel-logic tests without a GPU: the engine's device sources (safe_mpc_b200/csrc/dev_model.cuh, qp_warp.cuh)
+"""Kernel-logic tests without a GPU: the engine's device sources (safe_mpc_b200/csrc/dev_model.cuh, qp_split.cuh)
 compiled for the host by tests/emu and compared with the oracle.
 This is a test harness, not a fallback: the product never loads it."""
 import ctypes as C
@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 @pytest.fixture(scope='module')
 def emu():
     so = os.path.join(HERE, 'emu', 'libsmpc_emu.so')
-    srcs = [os.path.join(HERE, 'emu', 'emu.cpp')] + [os.path.join(HERE, '..', 'safe_mpc_b200', 'csrc', f) for f in ('dev_model.cuh', 'qp_warp.cuh')]
+    srcs = [os.path.join(HERE, 'emu', 'emu.cpp')] + [os.path.join(HERE, '..', 'safe_mpc_b200', 'csrc', f) for f in ('dev_model.cuh', 'qp_split.cuh')]
     if not os.path.isfile(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.run(['g++', '-O2', '-std=c++17', '-DEMU_QP', '-fPIC', '-shared', '-o', so, srcs[0]], check=True)
     return C.CDLL(so)
@@ -53,30 +53,63 @@ def test_analytic_linearisation_matches_ad_oracle(emu):
     assert (np.abs(rec - lin) / scale).max() < 1e-11
 
 
+def _emu_solve(emu, prob, lin, x0, r, act=None, order=0):
+    B, N = lin.shape[0], prob.N
+    z = np.zeros((B, N + 1, 15)); pi = np.zeros((B, N, 10)); lam = np.zeros((B, N + 1, abi.QP_NC)); t = np.zeros((B, N + 1, abi.QP_NC))
+    xt = np.full((B, N + 1, 10), np.nan); ut = np.full((B, N, 5), np.nan)
+    status = np.full(B, -1, dtype=np.int32); it = np.full(B, -1, dtype=np.int32); qst = np.full(B, -1, dtype=np.int32)
+    res = np.zeros((B, 5)); redo = C.c_int()
+    lin = np.ascontiguousarray(lin); x0 = np.ascontiguousarray(x0); r = np.ascontiguousarray(r, dtype=np.int32)
+    emu.emu_qp_solve(C.byref(prob), C.c_int(B), _p(lin), _p(x0), _p(r), _p(act) if act is not None else None, C.c_int(order),
+                     _p(z), _p(pi), _p(lam), _p(t), _p(xt), _p(ut), _p(status), _p(it), _p(qst), _p(res), C.byref(redo))
+    return dict(z=z, pi=pi, lam=lam, t=t, xt=xt, ut=ut, status=status, iter=it, qp_status=qst, res=res, redo=redo.value)
+
+
 @pytest.mark.parametrize('controller,cost', [('naive', 'ext'), ('st', 'ext'), ('htwa', 'ext'), ('receding', 'ext'),
-                                             ('real_receding', 'ext'), ('zerovel', 'ext'), ('backup', 'zero')])
-@pytest.mark.parametrize('lazy', [0, 1])
-def test_qp_kernel_source_matches_oracle(emu, controller, cost, lazy):
-    N, B = 10, 3
+                                             ('real_receding', 'ext'), ('zerovel', 'ext'), ('backup', 'zero'),
+                                             ('constraint_everywhere', 'ext'), ('naive', 'nls')])
+@pytest.mark.parametrize('order', [0, 1])
+def test_qp_kernel_source_matches_oracle(emu, controller, cost, order):
+    """The split IPM of safe_mpc_b200/csrc/qp_split.cuh (the source the CUDA kernels instantiate), run on the host in
+    two different work-item orders, against the oracle's QP solution: same iteration count and status, same iterate."""
+    N, B = 10, 35                      # 35 problems: two tiles, the second one padded
     prob, params, md = make_problem(controller, cost=cost, N=N)
-    o = Oracle(prob, B, 1)
+    o = Oracle(prob, B, 2)
     x0 = start_states(B, seed=11, vel=0.5)
     xg, ug = rollout_guess(x0, N, params.dt, seed=12)
     o.set_guess(xg, ug)
     rset = 3 if controller in ('receding', 'real_receding') else N
-    o.set_state(abi.STATE_R, np.full(B, rset, dtype=np.int32))
-    o.rti_solve(x0 + 1e-3)
+    r = np.full(B, rset, dtype=np.int32)
+    o.set_state(abi.STATE_R, r)
+    st_o = o.rti_solve(x0 + 1e-3)
     lin = o.get_lin(); dz, pi, lam, t = o.get_qp()
-    for b in range(B):
-        z = np.zeros((N + 1, 15)); pi_e = np.zeros((N, 10)); lam_e = np.zeros((N + 1, 44)); t_e = np.zeros((N + 1, 44))
-        it = C.c_int(); st = C.c_int(); res = np.zeros(5)
-        x0b = (x0[b] + 1e-3).copy()
-        emu.emu_qp_solve(C.byref(prob), _p(np.ascontiguousarray(lin[b])), _p(x0b), C.c_int(rset), C.c_int(lazy), _p(z), _p(pi_e), _p(lam_e), _p(t_e),
-                         C.byref(it), C.byref(st), _p(res))
-        _, _, oit, ost = o.qp_info(b)
-        assert (it.value, st.value) == (oit, ost)
-        zz = z.copy(); zz[N, :10] = z[N, 5:15]; zz[N, 10:] = 0
-        assert np.abs(zz - dz[b]).max() < 1e-9
-        assert np.abs(pi_e - pi[b]).max() < 1e-8
-        scale = np.maximum(1.0, np.abs(lam[b][:, :44]))
-        assert (np.abs(lam_e - lam[b][:, :44]) / scale).max() < 1e-6
+    xt_o, ut_o = o.get_temp()
+    e = _emu_solve(emu, prob, lin, x0 + 1e-3, r, order=order)
+    oit = np.array([o.qp_info(b)[2] for b in range(B)]); ost = np.array([o.qp_info(b)[3] for b in range(B)])
+    assert (e['iter'] == oit).all() and (e['qp_status'] == ost).all()
+    assert (e['status'] == st_o).all()
+    assert (np.abs(e['z'] - dz) / np.maximum(1.0, np.abs(dz))).max() < 1e-8
+    assert (np.abs(e['pi'] - pi) / np.maximum(1.0, np.abs(pi))).max() < 1e-7
+    assert (np.abs(e['lam'] - lam) / np.maximum(1.0, np.abs(lam))).max() < 1e-6
+    assert (np.abs(e['t'] - t) / np.maximum(1.0, np.abs(t))).max() < 1e-6
+    assert np.abs(e['xt'] - xt_o).max() < 1e-8 and (np.abs(e['ut'] - ut_o) / np.maximum(1.0, np.abs(ut_o))).max() < 1e-8
+
+
+def test_qp_kernel_source_mask_and_infeasible(emu):
+    """Masked problems keep their outputs untouched; an infeasible QP reports acados status 4 and a zero step."""
+    N, B = 8, 6
+    prob, params, md = make_problem('naive', N=N)
+    o = Oracle(prob, B, 2)
+    x0 = start_states(B, seed=3)
+    xg, ug = rollout_guess(x0, N, params.dt, seed=4)
+    xg[1, 3, 1] = md.x_max[1] + 2.0            # far outside the state box with x0 pinned -> inconsistent rows
+    o.set_guess(xg, ug)
+    act = np.ones(B, dtype=np.uint8); act[4] = 0
+    st_o = o.rti_solve(x0, active=act)
+    lin = o.get_lin()
+    e = _emu_solve(emu, prob, lin, x0, np.full(B, N, dtype=np.int32), act=act)
+    assert e['status'][4] == -1 and np.isnan(e['xt'][4]).all()
+    on = act.astype(bool)
+    assert (e['status'][on] == st_o[on]).all()
+    xt_o, ut_o = o.get_temp()
+    assert np.abs(e['xt'][on] - xt_o[on]).max() < 1e-9

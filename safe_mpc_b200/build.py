@@ -13,7 +13,7 @@ from concurrent.futures import ThreadPoolExecutor
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'csrc')
 LIB = os.path.join(CSRC, 'libsafe_mpc_b200.so')
 SOURCES = ['api.cu', 'kernels.cu', 'qp.cu']
-HEADERS = ['engine.cuh', 'qp_warp.cuh', 'dev_model.cuh', os.path.join('..', '..', 'include', 'safe_mpc_b200.h')]
+HEADERS = ['engine.cuh', 'qp_split.cuh', 'dev_model.cuh', os.path.join('..', '..', 'include', 'safe_mpc_b200.h')]
 NVCC_FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-Xcompiler', '-fPIC',
               '-Xptxas', '-v']
 
@@ -40,7 +40,7 @@ def build_cuda(force=False, verbose=False):
 
     def compile_one(src):
         obj = os.path.join(CSRC, src[:-3] + '.o')
-        cmd = [nvcc] + NVCC_FLAGS + ['-c', os.path.join(CSRC, src), '-o', obj]
+        cmd = [nvcc] + NVCC_FLAGS + os.environ.get('SMPC_NVCC_EXTRA', '').split() + ['-c', os.path.join(CSRC, src), '-o', obj]
         res = subprocess.run(cmd, capture_output=True, text=True)
         log.append((src, res.stderr))
         if res.returncode != 0:

@@ -30,12 +30,9 @@ struct smpc_handle {
   float* dW = nullptr;
   MlpWeights w{};
   // state
-  double *xg = nullptr, *ug = nullptr, *xt = nullptr, *ut = nullptr, *lin = nullptr, *plant_inertial = nullptr, *tau_noise = nullptr,
-         *x_viable = nullptr, *nn11 = nullptr, *scan11 = nullptr, *qpws = nullptr, *qpws_dbg = nullptr, *qp_res = nullptr, *x_in = nullptr, *u_out = nullptr,
-         *x0_last = nullptr;
-  int* qp_queue = nullptr;
-  int32_t* dbg_i32 = nullptr;
-  int qp_slots = 0;                 // persistent QP warps = workspace slots
+  double *xg = nullptr, *ug = nullptr, *xt = nullptr, *ut = nullptr, *plant_inertial = nullptr, *tau_noise = nullptr,
+         *x_viable = nullptr, *nn11 = nullptr, *scan11 = nullptr, *qp_res = nullptr, *x_in = nullptr, *u_out = nullptr;
+  QpSolver* qp = nullptr;           // split interior-point solver: tile-interleaved records + solver state
   const uint8_t* act_last = nullptr;
   bool solved = false;
   int32_t *fails = nullptr, *r = nullptr, *status = nullptr, *qp_iter = nullptr, *qp_status = nullptr, *cur_step = nullptr;
@@ -128,11 +125,10 @@ int solve_pipeline(smpc_handle* h, const double* x0_dev, const uint8_t* act) {
     const int mode = h->P.nn_rows == SMPC_NN_TERMINAL ? ROWS_TERMINAL : (h->P.nn_rows == SMPC_NN_EVERYWHERE ? ROWS_ALL : ROWS_RECEDING);
     launch_mlp(c, h->dP, h->w, B, N, mode, 0, h->xg, h->r, act, nullptr, h->nn11, true);
   }
-  launch_linearize(c, h->dP, B, N, h->xg, h->ug, h->r, act, h->nn11, h->lin);
+  launch_linearize(c, h->dP, B, N, h->xg, h->ug, h->r, act, h->nn11, qp_rec(h->qp));
   if (h->timed) cudaEventRecord(h->ev[1], h->stream);
-  if (x0_dev != h->x0_last) cudaMemcpyAsync(h->x0_last, x0_dev, sizeof(double) * B * NX, cudaMemcpyDeviceToDevice, h->stream);
-  launch_qp(c, h->dP, B, N, h->qp_slots, h->lin, x0_dev, h->r, act, h->qpws, h->qp_queue, h->xt, h->ut, h->status, h->qp_iter, h->qp_status,
-            h->qp_res);
+  cudaError_t qe = launch_qp_solve(c, h->dP, h->qp, x0_dev, h->r, act, h->xt, h->ut, h->status, h->qp_iter, h->qp_status, h->qp_res);
+  if (qe != cudaSuccess) return fail(h, SMPC_ERR_CUDA, "QP solve", qe);
   h->solved = true;
   if (h->timed) cudaEventRecord(h->ev[2], h->stream);
   return check_launch(h, "solve pipeline");
@@ -225,15 +221,15 @@ int smpc_create(const smpc_problem_t* prob, int32_t batch, int32_t device, smpc_
   }
   const size_t nx = (size_t)B * (N + 1) * NX, nu = (size_t)B * N * NU, nst = (size_t)B * (N + 1);
   CKC(dalloc(h, &h->xg, nx)); CKC(dalloc(h, &h->ug, nu)); CKC(dalloc(h, &h->xt, nx)); CKC(dalloc(h, &h->ut, nu));
-  CKC(dalloc(h, &h->lin, nst * REC));
   CKC(dalloc(h, &h->plant_inertial, (size_t)B * NQ * 10)); CKC(dalloc(h, &h->tau_noise, (size_t)B * NU));
   CKC(dalloc(h, &h->x_viable, (size_t)B * NX));
   CKC(dalloc(h, &h->nn11, nst * NN_OUT));
   if (prob->controller == SMPC_CTRL_RECEDING || prob->controller == SMPC_CTRL_REAL_RECEDING) CKC(dalloc(h, &h->scan11, nst * NN_OUT));
-  h->qp_slots = qp_grid(B);
-  CKC(dalloc(h, &h->qpws, (size_t)h->qp_slots * qp_ws_doubles(N)));
-  CKC(dalloc(h, &h->qp_queue, 1));
-  CKC(dalloc(h, &h->x0_last, (size_t)B * NX));
+  {
+    cudaError_t qe = cudaSuccess;
+    h->qp = qp_create(B, N, prob->qp_iter_max, h->stream, &qe);
+    if (!h->qp) { fail(nullptr, SMPC_ERR_CUDA, "qp_create", qe); smpc_destroy(h); return SMPC_ERR_CUDA; }
+  }
   CKC(dalloc(h, &h->qp_res, (size_t)B * 5));
   CKC(dalloc(h, &h->x_in, (size_t)B * NX)); CKC(dalloc(h, &h->u_out, (size_t)B * NU));
   CKC(dalloc(h, &h->fails, (size_t)B)); CKC(dalloc(h, &h->r, (size_t)B)); CKC(dalloc(h, &h->status, (size_t)B));
@@ -261,6 +257,7 @@ void smpc_destroy(smpc_handle_t* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (void* p : h->allocs) cudaFree(p);
+  qp_destroy(h->qp);
   if (h->stage) cudaFree(h->stage);
   for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -398,7 +395,11 @@ int smpc_nn_constraint(smpc_handle_t* h, int32_t n, const double* x, double* cva
 
 int smpc_get_lin(smpc_handle_t* h, double* lin, int32_t mem) {
   const size_t bytes = sizeof(double) * h->B * (h->N + 1) * REC;
-  return copy_out(h, lin, h->lin, bytes, mem);      // records are kept in the caller layout [B][N+1][REC]
+  if (mem == SMPC_DEVICE) { launch_rec_untile(h->ctx(), h->qp, lin); return check_launch(h, "get_lin"); }
+  int rc = stage_reserve(h, bytes); if (rc) return rc;
+  launch_rec_untile(h->ctx(), h->qp, (double*)h->stage);      // records are kept tile-interleaved; hand them back as [B][N+1][REC]
+  rc = check_launch(h, "get_lin"); if (rc) return rc;
+  return copy_out(h, lin, h->stage, bytes, mem);
 }
 
 int smpc_get_qp(smpc_handle_t* h, double* dz, double* pi, double* lam, double* t, int32_t mem) {
@@ -407,18 +408,8 @@ int smpc_get_qp(smpc_handle_t* h, double* dz, double* pi, double* lam, double* t
   if (!h->solved) return fail(h, SMPC_ERR_ARG, "smpc_get_qp: no smpc_rti_solve / smpc_controller_step yet");
   int rc = stage_reserve(h, b1 + b2 + 2 * b3); if (rc) return rc;
   char* s = (char*)h->stage;
-  // The solver keeps its state in per-warp workspace slots that are reused from problem to problem.  To hand the
-  // per-problem solution back, solve the stored QPs once more with one slot per problem (same records, same x0:
-  // bit-identical results).
-  const size_t nxs = (size_t)h->B * (h->N + 1) * NX, nus = (size_t)h->B * h->N * NU;
-  if (!h->qpws_dbg) {
-    CK(h, dalloc(h, &h->qpws_dbg, (size_t)h->B * qp_ws_doubles(h->N) + nxs + nus + (size_t)h->B * 5));
-    CK(h, dalloc(h, &h->dbg_i32, (size_t)h->B * 3));
-  }
-  double* dxt = h->qpws_dbg + (size_t)h->B * qp_ws_doubles(h->N);      // the re-solve must not disturb x_temp / status
-  launch_qp(h->ctx(), h->dP, h->B, h->N, h->B, h->lin, h->x0_last, h->r, nullptr, h->qpws_dbg, nullptr, dxt, dxt + nxs, h->dbg_i32,
-            h->dbg_i32 + h->B, h->dbg_i32 + 2 * h->B, dxt + nxs + nus);
-  launch_dump_qp(h->ctx(), h->B, h->N, h->qpws_dbg, h->lin, (double*)s, (double*)(s + b1), (double*)(s + b1 + b2), (double*)(s + b1 + b2 + b3));
+  // the final iterate of every problem stays in the solver's ping-pong buffers until the next solve
+  launch_dump_qp(h->ctx(), h->dP, h->qp, (double*)s, (double*)(s + b1), (double*)(s + b1 + b2), (double*)(s + b1 + b2 + b3));
   rc = check_launch(h, "get_qp"); if (rc) return rc;
   rc = copy_out(h, dz, s, b1, mem); if (rc) return rc;
   rc = copy_out(h, pi, s + b1, b2, mem); if (rc) return rc;

@@ -6,7 +6,7 @@
 #include <string>
 
 #include "../../include/safe_mpc_b200.h"
-#include "qp_warp.cuh"
+#include "qp_split.cuh"
 
 namespace smpc {
 
@@ -45,7 +45,6 @@ void launch_kin(const LaunchCtx& c, const smpc_problem_t* dP, int n, const doubl
 void launch_fill_i32(const LaunchCtx& c, int32_t* p, int n, int32_t v);
 void launch_fill_f64(const LaunchCtx& c, double* p, size_t n, double v);
 void launch_set_xviable_from_guess(const LaunchCtx& c, int B, int N, const double* xg, double* xv);
-void launch_dump_qp(const LaunchCtx& c, int B, int N, const double* ws, const double* lin, double* dz, double* pi, double* lam, double* t);
 
 // sim kernels
 struct SimDev {
@@ -61,14 +60,17 @@ void launch_sim_post(const LaunchCtx& c, const SimDev& s, const smpc_problem_t* 
                      const double* bk_ut, const double* inertial, const double* noise, const int32_t* qp_iter_bk);
 void launch_sim_outcome(const LaunchCtx& c, const SimDev& s, const smpc_problem_t* dP, int32_t* out);
 
-// qp.cu
-size_t qp_ws_doubles(int N);          // workspace of one warp (slot)
-size_t qp_smem_bytes();
-int qp_grid(int B);                   // number of persistent one-warp CTAs (= workspace slots) for a batch of B; sets kernel attributes
-// queue != nullptr: `grid` persistent warps pull problems from the atomic queue; queue == nullptr: CTA b solves problem b
-// in workspace slot b (grid must equal B; used when the caller wants the per-problem QP solution back)
-void launch_qp(const LaunchCtx& c, const smpc_problem_t* dP, int B, int N, int grid, const double* lin, const double* x0, const int32_t* r,
-               const uint8_t* act, double* ws, int* queue, double* xt, double* ut, int32_t* status, int32_t* qp_iter, int32_t* qp_status,
-               double* qp_res);
+// qp.cu -- split interior-point solver (qp_split.cuh)
+struct QpSolver;
+size_t qp_bytes(int B, int N);
+QpSolver* qp_create(int B, int N, int iter_max, cudaStream_t stream, cudaError_t* err);
+void qp_destroy(QpSolver* s);
+double* qp_rec(QpSolver* s);                  // tile-interleaved stage records [T][N+1][REC][32] the linearisation writes
+int qp_last_iterations(const QpSolver* s);    // IPM iterations of the slowest problem of the last solve
+// one batched solve; reads the records of qp_rec(); problems with act == 0 are skipped and keep their outputs
+cudaError_t launch_qp_solve(const LaunchCtx& c, const smpc_problem_t* dP, QpSolver* s, const double* x0, const int32_t* r, const uint8_t* act,
+                            double* xt, double* ut, int32_t* status, int32_t* qp_iter, int32_t* qp_status, double* qp_res);
+void launch_rec_untile(const LaunchCtx& c, QpSolver* s, double* out);
+void launch_dump_qp(const LaunchCtx& c, const smpc_problem_t* dP, QpSolver* s, double* dz, double* pi, double* lam, double* t);
 
 }  // namespace smpc

@@ -195,10 +195,13 @@ void launch_mlp(const LaunchCtx& c, const smpc_problem_t* dP, const MlpWeights& 
 __global__ void __launch_bounds__(128)
 linearize_kernel(const smpc_problem_t* __restrict__ dP, int B, int N, const double* __restrict__ xg, const double* __restrict__ ug,
                  const int32_t* __restrict__ r, const uint8_t* __restrict__ act, const double* __restrict__ nn11, double* lin) {
-  // one contiguous record per (problem, stage), [B][N+1][REC]: the QP kernel streams whole records with bulk copies
+  // records are written tile-interleaved, [tile][stage][field][lane] (qp_split.cuh): thread = lane of warp (tile, stage),
+  // so every field store of a warp is one contiguous 256-byte segment
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= B * (N + 1)) return;
-  const int b = idx / (N + 1), k = idx % (N + 1);
+  const int lane = idx & (TL - 1), w = idx / TL;
+  const int tile = w / (N + 1), k = w % (N + 1);
+  const int b = tile * TL + lane;
+  if (b >= B) return;
   if (act && !act[b]) return;
   const smpc_problem_t& P = *dP;
   double x[NX], u[NU], xn[NX];
@@ -210,12 +213,12 @@ linearize_kernel(const smpc_problem_t* __restrict__ dP, int B, int N, const doub
   const bool has_nn = stage_has_nn(P, k);
   bool gate = true;
   if (P.nn_rows == SMPC_NN_RECEDING && k < N) gate = (k == r[b]);      // controller.py:452-469
-  double* rec = lin + (size_t)idx * REC;
-  linearize_stage(P, k, x, u, xn, has_nn, gate, nn11 + (size_t)idx * NN_OUT, rec, 1);
+  double* rec = lin + qs_blk(tile, N, k, REC, lane);
+  linearize_stage(P, k, x, u, xn, has_nn, gate, nn11 + ((size_t)b * (N + 1) + k) * NN_OUT, rec, TL);
 }
 void launch_linearize(const LaunchCtx& c, const smpc_problem_t* dP, int B, int N, const double* xg, const double* ug, const int32_t* r,
                       const uint8_t* act, const double* nn11, double* lin) {
-  const int n = B * (N + 1);
+  const int n = ((B + TL - 1) / TL) * (N + 1) * TL;
   linearize_kernel<<<GRID1D(n, 128), 128, 0, c.stream>>>(dP, B, N, xg, ug, r, act, nn11, lin);
   ++*c.launches;
 }

@@ -43,12 +43,17 @@ SMPC_HD constexpr int trs(int i, int j) { return i >= j ? tri(i, j) : tri(j, i);
 
 // iterate block (also the layout of the step block)
 enum { I_Z = 0, I_PIM = 15, I_LAM = 25, I_T = 69, I_SLK = 113, NIT = 120 };   // I_SLK: s_l s_u lam_sl lam_su t_sl t_su
-// condensed stage block (prep -> ric1 / ric2)
-enum { H_M = 0, H_GA = 120, H_RB = 135, NHC = 145 };
-// corrector terms (step0 -> ric2): v1 = C'(dlam_aff dt_aff / t), v2 = C'(1 / t)
-enum { V_1 = 0, V_2 = 15, NV = 30 };
-// Riccati factors (ric1 -> ric2): T[15][5] elimination multipliers (T[j][j] = 1/d_j), P packed 10x10, l~(5) p(10), P_{k+1} res_b
-enum { F_T = 0, F_P = 75, F_LP = 130, F_WV = 145, NFAC = 155 };
+// solver block of one stage: everything the Riccati sweeps read or write, ordered so that each sweep fetches one
+// contiguous range:   ric1 backward reads [B_M, B_LP), writes [B_LP, B_V1);   ric1 forward reads [B_RB, B_WV);
+// ric2 backward reads [B_GA, B_P) + [B_V1, NSB), writes B_LP;   ric2 forward reads [B_RB, B_V1)
+//   M    condensed stage matrix H + reg + C' Gam C, packed lower triangle (prep)
+//   GA   affine gradient res_g + C' gam (prep)          RB   dynamics residual of the link k -> k+1 (prep)
+//   LP   l~ (5), p (10) of the current solve (ric1 / ric2)
+//   T    elimination multipliers T[15][5], T[j][j] = 1/d_j (ric1)
+//   WV   P_{k+1} res_b (ric1)                           P    Riccati matrix, packed 10x10 (ric1)
+//   V1   C'(dlam_aff dt_aff / t), V2 = C'(1 / t): corrector terms (step0)
+enum { B_M = 0, B_GA = 120, B_RB = 135, B_LP = 145, B_T = 160, B_WV = 235, B_P = 245, B_V1 = 300, B_V2 = 315, NSB = 330 };
+enum { H_M = B_M, H_GA = B_GA, H_RB = B_RB, F_LP = B_LP, F_T = B_T, F_WV = B_WV, F_P = B_P, V_1 = B_V1, V_2 = B_V2, NHC = NSB, NFAC = NSB, NV = NSB };
 enum { NPROD = 46 };               // dlam_aff * dt_aff per slot (44) + the two slack slots
 enum { R_NG = 0, R_NB = 1, R_ND = 2, R_NM = 3, R_MU = 4, R_CHK = 5, R_CNT = 6, NRES = 8 };
 enum { S_ALPHA = 0, S_LIN = 1, S_QUAD = 2, NSTP = 4 };
@@ -61,9 +66,7 @@ struct QsBufs {
   const double* rec;     // [T][N+1][REC][TL]   stage records (linearisation)
   double* it[2];         // [T][N+1][NIT][TL]   iterate, ping-pong
   double* st;            // [T][N+1][NIT][TL]   step
-  double* hc;            // [T][N+1][NHC][TL]
-  double* v;             // [T][N+1][NV][TL]
-  double* fac;           // [T][N+1][NFAC][TL]
+  double* sb;            // [T][N+1][NSB][TL]   solver block (condensed matrices, Riccati factors, corrector terms)
   double* prod;          // [T][N+1][NPROD][TL]
   double* res;           // [T][N+1][NRES][TL]
   double* stp;           // [T][N+1][NSTP][TL]
@@ -138,7 +141,7 @@ SMPC_HD void qs_prep(const smpc_problem_t& P, const QsBufs& q, int tile, int lan
   double* ito = q.it[kk & 1] + qs_blk(tile, N, k, NIT, lane);
   const double* iti = q.it[(kk & 1) ^ 1] + qs_blk(tile, N, k, NIT, lane);
   const double* st = q.st + qs_blk(tile, N, k, NIT, lane);
-  double* hc = q.hc + qs_blk(tile, N, k, NHC, lane);
+  double* hc = q.sb + qs_blk(tile, N, k, NHC, lane);
   const StageFlags F = qs_flags(P, k);
   const double lam_min = 1e-16, t_min = 1e-16, thr0 = 1e-1, mu0 = P.qp_mu0, reg = P.qp_reg_prim;
   const double dt = P.dt, a2 = 0.5 * P.dt * P.dt;
@@ -469,20 +472,34 @@ SMPC_HD double qs_y(int i, int c, double dt, double a2, PF Pn) {
   return y;
 }
 
+// The sweeps are written against a small warp policy W (lane id, warp barrier, staged copies of a contiguous field
+// range of a stage block into on-chip memory one stage ahead of its use): TMA bulk copies + mbarriers on the device
+// (qp.cu), memcpy in tests/emu.  w.buf(b) is staging buffer b with this lane's offset applied, field f at [f * TL].
+enum { RIC1_STAGE_FIELDS = B_LP - B_M, RIC2_STAGE_FIELDS = B_V1 - B_RB };   // largest range each kernel stages (145, 165)
+
 // ric1: backward factorisation with the affine gradient, stage-0 solve, forward substitution of the affine direction.
-// psm: scratch for two packed P matrices + p, [2][65][TL] doubles, indexed like every other block (lane already added).
-SMPC_HD void qs_ric1(const smpc_problem_t& P, const QsBufs& q, int tile, int lane, double* psm) {
-  const int N = q.N;
+// psm: on-chip scratch for two packed P matrices + p, [2][65][TL] doubles (lane offset applied).
+template <class W>
+SMPC_HD void qs_ric1(const smpc_problem_t& P, const QsBufs& q, int tile, W& w, double* psm) {
+  const int N = q.N, lane = w.lane();
   const int32_t* pi = q.pi + qs_pb(tile, NPI, lane);
-  if (!QF(pi, J_ACT)) return;
+  const bool on = QF(pi, J_ACT) != 0;
+  if (!w.any(on)) return;
   double* pd = q.pd + qs_pb(tile, NPD, lane);
   const double dt = P.dt, a2 = 0.5 * P.dt * P.dt;
+  const double* gsb = q.sb + qs_blk(tile, N, 0, NSB, 0);       // stage blocks of this tile (no lane offset)
+  const size_t sstride = (size_t)NSB * TL;
   double dx[10];
+  w.fetch_begin(N & 1, B_LP - B_M);
+  w.fetch(N & 1, 0, gsb + (size_t)N * sstride, B_M, B_LP - B_M);
   for (int k = N; k >= 0; --k) {
-    const double* hc = q.hc + qs_blk(tile, N, k, NHC, lane);
-    double* fac = q.fac + qs_blk(tile, N, k, NFAC, lane);
-    double* pcur = psm + (size_t)(k & 1) * 65 * TL;            // P_k, p_k
-    const double* pnx = psm + (size_t)((k & 1) ^ 1) * 65 * TL; // P_{k+1}, p_{k+1}
+    w.sync();                                                    // every lane is done with the buffer of stage k + 1
+    if (k > 0) { w.fetch_begin((k - 1) & 1, B_LP - B_M); w.fetch((k - 1) & 1, 0, gsb + (size_t)(k - 1) * sstride, B_M, B_LP - B_M); }
+    w.wait(k & 1);
+    const double* hc = w.buf(k & 1);                             // fields B_M .. B_LP at their own offsets
+    double* fac = q.sb + qs_blk(tile, N, k, NSB, lane);
+    double* pcur = psm + (size_t)(k & 1) * 65 * TL;              // P_k, p_k
+    const double* pnx = psm + (size_t)((k & 1) ^ 1) * 65 * TL;   // P_{k+1}, p_{k+1}
     auto Pn = [&](int idx) { return QF(pnx, idx); };
     // gradient: g = ga + [B A]' (P_{k+1} rb + p_{k+1})
     double g[15];
@@ -497,7 +514,7 @@ SMPC_HD void qs_ric1(const smpc_problem_t& P, const QsBufs& q, int tile, int lan
         double s = 0.0;
 #pragma unroll
         for (int j = 0; j < 10; ++j) s += Pn(trs(i, j)) * rb[j];
-        QF(fac, F_WV + i) = s;
+        if (on) QF(fac, F_WV + i) = s;
         y[i] = s + QF(pnx, 55 + i);
       }
 #pragma unroll
@@ -518,8 +535,8 @@ SMPC_HD void qs_ric1(const smpc_problem_t& P, const QsBufs& q, int tile, int lan
       for (int j = 0; j < 5; ++j)
         if (j <= i) pan[i][j] = QF(hc, H_M + tri(i, j)) + (k < N ? qs_y(i, j, dt, a2, Pn) : 0.0);
     // eliminate the control columns in place (LDL' form; a non-positive pivot zeroes the column, as BLASFEO dpotrf and
-    // the oracle).  Rows are walked downwards-to-upwards so that the un-scaled column entries pan[c][j] of the rows
-    // above are still available; afterwards pan[i][j] holds the multiplier t_ij (i > j) and pan[j][j] = 1/d_j.
+    // the oracle).  Rows are walked bottom-up so that the un-scaled column entries pan[c][j] of the rows above are
+    // still available; afterwards pan[i][j] holds the multiplier t_ij (i > j) and pan[j][j] = 1/d_j.
     double dd[5];
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
@@ -537,13 +554,15 @@ SMPC_HD void qs_ric1(const smpc_problem_t& P, const QsBufs& q, int tile, int lan
       }
       pan[j][j] = invd;
     }
+    if (on) {
 #pragma unroll
-    for (int i = 0; i < 15; ++i)
+      for (int i = 0; i < 15; ++i)
 #pragma unroll
-      for (int j = 0; j < 5; ++j)
-        if (j <= i) QF(fac, F_T + i * 5 + j) = pan[i][j];
+        for (int j = 0; j < 5; ++j)
+          if (j <= i) QF(fac, F_T + i * 5 + j) = pan[i][j];
 #pragma unroll
-    for (int i = 0; i < 15; ++i) QF(fac, F_LP + i) = g[i];
+      for (int i = 0; i < 15; ++i) QF(fac, F_LP + i) = g[i];
+    }
 #pragma unroll
     for (int i = 0; i < 10; ++i) QF(pcur, 55 + i) = g[5 + i];
     // P_k = trailing block - T_x D T_x'
@@ -558,7 +577,7 @@ SMPC_HD void qs_ric1(const smpc_problem_t& P, const QsBufs& q, int tile, int lan
 #pragma unroll
         for (int j = 0; j < 5; ++j) v -= sd[j] * pan[c][j];
         QF(pcur, tri(i - 5, c - 5)) = v;
-        QF(fac, F_P + tri(i - 5, c - 5)) = v;
+        if (on) QF(fac, F_P + tri(i - 5, c - 5)) = v;
       }
     }
     if (k == 0) {
@@ -574,7 +593,6 @@ SMPC_HD void qs_ric1(const smpc_problem_t& P, const QsBufs& q, int tile, int lan
       for (int j = 0; j < 10; ++j) {
         const double d = m[j][j];
         const double invd = d > 0.0 ? 1.0 / d : 0.0;
-        QF(pd, D_T0 + tri(j, j)) = invd;
         m[j][j] = invd;
 #pragma unroll
         for (int i = 9; i > j; --i) {       // bottom-up: the rows above still hold their un-scaled column entries
@@ -583,8 +601,13 @@ SMPC_HD void qs_ric1(const smpc_problem_t& P, const QsBufs& q, int tile, int lan
 #pragma unroll
           for (int c = j + 1; c <= i; ++c) m[i][c] -= t * m[c][j];
           m[i][j] = t;
-          QF(pd, D_T0 + tri(i, j)) = t;
         }
+      }
+      if (on) {
+#pragma unroll
+        for (int i = 0; i < 10; ++i)
+#pragma unroll
+          for (int c = 0; c <= i; ++c) QF(pd, D_T0 + tri(i, c)) = m[i][c];
       }
 #pragma unroll
       for (int i = 9; i >= 0; --i) {
@@ -595,10 +618,16 @@ SMPC_HD void qs_ric1(const smpc_problem_t& P, const QsBufs& q, int tile, int lan
       }
     }
   }
-  // forward substitution (affine direction)
+  // forward substitution (affine direction): stages fetch RB, LP, T = fields [B_RB, B_WV)
+  w.publish();
+  w.sync();
+  w.fetch_begin(0, B_WV - B_RB);
+  w.fetch(0, 0, gsb, B_RB, B_WV - B_RB);
   for (int k = 0; k <= N; ++k) {
-    const double* fac = q.fac + qs_blk(tile, N, k, NFAC, lane);
-    const double* hc = q.hc + qs_blk(tile, N, k, NHC, lane);
+    w.sync();
+    if (k < N) { w.fetch_begin((k + 1) & 1, B_WV - B_RB); w.fetch((k + 1) & 1, 0, gsb + (size_t)(k + 1) * sstride, B_RB, B_WV - B_RB); }
+    w.wait(k & 1);
+    const double* sb = w.buf(k & 1) - (size_t)B_RB * TL;         // sb[f] valid for B_RB <= f < B_WV
     double* st = q.st + qs_blk(tile, N, k, NIT, lane);
     double du[5];
 #pragma unroll
@@ -606,26 +635,28 @@ SMPC_HD void qs_ric1(const smpc_problem_t& P, const QsBufs& q, int tile, int lan
     if (k < N) {
 #pragma unroll
       for (int i = 0; i < 5; ++i) {
-        double w = QF(fac, F_T + i * 5 + i) * QF(fac, F_LP + i);
+        double ws = QF(sb, F_T + i * 5 + i) * QF(sb, F_LP + i);
 #pragma unroll
-        for (int r = 0; r < 10; ++r) w += QF(fac, F_T + (5 + r) * 5 + i) * dx[r];
-        du[i] = -w;
+        for (int r = 0; r < 10; ++r) ws += QF(sb, F_T + (5 + r) * 5 + i) * dx[r];
+        du[i] = -ws;
       }
 #pragma unroll
       for (int c = 4; c >= 1; --c)
 #pragma unroll
-        for (int i = 0; i < c; ++i) du[i] -= QF(fac, F_T + c * 5 + i) * du[c];
+        for (int i = 0; i < c; ++i) du[i] -= QF(sb, F_T + c * 5 + i) * du[c];
     }
+    if (on) {
 #pragma unroll
-    for (int i = 0; i < 5; ++i) QF(st, I_Z + i) = du[i];
+      for (int i = 0; i < 5; ++i) QF(st, I_Z + i) = du[i];
 #pragma unroll
-    for (int i = 0; i < 10; ++i) QF(st, I_Z + 5 + i) = dx[i];
+      for (int i = 0; i < 10; ++i) QF(st, I_Z + 5 + i) = dx[i];
+    }
     if (k < N) {
       double nx[10];
 #pragma unroll
       for (int j = 0; j < 5; ++j) {
-        nx[j] = dx[j] + dt * dx[5 + j] + a2 * du[j] + QF(hc, H_RB + j);
-        nx[5 + j] = dx[5 + j] + dt * du[j] + QF(hc, H_RB + 5 + j);
+        nx[j] = dx[j] + dt * dx[5 + j] + a2 * du[j] + QF(sb, H_RB + j);
+        nx[5 + j] = dx[5 + j] + dt * du[j] + QF(sb, H_RB + 5 + j);
       }
 #pragma unroll
       for (int j = 0; j < 10; ++j) dx[j] = nx[j];
@@ -637,6 +668,7 @@ SMPC_HD void qs_ric1(const smpc_problem_t& P, const QsBufs& q, int tile, int lan
 SMPC_HD void qs_reduce_step(const QsBufs& q, int tile, int lane, double& alpha, double& s_lin, double& s_quad) {
   const int N = q.N;
   alpha = 1.0; s_lin = 0.0; s_quad = 0.0;
+#pragma unroll 8
   for (int k = 0; k <= N; ++k) {
     const double* stp = q.stp + qs_blk(tile, N, k, NSTP, lane);
     alpha = fmin(alpha, QF(stp, S_ALPHA)); s_lin += QF(stp, S_LIN); s_quad += QF(stp, S_QUAD);
@@ -645,37 +677,54 @@ SMPC_HD void qs_reduce_step(const QsBufs& q, int tile, int lane, double& alpha, 
 
 // ric2: vector-only backward sweep for the corrector (mode 1) / centering (mode 2) right-hand side, stage-0 solve,
 // forward substitution with the multiplier steps.  In mode 1 the prologue turns the affine step statistics into sigma.
-SMPC_HD void qs_ric2(const smpc_problem_t& P, const QsBufs& q, int tile, int lane, int mode) {
-  const int N = q.N;
+template <class W>
+SMPC_HD void qs_ric2(const smpc_problem_t& P, const QsBufs& q, int tile, W& w, int mode) {
+  const int N = q.N, lane = w.lane();
   const int32_t* pi = q.pi + qs_pb(tile, NPI, lane);
-  if (!QF(pi, J_ACT)) return;
-  if (mode == 2 && !QF(pi, J_REDO)) return;
+  const bool on = QF(pi, J_ACT) != 0 && (mode != 2 || QF(pi, J_REDO) != 0);
+  if (!w.any(on)) return;
   double* pd = q.pd + qs_pb(tile, NPD, lane);
   const double dt = P.dt, a2 = 0.5 * P.dt * P.dt;
-  double sigmu;
+  const double* gsb = q.sb + qs_blk(tile, N, 0, NSB, 0);
+  const size_t sstride = (size_t)NSB * TL;
+  // backward stages fetch GA RB LP T WV = [B_GA, B_P) -> staging fields 0..124, and V1 V2 = [B_V1, NSB) -> 125..154
+  const int n1 = B_P - B_GA, n2 = NSB - B_V1;
+  w.fetch_begin(N & 1, n1 + n2);
+  w.fetch(N & 1, 0, gsb + (size_t)N * sstride, B_GA, n1);
+  w.fetch(N & 1, n1, gsb + (size_t)N * sstride, B_V1, n2);
+  double sigmu = 0.0;
   if (mode == 1) {
-    double alpha, s_lin, s_quad;
-    qs_reduce_step(q, tile, lane, alpha, s_lin, s_quad);
-    const double mu = QF(pd, D_MU);
-    const double mu_aff = mu + (alpha * s_lin + alpha * alpha * s_quad) / QF(pi, J_NC);
-    double sigma = mu_aff / mu; sigma = sigma * sigma * sigma;
-    sigmu = sigma * mu;
-    QF(pd, D_MUAFF) = mu_aff; QF(pd, D_SIGMU) = sigmu;
+    if (on) {
+      double alpha, s_lin, s_quad;
+      qs_reduce_step(q, tile, lane, alpha, s_lin, s_quad);
+      const double mu = QF(pd, D_MU);
+      const double mu_aff = mu + (alpha * s_lin + alpha * alpha * s_quad) / QF(pi, J_NC);
+      double sigma = mu_aff / mu; sigma = sigma * sigma * sigma;
+      sigmu = sigma * mu;
+      QF(pd, D_MUAFF) = mu_aff; QF(pd, D_SIGMU) = sigmu;
+    }
   } else sigmu = QF(pd, D_SIGMU);
   double pn[10], dx[10];
 #pragma unroll
-  for (int i = 0; i < 10; ++i) pn[i] = 0.0;
+  for (int i = 0; i < 10; ++i) { pn[i] = 0.0; dx[i] = 0.0; }
   for (int k = N; k >= 0; --k) {
-    const double* hc = q.hc + qs_blk(tile, N, k, NHC, lane);
-    const double* vv = q.v + qs_blk(tile, N, k, NV, lane);
-    double* fac = q.fac + qs_blk(tile, N, k, NFAC, lane);
+    w.sync();
+    if (k > 0) {
+      w.fetch_begin((k - 1) & 1, n1 + n2);
+      w.fetch((k - 1) & 1, 0, gsb + (size_t)(k - 1) * sstride, B_GA, n1);
+      w.fetch((k - 1) & 1, n1, gsb + (size_t)(k - 1) * sstride, B_V1, n2);
+    }
+    w.wait(k & 1);
+    const double* sb = w.buf(k & 1) - (size_t)B_GA * TL;           // sb[f] valid for B_GA <= f < B_P
+    const double* vv = w.buf(k & 1) - (size_t)(B_V1 - n1) * TL;    // vv[f] valid for B_V1 <= f < NSB
+    double* fac = q.sb + qs_blk(tile, N, k, NSB, lane);
     double g[15];
 #pragma unroll
-    for (int i = 0; i < 15; ++i) g[i] = QF(hc, H_GA + i) + (mode == 1 ? QF(vv, V_1 + i) : 0.0) - sigmu * QF(vv, V_2 + i);
+    for (int i = 0; i < 15; ++i) g[i] = QF(sb, H_GA + i) + (mode == 1 ? QF(vv, V_1 + i) : 0.0) - sigmu * QF(vv, V_2 + i);
     if (k < N) {
       double y[10];
 #pragma unroll
-      for (int i = 0; i < 10; ++i) y[i] = QF(fac, F_WV + i) + pn[i];
+      for (int i = 0; i < 10; ++i) y[i] = QF(sb, F_WV + i) + pn[i];
 #pragma unroll
       for (int j = 0; j < 5; ++j) {
         g[j] += a2 * y[j] + dt * y[5 + j];
@@ -689,9 +738,11 @@ SMPC_HD void qs_ric2(const smpc_problem_t& P, const QsBufs& q, int tile, int lan
 #pragma unroll
     for (int j = 0; j < 5; ++j)
 #pragma unroll
-      for (int i = j + 1; i < 15; ++i) g[i] -= QF(fac, F_T + i * 5 + j) * g[j];
+      for (int i = j + 1; i < 15; ++i) g[i] -= QF(sb, F_T + i * 5 + j) * g[j];
+    if (on) {
 #pragma unroll
-    for (int i = 0; i < 15; ++i) QF(fac, F_LP + i) = g[i];
+      for (int i = 0; i < 15; ++i) QF(fac, F_LP + i) = g[i];
+    }
 #pragma unroll
     for (int i = 0; i < 10; ++i) pn[i] = g[5 + i];
     if (k == 0) {
@@ -709,20 +760,27 @@ SMPC_HD void qs_ric2(const smpc_problem_t& P, const QsBufs& q, int tile, int lan
       }
     }
   }
+  // forward: stages fetch RB LP T WV P = [B_RB, B_V1)
+  w.publish();
+  w.sync();
+  w.fetch_begin(0, B_V1 - B_RB);
+  w.fetch(0, 0, gsb, B_RB, B_V1 - B_RB);
   for (int k = 0; k <= N; ++k) {
-    const double* fac = q.fac + qs_blk(tile, N, k, NFAC, lane);
-    const double* hc = q.hc + qs_blk(tile, N, k, NHC, lane);
+    w.sync();
+    if (k < N) { w.fetch_begin((k + 1) & 1, B_V1 - B_RB); w.fetch((k + 1) & 1, 0, gsb + (size_t)(k + 1) * sstride, B_RB, B_V1 - B_RB); }
+    w.wait(k & 1);
+    const double* sb = w.buf(k & 1) - (size_t)B_RB * TL;
     double* st = q.st + qs_blk(tile, N, k, NIT, lane);
     // multiplier step of the link k-1 -> k:  dpi = P_k dx_k + p_k
 #pragma unroll
     for (int i = 0; i < 10; ++i) {
       double s = 0.0;
       if (k > 0) {
-        s = QF(fac, F_LP + 5 + i);
+        s = QF(sb, F_LP + 5 + i);
 #pragma unroll
-        for (int j = 0; j < 10; ++j) s += QF(fac, F_P + trs(i, j)) * dx[j];
+        for (int j = 0; j < 10; ++j) s += QF(sb, F_P + trs(i, j)) * dx[j];
       }
-      QF(st, I_PIM + i) = s;
+      if (on) QF(st, I_PIM + i) = s;
     }
     double du[5];
 #pragma unroll
@@ -730,26 +788,28 @@ SMPC_HD void qs_ric2(const smpc_problem_t& P, const QsBufs& q, int tile, int lan
     if (k < N) {
 #pragma unroll
       for (int i = 0; i < 5; ++i) {
-        double w = QF(fac, F_T + i * 5 + i) * QF(fac, F_LP + i);
+        double ws = QF(sb, F_T + i * 5 + i) * QF(sb, F_LP + i);
 #pragma unroll
-        for (int r = 0; r < 10; ++r) w += QF(fac, F_T + (5 + r) * 5 + i) * dx[r];
-        du[i] = -w;
+        for (int r = 0; r < 10; ++r) ws += QF(sb, F_T + (5 + r) * 5 + i) * dx[r];
+        du[i] = -ws;
       }
 #pragma unroll
       for (int c = 4; c >= 1; --c)
 #pragma unroll
-        for (int i = 0; i < c; ++i) du[i] -= QF(fac, F_T + c * 5 + i) * du[c];
+        for (int i = 0; i < c; ++i) du[i] -= QF(sb, F_T + c * 5 + i) * du[c];
     }
+    if (on) {
 #pragma unroll
-    for (int i = 0; i < 5; ++i) QF(st, I_Z + i) = du[i];
+      for (int i = 0; i < 5; ++i) QF(st, I_Z + i) = du[i];
 #pragma unroll
-    for (int i = 0; i < 10; ++i) QF(st, I_Z + 5 + i) = dx[i];
+      for (int i = 0; i < 10; ++i) QF(st, I_Z + 5 + i) = dx[i];
+    }
     if (k < N) {
       double nx[10];
 #pragma unroll
       for (int j = 0; j < 5; ++j) {
-        nx[j] = dx[j] + dt * dx[5 + j] + a2 * du[j] + QF(hc, H_RB + j);
-        nx[5 + j] = dx[5 + j] + dt * du[j] + QF(hc, H_RB + 5 + j);
+        nx[j] = dx[j] + dt * dx[5 + j] + a2 * du[j] + QF(sb, H_RB + j);
+        nx[5 + j] = dx[5 + j] + dt * du[j] + QF(sb, H_RB + 5 + j);
       }
 #pragma unroll
       for (int j = 0; j < 10; ++j) dx[j] = nx[j];
@@ -913,7 +973,7 @@ SMPC_HD void qs_step(const smpc_problem_t& P, const QsBufs& q, int tile, int lan
     for (int h = 0; h < 6; ++h) QF(st, I_SLK + h) = 0.0;
   }
   if (mode == 0) {
-    double* vv = q.v + qs_blk(tile, N, k, NV, lane);
+    double* vv = q.sb + qs_blk(tile, N, k, NV, lane);
     if (k == N) {
 #pragma unroll
       for (int i = 0; i < 5; ++i) { v1[i] = 0.0; v2[i] = 0.0; }

@@ -48,6 +48,28 @@ namespace {
 // over (tile, stage, lane) in a caller-chosen order (ascending / descending), so that a phase that reads what
 // another work item of the same phase writes shows up as an order-dependent result in the parity test.
 // ----------------------------------------------------------------------------------------------------------------
+// host stand-in of the staged copies of the Riccati sweeps: one lane at a time; lazy = 1 performs a copy only when it
+// is waited for (a fetch issued before its source has been written then shows up as wrong numbers)
+struct HostStage {
+  int ln, nfb, lazy;
+  std::vector<double> mem;
+  struct Copy { double* dst; const double* src; size_t n; };
+  std::vector<Copy> pend[2];
+  HostStage(int lane_, int nfb_, int lazy_) : ln(lane_), nfb(nfb_), lazy(lazy_), mem((size_t)2 * nfb_ * TL, 0.0) {}
+  int lane() const { return ln; }
+  bool any(bool v) const { return v; }
+  void sync() const {}
+  double* buf(int b) { return mem.data() + (size_t)b * nfb * TL + ln; }
+  void fetch_begin(int, int) {}
+  void fetch(int b, int dst_field, const double* gblock, int src_field, int nfields) {
+    Copy c{mem.data() + ((size_t)b * nfb + dst_field) * TL, gblock + (size_t)src_field * TL, (size_t)nfields * TL};
+    if (dst_field + nfields > nfb) { fprintf(stderr, "emu: staging overflow\n"); abort(); }
+    if (lazy) pend[b].push_back(c); else std::memcpy(c.dst, c.src, c.n * sizeof(double));
+  }
+  void wait(int b) { for (auto& c : pend[b]) std::memcpy(c.dst, c.src, c.n * sizeof(double)); pend[b].clear(); }
+  void publish() const {}
+};
+
 struct HostBackend {
   const smpc_problem_t& P;
   QsBufs q;
@@ -72,8 +94,8 @@ struct HostBackend {
     n_active = 0;
     each_problem([&](int t, int l) { if (qs_ctl(P, q, t, l, kk, xt, ut, status, qp_iter, qp_status, qp_res)) ++n_active; });
   }
-  void ric1() { each_problem([&](int t, int l) { qs_ric1(P, q, t, l, psm.data() + l); }); }
-  void ric2(int mode) { each_problem([&](int t, int l) { qs_ric2(P, q, t, l, mode); }); }
+  void ric1() { each_problem([&](int t, int l) { HostStage w(l, RIC1_STAGE_FIELDS, order); qs_ric1(P, q, t, w, psm.data() + l); }); }
+  void ric2(int mode) { each_problem([&](int t, int l) { HostStage w(l, RIC2_STAGE_FIELDS, order); qs_ric2(P, q, t, w, mode); }); }
   void step(int kk, int mode) { each_stage([&](int t, int l, int k) { qs_step(P, q, t, l, k, kk, mode); }); }
   void red(bool after) { each_problem([&](int t, int l) { qs_red(P, q, t, l, after); }); }
   void sync(int& na, int& nr) {
@@ -91,14 +113,13 @@ extern "C" int emu_qp_solve(const smpc_problem_t* P, int B, const double* rec, c
                             int32_t* qp_iter, int32_t* qp_status, double* qp_res, int* n_redo_total) {
   const int N = P->N, T = (B + TL - 1) / TL;
   const size_t S = (size_t)T * (N + 1) * TL;
-  std::vector<double> vrec(S * REC, 0.0), it0(S * NIT, 0.0), it1(S * NIT, 0.0), st(S * NIT, 0.0), hc(S * NHC, 0.0), vv(S * NV, 0.0),
-      fac(S * NFAC, 0.0), prod(S * NPROD, 0.0), res(S * NRES, 0.0), stp(S * NSTP, 0.0), pd((size_t)T * NPD * TL, 0.0);
+  std::vector<double> vrec(S * REC, 0.0), it0(S * NIT, 0.0), it1(S * NIT, 0.0), st(S * NIT, 0.0), sb(S * NSB, 0.0), prod(S * NPROD, 0.0), res(S * NRES, 0.0), stp(S * NSTP, 0.0), pd((size_t)T * NPD * TL, 0.0);
   std::vector<int32_t> pi32((size_t)T * NPI * TL, 0);
   for (int b = 0; b < B; ++b)
     for (int k = 0; k <= N; ++k)
       for (int f = 0; f < REC; ++f)
         vrec[qs_blk(b / TL, N, k, REC, b % TL) + (size_t)f * TL] = rec[((size_t)b * (N + 1) + k) * REC + f];
-  QsBufs q{vrec.data(), {it0.data(), it1.data()}, st.data(), hc.data(), vv.data(), fac.data(), prod.data(), res.data(), stp.data(),
+  QsBufs q{vrec.data(), {it0.data(), it1.data()}, st.data(), sb.data(), prod.data(), res.data(), stp.data(),
            pd.data(), pi32.data(), N};
   HostBackend bk{*P, q, B, T, N, order, x0, r, act, xt, ut, status, qp_iter, qp_status, qp_res, std::vector<double>(2 * 65 * TL, 0.0)};
   struct Counting : HostBackend {

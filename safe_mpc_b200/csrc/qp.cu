@@ -17,6 +17,12 @@ namespace smpc {
 namespace {
 
 constexpr int SP_WARPS = 4;      // warps per CTA of the stage-parallel kernels
+#ifndef QS_RIC_NBUF
+#define QS_RIC_NBUF 1            // staging buffers of the Riccati sweeps (1: more resident warps per SM, no fetch overlap)
+#endif
+#ifndef QS_PREP_MINB
+#define QS_PREP_MINB 4
+#endif
 #ifndef QS_SP_MINB
 #define QS_SP_MINB 3             // resident CTAs per SM the register allocation of prep / step is sized for
 #endif
@@ -26,10 +32,14 @@ __global__ void __launch_bounds__(32) qs_init_kernel(QsBufs q, int B, const doub
   qs_init(q, blockIdx.x, threadIdx.x, B, x0, r, act);
 }
 
-__global__ void __launch_bounds__(32 * SP_WARPS, QS_SP_MINB) qs_prep_kernel(const smpc_problem_t* __restrict__ dP, QsBufs q, int T, int kk) {
-  const int w = blockIdx.x * SP_WARPS + (threadIdx.x >> 5);
+constexpr size_t PREP_SMEM = sizeof(double) * 2 * PREP_SCRATCH * TL;
+constexpr int PREP_WARPS = 2;    // warps per CTA of prep: 2 x 26.9 KB of lane-private Jacobian scratch, 4 CTAs per SM
+__global__ void __launch_bounds__(32 * PREP_WARPS, QS_PREP_MINB) qs_prep_kernel(const smpc_problem_t* __restrict__ dP, QsBufs q, int T, int kk) {
+  extern __shared__ __align__(128) double jsm_all[];
+  const int wi = threadIdx.x >> 5;
+  const int w = blockIdx.x * PREP_WARPS + wi;
   if (w >= T * (q.N + 1)) return;
-  qs_prep(*dP, q, w / (q.N + 1), threadIdx.x & 31, w % (q.N + 1), kk);
+  qs_prep(*dP, q, w / (q.N + 1), threadIdx.x & 31, w % (q.N + 1), kk, jsm_all + (size_t)wi * PREP_SCRATCH * TL + (threadIdx.x & 31));
 }
 
 template <int MODE>
@@ -39,11 +49,19 @@ __global__ void __launch_bounds__(32 * SP_WARPS, QS_SP_MINB) qs_step_kernel(cons
   qs_step(*dP, q, w / (q.N + 1), threadIdx.x & 31, w % (q.N + 1), kk, MODE);
 }
 
-__global__ void __launch_bounds__(32) qs_ctl_kernel(const smpc_problem_t* __restrict__ dP, QsBufs q, int kk, double* xt, double* ut,
-                                                     int32_t* status, int32_t* qp_iter, int32_t* qp_status, double* qp_res, int* counters) {
-  const bool on = qs_ctl(*dP, q, blockIdx.x, threadIdx.x, kk, xt, ut, status, qp_iter, qp_status, qp_res);
+__global__ void __launch_bounds__(32) qs_ctl_kernel(const smpc_problem_t* __restrict__ dP, QsBufs q, int kk, int32_t* status, int32_t* qp_iter,
+                                                     int32_t* qp_status, double* qp_res, int* counters) {
+  const bool on = qs_ctl(*dP, q, blockIdx.x, threadIdx.x, kk, status, qp_iter, qp_status, qp_res);
   const unsigned m = __ballot_sync(0xffffffffu, on);
   if (threadIdx.x == 0 && m) atomicAdd(&counters[2 * kk], __popc(m));
+}
+
+__global__ void __launch_bounds__(32 * SP_WARPS) qs_final_kernel(QsBufs q, int T, int B, const uint8_t* __restrict__ act, int32_t* status,
+                                                                 double* xt, double* ut) {
+  const int w = blockIdx.x * SP_WARPS + (threadIdx.x >> 5);
+  if (w >= T * (q.N + 1)) return;
+  const int tile = w / (q.N + 1), lane = threadIdx.x & 31;
+  if (qs_final(q, tile, lane, w % (q.N + 1), act, B, status, xt, ut)) atomicExch(&status[tile * TL + lane], 1);
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -56,6 +74,7 @@ struct TmaStage {
   uint32_t phase[2];
   int ln, nfb;
   __device__ __forceinline__ int lane() const { return ln; }
+  __device__ __forceinline__ int nbuf() const { return QS_RIC_NBUF; }
   __device__ __forceinline__ bool any(bool v) const { return __any_sync(0xffffffffu, v) != 0; }
   __device__ __forceinline__ void sync() const { __syncwarp(); }
   __device__ __forceinline__ double* buf(int b) const { return sm + (size_t)b * nfb * TL + ln; }
@@ -91,15 +110,15 @@ struct TmaStage {
   __device__ __forceinline__ void publish() const { asm volatile("fence.proxy.async;" ::: "memory"); }
 };
 
-constexpr size_t RIC1_SMEM = sizeof(double) * (2 * RIC1_STAGE_FIELDS + 2 * 65) * TL + 16;
-constexpr size_t RIC2_SMEM = sizeof(double) * (2 * RIC2_STAGE_FIELDS) * TL + 16;
+constexpr size_t RIC1_SMEM = sizeof(double) * (QS_RIC_NBUF * RIC1_STAGE_FIELDS + 65) * TL + 16;
+constexpr size_t RIC2_SMEM = sizeof(double) * (QS_RIC_NBUF * RIC2_STAGE_FIELDS) * TL + 16;
 
 __global__ void __launch_bounds__(32) qs_ric1_kernel(const smpc_problem_t* __restrict__ dP, QsBufs q) {
   extern __shared__ __align__(128) double smem[];
   TmaStage w;
   w.sm = smem; w.nfb = RIC1_STAGE_FIELDS; w.ln = threadIdx.x;
-  double* psm = smem + (size_t)2 * RIC1_STAGE_FIELDS * TL;
-  w.bar = reinterpret_cast<uint64_t*>(psm + 2 * 65 * TL);
+  double* psm = smem + (size_t)QS_RIC_NBUF * RIC1_STAGE_FIELDS * TL;
+  w.bar = reinterpret_cast<uint64_t*>(psm + 65 * TL);
   w.init();
   qs_ric1(*dP, q, blockIdx.x, w, psm + threadIdx.x);
 }
@@ -109,7 +128,7 @@ __global__ void __launch_bounds__(32) qs_ric2_kernel(const smpc_problem_t* __res
   extern __shared__ __align__(128) double smem[];
   TmaStage w;
   w.sm = smem; w.nfb = RIC2_STAGE_FIELDS; w.ln = threadIdx.x;
-  w.bar = reinterpret_cast<uint64_t*>(smem + (size_t)2 * RIC2_STAGE_FIELDS * TL);
+  w.bar = reinterpret_cast<uint64_t*>(smem + (size_t)QS_RIC_NBUF * RIC2_STAGE_FIELDS * TL);
   w.init();
   qs_ric2(*dP, q, blockIdx.x, w, MODE);
 }
@@ -190,6 +209,7 @@ QpSolver* qp_create(int B, int N, int iter_max, cudaStream_t stream, cudaError_t
   if (e == cudaSuccess) e = cudaMemsetAsync(s->pi, 0, sizeof(int32_t) * T * NPI * TL, stream);
   if (e == cudaSuccess) e = cudaMalloc((void**)&s->counters, sizeof(int) * 2 * (iter_max + 2));
   if (e == cudaSuccess) e = cudaMallocHost((void**)&s->h_counters, sizeof(int) * 2);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(qs_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PREP_SMEM);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(qs_ric1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RIC1_SMEM);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(qs_ric2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RIC2_SMEM);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(qs_ric2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RIC2_SMEM);
@@ -239,10 +259,13 @@ struct DeviceBackend {
     qs_init_kernel<<<s->T, 32, 0, c.stream>>>(s->q, s->B, x0, r, act);
     count();
   }
-  void prep(int kk) { qs_prep_kernel<<<sp_grid(), 32 * SP_WARPS, 0, c.stream>>>(dP, s->q, s->T, kk); count(); }
+  void prep(int kk) {
+    qs_prep_kernel<<<(s->T * (s->N + 1) + PREP_WARPS - 1) / PREP_WARPS, 32 * PREP_WARPS, PREP_SMEM, c.stream>>>(dP, s->q, s->T, kk);
+    count();
+  }
   void ctl(int kk) {
     kk_last = kk;
-    qs_ctl_kernel<<<s->T, 32, 0, c.stream>>>(dP, s->q, kk, xt, ut, status, qp_iter, qp_status, qp_res, s->counters);
+    qs_ctl_kernel<<<s->T, 32, 0, c.stream>>>(dP, s->q, kk, status, qp_iter, qp_status, qp_res, s->counters);
     count();
   }
   void ric1() { qs_ric1_kernel<<<s->T, 32, RIC1_SMEM, c.stream>>>(dP, s->q); count(); }
@@ -257,6 +280,7 @@ struct DeviceBackend {
     else qs_step_kernel<2><<<sp_grid(), 32 * SP_WARPS, 0, c.stream>>>(dP, s->q, s->T, kk);
     count();
   }
+  void final() { qs_final_kernel<<<sp_grid(), 32 * SP_WARPS, 0, c.stream>>>(s->q, s->T, s->B, act, status, xt, ut); count(); }
   void red(bool after) { qs_red_kernel<<<s->T, 32, 0, c.stream>>>(dP, s->q, kk_last, after ? 1 : 0, s->counters); count(); }
   void sync(int& na, int& nr) {
     cudaError_t e = cudaMemcpyAsync(s->h_counters, s->counters + 2 * kk_last, 2 * sizeof(int), cudaMemcpyDeviceToHost, c.stream);

@@ -129,7 +129,10 @@ struct QsNorms {
 // ================================================================================================================
 // prep: (cold start | primal-dual update) + residuals + condensation.   thread = (problem, stage)
 // ================================================================================================================
-SMPC_HD void qs_prep(const smpc_problem_t& P, const QsBufs& q, int tile, int lane, int k, int kk) {
+// jsm: lane-private on-chip scratch [PREP_SCRATCH][TL] (lane offset applied) that keeps the torque and capsule Jacobians
+// of the stage between their three uses (row products, multiplier terms, condensation): each entry is read ~10 times.
+enum { PREP_SCRATCH = 105 };
+SMPC_HD void qs_prep(const smpc_problem_t& P, const QsBufs& q, int tile, int lane, int k, int kk, double* jsm) {
   const int N = q.N;
   const int32_t* pi = q.pi + qs_pb(tile, NPI, lane);
   if (!QF(pi, J_ACT)) return;
@@ -165,8 +168,6 @@ SMPC_HD void qs_prep(const smpc_problem_t& P, const QsBufs& q, int tile, int lan
 #pragma unroll
     for (int i = 0; i < 5; ++i) z[i] = 0.0;
   }
-#pragma unroll
-  for (int i = 0; i < 15; ++i) QF(ito, I_Z + i) = z[i];
 
   // ---- stationarity residual: H z + g + [B A]' pi_{k+1} - pi_k  (inequality multipliers are added row by row below) ----
   double rg[15], gd[15];
@@ -185,11 +186,11 @@ SMPC_HD void qs_prep(const smpc_problem_t& P, const QsBufs& q, int tile, int lan
     }
   }
   // multipliers of the dynamics: pi_k (link k-1 -> k, stored with stage k), pi_{k+1}
+  double pimv[10];
 #pragma unroll
   for (int j = 0; j < 10; ++j) {
-    const double pim = (first || k == 0) ? 0.0 : QF(iti, I_PIM + j) + a * QF(st, I_PIM + j);
-    QF(ito, I_PIM + j) = pim;
-    rg[5 + j] -= pim;
+    pimv[j] = (first || k == 0) ? 0.0 : QF(iti, I_PIM + j) + a * QF(st, I_PIM + j);
+    rg[5 + j] -= pimv[j];
   }
   if (k < N) {
     const double* itn = q.it[(kk & 1) ^ 1] + qs_blk(tile, N, k + 1, NIT, lane);
@@ -222,16 +223,25 @@ SMPC_HD void qs_prep(const smpc_problem_t& P, const QsBufs& q, int tile, int lan
 #pragma unroll
     for (int j = 0; j < 10; ++j) { QF(hc, H_RB + j) = rb[j]; nr.nb = fmax(nr.nb, fabs(rb[j])); nr.chk += rb[j]; }
   }
+  // (stores of this phase come after all of its loads, see the note on the row phases below)
+#pragma unroll
+  for (int i = 0; i < 15; ++i) QF(ito, I_Z + i) = z[i];
+#pragma unroll
+  for (int j = 0; j < 10; ++j) QF(ito, I_PIM + j) = pimv[j];
 
   // ---- rows: (lam, t) update or cold start, residuals, condensation terms ----
-  // one side of a row; returns G = lam/t and c = (lam t - lam r)/t  (mode-0 right-hand side)
-  auto side = [&](int slot, double sgn, double az, double bnd, double slack, double tinit, double& lam, double& G, double& c) {
-    double t;
+  // Loads and stores are kept in separate phases (all row products and all updated (lam, t) of a row group first, then
+  // the stores): the compiler may not move a load above a store it cannot prove disjoint, and one load round trip per
+  // slot would serialise the thread on memory latency.
+  auto upd = [&](int slot, double tinit, double& lam, double& t) {
     if (first) { t = tinit; lam = mu0 / t; }
     else {
       lam = fmax(QF(iti, I_LAM + slot) + a * QF(st, I_LAM + slot), lam_min);
       t = fmax(QF(iti, I_T + slot) + a * QF(st, I_T + slot), t_min);
     }
+  };
+  // one side of a row; returns G = lam/t and c = (lam t - lam r)/t  (mode-0 right-hand side)
+  auto side = [&](int slot, double sgn, double az, double bnd, double slack, double lam, double t, double& G, double& c) {
     QF(ito, I_LAM + slot) = lam; QF(ito, I_T + slot) = t;
     const double r = t - (sgn * (az - bnd) + slack);
     const double rm = lam * t;
@@ -240,84 +250,116 @@ SMPC_HD void qs_prep(const smpc_problem_t& P, const QsBufs& q, int tile, int lan
     c = (rm - lam * r) * it_;
     nr.mu += rm; nr.chk += rm + r; nr.nm = fmax(nr.nm, fabs(rm)); nr.nd = fmax(nr.nd, fabs(r)); nr.cnt += 1;
   };
-  double Gb[10], Gg[12];
-  // box rows
+  // row products and bounds of the general rows (loads only)
+  double azg[12], glo[12], ghi[12];
 #pragma unroll
-  for (int j = 0; j < 10; ++j) {
-    double tl = 0.0, tu = 0.0;
-    if (first) qs_zinit(blo[j], bhi[j], tl, tu);
-    double ll, lu, Gl, Gu, cl, cu;
-    side(j, 1.0, z[5 + j], blo[j], 0.0, tl, ll, Gl, cl);
-    side(QNR + j, -1.0, z[5 + j], bhi[j], 0.0, tu, lu, Gu, cu);
-    Gb[j] = Gl + Gu;
-    rg[5 + j] += lu - ll;
-    gd[5 + j] += cl - cu;
-  }
-  // torque rows
-#pragma unroll
-  for (int r = 0; r < 5; ++r) Gg[r] = 0.0;
+  for (int r = 0; r < 12; ++r) { azg[r] = 0.0; glo[r] = 0.0; ghi[r] = 0.0; }
   if (F.tau) {
 #pragma unroll
     for (int r = 0; r < 5; ++r) {
       double az = 0.0;
 #pragma unroll
-      for (int c = 0; c < 15; ++c) az += QF(rec, SMPC_REC_JTAU + r * 15 + c) * z[c];
+      for (int c = 0; c < 15; ++c) { const double jv = QF(rec, SMPC_REC_JTAU + r * 15 + c); QF(jsm, r * 15 + c) = jv; az += jv * z[c]; }
       const double v = QF(rec, SMPC_REC_TAU + r);
-      const double lo = P.tau_min[r] - v, hi = P.tau_max[r] - v;
-      double ll, lu, Gl, Gu, cl, cu;
-      side(10 + r, 1.0, az, lo, 0.0, fmax(thr0, az - lo), ll, Gl, cl);
-      side(QNR + 10 + r, -1.0, az, hi, 0.0, fmax(thr0, hi - az), lu, Gu, cu);
-      Gg[r] = Gl + Gu;
-      const double nu = lu - ll, gam = cl - cu;
-#pragma unroll
-      for (int c = 0; c < 15; ++c) { const double jv = QF(rec, SMPC_REC_JTAU + r * 15 + c); rg[c] += jv * nu; gd[c] += jv * gam; }
+      azg[r] = az; glo[r] = P.tau_min[r] - v; ghi[r] = P.tau_max[r] - v;
     }
   }
-  // capsule rows
-#pragma unroll
-  for (int p = 0; p < 6; ++p) Gg[5 + p] = 0.0;
   if (F.dist) {
 #pragma unroll
     for (int p = 0; p < 6; ++p) {
       double az = 0.0;
 #pragma unroll
-      for (int c = 0; c < 5; ++c) az += QF(rec, SMPC_REC_JDIST + p * 5 + c) * z[5 + c];
+      for (int c = 0; c < 5; ++c) { const double jv = QF(rec, SMPC_REC_JDIST + p * 5 + c); QF(jsm, 75 + p * 5 + c) = jv; az += jv * z[5 + c]; }
       const double v = QF(rec, SMPC_REC_DIST + p);
-      const double lo = P.pair_lo_ocp[p] - v, hi = P.pair_hi - v;
-      double ll, lu, Gl, Gu, cl, cu;
-      side(15 + p, 1.0, az, lo, 0.0, fmax(thr0, az - lo), ll, Gl, cl);
-      side(QNR + 15 + p, -1.0, az, hi, 0.0, fmax(thr0, hi - az), lu, Gu, cu);
-      Gg[5 + p] = Gl + Gu;
-      const double nu = lu - ll, gam = cl - cu;
-#pragma unroll
-      for (int c = 0; c < 5; ++c) { const double jv = QF(rec, SMPC_REC_JDIST + p * 5 + c); rg[5 + c] += jv * nu; gd[5 + c] += jv * gam; }
+      azg[5 + p] = az; glo[5 + p] = P.pair_lo_ocp[p] - v; ghi[5 + p] = P.pair_hi - v;
     }
   }
-  // viability row (may be soft)
-  Gg[11] = 0.0;
   if (F.nn) {
     double az = 0.0;
 #pragma unroll
     for (int c = 0; c < 10; ++c) az += QF(rec, SMPC_REC_JNN + c) * z[5 + c];
     const double v = QF(rec, SMPC_REC_NN);
-    const double lo = 0.0 - v, hi = 1e6 - v;
-    double sl[2] = {0.0, 0.0}, ls[2] = {0.0, 0.0}, ts[2] = {0.0, 0.0};
-    if (F.soft) {
+    azg[11] = az; glo[11] = 0.0 - v; ghi[11] = 1e6 - v;
+  }
+  double Gb[10], Gg[12];
+  // box rows
+  {
+    double bl[20], bt[20];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        if (first) { sl[h] = thr0; ls[h] = mu0 / thr0; ts[h] = thr0; }
-        else {
-          sl[h] = QF(iti, I_SLK + h) + a * QF(st, I_SLK + h);
-          ls[h] = fmax(QF(iti, I_SLK + 2 + h) + a * QF(st, I_SLK + 2 + h), lam_min);
-          ts[h] = fmax(QF(iti, I_SLK + 4 + h) + a * QF(st, I_SLK + 4 + h), t_min);
-        }
-      }
+    for (int j = 0; j < 10; ++j) {
+      double tl = 0.0, tu = 0.0;
+      if (first) qs_zinit(blo[j], bhi[j], tl, tu);
+      upd(j, tl, bl[j], bt[j]);
+      upd(QNR + j, tu, bl[10 + j], bt[10 + j]);
     }
 #pragma unroll
+    for (int j = 0; j < 10; ++j) {
+      double Gl, Gu, cl, cu;
+      side(j, 1.0, z[5 + j], blo[j], 0.0, bl[j], bt[j], Gl, cl);
+      side(QNR + j, -1.0, z[5 + j], bhi[j], 0.0, bl[10 + j], bt[10 + j], Gu, cu);
+      Gb[j] = Gl + Gu;
+      rg[5 + j] += bl[10 + j] - bl[j];
+      gd[5 + j] += cl - cu;
+    }
+  }
+  // general rows: updated (lam, t) of every slot, slack triplets of the soft row
+  double gl[24], gt[24];
+#pragma unroll
+  for (int r = 0; r < 12; ++r) {
+    const bool pres = r < 5 ? F.tau : (r < 11 ? F.dist : F.nn);
+    gl[r] = gt[r] = gl[12 + r] = gt[12 + r] = 0.0;
+    if (pres) {
+      upd(10 + r, fmax(thr0, azg[r] - glo[r]), gl[r], gt[r]);
+      upd(QNR + 10 + r, fmax(thr0, ghi[r] - azg[r]), gl[12 + r], gt[12 + r]);
+    }
+  }
+  double sl[2] = {0.0, 0.0}, ls[2] = {0.0, 0.0}, ts[2] = {0.0, 0.0};
+  if (F.soft) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (first) { sl[h] = thr0; ls[h] = mu0 / thr0; ts[h] = thr0; }
+      else {
+        sl[h] = QF(iti, I_SLK + h) + a * QF(st, I_SLK + h);
+        ls[h] = fmax(QF(iti, I_SLK + 2 + h) + a * QF(st, I_SLK + 2 + h), lam_min);
+        ts[h] = fmax(QF(iti, I_SLK + 4 + h) + a * QF(st, I_SLK + 4 + h), t_min);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 12; ++r) Gg[r] = 0.0;
+  if (F.tau) {
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {
+      double Gl, Gu, cl, cu;
+      side(10 + r, 1.0, azg[r], glo[r], 0.0, gl[r], gt[r], Gl, cl);
+      side(QNR + 10 + r, -1.0, azg[r], ghi[r], 0.0, gl[12 + r], gt[12 + r], Gu, cu);
+      Gg[r] = Gl + Gu;
+      const double nu = gl[12 + r] - gl[r], gam = cl - cu;
+#pragma unroll
+      for (int c = 0; c < 15; ++c) { const double jv = QF(jsm, r * 15 + c); rg[c] += jv * nu; gd[c] += jv * gam; }
+    }
+  }
+  if (F.dist) {
+#pragma unroll
+    for (int p = 0; p < 6; ++p) {
+      const int r = 5 + p;
+      double Gl, Gu, cl, cu;
+      side(10 + r, 1.0, azg[r], glo[r], 0.0, gl[r], gt[r], Gl, cl);
+      side(QNR + 10 + r, -1.0, azg[r], ghi[r], 0.0, gl[12 + r], gt[12 + r], Gu, cu);
+      Gg[r] = Gl + Gu;
+      const double nu = gl[12 + r] - gl[r], gam = cl - cu;
+#pragma unroll
+      for (int c = 0; c < 5; ++c) { const double jv = QF(jsm, 75 + p * 5 + c); rg[5 + c] += jv * nu; gd[5 + c] += jv * gam; }
+    }
+  }
+  // viability row (may be soft)
+  if (F.nn) {
+#pragma unroll
     for (int h = 0; h < 2; ++h) { QF(ito, I_SLK + h) = sl[h]; QF(ito, I_SLK + 2 + h) = ls[h]; QF(ito, I_SLK + 4 + h) = ts[h]; }
-    double ll, lu, Gl, Gu, cl, cu;
-    side(21, 1.0, az, lo, sl[0], fmax(thr0, az - lo), ll, Gl, cl);
-    side(QNR + 21, -1.0, az, hi, sl[1], fmax(thr0, hi - az), lu, Gu, cu);
+    const double ll = gl[11], lu = gl[23];
+    double Gl, Gu, cl, cu;
+    side(21, 1.0, azg[11], glo[11], sl[0], gl[11], gt[11], Gl, cl);
+    side(QNR + 21, -1.0, azg[11], ghi[11], sl[1], gl[23], gt[23], Gu, cu);
     if (F.soft) {
       const double lam2[2] = {ll, lu};
       double G2[2] = {Gl, Gu}, c2[2] = {cl, cu};
@@ -342,9 +384,6 @@ SMPC_HD void qs_prep(const smpc_problem_t& P, const QsBufs& q, int tile, int lan
     const double nu = lu - ll, gam = cl - cu;
 #pragma unroll
     for (int c = 0; c < 10; ++c) { const double jv = QF(rec, SMPC_REC_JNN + c); rg[5 + c] += jv * nu; gd[5 + c] += jv * gam; }
-  } else {
-#pragma unroll
-    for (int h = 0; h < 6; ++h) QF(ito, I_SLK + h) = 0.0;
   }
   if (k == N) {
 #pragma unroll
@@ -370,17 +409,17 @@ SMPC_HD void qs_prep(const smpc_problem_t& P, const QsBufs& q, int tile, int lan
       if (F.tau) {
 #pragma unroll
         for (int r = 0; r < 5; ++r) {
-          const double w = Gg[r] * QF(rec, SMPC_REC_JTAU + r * 15 + i);
+          const double w = Gg[r] * QF(jsm, r * 15 + i);
 #pragma unroll
-          for (int c = 0; c <= i; ++c) acc[c] += w * QF(rec, SMPC_REC_JTAU + r * 15 + c);
+          for (int c = 0; c <= i; ++c) acc[c] += w * QF(jsm, r * 15 + c);
         }
       }
       if (F.dist && i >= 5 && i < 10) {
 #pragma unroll
         for (int p = 0; p < 6; ++p) {
-          const double w = Gg[5 + p] * QF(rec, SMPC_REC_JDIST + p * 5 + i - 5);
+          const double w = Gg[5 + p] * QF(jsm, 75 + p * 5 + i - 5);
 #pragma unroll
-          for (int c = 5; c <= i; ++c) acc[c] += w * QF(rec, SMPC_REC_JDIST + p * 5 + c - 5);
+          for (int c = 5; c <= i; ++c) acc[c] += w * QF(jsm, 75 + p * 5 + c - 5);
         }
       }
       if (F.nn && i >= 5) {
@@ -401,13 +440,14 @@ SMPC_HD void qs_prep(const smpc_problem_t& P, const QsBufs& q, int tile, int lan
 // ctl: residual norms of the new iterate, exit tests (same control flow as the oracle's QpIpm::solve), result.
 // thread = problem.  Returns true when the problem stays active.
 // ================================================================================================================
-SMPC_HD bool qs_ctl(const smpc_problem_t& P, const QsBufs& q, int tile, int lane, int kk, double* xt, double* ut, int32_t* status,
-                    int32_t* qp_iter, int32_t* qp_status, double* qp_res) {
+SMPC_HD bool qs_ctl(const smpc_problem_t& P, const QsBufs& q, int tile, int lane, int kk, int32_t* status, int32_t* qp_iter,
+                    int32_t* qp_status, double* qp_res) {
   const int N = q.N;
   int32_t* pi = q.pi + qs_pb(tile, NPI, lane);
   if (!QF(pi, J_ACT)) return false;
   double* pd = q.pd + qs_pb(tile, NPD, lane);
   double ng = 0.0, nb = 0.0, nd = 0.0, nm = 0.0, mu = 0.0, chk = 0.0, cnt = 0.0;
+#pragma unroll 8
   for (int k = 0; k <= N; ++k) {
     const double* res = q.res + qs_blk(tile, N, k, NRES, lane);
     ng = fmax(ng, QF(res, R_NG)); nb = fmax(nb, QF(res, R_NB)); nd = fmax(nd, QF(res, R_ND)); nm = fmax(nm, QF(res, R_NM));
@@ -429,29 +469,37 @@ SMPC_HD bool qs_ctl(const smpc_problem_t& P, const QsBufs& q, int tile, int lane
   int qst;
   if (nan) qst = 3; else if (!unconv) qst = 0; else if (kk >= P.qp_iter_max) qst = 1; else qst = 2;
   QF(pi, J_ACT) = 0; QF(pi, J_ITER) = kk; QF(pi, J_QST) = qst; QF(pi, J_ITBUF) = kk & 1;
-  // ---- full step and status mapping (acados SQP_RTI: QP success / max-iter -> step taken, else QP failure) ----
+  // status mapping of acados SQP_RTI: QP success / max-iter -> step taken (qs_final writes it), else QP failure
   const int b = QF(pi, J_B);
-  const bool ok = (qst == 0 || qst == 1);
-  bool znan = false;
-  double* xtb = xt + (size_t)b * (N + 1) * NX;
-  double* utb = ut + (size_t)b * N * NU;
-  for (int k = 0; k <= N; ++k) {
-    const double* it = q.it[kk & 1] + qs_blk(tile, N, k, NIT, lane);
-    const double* rec = q.rec + qs_blk(tile, N, k, REC, lane);
-    for (int j = 0; j < NZ; ++j) {
-      if (j < NU && k == N) continue;
-      const double z = ok ? QF(it, I_Z + j) : 0.0;
-      znan |= (z != z);
-      if (j < NU) utb[k * NU + j] = QF(rec, SMPC_REC_U + j) + z;
-      else xtb[k * NX + j - NU] = QF(rec, SMPC_REC_X + j - NU) + z;
-    }
-  }
-  status[b] = ok ? (znan ? 1 : 0) : 4;
+  status[b] = (qst == 0 || qst == 1) ? 0 : 4;
   qp_iter[b] = kk;
   qp_status[b] = qst;
   for (int c = 0; c < 4; ++c) qp_res[(size_t)b * 5 + c] = QF(pd, D_RES + c);
   qp_res[(size_t)b * 5 + 4] = mu;
   return false;
+}
+
+// final: full step x_temp = x_guess + dx, u_temp = u_guess + du of one stage of a problem that took part in this solve
+// (zero step after a QP failure; a NaN in an accepted step turns the status into acados' 1).   thread = (problem, stage)
+// returns true when this stage found a NaN in an accepted step (the caller raises status[b] to 1)
+SMPC_HD bool qs_final(const QsBufs& q, int tile, int lane, int k, const uint8_t* act, int B, const int32_t* status, double* xt, double* ut) {
+  const int N = q.N;
+  const int32_t* pi = q.pi + qs_pb(tile, NPI, lane);
+  const int b = tile * TL + lane;
+  if (b >= B || (act && !act[b])) return false;
+  const bool ok = status[b] != 4;
+  const double* it = q.it[QF(pi, J_ITBUF)] + qs_blk(tile, N, k, NIT, lane);
+  const double* rec = q.rec + qs_blk(tile, N, k, REC, lane);
+  bool znan = false;
+  if (k < N) {
+    double* utb = ut + ((size_t)b * N + k) * NU;
+#pragma unroll
+    for (int j = 0; j < NU; ++j) { const double z = ok ? QF(it, I_Z + j) : 0.0; znan |= (z != z); utb[j] = QF(rec, SMPC_REC_U + j) + z; }
+  }
+  double* xtb = xt + ((size_t)b * (N + 1) + k) * NX;
+#pragma unroll
+  for (int j = 0; j < NX; ++j) { const double z = ok ? QF(it, I_Z + NU + j) : 0.0; znan |= (z != z); xtb[j] = QF(rec, SMPC_REC_X + j) + z; }
+  return znan;
 }
 
 // ================================================================================================================
@@ -478,7 +526,7 @@ SMPC_HD double qs_y(int i, int c, double dt, double a2, PF Pn) {
 enum { RIC1_STAGE_FIELDS = B_LP - B_M, RIC2_STAGE_FIELDS = B_V1 - B_RB };   // largest range each kernel stages (145, 165)
 
 // ric1: backward factorisation with the affine gradient, stage-0 solve, forward substitution of the affine direction.
-// psm: on-chip scratch for two packed P matrices + p, [2][65][TL] doubles (lane offset applied).
+// psm: on-chip scratch for the packed P matrix + p of the running stage, [65][TL] doubles (lane offset applied).
 template <class W>
 SMPC_HD void qs_ric1(const smpc_problem_t& P, const QsBufs& q, int tile, W& w, double* psm) {
   const int N = q.N, lane = w.lane();
@@ -490,16 +538,20 @@ SMPC_HD void qs_ric1(const smpc_problem_t& P, const QsBufs& q, int tile, W& w, d
   const double* gsb = q.sb + qs_blk(tile, N, 0, NSB, 0);       // stage blocks of this tile (no lane offset)
   const size_t sstride = (size_t)NSB * TL;
   double dx[10];
-  w.fetch_begin(N & 1, B_LP - B_M);
-  w.fetch(N & 1, 0, gsb + (size_t)N * sstride, B_M, B_LP - B_M);
+  // staging: with two buffers stage k - 1 is fetched while stage k is processed; with one buffer (more warps per SM)
+  // the fetch of stage k - 1 is issued once every lane is done with stage k
+  const int nb1 = w.nbuf() - 1;
+  w.fetch_begin(N & nb1, B_LP - B_M);
+  w.fetch(N & nb1, 0, gsb + (size_t)N * sstride, B_M, B_LP - B_M);
   for (int k = N; k >= 0; --k) {
     w.sync();                                                    // every lane is done with the buffer of stage k + 1
-    if (k > 0) { w.fetch_begin((k - 1) & 1, B_LP - B_M); w.fetch((k - 1) & 1, 0, gsb + (size_t)(k - 1) * sstride, B_M, B_LP - B_M); }
-    w.wait(k & 1);
-    const double* hc = w.buf(k & 1);                             // fields B_M .. B_LP at their own offsets
+    if (nb1 && k > 0) { w.fetch_begin((k - 1) & 1, B_LP - B_M); w.fetch((k - 1) & 1, 0, gsb + (size_t)(k - 1) * sstride, B_M, B_LP - B_M); }
+    if (!nb1 && k < N) { w.fetch_begin(0, B_LP - B_M); w.fetch(0, 0, gsb + (size_t)k * sstride, B_M, B_LP - B_M); }
+    w.wait(k & nb1);
+    const double* hc = w.buf(k & nb1);                           // fields B_M .. B_LP at their own offsets
     double* fac = q.sb + qs_blk(tile, N, k, NSB, lane);
-    double* pcur = psm + (size_t)(k & 1) * 65 * TL;              // P_k, p_k
-    const double* pnx = psm + (size_t)((k & 1) ^ 1) * 65 * TL;   // P_{k+1}, p_{k+1}
+    double* pcur = psm;                                          // P_{k+1}, p_{k+1} on entry; P_k, p_k on exit (in place)
+    const double* pnx = psm;
     auto Pn = [&](int idx) { return QF(pnx, idx); };
     // gradient: g = ga + [B A]' (P_{k+1} rb + p_{k+1})
     double g[15];
@@ -565,21 +617,32 @@ SMPC_HD void qs_ric1(const smpc_problem_t& P, const QsBufs& q, int tile, W& w, d
     }
 #pragma unroll
     for (int i = 0; i < 10; ++i) QF(pcur, 55 + i) = g[5 + i];
-    // P_k = trailing block - T_x D T_x'
+    // P_k = trailing block - T_x D T_x', written in place over P_{k+1}: the vv block first, then vq, then qq -- an entry of
+    // a later block only reads P_{k+1} entries of its own and of later blocks (qs_y), so nothing it needs is overwritten
+    double sdx[10][5];
 #pragma unroll
-    for (int i = 5; i < 15; ++i) {
-      double sd[5];
+    for (int i = 5; i < 15; ++i)
 #pragma unroll
-      for (int j = 0; j < 5; ++j) sd[j] = pan[i][j] * dd[j];
+      for (int j = 0; j < 5; ++j) sdx[i - 5][j] = pan[i][j] * dd[j];
+    auto trail = [&](int i, int c) {
+      double v = QF(hc, H_M + tri(i, c)) + (k < N ? qs_y(i, c, dt, a2, Pn) : 0.0);
 #pragma unroll
-      for (int c = 5; c <= i; ++c) {
-        double v = QF(hc, H_M + tri(i, c)) + (k < N ? qs_y(i, c, dt, a2, Pn) : 0.0);
+      for (int j = 0; j < 5; ++j) v -= sdx[i - 5][j] * pan[c][j];
+      QF(pcur, tri(i - 5, c - 5)) = v;
+      if (on) QF(fac, F_P + tri(i - 5, c - 5)) = v;
+    };
 #pragma unroll
-        for (int j = 0; j < 5; ++j) v -= sd[j] * pan[c][j];
-        QF(pcur, tri(i - 5, c - 5)) = v;
-        if (on) QF(fac, F_P + tri(i - 5, c - 5)) = v;
-      }
-    }
+    for (int i = 10; i < 15; ++i)
+#pragma unroll
+      for (int c = 10; c <= i; ++c) trail(i, c);
+#pragma unroll
+    for (int i = 10; i < 15; ++i)
+#pragma unroll
+      for (int c = 5; c < 10; ++c) trail(i, c);
+#pragma unroll
+    for (int i = 5; i < 10; ++i)
+#pragma unroll
+      for (int c = 5; c <= i; ++c) trail(i, c);
     if (k == 0) {
       // factorise P_0 (kept per problem for the re-solves) and solve P_0 dx_0 = -p_0
       double m[10][10], gg[10];
@@ -625,9 +688,10 @@ SMPC_HD void qs_ric1(const smpc_problem_t& P, const QsBufs& q, int tile, W& w, d
   w.fetch(0, 0, gsb, B_RB, B_WV - B_RB);
   for (int k = 0; k <= N; ++k) {
     w.sync();
-    if (k < N) { w.fetch_begin((k + 1) & 1, B_WV - B_RB); w.fetch((k + 1) & 1, 0, gsb + (size_t)(k + 1) * sstride, B_RB, B_WV - B_RB); }
-    w.wait(k & 1);
-    const double* sb = w.buf(k & 1) - (size_t)B_RB * TL;         // sb[f] valid for B_RB <= f < B_WV
+    if (nb1 && k < N) { w.fetch_begin((k + 1) & 1, B_WV - B_RB); w.fetch((k + 1) & 1, 0, gsb + (size_t)(k + 1) * sstride, B_RB, B_WV - B_RB); }
+    if (!nb1 && k > 0) { w.fetch_begin(0, B_WV - B_RB); w.fetch(0, 0, gsb + (size_t)k * sstride, B_RB, B_WV - B_RB); }
+    w.wait(k & nb1);
+    const double* sb = w.buf(k & nb1) - (size_t)B_RB * TL;       // sb[f] valid for B_RB <= f < B_WV
     double* st = q.st + qs_blk(tile, N, k, NIT, lane);
     double du[5];
 #pragma unroll
@@ -689,9 +753,10 @@ SMPC_HD void qs_ric2(const smpc_problem_t& P, const QsBufs& q, int tile, W& w, i
   const size_t sstride = (size_t)NSB * TL;
   // backward stages fetch GA RB LP T WV = [B_GA, B_P) -> staging fields 0..124, and V1 V2 = [B_V1, NSB) -> 125..154
   const int n1 = B_P - B_GA, n2 = NSB - B_V1;
-  w.fetch_begin(N & 1, n1 + n2);
-  w.fetch(N & 1, 0, gsb + (size_t)N * sstride, B_GA, n1);
-  w.fetch(N & 1, n1, gsb + (size_t)N * sstride, B_V1, n2);
+  const int nb1 = w.nbuf() - 1;
+  w.fetch_begin(N & nb1, n1 + n2);
+  w.fetch(N & nb1, 0, gsb + (size_t)N * sstride, B_GA, n1);
+  w.fetch(N & nb1, n1, gsb + (size_t)N * sstride, B_V1, n2);
   double sigmu = 0.0;
   if (mode == 1) {
     if (on) {
@@ -709,14 +774,15 @@ SMPC_HD void qs_ric2(const smpc_problem_t& P, const QsBufs& q, int tile, W& w, i
   for (int i = 0; i < 10; ++i) { pn[i] = 0.0; dx[i] = 0.0; }
   for (int k = N; k >= 0; --k) {
     w.sync();
-    if (k > 0) {
-      w.fetch_begin((k - 1) & 1, n1 + n2);
-      w.fetch((k - 1) & 1, 0, gsb + (size_t)(k - 1) * sstride, B_GA, n1);
-      w.fetch((k - 1) & 1, n1, gsb + (size_t)(k - 1) * sstride, B_V1, n2);
+    if (nb1 ? k > 0 : k < N) {
+      const int kf = nb1 ? k - 1 : k;
+      w.fetch_begin(kf & nb1, n1 + n2);
+      w.fetch(kf & nb1, 0, gsb + (size_t)kf * sstride, B_GA, n1);
+      w.fetch(kf & nb1, n1, gsb + (size_t)kf * sstride, B_V1, n2);
     }
-    w.wait(k & 1);
-    const double* sb = w.buf(k & 1) - (size_t)B_GA * TL;           // sb[f] valid for B_GA <= f < B_P
-    const double* vv = w.buf(k & 1) - (size_t)(B_V1 - n1) * TL;    // vv[f] valid for B_V1 <= f < NSB
+    w.wait(k & nb1);
+    const double* sb = w.buf(k & nb1) - (size_t)B_GA * TL;         // sb[f] valid for B_GA <= f < B_P
+    const double* vv = w.buf(k & nb1) - (size_t)(B_V1 - n1) * TL;  // vv[f] valid for B_V1 <= f < NSB
     double* fac = q.sb + qs_blk(tile, N, k, NSB, lane);
     double g[15];
 #pragma unroll
@@ -767,9 +833,10 @@ SMPC_HD void qs_ric2(const smpc_problem_t& P, const QsBufs& q, int tile, W& w, i
   w.fetch(0, 0, gsb, B_RB, B_V1 - B_RB);
   for (int k = 0; k <= N; ++k) {
     w.sync();
-    if (k < N) { w.fetch_begin((k + 1) & 1, B_V1 - B_RB); w.fetch((k + 1) & 1, 0, gsb + (size_t)(k + 1) * sstride, B_RB, B_V1 - B_RB); }
-    w.wait(k & 1);
-    const double* sb = w.buf(k & 1) - (size_t)B_RB * TL;
+    if (nb1 && k < N) { w.fetch_begin((k + 1) & 1, B_V1 - B_RB); w.fetch((k + 1) & 1, 0, gsb + (size_t)(k + 1) * sstride, B_RB, B_V1 - B_RB); }
+    if (!nb1 && k > 0) { w.fetch_begin(0, B_V1 - B_RB); w.fetch(0, 0, gsb + (size_t)k * sstride, B_RB, B_V1 - B_RB); }
+    w.wait(k & nb1);
+    const double* sb = w.buf(k & nb1) - (size_t)B_RB * TL;
     double* st = q.st + qs_blk(tile, N, k, NIT, lane);
     // multiplier step of the link k-1 -> k:  dpi = P_k dx_k + p_k
 #pragma unroll
@@ -843,11 +910,10 @@ SMPC_HD void qs_step(const smpc_problem_t& P, const QsBufs& q, int tile, int lan
 #pragma unroll
   for (int i = 0; i < 15; ++i) { v1[i] = 0.0; v2[i] = 0.0; }
 
+  // Loads and stores are kept in separate phases per row group (see qs_prep).
   // one side of a hard row.  e1 / e2: this side's contribution to the corrector terms (signed)
-  auto side = [&](int slot, double sgn, double az, double adz, double bnd, double& e1, double& e2) {
-    const double lam = QF(it, I_LAM + slot), t = QF(it, I_T + slot);
+  auto side = [&](int slot, double sgn, double az, double adz, double bnd, double lam, double t, double pr, double& e1, double& e2) {
     const double r = t - sgn * (az - bnd);
-    const double pr = mode == 1 ? QF(prod, slot) : 0.0;
     const double rm = qs_rm(mode, lam * t, pr, sigmu);
     const double it_ = 1.0 / t;
     const double dtt = sgn * adz - r;
@@ -859,15 +925,29 @@ SMPC_HD void qs_step(const smpc_problem_t& P, const QsBufs& q, int tile, int lan
     else { QF(st, I_LAM + slot) = dl; QF(st, I_T + slot) = dtt; }
   };
   // box rows
+  {
+    double lo[10], hi[10], bl[20], bt[20], bp[20];
 #pragma unroll
-  for (int j = 0; j < 10; ++j) {
-    double lo, hi;
-    qs_box(P, q, tile, lane, k, j, QF(pd, D_X0 + j), rrec, lo, hi);
-    double e1 = 0.0, e2 = 0.0;
-    side(j, 1.0, z[5 + j], dz[5 + j], lo, e1, e2);
-    side(QNR + j, -1.0, z[5 + j], dz[5 + j], hi, e1, e2);
-    v1[5 + j] += e1; v2[5 + j] += e2;
+    for (int j = 0; j < 10; ++j) {
+      qs_box(P, q, tile, lane, k, j, QF(pd, D_X0 + j), rrec, lo[j], hi[j]);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        bl[h * 10 + j] = QF(it, I_LAM + h * QNR + j); bt[h * 10 + j] = QF(it, I_T + h * QNR + j);
+        bp[h * 10 + j] = mode == 1 ? QF(prod, h * QNR + j) : 0.0;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 10; ++j) {
+      double e1 = 0.0, e2 = 0.0;
+      side(j, 1.0, z[5 + j], dz[5 + j], lo[j], bl[j], bt[j], bp[j], e1, e2);
+      side(QNR + j, -1.0, z[5 + j], dz[5 + j], hi[j], bl[10 + j], bt[10 + j], bp[10 + j], e1, e2);
+      v1[5 + j] += e1; v2[5 + j] += e2;
+    }
   }
+  // general rows: row products of z and dz, bounds (loads only)
+  double azg[12], adg[12], glo[12], ghi[12];
+#pragma unroll
+  for (int r = 0; r < 12; ++r) { azg[r] = adg[r] = glo[r] = ghi[r] = 0.0; }
   if (F.tau) {
 #pragma unroll
     for (int r = 0; r < 5; ++r) {
@@ -875,17 +955,8 @@ SMPC_HD void qs_step(const smpc_problem_t& P, const QsBufs& q, int tile, int lan
 #pragma unroll
       for (int c = 0; c < 15; ++c) { const double jv = QF(rec, SMPC_REC_JTAU + r * 15 + c); az += jv * z[c]; adz += jv * dz[c]; }
       const double v = QF(rec, SMPC_REC_TAU + r);
-      double e1 = 0.0, e2 = 0.0;
-      side(10 + r, 1.0, az, adz, P.tau_min[r] - v, e1, e2);
-      side(QNR + 10 + r, -1.0, az, adz, P.tau_max[r] - v, e1, e2);
-      if (mode == 0) {
-#pragma unroll
-        for (int c = 0; c < 15; ++c) { const double jv = QF(rec, SMPC_REC_JTAU + r * 15 + c); v1[c] += jv * e1; v2[c] += jv * e2; }
-      }
+      azg[r] = az; adg[r] = adz; glo[r] = P.tau_min[r] - v; ghi[r] = P.tau_max[r] - v;
     }
-  } else if (mode != 0) {
-#pragma unroll
-    for (int r = 0; r < 5; ++r) { QF(st, I_LAM + 10 + r) = 0.0; QF(st, I_T + 10 + r) = 0.0; QF(st, I_LAM + QNR + 10 + r) = 0.0; QF(st, I_T + QNR + 10 + r) = 0.0; }
   }
   if (F.dist) {
 #pragma unroll
@@ -894,27 +965,65 @@ SMPC_HD void qs_step(const smpc_problem_t& P, const QsBufs& q, int tile, int lan
 #pragma unroll
       for (int c = 0; c < 5; ++c) { const double jv = QF(rec, SMPC_REC_JDIST + p * 5 + c); az += jv * z[5 + c]; adz += jv * dz[5 + c]; }
       const double v = QF(rec, SMPC_REC_DIST + p);
-      double e1 = 0.0, e2 = 0.0;
-      side(15 + p, 1.0, az, adz, P.pair_lo_ocp[p] - v, e1, e2);
-      side(QNR + 15 + p, -1.0, az, adz, P.pair_hi - v, e1, e2);
-      if (mode == 0) {
-#pragma unroll
-        for (int c = 0; c < 5; ++c) { const double jv = QF(rec, SMPC_REC_JDIST + p * 5 + c); v1[5 + c] += jv * e1; v2[5 + c] += jv * e2; }
-      }
+      azg[5 + p] = az; adg[5 + p] = adz; glo[5 + p] = P.pair_lo_ocp[p] - v; ghi[5 + p] = P.pair_hi - v;
     }
-  } else if (mode != 0) {
-#pragma unroll
-    for (int p = 0; p < 6; ++p) { QF(st, I_LAM + 15 + p) = 0.0; QF(st, I_T + 15 + p) = 0.0; QF(st, I_LAM + QNR + 15 + p) = 0.0; QF(st, I_T + QNR + 15 + p) = 0.0; }
   }
   if (F.nn) {
     double az = 0.0, adz = 0.0;
 #pragma unroll
     for (int c = 0; c < 10; ++c) { const double jv = QF(rec, SMPC_REC_JNN + c); az += jv * z[5 + c]; adz += jv * dz[5 + c]; }
     const double v = QF(rec, SMPC_REC_NN);
+    azg[11] = az; adg[11] = adz; glo[11] = 0.0 - v; ghi[11] = 1e6 - v;
+  }
+  if (F.tau) {
+    double gl[10], gt[10], gp[10];
+#pragma unroll
+    for (int r = 0; r < 5; ++r)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int slot = h * QNR + 10 + r;
+        gl[h * 5 + r] = QF(it, I_LAM + slot); gt[h * 5 + r] = QF(it, I_T + slot); gp[h * 5 + r] = mode == 1 ? QF(prod, slot) : 0.0;
+      }
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {
+      double e1 = 0.0, e2 = 0.0;
+      side(10 + r, 1.0, azg[r], adg[r], glo[r], gl[r], gt[r], gp[r], e1, e2);
+      side(QNR + 10 + r, -1.0, azg[r], adg[r], ghi[r], gl[5 + r], gt[5 + r], gp[5 + r], e1, e2);
+      if (mode == 0) {
+#pragma unroll
+        for (int c = 0; c < 15; ++c) { const double jv = QF(rec, SMPC_REC_JTAU + r * 15 + c); v1[c] += jv * e1; v2[c] += jv * e2; }
+      }
+    }
+  }
+  if (F.dist) {
+    double gl[12], gt[12], gp[12];
+#pragma unroll
+    for (int p = 0; p < 6; ++p)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int slot = h * QNR + 15 + p;
+        gl[h * 6 + p] = QF(it, I_LAM + slot); gt[h * 6 + p] = QF(it, I_T + slot); gp[h * 6 + p] = mode == 1 ? QF(prod, slot) : 0.0;
+      }
+#pragma unroll
+    for (int p = 0; p < 6; ++p) {
+      double e1 = 0.0, e2 = 0.0;
+      side(15 + p, 1.0, azg[5 + p], adg[5 + p], glo[5 + p], gl[p], gt[p], gp[p], e1, e2);
+      side(QNR + 15 + p, -1.0, azg[5 + p], adg[5 + p], ghi[5 + p], gl[6 + p], gt[6 + p], gp[6 + p], e1, e2);
+      if (mode == 0) {
+#pragma unroll
+        for (int c = 0; c < 5; ++c) { const double jv = QF(rec, SMPC_REC_JDIST + p * 5 + c); v1[5 + c] += jv * e1; v2[5 + c] += jv * e2; }
+      }
+    }
+  }
+  if (F.nn) {
+    const double az = azg[11], adz = adg[11];
+    const double v = QF(rec, SMPC_REC_NN);
     double e1 = 0.0, e2 = 0.0;
     if (!F.soft) {
-      side(21, 1.0, az, adz, 0.0 - v, e1, e2);
-      side(QNR + 21, -1.0, az, adz, 1e6 - v, e1, e2);
+      const double l0 = QF(it, I_LAM + 21), t0 = QF(it, I_T + 21), p0 = mode == 1 ? QF(prod, 21) : 0.0;
+      const double l1 = QF(it, I_LAM + QNR + 21), t1 = QF(it, I_T + QNR + 21), p1 = mode == 1 ? QF(prod, QNR + 21) : 0.0;
+      side(21, 1.0, az, adz, 0.0 - v, l0, t0, p0, e1, e2);
+      side(QNR + 21, -1.0, az, adz, 1e6 - v, l1, t1, p1, e1, e2);
       if (mode != 0) {
 #pragma unroll
         for (int h = 0; h < 6; ++h) QF(st, I_SLK + h) = 0.0;
@@ -967,10 +1076,6 @@ SMPC_HD void qs_step(const smpc_problem_t& P, const QsBufs& q, int tile, int lan
 #pragma unroll
       for (int c = 0; c < 10; ++c) { const double jv = QF(rec, SMPC_REC_JNN + c); v1[5 + c] += jv * e1; v2[5 + c] += jv * e2; }
     }
-  } else if (mode != 0) {
-    QF(st, I_LAM + 21) = 0.0; QF(st, I_T + 21) = 0.0; QF(st, I_LAM + QNR + 21) = 0.0; QF(st, I_T + QNR + 21) = 0.0;
-#pragma unroll
-    for (int h = 0; h < 6; ++h) QF(st, I_SLK + h) = 0.0;
   }
   if (mode == 0) {
     double* vv = q.sb + qs_blk(tile, N, k, NV, lane);
@@ -1039,6 +1144,7 @@ int qs_drive(BK& bk) {
     ++kk;
     bk.prep(kk);
   }
+  bk.final();
   return kk;
 }
 

@@ -51,7 +51,8 @@ namespace {
 // host stand-in of the staged copies of the Riccati sweeps: one lane at a time; lazy = 1 performs a copy only when it
 // is waited for (a fetch issued before its source has been written then shows up as wrong numbers)
 struct HostStage {
-  int ln, nfb, lazy;
+  int ln, nfb, lazy, nb = 2;
+  int nbuf() const { return nb; }
   std::vector<double> mem;
   struct Copy { double* dst; const double* src; size_t n; };
   std::vector<Copy> pend[2];
@@ -89,14 +90,18 @@ struct HostBackend {
     for (int t = 0; t < T; ++t) for (int lx = 0; lx < TL; ++lx) f(t, order ? TL - 1 - lx : lx);
   }
   void init() { each_problem([&](int t, int l) { qs_init(q, t, l, B, x0, r, act); }); }
-  void prep(int kk) { each_stage([&](int t, int l, int k) { qs_prep(P, q, t, l, k, kk); }); }
+  void prep(int kk) {
+    std::vector<double> jsm((size_t)PREP_SCRATCH * TL, 0.0);
+    each_stage([&](int t, int l, int k) { qs_prep(P, q, t, l, k, kk, jsm.data() + l); });
+  }
   void ctl(int kk) {
     n_active = 0;
-    each_problem([&](int t, int l) { if (qs_ctl(P, q, t, l, kk, xt, ut, status, qp_iter, qp_status, qp_res)) ++n_active; });
+    each_problem([&](int t, int l) { if (qs_ctl(P, q, t, l, kk, status, qp_iter, qp_status, qp_res)) ++n_active; });
   }
-  void ric1() { each_problem([&](int t, int l) { HostStage w(l, RIC1_STAGE_FIELDS, order); qs_ric1(P, q, t, w, psm.data() + l); }); }
-  void ric2(int mode) { each_problem([&](int t, int l) { HostStage w(l, RIC2_STAGE_FIELDS, order); qs_ric2(P, q, t, w, mode); }); }
+  void ric1() { each_problem([&](int t, int l) { HostStage w(l, RIC1_STAGE_FIELDS, order); w.nb = 2 - order; qs_ric1(P, q, t, w, psm.data() + l); }); }
+  void ric2(int mode) { each_problem([&](int t, int l) { HostStage w(l, RIC2_STAGE_FIELDS, order); w.nb = 2 - order; qs_ric2(P, q, t, w, mode); }); }
   void step(int kk, int mode) { each_stage([&](int t, int l, int k) { qs_step(P, q, t, l, k, kk, mode); }); }
+  void final() { each_stage([&](int t, int l, int k) { if (qs_final(q, t, l, k, act, B, status, xt, ut)) status[t * TL + l] = 1; }); }
   void red(bool after) { each_problem([&](int t, int l) { qs_red(P, q, t, l, after); }); }
   void sync(int& na, int& nr) {
     na = n_active; nr = 0;
@@ -121,7 +126,7 @@ extern "C" int emu_qp_solve(const smpc_problem_t* P, int B, const double* rec, c
         vrec[qs_blk(b / TL, N, k, REC, b % TL) + (size_t)f * TL] = rec[((size_t)b * (N + 1) + k) * REC + f];
   QsBufs q{vrec.data(), {it0.data(), it1.data()}, st.data(), sb.data(), prod.data(), res.data(), stp.data(),
            pd.data(), pi32.data(), N};
-  HostBackend bk{*P, q, B, T, N, order, x0, r, act, xt, ut, status, qp_iter, qp_status, qp_res, std::vector<double>(2 * 65 * TL, 0.0)};
+  HostBackend bk{*P, q, B, T, N, order, x0, r, act, xt, ut, status, qp_iter, qp_status, qp_res, std::vector<double>(65 * TL, 0.0)};
   struct Counting : HostBackend {
     int redo = 0;
     void sync(int& na, int& nr) { HostBackend::sync(na, nr); redo += nr; }

@@ -10,6 +10,10 @@
 //   ctl / red     one thread per problem.
 // The host reads two counters (problems still active, problems that asked for the centering re-solve) once per IPM
 // iteration; everything else is asynchronous on the handle's stream.
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
 #include "engine.cuh"
 
 namespace smpc {
@@ -32,7 +36,7 @@ __global__ void __launch_bounds__(32) qs_init_kernel(QsBufs q, int B, const doub
   qs_init(q, blockIdx.x, threadIdx.x, B, x0, r, act);
 }
 
-constexpr size_t PREP_SMEM = sizeof(double) * 2 * PREP_SCRATCH * TL;
+constexpr size_t PREP_SMEM = sizeof(double) * 2 * PREP_SCRATCH * TL + 512;   // a retiring prep CTA leaves room for one Riccati CTA
 constexpr int PREP_WARPS = 2;    // warps per CTA of prep: 2 x 26.9 KB of lane-private Jacobian scratch, 4 CTAs per SM
 __global__ void __launch_bounds__(32 * PREP_WARPS, QS_PREP_MINB) qs_prep_kernel(const smpc_problem_t* __restrict__ dP, QsBufs q, int T, int kk) {
   extern __shared__ __align__(128) double jsm_all[];
@@ -184,13 +188,32 @@ __global__ void dump_qp_kernel(const smpc_problem_t* __restrict__ dP, QsBufs q, 
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------ solver object
-struct QpSolver {
-  int B = 0, N = 0, T = 0, iter_max = 0;
+#ifndef QS_GROUPS
+#define QS_GROUPS 3              // tile groups solved concurrently on their own streams (see QsLoop)
+#endif
+constexpr int MAX_GROUPS = 8;
+
+struct QpGroup {
   QsBufs q{};
+  int T = 0;                    // tiles of this group
+  cudaStream_t stream = nullptr;   // stage-parallel kernels (bandwidth-bound)
+  cudaStream_t hi = nullptr;       // Riccati sweeps (latency-bound, few warps): higher priority, so that their CTAs take the
+                                   // slots that retiring stage-parallel CTAs of the other groups free
+  cudaEvent_t ev = nullptr;     // counters of the current iteration have landed in h_counters
+  cudaEvent_t evx = nullptr;    // hand-over between the two streams
+  int* counters = nullptr;      // [2 (iter_max + 2)]: active / redo per IPM iteration
+  int* h_counters = nullptr;    // pinned, 2 ints
+};
+
+struct QpSolver {
+  int B = 0, N = 0, T = 0, iter_max = 0, G = 1;
+  QsBufs q{};                   // whole batch (group 0 .. G-1 are sub-ranges of its tiles)
+  QpGroup grp[MAX_GROUPS];
   double* block = nullptr;      // one allocation for all double arrays
   int32_t* pi = nullptr;
-  int* counters = nullptr;      // [2 (iter_max + 2)]: active / redo per IPM iteration
-  int* h_counters = nullptr;    // pinned
+  int* counters = nullptr;
+  int* h_counters = nullptr;
+  cudaEvent_t ev_in = nullptr;  // inputs (records, x0) are ready on the caller's stream
   int last_iters = 0;
 };
 
@@ -203,16 +226,33 @@ QpSolver* qp_create(int B, int N, int iter_max, cudaStream_t stream, cudaError_t
   QpSolver* s = new QpSolver;
   s->B = B; s->N = N; s->T = (B + TL - 1) / TL; s->iter_max = iter_max;
   const size_t T = s->T, S = T * (N + 1) * TL;
+  // groups: at least ~64 tiles each so that the stage-parallel kernels of one group still fill the GPU
+  int G = QS_GROUPS;
+  if (const char* e = getenv("SMPC_QP_GROUPS")) G = atoi(e);
+  while (G > 1 && s->T / G < 64) --G;
+  if (G < 1) G = 1;
+  if (G > MAX_GROUPS) G = MAX_GROUPS;
+  s->G = G;
+  const size_t ncnt = (size_t)2 * (iter_max + 2);
   cudaError_t e = cudaMalloc((void**)&s->block, qp_bytes(B, N));
   if (e == cudaSuccess) e = cudaMemsetAsync(s->block, 0, qp_bytes(B, N), stream);
   if (e == cudaSuccess) e = cudaMalloc((void**)&s->pi, sizeof(int32_t) * T * NPI * TL);
   if (e == cudaSuccess) e = cudaMemsetAsync(s->pi, 0, sizeof(int32_t) * T * NPI * TL, stream);
-  if (e == cudaSuccess) e = cudaMalloc((void**)&s->counters, sizeof(int) * 2 * (iter_max + 2));
-  if (e == cudaSuccess) e = cudaMallocHost((void**)&s->h_counters, sizeof(int) * 2);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&s->counters, sizeof(int) * ncnt * G);
+  if (e == cudaSuccess) e = cudaMallocHost((void**)&s->h_counters, sizeof(int) * 2 * G);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_in, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(qs_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PREP_SMEM);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(qs_ric1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RIC1_SMEM);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(qs_ric2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RIC2_SMEM);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(qs_ric2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RIC2_SMEM);
+  for (int g = 0; g < G && e == cudaSuccess; ++g) {
+    int plo = 0, phi = 0;
+    cudaDeviceGetStreamPriorityRange(&plo, &phi);
+    e = cudaStreamCreateWithPriority(&s->grp[g].stream, cudaStreamNonBlocking, plo);
+    if (e == cudaSuccess && G > 1 && !getenv("SMPC_QP_NOPRIO")) e = cudaStreamCreateWithPriority(&s->grp[g].hi, cudaStreamNonBlocking, phi);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->grp[g].ev, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->grp[g].evx, cudaEventDisableTiming);
+  }
   if (e != cudaSuccess) { *err = e; qp_destroy(s); return nullptr; }
   double* p = s->block;
   double* rec = p; p += S * REC;
@@ -227,12 +267,32 @@ QpSolver* qp_create(int B, int N, int iter_max, cudaStream_t stream, cudaError_t
   s->q.pd = p;
   s->q.pi = s->pi;
   s->q.N = N;
+  s->q.tile0 = 0;
+  for (int g = 0; g < G; ++g) {
+    QpGroup& gr = s->grp[g];
+    const int t0 = (int)((long long)s->T * g / G), t1 = (int)((long long)s->T * (g + 1) / G);
+    const size_t so = (size_t)t0 * (N + 1) * TL;
+    gr.T = t1 - t0;
+    gr.q = s->q;
+    gr.q.rec = s->q.rec + so * REC; gr.q.it[0] = s->q.it[0] + so * NIT; gr.q.it[1] = s->q.it[1] + so * NIT; gr.q.st = s->q.st + so * NIT;
+    gr.q.sb = s->q.sb + so * NSB; gr.q.prod = s->q.prod + so * NPROD; gr.q.res = s->q.res + so * NRES; gr.q.stp = s->q.stp + so * NSTP;
+    gr.q.pd = s->q.pd + (size_t)t0 * NPD * TL; gr.q.pi = s->q.pi + (size_t)t0 * NPI * TL; gr.q.tile0 = t0;
+    gr.counters = s->counters + ncnt * g;
+    gr.h_counters = s->h_counters + 2 * g;
+  }
   *err = cudaSuccess;
   return s;
 }
 
 void qp_destroy(QpSolver* s) {
   if (!s) return;
+  for (int g = 0; g < MAX_GROUPS; ++g) {
+    if (s->grp[g].stream) { cudaStreamSynchronize(s->grp[g].stream); cudaStreamDestroy(s->grp[g].stream); }
+    if (s->grp[g].hi) { cudaStreamSynchronize(s->grp[g].hi); cudaStreamDestroy(s->grp[g].hi); }
+    if (s->grp[g].ev) cudaEventDestroy(s->grp[g].ev);
+    if (s->grp[g].evx) cudaEventDestroy(s->grp[g].evx);
+  }
+  if (s->ev_in) cudaEventDestroy(s->ev_in);
   if (s->block) cudaFree(s->block);
   if (s->pi) cudaFree(s->pi);
   if (s->counters) cudaFree(s->counters);
@@ -242,60 +302,121 @@ void qp_destroy(QpSolver* s) {
 
 double* qp_rec(QpSolver* s) { return const_cast<double*>(s->q.rec); }
 int qp_last_iterations(const QpSolver* s) { return s->last_iters; }
+int qp_groups(const QpSolver* s) { return s->G; }
 
 namespace {
+// optional timeline (SMPC_QP_TRACE=1): one event pair per kernel, printed to stderr after the solve
+struct TraceRec { int g; const char* name; int kk; cudaEvent_t a, b; };
+static std::vector<TraceRec> g_trace;
+static bool trace_on() { static int v = -1; if (v < 0) v = getenv("SMPC_QP_TRACE") ? 1 : 0; return v == 1; }
+
+// kernel launches of one tile group on its own stream
 struct DeviceBackend {
-  const LaunchCtx& c;
+  int64_t* launches;
   const smpc_problem_t* dP;
   QpSolver* s;
+  QpGroup* g;
   const double* x0; const int32_t* r; const uint8_t* act;
   double *xt, *ut; int32_t *status, *qp_iter, *qp_status; double* qp_res;
   int kk_last = 0;
   cudaError_t err = cudaSuccess;
-  int sp_grid() const { return (s->T * (s->N + 1) + SP_WARPS - 1) / SP_WARPS; }
-  void count(int n = 1) { *c.launches += n; }
+  bool on_hi = false;
+  // stream for the next kernel; a change of stream is ordered after everything queued on the other one
+  cudaStream_t st(bool hi) {
+    if (!g->hi) return g->stream;
+    if (hi != on_hi) {
+      cudaEventRecord(g->evx, on_hi ? g->hi : g->stream);
+      cudaStreamWaitEvent(hi ? g->hi : g->stream, g->evx, 0);
+      on_hi = hi;
+    }
+    return hi ? g->hi : g->stream;
+  }
+  int sp_grid() const { return (g->T * (s->N + 1) + SP_WARPS - 1) / SP_WARPS; }
+  void count(int n = 1) { *launches += n; }
+  int gi() const { return (int)(g - s->grp); }
+  void tr0(const char* name, cudaStream_t stm) {
+    if (!trace_on()) return;
+    TraceRec r{gi(), name, kk_last, nullptr, nullptr};
+    cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, stm);
+    g_trace.push_back(r);
+  }
+  void tr1(cudaStream_t stm) { if (trace_on()) cudaEventRecord(g_trace.back().b, stm); }
   void init() {
-    cudaMemsetAsync(s->counters, 0, sizeof(int) * 2 * (s->iter_max + 2), c.stream);
-    qs_init_kernel<<<s->T, 32, 0, c.stream>>>(s->q, s->B, x0, r, act);
+    cudaMemsetAsync(g->counters, 0, sizeof(int) * 2 * (s->iter_max + 2), st(false));
+    { cudaStream_t stm_ = st(false); tr0("qs_init_kernel", stm_); qs_init_kernel<<<g->T, 32, 0, stm_>>>(g->q, s->B, x0, r, act); tr1(stm_); }
     count();
   }
   void prep(int kk) {
-    qs_prep_kernel<<<(s->T * (s->N + 1) + PREP_WARPS - 1) / PREP_WARPS, 32 * PREP_WARPS, PREP_SMEM, c.stream>>>(dP, s->q, s->T, kk);
+    { cudaStream_t stm_ = st(false); tr0("qs_prep_kernel", stm_); qs_prep_kernel<<<(g->T * (s->N + 1) + PREP_WARPS - 1) / PREP_WARPS, 32 * PREP_WARPS, PREP_SMEM, stm_>>>(dP, g->q, g->T, kk); tr1(stm_); }
     count();
   }
   void ctl(int kk) {
     kk_last = kk;
-    qs_ctl_kernel<<<s->T, 32, 0, c.stream>>>(dP, s->q, kk, status, qp_iter, qp_status, qp_res, s->counters);
+    { cudaStream_t stm_ = st(false); tr0("qs_ctl_kernel", stm_); qs_ctl_kernel<<<g->T, 32, 0, stm_>>>(dP, g->q, kk, status, qp_iter, qp_status, qp_res, g->counters); tr1(stm_); }
     count();
   }
-  void ric1() { qs_ric1_kernel<<<s->T, 32, RIC1_SMEM, c.stream>>>(dP, s->q); count(); }
+  void ric1() { { cudaStream_t stm_ = st(true); tr0("qs_ric1_kernel", stm_); qs_ric1_kernel<<<g->T, 32, RIC1_SMEM, stm_>>>(dP, g->q); tr1(stm_); } count(); }
   void ric2(int mode) {
-    if (mode == 1) qs_ric2_kernel<1><<<s->T, 32, RIC2_SMEM, c.stream>>>(dP, s->q);
-    else qs_ric2_kernel<2><<<s->T, 32, RIC2_SMEM, c.stream>>>(dP, s->q);
+    if (mode == 1) { cudaStream_t stm_ = st(true); tr0("qs_ric2_kernel<1>", stm_); qs_ric2_kernel<1><<<g->T, 32, RIC2_SMEM, stm_>>>(dP, g->q); tr1(stm_); }
+    else { cudaStream_t stm_ = st(true); tr0("qs_ric2_kernel<2>", stm_); qs_ric2_kernel<2><<<g->T, 32, RIC2_SMEM, stm_>>>(dP, g->q); tr1(stm_); }
     count();
   }
   void step(int kk, int mode) {
-    if (mode == 0) qs_step_kernel<0><<<sp_grid(), 32 * SP_WARPS, 0, c.stream>>>(dP, s->q, s->T, kk);
-    else if (mode == 1) qs_step_kernel<1><<<sp_grid(), 32 * SP_WARPS, 0, c.stream>>>(dP, s->q, s->T, kk);
-    else qs_step_kernel<2><<<sp_grid(), 32 * SP_WARPS, 0, c.stream>>>(dP, s->q, s->T, kk);
+    if (mode == 0) { cudaStream_t stm_ = st(false); tr0("qs_step_kernel<0>", stm_); qs_step_kernel<0><<<sp_grid(), 32 * SP_WARPS, 0, stm_>>>(dP, g->q, g->T, kk); tr1(stm_); }
+    else if (mode == 1) { cudaStream_t stm_ = st(false); tr0("qs_step_kernel<1>", stm_); qs_step_kernel<1><<<sp_grid(), 32 * SP_WARPS, 0, stm_>>>(dP, g->q, g->T, kk); tr1(stm_); }
+    else { cudaStream_t stm_ = st(false); tr0("qs_step_kernel<2>", stm_); qs_step_kernel<2><<<sp_grid(), 32 * SP_WARPS, 0, stm_>>>(dP, g->q, g->T, kk); tr1(stm_); }
     count();
   }
-  void final() { qs_final_kernel<<<sp_grid(), 32 * SP_WARPS, 0, c.stream>>>(s->q, s->T, s->B, act, status, xt, ut); count(); }
-  void red(bool after) { qs_red_kernel<<<s->T, 32, 0, c.stream>>>(dP, s->q, kk_last, after ? 1 : 0, s->counters); count(); }
-  void sync(int& na, int& nr) {
-    cudaError_t e = cudaMemcpyAsync(s->h_counters, s->counters + 2 * kk_last, 2 * sizeof(int), cudaMemcpyDeviceToHost, c.stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(c.stream);
+  void final() { { cudaStream_t stm_ = st(false); tr0("qs_final_kernel", stm_); qs_final_kernel<<<sp_grid(), 32 * SP_WARPS, 0, stm_>>>(g->q, g->T, s->B, act, status, xt, ut); tr1(stm_); } count(); }
+  void red(bool after) { { cudaStream_t stm_ = st(false); tr0("qs_red_kernel", stm_); qs_red_kernel<<<g->T, 32, 0, stm_>>>(dP, g->q, kk_last, after ? 1 : 0, g->counters); tr1(stm_); } count(); }
+  void request_counters() {
+    cudaError_t e = cudaMemcpyAsync(g->h_counters, g->counters + 2 * kk_last, 2 * sizeof(int), cudaMemcpyDeviceToHost, st(false));
+    if (e == cudaSuccess) e = cudaEventRecord(g->ev, st(false));
+    if (e != cudaSuccess) err = e;
+  }
+  void wait_counters(int& na, int& nr) {
+    cudaError_t e = err == cudaSuccess ? cudaEventSynchronize(g->ev) : err;
     if (e != cudaSuccess) { err = e; na = 0; nr = 0; return; }     // stop iterating; the caller reports the error
-    na = s->h_counters[0]; nr = s->h_counters[1];
+    na = g->h_counters[0]; nr = g->h_counters[1];
+    if (trace_on()) fprintf(stderr, "QPCOUNT g=%d kk=%d active=%d redo=%d\n", gi(), kk_last, na, nr);
   }
 };
 }  // namespace
 
 cudaError_t launch_qp_solve(const LaunchCtx& c, const smpc_problem_t* dP, QpSolver* s, const double* x0, const int32_t* r, const uint8_t* act,
                             double* xt, double* ut, int32_t* status, int32_t* qp_iter, int32_t* qp_status, double* qp_res) {
-  DeviceBackend bk{c, dP, s, x0, r, act, xt, ut, status, qp_iter, qp_status, qp_res};
-  s->last_iters = qs_drive(bk);
-  return bk.err;
+  // the group streams start after everything queued on the caller's stream (linearisation, input copies) ...
+  cudaError_t e = cudaEventRecord(s->ev_in, c.stream);
+  if (e != cudaSuccess) return e;
+  DeviceBackend bk[MAX_GROUPS];
+  for (int g = 0; g < s->G; ++g) {
+    e = cudaStreamWaitEvent(s->grp[g].stream, s->ev_in, 0);
+    if (e != cudaSuccess) return e;
+    bk[g] = DeviceBackend{c.launches, dP, s, &s->grp[g], x0, r, act, xt, ut, status, qp_iter, qp_status, qp_res};
+  }
+  s->last_iters = qs_drive(bk, s->G);
+  if (trace_on()) {
+    for (int g = 0; g < s->G; ++g) cudaStreamSynchronize(bk[g].st(false));
+    if (!g_trace.empty()) {
+      cudaEvent_t t0 = g_trace[0].a;
+      for (auto& r : g_trace) {
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, t0, r.a); cudaEventElapsedTime(&b, t0, r.b);
+        fprintf(stderr, "QPTRACE g=%d kk=%d %-12s start=%9.3f end=%9.3f dur=%8.3f\n", r.g, r.kk, r.name, a, b, b - a);
+      }
+      for (auto& r : g_trace) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+      g_trace.clear();
+    }
+  }
+  // ... and the caller's stream continues after the last kernel of every group
+  for (int g = 0; g < s->G; ++g) {
+    if (bk[g].err != cudaSuccess) return bk[g].err;
+    e = cudaEventRecord(s->grp[g].ev, bk[g].st(false));
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(c.stream, s->grp[g].ev, 0);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
 }
 
 void launch_rec_untile(const LaunchCtx& c, QpSolver* s, double* out) {

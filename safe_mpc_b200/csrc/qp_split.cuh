@@ -73,6 +73,7 @@ struct QsBufs {
   double* pd;            // [T][NPD][TL]
   int32_t* pi;           // [T][NPI][TL]
   int N;
+  int tile0;             // first tile of this group in the batch (problem index b = 32 (tile0 + tile) + lane)
 };
 
 #define QF(p, f) (p)[(size_t)(f) * TL]
@@ -485,7 +486,7 @@ SMPC_HD bool qs_ctl(const smpc_problem_t& P, const QsBufs& q, int tile, int lane
 SMPC_HD bool qs_final(const QsBufs& q, int tile, int lane, int k, const uint8_t* act, int B, const int32_t* status, double* xt, double* ut) {
   const int N = q.N;
   const int32_t* pi = q.pi + qs_pb(tile, NPI, lane);
-  const int b = tile * TL + lane;
+  const int b = (q.tile0 + tile) * TL + lane;
   if (b >= B || (act && !act[b])) return false;
   const bool ok = status[b] != 4;
   const double* it = q.it[QF(pi, J_ITBUF)] + qs_blk(tile, N, k, NIT, lane);
@@ -1113,7 +1114,7 @@ SMPC_HD void qs_red(const smpc_problem_t& P, const QsBufs& q, int tile, int lane
 
 // per-problem initialisation of one solve.   thread = problem (lane of a tile; b = 32 tile + lane may be >= B: padding)
 SMPC_HD void qs_init(const QsBufs& q, int tile, int lane, int B, const double* x0, const int32_t* r, const uint8_t* act) {
-  const int b = tile * TL + lane;
+  const int b = (q.tile0 + tile) * TL + lane;
   int32_t* pi = q.pi + qs_pb(tile, NPI, lane);
   double* pd = q.pd + qs_pb(tile, NPD, lane);
   const bool on = b < B && (!act || act[b]);
@@ -1123,29 +1124,50 @@ SMPC_HD void qs_init(const QsBufs& q, int tile, int lane, int B, const double* x
   QF(pd, D_MU) = 0.0; QF(pd, D_MUAFF) = 0.0; QF(pd, D_SIGMU) = 0.0; QF(pd, D_ALPHA) = 1.0; QF(pd, D_STEP) = 0.0;
 }
 
-// Host-side sequencing of one batched solve; BK launches the phases (CUDA kernels in qp.cu, plain loops in tests/emu).
-// sync(n_active, n_redo) is the one host round trip per IPM iteration.
+// Host-side sequencing of one batched solve of one group of tiles; BK launches the phases (CUDA kernels in qp.cu, plain
+// loops in tests/emu).  issue() queues one IPM iteration up to the step-length decision and requests the two counters
+// (problems still active, problems that asked for the centering re-solve); advance() waits for them -- the one host
+// round trip per iteration -- and queues the rest.  Several groups are driven round-robin so that the latency-bound
+// Riccati sweeps of one group overlap the bandwidth-bound stage-parallel kernels of the others.
 template <class BK>
-int qs_drive(BK& bk) {
-  bk.init();
+struct QsLoop {
+  BK& bk;
   int kk = 0;
-  bk.prep(0);
-  for (;;) {
+  bool done = false;
+  explicit QsLoop(BK& b) : bk(b) {}
+  void issue() {
     bk.ctl(kk);
     bk.ric1();
     bk.step(kk, 0);
     bk.ric2(1);
     bk.step(kk, 1);
     bk.red(false);
+    bk.request_counters();
+  }
+  void start() { bk.init(); bk.prep(0); issue(); }
+  void advance() {
     int n_active = 0, n_redo = 0;
-    bk.sync(n_active, n_redo);
-    if (n_active == 0) break;
+    bk.wait_counters(n_active, n_redo);
+    if (n_active == 0) { bk.final(); done = true; return; }
     if (n_redo > 0) { bk.ric2(2); bk.step(kk, 2); bk.red(true); }
     ++kk;
     bk.prep(kk);
+    issue();
   }
-  bk.final();
-  return kk;
+};
+
+template <class BK>
+int qs_drive(BK* groups, int n_groups) {
+  QsLoop<BK>* loops[8];
+  for (int g = 0; g < n_groups; ++g) { loops[g] = new QsLoop<BK>(groups[g]); loops[g]->start(); }
+  int kmax = 0;
+  for (bool any = true; any;) {
+    any = false;
+    for (int g = 0; g < n_groups; ++g)
+      if (!loops[g]->done) { loops[g]->advance(); any = any || !loops[g]->done; }
+  }
+  for (int g = 0; g < n_groups; ++g) { kmax = loops[g]->kk > kmax ? loops[g]->kk : kmax; delete loops[g]; }
+  return kmax;
 }
 
 }  // namespace smpc

@@ -101,11 +101,14 @@ struct HostBackend {
   void ric1() { each_problem([&](int t, int l) { HostStage w(l, RIC1_STAGE_FIELDS, order); w.nb = 2 - order; qs_ric1(P, q, t, w, psm.data() + l); }); }
   void ric2(int mode) { each_problem([&](int t, int l) { HostStage w(l, RIC2_STAGE_FIELDS, order); w.nb = 2 - order; qs_ric2(P, q, t, w, mode); }); }
   void step(int kk, int mode) { each_stage([&](int t, int l, int k) { qs_step(P, q, t, l, k, kk, mode); }); }
-  void final() { each_stage([&](int t, int l, int k) { if (qs_final(q, t, l, k, act, B, status, xt, ut)) status[t * TL + l] = 1; }); }
+  void final() { each_stage([&](int t, int l, int k) { if (qs_final(q, t, l, k, act, B, status, xt, ut)) status[(q.tile0 + t) * TL + l] = 1; }); }
   void red(bool after) { each_problem([&](int t, int l) { qs_red(P, q, t, l, after); }); }
-  void sync(int& na, int& nr) {
+  int redo_total = 0;
+  void request_counters() {}
+  void wait_counters(int& na, int& nr) {
     na = n_active; nr = 0;
     each_problem([&](int t, int l) { const int32_t* pi = q.pi + qs_pb(t, NPI, l); if (QF(pi, J_ACT) && QF(pi, J_REDO)) ++nr; });
+    redo_total += nr;
   }
 };
 }  // namespace
@@ -125,15 +128,23 @@ extern "C" int emu_qp_solve(const smpc_problem_t* P, int B, const double* rec, c
       for (int f = 0; f < REC; ++f)
         vrec[qs_blk(b / TL, N, k, REC, b % TL) + (size_t)f * TL] = rec[((size_t)b * (N + 1) + k) * REC + f];
   QsBufs q{vrec.data(), {it0.data(), it1.data()}, st.data(), sb.data(), prod.data(), res.data(), stp.data(),
-           pd.data(), pi32.data(), N};
+           pd.data(), pi32.data(), N, 0};
   HostBackend bk{*P, q, B, T, N, order, x0, r, act, xt, ut, status, qp_iter, qp_status, qp_res, std::vector<double>(65 * TL, 0.0)};
-  struct Counting : HostBackend {
-    int redo = 0;
-    void sync(int& na, int& nr) { HostBackend::sync(na, nr); redo += nr; }
-  };
-  Counting cb{bk};
-  qs_drive(cb);
-  if (n_redo_total) *n_redo_total = cb.redo;
+  // two groups of tiles when there is more than one tile (exercises the group offsets), driven round-robin
+  const int G = T > 1 ? 2 : 1;
+  std::vector<HostBackend> gb;
+  for (int g = 0; g < G; ++g) {
+    const int t0 = g == 0 ? 0 : T / 2, t1 = (g == G - 1) ? T : T / 2;
+    HostBackend b2 = bk;
+    const size_t so = (size_t)t0 * (N + 1) * TL;
+    b2.q.rec = q.rec + so * REC; b2.q.it[0] = q.it[0] + so * NIT; b2.q.it[1] = q.it[1] + so * NIT; b2.q.st = q.st + so * NIT;
+    b2.q.sb = q.sb + so * NSB; b2.q.prod = q.prod + so * NPROD; b2.q.res = q.res + so * NRES; b2.q.stp = q.stp + so * NSTP;
+    b2.q.pd = q.pd + (size_t)t0 * NPD * TL; b2.q.pi = q.pi + (size_t)t0 * NPI * TL; b2.q.tile0 = t0;
+    b2.T = t1 - t0;
+    gb.push_back(b2);
+  }
+  qs_drive(gb.data(), G);
+  if (n_redo_total) { *n_redo_total = 0; for (auto& b2 : gb) *n_redo_total += b2.redo_total; }
   for (int b = 0; b < B; ++b) {
     const int tile = b / TL, lane = b % TL;
     const int buf = QF(pi32.data() + qs_pb(tile, NPI, lane), J_ITBUF);

@@ -181,17 +181,34 @@ def run_engine(a):
     solves = (c1['rti_solves'] - c0['rti_solves']) + (c1['backup_solves'] - c0['backup_solves'])
     ipm = c1['ipm_iterations'] - c0['ipm_iterations']
 
-    # ---- dominant kernel (QP) timed alone on this stream, for the roofline ----
+    # ---- the QP solve timed alone, with one CUDA-event pair per kernel on the stream it is launched on (roofline) ----
+    # (a second handle with a single tile group, so that no two kernels of the solve overlap while they are timed)
+    os.environ['SMPC_QP_GROUPS'] = '1'
+    probe, _bk, _ = make_handles(Engine, params, md, a.controller, B, local_rank)
+    os.environ.pop('SMPC_QP_GROUPS')
+    probe.set_guess(*main.get_guess())
     xs = torch.tensor(x0, device=dev)
+    probe.rti_solve(xs); probe.sync()
+    probe.set_profiling(True)
+    profs = []
+    for _ in range(3):
+        probe.rti_solve(xs); probe.sync()
+        profs.append((probe.profile(), probe.times()))
+    probe.set_profiling(False)
+    qp_iter_probe = probe.get_state(abi.STATE_QP_ITER)
+    probe.close(); _bk.close()
     main.rti_solve(xs); main.sync()
     tq = []
     for _ in range(3):
         main.rti_solve(xs); main.sync()
-        t = main_times(main)
-        tq.append(t)
+        tq.append(main.times())
+    (kern, span_ms, it_max), tms = profs[-1]
     qp_ms = float(np.median([t['time_qp'] for t in tq]) * 1e3)
+    qp_ms_1group = float(np.median([p[1]['time_qp'] for p in profs]) * 1e3)
     lin_ms = float(np.median([t['time_lin'] for t in tq]) * 1e3)
     it_qp = float(main.get_state(abi.STATE_QP_ITER).mean())
+    prep_ms, prep_n = kern['qs_prep']
+    kern_total = sum(v[0] for v in kern.values())
 
     # ---- end to end through the C ABI with host buffers (H2D / D2H inside the timed region) ----
     e2e = None
@@ -228,9 +245,16 @@ def run_engine(a):
         pass
     hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
     peak_src = 'measured (MEASURED_PEAKS.json hbm_gbs)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s (B200_PROFILING.md)'
-    # algorithmic bytes of one QP launch: stage records in, x_temp/u_temp + status out
-    alg_bytes = B * ((N + 1) * abi.REC * 8 + ((N + 1) * abi.NX + N * abi.NU) * 8 + abi.NX * 8 + 12)
-    achieved = alg_bytes / (qp_ms * 1e-3) / 1e9
+    # Dominant kernel = qs_prep (update + residuals + condensation, one thread per (problem, stage)).  Algorithmic bytes per
+    # (problem, stage) = every array field the phase has to read or write once: 436 read + 265 written
+    # doubles = 5608 B.
+    prep_bytes_unit = (436 + 265) * 8
+    # a problem takes part in the prep launches kk = 0 .. iter_b of a solve; later launches skip it
+    visits = float((qp_iter_probe + 1).sum())
+    alg_bytes = visits * (N + 1) * prep_bytes_unit / max(1, prep_n)          # per launch, averaged over the launches of one solve
+    prep_launch_ms = prep_ms / max(1, prep_n)
+    achieved = alg_bytes / (prep_launch_ms * 1e-3) / 1e9
+    flops_solve = 0.48e6 * float(main.get_state(abi.STATE_QP_ITER).sum())       # 0.48 MFLOP per IPM iteration
     value = solves_all / (ms_max * 1e-3)
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
@@ -245,9 +269,16 @@ def run_engine(a):
         'ipm_iterations_per_solve': ipm / max(1, solves),
         'gpu_launches': int(sum(v[3] for v in allv)),
         'clocks': clocks,
-        'roofline': {'kernel': 'qp_kernel', 'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak,
-                     'traffic': None, 'peak_source': peak_src, 'algorithmic_bytes_per_launch': alg_bytes, 'launch_ms': qp_ms,
-                     'ipm_iterations': it_qp, 'linearize_ms': lin_ms},
+        'roofline': {'kernel': 'qs_prep_kernel', 'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak,
+                     'traffic': 2.26e9 if (B, N) == (10000, 45) else None,
+                     'traffic_source': 'ncu dram__bytes_read+write per launch, profiles/r01_qp_v6_launches.md (B=10000, N=45 only)',
+                     'peak_source': peak_src, 'algorithmic_bytes_per_launch': alg_bytes, 'launch_ms': prep_launch_ms,
+                     'launches_per_solve': prep_n, 'share_of_qp_solve': prep_ms / max(kern_total, 1e-9),
+                     'note': 'bytes and time are averaged over every qs_prep launch of one solve; a launch only touches the problems still iterating'},
+        'qp_solve': {'ms': qp_ms, 'ms_single_tile_group': qp_ms_1group, 'linearize_ms': lin_ms, 'ipm_iterations_mean': it_qp, 'ipm_iterations_max': it_max,
+                     'algorithmic_fp64_tflops': flops_solve / (qp_ms * 1e-3) / 1e12,
+                     'kernel_ms': {k: round(v[0], 3) for k, v in kern.items()}, 'kernel_launches': {k: v[1] for k, v in kern.items()},
+                     'kernel_ms_note': 'per-kernel sums of one solve timed with a single tile group (no overlap between kernels)'},
         'outcome': D.outcome_counts(outcome),
     }
     if e2e:
@@ -270,7 +301,7 @@ def guess_copy(main):
 
 
 def main_qp_bytes(N):
-    return ((N + 1) * (736 + abi.REC) + 320) * 8     # stage blocks (qp_lanes.cuh QP_ST) + stage records
+    return (N + 1) * (abi.REC + 3 * 120 + 330 + 46 + 8 + 4) * 8     # per problem: records, iterate x2, step, solver block, products, partials (qp_split.cuh)
 
 
 def main():

@@ -246,6 +246,14 @@ int smpc_sim_get_counters(smpc_sim_t* s, int64_t* out4);
 /* --- timing of the last rti_solve/controller_step, milliseconds, CUDA events (replaces get_stats, controller.py:192-193) ---
  * out[0]=time_lin out[1]=time_sim out[2]=time_qp out[3]=time_qp_solver_call out[4]=time_glob out[5]=time_reg out[6]=time_tot */
 int smpc_get_times(smpc_handle_t* h, double* out7);
+/* per-kernel timing of the QP solver (the split interior-point kernels of csrc/qp.cu), CUDA events on the streams the
+ * kernels are launched on.  smpc_set_profiling(h, 1) makes every following solve record one event pair per kernel (and
+ * synchronise at its end); smpc_get_profile returns, for the last solve, the summed duration [ms] and the launch count per
+ * kernel kind (index = SMPC_PROF_*), the span of the whole solve [ms] and the IPM iterations of the slowest problem. */
+enum { SMPC_PROF_INIT = 0, SMPC_PROF_PREP = 1, SMPC_PROF_CTL = 2, SMPC_PROF_RIC1 = 3, SMPC_PROF_STEP0 = 4, SMPC_PROF_RIC2 = 5,
+       SMPC_PROF_STEP1 = 6, SMPC_PROF_RED = 7, SMPC_PROF_RIC2C = 8, SMPC_PROF_STEP2 = 9, SMPC_PROF_FINAL = 10, SMPC_PROF_N = 11 };
+int smpc_set_profiling(smpc_handle_t* h, int32_t enable);
+int smpc_get_profile(smpc_handle_t* h, double* ms /*[SMPC_PROF_N]*/, int32_t* count /*[SMPC_PROF_N]*/, double* span_ms, int32_t* iterations);
 /* number of kernels this handle has launched so far (bench.py "gpu_launches") */
 int64_t smpc_launch_count(const smpc_handle_t* h);
 /* the CUDA stream the handle launches on (cudaStream_t as void*) */

@@ -42,6 +42,7 @@ struct smpc_handle {
   size_t stage_bytes = 0;
   double times[7] = {0, 0, 0, 0, 0, 0, 0};
   bool timed = false;
+  int times_pending = 0;        // 1: events of an rti_solve recorded, 2: of a controller_step; collected by smpc_get_times
   LaunchCtx ctx() { return LaunchCtx{stream, &launches}; }
 };
 
@@ -301,7 +302,7 @@ int smpc_rti_solve(smpc_handle_t* h, const double* x0, const uint8_t* active, in
   h->timed = true;
   rc = solve_pipeline(h, xd, act);
   if (rc) return rc;
-  if (mem == SMPC_HOST) { CK(h, cudaStreamSynchronize(h->stream)); collect_times(h, false); }
+  h->times_pending = 1;
   return copy_out(h, status, h->status, sizeof(int32_t) * h->B, mem);
 }
 
@@ -321,9 +322,8 @@ int smpc_controller_step(smpc_handle_t* h, const double* x, const uint8_t* activ
   h->timed = true;
   rc = step_pipeline(h, xd, act, ud, ad);
   if (rc) return rc;
+  h->times_pending = 2;
   if (mem == SMPC_HOST) {
-    CK(h, cudaStreamSynchronize(h->stream));
-    collect_times(h, true);
     rc = copy_out(h, u, h->u_out, sizeof(double) * h->B * NU, mem); if (rc) return rc;
     rc = copy_out(h, abort_flag, h->abort_flag, (size_t)h->B, mem);
   }
@@ -439,7 +439,22 @@ int smpc_set_state_i32(smpc_handle_t* h, int32_t f, const int32_t* in, int32_t m
 }
 int smpc_get_x_viable(smpc_handle_t* h, double* xv, int32_t mem) { return copy_out(h, xv, h->x_viable, sizeof(double) * h->B * NX, mem); }
 
-int smpc_get_times(smpc_handle_t* h, double* out7) { for (int i = 0; i < 7; ++i) out7[i] = h->times[i]; return SMPC_OK; }
+int smpc_set_profiling(smpc_handle_t* h, int32_t enable) { qp_set_profiling(h->qp, enable != 0); return SMPC_OK; }
+int smpc_get_profile(smpc_handle_t* h, double* ms, int32_t* count, double* span_ms, int32_t* iterations) {
+  if (!ms || !count || !span_ms || !iterations) return fail(h, SMPC_ERR_ARG, "smpc_get_profile: NULL output");
+  qp_get_profile(h->qp, ms, count, span_ms);
+  *iterations = qp_last_iterations(h->qp);
+  return SMPC_OK;
+}
+int smpc_get_times(smpc_handle_t* h, double* out7) {
+  if (h->times_pending) {
+    CK(h, cudaStreamSynchronize(h->stream));
+    collect_times(h, h->times_pending == 2);
+    h->times_pending = 0;
+  }
+  for (int i = 0; i < 7; ++i) out7[i] = h->times[i];
+  return SMPC_OK;
+}
 int64_t smpc_launch_count(const smpc_handle_t* h) { return h->launches; }
 void* smpc_stream(smpc_handle_t* h) { return (void*)h->stream; }
 int smpc_sync(smpc_handle_t* h) { CK(h, cudaStreamSynchronize(h->stream)); return check_launch(h, "sync"); }

@@ -67,7 +67,9 @@ QpSolver* qp_create(int B, int N, int iter_max, cudaStream_t stream, cudaError_t
 void qp_destroy(QpSolver* s);
 double* qp_rec(QpSolver* s);                  // tile-interleaved stage records [T][N+1][REC][32] the linearisation writes
 int qp_groups(const QpSolver* s);              // tile groups solved concurrently
-int qp_last_iterations(const QpSolver* s);    // IPM iterations of the slowest problem of the last solve
+int qp_last_iterations(const QpSolver* s);
+void qp_set_profiling(QpSolver* s, bool on);
+void qp_get_profile(const QpSolver* s, double* ms, int32_t* n, double* span_ms);    // IPM iterations of the slowest problem of the last solve
 // one batched solve; reads the records of qp_rec(); problems with act == 0 are skipped and keep their outputs
 cudaError_t launch_qp_solve(const LaunchCtx& c, const smpc_problem_t* dP, QpSolver* s, const double* x0, const int32_t* r, const uint8_t* act,
                             double* xt, double* ut, int32_t* status, int32_t* qp_iter, int32_t* qp_status, double* qp_res);

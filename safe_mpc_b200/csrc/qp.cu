@@ -12,6 +12,7 @@
 // iteration; everything else is asynchronous on the handle's stream.
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "engine.cuh"
@@ -215,6 +216,10 @@ struct QpSolver {
   int* h_counters = nullptr;
   cudaEvent_t ev_in = nullptr;  // inputs (records, x0) are ready on the caller's stream
   int last_iters = 0;
+  bool profile = false;         // record one event pair per kernel of the next solves (smpc_set_profiling)
+  double prof_ms[SMPC_PROF_N] = {0};
+  int32_t prof_n[SMPC_PROF_N] = {0};
+  double prof_span_ms = 0.0;
 };
 
 size_t qp_bytes(int B, int N) {
@@ -303,12 +308,25 @@ void qp_destroy(QpSolver* s) {
 double* qp_rec(QpSolver* s) { return const_cast<double*>(s->q.rec); }
 int qp_last_iterations(const QpSolver* s) { return s->last_iters; }
 int qp_groups(const QpSolver* s) { return s->G; }
+void qp_set_profiling(QpSolver* s, bool on) { s->profile = on; }
+void qp_get_profile(const QpSolver* s, double* ms, int32_t* n, double* span_ms) {
+  for (int i = 0; i < SMPC_PROF_N; ++i) { ms[i] = s->prof_ms[i]; n[i] = s->prof_n[i]; }
+  *span_ms = s->prof_span_ms;
+}
 
 namespace {
 // optional timeline (SMPC_QP_TRACE=1): one event pair per kernel, printed to stderr after the solve
 struct TraceRec { int g; const char* name; int kk; cudaEvent_t a, b; };
 static std::vector<TraceRec> g_trace;
-static bool trace_on() { static int v = -1; if (v < 0) v = getenv("SMPC_QP_TRACE") ? 1 : 0; return v == 1; }
+static bool g_profile = false;
+static bool trace_print() { static int v = -1; if (v < 0) v = getenv("SMPC_QP_TRACE") ? 1 : 0; return v == 1; }
+static bool trace_on() { return g_profile || trace_print(); }
+static int prof_slot(const char* n) {
+  static const char* names[SMPC_PROF_N] = {"qs_init_kernel", "qs_prep_kernel", "qs_ctl_kernel", "qs_ric1_kernel", "qs_step_kernel<0>", "qs_ric2_kernel<1>",
+                                           "qs_step_kernel<1>", "qs_red_kernel", "qs_ric2_kernel<2>", "qs_step_kernel<2>", "qs_final_kernel"};
+  for (int i = 0; i < SMPC_PROF_N; ++i) if (names[i] && !strcmp(names[i], n)) return i;
+  return 0;
+}
 
 // kernel launches of one tile group on its own stream
 struct DeviceBackend {
@@ -379,13 +397,14 @@ struct DeviceBackend {
     cudaError_t e = err == cudaSuccess ? cudaEventSynchronize(g->ev) : err;
     if (e != cudaSuccess) { err = e; na = 0; nr = 0; return; }     // stop iterating; the caller reports the error
     na = g->h_counters[0]; nr = g->h_counters[1];
-    if (trace_on()) fprintf(stderr, "QPCOUNT g=%d kk=%d active=%d redo=%d\n", gi(), kk_last, na, nr);
+    if (trace_print()) fprintf(stderr, "QPCOUNT g=%d kk=%d active=%d redo=%d\n", gi(), kk_last, na, nr);
   }
 };
 }  // namespace
 
 cudaError_t launch_qp_solve(const LaunchCtx& c, const smpc_problem_t* dP, QpSolver* s, const double* x0, const int32_t* r, const uint8_t* act,
                             double* xt, double* ut, int32_t* status, int32_t* qp_iter, int32_t* qp_status, double* qp_res) {
+  g_profile = s->profile;
   // the group streams start after everything queued on the caller's stream (linearisation, input copies) ...
   cudaError_t e = cudaEventRecord(s->ev_in, c.stream);
   if (e != cudaSuccess) return e;
@@ -400,11 +419,17 @@ cudaError_t launch_qp_solve(const LaunchCtx& c, const smpc_problem_t* dP, QpSolv
     for (int g = 0; g < s->G; ++g) cudaStreamSynchronize(bk[g].st(false));
     if (!g_trace.empty()) {
       cudaEvent_t t0 = g_trace[0].a;
+      for (int i = 0; i < SMPC_PROF_N; ++i) { s->prof_ms[i] = 0.0; s->prof_n[i] = 0; }
+      float t_end = 0;
       for (auto& r : g_trace) {
         float a = 0, b = 0;
         cudaEventElapsedTime(&a, t0, r.a); cudaEventElapsedTime(&b, t0, r.b);
-        fprintf(stderr, "QPTRACE g=%d kk=%d %-12s start=%9.3f end=%9.3f dur=%8.3f\n", r.g, r.kk, r.name, a, b, b - a);
+        if (trace_print()) fprintf(stderr, "QPTRACE g=%d kk=%d %-12s start=%9.3f end=%9.3f dur=%8.3f\n", r.g, r.kk, r.name, a, b, b - a);
+        const int sl = prof_slot(r.name);
+        s->prof_ms[sl] += b - a; s->prof_n[sl] += 1;
+        t_end = b > t_end ? b : t_end;
       }
+      s->prof_span_ms = t_end;
       for (auto& r : g_trace) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
       g_trace.clear();
     }

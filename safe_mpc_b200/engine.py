@@ -63,6 +63,19 @@ class Engine(EngineBase):
     def stream(self) -> int:
         return int(self.lib.smpc_stream(self.h) or 0)
 
+    PROF_NAMES = ['qs_init', 'qs_prep', 'qs_ctl', 'qs_ric1', 'qs_step0', 'qs_ric2', 'qs_step1', 'qs_red', 'qs_ric2_centering',
+                  'qs_step2_centering', 'qs_final']
+
+    def set_profiling(self, on: bool):
+        self._call('set_profiling', C.c_int32(int(on)))
+
+    def profile(self):
+        """Per-kernel durations of the last QP solve (after set_profiling(True)): {name: (total_ms, launches)}, span, iterations."""
+        ms = (C.c_double * len(self.PROF_NAMES))(); n = (C.c_int32 * len(self.PROF_NAMES))()
+        span = C.c_double(); it = C.c_int32()
+        self._call('get_profile', ms, n, C.byref(span), C.byref(it))
+        return {k: (ms[i], n[i]) for i, k in enumerate(self.PROF_NAMES)}, span.value, it.value
+
     def times(self):
         out = (C.c_double * 7)()
         self._call('get_times', out)

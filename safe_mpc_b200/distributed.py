@@ -70,4 +70,4 @@ def outcome_counts(outcome):
     coll = (o & abi.OUT_COLLIDED) != 0
     viable = ((o & abi.OUT_ABORTED) != 0) & ~conv & ~coll
     return {'completed': int(conv.sum()), 'collisions': int(coll.sum()), 'viable': int(viable.sum()),
-            'not_converged': int(len(o) - conv.sum() - coll.sum())}
+            'not_converged': int(len(o) - (conv | coll | viable).sum())}

@@ -328,6 +328,7 @@ def main():
         run_reference(a)
     else:
         run_engine(a)
+        D.finalize()
 
 
 if __name__ == '__main__':

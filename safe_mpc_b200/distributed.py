@@ -27,6 +27,12 @@ def init(backend: str):
     return rank, local_rank, world
 
 
+def finalize():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        dist.destroy_process_group()
+
+
 def barrier():
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized():

@@ -39,12 +39,13 @@ __global__ void __launch_bounds__(32) qs_init_kernel(QsBufs q, int B, const doub
 
 constexpr size_t PREP_SMEM = sizeof(double) * 2 * PREP_SCRATCH * TL + 512;   // a retiring prep CTA leaves room for one Riccati CTA
 constexpr int PREP_WARPS = 2;    // warps per CTA of prep: 2 x 26.9 KB of lane-private Jacobian scratch, 4 CTAs per SM
+template <bool FIRST>
 __global__ void __launch_bounds__(32 * PREP_WARPS, QS_PREP_MINB) qs_prep_kernel(const smpc_problem_t* __restrict__ dP, QsBufs q, int T, int kk) {
   extern __shared__ __align__(128) double jsm_all[];
   const int wi = threadIdx.x >> 5;
   const int w = blockIdx.x * PREP_WARPS + wi;
   if (w >= T * (q.N + 1)) return;
-  qs_prep(*dP, q, w / (q.N + 1), threadIdx.x & 31, w % (q.N + 1), kk, jsm_all + (size_t)wi * PREP_SCRATCH * TL + (threadIdx.x & 31));
+  qs_prep<FIRST>(*dP, q, w / (q.N + 1), threadIdx.x & 31, w % (q.N + 1), kk, jsm_all + (size_t)wi * PREP_SCRATCH * TL + (threadIdx.x & 31));
 }
 
 template <int MODE>
@@ -110,6 +111,11 @@ struct TmaStage {
       asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(addr), "r"(par) : "memory");
     } while (!ok);
     phase[b] = par ^ 1u;
+  }
+  // hint: start moving a field range of a stage block towards L2
+  __device__ __forceinline__ void prefetch(const double* gblock, int src_field, int nfields) const {
+    if (ln == 0)
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gblock + (size_t)src_field * TL), "r"(nfields * TL * 8) : "memory");
   }
   // this lane's global stores become visible to bulk copies issued after the next warp barrier
   __device__ __forceinline__ void publish() const { asm volatile("fence.proxy.async;" ::: "memory"); }
@@ -246,7 +252,8 @@ QpSolver* qp_create(int B, int N, int iter_max, cudaStream_t stream, cudaError_t
   if (e == cudaSuccess) e = cudaMalloc((void**)&s->counters, sizeof(int) * ncnt * G);
   if (e == cudaSuccess) e = cudaMallocHost((void**)&s->h_counters, sizeof(int) * 2 * G);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_in, cudaEventDisableTiming);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(qs_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PREP_SMEM);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(qs_prep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PREP_SMEM);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(qs_prep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PREP_SMEM);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(qs_ric1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RIC1_SMEM);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(qs_ric2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RIC2_SMEM);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(qs_ric2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RIC2_SMEM);
@@ -366,7 +373,14 @@ struct DeviceBackend {
     count();
   }
   void prep(int kk) {
-    { cudaStream_t stm_ = st(false); tr0("qs_prep_kernel", stm_); qs_prep_kernel<<<(g->T * (s->N + 1) + PREP_WARPS - 1) / PREP_WARPS, 32 * PREP_WARPS, PREP_SMEM, stm_>>>(dP, g->q, g->T, kk); tr1(stm_); }
+    {
+      cudaStream_t stm_ = st(false);
+      const int grid = (g->T * (s->N + 1) + PREP_WARPS - 1) / PREP_WARPS;
+      tr0("qs_prep_kernel", stm_);
+      if (kk == 0) qs_prep_kernel<true><<<grid, 32 * PREP_WARPS, PREP_SMEM, stm_>>>(dP, g->q, g->T, kk);
+      else qs_prep_kernel<false><<<grid, 32 * PREP_WARPS, PREP_SMEM, stm_>>>(dP, g->q, g->T, kk);
+      tr1(stm_);
+    }
     count();
   }
   void ctl(int kk) {

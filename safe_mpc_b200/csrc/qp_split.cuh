@@ -133,12 +133,13 @@ struct QsNorms {
 // jsm: lane-private on-chip scratch [PREP_SCRATCH][TL] (lane offset applied) that keeps the torque and capsule Jacobians
 // of the stage between their three uses (row products, multiplier terms, condensation): each entry is read ~10 times.
 enum { PREP_SCRATCH = 105 };
+template <bool FIRST>
 SMPC_HD void qs_prep(const smpc_problem_t& P, const QsBufs& q, int tile, int lane, int k, int kk, double* jsm) {
   const int N = q.N;
   const int32_t* pi = q.pi + qs_pb(tile, NPI, lane);
   if (!QF(pi, J_ACT)) return;
   const double* pd = q.pd + qs_pb(tile, NPD, lane);
-  const bool first = kk == 0;
+  constexpr bool first = FIRST;            // cold start (kk == 0) is its own instantiation: half the code, no runtime branches
   const double a = first ? 0.0 : QF(pd, D_STEP);
   const int rrec = QF(pi, J_R);
   const double* rec = q.rec + qs_blk(tile, N, k, REC, lane);
@@ -548,6 +549,7 @@ SMPC_HD void qs_ric1(const smpc_problem_t& P, const QsBufs& q, int tile, W& w, d
     w.sync();                                                    // every lane is done with the buffer of stage k + 1
     if (nb1 && k > 0) { w.fetch_begin((k - 1) & 1, B_LP - B_M); w.fetch((k - 1) & 1, 0, gsb + (size_t)(k - 1) * sstride, B_M, B_LP - B_M); }
     if (!nb1 && k < N) { w.fetch_begin(0, B_LP - B_M); w.fetch(0, 0, gsb + (size_t)k * sstride, B_M, B_LP - B_M); }
+    if (!nb1 && k > 0) w.prefetch(gsb + (size_t)(k - 1) * sstride, B_M, B_LP - B_M);      // next stage on its way to L2 meanwhile
     w.wait(k & nb1);
     const double* hc = w.buf(k & nb1);                           // fields B_M .. B_LP at their own offsets
     double* fac = q.sb + qs_blk(tile, N, k, NSB, lane);
@@ -691,6 +693,7 @@ SMPC_HD void qs_ric1(const smpc_problem_t& P, const QsBufs& q, int tile, W& w, d
     w.sync();
     if (nb1 && k < N) { w.fetch_begin((k + 1) & 1, B_WV - B_RB); w.fetch((k + 1) & 1, 0, gsb + (size_t)(k + 1) * sstride, B_RB, B_WV - B_RB); }
     if (!nb1 && k > 0) { w.fetch_begin(0, B_WV - B_RB); w.fetch(0, 0, gsb + (size_t)k * sstride, B_RB, B_WV - B_RB); }
+    if (!nb1 && k < N) w.prefetch(gsb + (size_t)(k + 1) * sstride, B_RB, B_WV - B_RB);
     w.wait(k & nb1);
     const double* sb = w.buf(k & nb1) - (size_t)B_RB * TL;       // sb[f] valid for B_RB <= f < B_WV
     double* st = q.st + qs_blk(tile, N, k, NIT, lane);
@@ -781,6 +784,7 @@ SMPC_HD void qs_ric2(const smpc_problem_t& P, const QsBufs& q, int tile, W& w, i
       w.fetch(kf & nb1, 0, gsb + (size_t)kf * sstride, B_GA, n1);
       w.fetch(kf & nb1, n1, gsb + (size_t)kf * sstride, B_V1, n2);
     }
+    if (!nb1 && k > 0) { w.prefetch(gsb + (size_t)(k - 1) * sstride, B_GA, n1); w.prefetch(gsb + (size_t)(k - 1) * sstride, B_V1, n2); }
     w.wait(k & nb1);
     const double* sb = w.buf(k & nb1) - (size_t)B_GA * TL;         // sb[f] valid for B_GA <= f < B_P
     const double* vv = w.buf(k & nb1) - (size_t)(B_V1 - n1) * TL;  // vv[f] valid for B_V1 <= f < NSB
@@ -836,6 +840,7 @@ SMPC_HD void qs_ric2(const smpc_problem_t& P, const QsBufs& q, int tile, W& w, i
     w.sync();
     if (nb1 && k < N) { w.fetch_begin((k + 1) & 1, B_V1 - B_RB); w.fetch((k + 1) & 1, 0, gsb + (size_t)(k + 1) * sstride, B_RB, B_V1 - B_RB); }
     if (!nb1 && k > 0) { w.fetch_begin(0, B_V1 - B_RB); w.fetch(0, 0, gsb + (size_t)k * sstride, B_RB, B_V1 - B_RB); }
+    if (!nb1 && k < N) w.prefetch(gsb + (size_t)(k + 1) * sstride, B_RB, B_V1 - B_RB);
     w.wait(k & nb1);
     const double* sb = w.buf(k & nb1) - (size_t)B_RB * TL;
     double* st = q.st + qs_blk(tile, N, k, NIT, lane);
@@ -906,7 +911,10 @@ SMPC_HD void qs_step(const smpc_problem_t& P, const QsBufs& q, int tile, int lan
   double z[15], dz[15];
 #pragma unroll
   for (int i = 0; i < 15; ++i) { z[i] = QF(it, I_Z + i); dz[i] = QF(st, I_Z + i); }
-  double alpha = 1.0, s_lin = 0.0, s_quad = 0.0;
+  // step length = min over the slots of lam / (-dlam), t / (-dt) (negative steps only), kept as a fraction an / ad and
+  // compared by cross-multiplication: one division per thread instead of two per slot
+  double an = 1.0, ad = 1.0, s_lin = 0.0, s_quad = 0.0;
+  auto ratio = [&](double num, double neg_den) { if (neg_den < 0.0 && num * ad < an * (-neg_den)) { an = num; ad = -neg_den; } };
   double v1[15], v2[15];
 #pragma unroll
   for (int i = 0; i < 15; ++i) { v1[i] = 0.0; v2[i] = 0.0; }
@@ -919,8 +927,7 @@ SMPC_HD void qs_step(const smpc_problem_t& P, const QsBufs& q, int tile, int lan
     const double it_ = 1.0 / t;
     const double dtt = sgn * adz - r;
     const double dl = -(rm + lam * dtt) * it_;
-    if (dl < 0.0) alpha = fmin(alpha, -lam / dl);
-    if (dtt < 0.0) alpha = fmin(alpha, -t / dtt);
+    ratio(lam, dl); ratio(t, dtt);
     s_lin += lam * dtt + t * dl; s_quad += dl * dtt;
     if (mode == 0) { const double pp = dl * dtt; QF(prod, slot) = pp; e1 += sgn * pp * it_; e2 += sgn * it_; }
     else { QF(st, I_LAM + slot) = dl; QF(st, I_T + slot) = dtt; }
@@ -1052,13 +1059,11 @@ SMPC_HD void qs_step(const smpc_problem_t& P, const QsBufs& q, int tile, int lan
         const double ds = -(rgs + c + cs + sgn * G * adz) * W;
         const double dts = ds - rsl;
         const double dls = -(rms + ls * dts) * its;
-        if (dls < 0.0) alpha = fmin(alpha, -ls / dls);
-        if (dts < 0.0) alpha = fmin(alpha, -ts / dts);
+        ratio(ls, dls); ratio(ts, dts);
         s_lin += ls * dts + ts * dls; s_quad += dls * dts;
         const double dtt = sgn * adz + ds - r;
         const double dl = -(rm + lam * dtt) * it_;
-        if (dl < 0.0) alpha = fmin(alpha, -lam / dl);
-        if (dtt < 0.0) alpha = fmin(alpha, -t / dtt);
+        ratio(lam, dl); ratio(t, dtt);
         s_lin += lam * dtt + t * dl; s_quad += dl * dtt;
         if (mode == 0) {
           const double pp = dl * dtt, sp = dls * dts;
@@ -1088,7 +1093,7 @@ SMPC_HD void qs_step(const smpc_problem_t& P, const QsBufs& q, int tile, int lan
     for (int i = 0; i < 15; ++i) { QF(vv, V_1 + i) = v1[i]; QF(vv, V_2 + i) = v2[i]; }
   }
   double* stp = q.stp + qs_blk(tile, N, k, NSTP, lane);
-  QF(stp, S_ALPHA) = alpha; QF(stp, S_LIN) = s_lin; QF(stp, S_QUAD) = s_quad;
+  QF(stp, S_ALPHA) = an / ad; QF(stp, S_LIN) = s_lin; QF(stp, S_QUAD) = s_quad;
 }
 
 // ================================================================================================================

@@ -69,6 +69,7 @@ struct HostStage {
   }
   void wait(int b) { for (auto& c : pend[b]) std::memcpy(c.dst, c.src, c.n * sizeof(double)); pend[b].clear(); }
   void publish() const {}
+  void prefetch(const double*, int, int) const {}
 };
 
 struct HostBackend {
@@ -92,7 +93,9 @@ struct HostBackend {
   void init() { each_problem([&](int t, int l) { qs_init(q, t, l, B, x0, r, act); }); }
   void prep(int kk) {
     std::vector<double> jsm((size_t)PREP_SCRATCH * TL, 0.0);
-    each_stage([&](int t, int l, int k) { qs_prep(P, q, t, l, k, kk, jsm.data() + l); });
+    each_stage([&](int t, int l, int k) {
+      if (kk == 0) qs_prep<true>(P, q, t, l, k, kk, jsm.data() + l); else qs_prep<false>(P, q, t, l, k, kk, jsm.data() + l);
+    });
   }
   void ctl(int kk) {
     n_active = 0;

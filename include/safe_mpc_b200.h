@@ -70,6 +70,8 @@ enum {
   SMPC_NN_EVERYWHERE = 3        /* stages 1..N, never gated                        */
 };
 
+enum { SMPC_NN_STRICT = 0, SMPC_NN_TF32X3 = 1 };
+
 enum { SMPC_COST_ZERO = 0, SMPC_COST_EXT = 1, SMPC_COST_NLS = 2 };
 
 /*
@@ -124,7 +126,10 @@ typedef struct smpc_problem {
   int32_t lm_scale_dt;           /* 1: LM term is scaled by the stage time step for k<N (acados
                                     ocp_nlp_approximate_qp_matrices convention)    */
   int32_t qp_cond_pred_corr;     /* HPIPM BALANCE: 1                                              */
-  int32_t reserved_i[3];
+  int32_t nn_precision;          /* SMPC_NN_STRICT: fp32 weights, fp64 accumulation (FP64 pipe);
+                                    SMPC_NN_TF32X3: fp32-class evaluation on the tensor cores (the precision of the
+                                    reference's libtorch call, safe_set.py:76-94), see csrc/mlp_tc.cu              */
+  int32_t reserved_i[2];
   /* ---- scalars ---- */
   double dt;                     /* config.yaml:7                                                 */
   double q_weight, r_weight;     /* config.yaml:35,39                                             */

@@ -29,6 +29,9 @@ struct smpc_handle {
   // network
   float* dW = nullptr;
   MlpWeights w{};
+  float* dWtc = nullptr;            // packed tf32 hi / lo stage images of the tensor-core path (mlp_tc.cu)
+  MlpTcWeights wtc{};
+  int n_sm = 0;
   // state
   double *xg = nullptr, *ug = nullptr, *xt = nullptr, *ut = nullptr, *plant_inertial = nullptr, *tau_noise = nullptr,
          *x_viable = nullptr, *nn11 = nullptr, *scan11 = nullptr, *qp_res = nullptr, *x_in = nullptr, *u_out = nullptr;
@@ -117,6 +120,14 @@ int mask_in(smpc_handle* h, const uint8_t* active, int mem, const uint8_t** out)
   return rc;
 }
 
+// viability network on the rows selected by `mode`: strict fp64-accumulate kernel or the tensor-core kernel (nn_precision)
+void run_mlp(smpc_handle* h, int B, int N, int mode, int n_flat, const double* xsrc, const uint8_t* act, const uint8_t* need, double* out11,
+             bool want_grad) {
+  LaunchCtx c = h->ctx();
+  if (h->P.nn_precision == SMPC_NN_TF32X3) launch_mlp_tc(c, h->dP, h->wtc, h->n_sm, B, N, mode, n_flat, xsrc, h->r, act, need, out11, want_grad);
+  else launch_mlp(c, h->dP, h->w, B, N, mode, n_flat, xsrc, h->r, act, need, out11, want_grad);
+}
+
 // linearise + QP for the problems in `act` at the stored guess: AbstractController.solve (controller.py:136-167)
 int solve_pipeline(smpc_handle* h, const double* x0_dev, const uint8_t* act) {
   LaunchCtx c = h->ctx();
@@ -124,7 +135,7 @@ int solve_pipeline(smpc_handle* h, const double* x0_dev, const uint8_t* act) {
   if (h->timed) cudaEventRecord(h->ev[0], h->stream);
   if (h->P.nn_rows != SMPC_NN_NONE) {
     const int mode = h->P.nn_rows == SMPC_NN_TERMINAL ? ROWS_TERMINAL : (h->P.nn_rows == SMPC_NN_EVERYWHERE ? ROWS_ALL : ROWS_RECEDING);
-    launch_mlp(c, h->dP, h->w, B, N, mode, 0, h->xg, h->r, act, nullptr, h->nn11, true);
+    run_mlp(h, B, N, mode, 0, h->xg, act, nullptr, h->nn11, true);
   }
   launch_linearize(c, h->dP, B, N, h->xg, h->ug, h->r, act, h->nn11, qp_rec(h->qp));
   if (h->timed) cudaEventRecord(h->ev[1], h->stream);
@@ -144,7 +155,7 @@ int step_pipeline(smpc_handle* h, const double* x_dev, const uint8_t* act, doubl
   if (rc) return rc;
   launch_ctrl_post1(c, h->dP, B, N, act, h->xg, h->ug, h->xt, h->status, h->fails, h->r, h->x_viable, h->need_scan, abort_dev, u_dev);
   if (h->P.controller == SMPC_CTRL_RECEDING || h->P.controller == SMPC_CTRL_REAL_RECEDING)
-    launch_mlp(c, h->dP, h->w, B, N, ROWS_ALL, 0, h->xt, h->r, act, h->need_scan, h->scan11, false);
+    run_mlp(h, B, N, ROWS_ALL, 0, h->xt, act, h->need_scan, h->scan11, false);
   launch_ctrl_post2(c, h->dP, B, N, act, h->xg, h->ug, h->xt, h->ut, h->fails, h->r, h->cur_step, h->need_scan, h->scan11, abort_dev, u_dev);
   if (h->timed) cudaEventRecord(h->ev[3], h->stream);
   return check_launch(h, "controller step pipeline");
@@ -212,6 +223,22 @@ int smpc_create(const smpc_problem_t* prob, int32_t batch, int32_t device, smpc_
     h->w.W3 = d; d += sq; h->w.b3 = d; d += SMPC_HID;
     h->w.W4 = d; d += SMPC_HID; h->w.b4 = d; d += 1;
     h->w.W2t = d; d += sq; h->w.W3t = d;
+    if (prob->nn_precision == SMPC_NN_TF32X3) {
+      cudaDeviceProp dp;
+      CKC(cudaGetDeviceProperties(&dp, device));
+      if (dp.major < 10) { fail(nullptr, SMPC_ERR_UNSUPPORTED, "smpc_create: nn_precision = SMPC_NN_TF32X3 needs tcgen05 (sm_100a)"); smpc_destroy(h); return SMPC_ERR_UNSUPPORTED; }
+      h->n_sm = dp.multiProcessorCount;
+      std::vector<float> packed(mlp_tc_packed_floats());
+      mlp_tc_pack(W2, W3, packed.data());
+      CKC(dalloc(h, &h->dWtc, packed.size()));
+      CKC(cudaMemcpyAsync(h->dWtc, packed.data(), packed.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+      CKC(cudaStreamSynchronize(h->stream));
+      CKC(mlp_tc_prepare());
+      h->wtc = MlpTcWeights{h->w.W1, h->w.b1, h->w.b2, h->w.b3, h->w.W4, h->w.b4, h->dWtc};
+    }
+  }
+  if (prob->nn_precision != SMPC_NN_STRICT && prob->nn_precision != SMPC_NN_TF32X3) {
+    fail(nullptr, SMPC_ERR_ARG, "smpc_create: unknown nn_precision"); smpc_destroy(h); return SMPC_ERR_ARG;
   }
   CKC(dalloc(h, &h->dP, 1));
   {
@@ -382,7 +409,7 @@ int smpc_nn_constraint(smpc_handle_t* h, int32_t n, const double* x, double* cva
   const double* xd = x;
   if (mem == SMPC_HOST) { rc = copy_in(h, s, x, bx, mem); if (rc) return rc; xd = (double*)s; }
   double* o11 = (double*)(s + bx);
-  launch_mlp(h->ctx(), h->dP, h->w, n, 0, ROWS_FLAT, n, xd, nullptr, nullptr, nullptr, o11, true);
+  run_mlp(h, n, 0, ROWS_FLAT, n, xd, nullptr, nullptr, o11, true);
   rc = check_launch(h, "nn_constraint"); if (rc) return rc;
   // de-interleave [n][11] -> c[n], grad[n][10]
   double* dc = (double*)(s + bx + bo);

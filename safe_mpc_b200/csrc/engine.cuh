@@ -21,6 +21,27 @@ struct MlpWeights {
 // which (problem, stage) rows the viability network is evaluated on
 enum { ROWS_TERMINAL = 0, ROWS_ALL = 1, ROWS_RECEDING = 2, ROWS_FLAT = 3 };
 
+// operands of the tensor-core evaluation of the network (mlp_tc.cu): plain fp32 vectors + the packed hi / lo stage images
+struct MlpTcWeights {
+  const float *W1, *b1, *b2, *b3, *W4, *b4;
+  const float* packed;
+};
+
+#if defined(__CUDACC__)
+// row i of an evaluation -> (problem b, stage k); false when the row is not evaluated
+__device__ __forceinline__ bool mlp_row(int rows_mode, int i, int B, int N, const int32_t* r, const uint8_t* act, const uint8_t* need,
+                                        int& b, int& k) {
+  if (rows_mode == ROWS_TERMINAL) { b = i; k = N; }
+  else if (rows_mode == ROWS_ALL) { b = i / N; k = 1 + i % N; }
+  else if (rows_mode == ROWS_RECEDING) { b = i >> 1; if (b >= B) return false; k = (i & 1) ? N : r[b]; if (k < 1 || (!(i & 1) && k >= N)) return false; }
+  else { b = i; k = 0; return true; }
+  if (b >= B) return false;
+  if (act && !act[b]) return false;
+  if (need && !need[b]) return false;
+  return true;
+}
+#endif
+
 struct LaunchCtx {
   cudaStream_t stream;
   int64_t* launches;
@@ -30,6 +51,12 @@ struct LaunchCtx {
 void launch_prep(const LaunchCtx& c, const smpc_problem_t* dP, int B, int N, double* xg, const double* ug, const uint8_t* act, bool correct);
 void launch_mlp(const LaunchCtx& c, const smpc_problem_t* dP, const MlpWeights& w, int B, int N, int rows_mode, int n_flat,
                 const double* xsrc, const int32_t* r, const uint8_t* act, const uint8_t* need, double* out11, bool want_grad);
+// mlp_tc.cu -- the same evaluation on the tensor cores (fp32 class, smpc_problem_t::nn_precision = 1)
+size_t mlp_tc_packed_floats();
+void mlp_tc_pack(const float* W2, const float* W3, float* out);
+cudaError_t mlp_tc_prepare();
+void launch_mlp_tc(const LaunchCtx& c, const smpc_problem_t* dP, const MlpTcWeights& w, int n_sm, int B, int N, int rows_mode, int n_flat,
+                   const double* xsrc, const int32_t* r, const uint8_t* act, const uint8_t* need, double* out11, bool want_grad);
 void launch_linearize(const LaunchCtx& c, const smpc_problem_t* dP, int B, int N, const double* xg, const double* ug,
                       const int32_t* r, const uint8_t* act, const double* nn11, double* lin);
 void launch_ctrl_post1(const LaunchCtx& c, const smpc_problem_t* dP, int B, int N, const uint8_t* act, const double* xg, const double* ug,

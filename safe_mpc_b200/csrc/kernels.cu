@@ -40,18 +40,6 @@ void launch_prep(const LaunchCtx& c, const smpc_problem_t* dP, int B, int N, dou
 constexpr int MLP_R = 16;
 constexpr int HID = SMPC_HID;
 
-__device__ __forceinline__ bool mlp_row(int rows_mode, int i, int B, int N, const int32_t* r, const uint8_t* act, const uint8_t* need,
-                                        int& b, int& k) {
-  if (rows_mode == ROWS_TERMINAL) { b = i; k = N; }
-  else if (rows_mode == ROWS_ALL) { b = i / N; k = 1 + i % N; }
-  else if (rows_mode == ROWS_RECEDING) { b = i >> 1; if (b >= B) return false; k = (i & 1) ? N : r[b]; if (k < 1 || (!(i & 1) && k >= N)) return false; }
-  else { b = i; k = 0; return true; }
-  if (b >= B) return false;
-  if (act && !act[b]) return false;
-  if (need && !need[b]) return false;
-  return true;
-}
-
 __global__ void __launch_bounds__(HID)
 mlp_kernel(const smpc_problem_t* __restrict__ dP, MlpWeights w, int B, int N, int rows_mode, int n_rows, const double* __restrict__ xsrc,
            const int32_t* __restrict__ r, const uint8_t* __restrict__ act, const uint8_t* __restrict__ need, double* out11, int want_grad) {

@@ -17,6 +17,8 @@ _LIB = None
 
 
 def library_path():
+    if os.environ.get('SMPC_LIB'):          # development: a variant build of the same library (scripts/build_variant.sh)
+        return os.environ['SMPC_LIB']
     return os.path.join(os.path.dirname(os.path.abspath(__file__)), 'csrc', 'libsafe_mpc_b200.so')
 
 

@@ -114,8 +114,12 @@ class ModelData:
         self.n_points = len(order)
 
 
-def build_problem(params, controller: str, cost: str = 'ext', N: int | None = None, model: ModelData | None = None):
-    """-> (abi.Problem, keepalive).  ``keepalive`` owns the weight buffer the struct points to."""
+def build_problem(params, controller: str, cost: str = 'ext', N: int | None = None, model: ModelData | None = None,
+                  nn_precision: str | None = None):
+    """-> (abi.Problem, keepalive).  ``keepalive`` owns the weight buffer the struct points to.
+
+    ``nn_precision``: 'strict' (fp32 weights, fp64 accumulation) or 'tf32x3' (fp32-class evaluation on the tensor cores,
+    the precision of the reference's libtorch call); default: ``params.nn_precision`` if set, else 'strict'."""
     if controller not in CONTROLLERS:
         raise ValueError(f'Controller {controller} not available')
     ctrl, nn_rows, soft = CONTROLLERS[controller]
@@ -149,6 +153,7 @@ def build_problem(params, controller: str, cost: str = 'ext', N: int | None = No
         p, nq=nq, N=N, n_pairs=abi.NPAIR, n_points=md.n_points, controller=ctrl, nn_rows=nn_rows,
         nn_terminal_soft=int(soft), stage0_collision_rows=int(not params.noise > 0), cost_type=COSTS[cost],
         abort_flag=int(params.abort_flag), qp_iter_max=int(params.qp_max_iter), lm_scale_dt=1, qp_cond_pred_corr=1,
+        nn_precision=abi.NN_PRECISION[nn_precision or getattr(params, 'nn_precision', None) or 'strict'],
         dt=params.dt, q_weight=params.Q_weight, r_weight=params.R_weight, lm=params.levenberg_marquardt,
         alpha=params.alpha, eps=params.eps, slack_penalty_e=penalty,
         tol_x=params.tol_x, tol_tau=params.tol_tau, tol_obs=params.tol_obs, tol_safe=params.tol_safe_set,

@@ -32,9 +32,12 @@ UNIT = 'RTI iterations/s'
 Q0 = np.array([-0.3, 0.8, -1.65, 0.658, 0.0])
 
 
+NN_PRECISION = 'strict'      # set from --nn-precision
+
+
 def workload(controller, N, noise, seed, lo, hi):
     """Synthetic inputs of problems [lo, hi): initial states around the shipped IC, perturbed plants, torque noise."""
-    args = default_args(controller=controller, horizon=N, noise=noise)
+    args = default_args(controller=controller, horizon=N, noise=noise, nn_precision=NN_PRECISION)
     params = Parameters(args, 'z1', rti=True)
     params.N = N
     md = ModelData(params)
@@ -230,6 +233,11 @@ def run_engine(a):
         e2e = {'steps': n_e2e, 'seconds': e2e_s, 'solves': n_e2e * B,
                'h2d': B * (abi.NX * 8 + abi.NU * 8) + B * (abi.NX + abi.NU) * 8, 'd2h': B * (abi.NU * 8 + 1) + B * (abi.NX + abi.NU) * 8}
 
+    # ---- the viability network kernels timed alone on the row count of configs[2] (a row per problem and stage) ----
+    mlp = None
+    if rank == 0 and not a.no_mlp:
+        mlp = time_mlp(params, md, B * N, local_rank, dev)
+
     # ---- aggregate over ranks ----
     vec = [ms, solves, ipm, l1 - l0, (e2e['seconds'] if e2e else 0.0), (e2e['solves'] if e2e else 0.0)]
     allv = D.all_gather_vector(vec, device=dev)
@@ -264,7 +272,7 @@ def run_engine(a):
                                f'synthetic Z1-like 5-DOF chain + random-init viability MLP 10-256-256-256-1',
                    'batch_per_gpu': B, 'global_batch': B * world, 'parallelism': f'dp{world} (problem sharding, no hot-path collective)',
                    'l2': f'working set {B * (main_qp_bytes(N)) / 1e9:.2f} GB per GPU > 126 MB L2 (no flush needed)',
-                   'noise_percent': a.noise, 'sqp_warm_start_iters': a.sqp_iters},
+                   'noise_percent': a.noise, 'sqp_warm_start_iters': a.sqp_iters, 'nn_precision': a.nn_precision},
         'p50_step_ms': float(np.percentile(lat, 50)), 'p99_step_ms': float(np.percentile(lat, 99)),
         'ipm_iterations_per_solve': ipm / max(1, solves),
         'gpu_launches': int(sum(v[3] for v in allv)),
@@ -281,6 +289,13 @@ def run_engine(a):
                      'kernel_ms_note': 'per-kernel sums of one solve timed with a single tile group (no overlap between kernels)'},
         'outcome': D.outcome_counts(outcome),
     }
+    if mlp:
+        tpeak = float(peaks.get('bf16_tflops', peaks.get('bf16_dense_tflops', 1590.0))) / 2
+        mlp['tensor_peak_tf32_tflops'] = tpeak
+        mlp['tensor_peak_source'] = ('half of the measured dense bf16 peak (MEASURED_PEAKS.json)' if any(k in peaks for k in ('bf16_tflops', 'bf16_dense_tflops'))
+                                     else 'half of the fallback dense bf16 peak 1.59 PFLOP/s (B200_PROFILING.md)')
+        mlp['tf32x3']['frac_of_tensor_peak'] = mlp['tf32x3']['executed_tf32_tflops'] / tpeak
+        line['viability_network'] = mlp
     if e2e:
         e2e_s = max(v[4] for v in allv)
         line['e2e'] = {'value': sum(v[5] for v in allv) / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': e2e['h2d'], 'd2h_bytes_per_step': e2e['d2h'],
@@ -290,6 +305,35 @@ def run_engine(a):
         line['cpu_baseline'] = {'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': 'port', 'sample': r['sample'],
                                 'ipm_iterations_per_solve': r['ipm_per_solve']}
     print(json.dumps(line), flush=True)
+
+
+def time_mlp(params, md, n_rows, device_index, dev):
+    """c(x) and dc/dx of n_rows states resident in HBM through smpc_nn_constraint: strict kernel vs tensor-core kernel."""
+    import torch
+    from safe_mpc_b200.engine import Engine
+    rng = np.random.default_rng(7)
+    mid, half = 0.5 * (md.x_min + md.x_max), 0.5 * (md.x_max - md.x_min)
+    x = mid + 0.8 * half * rng.uniform(-1, 1, (n_rows, abi.NX))
+    xd = torch.tensor(x, device=dev)
+    out = {'rows': n_rows, 'algorithmic_flop_per_row': 535040}
+    for name in ('strict', 'tf32x3'):
+        prob, keep = build_problem(params, 'st', cost='ext', model=md, nn_precision=name)
+        eng = Engine(prob, 64, device_index)
+        stream = torch.cuda.ExternalStream(eng.stream(), device=dev)
+        eng.nn_constraint(xd); eng.sync()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+        ev[0].record(stream)
+        for i in range(5):
+            eng.nn_constraint(xd)
+            ev[i + 1].record(stream)
+        eng.sync(); torch.cuda.synchronize()
+        ms = float(np.median([ev[i].elapsed_time(ev[i + 1]) for i in range(5)]))
+        out[name] = {'ms': ms, 'algorithmic_tflops': n_rows * 535040 / (ms * 1e-3) / 1e12}
+        if name == 'tf32x3':
+            # the four 256 x 256 contractions (491 520 of the 535 040 flop) run as three tf32 products each
+            out[name]['executed_tf32_tflops'] = n_rows * 3 * 4 * 2 * 256 * 256 / (ms * 1e-3) / 1e12
+        eng.close()
+    return out
 
 
 def main_times(main):
@@ -321,7 +365,12 @@ def main():
     ap.add_argument('--cpu-steps', type=int, default=8, dest='cpu_steps')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-mlp', action='store_true', dest='no_mlp')
+    ap.add_argument('--nn-precision', default='strict', choices=['strict', 'tf32x3'], dest='nn_precision',
+                    help='viability network arithmetic of the timed closed loop (the tensor-core kernel is always timed alone as well)')
     a = ap.parse_args()
+    global NN_PRECISION
+    NN_PRECISION = a.nn_precision
     if a.warmup < 3 and a.impl == 'engine':
         a.warmup = 3
     if a.impl == 'reference':

@@ -18,7 +18,8 @@
 //   Weights are pre-split (hi / lo) and pre-packed on the host into the exact shared-memory image of a K-stage, and streamed
 //   L2 -> shared memory with 1-D TMA bulk copies (cp.async.bulk + mbarrier) by a producer thread; one elected thread issues
 //   the MMAs; tcgen05.commit releases weight stages and signals the epilogue.
-// Warp roles: 0-3 epilogue / CUDA-core layers (TMEM lanes 32 w .. 32 w + 31), 4 weight producer, 5 MMA issuer.
+// Warp roles: 0-7 epilogue / CUDA-core layers (warp w: TMEM lanes 32 (w % 4) .. + 31, rows 32 (w / 4) .. + 31 of the tile; two warps per
+// scheduler because the epilogue is a long dependent instruction stream), 8 weight producer, 9 MMA issuer.
 #include <cstring>
 #include <vector>
 
@@ -38,7 +39,8 @@ constexpr int XBYTES = (HID / 4) * XPITCH;  // one of X_hi / X_lo
 constexpr int WROWB = 128 * 16;             // bytes of one k-chunk of one half of the weight operand: 128 units x 16 B
 constexpr int WHALF = (KC / 4) * WROWB;     // one (hi|lo, half) block of a stage
 constexpr int WSTAGE = 4 * WHALF;           // [hl][half][chunk][unit][4 floats] = 32 KB
-constexpr int TC_THREADS = 192;
+constexpr int NCW = 8;                       // epilogue / CUDA-core warps: warp w owns TMEM lanes 32 (w % 4) .., columns 32 (w / 4) ..
+constexpr int TC_THREADS = 32 * (NCW + 2);
 constexpr int D1COL = 128, D2COL = 256, TMEM_COLS = 512;
 
 constexpr int OFF_XH = 0;
@@ -47,15 +49,13 @@ constexpr int OFF_W = OFF_XL + XBYTES;
 constexpr int OFF_W1 = OFF_W + NSLOT * WSTAGE;          // float [256][10]
 constexpr int OFF_VEC = OFF_W1 + HID * NX * 4;          // float b1[256] b2[256] b3[256] W4[256]
 constexpr int OFF_INF = OFF_VEC + 4 * HID * 4;          // float [R][10]
-constexpr int OFF_IN64 = OFF_INF + R * NX * 4;          // double [R][10]
-constexpr int OFF_GIN = OFF_IN64 + R * NX * 8;          // float [R][10]
-constexpr int OFF_YP = OFF_GIN + R * NX * 4;            // float [4][R]
-constexpr int OFF_NRM = OFF_YP + 4 * R * 4;             // double [R]
-constexpr int OFF_META = OFF_NRM + R * 8;               // int rowb[R], rowk[R], valid[R], vote[4]
+constexpr int OFF_GIN = OFF_INF + R * NX * 4;           // float [4][R][10]  (partial sums over a quarter of the hidden units)
+constexpr int OFF_YP = OFF_GIN + 4 * R * NX * 4;        // float [4][R]
+constexpr int OFF_META = OFF_YP + 4 * R * 4;            // int rowb[R], rowk[R], valid[R], vote[4]
 constexpr int OFF_BAR = OFF_META + (3 * R + 4) * 4;     // uint64 full[NSLOT], empty[NSLOT], acc_full, x_ready
 constexpr int OFF_TMEM = OFF_BAR + (2 * NSLOT + 2) * 8;
 constexpr int TC_SMEM = OFF_TMEM + 16;
-static_assert(OFF_W % 128 == 0 && OFF_IN64 % 8 == 0 && OFF_NRM % 8 == 0 && OFF_BAR % 8 == 0, "alignment");
+static_assert(OFF_W % 128 == 0 && OFF_BAR % 8 == 0, "alignment");
 static_assert(TC_SMEM <= 232448, "shared memory budget");
 
 // instruction descriptor of tcgen05.mma.kind::tf32: D fp32, A/B tf32, both K-major, M = 128, N = R
@@ -107,7 +107,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                "r"(bytes), "r"(s32(bar))
                : "memory");
 }
-__device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, %0;" ::"n"(32 * NCW) : "memory"); }
 
 #define V32_OUT(v)                                                                                                              \
   "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),       \
@@ -159,7 +159,9 @@ __host__ __device__ __forceinline__ void split_tf32(float a, float& hi, float& l
 __device__ __forceinline__ float gelu_f32(float x, float& d) {        // GELU(tanh) and its derivative (safe_set.py:31-40)
   const float k0 = 0.7978845608028654f, k1 = 0.044715f;
   const float x2 = x * x;
-  const float t = tanhf(k0 * (x + k1 * x * x2));
+  // tanh(u) = 1 - 2 / (exp(2u) + 1) with the hardware exp2 / reciprocal: absolute error ~2e-7, no branches
+  const float e = __expf(2.0f * k0 * (x + k1 * x * x2));
+  const float t = 1.0f - __fdividef(2.0f, e + 1.0f);
   d = 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * k0 * (1.0f + 3.0f * k1 * x2);
   return 0.5f * x * (1.0f + t);
 }
@@ -192,11 +194,10 @@ enum { L_FWD2 = 0, L_FWD3 = 1, L_BWD3 = 2, L_BWD2 = 3 };
 
 // epilogue of one tensor-core layer for the thread that owns TMEM lane j (units j and 128 + j)
 template <int L>
-__device__ __forceinline__ void epilogue(unsigned char* sm, uint32_t tlane, int j, int warp, int lane, bool want_grad) {
+__device__ __forceinline__ void epilogue(unsigned char* sm, uint32_t tlane, int j, int c, int warp, int lane, bool want_grad) {
   const float* vec = reinterpret_cast<const float*>(sm + OFF_VEC);
   float* YP = reinterpret_cast<float*>(sm + OFF_YP);
-#pragma unroll 1
-  for (int c = 0; c < 2; ++c) {
+  {
     float yp[32];
     if (L == L_FWD3) {
 #pragma unroll
@@ -244,7 +245,7 @@ __device__ __forceinline__ void epilogue(unsigned char* sm, uint32_t tlane, int 
           yp[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
         }
       }
-      YP[warp * R + c * 32 + lane] = yp[0];
+      YP[(warp & 3) * R + c * 32 + lane] = yp[0];
     }
   }
   if (L == L_FWD2) tmem_st_wait();
@@ -273,7 +274,7 @@ mlp_tc_kernel(const smpc_problem_t* __restrict__ dP, MlpTcWeights w, int B, int 
   if (tid == 0) {
     for (int s = 0; s < NSLOT; ++s) { mbar_init(bar_full + s, 1); mbar_init(bar_empty + s, 1); }
     mbar_init(bar_acc, 1);
-    mbar_init(bar_x, 128);
+    mbar_init(bar_x, 32 * NCW);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -285,7 +286,7 @@ mlp_tc_kernel(const smpc_problem_t* __restrict__ dP, MlpTcWeights w, int B, int 
   fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp == NCW) {
     // =========================== weight producer ===========================
     uint32_t cnt = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -302,7 +303,7 @@ mlp_tc_kernel(const smpc_problem_t* __restrict__ dP, MlpTcWeights w, int B, int 
       }
       __syncwarp();
     }
-  } else if (warp == 5) {
+  } else if (warp == NCW + 1) {
     // =========================== MMA issuer ===========================
     uint32_t cnt = 0, xph = 0;
     const uint32_t xh = s32(sm + OFF_XH), xl = s32(sm + OFF_XL), wb = s32(sm + OFF_W);
@@ -339,15 +340,14 @@ mlp_tc_kernel(const smpc_problem_t* __restrict__ dP, MlpTcWeights w, int B, int 
       __syncwarp();
     }
   } else {
-    // =========================== CUDA-core layers + epilogues (128 threads) ===========================
+    // =========================== CUDA-core layers + epilogues (256 threads) ===========================
     const smpc_problem_t& P = *dP;
-    const int j = tid;                                      // TMEM lane = hidden unit (and unit 128 + j)
-    const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
+    const int j = tid & 127;                                // TMEM lane = hidden unit (and unit 128 + j)
+    const int cg = tid >> 7;                                // which 32 rows (TMEM columns) of the tile this thread handles
+    const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     float* INF = reinterpret_cast<float*>(sm + OFF_INF);
-    double* IN64 = reinterpret_cast<double*>(sm + OFF_IN64);
     float* GIN = reinterpret_cast<float*>(sm + OFF_GIN);
     float* YP = reinterpret_cast<float*>(sm + OFF_YP);
-    double* NRM = reinterpret_cast<double*>(sm + OFF_NRM);
     int* rowb = reinterpret_cast<int*>(sm + OFF_META);
     int* rowk = rowb + R;
     int* valid = rowk + R;
@@ -371,8 +371,7 @@ mlp_tc_kernel(const smpc_problem_t* __restrict__ dP, MlpTcWeights w, int B, int 
           for (int q = 0; q < NX; ++q) in[q] = 0.0;
         }
 #pragma unroll
-        for (int q = 0; q < NX; ++q) { IN64[tid * NX + q] = in[q]; INF[tid * NX + q] = (float)in[q]; }
-        NRM[tid] = nrm;
+        for (int q = 0; q < NX; ++q) INF[tid * NX + q] = (float)in[q];
         const unsigned m = __ballot_sync(0xffffffffu, v);
         if (lane == 0) vote[warp] = m != 0;
       }
@@ -388,8 +387,8 @@ mlp_tc_kernel(const smpc_problem_t* __restrict__ dP, MlpTcWeights w, int B, int 
 #pragma unroll
         for (int q = 0; q < NX; ++q) w1[q] = W1s[unit * NX + q];
         const float bias = vec[unit];
-#pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
+        {
+          const int c = cg;
           uint32_t dv[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
@@ -410,38 +409,40 @@ mlp_tc_kernel(const smpc_problem_t* __restrict__ dP, MlpTcWeights w, int B, int 
 
       // ---- tensor-core layers ----
       mbar_wait(bar_acc, aph); aph ^= 1; fence_after();
-      epilogue<L_FWD2>(sm, tlane, j, warp, lane, want_grad);
+      epilogue<L_FWD2>(sm, tlane, j, cg, warp, lane, want_grad);
       fence_async_smem(); fence_before(); mbar_arrive(bar_x);
 
       mbar_wait(bar_acc, aph); aph ^= 1; fence_after();
-      epilogue<L_FWD3>(sm, tlane, j, warp, lane, want_grad);
+      epilogue<L_FWD3>(sm, tlane, j, cg, warp, lane, want_grad);
       if (want_grad) {
         fence_async_smem(); fence_before(); mbar_arrive(bar_x);
         mbar_wait(bar_acc, aph); aph ^= 1; fence_after();
-        epilogue<L_BWD3>(sm, tlane, j, warp, lane, true);
+        epilogue<L_BWD3>(sm, tlane, j, cg, warp, lane, true);
         fence_async_smem(); fence_before(); mbar_arrive(bar_x);
         mbar_wait(bar_acc, aph); aph ^= 1; fence_after();
-        epilogue<L_BWD2>(sm, tlane, j, warp, lane, true);   // X = g1 (hi + lo)
+        epilogue<L_BWD2>(sm, tlane, j, cg, warp, lane, true);   // X = g1 (hi + lo)
       }
       fence_before();
       bar_compute();
 
       // ---- last reverse layer on the CUDA cores: gin[n][i] = sum_k W1[k][i] g1[k][n] ----
       if (want_grad) {
-        const int n = tid & (R - 1), half = tid >> 6;
-        float g[5] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+        const int n = tid & (R - 1), part = tid >> 6;       // part: quarter of the hidden units
+        float g[NX];
+#pragma unroll
+        for (int q = 0; q < NX; ++q) g[q] = 0.0f;
 #pragma unroll 4
-        for (int ch = 0; ch < HID / 4; ++ch) {
+        for (int ch = part * (HID / 16); ch < (part + 1) * (HID / 16); ++ch) {
           const float4 hi = *reinterpret_cast<const float4*>(sm + OFF_XH + ch * XPITCH + n * 16);
           const float4 lo = *reinterpret_cast<const float4*>(sm + OFF_XL + ch * XPITCH + n * 16);
           const float gv[4] = {hi.x + lo.x, hi.y + lo.y, hi.z + lo.z, hi.w + lo.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e)
 #pragma unroll
-            for (int q = 0; q < 5; ++q) g[q] = fmaf(W1s[(ch * 4 + e) * NX + half * 5 + q], gv[e], g[q]);
+            for (int q = 0; q < NX; ++q) g[q] = fmaf(W1s[(ch * 4 + e) * NX + q], gv[e], g[q]);
         }
 #pragma unroll
-        for (int q = 0; q < 5; ++q) GIN[n * NX + half * 5 + q] = g[q];
+        for (int q = 0; q < NX; ++q) GIN[(part * R + n) * NX + q] = g[q];
       }
       bar_compute();
       // ---- c(x), dc/dx in fp64 from the fp32 network output (safe_set.py:100-104) ----
@@ -449,8 +450,11 @@ mlp_tc_kernel(const smpc_problem_t* __restrict__ dP, MlpTcWeights w, int B, int 
         const double y = (double)w.b4[0] + ((double)YP[tid] + (double)YP[R + tid] + (double)YP[2 * R + tid] + (double)YP[3 * R + tid]);
         double gin[NX], grad[NX];
 #pragma unroll
-        for (int q = 0; q < NX; ++q) gin[q] = want_grad ? (double)GIN[tid * NX + q] : 0.0;
-        const double cval = nn_output(P, IN64 + tid * NX, NRM[tid], y, want_grad ? gin : nullptr, want_grad ? grad : nullptr);
+        for (int q = 0; q < NX; ++q)
+          gin[q] = want_grad ? (double)((GIN[tid * NX + q] + GIN[(R + tid) * NX + q]) + (GIN[(2 * R + tid) * NX + q] + GIN[(3 * R + tid) * NX + q])) : 0.0;
+        double in[NX], nrm;                                // psi(x) again in fp64 (cheaper than keeping it in shared memory)
+        nn_input(P, (rows_mode == ROWS_FLAT) ? xsrc + (size_t)rowb[tid] * NX : xsrc + ((size_t)rowb[tid] * (N + 1) + rowk[tid]) * NX, in, &nrm);
+        const double cval = nn_output(P, in, nrm, y, want_grad ? gin : nullptr, want_grad ? grad : nullptr);
         double* o = (rows_mode == ROWS_FLAT) ? out11 + (size_t)rowb[tid] * NN_OUT : out11 + ((size_t)rowb[tid] * (N + 1) + rowk[tid]) * NN_OUT;
         o[0] = cval;
         if (want_grad) {

@@ -32,6 +32,8 @@ constexpr int SP_WARPS = 4;      // warps per CTA of the stage-parallel kernels
 #define QS_SP_MINB 3             // resident CTAs per SM the register allocation of prep / step is sized for
 #endif
 
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
 __global__ void __launch_bounds__(32) qs_init_kernel(QsBufs q, int B, const double* __restrict__ x0, const int32_t* __restrict__ r,
                                                       const uint8_t* __restrict__ act) {
   qs_init(q, blockIdx.x, threadIdx.x, B, x0, r, act);
@@ -46,6 +48,360 @@ __global__ void __launch_bounds__(32 * PREP_WARPS, QS_PREP_MINB) qs_prep_kernel(
   const int w = blockIdx.x * PREP_WARPS + wi;
   if (w >= T * (q.N + 1)) return;
   qs_prep<FIRST>(*dP, q, w / (q.N + 1), threadIdx.x & 31, w % (q.N + 1), kk, jsm_all + (size_t)wi * PREP_SCRATCH * TL + (threadIdx.x & 31));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// prep, cooperative form (IPM iterations kk >= 1): one CTA of four warps per (tile, stage).
+// The whole input of the work item -- stage record, previous iterate, step: 107.5 KB -- is staged into shared memory by three
+// TMA bulk copies, so no warp ever waits on a global load in the middle of its instruction stream (the thread-per-stage form
+// above spends 14 of 23 cycles per instruction there, profiles/r01_qp_v6_launches.md); the instruction stream of qs_prep is
+// split over the four warps (lane = problem in all of them):
+//   rows    warp 0: iterate update, stationarity base, dynamics residual, box rows 0-3     warp 1: box rows 4-9
+//           warp 2: torque rows                                                           warp 3: capsule rows + viability row
+//           every row leaves (nu = lam_u - lam_l, gam = c_l - c_u, G = G_l + G_u) in the shared-memory slots of its own,
+//           already consumed, multipliers; every warp leaves its residual-norm partials the same way
+//   merge   warp 0: C' nu, C' gam -> stationarity residual and affine gradient, norms     warps 1-3: rows of H + C' G C
+// Same arithmetic per term as qs_prep<false>; only the order of the sums over the row groups differs.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int PC_REC0 = SMPC_REC_X;                       // first staged record field (the controls of the guess are not needed)
+constexpr int PC_NREC = 180;                              // staged record fields [5, 185)
+constexpr int PC_WARPS = 4;
+constexpr size_t PC_SMEM = sizeof(double) * (PC_NREC + 2 * NIT) * TL + 16;
+static_assert(PC_REC0 + PC_NREC > SMPC_REC_HQ && PC_REC0 + PC_NREC <= SMPC_REC, "staged record range");
+
+__device__ __forceinline__ void pc_row_out(double* s_it, int sl, double nu, double gam, double G) {
+  QF(s_it, I_LAM + sl) = nu; QF(s_it, I_LAM + QNR + sl) = gam; QF(s_it, I_T + sl) = G;
+}
+
+__global__ void __launch_bounds__(32 * PC_WARPS, 2) qs_prep_coop_kernel(const smpc_problem_t* __restrict__ dP, QsBufs q, int T, int kk) {
+  extern __shared__ __align__(128) double pc_sm[];
+  const smpc_problem_t& P = *dP;
+  const int N = q.N;
+  const int tile = blockIdx.x / (N + 1), k = blockIdx.x % (N + 1);
+  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+  const int32_t* pi = q.pi + qs_pb(tile, NPI, lane);
+  const bool on = QF(pi, J_ACT) != 0;
+  if (!__any_sync(0xffffffffu, on)) return;               // (same decision in the four warps: same tile)
+  double* g_rec_blk = const_cast<double*>(q.rec) + qs_blk(tile, N, k, REC, 0);
+  const double* g_it_blk = q.it[(kk & 1) ^ 1] + qs_blk(tile, N, k, NIT, 0);
+  const double* g_st_blk = q.st + qs_blk(tile, N, k, NIT, 0);
+  double* sm_rec = pc_sm;
+  double* sm_it = sm_rec + (size_t)PC_NREC * TL;
+  double* sm_st = sm_it + (size_t)NIT * TL;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sm_st + (size_t)NIT * TL);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const uint32_t nb_rec = PC_NREC * TL * 8, nb_it = NIT * TL * 8;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(nb_rec + 2 * nb_it) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sm_rec)),
+                 "l"(g_rec_blk + (size_t)PC_REC0 * TL), "r"(nb_rec), "r"(smem_u32(bar)) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sm_it)),
+                 "l"(g_it_blk), "r"(nb_it), "r"(smem_u32(bar)) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sm_st)),
+                 "l"(g_st_blk), "r"(nb_it), "r"(smem_u32(bar)) : "memory");
+  }
+  // lane views: field f of the record at rs[f * TL] (valid for PC_REC0 <= f < PC_REC0 + PC_NREC)
+  const double* rs = sm_rec - (size_t)PC_REC0 * TL + lane;
+  double* s_it = sm_it + lane;
+  double* s_st = sm_st + lane;
+  const double* pd = q.pd + qs_pb(tile, NPD, lane);
+  const double a = QF(pd, D_STEP);
+  const int rrec = QF(pi, J_R);
+  double* ito = q.it[kk & 1] + qs_blk(tile, N, k, NIT, lane);
+  double* hc = q.sb + qs_blk(tile, N, k, NHC, lane);
+  const StageFlags F = qs_flags(P, k);
+  const double lam_min = 1e-16, t_min = 1e-16, reg = P.qp_reg_prim;
+  const double dt = P.dt, a2 = 0.5 * P.dt * P.dt;
+
+  // neighbour data of warp 0 (global; issued before the wait so that the round trip overlaps the staging)
+  double pqn[10], znx[10];
+  if (wi == 0) {
+#pragma unroll
+    for (int j = 0; j < 10; ++j) { pqn[j] = 0.0; znx[j] = 0.0; }
+    if (k < N) {
+      const double* itn = q.it[(kk & 1) ^ 1] + qs_blk(tile, N, k + 1, NIT, lane);
+      const double* stn = q.st + qs_blk(tile, N, k + 1, NIT, lane);
+#pragma unroll
+      for (int j = 0; j < 10; ++j) {
+        pqn[j] = QF(itn, I_PIM + j) + a * QF(stn, I_PIM + j);
+        znx[j] = QF(itn, I_Z + 5 + j) + a * QF(stn, I_Z + 5 + j);
+      }
+    }
+  }
+  __syncthreads();                                         // barrier initialised before anyone polls it
+  {
+    uint32_t ok;
+    do {
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(smem_u32(bar)), "r"(0) : "memory");
+    } while (!ok);
+  }
+
+  // ---- iterate of this stage (every warp) ----
+  double z[15];
+#pragma unroll
+  for (int i = 0; i < 15; ++i) z[i] = QF(s_it, I_Z + i) + a * QF(s_st, I_Z + i);
+  if (k == N) {
+#pragma unroll
+    for (int i = 0; i < 5; ++i) z[i] = 0.0;
+  }
+  // box of dx_j (qs_box with the record of this stage in shared memory)
+  auto box = [&](int j, double& lo, double& hi) {
+    const double xk = QF(rs, SMPC_REC_X + j);
+    if (k == 0) { lo = QF(pd, D_X0 + j) - xk; hi = lo; }
+    else if (k == N) { lo = P.lbx_e[j] - xk; hi = P.ubx_e[j] - xk; }
+    else if (P.controller == SMPC_CTRL_REAL_RECEDING) {
+      if (k == rrec) { const double c = QF(q.rec + qs_blk(tile, N, k + 1, REC, lane), SMPC_REC_X + j); lo = c - 1e-3 - xk; hi = c + 1e-3 - xk; }
+      else { lo = P.x_min[j] - xk; hi = P.x_max[j] - xk; }
+    } else { lo = P.lbx[j] - xk; hi = P.ubx[j] - xk; }
+  };
+  QsNorms nr;
+  nr.ng = nr.nb = nr.nd = nr.nm = nr.mu = nr.chk = 0.0; nr.cnt = 0;
+  auto upd = [&](int slot, double& lam, double& t) {
+    lam = fmax(QF(s_it, I_LAM + slot) + a * QF(s_st, I_LAM + slot), lam_min);
+    t = fmax(QF(s_it, I_T + slot) + a * QF(s_st, I_T + slot), t_min);
+  };
+  auto side = [&](int slot, double sgn, double az, double bnd, double slack, double lam, double t, double& G, double& c) {
+    if (on) { QF(ito, I_LAM + slot) = lam; QF(ito, I_T + slot) = t; }
+    const double r = t - (sgn * (az - bnd) + slack);
+    const double rm = lam * t;
+    const double it_ = qs_rcp(t);
+    G = lam * it_;
+    c = (rm - lam * r) * it_;
+    nr.mu += rm; nr.chk += rm + r; nr.nm = fmax(nr.nm, fabs(rm)); nr.nd = fmax(nr.nd, fabs(r)); nr.cnt += 1;
+  };
+  // a hard two-sided row: update, residuals, (nu, gam, G) into the row's own shared-memory slots
+  auto hard_row = [&](int sl, double az, double lo, double hi) {
+    double ll, tl, lu, tu, Gl, Gu, cl, cu;
+    upd(sl, ll, tl); upd(QNR + sl, lu, tu);
+    side(sl, 1.0, az, lo, 0.0, ll, tl, Gl, cl);
+    side(QNR + sl, -1.0, az, hi, 0.0, lu, tu, Gu, cu);
+    pc_row_out(s_it, sl, lu - ll, cl - cu, Gl + Gu);
+  };
+
+  double rg[15];                                           // warp 0: stationarity residual without the inequality multipliers
+  if (wi == 0) {
+    const double hu = QF(rs, SMPC_REC_HU), hq = QF(rs, SMPC_REC_HQ), hv = QF(rs, SMPC_REC_HV);
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      rg[i] = (k == N) ? 0.0 : hu * z[i] + QF(rs, SMPC_REC_G + i);
+      double s = QF(rs, SMPC_REC_G + 5 + i) + hq * z[5 + i];
+#pragma unroll
+      for (int j = 0; j < 5; ++j) s += QF(rs, SMPC_REC_HQQ + trs(i, j)) * z[5 + j];
+      rg[5 + i] = s;
+      rg[10 + i] = QF(rs, SMPC_REC_G + 10 + i) + hv * z[10 + i];
+    }
+    double pimv[10];
+#pragma unroll
+    for (int j = 0; j < 10; ++j) {
+      pimv[j] = (k == 0) ? 0.0 : QF(s_it, I_PIM + j) + a * QF(s_st, I_PIM + j);
+      rg[5 + j] -= pimv[j];
+    }
+    if (k < N) {
+      double rb[10];
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        rb[j] = z[5 + j] + dt * z[10 + j] + a2 * z[j] + QF(rs, SMPC_REC_B + j);
+        rb[5 + j] = z[10 + j] + dt * z[j] + QF(rs, SMPC_REC_B + 5 + j);
+        const double pq = pqn[j], pv = pqn[5 + j];
+        rg[j] += a2 * pq + dt * pv;
+        rg[5 + j] += pq;
+        rg[10 + j] += dt * pq + pv;
+        rb[j] -= znx[j];
+        rb[5 + j] -= znx[5 + j];
+      }
+#pragma unroll
+      for (int j = 0; j < 10; ++j) { if (on) QF(hc, H_RB + j) = rb[j]; nr.nb = fmax(nr.nb, fabs(rb[j])); nr.chk += rb[j]; }
+    }
+    if (on) {
+#pragma unroll
+      for (int i = 0; i < 15; ++i) QF(ito, I_Z + i) = z[i];
+#pragma unroll
+      for (int j = 0; j < 10; ++j) QF(ito, I_PIM + j) = pimv[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { double lo, hi; box(j, lo, hi); hard_row(j, z[5 + j], lo, hi); }
+  } else if (wi == 1) {
+#pragma unroll
+    for (int j = 4; j < 10; ++j) { double lo, hi; box(j, lo, hi); hard_row(j, z[5 + j], lo, hi); }
+  } else if (wi == 2) {
+    if (F.tau) {
+#pragma unroll
+      for (int r = 0; r < 5; ++r) {
+        double az = 0.0;
+#pragma unroll
+        for (int c = 0; c < 15; ++c) az += QF(rs, SMPC_REC_JTAU + r * 15 + c) * z[c];
+        const double v = QF(rs, SMPC_REC_TAU + r);
+        hard_row(10 + r, az, P.tau_min[r] - v, P.tau_max[r] - v);
+      }
+    }
+  } else {
+    if (F.dist) {
+#pragma unroll
+      for (int p = 0; p < 6; ++p) {
+        double az = 0.0;
+#pragma unroll
+        for (int c = 0; c < 5; ++c) az += QF(rs, SMPC_REC_JDIST + p * 5 + c) * z[5 + c];
+        const double v = QF(rs, SMPC_REC_DIST + p);
+        hard_row(15 + p, az, P.pair_lo_ocp[p] - v, P.pair_hi - v);
+      }
+    }
+    if (F.nn) {
+      double az = 0.0;
+#pragma unroll
+      for (int c = 0; c < 10; ++c) az += QF(rs, SMPC_REC_JNN + c) * z[5 + c];
+      const double v = QF(rs, SMPC_REC_NN);
+      double sl[2] = {0.0, 0.0}, ls[2] = {0.0, 0.0}, ts[2] = {0.0, 0.0};
+      if (F.soft) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          sl[h] = QF(s_it, I_SLK + h) + a * QF(s_st, I_SLK + h);
+          ls[h] = fmax(QF(s_it, I_SLK + 2 + h) + a * QF(s_st, I_SLK + 2 + h), lam_min);
+          ts[h] = fmax(QF(s_it, I_SLK + 4 + h) + a * QF(s_st, I_SLK + 4 + h), t_min);
+        }
+      }
+      if (on) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) { QF(ito, I_SLK + h) = sl[h]; QF(ito, I_SLK + 2 + h) = ls[h]; QF(ito, I_SLK + 4 + h) = ts[h]; }
+      }
+      double ll, tl, lu, tu, Gl, Gu, cl, cu;
+      upd(21, ll, tl); upd(QNR + 21, lu, tu);
+      side(21, 1.0, az, 0.0 - v, sl[0], ll, tl, Gl, cl);
+      side(QNR + 21, -1.0, az, 1e6 - v, sl[1], lu, tu, Gu, cu);
+      if (F.soft) {
+        const double lam2[2] = {ll, lu};
+        double G2[2] = {Gl, Gu}, c2[2] = {cl, cu};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const double rsl = ts[h] - sl[h];
+          const double rgs = F.zpen - lam2[h] - ls[h];
+          const double rms = ls[h] * ts[h];
+          const double its = qs_rcp(ts[h]);
+          const double Gs = ls[h] * its;
+          const double cs = (rms - ls[h] * rsl) * its;
+          const double Wl = qs_rcp(G2[h] + Gs);
+          c2[h] = c2[h] - G2[h] * Wl * (rgs + c2[h] + cs);
+          G2[h] = G2[h] * Gs * Wl;
+          nr.mu += rms; nr.chk += rms + rsl + rgs;
+          nr.nm = fmax(nr.nm, fabs(rms)); nr.nd = fmax(nr.nd, fabs(rsl)); nr.ng = fmax(nr.ng, fabs(rgs));
+          nr.cnt += 1;
+        }
+        Gl = G2[0]; Gu = G2[1]; cl = c2[0]; cu = c2[1];
+      }
+      pc_row_out(s_it, 21, lu - ll, cl - cu, Gl + Gu);
+    }
+  }
+  // residual-norm partials of this warp -> consumed step slots of its first rows (warp 0: box 0, 1; 1: box 4, 5; 2: torque 0, 1; 3: capsule 0, 1)
+  {
+    const int s0 = wi == 0 ? 0 : (wi == 1 ? 4 : (wi == 2 ? 10 : 15));
+    QF(s_st, I_LAM + s0) = nr.mu; QF(s_st, I_LAM + QNR + s0) = nr.chk; QF(s_st, I_T + s0) = nr.nm; QF(s_st, I_T + QNR + s0) = nr.nd;
+    QF(s_st, I_LAM + s0 + 1) = nr.ng; QF(s_st, I_LAM + QNR + s0 + 1) = (double)nr.cnt;
+  }
+  __syncthreads();
+
+  if (wi == 0) {
+    // ---- merge: rg += C' nu, gd = C' gam; norms; affine gradient ----
+    double gd[15];
+#pragma unroll
+    for (int i = 0; i < 15; ++i) gd[i] = 0.0;
+#pragma unroll
+    for (int j = 0; j < 10; ++j) { rg[5 + j] += QF(s_it, I_LAM + j); gd[5 + j] += QF(s_it, I_LAM + QNR + j); }
+    if (F.tau) {
+#pragma unroll
+      for (int r = 0; r < 5; ++r) {
+        const double nu = QF(s_it, I_LAM + 10 + r), gam = QF(s_it, I_LAM + QNR + 10 + r);
+#pragma unroll
+        for (int c = 0; c < 15; ++c) { const double jv = QF(rs, SMPC_REC_JTAU + r * 15 + c); rg[c] += jv * nu; gd[c] += jv * gam; }
+      }
+    }
+    if (F.dist) {
+#pragma unroll
+      for (int p = 0; p < 6; ++p) {
+        const double nu = QF(s_it, I_LAM + 15 + p), gam = QF(s_it, I_LAM + QNR + 15 + p);
+#pragma unroll
+        for (int c = 0; c < 5; ++c) { const double jv = QF(rs, SMPC_REC_JDIST + p * 5 + c); rg[5 + c] += jv * nu; gd[5 + c] += jv * gam; }
+      }
+    }
+    if (F.nn) {
+      const double nu = QF(s_it, I_LAM + 21), gam = QF(s_it, I_LAM + QNR + 21);
+#pragma unroll
+      for (int c = 0; c < 10; ++c) { const double jv = QF(rs, SMPC_REC_JNN + c); rg[5 + c] += jv * nu; gd[5 + c] += jv * gam; }
+    }
+    if (k == N) {
+#pragma unroll
+      for (int i = 0; i < 5; ++i) { rg[i] = 0.0; gd[i] = 0.0; }
+    }
+    double ng = 0.0, nb = nr.nb, nd = 0.0, nm = 0.0, mu = 0.0, chk = 0.0, cnt = 0.0;
+#pragma unroll
+    for (int w = 0; w < PC_WARPS; ++w) {
+      const int s0 = w == 0 ? 0 : (w == 1 ? 4 : (w == 2 ? 10 : 15));
+      mu += QF(s_st, I_LAM + s0); chk += QF(s_st, I_LAM + QNR + s0);
+      nm = fmax(nm, QF(s_st, I_T + s0)); nd = fmax(nd, QF(s_st, I_T + QNR + s0));
+      ng = fmax(ng, QF(s_st, I_LAM + s0 + 1)); cnt += QF(s_st, I_LAM + QNR + s0 + 1);
+    }
+#pragma unroll
+    for (int i = 0; i < 15; ++i) { ng = fmax(ng, fabs(rg[i])); chk += rg[i]; if (on) QF(hc, H_GA + i) = rg[i] + gd[i]; }
+    if (on) {
+      double* res = q.res + qs_blk(tile, N, k, NRES, lane);
+      QF(res, R_NG) = ng; QF(res, R_NB) = nb; QF(res, R_ND) = nd; QF(res, R_NM) = nm;
+      QF(res, R_MU) = mu; QF(res, R_CHK) = chk; QF(res, R_CNT) = cnt;
+    }
+  } else {
+    // ---- merge: rows of the condensed stage matrix H + reg + C' Gam C (warp 1: rows 0-8, 2: 9-11, 3: 12-14) ----
+    const double hu = (k == N) ? 1.0 : QF(rs, SMPC_REC_HU) + reg;
+    const double hq = QF(rs, SMPC_REC_HQ) + reg, hv = QF(rs, SMPC_REC_HV) + reg;
+    double Gg[12];
+#pragma unroll
+    for (int r = 0; r < 12; ++r) {
+      const bool pres = r < 5 ? F.tau : (r < 11 ? F.dist : F.nn);
+      Gg[r] = pres ? QF(s_it, I_T + 10 + r) : 0.0;
+    }
+    auto mrow = [&](int i) {
+      double acc[15];
+#pragma unroll
+      for (int c = 0; c <= i; ++c) {
+        double v = 0.0;
+        if (c == i) v = i < 5 ? hu : ((i < 10 ? hq : hv) + QF(s_it, I_T + (i >= 5 ? i - 5 : 0)));
+        if (i >= 5 && i < 10 && c >= 5) v += QF(rs, SMPC_REC_HQQ + tri(i - 5, c - 5));
+        acc[c] = v;
+      }
+      if (F.tau) {
+#pragma unroll
+        for (int r = 0; r < 5; ++r) {
+          const double w = Gg[r] * QF(rs, SMPC_REC_JTAU + r * 15 + i);
+#pragma unroll
+          for (int c = 0; c <= i; ++c) acc[c] += w * QF(rs, SMPC_REC_JTAU + r * 15 + c);
+        }
+      }
+      if (F.dist && i >= 5 && i < 10) {
+#pragma unroll
+        for (int p = 0; p < 6; ++p) {
+          const double w = Gg[5 + p] * QF(rs, SMPC_REC_JDIST + p * 5 + i - 5);
+#pragma unroll
+          for (int c = 5; c <= i; ++c) acc[c] += w * QF(rs, SMPC_REC_JDIST + p * 5 + c - 5);
+        }
+      }
+      if (F.nn && i >= 5) {
+        const double w = Gg[11] * QF(rs, SMPC_REC_JNN + i - 5);
+#pragma unroll
+        for (int c = 5; c <= i; ++c) acc[c] += w * QF(rs, SMPC_REC_JNN + c - 5);
+      }
+      if (on) {
+#pragma unroll
+        for (int c = 0; c <= i; ++c) QF(hc, H_M + tri(i, c)) = acc[c];
+      }
+    };
+    if (wi == 1) {
+#pragma unroll
+      for (int i = 0; i < 9; ++i) mrow(i);
+    } else if (wi == 2) {
+#pragma unroll
+      for (int i = 9; i < 12; ++i) mrow(i);
+    } else {
+#pragma unroll
+      for (int i = 12; i < 15; ++i) mrow(i);
+    }
+  }
 }
 
 template <int MODE>
@@ -70,7 +426,6 @@ __global__ void __launch_bounds__(32 * SP_WARPS) qs_final_kernel(QsBufs q, int T
   if (qs_final(q, tile, lane, w % (q.N + 1), act, B, status, xt, ut)) atomicExch(&status[tile * TL + lane], 1);
 }
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // Device warp policy of the Riccati sweeps: two staging buffers of `nfb` fields x 32 lanes in shared memory, filled by
 // TMA 1-D bulk copies (cp.async.bulk global -> shared, mbarrier completion) that lane 0 issues one stage ahead.
@@ -222,6 +577,7 @@ struct QpSolver {
   int* h_counters = nullptr;
   cudaEvent_t ev_in = nullptr;  // inputs (records, x0) are ready on the caller's stream
   int last_iters = 0;
+  bool coop_prep = true;        // kk >= 1: four-warp cooperative prep with TMA-staged inputs (SMPC_QP_PREP=thread selects the thread-per-stage form)
   bool profile = false;         // record one event pair per kernel of the next solves (smpc_set_profiling)
   double prof_ms[SMPC_PROF_N] = {0};
   int32_t prof_n[SMPC_PROF_N] = {0};
@@ -254,6 +610,8 @@ QpSolver* qp_create(int B, int N, int iter_max, cudaStream_t stream, cudaError_t
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_in, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(qs_prep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PREP_SMEM);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(qs_prep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PREP_SMEM);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(qs_prep_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PC_SMEM);
+  if (const char* pe = getenv("SMPC_QP_PREP")) s->coop_prep = strcmp(pe, "thread") != 0;
   if (e == cudaSuccess) e = cudaFuncSetAttribute(qs_ric1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RIC1_SMEM);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(qs_ric2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RIC2_SMEM);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(qs_ric2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RIC2_SMEM);
@@ -344,6 +702,7 @@ struct DeviceBackend {
   const double* x0; const int32_t* r; const uint8_t* act;
   double *xt, *ut; int32_t *status, *qp_iter, *qp_status; double* qp_res;
   int kk_last = 0;
+  int n_active_last = 1 << 30;  // problems still iterating after the last control kernel the host has seen
   cudaError_t err = cudaSuccess;
   bool on_hi = false;
   // stream for the next kernel; a change of stream is ordered after everything queued on the other one
@@ -378,6 +737,9 @@ struct DeviceBackend {
       const int grid = (g->T * (s->N + 1) + PREP_WARPS - 1) / PREP_WARPS;
       tr0("qs_prep_kernel", stm_);
       if (kk == 0) qs_prep_kernel<true><<<grid, 32 * PREP_WARPS, PREP_SMEM, stm_>>>(dP, g->q, g->T, kk);
+      // the cooperative form stages whole (tile, stage) blocks, the thread-per-stage form only touches the lanes that still iterate:
+      // measured break-even at about half of the problems active (full launch 0.57 ms against 1.02 ms)
+      else if (s->coop_prep && 2 * n_active_last >= 32 * g->T) qs_prep_coop_kernel<<<g->T * (s->N + 1), 32 * PC_WARPS, PC_SMEM, stm_>>>(dP, g->q, g->T, kk);
       else qs_prep_kernel<false><<<grid, 32 * PREP_WARPS, PREP_SMEM, stm_>>>(dP, g->q, g->T, kk);
       tr1(stm_);
     }
@@ -411,6 +773,7 @@ struct DeviceBackend {
     cudaError_t e = err == cudaSuccess ? cudaEventSynchronize(g->ev) : err;
     if (e != cudaSuccess) { err = e; na = 0; nr = 0; return; }     // stop iterating; the caller reports the error
     na = g->h_counters[0]; nr = g->h_counters[1];
+    n_active_last = na;
     if (trace_print()) fprintf(stderr, "QPCOUNT g=%d kk=%d active=%d redo=%d\n", gi(), kk_last, na, nr);
   }
 };

@@ -345,7 +345,7 @@ def guess_copy(main):
 
 
 def main_qp_bytes(N):
-    return (N + 1) * (abi.REC + 3 * 120 + 330 + 46 + 8 + 4) * 8     # per problem: records, iterate x2, step, solver block, products, partials (qp_split.cuh)
+    return (N + 1) * (abi.REC + 3 * 120 + 25 + 345 + 46 + 8 + 4) * 8     # per problem: records, iterate x2, step, solver block, products, partials (qp_split.cuh)
 
 
 def main():

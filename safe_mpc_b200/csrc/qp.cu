@@ -489,14 +489,13 @@ __global__ void __launch_bounds__(32) qs_ric1_kernel(const smpc_problem_t* __res
   qs_ric1(*dP, q, blockIdx.x, w, psm + threadIdx.x);
 }
 
-template <int MODE>
 __global__ void __launch_bounds__(32) qs_ric2_kernel(const smpc_problem_t* __restrict__ dP, QsBufs q) {
   extern __shared__ __align__(128) double smem[];
   TmaStage w;
   w.sm = smem; w.nfb = RIC2_STAGE_FIELDS; w.ln = threadIdx.x;
   w.bar = reinterpret_cast<uint64_t*>(smem + (size_t)QS_RIC_NBUF * RIC2_STAGE_FIELDS * TL);
   w.init();
-  qs_ric2(*dP, q, blockIdx.x, w, MODE);
+  qs_ric2(*dP, q, blockIdx.x, w);
 }
 
 __global__ void __launch_bounds__(32) qs_red_kernel(const smpc_problem_t* __restrict__ dP, QsBufs q, int kk, int after_redo, int* counters) {
@@ -586,7 +585,7 @@ struct QpSolver {
 
 size_t qp_bytes(int B, int N) {
   const size_t T = (B + TL - 1) / TL, S = T * (N + 1) * TL;
-  return sizeof(double) * (S * (REC + 3 * NIT + NSB + NPROD + NRES + NSTP) + T * NPD * TL);
+  return sizeof(double) * (S * (REC + 3 * NIT + NS2 + NSB + NPROD + NRES + NSTP) + T * NPD * TL);
 }
 
 QpSolver* qp_create(int B, int N, int iter_max, cudaStream_t stream, cudaError_t* err) {
@@ -613,8 +612,7 @@ QpSolver* qp_create(int B, int N, int iter_max, cudaStream_t stream, cudaError_t
   if (e == cudaSuccess) e = cudaFuncSetAttribute(qs_prep_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PC_SMEM);
   if (const char* pe = getenv("SMPC_QP_PREP")) s->coop_prep = strcmp(pe, "thread") != 0;
   if (e == cudaSuccess) e = cudaFuncSetAttribute(qs_ric1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RIC1_SMEM);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(qs_ric2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RIC2_SMEM);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(qs_ric2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RIC2_SMEM);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(qs_ric2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RIC2_SMEM);
   for (int g = 0; g < G && e == cudaSuccess; ++g) {
     int plo = 0, phi = 0;
     cudaDeviceGetStreamPriorityRange(&plo, &phi);
@@ -630,6 +628,7 @@ QpSolver* qp_create(int B, int N, int iter_max, cudaStream_t stream, cudaError_t
   s->q.it[0] = p; p += S * NIT;
   s->q.it[1] = p; p += S * NIT;
   s->q.st = p; p += S * NIT;
+  s->q.st2 = p; p += S * NS2;
   s->q.sb = p; p += S * NSB;
   s->q.prod = p; p += S * NPROD;
   s->q.res = p; p += S * NRES;
@@ -644,7 +643,7 @@ QpSolver* qp_create(int B, int N, int iter_max, cudaStream_t stream, cudaError_t
     const size_t so = (size_t)t0 * (N + 1) * TL;
     gr.T = t1 - t0;
     gr.q = s->q;
-    gr.q.rec = s->q.rec + so * REC; gr.q.it[0] = s->q.it[0] + so * NIT; gr.q.it[1] = s->q.it[1] + so * NIT; gr.q.st = s->q.st + so * NIT;
+    gr.q.rec = s->q.rec + so * REC; gr.q.it[0] = s->q.it[0] + so * NIT; gr.q.it[1] = s->q.it[1] + so * NIT; gr.q.st = s->q.st + so * NIT; gr.q.st2 = s->q.st2 + so * NS2;
     gr.q.sb = s->q.sb + so * NSB; gr.q.prod = s->q.prod + so * NPROD; gr.q.res = s->q.res + so * NRES; gr.q.stp = s->q.stp + so * NSTP;
     gr.q.pd = s->q.pd + (size_t)t0 * NPD * TL; gr.q.pi = s->q.pi + (size_t)t0 * NPI * TL; gr.q.tile0 = t0;
     gr.counters = s->counters + ncnt * g;
@@ -687,8 +686,8 @@ static bool g_profile = false;
 static bool trace_print() { static int v = -1; if (v < 0) v = getenv("SMPC_QP_TRACE") ? 1 : 0; return v == 1; }
 static bool trace_on() { return g_profile || trace_print(); }
 static int prof_slot(const char* n) {
-  static const char* names[SMPC_PROF_N] = {"qs_init_kernel", "qs_prep_kernel", "qs_ctl_kernel", "qs_ric1_kernel", "qs_step_kernel<0>", "qs_ric2_kernel<1>",
-                                           "qs_step_kernel<1>", "qs_red_kernel", "qs_ric2_kernel<2>", "qs_step_kernel<2>", "qs_final_kernel"};
+  static const char* names[SMPC_PROF_N] = {"qs_init_kernel", "qs_prep_kernel", "qs_ctl_kernel", "qs_ric1_kernel", "qs_step_kernel<0>", "qs_ric2_kernel",
+                                           "qs_step_kernel<1>", "qs_red_kernel", nullptr /* (the separate centering sweep is gone) */, "qs_step_kernel<2>", "qs_final_kernel"};
   for (int i = 0; i < SMPC_PROF_N; ++i) if (names[i] && !strcmp(names[i], n)) return i;
   return 0;
 }
@@ -751,11 +750,7 @@ struct DeviceBackend {
     count();
   }
   void ric1() { { cudaStream_t stm_ = st(true); tr0("qs_ric1_kernel", stm_); qs_ric1_kernel<<<g->T, 32, RIC1_SMEM, stm_>>>(dP, g->q); tr1(stm_); } count(); }
-  void ric2(int mode) {
-    if (mode == 1) { cudaStream_t stm_ = st(true); tr0("qs_ric2_kernel<1>", stm_); qs_ric2_kernel<1><<<g->T, 32, RIC2_SMEM, stm_>>>(dP, g->q); tr1(stm_); }
-    else { cudaStream_t stm_ = st(true); tr0("qs_ric2_kernel<2>", stm_); qs_ric2_kernel<2><<<g->T, 32, RIC2_SMEM, stm_>>>(dP, g->q); tr1(stm_); }
-    count();
-  }
+  void ric2() { { cudaStream_t stm_ = st(true); tr0("qs_ric2_kernel", stm_); qs_ric2_kernel<<<g->T, 32, RIC2_SMEM, stm_>>>(dP, g->q); tr1(stm_); } count(); }
   void step(int kk, int mode) {
     if (mode == 0) { cudaStream_t stm_ = st(false); tr0("qs_step_kernel<0>", stm_); qs_step_kernel<0><<<sp_grid(), 32 * SP_WARPS, 0, stm_>>>(dP, g->q, g->T, kk); tr1(stm_); }
     else if (mode == 1) { cudaStream_t stm_ = st(false); tr0("qs_step_kernel<1>", stm_); qs_step_kernel<1><<<sp_grid(), 32 * SP_WARPS, 0, stm_>>>(dP, g->q, g->T, kk); tr1(stm_); }

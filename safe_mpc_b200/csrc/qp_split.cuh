@@ -12,10 +12,11 @@
 //   ctl    (thread per problem)           reduce residual norms, convergence / failure logic, write result when done
 //   ric1   (thread per problem)           backward factorisation + forward substitution of the affine direction
 //   step0  (thread per (problem, stage))  affine (dlam, dt), step-length partials, dlam*dt products, corrector terms
-//   ric2   (thread per problem)           sigma; vector-only backward + forward sweep of the corrector direction
+//   ric2   (thread per problem)           sigma; vector-only backward + forward sweep of the corrector direction and, in the
+//                                         same pass, of the pure-centering direction
 //   step1  (thread per (problem, stage))  corrector (dlam, dt, dslack), step-length partials
 //   red    (thread per problem)           step length; conditional predictor-corrector decision
-//   ric2 / step1 / red in mode 2          pure centering re-solve for the problems that asked for it
+//   step1 / red in mode 2                 the problems that asked for it switch to the centering direction
 // Every lane owns a whole problem (or a whole stage of one): no shuffles, no barriers, no padding, 32 useful
 // operations per instruction, and each kernel body is a few KB of code (the monolithic v5 kernel was bound by
 // instruction fetch, profiles/r01_qp_v5_warp_per_problem.md).
@@ -45,15 +46,17 @@ SMPC_HD constexpr int trs(int i, int j) { return i >= j ? tri(i, j) : tri(j, i);
 enum { I_Z = 0, I_PIM = 15, I_LAM = 25, I_T = 69, I_SLK = 113, NIT = 120 };   // I_SLK: s_l s_u lam_sl lam_su t_sl t_su
 // solver block of one stage: everything the Riccati sweeps read or write, ordered so that each sweep fetches one
 // contiguous range:   ric1 backward reads [B_M, B_LP), writes [B_LP, B_V1);   ric1 forward reads [B_RB, B_WV);
-// ric2 backward reads [B_GA, B_P) + [B_V1, NSB), writes B_LP;   ric2 forward reads [B_RB, B_V1)
+// ric2 backward reads [B_GA, B_P) + [B_V1, NSB), writes B_LP, B_LP2;   ric2 forward reads [B_RB, B_V1)
 //   M    condensed stage matrix H + reg + C' Gam C, packed lower triangle (prep)
 //   GA   affine gradient res_g + C' gam (prep)          RB   dynamics residual of the link k -> k+1 (prep)
 //   LP   l~ (5), p (10) of the current solve (ric1 / ric2)
 //   T    elimination multipliers T[15][5], T[j][j] = 1/d_j (ric1)
 //   WV   P_{k+1} res_b (ric1)                           P    Riccati matrix, packed 10x10 (ric1)
+//   LP2  l~, p of the speculative centering solve (ric2)
 //   V1   C'(dlam_aff dt_aff / t), V2 = C'(1 / t): corrector terms (step0)
-enum { B_M = 0, B_GA = 120, B_RB = 135, B_LP = 145, B_T = 160, B_WV = 235, B_P = 245, B_V1 = 300, B_V2 = 315, NSB = 330 };
-enum { H_M = B_M, H_GA = B_GA, H_RB = B_RB, F_LP = B_LP, F_T = B_T, F_WV = B_WV, F_P = B_P, V_1 = B_V1, V_2 = B_V2, NHC = NSB, NFAC = NSB, NV = NSB };
+enum { B_M = 0, B_GA = 120, B_RB = 135, B_LP = 145, B_T = 160, B_WV = 235, B_P = 245, B_LP2 = 300, B_V1 = 315, B_V2 = 330, NSB = 345 };
+enum { H_M = B_M, H_GA = B_GA, H_RB = B_RB, F_LP = B_LP, F_T = B_T, F_WV = B_WV, F_P = B_P, F_LP2 = B_LP2, V_1 = B_V1, V_2 = B_V2, NHC = NSB, NFAC = NSB, NV = NSB };
+enum { NS2 = 25 };                 // centering direction: dz (15), dpi (10), same field order as the step block
 enum { NPROD = 46 };               // dlam_aff * dt_aff per slot (44) + the two slack slots
 enum { R_NG = 0, R_NB = 1, R_ND = 2, R_NM = 3, R_MU = 4, R_CHK = 5, R_CNT = 6, NRES = 8 };
 enum { S_ALPHA = 0, S_LIN = 1, S_QUAD = 2, NSTP = 4 };
@@ -66,6 +69,7 @@ struct QsBufs {
   const double* rec;     // [T][N+1][REC][TL]   stage records (linearisation)
   double* it[2];         // [T][N+1][NIT][TL]   iterate, ping-pong
   double* st;            // [T][N+1][NIT][TL]   step
+  double* st2;           // [T][N+1][NS2][TL]   pure-centering direction (dz, dpi) computed speculatively by ric2
   double* sb;            // [T][N+1][NSB][TL]   solver block (condensed matrices, Riccati factors, corrector terms)
   double* prod;          // [T][N+1][NPROD][TL]
   double* res;           // [T][N+1][NRES][TL]
@@ -760,13 +764,18 @@ SMPC_HD void qs_reduce_step(const QsBufs& q, int tile, int lane, double& alpha, 
   }
 }
 
-// ric2: vector-only backward sweep for the corrector (mode 1) / centering (mode 2) right-hand side, stage-0 solve,
-// forward substitution with the multiplier steps.  In mode 1 the prologue turns the affine step statistics into sigma.
+// ric2: vector-only backward sweep, stage-0 solve and forward substitution with the multiplier steps, for the corrector
+// right-hand side ga + v1 - sigma mu v2 AND, in the same pass, for the pure-centering right-hand side ga - sigma mu v2 that
+// the conditional predictor-corrector falls back to (HPIPM: when the corrected step would more than double mu_aff).  Both
+// share every factor load (T, P, WV, RB), the second vector rides in the latency shadow of the first, and the separate
+// centering sweep of the earlier versions (a full sequential pass for the 1-80 % of the problems that asked for it)
+// is gone; the arithmetic of each direction is unchanged.  The prologue turns the affine step statistics into sigma.
+// Directions: corrector -> st (Z, PIM) and LP; centering -> st2 (Z, PIM) and LP2.
 template <class W>
-SMPC_HD void qs_ric2(const smpc_problem_t& P, const QsBufs& q, int tile, W& w, int mode) {
+SMPC_HD void qs_ric2(const smpc_problem_t& P, const QsBufs& q, int tile, W& w) {
   const int N = q.N, lane = w.lane();
   const int32_t* pi = q.pi + qs_pb(tile, NPI, lane);
-  const bool on = QF(pi, J_ACT) != 0 && (mode != 2 || QF(pi, J_REDO) != 0);
+  const bool on = QF(pi, J_ACT) != 0;
   if (!w.any(on)) return;
   double* pd = q.pd + qs_pb(tile, NPD, lane);
   const double dt = P.dt, a2 = 0.5 * P.dt * P.dt;
@@ -779,20 +788,20 @@ SMPC_HD void qs_ric2(const smpc_problem_t& P, const QsBufs& q, int tile, W& w, i
   w.fetch(N & nb1, 0, gsb + (size_t)N * sstride, B_GA, n1);
   w.fetch(N & nb1, n1, gsb + (size_t)N * sstride, B_V1, n2);
   double sigmu = 0.0;
-  if (mode == 1) {
-    if (on) {
-      double alpha, s_lin, s_quad;
-      qs_reduce_step(q, tile, lane, alpha, s_lin, s_quad);
-      const double mu = QF(pd, D_MU);
-      const double mu_aff = mu + (alpha * s_lin + alpha * alpha * s_quad) / QF(pi, J_NC);
-      double sigma = mu_aff / mu; sigma = sigma * sigma * sigma;
-      sigmu = sigma * mu;
-      QF(pd, D_MUAFF) = mu_aff; QF(pd, D_SIGMU) = sigmu;
-    }
-  } else sigmu = QF(pd, D_SIGMU);
-  double pn[10], dx[10];
+  if (on) {
+    double alpha, s_lin, s_quad;
+    qs_reduce_step(q, tile, lane, alpha, s_lin, s_quad);
+    const double mu = QF(pd, D_MU);
+    const double mu_aff = mu + (alpha * s_lin + alpha * alpha * s_quad) / QF(pi, J_NC);
+    double sigma = mu_aff / mu; sigma = sigma * sigma * sigma;
+    sigmu = sigma * mu;
+    QF(pd, D_MUAFF) = mu_aff; QF(pd, D_SIGMU) = sigmu;
+  }
+  double pn[2][10], dx[2][10];
 #pragma unroll
-  for (int i = 0; i < 10; ++i) { pn[i] = 0.0; dx[i] = 0.0; }
+  for (int v = 0; v < 2; ++v)
+#pragma unroll
+    for (int i = 0; i < 10; ++i) { pn[v][i] = 0.0; dx[v][i] = 0.0; }
   for (int k = N; k >= 0; --k) {
     w.sync();
     if (nb1 ? k > 0 : k < N) {
@@ -806,49 +815,59 @@ SMPC_HD void qs_ric2(const smpc_problem_t& P, const QsBufs& q, int tile, W& w, i
     const double* sb = w.buf(k & nb1) - (size_t)B_GA * TL;         // sb[f] valid for B_GA <= f < B_P
     const double* vv = w.buf(k & nb1) - (size_t)(B_V1 - n1) * TL;  // vv[f] valid for B_V1 <= f < NSB
     double* fac = q.sb + qs_blk(tile, N, k, NSB, lane);
-    double g[15];
+    double g[2][15];
 #pragma unroll
-    for (int i = 0; i < 15; ++i) g[i] = QF(sb, H_GA + i) + (mode == 1 ? QF(vv, V_1 + i) : 0.0) - sigmu * QF(vv, V_2 + i);
+    for (int i = 0; i < 15; ++i) {
+      const double ga = QF(sb, H_GA + i), s2 = sigmu * QF(vv, V_2 + i);
+      g[0][i] = ga + QF(vv, V_1 + i) - s2;
+      g[1][i] = ga + 0.0 - s2;
+    }
     if (k < N) {
-      double y[10];
 #pragma unroll
-      for (int i = 0; i < 10; ++i) y[i] = QF(sb, F_WV + i) + pn[i];
+      for (int v = 0; v < 2; ++v) {
+        double y[10];
 #pragma unroll
-      for (int j = 0; j < 5; ++j) {
-        g[j] += a2 * y[j] + dt * y[5 + j];
-        g[5 + j] += y[j];
-        g[10 + j] += dt * y[j] + y[5 + j];
+        for (int i = 0; i < 10; ++i) y[i] = QF(sb, F_WV + i) + pn[v][i];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+          g[v][j] += a2 * y[j] + dt * y[5 + j];
+          g[v][5 + j] += y[j];
+          g[v][10 + j] += dt * y[j] + y[5 + j];
+        }
       }
     } else {
 #pragma unroll
-      for (int i = 0; i < 5; ++i) g[i] = 0.0;
+      for (int i = 0; i < 5; ++i) { g[0][i] = 0.0; g[1][i] = 0.0; }
     }
 #pragma unroll
     for (int j = 0; j < 5; ++j)
 #pragma unroll
-      for (int i = j + 1; i < 15; ++i) g[i] -= QF(sb, F_T + i * 5 + j) * g[j];
+      for (int i = j + 1; i < 15; ++i) { const double t = QF(sb, F_T + i * 5 + j); g[0][i] -= t * g[0][j]; g[1][i] -= t * g[1][j]; }
     if (on) {
 #pragma unroll
-      for (int i = 0; i < 15; ++i) QF(fac, F_LP + i) = g[i];
+      for (int i = 0; i < 15; ++i) { QF(fac, F_LP + i) = g[0][i]; QF(fac, F_LP2 + i) = g[1][i]; }
     }
 #pragma unroll
-    for (int i = 0; i < 10; ++i) pn[i] = g[5 + i];
+    for (int v = 0; v < 2; ++v)
+#pragma unroll
+      for (int i = 0; i < 10; ++i) pn[v][i] = g[v][5 + i];
     if (k == 0) {
 #pragma unroll
       for (int j = 0; j < 10; ++j)
 #pragma unroll
-        for (int i = j + 1; i < 10; ++i) pn[i] -= QF(pd, D_T0 + tri(i, j)) * pn[j];
+        for (int i = j + 1; i < 10; ++i) { const double t = QF(pd, D_T0 + tri(i, j)); pn[0][i] -= t * pn[0][j]; pn[1][i] -= t * pn[1][j]; }
 #pragma unroll
       for (int i = 9; i >= 0; --i) {
         const double invd = QF(pd, D_T0 + tri(i, i));
-        double acc = invd * pn[i];
+        double acc0 = invd * pn[0][i], acc1 = invd * pn[1][i];
 #pragma unroll
-        for (int c = i + 1; c < 10; ++c) acc += QF(pd, D_T0 + tri(c, i)) * dx[c];
-        dx[i] = invd > 0.0 ? -acc : 0.0;
+        for (int c = i + 1; c < 10; ++c) { const double t = QF(pd, D_T0 + tri(c, i)); acc0 += t * dx[0][c]; acc1 += t * dx[1][c]; }
+        dx[0][i] = invd > 0.0 ? -acc0 : 0.0;
+        dx[1][i] = invd > 0.0 ? -acc1 : 0.0;
       }
     }
   }
-  // forward: stages fetch RB LP T WV P = [B_RB, B_V1)
+  // forward: stages fetch RB LP T WV P LP2 = [B_RB, B_V1)
   w.publish();
   w.sync();
   w.fetch_begin(0, B_V1 - B_RB);
@@ -861,48 +880,53 @@ SMPC_HD void qs_ric2(const smpc_problem_t& P, const QsBufs& q, int tile, W& w, i
     w.wait(k & nb1);
     const double* sb = w.buf(k & nb1) - (size_t)B_RB * TL;
     double* st = q.st + qs_blk(tile, N, k, NIT, lane);
+    double* st2 = q.st2 + qs_blk(tile, N, k, NS2, lane);
     // multiplier step of the link k-1 -> k:  dpi = P_k dx_k + p_k
 #pragma unroll
     for (int i = 0; i < 10; ++i) {
-      double s = 0.0;
+      double s0 = 0.0, s1 = 0.0;
       if (k > 0) {
-        s = QF(sb, F_LP + 5 + i);
+        s0 = QF(sb, F_LP + 5 + i); s1 = QF(sb, F_LP2 + 5 + i);
 #pragma unroll
-        for (int j = 0; j < 10; ++j) s += QF(sb, F_P + trs(i, j)) * dx[j];
+        for (int j = 0; j < 10; ++j) { const double pv = QF(sb, F_P + trs(i, j)); s0 += pv * dx[0][j]; s1 += pv * dx[1][j]; }
       }
-      if (on) QF(st, I_PIM + i) = s;
+      if (on) { QF(st, I_PIM + i) = s0; QF(st2, I_PIM + i) = s1; }
     }
-    double du[5];
+    double du[2][5];
 #pragma unroll
-    for (int i = 0; i < 5; ++i) du[i] = 0.0;
+    for (int i = 0; i < 5; ++i) { du[0][i] = 0.0; du[1][i] = 0.0; }
     if (k < N) {
 #pragma unroll
       for (int i = 0; i < 5; ++i) {
-        double ws = QF(sb, F_T + i * 5 + i) * QF(sb, F_LP + i);
+        const double tii = QF(sb, F_T + i * 5 + i);
+        double ws0 = tii * QF(sb, F_LP + i), ws1 = tii * QF(sb, F_LP2 + i);
 #pragma unroll
-        for (int r = 0; r < 10; ++r) ws += QF(sb, F_T + (5 + r) * 5 + i) * dx[r];
-        du[i] = -ws;
+        for (int r = 0; r < 10; ++r) { const double t = QF(sb, F_T + (5 + r) * 5 + i); ws0 += t * dx[0][r]; ws1 += t * dx[1][r]; }
+        du[0][i] = -ws0; du[1][i] = -ws1;
       }
 #pragma unroll
       for (int c = 4; c >= 1; --c)
 #pragma unroll
-        for (int i = 0; i < c; ++i) du[i] -= QF(sb, F_T + c * 5 + i) * du[c];
+        for (int i = 0; i < c; ++i) { const double t = QF(sb, F_T + c * 5 + i); du[0][i] -= t * du[0][c]; du[1][i] -= t * du[1][c]; }
     }
     if (on) {
 #pragma unroll
-      for (int i = 0; i < 5; ++i) QF(st, I_Z + i) = du[i];
+      for (int i = 0; i < 5; ++i) { QF(st, I_Z + i) = du[0][i]; QF(st2, I_Z + i) = du[1][i]; }
 #pragma unroll
-      for (int i = 0; i < 10; ++i) QF(st, I_Z + 5 + i) = dx[i];
+      for (int i = 0; i < 10; ++i) { QF(st, I_Z + 5 + i) = dx[0][i]; QF(st2, I_Z + 5 + i) = dx[1][i]; }
     }
     if (k < N) {
-      double nx[10];
 #pragma unroll
-      for (int j = 0; j < 5; ++j) {
-        nx[j] = dx[j] + dt * dx[5 + j] + a2 * du[j] + QF(sb, H_RB + j);
-        nx[5 + j] = dx[5 + j] + dt * du[j] + QF(sb, H_RB + 5 + j);
+      for (int v = 0; v < 2; ++v) {
+        double nx[10];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+          nx[j] = dx[v][j] + dt * dx[v][5 + j] + a2 * du[v][j] + QF(sb, H_RB + j);
+          nx[5 + j] = dx[v][5 + j] + dt * du[v][j] + QF(sb, H_RB + 5 + j);
+        }
+#pragma unroll
+        for (int j = 0; j < 10; ++j) dx[v][j] = nx[j];
       }
-#pragma unroll
-      for (int j = 0; j < 10; ++j) dx[j] = nx[j];
     }
   }
 }
@@ -926,8 +950,15 @@ SMPC_HD void qs_step(const smpc_problem_t& P, const QsBufs& q, int tile, int lan
   double* prod = q.prod + qs_blk(tile, N, k, NPROD, lane);
   const StageFlags F = qs_flags(P, k);
   double z[15], dz[15];
+  if (mode == 2) {
+    // the centering direction was computed by ric2 next to the corrector: it becomes the step of this problem
+    const double* st2 = q.st2 + qs_blk(tile, N, k, NS2, lane);
 #pragma unroll
-  for (int i = 0; i < 15; ++i) { z[i] = QF(it, I_Z + i); dz[i] = QF(st, I_Z + i); }
+    for (int i = 0; i < 15; ++i) { z[i] = QF(it, I_Z + i); dz[i] = QF(st2, I_Z + i); }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 15; ++i) { z[i] = QF(it, I_Z + i); dz[i] = QF(st, I_Z + i); }
+  }
   // step length = min over the slots of lam / (-dlam), t / (-dt) (negative steps only), kept as a fraction an / ad and
   // compared by cross-multiplication: one division per thread instead of two per slot
   double an = 1.0, ad = 1.0, s_lin = 0.0, s_quad = 0.0;
@@ -1109,6 +1140,17 @@ SMPC_HD void qs_step(const smpc_problem_t& P, const QsBufs& q, int tile, int lan
 #pragma unroll
     for (int i = 0; i < 15; ++i) { QF(vv, V_1 + i) = v1[i]; QF(vv, V_2 + i) = v2[i]; }
   }
+  if (mode == 2) {
+    // (dz, dpi) of the step block <- centering direction (after every load of this thread, see the note on load / store phases)
+    const double* st2 = q.st2 + qs_blk(tile, N, k, NS2, lane);
+    double dpi[10];
+#pragma unroll
+    for (int j = 0; j < 10; ++j) dpi[j] = QF(st2, I_PIM + j);
+#pragma unroll
+    for (int i = 0; i < 15; ++i) QF(st, I_Z + i) = dz[i];
+#pragma unroll
+    for (int j = 0; j < 10; ++j) QF(st, I_PIM + j) = dpi[j];
+  }
   double* stp = q.stp + qs_blk(tile, N, k, NSTP, lane);
   QF(stp, S_ALPHA) = an / ad; QF(stp, S_LIN) = s_lin; QF(stp, S_QUAD) = s_quad;
 }
@@ -1161,7 +1203,7 @@ struct QsLoop {
     bk.ctl(kk);
     bk.ric1();
     bk.step(kk, 0);
-    bk.ric2(1);
+    bk.ric2();
     bk.step(kk, 1);
     bk.red(false);
     bk.request_counters();
@@ -1171,7 +1213,7 @@ struct QsLoop {
     int n_active = 0, n_redo = 0;
     bk.wait_counters(n_active, n_redo);
     if (n_active == 0) { bk.final(); done = true; return; }
-    if (n_redo > 0) { bk.ric2(2); bk.step(kk, 2); bk.red(true); }
+    if (n_redo > 0) { bk.step(kk, 2); bk.red(true); }
     ++kk;
     bk.prep(kk);
     issue();

@@ -102,7 +102,7 @@ struct HostBackend {
     each_problem([&](int t, int l) { if (qs_ctl(P, q, t, l, kk, status, qp_iter, qp_status, qp_res)) ++n_active; });
   }
   void ric1() { each_problem([&](int t, int l) { HostStage w(l, RIC1_STAGE_FIELDS, order); w.nb = 2 - order; qs_ric1(P, q, t, w, psm.data() + l); }); }
-  void ric2(int mode) { each_problem([&](int t, int l) { HostStage w(l, RIC2_STAGE_FIELDS, order); w.nb = 2 - order; qs_ric2(P, q, t, w, mode); }); }
+  void ric2() { each_problem([&](int t, int l) { HostStage w(l, RIC2_STAGE_FIELDS, order); w.nb = 2 - order; qs_ric2(P, q, t, w); }); }
   void step(int kk, int mode) { each_stage([&](int t, int l, int k) { qs_step(P, q, t, l, k, kk, mode); }); }
   void final() { each_stage([&](int t, int l, int k) { if (qs_final(q, t, l, k, act, B, status, xt, ut)) status[(q.tile0 + t) * TL + l] = 1; }); }
   void red(bool after) { each_problem([&](int t, int l) { qs_red(P, q, t, l, after); }); }
@@ -124,13 +124,13 @@ extern "C" int emu_qp_solve(const smpc_problem_t* P, int B, const double* rec, c
                             int32_t* qp_iter, int32_t* qp_status, double* qp_res, int* n_redo_total) {
   const int N = P->N, T = (B + TL - 1) / TL;
   const size_t S = (size_t)T * (N + 1) * TL;
-  std::vector<double> vrec(S * REC, 0.0), it0(S * NIT, 0.0), it1(S * NIT, 0.0), st(S * NIT, 0.0), sb(S * NSB, 0.0), prod(S * NPROD, 0.0), res(S * NRES, 0.0), stp(S * NSTP, 0.0), pd((size_t)T * NPD * TL, 0.0);
+  std::vector<double> vrec(S * REC, 0.0), it0(S * NIT, 0.0), it1(S * NIT, 0.0), st(S * NIT, 0.0), st2(S * NS2, 0.0), sb(S * NSB, 0.0), prod(S * NPROD, 0.0), res(S * NRES, 0.0), stp(S * NSTP, 0.0), pd((size_t)T * NPD * TL, 0.0);
   std::vector<int32_t> pi32((size_t)T * NPI * TL, 0);
   for (int b = 0; b < B; ++b)
     for (int k = 0; k <= N; ++k)
       for (int f = 0; f < REC; ++f)
         vrec[qs_blk(b / TL, N, k, REC, b % TL) + (size_t)f * TL] = rec[((size_t)b * (N + 1) + k) * REC + f];
-  QsBufs q{vrec.data(), {it0.data(), it1.data()}, st.data(), sb.data(), prod.data(), res.data(), stp.data(),
+  QsBufs q{vrec.data(), {it0.data(), it1.data()}, st.data(), st2.data(), sb.data(), prod.data(), res.data(), stp.data(),
            pd.data(), pi32.data(), N, 0};
   HostBackend bk{*P, q, B, T, N, order, x0, r, act, xt, ut, status, qp_iter, qp_status, qp_res, std::vector<double>(65 * TL, 0.0)};
   // two groups of tiles when there is more than one tile (exercises the group offsets), driven round-robin
@@ -140,7 +140,7 @@ extern "C" int emu_qp_solve(const smpc_problem_t* P, int B, const double* rec, c
     const int t0 = g == 0 ? 0 : T / 2, t1 = (g == G - 1) ? T : T / 2;
     HostBackend b2 = bk;
     const size_t so = (size_t)t0 * (N + 1) * TL;
-    b2.q.rec = q.rec + so * REC; b2.q.it[0] = q.it[0] + so * NIT; b2.q.it[1] = q.it[1] + so * NIT; b2.q.st = q.st + so * NIT;
+    b2.q.rec = q.rec + so * REC; b2.q.it[0] = q.it[0] + so * NIT; b2.q.it[1] = q.it[1] + so * NIT; b2.q.st = q.st + so * NIT; b2.q.st2 = q.st2 + so * NS2;
     b2.q.sb = q.sb + so * NSB; b2.q.prod = q.prod + so * NPROD; b2.q.res = q.res + so * NRES; b2.q.stp = q.stp + so * NSTP;
     b2.q.pd = q.pd + (size_t)t0 * NPD * TL; b2.q.pi = q.pi + (size_t)t0 * NPI * TL; b2.q.tile0 = t0;
     b2.T = t1 - t0;

@@ -262,6 +262,17 @@ def run_engine(a):
     alg_bytes = visits * (N + 1) * prep_bytes_unit / max(1, prep_n)          # per launch, averaged over the launches of one solve
     prep_launch_ms = prep_ms / max(1, prep_n)
     achieved = alg_bytes / (prep_launch_ms * 1e-3) / 1e9
+    # second kernel by time: the factorising Riccati sweep qs_ric1 (thread per problem, sequential in the stage index).  Per (problem, stage)
+    # it reads M, GA, RB (145) and, in the forward pass, RB, LP, T (100), and writes LP, T, WV, P (155) and dz (15): 415 doubles = 3 320 B.
+    # A launch walks every tile that still has an active problem, so the bytes are counted per problem of an active tile ~ active problems.
+    ric_ms, ric_n = kern['qs_ric1']
+    ric_bytes = visits * (N + 1) * 415 * 8 / max(1, ric_n)
+    ric_ach = ric_bytes / (ric_ms / max(1, ric_n) * 1e-3) / 1e9
+    ric_roof = {'kernel': 'qs_ric1_kernel', 'bound': 'hbm', 'achieved': ric_ach, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ric_ach / hbm_peak,
+                'traffic': 1.47e9 if (B, N) == (10000, 45) else None, 'launch_ms': ric_ms / max(1, ric_n), 'launches_per_solve': ric_n,
+                'share_of_qp_solve': ric_ms / max(kern_total, 1e-9),
+                'note': 'latency-bound sweep: one warp per tile of 32 problems, 46 dependent stages; a launch costs the same 0.33 ms whether 1 or 10 000 problems '
+                        'are still iterating, which is why its average fraction is far below that of a full launch (0.6 of the HBM peak, profiles/r01_qp_v7.md)'}
     flops_solve = 0.48e6 * float(main.get_state(abi.STATE_QP_ITER).sum())       # 0.48 MFLOP per IPM iteration
     value = solves_all / (ms_max * 1e-3)
     line = {
@@ -277,12 +288,14 @@ def run_engine(a):
         'ipm_iterations_per_solve': ipm / max(1, solves),
         'gpu_launches': int(sum(v[3] for v in allv)),
         'clocks': clocks,
-        'roofline': {'kernel': 'qs_prep_kernel', 'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak,
-                     'traffic': 2.26e9 if (B, N) == (10000, 45) else None,
-                     'traffic_source': 'ncu dram__bytes_read+write per launch, profiles/r01_qp_v6_launches.md (B=10000, N=45 only)',
+        'roofline': {'kernel': 'qs_prep_coop_kernel (IPM iterations >= 1; the cold start is qs_prep_kernel<true>)', 'bound': 'hbm', 'achieved': achieved,
+                     'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak,
+                     'traffic': 2.40e9 if (B, N) == (10000, 45) else None,
+                     'traffic_source': 'ncu dram__bytes_read+write of one full launch (all problems active), profiles/r01_qp_v7.md (B=10000, N=45 only)',
                      'peak_source': peak_src, 'algorithmic_bytes_per_launch': alg_bytes, 'launch_ms': prep_launch_ms,
                      'launches_per_solve': prep_n, 'share_of_qp_solve': prep_ms / max(kern_total, 1e-9),
                      'note': 'bytes and time are averaged over every qs_prep launch of one solve; a launch only touches the problems still iterating'},
+        'roofline_riccati': ric_roof,
         'qp_solve': {'ms': qp_ms, 'ms_single_tile_group': qp_ms_1group, 'linearize_ms': lin_ms, 'ipm_iterations_mean': it_qp, 'ipm_iterations_max': it_max,
                      'algorithmic_fp64_tflops': flops_solve / (qp_ms * 1e-3) / 1e12,
                      'kernel_ms': {k: round(v[0], 3) for k, v in kern.items()}, 'kernel_launches': {k: v[1] for k, v in kern.items()},

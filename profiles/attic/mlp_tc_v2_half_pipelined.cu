@@ -1,0 +1,564 @@
+// ARCHIVED EXPERIMENT (round 1, not built): half-pipelined variant of csrc/mlp_tc.cu -- a layer is issued as four (output half,
+// k half) blocks so that the epilogue of one output half runs under the MMAs of the other, accumulator of half 1 double-buffered,
+// 16 epilogue warps with 16-column tcgen05.ld/st.  Parity-green, but 3.2-3.5 ms per 460k rows against 2.99 ms for the simpler
+// kernel: the ncu source page (profiles/r01_mlp_tc.md) shows every role waiting on the weight ring (64 KB in flight per SM), so
+// overlapping MMA and epilogue buys nothing until the per-SM weight ingest is halved (cta_group::2 pair: each CTA streams only the
+// weights of its 128 units for 128 rows).  Kept as the starting point for that kernel.
+// Viability network on the 5th-generation tensor cores (tcgen05 + TMEM), "fp32 mode".
+//
+// NeuralNetwork / NetSafeSet of reference safe_set.py:26-43,71-104: c(x) = NN(psi(x)) (100 - alpha)/100 - |v| and dc/dx for
+// every (problem, stage) row that carries the viability constraint.  The reference evaluates the network in fp32 inside
+// libtorch (L4CasADi) and differentiates it with jacrev; this kernel reproduces that precision class: fp32 storage, fp32
+// accumulation, and the two 256 x 256 layers (forward and reverse sweep) as 3xTF32 split products on the tensor cores
+// (a = a_hi + a_lo, w = w_hi + w_lo, a w ~ a_hi w_hi + a_lo w_hi + a_hi w_lo: 2^-21 per product, i.e. fp32-class).
+// The strict fp64-accumulate kernel in kernels.cu stays the default (smpc_problem_t::nn_precision = 0).
+//
+// One CTA works on tiles of R = 64 rows.  Per tile
+//   layer 1 (10 -> 256), the output layer (256 -> 1) and the last reverse layer (256 -> 10) run on the CUDA cores (2 % of the flops);
+//   the four 256 x 256 contractions (forward 2, 3; reverse 3, 2) run as tcgen05.mma.kind::tf32 with
+//     D[unit (M = 128 per half)][row (N = 64)] += W[unit][k] * X[row][k]          (both operands K-major in shared memory)
+//   so that TMEM lane = hidden unit, TMEM column = row of the tile: the epilogue thread of lane j owns unit j (bias, GELU and
+//   its derivative are per-thread scalars/elementwise) and writes the next layer's operand X[row][k = j] straight back to
+//   shared memory in the canonical K-major core-matrix layout.  GELU derivatives of layers 1 and 2 stay in TMEM
+//   (tcgen05.st) until the reverse sweep multiplies them in.  TMEM: accumulator 128 columns, D1 128, D2 128.
+//   Weights are pre-split (hi / lo) and pre-packed on the host into the exact shared-memory image of a K-stage, and streamed
+//   L2 -> shared memory with 1-D TMA bulk copies (cp.async.bulk + mbarrier) by a producer thread; one elected thread issues
+//   the MMAs; tcgen05.commit releases weight stages and signals the epilogue.
+// Warp roles: 0-15 epilogue / CUDA-core layers (warp w: TMEM lanes 32 (w % 4) .. + 31, rows 16 (w / 4) .. + 15 of the tile; four warps per
+// scheduler because the kernel is bound by the issue rate of the epilogue's dependent fp32 instruction stream), 16 weight producer,
+// 17 MMA issuer.
+#include <cstring>
+#include <type_traits>
+#include <vector>
+
+#include "engine.cuh"
+
+namespace smpc {
+
+namespace {
+
+constexpr int R = 64;                       // rows per tile = MMA N
+constexpr int HID = SMPC_HID;               // 256
+constexpr int KC = 16;                      // k-values per weight stage (two K = 8 MMA steps)
+constexpr int NSTG = 2 * HID / KC;          // stages per layer: (output half, 16 k-values) each
+constexpr int NSLOT = 4;                    // weight ring slots
+constexpr int XPITCH = R * 16 + 16;         // bytes between consecutive 16-byte k-chunks of X (+16: conflict-free epilogue stores)
+constexpr int XBYTES = (HID / 4) * XPITCH;  // one of X_hi / X_lo
+constexpr int WROWB = 128 * 16;             // bytes of one k-chunk of one half of the weight operand: 128 units x 16 B
+constexpr int WHALF = (KC / 4) * WROWB;     // the hi (or lo) block of a stage
+constexpr int WSTAGE = 2 * WHALF;           // [hi|lo][chunk][unit][4 floats] = 16 KB
+constexpr int NCW = 16;                     // epilogue / CUDA-core warps: warp w owns TMEM lanes 32 (w % 4) .., columns CW (w / 4) ..
+constexpr int CW = 4 * R / NCW;             // rows of the tile (TMEM columns) per epilogue thread: 16
+constexpr int TC_THREADS = 32 * (NCW + 2);
+constexpr int ACC1COL = 64, D1COL = 192, D2COL = 320, TMEM_COLS = 512;   // accumulators: half 0 at 0, half 1 double-buffered at 64 / 128
+
+constexpr int OFF_XH = 0;
+constexpr int OFF_XL = OFF_XH + XBYTES;
+constexpr int OFF_W = OFF_XL + XBYTES;
+constexpr int OFF_W1 = OFF_W + NSLOT * WSTAGE;          // float [256][10]
+constexpr int OFF_VEC = OFF_W1 + HID * NX * 4;          // float b1[256] b2[256] b3[256] W4[256]
+constexpr int OFF_INF = OFF_VEC + 4 * HID * 4;          // float [R][10]
+constexpr int OFF_GIN = OFF_INF + R * NX * 4;           // float [4][R][10]  (partial sums over a quarter of the hidden units)
+constexpr int OFF_YP = OFF_GIN + 4 * R * NX * 4;        // float [4][R]
+constexpr int OFF_META = OFF_YP + 4 * R * 4;            // int rowb[R], rowk[R], valid[R], vote[4]
+constexpr int OFF_BAR = OFF_META + (3 * R + 4) * 4;     // uint64 full[NSLOT], empty[NSLOT], acc_full[2], x_ready[2]
+constexpr int OFF_TMEM = OFF_BAR + (2 * NSLOT + 4) * 8;
+constexpr int TC_SMEM = OFF_TMEM + 16;
+static_assert(OFF_W % 128 == 0 && OFF_BAR % 8 == 0, "alignment");
+static_assert(TC_SMEM <= 232448, "shared memory budget");
+
+// instruction descriptor of tcgen05.mma.kind::tf32: D fp32, A/B tf32, both K-major, M = 128, N = R
+constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(R >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+__device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// shared-memory matrix descriptor, K-major, no swizzle: core matrix = 8 rows x 16 B stored contiguously;
+// lbo = byte distance between the two core matrices along K, sbo = between 8-row groups along M / N
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((addr & 0x3ffffu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = s32(bar);
+  uint32_t ok;
+  do {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok)
+                 : "r"(addr), "r"(parity)
+                 : "memory");
+  } while (!ok);
+}
+// wait of a whole epilogue warp: one lane polls (with a short sleep between polls so that the sixteen waiting warps leave the issue
+// slots and the shared-memory port to the producer and MMA threads), the others join at the warp barrier
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, int lane) {
+  if (lane == 0) {
+    const uint32_t addr = s32(bar);
+    uint32_t ok;
+    for (;;) {
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                   : "=r"(ok)
+                   : "r"(addr), "r"(parity)
+                   : "memory");
+      if (ok) break;
+      __nanosleep(100);
+    }
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s32(dst)), "l"(src),
+               "r"(bytes), "r"(s32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, %0;" ::"n"(32 * NCW) : "memory"); }
+
+#define V32_OUT(v)                                                                                                              \
+  "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),       \
+      "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),      \
+      "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),      \
+      "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+#define V32_IN(v)                                                                                                               \
+  "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),     \
+      "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]),   \
+      "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]),   \
+      "r"(v[31])
+
+// 32 consecutive TMEM columns of this thread's lane -> registers (the wait makes them readable)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
+      "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : V32_OUT(v)
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
+      "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      V32_IN(v)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// 16-column forms
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                 "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+               "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+               "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+               : "memory");
+}
+
+// a = hi + lo with hi exactly representable in tf32 (round to nearest at 10 mantissa bits); lo keeps the next 11+ bits
+__host__ __device__ __forceinline__ void split_tf32(float a, float& hi, float& lo) {
+  uint32_t u;
+#if defined(__CUDA_ARCH__)
+  u = __float_as_uint(a);
+#else
+  std::memcpy(&u, &a, 4);
+#endif
+  u = (u + 0x1000u) & 0xffffe000u;
+#if defined(__CUDA_ARCH__)
+  hi = __uint_as_float(u);
+#else
+  std::memcpy(&hi, &u, 4);
+#endif
+  lo = a - hi;
+}
+
+__device__ __forceinline__ float gelu_f32(float x, float& d) {        // GELU(tanh) and its derivative (safe_set.py:31-40)
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  const float x2 = x * x;
+  // tanh(u) = 1 - 2 / (exp(2u) + 1) with the hardware exp2 / reciprocal: absolute error ~2e-7, no branches
+  const float e = __expf(2.0f * k0 * (x + k1 * x * x2));
+  const float t = 1.0f - __fdividef(2.0f, e + 1.0f);
+  d = 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * k0 * (1.0f + 3.0f * k1 * x2);
+  return 0.5f * x * (1.0f + t);
+}
+
+// byte offset of X[row n][k] inside X_hi / X_lo
+__device__ __forceinline__ int xoff(int n, int k) { return (k >> 2) * XPITCH + n * 16 + (k & 3) * 4; }
+
+__device__ __forceinline__ void x_store(unsigned char* sm, int n, int k, float a) {
+  float hi, lo;
+  split_tf32(a, hi, lo);
+  const int o = xoff(n, k);
+  *reinterpret_cast<float*>(sm + OFF_XH + o) = hi;
+  *reinterpret_cast<float*>(sm + OFF_XL + o) = lo;
+}
+
+// does tile `tile` hold at least one row that has to be evaluated?  (whole warp; same answer in every role)
+__device__ __forceinline__ bool tile_any(int tile, int rows_mode, int n_rows, int B, int N, const int32_t* r, const uint8_t* act,
+                                         const uint8_t* need, int lane) {
+  bool v = false;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int i = tile * R + h * 32 + lane;
+    int b, k;
+    v = v || (i < n_rows && mlp_row(rows_mode, i, B, N, r, act, need, b, k));
+  }
+  return __any_sync(0xffffffffu, v) != 0;
+}
+
+enum { L_FWD2 = 0, L_FWD3 = 1, L_BWD3 = 2, L_BWD2 = 3 };
+
+// epilogue of one output half (units h * 128 + j) of one tensor-core layer, for the thread that owns TMEM lane j and the rows
+// c * CW .. c * CW + CW - 1 of the tile; acc = TMEM column of the accumulator of this half
+template <int L>
+__device__ __forceinline__ void epilogue_half(unsigned char* sm, uint32_t tlane, uint32_t acc, int h, int j, int c, bool want_grad, float* yp) {
+  const float* vec = reinterpret_cast<const float*>(sm + OFF_VEC);
+  const int unit = h * 128 + j;
+  uint32_t v[CW], dv[CW];
+  tmem_ld16(tlane + acc + c * CW, v);
+  if (L == L_BWD3) tmem_ld16(tlane + D2COL + h * R + c * CW, dv);
+  if (L == L_BWD2) tmem_ld16(tlane + D1COL + h * R + c * CW, dv);
+  tmem_ld_wait();
+  const float bias = L == L_FWD2 ? vec[HID + unit] : (L == L_FWD3 ? vec[2 * HID + unit] : 0.0f);
+  const float w4 = vec[3 * HID + unit];
+#pragma unroll
+  for (int i = 0; i < CW; ++i) {
+    const int n = c * CW + i;
+    const float x = __uint_as_float(v[i]);
+    if (L == L_FWD2) {
+      float d;
+      const float a = gelu_f32(x + bias, d);
+      dv[i] = __float_as_uint(d);
+      x_store(sm, n, unit, a);
+    } else if (L == L_FWD3) {
+      float d;
+      const float a = gelu_f32(x + bias, d);
+      yp[i] = fmaf(w4, a, yp[i]);
+      if (want_grad) x_store(sm, n, unit, w4 * d);
+    } else {
+      x_store(sm, n, unit, x * __uint_as_float(dv[i]));
+    }
+  }
+  if (L == L_FWD2) { tmem_st16(tlane + D2COL + h * R + c * CW, dv); tmem_st_wait(); }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+mlp_tc_kernel(const smpc_problem_t* __restrict__ dP, MlpTcWeights w, int B, int N, int rows_mode, int n_rows, const double* __restrict__ xsrc,
+              const int32_t* __restrict__ r, const uint8_t* __restrict__ act, const uint8_t* __restrict__ need, double* out11, int want_grad) {
+  extern __shared__ __align__(128) unsigned char sm[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(sm + OFF_BAR);
+  uint64_t* bar_empty = bar_full + NSLOT;
+  uint64_t* bar_acc = bar_empty + NSLOT;     // [2]: accumulator of output half h complete
+  uint64_t* bar_x = bar_acc + 2;             // [2]: k-half h of the operand X written (and the accumulators it frees drained)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + OFF_TMEM);
+  const int n_tiles = (n_rows + R - 1) / R;
+  const int n_layers = want_grad ? 4 : 2;
+
+  // ---- one-time setup: small weights to shared memory, barriers, TMEM ----
+  {
+    float* W1s = reinterpret_cast<float*>(sm + OFF_W1);
+    float* vec = reinterpret_cast<float*>(sm + OFF_VEC);
+    for (int i = tid; i < HID * NX; i += TC_THREADS) W1s[i] = w.W1[i];
+    for (int i = tid; i < HID; i += TC_THREADS) { vec[i] = w.b1[i]; vec[HID + i] = w.b2[i]; vec[2 * HID + i] = w.b3[i]; vec[3 * HID + i] = w.W4[i]; }
+  }
+  if (tid == 0) {
+    for (int s = 0; s < NSLOT; ++s) { mbar_init(bar_full + s, 1); mbar_init(bar_empty + s, 1); }
+    for (int h = 0; h < 2; ++h) { mbar_init(bar_acc + h, 1); mbar_init(bar_x + h, 32 * NCW); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == NCW) {
+    // =========================== weight producer ===========================
+    uint32_t cnt = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      if (!tile_any(tile, rows_mode, n_rows, B, N, r, act, need, lane)) continue;
+      if (lane == 0) {
+        for (int l = 0; l < n_layers; ++l)
+          for (int s = 0; s < NSTG; ++s, ++cnt) {
+            const int slot = cnt % NSLOT;
+            mbar_wait(bar_empty + slot, ((cnt / NSLOT) & 1) ^ 1);
+            mbar_expect(bar_full + slot, WSTAGE);
+            bulk_g2s(sm + OFF_W + slot * WSTAGE, reinterpret_cast<const unsigned char*>(w.packed) + ((size_t)l * NSTG + s) * WSTAGE, WSTAGE,
+                     bar_full + slot);
+          }
+      }
+      __syncwarp();
+    }
+  } else if (warp == NCW + 1) {
+    // =========================== MMA issuer ===========================
+    // A layer is issued as four blocks (output half o, k half q) in the order (0,0) (1,0) (0,1) (1,1): the first two only need
+    // the k < 128 half of X, i.e. the epilogue of output half 0 of the previous layer; the accumulator of half 0 is complete
+    // after the third block, so its epilogue runs under the fourth, and the epilogue of half 1 under the first two blocks of the
+    // next layer (which is why the accumulator of half 1 is double-buffered).
+    uint32_t cnt = 0, lc = 0, xph[2] = {0, 0};
+    const uint32_t xh = s32(sm + OFF_XH), xl = s32(sm + OFF_XL), wb = s32(sm + OFF_W);
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      if (!tile_any(tile, rows_mode, n_rows, B, N, r, act, need, lane)) continue;
+      if (lane == 0) {
+        for (int l = 0; l < n_layers; ++l, ++lc) {
+#pragma unroll 1
+          for (int blk = 0; blk < 4; ++blk) {
+            const int o = blk & 1, q = blk >> 1;
+            if (o == 0) { mbar_wait(bar_x + q, xph[q]); xph[q] ^= 1; fence_after(); }
+            const uint32_t d = tmem + (o == 0 ? 0 : ACC1COL + R * (lc & 1));
+#pragma unroll 1
+            for (int s = 0; s < NSTG / 4; ++s, ++cnt) {
+              const int slot = cnt % NSLOT;
+              mbar_wait(bar_full + slot, (cnt / NSLOT) & 1);
+              fence_after();
+              const uint32_t ws = wb + slot * WSTAGE;
+#pragma unroll
+              for (int ks = 0; ks < KC / 8; ++ks) {
+                const uint32_t xo = (uint32_t)((q * (HID / 8) + s * (KC / 4) + ks * 2) * XPITCH);
+                const uint64_t bh = smem_desc(xh + xo, XPITCH, 128), bl = smem_desc(xl + xo, XPITCH, 128);
+                const uint64_t ah = smem_desc(ws + ks * 2 * WROWB, WROWB, 128);
+                const uint64_t al = smem_desc(ws + WHALF + ks * 2 * WROWB, WROWB, 128);
+                umma_tf32(d, al, bh, (q | s | ks) != 0);     // small terms first
+                umma_tf32(d, ah, bl, 1);
+                umma_tf32(d, ah, bh, 1);
+              }
+              umma_commit(bar_empty + slot);                  // the stage may be refilled once these MMAs have read it
+            }
+            if (blk == 2) umma_commit(bar_acc + 0);
+            if (blk == 3) umma_commit(bar_acc + 1);
+          }
+        }
+      }
+      __syncwarp();
+    }
+  } else {
+    // =========================== CUDA-core layers + epilogues (256 threads) ===========================
+    const smpc_problem_t& P = *dP;
+    const int j = tid & 127;                                // TMEM lane = hidden unit (and unit 128 + j)
+    const int cg = tid >> 7;                                // which CW rows (TMEM columns) of the tile this thread handles
+    const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    float* INF = reinterpret_cast<float*>(sm + OFF_INF);
+    float* GIN = reinterpret_cast<float*>(sm + OFF_GIN);
+    float* YP = reinterpret_cast<float*>(sm + OFF_YP);
+    int* rowb = reinterpret_cast<int*>(sm + OFF_META);
+    int* rowk = rowb + R;
+    int* valid = rowk + R;
+    int* vote = valid + R;
+    const float* W1s = reinterpret_cast<const float*>(sm + OFF_W1);
+    const float* vec = reinterpret_cast<const float*>(sm + OFF_VEC);
+    uint32_t aph[2] = {0, 0}, lc = 0;
+    // one tensor-core layer seen from the epilogue threads: output half h as soon as its accumulator is complete; `more`: another
+    // tensor-core layer follows and reads what this epilogue writes
+    auto layer = [&](auto tag, bool more, float* yp) {
+      constexpr int L = decltype(tag)::value;
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        mbar_wait_warp(bar_acc + h, aph[h], lane); aph[h] ^= 1; fence_after();
+        epilogue_half<L>(sm, tlane, h == 0 ? 0u : (uint32_t)(ACC1COL + R * (lc & 1)), h, j, cg, want_grad != 0, yp);
+        if (more) { fence_async_smem(); fence_before(); mbar_arrive(bar_x + h); }
+      }
+      ++lc;
+    };
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      // ---- gather the rows of the tile: psi(x) in fp64, fp32 copy for the network ----
+      if (tid < R) {
+        int b = 0, k = 0;
+        const int i = tile * R + tid;
+        const bool v = i < n_rows && mlp_row(rows_mode, i, B, N, r, act, need, b, k);
+        valid[tid] = v; rowb[tid] = b; rowk[tid] = k;
+        double in[NX], nrm = 1.0;
+        if (v) {
+          const double* x = (rows_mode == ROWS_FLAT) ? xsrc + (size_t)b * NX : xsrc + ((size_t)b * (N + 1) + k) * NX;
+          nn_input(P, x, in, &nrm);
+        } else {
+#pragma unroll
+          for (int q = 0; q < NX; ++q) in[q] = 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < NX; ++q) INF[tid * NX + q] = (float)in[q];
+        const unsigned m = __ballot_sync(0xffffffffu, v);
+        if (lane == 0) vote[warp] = m != 0;
+      }
+      bar_compute();
+      const bool any = vote[0] | vote[1];
+      if (!any) { bar_compute(); continue; }               // (second barrier: vote[] is rewritten by the next tile)
+
+      // ---- layer 1 on the CUDA cores: a1 -> X, GELU' -> TMEM D1; the k < 128 half is released first ----
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        const int unit = h * 128 + j;
+        float w1[NX];
+#pragma unroll
+        for (int q = 0; q < NX; ++q) w1[q] = W1s[unit * NX + q];
+        const float bias = vec[unit];
+        uint32_t dv[CW];
+#pragma unroll
+        for (int i = 0; i < CW; ++i) {
+          const int n = cg * CW + i;
+          float acc = bias;
+#pragma unroll
+          for (int q = 0; q < NX; ++q) acc = fmaf(w1[q], INF[n * NX + q], acc);
+          float d;
+          const float a = gelu_f32(acc, d);
+          dv[i] = __float_as_uint(d);
+          x_store(sm, n, unit, a);
+        }
+        tmem_st16(tlane + D1COL + h * R + cg * CW, dv);
+        tmem_st_wait();
+        fence_async_smem(); fence_before(); mbar_arrive(bar_x + h);
+      }
+
+      // ---- tensor-core layers ----
+      float yp[CW];
+#pragma unroll
+      for (int i = 0; i < CW; ++i) yp[i] = 0.0f;
+      layer(std::integral_constant<int, L_FWD2>{}, true, yp);
+      layer(std::integral_constant<int, L_FWD3>{}, want_grad != 0, yp);
+      {
+        // network output: sum of w4 a3 over the 32 lanes of the warp, CW = 16 rows at once: each butterfly step halves the rows a
+        // lane keeps; after four steps the lanes 2 m and 2 m + 1 hold the two halves of row cg * CW + m
+#pragma unroll
+        for (int s = 16, cnt = CW / 2; s >= 2; s >>= 1, cnt >>= 1) {
+#pragma unroll
+          for (int i = 0; i < cnt; ++i) {
+            const bool up = (lane & s) != 0;
+            const float keep = up ? yp[i + cnt] : yp[i];
+            const float send = up ? yp[i] : yp[i + cnt];
+            yp[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+          }
+        }
+        yp[0] += __shfl_xor_sync(0xffffffffu, yp[0], 1);
+        if ((lane & 1) == 0) YP[(warp & 3) * R + cg * CW + (lane >> 1)] = yp[0];
+      }
+      if (want_grad) {
+        layer(std::integral_constant<int, L_BWD3>{}, true, yp);
+        layer(std::integral_constant<int, L_BWD2>{}, false, yp);   // X = g1 (hi + lo)
+      }
+      fence_before();
+      bar_compute();
+
+      // ---- last reverse layer on the CUDA cores: gin[n][i] = sum_k W1[k][i] g1[k][n] ----
+      if (want_grad && tid < 4 * R) {
+        const int n = tid & (R - 1), part = tid >> 6;       // part: quarter of the hidden units
+        float g[NX];
+#pragma unroll
+        for (int q = 0; q < NX; ++q) g[q] = 0.0f;
+#pragma unroll 4
+        for (int ch = part * (HID / 16); ch < (part + 1) * (HID / 16); ++ch) {
+          const float4 hi = *reinterpret_cast<const float4*>(sm + OFF_XH + ch * XPITCH + n * 16);
+          const float4 lo = *reinterpret_cast<const float4*>(sm + OFF_XL + ch * XPITCH + n * 16);
+          const float gv[4] = {hi.x + lo.x, hi.y + lo.y, hi.z + lo.z, hi.w + lo.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+#pragma unroll
+            for (int q = 0; q < NX; ++q) g[q] = fmaf(W1s[(ch * 4 + e) * NX + q], gv[e], g[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < NX; ++q) GIN[(part * R + n) * NX + q] = g[q];
+      }
+      bar_compute();
+      // ---- c(x), dc/dx in fp64 from the fp32 network output (safe_set.py:100-104) ----
+      if (tid < R && valid[tid]) {
+        const double y = (double)w.b4[0] + ((double)YP[tid] + (double)YP[R + tid] + (double)YP[2 * R + tid] + (double)YP[3 * R + tid]);
+        double gin[NX], grad[NX];
+#pragma unroll
+        for (int q = 0; q < NX; ++q)
+          gin[q] = want_grad ? (double)((GIN[tid * NX + q] + GIN[(R + tid) * NX + q]) + (GIN[(2 * R + tid) * NX + q] + GIN[(3 * R + tid) * NX + q])) : 0.0;
+        double in[NX], nrm;                                // psi(x) again in fp64 (cheaper than keeping it in shared memory)
+        nn_input(P, (rows_mode == ROWS_FLAT) ? xsrc + (size_t)rowb[tid] * NX : xsrc + ((size_t)rowb[tid] * (N + 1) + rowk[tid]) * NX, in, &nrm);
+        const double cval = nn_output(P, in, nrm, y, want_grad ? gin : nullptr, want_grad ? grad : nullptr);
+        double* o = (rows_mode == ROWS_FLAT) ? out11 + (size_t)rowb[tid] * NN_OUT : out11 + ((size_t)rowb[tid] * (N + 1) + rowk[tid]) * NN_OUT;
+        o[0] = cval;
+        if (want_grad) {
+#pragma unroll
+          for (int q = 0; q < NX; ++q) o[1 + q] = grad[q];
+        }
+      }
+      bar_compute();                                       // tile buffers (meta, IN, YP, GIN, X) are free again
+    }
+  }
+
+  // ---- teardown ----
+  fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+}  // namespace
+
+// Host: split the four 256 x 256 operands into tf32 hi / lo and lay them out as the shared-memory images of the K-stages.
+// Operand of layer l is A_l[m][k] (m = output unit of the contraction, k = contraction index):
+//   forward 2: W2[m][k], forward 3: W3[m][k], reverse 3: W3[k][m], reverse 2: W2[k][m]      (nn.Linear: y = W x + b, W[out][in])
+// stage (o, q, s) = output half o = m / 128, k half q = k / 128, s = (k % 128) / KC, stored in issue order ((q * 2 + o) * 8 + s);
+// image of a stage: [hi|lo][chunk = (k % KC) / 4][row = m % 128][e = k % 4]
+size_t mlp_tc_packed_floats() { return (size_t)4 * NSTG * (WSTAGE / 4); }
+
+void mlp_tc_pack(const float* W2, const float* W3, float* out) {
+  for (int l = 0; l < 4; ++l) {
+    const float* W = (l == 0 || l == 3) ? W2 : W3;
+    const bool transposed = l >= 2;
+    for (int m = 0; m < HID; ++m)
+      for (int k = 0; k < HID; ++k) {
+        const float a = transposed ? W[(size_t)k * HID + m] : W[(size_t)m * HID + k];
+        float hi, lo;
+        split_tf32(a, hi, lo);
+        const int o = m / 128, row = m % 128, q = k / 128, s = (k % 128) / KC, chunk = (k % KC) / 4, e = k % 4;
+        const size_t base = ((size_t)l * NSTG + (size_t)(q * 2 + o) * (NSTG / 4) + s) * (WSTAGE / 4);
+        const size_t off = (size_t)chunk * (WROWB / 4) + (size_t)row * 4 + e;
+        out[base + off] = hi;
+        out[base + (WHALF / 4) + off] = lo;
+      }
+  }
+}
+
+cudaError_t mlp_tc_prepare() {
+  static bool done = false;
+  if (done) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+  if (e == cudaSuccess) done = true;
+  return e;
+}
+
+void launch_mlp_tc(const LaunchCtx& c, const smpc_problem_t* dP, const MlpTcWeights& w, int n_sm, int B, int N, int rows_mode, int n_flat,
+                   const double* xsrc, const int32_t* r, const uint8_t* act, const uint8_t* need, double* out11, bool want_grad) {
+  int n_rows = rows_mode == ROWS_TERMINAL ? B : rows_mode == ROWS_ALL ? B * N : rows_mode == ROWS_RECEDING ? 2 * B : n_flat;
+  if (rows_mode == ROWS_FLAT) B = n_flat;
+  if (n_rows <= 0) return;
+  const int n_tiles = (n_rows + R - 1) / R;
+  const int grid = n_tiles < n_sm ? n_tiles : n_sm;
+  mlp_tc_kernel<<<grid, TC_THREADS, TC_SMEM, c.stream>>>(dP, w, B, N, rows_mode, n_rows, xsrc, r, act, need, out11, want_grad ? 1 : 0);
+  ++*c.launches;
+}
+
+}  // namespace smpc

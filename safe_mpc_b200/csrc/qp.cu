@@ -489,6 +489,254 @@ __global__ void __launch_bounds__(32) qs_ric1_kernel(const smpc_problem_t* __res
   qs_ric1(*dP, q, blockIdx.x, w, psm + threadIdx.x);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// ric1, two warps per tile (lane = problem in both).  The sweep is a dependent instruction stream of ~2 000 instructions per
+// stage that a single warp issues at the latency of its FP64 chains (profiles/r01_qp_v7.md), so its duration -- the same for 1 or
+// 10 000 active problems -- is cut by splitting the stream, not by adding tiles:
+//   warp A (control columns):  y = P_{k+1} rb + p_{k+1}, gradient, the 15 x 5 panel, its LDL' elimination -> T, l~, p_k
+//   warp B (state block):      trailing base  M_xx + [A]' P_{k+1} [A]  for the 55 entries of the state block while A eliminates,
+//                              then  P_k = base - T_x D T_x'  once A has published T_x and D through shared memory
+// Two named barriers per stage (T published / P_k complete).  The staging buffer is released at the first barrier, so the TMA
+// fetch of the next stage runs under B's second half and A's stores.  Stage 0: B factorises P_0, solves for dx_0 and runs the
+// forward substitution with two staging buffers (the P scratch is free by then); A has exited.
+// Per-entry arithmetic and summation order are those of qs_ric1 (qp_split.cuh): results are bit-identical.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int R1X_XF = 55;                                                     // exchange: T rows 5-14 (50) + D (5)
+constexpr int R1X_FIELDS = RIC1_STAGE_FIELDS + 65 + R1X_XF;                    // 265
+constexpr int R1X_FWD = B_WV - B_RB;                                           // forward stage fetch: RB LP T (100 fields)
+constexpr int R1X_FWD1 = 136;                                                  // field offset of the second forward buffer
+static_assert(R1X_FWD1 >= R1X_FWD && R1X_FWD1 + R1X_FWD <= R1X_FIELDS, "forward buffers");
+constexpr size_t RIC1X_SMEM = sizeof(double) * R1X_FIELDS * TL + 32;
+
+__device__ __forceinline__ void r1x_bar() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
+__device__ __forceinline__ void r1x_fetch(double* dst, const double* src, int nfields, uint64_t* bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(nfields * TL * 8) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+               "r"(nfields * TL * 8), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void r1x_wait(uint64_t* bar, uint32_t& phase) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok;
+  do {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(addr), "r"(phase) : "memory");
+  } while (!ok);
+  phase ^= 1u;
+}
+
+__global__ void __launch_bounds__(64) qs_ric1x_kernel(const smpc_problem_t* __restrict__ dP, QsBufs q) {
+  extern __shared__ __align__(128) double smem[];
+  const smpc_problem_t& P = *dP;
+  const int N = q.N, tile = blockIdx.x, lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+  const int32_t* pi = q.pi + qs_pb(tile, NPI, lane);
+  const bool on = QF(pi, J_ACT) != 0;
+  if (!__any_sync(0xffffffffu, on)) return;                 // (both warps: same tile, same answer)
+  double* stg_all = smem;                                    // backward staging: fields [B_M, B_LP) at their own offsets
+  double* psm_all = smem + (size_t)RIC1_STAGE_FIELDS * TL;   // P_{k+1} (55) and p_{k+1} (10)
+  double* xch_all = psm_all + (size_t)65 * TL;               // T rows 5-14 and D of the running stage
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (size_t)R1X_FIELDS * TL);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar + 0)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar + 1)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  double* pd = q.pd + qs_pb(tile, NPD, lane);
+  const double dt = P.dt, a2 = 0.5 * P.dt * P.dt;
+  const double* gsb = q.sb + qs_blk(tile, N, 0, NSB, 0);
+  const size_t sstride = (size_t)NSB * TL;
+  const double* hc = stg_all + lane;
+  double* psm = psm_all + lane;
+  double* xch = xch_all + lane;
+  auto Pn = [&](int idx) { return QF(psm, idx); };
+  uint32_t ph0 = 0;
+  if (threadIdx.x == 0) r1x_fetch(stg_all, gsb + (size_t)N * sstride + (size_t)B_M * TL, B_LP - B_M, bar);
+  double dx[10];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) dx[i] = 0.0;
+
+  for (int k = N; k >= 0; --k) {
+    r1x_wait(bar, ph0);
+    double* fac = q.sb + qs_blk(tile, N, k, NSB, lane);
+    if (wi == 0) {
+      // ---------------- warp A: gradient, panel, elimination ----------------
+      double g[15];
+#pragma unroll
+      for (int i = 0; i < 15; ++i) g[i] = QF(hc, H_GA + i);
+      if (k < N) {
+        double rb[10], y[10];
+#pragma unroll
+        for (int j = 0; j < 10; ++j) rb[j] = QF(hc, H_RB + j);
+#pragma unroll
+        for (int i = 0; i < 10; ++i) {
+          double s = 0.0;
+#pragma unroll
+          for (int j = 0; j < 10; ++j) s += Pn(trs(i, j)) * rb[j];
+          if (on) QF(fac, F_WV + i) = s;
+          y[i] = s + QF(psm, 55 + i);
+        }
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+          g[j] += a2 * y[j] + dt * y[5 + j];
+          g[5 + j] += y[j];
+          g[10 + j] += dt * y[j] + y[5 + j];
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 5; ++i) g[i] = 0.0;
+      }
+      double pan[15][5];
+#pragma unroll
+      for (int i = 0; i < 15; ++i)
+#pragma unroll
+        for (int j = 0; j < 5; ++j)
+          if (j <= i) pan[i][j] = QF(hc, H_M + tri(i, j)) + (k < N ? qs_y(i, j, dt, a2, Pn) : 0.0);
+      double dd[5];
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        const double d = pan[j][j];
+        const double invd = d > 0.0 ? qs_rcp(d) : 0.0;
+        dd[j] = d > 0.0 ? d : 0.0;
+#pragma unroll
+        for (int i = 14; i > j; --i) {
+          const double t = pan[i][j] * invd;
+          g[i] -= t * g[j];
+#pragma unroll
+          for (int c = j + 1; c < 5; ++c)
+            if (c <= i) pan[i][c] -= t * pan[c][j];
+          pan[i][j] = t;
+        }
+        pan[j][j] = invd;
+      }
+#pragma unroll
+      for (int i = 5; i < 15; ++i)
+#pragma unroll
+        for (int j = 0; j < 5; ++j) QF(xch, (i - 5) * 5 + j) = pan[i][j];
+#pragma unroll
+      for (int j = 0; j < 5; ++j) QF(xch, 50 + j) = dd[j];
+#pragma unroll
+      for (int i = 0; i < 10; ++i) QF(psm, 55 + i) = g[5 + i];           // p_k (read by A at the next stage, by B at stage 0)
+      r1x_bar();                                                          // (1) T_x, D published; staging buffer free
+      if (lane == 0 && k > 0) r1x_fetch(stg_all, gsb + (size_t)(k - 1) * sstride + (size_t)B_M * TL, B_LP - B_M, bar);
+      if (on) {
+#pragma unroll
+        for (int i = 0; i < 15; ++i)
+#pragma unroll
+          for (int j = 0; j < 5; ++j)
+            if (j <= i) QF(fac, F_T + i * 5 + j) = pan[i][j];
+#pragma unroll
+        for (int i = 0; i < 15; ++i) QF(fac, F_LP + i) = g[i];
+      }
+      if (k == 0) asm volatile("fence.proxy.async;" ::: "memory");       // T, l~ of every stage visible to the bulk copies of the forward sweep
+      r1x_bar();                                                          // (2) P_k complete
+    } else {
+      // ---------------- warp B: state block ----------------
+      double tb[10][10];
+#pragma unroll
+      for (int i = 5; i < 15; ++i)
+#pragma unroll
+        for (int c = 5; c <= i; ++c) tb[i - 5][c - 5] = QF(hc, H_M + tri(i, c)) + (k < N ? qs_y(i, c, dt, a2, Pn) : 0.0);
+      r1x_bar();                                                          // (1)
+#pragma unroll
+      for (int i = 5; i < 15; ++i) {
+        double sdx[5];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) sdx[j] = QF(xch, (i - 5) * 5 + j) * QF(xch, 50 + j);
+#pragma unroll
+        for (int c = 5; c <= i; ++c) {
+          double v = tb[i - 5][c - 5];
+#pragma unroll
+          for (int j = 0; j < 5; ++j) v -= sdx[j] * QF(xch, (c - 5) * 5 + j);
+          tb[i - 5][c - 5] = v;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 10; ++i)
+#pragma unroll
+        for (int c = 0; c <= i; ++c) { QF(psm, tri(i, c)) = tb[i][c]; if (on) QF(fac, F_P + tri(i, c)) = tb[i][c]; }
+      if (k == 0) {
+        // factorise P_0 (kept per problem for the re-solves of ric2) and solve P_0 dx_0 = -p_0
+        double gg[10];
+#pragma unroll
+        for (int i = 0; i < 10; ++i) gg[i] = QF(psm, 55 + i);
+#pragma unroll
+        for (int j = 0; j < 10; ++j) {
+          const double d = tb[j][j];
+          const double invd = d > 0.0 ? qs_rcp(d) : 0.0;
+          tb[j][j] = invd;
+#pragma unroll
+          for (int i = 9; i > j; --i) {
+            const double t = tb[i][j] * invd;
+            gg[i] -= t * gg[j];
+#pragma unroll
+            for (int c = j + 1; c <= i; ++c) tb[i][c] -= t * tb[c][j];
+            tb[i][j] = t;
+          }
+        }
+        if (on) {
+#pragma unroll
+          for (int i = 0; i < 10; ++i)
+#pragma unroll
+            for (int c = 0; c <= i; ++c) QF(pd, D_T0 + tri(i, c)) = tb[i][c];
+        }
+#pragma unroll
+        for (int i = 9; i >= 0; --i) {
+          double acc = tb[i][i] * gg[i];
+#pragma unroll
+          for (int c = i + 1; c < 10; ++c) acc += tb[c][i] * dx[c];
+          dx[i] = tb[i][i] > 0.0 ? -acc : 0.0;
+        }
+      }
+      r1x_bar();                                                          // (2)
+    }
+  }
+  if (wi == 0) return;
+
+  // ---------------- warp B: forward substitution (affine direction), two staging buffers ----------------
+  uint32_t ph[2] = {ph0, 0};
+  double* fb[2] = {smem, smem + (size_t)R1X_FWD1 * TL};
+  if (lane == 0) r1x_fetch(fb[0], gsb + (size_t)B_RB * TL, R1X_FWD, bar + 0);
+  for (int k = 0; k <= N; ++k) {
+    __syncwarp();                                                          // every lane is done with the buffer of stage k - 1
+    if (lane == 0 && k < N) r1x_fetch(fb[(k + 1) & 1], gsb + (size_t)(k + 1) * sstride + (size_t)B_RB * TL, R1X_FWD, bar + ((k + 1) & 1));
+    r1x_wait(bar + (k & 1), ph[k & 1]);
+    const double* sb = fb[k & 1] + lane - (size_t)B_RB * TL;               // sb[f] valid for B_RB <= f < B_WV
+    double* st = q.st + qs_blk(tile, N, k, NIT, lane);
+    double du[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) du[i] = 0.0;
+    if (k < N) {
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        double ws = QF(sb, F_T + i * 5 + i) * QF(sb, F_LP + i);
+#pragma unroll
+        for (int r = 0; r < 10; ++r) ws += QF(sb, F_T + (5 + r) * 5 + i) * dx[r];
+        du[i] = -ws;
+      }
+#pragma unroll
+      for (int c = 4; c >= 1; --c)
+#pragma unroll
+        for (int i = 0; i < c; ++i) du[i] -= QF(sb, F_T + c * 5 + i) * du[c];
+    }
+    if (on) {
+#pragma unroll
+      for (int i = 0; i < 5; ++i) QF(st, I_Z + i) = du[i];
+#pragma unroll
+      for (int i = 0; i < 10; ++i) QF(st, I_Z + 5 + i) = dx[i];
+    }
+    if (k < N) {
+      double nx[10];
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        nx[j] = dx[j] + dt * dx[5 + j] + a2 * du[j] + QF(sb, H_RB + j);
+        nx[5 + j] = dx[5 + j] + dt * du[j] + QF(sb, H_RB + 5 + j);
+      }
+#pragma unroll
+      for (int j = 0; j < 10; ++j) dx[j] = nx[j];
+    }
+  }
+}
+
 __global__ void __launch_bounds__(32) qs_ric2_kernel(const smpc_problem_t* __restrict__ dP, QsBufs q) {
   extern __shared__ __align__(128) double smem[];
   TmaStage w;
@@ -576,6 +824,7 @@ struct QpSolver {
   int* h_counters = nullptr;
   cudaEvent_t ev_in = nullptr;  // inputs (records, x0) are ready on the caller's stream
   int last_iters = 0;
+  bool split_ric1 = true;       // two warps per tile in the factorising Riccati sweep (SMPC_QP_RIC1=single selects the one-warp form)
   bool coop_prep = true;        // kk >= 1: four-warp cooperative prep with TMA-staged inputs (SMPC_QP_PREP=thread selects the thread-per-stage form)
   bool profile = false;         // record one event pair per kernel of the next solves (smpc_set_profiling)
   double prof_ms[SMPC_PROF_N] = {0};
@@ -612,6 +861,8 @@ QpSolver* qp_create(int B, int N, int iter_max, cudaStream_t stream, cudaError_t
   if (e == cudaSuccess) e = cudaFuncSetAttribute(qs_prep_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PC_SMEM);
   if (const char* pe = getenv("SMPC_QP_PREP")) s->coop_prep = strcmp(pe, "thread") != 0;
   if (e == cudaSuccess) e = cudaFuncSetAttribute(qs_ric1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RIC1_SMEM);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(qs_ric1x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RIC1X_SMEM);
+  if (const char* re = getenv("SMPC_QP_RIC1")) s->split_ric1 = strcmp(re, "single") != 0;
   if (e == cudaSuccess) e = cudaFuncSetAttribute(qs_ric2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RIC2_SMEM);
   for (int g = 0; g < G && e == cudaSuccess; ++g) {
     int plo = 0, phi = 0;
@@ -749,7 +1000,16 @@ struct DeviceBackend {
     { cudaStream_t stm_ = st(false); tr0("qs_ctl_kernel", stm_); qs_ctl_kernel<<<g->T, 32, 0, stm_>>>(dP, g->q, kk, status, qp_iter, qp_status, qp_res, g->counters); tr1(stm_); }
     count();
   }
-  void ric1() { { cudaStream_t stm_ = st(true); tr0("qs_ric1_kernel", stm_); qs_ric1_kernel<<<g->T, 32, RIC1_SMEM, stm_>>>(dP, g->q); tr1(stm_); } count(); }
+  void ric1() {
+    {
+      cudaStream_t stm_ = st(true);
+      tr0("qs_ric1_kernel", stm_);
+      if (s->split_ric1) qs_ric1x_kernel<<<g->T, 64, RIC1X_SMEM, stm_>>>(dP, g->q);
+      else qs_ric1_kernel<<<g->T, 32, RIC1_SMEM, stm_>>>(dP, g->q);
+      tr1(stm_);
+    }
+    count();
+  }
   void ric2() { { cudaStream_t stm_ = st(true); tr0("qs_ric2_kernel", stm_); qs_ric2_kernel<<<g->T, 32, RIC2_SMEM, stm_>>>(dP, g->q); tr1(stm_); } count(); }
   void step(int kk, int mode) {
     if (mode == 0) { cudaStream_t stm_ = st(false); tr0("qs_step_kernel<0>", stm_); qs_step_kernel<0><<<sp_grid(), 32 * SP_WARPS, 0, stm_>>>(dP, g->q, g->T, kk); tr1(stm_); }

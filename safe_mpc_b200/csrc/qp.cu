@@ -737,6 +737,221 @@ __global__ void __launch_bounds__(64) qs_ric1x_kernel(const smpc_problem_t* __re
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Tail kernels: one WARP per problem.  The lane-per-problem sweeps above take the same time for 1 or 10 000 active problems
+// (46 dependent stages of a ~2 000-instruction stream); in the last iterations of a solve a handful of problems are left -- and
+// a problem that runs into qp_max_iter holds the whole batch for hundreds of iterations.  When few problems iterate the host
+// switches to these kernels: the lanes of a warp own the rows / entries of ONE problem, so the dependent chain of a stage is
+// ~150 instructions instead of ~2 000.  Every entry is computed with the expressions and the summation order of qs_ric1 /
+// qs_ric2 (qp_split.cuh), so a problem gets bit-identical results whichever kernel serves it.  One CTA per tile, warp w =
+// problem w of the tile; warps of finished problems exit at once.  The accesses of a warp are 8-byte reads 256 B apart (the
+// layout is made for the lane-per-problem kernels) -- irrelevant for the few hundred problems these kernels are used for.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int RT_S = 184;                      // staged fields of one stage (largest range: ric2 forward, 180)
+constexpr int RT_PB = RT_S;                    // P / p double buffer [2][65] (ric1) or pn, dx vectors (ric2)
+constexpr int RT_TX = RT_PB + 130;             // pan rows [15][5], D [5], exchange [12]
+constexpr int RT_PER_WARP = RT_TX + 75 + 5 + 12 + 4;
+constexpr int RT_WARPS = 16;                   // warps (problems) per CTA: two CTAs per tile, 128 registers per thread
+constexpr size_t RT_SMEM = sizeof(double) * RT_PER_WARP * RT_WARPS;
+
+// fields [f0, f0 + nf) of one stage of one problem: issued one stage ahead into registers (RT_NR per lane), parked in shared
+// memory when their stage starts, so that the global round trip of stage k - 1 runs under the arithmetic of stage k
+constexpr int RT_NR = 6;
+__device__ __forceinline__ void rt_issue(double (&r)[RT_NR], const double* gblock_lane, int f0, int nf, int lane) {
+#pragma unroll
+  for (int u = 0; u < RT_NR; ++u) {
+    const int f = lane + 32 * u;
+    r[u] = f < nf ? gblock_lane[(size_t)(f0 + f) * TL] : 0.0;
+  }
+}
+__device__ __forceinline__ void rt_park(double* S, const double (&r)[RT_NR], int nf, int lane) {
+#pragma unroll
+  for (int u = 0; u < RT_NR; ++u) {
+    const int f = lane + 32 * u;
+    if (f < nf) S[f] = r[u];
+  }
+}
+
+__global__ void __launch_bounds__(32 * RT_WARPS) qs_ric1t_kernel(const smpc_problem_t* __restrict__ dP, QsBufs q) {
+  extern __shared__ __align__(16) double rt_sm[];
+  const smpc_problem_t& P = *dP;
+  const int N = q.N, tile = blockIdx.x / (32 / RT_WARPS), wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pl = (blockIdx.x % (32 / RT_WARPS)) * RT_WARPS + wi;          // problem (lane of the tile) this warp serves
+  const int32_t* pi = q.pi + qs_pb(tile, NPI, pl);
+  if (!QF(pi, J_ACT)) return;
+  double* S = rt_sm + (size_t)wi * RT_PER_WARP;             // staged fields, index = field - first field of the range
+  double* Pb = S + RT_PB;                                    // [2][65]: P (55) and p (10) of stage k + 1 / k
+  double* TX = S + RT_TX;                                    // [75] multipliers, then D [5], then exchange [12]
+  double* DD = TX + 75;
+  double* X = DD + 5;
+  double* pd = q.pd + qs_pb(tile, NPD, pl);
+  const double dt = P.dt, a2 = 0.5 * P.dt * P.dt;
+  const double* gsb = q.sb + qs_blk(tile, N, 0, NSB, pl);    // stage blocks, lane offset of this problem applied
+  const size_t sstride = (size_t)NSB * TL;
+  int cur = 0;                                               // Pb[cur] = (P_{k+1}, p_{k+1})
+  double rr[RT_NR];
+  rt_issue(rr, gsb + (size_t)N * sstride, B_M, B_LP - B_M, lane);
+
+  for (int k = N; k >= 0; --k) {
+    const double* pc = Pb + cur * 65;
+    double* pn_ = Pb + (cur ^ 1) * 65;
+    auto Pn = [&](int idx) { return pc[idx]; };
+    rt_park(S, rr, B_LP - B_M, lane);                                      // M GA RB at S[field]
+    if (k > 0) rt_issue(rr, gsb + (size_t)(k - 1) * sstride, B_M, B_LP - B_M, lane);
+    __syncwarp();
+    double* fac = q.sb + qs_blk(tile, N, k, NSB, pl);
+    // y = P rb + p  (lanes 0-9)
+    if (k < N && lane < 10) {
+      double s_ = 0.0;
+#pragma unroll
+      for (int j = 0; j < 10; ++j) s_ += Pn(trs(lane, j)) * S[H_RB + j];
+      QF(fac, F_WV + lane) = s_;
+      X[lane] = s_ + pc[55 + lane];
+    }
+    __syncwarp();
+    // gradient and panel row of lane i < 15
+    double g = 0.0, pan[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    if (lane < 15) {
+      g = S[H_GA + lane];
+      if (k < N) {
+        if (lane < 5) g += a2 * X[lane] + dt * X[5 + lane];
+        else if (lane < 10) g += X[lane - 5];
+        else g += dt * X[lane - 10] + X[lane - 5];
+      } else if (lane < 5) g = 0.0;
+#pragma unroll
+      for (int j = 0; j < 5; ++j)
+        if (j <= lane) pan[j] = S[H_M + tri(lane, j)] + (k < N ? qs_y(lane, j, dt, a2, Pn) : 0.0);
+    }
+    __syncwarp();                                                          // X (y) consumed
+    // LDL' elimination of the control columns: lane i owns row i
+    double dd[5];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      if (lane >= j && lane <= 4) X[lane] = pan[j];                        // column j of the rows j..4, not yet scaled
+      if (lane == j) X[8] = g;
+      __syncwarp();
+      const double d = X[j];
+      const double invd = d > 0.0 ? qs_rcp(d) : 0.0;
+      dd[j] = d > 0.0 ? d : 0.0;
+      if (lane > j && lane < 15) {
+        const double t = pan[j] * invd;
+        g -= t * X[8];
+#pragma unroll
+        for (int c = j + 1; c < 5; ++c)
+          if (c <= lane) pan[c] -= t * X[c];
+        pan[j] = t;
+      }
+      if (lane == j) pan[j] = invd;
+      __syncwarp();
+    }
+    if (lane < 15) {
+#pragma unroll
+      for (int j = 0; j < 5; ++j)
+        if (j <= lane) { TX[lane * 5 + j] = pan[j]; QF(fac, F_T + lane * 5 + j) = pan[j]; }
+      QF(fac, F_LP + lane) = g;
+      if (lane >= 5) pn_[55 + lane - 5] = g;                               // p_k
+    }
+    if (lane < 5) DD[lane] = dd[lane];
+    __syncwarp();
+    // P_k = trailing block - T_x D T_x': entry e = tri(r, s_) of the state block, two entries per lane
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int e = lane + 32 * h;
+      if (e < 55) {
+        int r = 0;
+        while (tri(r + 1, 0) <= e) ++r;
+        const int c_ = e - tri(r, 0);
+        const int i = 5 + r, c = 5 + c_;
+        double v = S[H_M + tri(i, c)] + (k < N ? qs_y(i, c, dt, a2, Pn) : 0.0);
+#pragma unroll
+        for (int j = 0; j < 5; ++j) v -= (TX[i * 5 + j] * DD[j]) * TX[c * 5 + j];
+        pn_[e] = v;
+        QF(fac, F_P + e) = v;
+      }
+    }
+    __syncwarp();
+    cur ^= 1;
+  }
+  // stage 0: factorise P_0 (kept for ric2) and solve P_0 dx_0 = -p_0   (one lane; once per sweep)
+  double* DX = X;                                                          // [10]
+  if (lane == 0) {
+    const double* p0 = Pb + cur * 65;
+    double m[10][10], gg[10], dx[10];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+      gg[i] = p0[55 + i];
+#pragma unroll
+      for (int c = 0; c <= i; ++c) m[i][c] = p0[tri(i, c)];
+    }
+#pragma unroll
+    for (int j = 0; j < 10; ++j) {
+      const double d = m[j][j];
+      const double invd = d > 0.0 ? qs_rcp(d) : 0.0;
+      m[j][j] = invd;
+#pragma unroll
+      for (int i = 9; i > j; --i) {
+        const double t = m[i][j] * invd;
+        gg[i] -= t * gg[j];
+#pragma unroll
+        for (int c = j + 1; c <= i; ++c) m[i][c] -= t * m[c][j];
+        m[i][j] = t;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 10; ++i)
+#pragma unroll
+      for (int c = 0; c <= i; ++c) QF(pd, D_T0 + tri(i, c)) = m[i][c];
+#pragma unroll
+    for (int i = 9; i >= 0; --i) {
+      double acc = m[i][i] * gg[i];
+#pragma unroll
+      for (int c = i + 1; c < 10; ++c) acc += m[c][i] * dx[c];
+      dx[i] = m[i][i] > 0.0 ? -acc : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < 10; ++i) DX[i] = dx[i];
+  }
+  __threadfence_block();
+  __syncwarp();
+  // forward substitution (affine direction): lanes 0-4 own du, lanes 0-9 own dx
+  double* ZZ = TX;                                                         // [15] dz of the running stage
+  double* DU = TX + 16;                                                    // [5]
+  rt_issue(rr, gsb, B_RB, B_WV - B_RB, lane);
+  for (int k = 0; k <= N; ++k) {
+    rt_park(S, rr, B_WV - B_RB, lane);                                      // RB LP T at S[field - B_RB]
+    if (k < N) rt_issue(rr, gsb + (size_t)(k + 1) * sstride, B_RB, B_WV - B_RB, lane);
+    __syncwarp();
+    const double* sb = S - B_RB;
+    double du = 0.0;
+    if (k < N && lane < 5) {
+      double ws = sb[F_T + lane * 5 + lane] * sb[F_LP + lane];
+#pragma unroll
+      for (int r = 0; r < 10; ++r) ws += sb[F_T + (5 + r) * 5 + lane] * DX[r];
+      du = -ws;
+    }
+    if (k < N) {
+      // du[i] -= T[c][i] du[c] for c = 4 .. 1, i < c (the order of qs_ric1)
+#pragma unroll
+      for (int c = 4; c >= 1; --c) {
+        const double duc = __shfl_sync(0xffffffffu, du, c);
+        if (lane < c) du -= sb[F_T + c * 5 + lane] * duc;
+      }
+    }
+    if (lane < 5) { ZZ[lane] = du; DU[lane] = du; }
+    if (lane < 10) ZZ[5 + lane] = DX[lane];
+    __syncwarp();
+    double nx = 0.0;
+    if (k < N && lane < 10) {
+      if (lane < 5) nx = DX[lane] + dt * DX[5 + lane] + a2 * DU[lane] + sb[H_RB + lane];
+      else nx = DX[lane] + dt * DU[lane - 5] + sb[H_RB + lane];
+    }
+    if (lane < 15) QF(q.st + qs_blk(tile, N, k, NIT, pl), I_Z + lane) = ZZ[lane];
+    __syncwarp();
+    if (k < N && lane < 10) DX[lane] = nx;
+    __syncwarp();
+  }
+}
+
 __global__ void __launch_bounds__(32) qs_ric2_kernel(const smpc_problem_t* __restrict__ dP, QsBufs q) {
   extern __shared__ __align__(128) double smem[];
   TmaStage w;
@@ -824,6 +1039,7 @@ struct QpSolver {
   int* h_counters = nullptr;
   cudaEvent_t ev_in = nullptr;  // inputs (records, x0) are ready on the caller's stream
   int last_iters = 0;
+  int tail_max = 384;           // a tile group with at most this many problems still iterating is served by the warp-per-problem sweeps (0: never)
   bool split_ric1 = true;       // two warps per tile in the factorising Riccati sweep (SMPC_QP_RIC1=single selects the one-warp form)
   bool coop_prep = true;        // kk >= 1: four-warp cooperative prep with TMA-staged inputs (SMPC_QP_PREP=thread selects the thread-per-stage form)
   bool profile = false;         // record one event pair per kernel of the next solves (smpc_set_profiling)
@@ -863,6 +1079,8 @@ QpSolver* qp_create(int B, int N, int iter_max, cudaStream_t stream, cudaError_t
   if (e == cudaSuccess) e = cudaFuncSetAttribute(qs_ric1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RIC1_SMEM);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(qs_ric1x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RIC1X_SMEM);
   if (const char* re = getenv("SMPC_QP_RIC1")) s->split_ric1 = strcmp(re, "single") != 0;
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(qs_ric1t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RT_SMEM);
+  if (const char* te = getenv("SMPC_QP_TAIL")) s->tail_max = atoi(te);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(qs_ric2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RIC2_SMEM);
   for (int g = 0; g < G && e == cudaSuccess; ++g) {
     int plo = 0, phi = 0;
@@ -1004,7 +1222,8 @@ struct DeviceBackend {
     {
       cudaStream_t stm_ = st(true);
       tr0("qs_ric1_kernel", stm_);
-      if (s->split_ric1) qs_ric1x_kernel<<<g->T, 64, RIC1X_SMEM, stm_>>>(dP, g->q);
+      if (n_active_last <= s->tail_max) qs_ric1t_kernel<<<g->T * (32 / RT_WARPS), 32 * RT_WARPS, RT_SMEM, stm_>>>(dP, g->q);
+      else if (s->split_ric1) qs_ric1x_kernel<<<g->T, 64, RIC1X_SMEM, stm_>>>(dP, g->q);
       else qs_ric1_kernel<<<g->T, 32, RIC1_SMEM, stm_>>>(dP, g->q);
       tr1(stm_);
     }

@@ -952,6 +952,164 @@ __global__ void __launch_bounds__(32 * RT_WARPS) qs_ric1t_kernel(const smpc_prob
   }
 }
 
+// ric2 for the tail: one warp per problem, lanes 0-15 carry the corrector direction, lanes 16-31 the centering direction
+// (row / entry index = lane & 15).  Expressions and summation order of qs_ric2.
+__global__ void __launch_bounds__(32 * RT_WARPS) qs_ric2t_kernel(const smpc_problem_t* __restrict__ dP, QsBufs q) {
+  extern __shared__ __align__(16) double rt_sm[];
+  const smpc_problem_t& P = *dP;
+  const int N = q.N, tile = blockIdx.x / (32 / RT_WARPS), wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pl = (blockIdx.x % (32 / RT_WARPS)) * RT_WARPS + wi;
+  const int32_t* pi = q.pi + qs_pb(tile, NPI, pl);
+  if (!QF(pi, J_ACT)) return;
+  const int v = lane >> 4, i = lane & 15;                   // direction, row
+  const unsigned hb = lane & 16;                             // first lane of this half warp
+  double* S = rt_sm + (size_t)wi * RT_PER_WARP;
+  double* YV = S + RT_PB;                                    // [2][10] y, then pn
+  double* PN = YV + 20;                                      // [2][10]
+  double* DXV = PN + 20;                                     // [2][10]
+  double* DUV = DXV + 20;                                    // [2][5]
+  double* T0 = DUV + 10;                                     // [55] factor of P_0
+  double* pd = q.pd + qs_pb(tile, NPD, pl);
+  const double dt = P.dt, a2 = 0.5 * P.dt * P.dt;
+  const double* gsb = q.sb + qs_blk(tile, N, 0, NSB, pl);
+  const size_t sstride = (size_t)NSB * TL;
+  const int n1 = B_P - B_GA, n2 = NSB - B_V1;
+
+  // ---- sigma from the affine step statistics (sums over the stages in stage order, like qs_reduce_step) ----
+  double sigmu;
+  {
+    double* RS = S;                                          // [3][N + 1]
+    for (int k = lane; k <= N; k += 32) {
+      const double* stp = q.stp + qs_blk(tile, N, k, NSTP, pl);
+      RS[k] = QF(stp, S_ALPHA); RS[(N + 1) + k] = QF(stp, S_LIN); RS[2 * (N + 1) + k] = QF(stp, S_QUAD);
+    }
+    __syncwarp();
+    double sm_ = 0.0;
+    if (lane == 0) {
+      double alpha = 1.0, s_lin = 0.0, s_quad = 0.0;
+      for (int k = 0; k <= N; ++k) { alpha = fmin(alpha, RS[k]); s_lin += RS[(N + 1) + k]; s_quad += RS[2 * (N + 1) + k]; }
+      const double mu = QF(pd, D_MU);
+      const double mu_aff = mu + (alpha * s_lin + alpha * alpha * s_quad) / QF(pi, J_NC);
+      double sigma = mu_aff / mu; sigma = sigma * sigma * sigma;
+      sm_ = sigma * mu;
+      QF(pd, D_MUAFF) = mu_aff; QF(pd, D_SIGMU) = sm_;
+    }
+    sigmu = __shfl_sync(0xffffffffu, sm_, 0);
+    __syncwarp();
+  }
+  if (i < 10) { PN[v * 10 + i] = 0.0; DXV[v * 10 + i] = 0.0; }
+  for (int e = lane; e < 55; e += 32) T0[e] = QF(pd, D_T0 + e);
+  double rr[RT_NR];
+  // backward stage fields: [B_GA, B_P) at S[f - B_GA], [B_V1, NSB) at S[n1 + f - B_V1]
+  auto issue_b = [&](int k) {
+    const double* blk = gsb + (size_t)k * sstride;
+#pragma unroll
+    for (int u = 0; u < RT_NR; ++u) {
+      const int f = lane + 32 * u;
+      rr[u] = f < n1 ? blk[(size_t)(B_GA + f) * TL] : (f < n1 + n2 ? blk[(size_t)(B_V1 + f - n1) * TL] : 0.0);
+    }
+  };
+  issue_b(N);
+  for (int k = N; k >= 0; --k) {
+    rt_park(S, rr, n1 + n2, lane);
+    if (k > 0) issue_b(k - 1);
+    __syncwarp();
+    const double* sb = S - B_GA;                              // sb[f] valid for B_GA <= f < B_P
+    const double* vv = S + n1 - B_V1;                         // vv[f] valid for B_V1 <= f < NSB
+    double* fac = q.sb + qs_blk(tile, N, k, NSB, pl);
+    if (k < N && i < 10) YV[v * 10 + i] = sb[F_WV + i] + PN[v * 10 + i];
+    __syncwarp();
+    double g = 0.0;
+    if (i < 15) {
+      const double ga = sb[H_GA + i], s2 = sigmu * vv[V_2 + i];
+      g = v == 0 ? ga + vv[V_1 + i] - s2 : ga + 0.0 - s2;
+      if (k < N) {
+        const double* y = YV + v * 10;
+        if (i < 5) g += a2 * y[i] + dt * y[5 + i];
+        else if (i < 10) g += y[i - 5];
+        else g += dt * y[i - 10] + y[i - 5];
+      } else if (i < 5) g = 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      const double gj = __shfl_sync(0xffffffffu, g, hb | j);
+      if (i > j && i < 15) g -= sb[F_T + i * 5 + j] * gj;
+    }
+    if (i < 15) QF(fac, (v == 0 ? F_LP : F_LP2) + i) = g;
+    __syncwarp();                                             // y consumed by every lane
+    if (i >= 5 && i < 15) PN[v * 10 + i - 5] = g;
+    __syncwarp();
+  }
+  // stage 0: P_0 dx_0 = -p_0 with the factor kept by ric1 (one lane per direction)
+  if (i == 0) {
+    double pn[10], dx[10];
+#pragma unroll
+    for (int r = 0; r < 10; ++r) pn[r] = PN[v * 10 + r];
+#pragma unroll
+    for (int j = 0; j < 10; ++j)
+#pragma unroll
+      for (int r = j + 1; r < 10; ++r) pn[r] -= T0[tri(r, j)] * pn[j];
+#pragma unroll
+    for (int r = 9; r >= 0; --r) {
+      const double invd = T0[tri(r, r)];
+      double acc = invd * pn[r];
+#pragma unroll
+      for (int c = r + 1; c < 10; ++c) acc += T0[tri(c, r)] * dx[c];
+      dx[r] = invd > 0.0 ? -acc : 0.0;
+    }
+#pragma unroll
+    for (int r = 0; r < 10; ++r) DXV[v * 10 + r] = dx[r];
+  }
+  __syncwarp();
+  // forward: stages fetch RB LP T WV P LP2 = [B_RB, B_V1) at S[f - B_RB]
+  rt_issue(rr, gsb, B_RB, B_V1 - B_RB, lane);
+  for (int k = 0; k <= N; ++k) {
+    rt_park(S, rr, B_V1 - B_RB, lane);
+    if (k < N) rt_issue(rr, gsb + (size_t)(k + 1) * sstride, B_RB, B_V1 - B_RB, lane);
+    __syncwarp();
+    const double* sb = S - B_RB;
+    const double* dx = DXV + v * 10;
+    const int lp = v == 0 ? F_LP : F_LP2;
+    double* sto = v == 0 ? q.st + qs_blk(tile, N, k, NIT, pl) : q.st2 + qs_blk(tile, N, k, NS2, pl);
+    // multiplier step of the link k-1 -> k:  dpi = P_k dx_k + p_k
+    if (i < 10) {
+      double s_ = 0.0;
+      if (k > 0) {
+        s_ = sb[lp + 5 + i];
+#pragma unroll
+        for (int j = 0; j < 10; ++j) s_ += sb[F_P + trs(i, j)] * dx[j];
+      }
+      QF(sto, I_PIM + i) = s_;
+    }
+    double du = 0.0;
+    if (k < N && i < 5) {
+      double ws = sb[F_T + i * 5 + i] * sb[lp + i];
+#pragma unroll
+      for (int r = 0; r < 10; ++r) ws += sb[F_T + (5 + r) * 5 + i] * dx[r];
+      du = -ws;
+    }
+    if (k < N) {
+#pragma unroll
+      for (int c = 4; c >= 1; --c) {
+        const double duc = __shfl_sync(0xffffffffu, du, hb | c);
+        if (i < c) du -= sb[F_T + c * 5 + i] * duc;
+      }
+    }
+    if (i < 5) { DUV[v * 5 + i] = du; QF(sto, I_Z + i) = du; }
+    if (i < 10) QF(sto, I_Z + 5 + i) = dx[i];
+    __syncwarp();
+    double nx = 0.0;
+    if (k < N && i < 10) {
+      const double* duv = DUV + v * 5;
+      if (i < 5) nx = dx[i] + dt * dx[5 + i] + a2 * duv[i] + sb[H_RB + i];
+      else nx = dx[i] + dt * duv[i - 5] + sb[H_RB + i];
+    }
+    __syncwarp();
+    if (k < N && i < 10) DXV[v * 10 + i] = nx;
+    __syncwarp();
+  }
+}
+
 __global__ void __launch_bounds__(32) qs_ric2_kernel(const smpc_problem_t* __restrict__ dP, QsBufs q) {
   extern __shared__ __align__(128) double smem[];
   TmaStage w;
@@ -1080,6 +1238,7 @@ QpSolver* qp_create(int B, int N, int iter_max, cudaStream_t stream, cudaError_t
   if (e == cudaSuccess) e = cudaFuncSetAttribute(qs_ric1x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RIC1X_SMEM);
   if (const char* re = getenv("SMPC_QP_RIC1")) s->split_ric1 = strcmp(re, "single") != 0;
   if (e == cudaSuccess) e = cudaFuncSetAttribute(qs_ric1t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RT_SMEM);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(qs_ric2t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RT_SMEM);
   if (const char* te = getenv("SMPC_QP_TAIL")) s->tail_max = atoi(te);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(qs_ric2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RIC2_SMEM);
   for (int g = 0; g < G && e == cudaSuccess; ++g) {
@@ -1229,7 +1388,16 @@ struct DeviceBackend {
     }
     count();
   }
-  void ric2() { { cudaStream_t stm_ = st(true); tr0("qs_ric2_kernel", stm_); qs_ric2_kernel<<<g->T, 32, RIC2_SMEM, stm_>>>(dP, g->q); tr1(stm_); } count(); }
+  void ric2() {
+    {
+      cudaStream_t stm_ = st(true);
+      tr0("qs_ric2_kernel", stm_);
+      if (n_active_last <= s->tail_max) qs_ric2t_kernel<<<g->T * (32 / RT_WARPS), 32 * RT_WARPS, RT_SMEM, stm_>>>(dP, g->q);
+      else qs_ric2_kernel<<<g->T, 32, RIC2_SMEM, stm_>>>(dP, g->q);
+      tr1(stm_);
+    }
+    count();
+  }
   void step(int kk, int mode) {
     if (mode == 0) { cudaStream_t stm_ = st(false); tr0("qs_step_kernel<0>", stm_); qs_step_kernel<0><<<sp_grid(), 32 * SP_WARPS, 0, stm_>>>(dP, g->q, g->T, kk); tr1(stm_); }
     else if (mode == 1) { cudaStream_t stm_ = st(false); tr0("qs_step_kernel<1>", stm_); qs_step_kernel<1><<<sp_grid(), 32 * SP_WARPS, 0, stm_>>>(dP, g->q, g->T, kk); tr1(stm_); }

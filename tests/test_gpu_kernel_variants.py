@@ -1,0 +1,70 @@
+"""The QP solver picks between kernel forms at run time (csrc/qp.cu): cooperative / thread-per-stage prep by the active fraction,
+two-warp / one-warp factorising sweep, lane-per-problem / warp-per-problem (tail) Riccati sweeps by the active count.  Small test
+batches would only ever see the tail forms, so every form is forced here through the development switches and checked against the
+oracle; the Riccati forms share expressions and summation order and must agree bit for bit."""
+import os
+
+import numpy as np
+import pytest
+
+from tests.common import make_problem, start_states, rollout_guess
+
+pytestmark = pytest.mark.gpu
+
+B, N = 160, 30
+
+
+def _solve(controller, env):
+    from safe_mpc_b200.engine import Engine
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        prob, params, md = make_problem(controller, N=N)
+        eng = Engine(prob, B, 0)            # the switches are read when the handle is created
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    x0 = start_states(B, seed=21)
+    xg, ug = rollout_guess(x0, N, params.dt, seed=22, scale=1.0)
+    eng.set_guess(xg, ug)
+    st = eng.rti_solve(x0)
+    xt, ut = eng.get_temp()
+    from safe_mpc_b200 import abi
+    it = eng.get_state(abi.STATE_QP_ITER)
+    eng.close()
+    return st, xt, ut, it, (prob, params, x0, xg, ug)
+
+
+@pytest.mark.parametrize('controller', ['st', 'receding', 'htwa'])
+def test_riccati_forms_agree_bitwise_and_with_the_oracle(controller):
+    from oracle.oracle import Oracle
+    tail = _solve(controller, {'SMPC_QP_TAIL': '100000'})                       # warp-per-problem sweeps from the first iteration
+    bulk2 = _solve(controller, {'SMPC_QP_TAIL': '0'})                           # lane-per-problem sweeps, two-warp factorisation
+    bulk1 = _solve(controller, {'SMPC_QP_TAIL': '0', 'SMPC_QP_RIC1': 'single'}) # one-warp factorisation
+    for other in (bulk2, bulk1):
+        assert np.array_equal(tail[0], other[0]) and np.array_equal(tail[3], other[3])
+        assert np.array_equal(tail[1], other[1]) and np.array_equal(tail[2], other[2])
+    prob, params, x0, xg, ug = tail[4]
+    orc = Oracle(prob, B, 0)
+    orc.set_guess(xg, ug)
+    st_o = orc.rti_solve(x0)
+    xt_o, ut_o = orc.get_temp()
+    assert (st_o == tail[0]).all()
+    ok = st_o == 0
+    assert ok.any()
+    assert np.abs(tail[1][ok] - xt_o[ok]).max() <= 1e-6 * max(1.0, np.abs(xt_o[ok]).max())
+    assert np.abs(tail[2][ok] - ut_o[ok]).max() <= 1e-6 * max(1.0, np.abs(ut_o[ok]).max())
+
+
+def test_prep_forms_agree(controller='st'):
+    coop = _solve(controller, {'SMPC_QP_TAIL': '0'})
+    thread = _solve(controller, {'SMPC_QP_TAIL': '0', 'SMPC_QP_PREP': 'thread'})
+    assert np.array_equal(coop[0], thread[0])
+    ok = coop[0] == 0
+    # same arithmetic per term, different order of the sums over the row groups
+    assert np.abs(coop[1][ok] - thread[1][ok]).max() <= 1e-8 * max(1.0, np.abs(coop[1][ok]).max())
+    assert np.abs(coop[2][ok] - thread[2][ok]).max() <= 1e-8 * max(1.0, np.abs(coop[2][ok]).max())
+    assert np.abs(coop[3].astype(int) - thread[3].astype(int)).max() <= 1

@@ -1365,8 +1365,9 @@ struct DeviceBackend {
       tr0("qs_prep_kernel", stm_);
       if (kk == 0) qs_prep_kernel<true><<<grid, 32 * PREP_WARPS, PREP_SMEM, stm_>>>(dP, g->q, g->T, kk);
       // the cooperative form stages whole (tile, stage) blocks, the thread-per-stage form only touches the lanes that still iterate:
-      // measured break-even at about half of the problems active (full launch 0.57 ms against 1.02 ms)
-      else if (s->coop_prep && 2 * n_active_last >= 32 * g->T) qs_prep_coop_kernel<<<g->T * (s->N + 1), 32 * PC_WARPS, PC_SMEM, stm_>>>(dP, g->q, g->T, kk);
+      // measured break-even at about half of the problems active (full launch 0.57 ms against 1.02 ms).  In the deep tail (a handful of
+      // tiles) throughput does not matter and the cooperative form has the shorter critical path (33 against 43 us)
+      else if (s->coop_prep && (2 * n_active_last >= 32 * g->T || n_active_last <= s->tail_max)) qs_prep_coop_kernel<<<g->T * (s->N + 1), 32 * PC_WARPS, PC_SMEM, stm_>>>(dP, g->q, g->T, kk);
       else qs_prep_kernel<false><<<grid, 32 * PREP_WARPS, PREP_SMEM, stm_>>>(dP, g->q, g->T, kk);
       tr1(stm_);
     }

@@ -59,7 +59,8 @@ enum {
   SMPC_CTRL_RECEDING = 5,       /* RecedingController         controller.py:404-502 */
   SMPC_CTRL_REAL_RECEDING = 6,  /* RealReceding               controller.py:504-565 */
   SMPC_CTRL_EVERYWHERE = 7,     /* ControllerSafeSetEverywhere controller.py:646-689 */
-  SMPC_CTRL_BACKUP = 8          /* SafeBackupController       controller.py:692-712 */
+  SMPC_CTRL_BACKUP = 8,         /* SafeBackupController       controller.py:692-712 */
+  SMPC_CTRL_PARALLEL = 9        /* ParallelController         controller.py:567-644 (N solves per step, one per candidate node) */
 };
 
 /* which stages carry the viability-network row (safe_set.py:82-104) */
@@ -67,7 +68,8 @@ enum {
   SMPC_NN_NONE = 0,
   SMPC_NN_TERMINAL = 1,         /* ST / STWA / HTWA / RealReceding                  */
   SMPC_NN_RECEDING = 2,         /* stages 1..N-1 gated by p[4], terminal always on */
-  SMPC_NN_EVERYWHERE = 3        /* stages 1..N, never gated                        */
+  SMPC_NN_EVERYWHERE = 3,       /* stages 1..N, never gated                        */
+  SMPC_NN_PARALLEL = 4          /* stages 1..N, all hard, only the candidate node of the running solve is on (controller.py:578-588) */
 };
 
 enum { SMPC_NN_STRICT = 0, SMPC_NN_TF32X3 = 1 };

@@ -50,7 +50,7 @@ struct orc_handle {
   int mlp_fp32 = 0;
   std::vector<double> xg, ug, xt, ut, lin, plant_inertial, tau_noise, x_viable;
   std::vector<double> qp_z, qp_pi, qp_lam, qp_t, qp_res;
-  std::vector<int32_t> fails, r, status, qp_iter, qp_status, cur_step;
+  std::vector<int32_t> fails, r, status, qp_iter, qp_status, cur_step, cand;
   std::vector<Workspace> ws;   // one per thread
 };
 
@@ -103,7 +103,7 @@ bool collision_free(const orc_problem_t& P, const double* x) {
 bool stage_has_nn(const orc_problem_t& P, int k) {
   switch (P.nn_rows) {
     case SMPC_NN_TERMINAL: return k == P.N;
-    case SMPC_NN_RECEDING: case SMPC_NN_EVERYWHERE: return k >= 1;
+    case SMPC_NN_RECEDING: case SMPC_NN_EVERYWHERE: case SMPC_NN_PARALLEL: return k >= 1;
     default: return false;
   }
 }
@@ -268,6 +268,7 @@ void stage_box(const orc_handle& h, int b, int k, const double* x0, double* lo, 
 bool gate_on(const orc_handle& h, int b, int k) {
   const orc_problem_t& P = h.P;
   if (P.nn_rows == SMPC_NN_RECEDING && k < P.N) return k == h.r[b];   // controller.py:452-469
+  if (P.nn_rows == SMPC_NN_PARALLEL) return k == h.cand[b];           // controller.py:578-588 (constrain_n)
   return true;
 }
 
@@ -378,8 +379,55 @@ bool check_safe(const orc_handle& h, const double* x) {     // safe_set.py:61-68
   return (0.0 - h.P.tol_safe <= c) && (c <= 1e6 + h.P.tol_safe);
 }
 
+// ParallelController.step (controller.py:614-640): one solve per candidate node n = N .. 1 (sing_step :596-612), best node kept
+bool parallel_step_one(orc_handle& h, int b, const double* x, double* u, Workspace& W) {
+  const orc_problem_t& P = h.P;
+  const int N = P.N;
+  double* xg = &h.xg[(size_t)b * (N + 1) * NX];
+  double* ug = &h.ug[(size_t)b * N * NU];
+  double* xt = &h.xt[(size_t)b * (N + 1) * NX];
+  double* ut = &h.ut[(size_t)b * N * NU];
+  for (int k = 0; k < N; ++k) f_disc(P.dt, xg + k * NX, ug + k * NU, xg + (k + 1) * NX);      // guessCorrection
+  int node_success = 0;
+  std::vector<double> bx, bu;
+  for (int n = N; n >= 1; --n) {
+    h.cand[b] = n;                                                   // constrain_n(n)
+    const int status = rti_solve_one(h, b, x, W);
+    int checked_r = 0;                                               // check_safe_n (:590-595)
+    for (int i = h.r[b]; i <= N; ++i) if (check_safe(h, xt + i * NX)) checked_r = i;
+    int result = 0;
+    if (status == 0) {
+      const int constr_ver = checked_r >= h.r[b] ? checked_r : std::min(n, (int)h.r[b]);
+      if (constr_ver - h.r[b] >= 0 && check_state_constraints_traj(h, b)) result = constr_ver;
+    }
+    if (result > node_success) {
+      node_success = result;
+      bx.assign(xt, xt + (size_t)(N + 1) * NX); bu.assign(ut, ut + (size_t)N * NU);
+      if (result == N) break;
+    }
+  }
+  if (node_success > 1) {
+    h.r[b] = node_success;
+    std::copy(bx.begin(), bx.end(), xt); std::copy(bu.begin(), bu.end(), ut);
+    h.fails[b] = 0;
+  } else {
+    h.fails[b] += 1;
+    if (h.r[b] == 1) {
+      for (int i = 0; i < NX; ++i) h.x_viable[(size_t)b * NX + i] = xg[NX + i];
+      h.r[b] = N;
+      for (int i = 0; i < NU; ++i) u[i] = ug[i];
+      return true;
+    }
+  }
+  h.r[b] -= 1;
+  h.cur_step[b] += 1;
+  provide_control(h, b, u);
+  return false;
+}
+
 // controller.step(x) for problem b; returns abort flag
 bool controller_step_one(orc_handle& h, int b, const double* x, double* u, Workspace& W) {
+  if (h.P.controller == SMPC_CTRL_PARALLEL) return parallel_step_one(h, b, x, u, W);
   const orc_problem_t& P = h.P;
   const int N = P.N;
   double* xg = &h.xg[(size_t)b * (N + 1) * NX];
@@ -493,7 +541,7 @@ int orc_create(const orc_problem_t* prob, int32_t batch, int32_t threads, orc_ha
   h->qp_z.assign((size_t)B * (N + 1) * 15, 0.0); h->qp_pi.assign((size_t)B * N * NX, 0.0);
   h->qp_lam.assign((size_t)B * (N + 1) * SMPC_QP_NC, 0.0); h->qp_t = h->qp_lam;
   h->qp_res.assign((size_t)B * 5, 0.0);
-  h->fails.assign(B, 0); h->r.assign(B, N); h->status.assign(B, 4); h->qp_iter.assign(B, 0); h->qp_status.assign(B, 0); h->cur_step.assign(B, 0);
+  h->fails.assign(B, 0); h->r.assign(B, N); h->cand.assign(B, N); h->status.assign(B, 4); h->qp_iter.assign(B, 0); h->qp_status.assign(B, 0); h->cur_step.assign(B, 0);
   h->ws.resize(h->threads);
   *out = h;
   return SMPC_OK;

@@ -28,8 +28,8 @@ OUT_CONVERGED, OUT_COLLIDED, OUT_ABORTED = 1, 2, 4
 HOST, DEVICE = 0, 1
 
 CTRL = {'naive': 0, 'zerovel': 1, 'st': 2, 'stwa': 3, 'htwa': 4, 'receding': 5, 'real_receding': 6,
-        'constraint_everywhere': 7, 'backup': 8}
-NN_NONE, NN_TERMINAL, NN_RECEDING, NN_EVERYWHERE = 0, 1, 2, 3
+        'constraint_everywhere': 7, 'backup': 8, 'parallel': 9}
+NN_NONE, NN_TERMINAL, NN_RECEDING, NN_EVERYWHERE, NN_PARALLEL = 0, 1, 2, 3, 4
 NN_PRECISION = {'strict': 0, 'tf32x3': 1}
 COST_ZERO, COST_EXT, COST_NLS = 0, 1, 2
 STATE_FAILS, STATE_R, STATE_STATUS, STATE_QP_ITER, STATE_QP_STATUS = 0, 1, 2, 3, 4

@@ -169,6 +169,13 @@ class RealReceding(STWAController):                      # controller.py:504-565
     engine_name = 'real_receding'
 
 
+class ParallelController(RecedingController):            # controller.py:567-644
+    """One solve per candidate node n = N .. 1 in every step (sing_step, controller.py:596-612), the best node kept; the engine batches
+    each candidate over the problems that have not reached n = N yet.  Like the reference, ``get_controller`` has no key for it
+    (utils.py:64-75): construct it directly."""
+    engine_name = 'parallel'
+
+
 class ControllerSafeSetEverywhere(STWAController):       # controller.py:646-689
     engine_name = 'constraint_everywhere'
 

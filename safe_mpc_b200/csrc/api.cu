@@ -40,6 +40,12 @@ struct smpc_handle {
   bool solved = false;
   int32_t *fails = nullptr, *r = nullptr, *status = nullptr, *qp_iter = nullptr, *qp_status = nullptr, *cur_step = nullptr;
   uint8_t *act = nullptr, *need_scan = nullptr, *abort_flag = nullptr;
+  // ParallelController (controller.py:567-644): candidate node of the running solve, best node so far and its trajectory
+  int32_t *cand = nullptr, *par_best = nullptr;
+  uint8_t *par_done = nullptr, *par_act = nullptr;
+  double *par_xt = nullptr, *par_ut = nullptr;
+  int* par_open = nullptr;          // device: problems that still have candidates to try
+  int* h_par_open = nullptr;        // pinned
   // staging for host callers
   void* stage = nullptr;
   size_t stage_bytes = 0;
@@ -124,8 +130,9 @@ int mask_in(smpc_handle* h, const uint8_t* active, int mem, const uint8_t** out)
 void run_mlp(smpc_handle* h, int B, int N, int mode, int n_flat, const double* xsrc, const uint8_t* act, const uint8_t* need, double* out11,
              bool want_grad) {
   LaunchCtx c = h->ctx();
-  if (h->P.nn_precision == SMPC_NN_TF32X3) launch_mlp_tc(c, h->dP, h->wtc, h->n_sm, B, N, mode, n_flat, xsrc, h->r, act, need, out11, want_grad);
-  else launch_mlp(c, h->dP, h->w, B, N, mode, n_flat, xsrc, h->r, act, need, out11, want_grad);
+  const int32_t* ridx = h->P.nn_rows == SMPC_NN_PARALLEL ? h->cand : h->r;      // stage index of the gated row
+  if (h->P.nn_precision == SMPC_NN_TF32X3) launch_mlp_tc(c, h->dP, h->wtc, h->n_sm, B, N, mode, n_flat, xsrc, ridx, act, need, out11, want_grad);
+  else launch_mlp(c, h->dP, h->w, B, N, mode, n_flat, xsrc, ridx, act, need, out11, want_grad);
 }
 
 // linearise + QP for the problems in `act` at the stored guess: AbstractController.solve (controller.py:136-167)
@@ -134,10 +141,10 @@ int solve_pipeline(smpc_handle* h, const double* x0_dev, const uint8_t* act) {
   const int B = h->B, N = h->N;
   if (h->timed) cudaEventRecord(h->ev[0], h->stream);
   if (h->P.nn_rows != SMPC_NN_NONE) {
-    const int mode = h->P.nn_rows == SMPC_NN_TERMINAL ? ROWS_TERMINAL : (h->P.nn_rows == SMPC_NN_EVERYWHERE ? ROWS_ALL : ROWS_RECEDING);
+    const int mode = h->P.nn_rows == SMPC_NN_TERMINAL ? ROWS_TERMINAL : (h->P.nn_rows == SMPC_NN_EVERYWHERE ? ROWS_ALL : (h->P.nn_rows == SMPC_NN_PARALLEL ? ROWS_CAND : ROWS_RECEDING));
     run_mlp(h, B, N, mode, 0, h->xg, act, nullptr, h->nn11, true);
   }
-  launch_linearize(c, h->dP, B, N, h->xg, h->ug, h->r, act, h->nn11, qp_rec(h->qp));
+  launch_linearize(c, h->dP, B, N, h->xg, h->ug, h->P.nn_rows == SMPC_NN_PARALLEL ? h->cand : h->r, act, h->nn11, qp_rec(h->qp));
   if (h->timed) cudaEventRecord(h->ev[1], h->stream);
   cudaError_t qe = launch_qp_solve(c, h->dP, h->qp, x0_dev, h->r, act, h->xt, h->ut, h->status, h->qp_iter, h->qp_status, h->qp_res);
   if (qe != cudaSuccess) return fail(h, SMPC_ERR_CUDA, "QP solve", qe);
@@ -151,6 +158,27 @@ int step_pipeline(smpc_handle* h, const double* x_dev, const uint8_t* act, doubl
   LaunchCtx c = h->ctx();
   const int B = h->B, N = h->N;
   launch_prep(c, h->dP, B, N, h->xg, h->ug, act, h->P.controller != SMPC_CTRL_REAL_RECEDING);
+  if (h->P.controller == SMPC_CTRL_PARALLEL) {
+    // ParallelController.step (controller.py:614-640): one batched solve per candidate node n = N .. 1 for the problems that have
+    // not reached n = N yet; the host reads one counter per candidate to stop early
+    launch_par_begin(c, B, act, h->par_best, h->par_done, h->par_act, h->par_open);
+    for (int n = N; n >= 1; --n) {
+      launch_fill_i32(c, h->cand, B, n);
+      int rc = solve_pipeline(h, x_dev, h->par_act);
+      if (rc) return rc;
+      run_mlp(h, B, N, ROWS_ALL, 0, h->xt, h->par_act, nullptr, h->scan11, false);
+      launch_par_eval(c, h->dP, B, N, n, h->par_act, h->status, h->r, h->xt, h->ut, h->scan11, h->par_best, h->par_xt, h->par_ut, h->par_done,
+                      h->par_act, h->par_open);
+      CK(h, cudaMemcpyAsync(h->h_par_open, h->par_open, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+      CK(h, cudaStreamSynchronize(h->stream));
+      if (*h->h_par_open == 0) break;
+    }
+    launch_par_post(c, h->dP, B, N, act, h->xg, h->ug, h->xt, h->ut, h->par_best, h->par_xt, h->par_ut, h->fails, h->r, h->x_viable, h->need_scan,
+                    abort_dev, u_dev);
+    launch_ctrl_post2(c, h->dP, B, N, act, h->xg, h->ug, h->xt, h->ut, h->fails, h->r, h->cur_step, h->need_scan, h->scan11, abort_dev, u_dev);
+    if (h->timed) cudaEventRecord(h->ev[3], h->stream);
+    return check_launch(h, "parallel controller step pipeline");
+  }
   int rc = solve_pipeline(h, x_dev, act);
   if (rc) return rc;
   launch_ctrl_post1(c, h->dP, B, N, act, h->xg, h->ug, h->xt, h->status, h->fails, h->r, h->x_viable, h->need_scan, abort_dev, u_dev);
@@ -252,7 +280,15 @@ int smpc_create(const smpc_problem_t* prob, int32_t batch, int32_t device, smpc_
   CKC(dalloc(h, &h->plant_inertial, (size_t)B * NQ * 10)); CKC(dalloc(h, &h->tau_noise, (size_t)B * NU));
   CKC(dalloc(h, &h->x_viable, (size_t)B * NX));
   CKC(dalloc(h, &h->nn11, nst * NN_OUT));
-  if (prob->controller == SMPC_CTRL_RECEDING || prob->controller == SMPC_CTRL_REAL_RECEDING) CKC(dalloc(h, &h->scan11, nst * NN_OUT));
+  if (prob->controller == SMPC_CTRL_RECEDING || prob->controller == SMPC_CTRL_REAL_RECEDING || prob->controller == SMPC_CTRL_PARALLEL)
+    CKC(dalloc(h, &h->scan11, nst * NN_OUT));
+  CKC(dalloc(h, &h->cand, (size_t)B));
+  if (prob->controller == SMPC_CTRL_PARALLEL) {
+    if (prob->nn_rows != SMPC_NN_PARALLEL) { fail(nullptr, SMPC_ERR_ARG, "smpc_create: SMPC_CTRL_PARALLEL needs nn_rows = SMPC_NN_PARALLEL"); smpc_destroy(h); return SMPC_ERR_ARG; }
+    CKC(dalloc(h, &h->par_best, (size_t)B)); CKC(dalloc(h, &h->par_done, (size_t)B)); CKC(dalloc(h, &h->par_act, (size_t)B));
+    CKC(dalloc(h, &h->par_xt, nx)); CKC(dalloc(h, &h->par_ut, nu)); CKC(dalloc(h, &h->par_open, (size_t)1));
+    CKC(cudaMallocHost((void**)&h->h_par_open, sizeof(int)));
+  }
   {
     cudaError_t qe = cudaSuccess;
     h->qp = qp_create(B, N, prob->qp_iter_max, h->stream, &qe);
@@ -272,6 +308,7 @@ int smpc_create(const smpc_problem_t* prob, int32_t batch, int32_t device, smpc_
   }
   LaunchCtx c = h->ctx();
   launch_fill_i32(c, h->r, B, N);
+  launch_fill_i32(c, h->cand, B, N);
   launch_fill_i32(c, h->status, B, 4);
   CKC(cudaStreamSynchronize(h->stream));
   CKC(cudaGetLastError());
@@ -284,6 +321,7 @@ void smpc_destroy(smpc_handle_t* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->h_par_open) cudaFreeHost(h->h_par_open);
   for (void* p : h->allocs) cudaFree(p);
   qp_destroy(h->qp);
   if (h->stage) cudaFree(h->stage);

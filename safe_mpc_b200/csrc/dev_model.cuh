@@ -426,7 +426,7 @@ SMPC_HD void linearize_stage(const smpc_problem_t& P, int k, const double* x, co
 }
 
 SMPC_HD bool stage_has_nn(const smpc_problem_t& P, int k) {
-  return (P.nn_rows == SMPC_NN_TERMINAL && k == P.N) || ((P.nn_rows == SMPC_NN_RECEDING || P.nn_rows == SMPC_NN_EVERYWHERE) && k >= 1);
+  return (P.nn_rows == SMPC_NN_TERMINAL && k == P.N) || ((P.nn_rows == SMPC_NN_RECEDING || P.nn_rows == SMPC_NN_EVERYWHERE || P.nn_rows == SMPC_NN_PARALLEL) && k >= 1);
 }
 
 // M(q) (row-major 5x5) and h(q, v) of the chain with inertial parameters I

@@ -19,7 +19,7 @@ struct MlpWeights {
 };
 
 // which (problem, stage) rows the viability network is evaluated on
-enum { ROWS_TERMINAL = 0, ROWS_ALL = 1, ROWS_RECEDING = 2, ROWS_FLAT = 3 };
+enum { ROWS_TERMINAL = 0, ROWS_ALL = 1, ROWS_RECEDING = 2, ROWS_FLAT = 3, ROWS_CAND = 4 };   // ROWS_CAND: one row per problem, at stage r[b]
 
 // operands of the tensor-core evaluation of the network (mlp_tc.cu): plain fp32 vectors + the packed hi / lo stage images
 struct MlpTcWeights {
@@ -34,6 +34,7 @@ __device__ __forceinline__ bool mlp_row(int rows_mode, int i, int B, int N, cons
   if (rows_mode == ROWS_TERMINAL) { b = i; k = N; }
   else if (rows_mode == ROWS_ALL) { b = i / N; k = 1 + i % N; }
   else if (rows_mode == ROWS_RECEDING) { b = i >> 1; if (b >= B) return false; k = (i & 1) ? N : r[b]; if (k < 1 || (!(i & 1) && k >= N)) return false; }
+  else if (rows_mode == ROWS_CAND) { b = i; if (b >= B) return false; k = r[b]; if (k < 1 || k > N) return false; }
   else { b = i; k = 0; return true; }
   if (b >= B) return false;
   if (act && !act[b]) return false;
@@ -65,6 +66,14 @@ void launch_ctrl_post1(const LaunchCtx& c, const smpc_problem_t* dP, int B, int 
 void launch_ctrl_post2(const LaunchCtx& c, const smpc_problem_t* dP, int B, int N, const uint8_t* act, double* xg, double* ug,
                        const double* xt, const double* ut, const int32_t* fails, int32_t* r, int32_t* cur_step,
                        const uint8_t* need_scan, const double* scan11, const uint8_t* abort_flag, double* u_out);
+// ParallelController (controller.py:567-644): bookkeeping of the candidate-node loop
+void launch_par_begin(const LaunchCtx& c, int B, const uint8_t* act, int32_t* best, uint8_t* done, uint8_t* act2, int* n_open);
+void launch_par_eval(const LaunchCtx& c, const smpc_problem_t* dP, int B, int N, int n, const uint8_t* act2_in, const int32_t* status, const int32_t* r,
+                     const double* xt, const double* ut, const double* scan11, int32_t* best, double* best_xt, double* best_ut, uint8_t* done,
+                     uint8_t* act2_out, int* n_open);
+void launch_par_post(const LaunchCtx& c, const smpc_problem_t* dP, int B, int N, const uint8_t* act, const double* xg, const double* ug, double* xt,
+                     double* ut, const int32_t* best, const double* best_xt, const double* best_ut, int32_t* fails, int32_t* r, double* x_viable,
+                     uint8_t* need_scan, uint8_t* abort_flag, double* u_out);
 void launch_plant(const LaunchCtx& c, const smpc_problem_t* dP, int B, const double* inertial, const double* noise, const double* x,
                   const double* u, const uint8_t* act, double* xn, double* a);
 void launch_tau(const LaunchCtx& c, const smpc_problem_t* dP, int n, const double* x, const double* u, double* tau);

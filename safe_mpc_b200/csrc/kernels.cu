@@ -167,7 +167,7 @@ mlp_kernel(const smpc_problem_t* __restrict__ dP, MlpWeights w, int B, int N, in
 
 void launch_mlp(const LaunchCtx& c, const smpc_problem_t* dP, const MlpWeights& w, int B, int N, int rows_mode, int n_flat,
                 const double* xsrc, const int32_t* r, const uint8_t* act, const uint8_t* need, double* out11, bool want_grad) {
-  int n_rows = rows_mode == ROWS_TERMINAL ? B : rows_mode == ROWS_ALL ? B * N : rows_mode == ROWS_RECEDING ? 2 * B : n_flat;
+  int n_rows = (rows_mode == ROWS_TERMINAL || rows_mode == ROWS_CAND) ? B : rows_mode == ROWS_ALL ? B * N : rows_mode == ROWS_RECEDING ? 2 * B : n_flat;
   if (rows_mode == ROWS_FLAT) B = n_flat;
   if (n_rows <= 0) return;
   const size_t smem = sizeof(double) * (5 * MLP_R * HID + MLP_R * NX * 2 + 2 * MLP_R);
@@ -201,6 +201,7 @@ linearize_kernel(const smpc_problem_t* __restrict__ dP, int B, int N, const doub
   const bool has_nn = stage_has_nn(P, k);
   bool gate = true;
   if (P.nn_rows == SMPC_NN_RECEDING && k < N) gate = (k == r[b]);      // controller.py:452-469
+  if (P.nn_rows == SMPC_NN_PARALLEL) gate = (k == r[b]);               // controller.py:578-588 (r = candidate node of this solve)
   double* rec = lin + qs_blk(tile, N, k, REC, lane);
   linearize_stage(P, k, x, u, xn, has_nn, gate, nn11 + ((size_t)b * (N + 1) + k) * NN_OUT, rec, TL);
 }
@@ -305,6 +306,102 @@ void launch_ctrl_post2(const LaunchCtx& c, const smpc_problem_t* dP, int B, int 
                        const double* xt, const double* ut, const int32_t* fails, int32_t* r, int32_t* cur_step, const uint8_t* need_scan,
                        const double* scan11, const uint8_t* abort_flag, double* u_out) {
   ctrl_post2_kernel<<<GRID1D(B, 128), 128, 0, c.stream>>>(dP, B, N, act, xg, ug, xt, ut, fails, r, cur_step, need_scan, scan11, abort_flag, u_out);
+  ++*c.launches;
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// ParallelController.step (controller.py:614-640): the host loops over the candidate nodes n = N .. 1 (one batched solve each);
+// these kernels keep, per problem, the best node so far (sing_step :596-612) and finish the step.
+// ----------------------------------------------------------------------------------------------------------------
+__global__ void par_begin_kernel(int B, const uint8_t* __restrict__ act, int32_t* best, uint8_t* done, uint8_t* act2, int* n_open) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const bool on = !act || act[b];
+  best[b] = 0; done[b] = 0; act2[b] = on ? 1 : 0;
+  if (on) atomicAdd(n_open, 1);
+}
+void launch_par_begin(const LaunchCtx& c, int B, const uint8_t* act, int32_t* best, uint8_t* done, uint8_t* act2, int* n_open) {
+  cudaMemsetAsync(n_open, 0, sizeof(int), c.stream);
+  par_begin_kernel<<<GRID1D(B, 128), 128, 0, c.stream>>>(B, act, best, done, act2, n_open);
+  ++*c.launches;
+}
+
+__global__ void par_eval_kernel(const smpc_problem_t* __restrict__ dP, int B, int N, int n, const uint8_t* __restrict__ act2_in,
+                                const int32_t* __restrict__ status, const int32_t* __restrict__ r, const double* __restrict__ xt,
+                                const double* __restrict__ ut, const double* __restrict__ scan11, int32_t* best, double* best_xt, double* best_ut,
+                                uint8_t* done, uint8_t* act2_out, int* n_open) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B || !act2_in[b]) return;
+  const smpc_problem_t& P = *dP;
+  const double* xtb = xt + (size_t)b * (N + 1) * NX;
+  const int rb = r[b];
+  int checked_r = 0;                                               // check_safe_n (:590-595)
+  for (int i = rb; i <= N; ++i) {
+    const double cval = scan11[((size_t)b * (N + 1) + i) * NN_OUT];
+    if (i >= 1 && (0.0 - P.tol_safe <= cval) && (cval <= 1e6 + P.tol_safe)) checked_r = i;
+  }
+  int result = 0;
+  if (status[b] == 0) {
+    const int constr_ver = checked_r >= rb ? checked_r : (n < rb ? n : rb);
+    if (constr_ver - rb >= 0 && check_state_constraints_traj(P, xtb, N)) result = constr_ver;
+  }
+  if (result > best[b]) {
+    best[b] = result;
+    double* bx = best_xt + (size_t)b * (N + 1) * NX;
+    double* bu = best_ut + (size_t)b * N * NU;
+    const double* utb = ut + (size_t)b * N * NU;
+    for (int i = 0; i < (N + 1) * NX; ++i) bx[i] = xtb[i];
+    for (int i = 0; i < N * NU; ++i) bu[i] = utb[i];
+    if (result == N) done[b] = 1;
+  }
+  const bool open = !done[b] && n > 1;
+  act2_out[b] = open ? 1 : 0;
+  if (open) atomicAdd(n_open, 1);
+}
+void launch_par_eval(const LaunchCtx& c, const smpc_problem_t* dP, int B, int N, int n, const uint8_t* act2_in, const int32_t* status, const int32_t* r,
+                     const double* xt, const double* ut, const double* scan11, int32_t* best, double* best_xt, double* best_ut, uint8_t* done,
+                     uint8_t* act2_out, int* n_open) {
+  cudaMemsetAsync(n_open, 0, sizeof(int), c.stream);
+  par_eval_kernel<<<GRID1D(B, 128), 128, 0, c.stream>>>(dP, B, N, n, act2_in, status, r, xt, ut, scan11, best, best_xt, best_ut, done, act2_out, n_open);
+  ++*c.launches;
+}
+
+__global__ void par_post_kernel(const smpc_problem_t* __restrict__ dP, int B, int N, const uint8_t* __restrict__ act, const double* __restrict__ xg,
+                                const double* __restrict__ ug, double* xt, double* ut, const int32_t* __restrict__ best,
+                                const double* __restrict__ best_xt, const double* __restrict__ best_ut, int32_t* fails, int32_t* r, double* x_viable,
+                                uint8_t* need_scan, uint8_t* abort_flag, double* u_out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  if (act && !act[b]) return;
+  need_scan[b] = 0;
+  abort_flag[b] = 0;
+  const double* xgb = xg + (size_t)b * (N + 1) * NX;
+  const double* ugb = ug + (size_t)b * N * NU;
+  if (best[b] > 1) {                                               // controller.py:625-629
+    r[b] = best[b];
+    double* xtb = xt + (size_t)b * (N + 1) * NX;
+    double* utb = ut + (size_t)b * N * NU;
+    const double* bx = best_xt + (size_t)b * (N + 1) * NX;
+    const double* bu = best_ut + (size_t)b * N * NU;
+    for (int i = 0; i < (N + 1) * NX; ++i) xtb[i] = bx[i];
+    for (int i = 0; i < N * NU; ++i) utb[i] = bu[i];
+    fails[b] = 0;
+  } else {                                                         // :630-636
+    fails[b] += 1;
+    if (r[b] == 1) {
+      for (int i = 0; i < NX; ++i) x_viable[(size_t)b * NX + i] = xgb[NX + i];
+      r[b] = N;
+      for (int i = 0; i < NU; ++i) u_out[(size_t)b * NU + i] = ugb[i];
+      abort_flag[b] = 1;
+      return;
+    }
+  }
+  r[b] -= 1;                                                       // :637 (current_step and provideControl: ctrl_post2)
+}
+void launch_par_post(const LaunchCtx& c, const smpc_problem_t* dP, int B, int N, const uint8_t* act, const double* xg, const double* ug, double* xt,
+                     double* ut, const int32_t* best, const double* best_xt, const double* best_ut, int32_t* fails, int32_t* r, double* x_viable,
+                     uint8_t* need_scan, uint8_t* abort_flag, double* u_out) {
+  par_post_kernel<<<GRID1D(B, 128), 128, 0, c.stream>>>(dP, B, N, act, xg, ug, xt, ut, best, best_xt, best_ut, fails, r, x_viable, need_scan, abort_flag, u_out);
   ++*c.launches;
 }
 

@@ -26,6 +26,7 @@ CONTROLLERS = {
     'real_receding': (abi.CTRL['real_receding'], abi.NN_TERMINAL, False),
     'constraint_everywhere': (abi.CTRL['constraint_everywhere'], abi.NN_EVERYWHERE, False),
     'backup': (abi.CTRL['backup'], abi.NN_NONE, False),
+    'parallel': (abi.CTRL['parallel'], abi.NN_PARALLEL, False),     # controller.py:573-576: hard terminal + hard running rows
 }
 
 COSTS = {'zero': abi.COST_ZERO, 'ext': abi.COST_EXT, 'nls': abi.COST_NLS}

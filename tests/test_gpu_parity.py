@@ -187,3 +187,33 @@ def test_device_pointer_path_matches_host_path():
     assert u_d.is_cuda
     _close(u_d.cpu().numpy(), u_o, RTOL, 'u (device path)')
     np.testing.assert_array_equal(ab_d.cpu().numpy(), ab_o)
+
+
+@pytest.mark.parametrize('alpha', [10.0, 60.0])
+def test_parallel_controller_steps(alpha):
+    """ParallelController.step (controller.py:614-640): N solves per step, one per candidate node; the node kept, the receding index,
+    fails / abort and the control agree with the oracle.  alpha = 60 tightens the viability row so that candidates fail."""
+    B, N = 20, 8
+    eng, orc, prob, params, md = _pair('parallel', 'ext', N, B, alpha=alpha)
+    x0 = start_states(B, seed=51, vel=0.6)
+    xg, ug = rollout_guess(x0, N, params.dt, seed=52, scale=1.0)
+    for e in (eng, orc):
+        e.set_guess(xg, ug); e.reset_controller()
+    x_g, x_o = x0.copy(), x0.copy()
+    keep = np.ones(B, dtype=bool)
+    seen_r = set()
+    for step in range(8):
+        u_g, ab_g = eng.controller_step(x_g); u_o, ab_o = orc.controller_step(x_o)
+        keep &= _well_posed(orc, B, margin=0.05)
+        m = keep
+        np.testing.assert_array_equal(ab_g[m], ab_o[m], err_msg=f'abort flags, step {step}')
+        np.testing.assert_array_equal(eng.get_state(abi.STATE_FAILS)[m], orc.get_state(abi.STATE_FAILS)[m], err_msg=f'fails, step {step}')
+        np.testing.assert_array_equal(eng.get_state(abi.STATE_R)[m], orc.get_state(abi.STATE_R)[m], err_msg=f'r, step {step}')
+        seen_r |= set(orc.get_state(abi.STATE_R)[m].tolist())
+        _close(u_g[m], u_o[m], RTOL, f'u step {step}')
+        xgg, ugg = eng.get_guess(); xgo, ugo = orc.get_guess()
+        _close(xgg[m], xgo[m], RTOL, f'x_guess step {step}'); _close(ugg[m], ugo[m], RTOL, f'u_guess step {step}')
+        x_g, _ = eng.plant_step(x_g, u_g); x_o, _ = orc.plant_step(x_o, u_o)
+        _close(x_g[m], x_o[m], RTOL, f'x step {step}')
+    assert keep.sum() >= B // 2, f'only {keep.sum()} of {B} problems stayed well-posed'
+    print('receding indices seen:', sorted(seen_r))

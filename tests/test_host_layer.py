@@ -29,6 +29,12 @@ def test_get_controller_keys_and_errors():
     for bad in ('stwa', 'parallel', 'nope'):                 # utils.py:64-75 has no such keys
         with pytest.raises(ValueError, match='not available'):
             get_controller(bad, model)
+    # the classes the reference defines without a CLI key exist and are wired to their engine state machines
+    assert issubclass(C.ParallelController, C.RecedingController) and C.ParallelController.engine_name == 'parallel'
+    assert C.STWAController.engine_name == 'stwa'
+    from safe_mpc_b200.problem import CONTROLLERS
+    from safe_mpc_b200 import abi
+    assert CONTROLLERS['parallel'] == (abi.CTRL['parallel'], abi.NN_PARALLEL, False)
 
 
 def test_model_attributes_and_predicates():

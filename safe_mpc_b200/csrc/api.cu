@@ -30,6 +30,8 @@ struct smpc_handle {
   float* dW = nullptr;
   MlpWeights w{};
   float* dWtc = nullptr;            // packed tf32 hi / lo stage images of the tensor-core path (mlp_tc.cu)
+  float* dWtc2 = nullptr;           // the same per CTA of the pair kernel (mlp_tc2.cu)
+  bool tc_pair = false;             // SMPC_MLP_TC=pair: the CTA-pair kernel (cta_group::2) instead of one CTA per tile
   MlpTcWeights wtc{};
   int n_sm = 0;
   // state
@@ -131,7 +133,8 @@ void run_mlp(smpc_handle* h, int B, int N, int mode, int n_flat, const double* x
              bool want_grad) {
   LaunchCtx c = h->ctx();
   const int32_t* ridx = h->P.nn_rows == SMPC_NN_PARALLEL ? h->cand : h->r;      // stage index of the gated row
-  if (h->P.nn_precision == SMPC_NN_TF32X3) launch_mlp_tc(c, h->dP, h->wtc, h->n_sm, B, N, mode, n_flat, xsrc, ridx, act, need, out11, want_grad);
+  if (h->P.nn_precision == SMPC_NN_TF32X3 && h->tc_pair) launch_mlp_tc2(c, h->dP, h->wtc, h->n_sm, B, N, mode, n_flat, xsrc, ridx, act, need, out11, want_grad);
+  else if (h->P.nn_precision == SMPC_NN_TF32X3) launch_mlp_tc(c, h->dP, h->wtc, h->n_sm, B, N, mode, n_flat, xsrc, ridx, act, need, out11, want_grad);
   else launch_mlp(c, h->dP, h->w, B, N, mode, n_flat, xsrc, ridx, act, need, out11, want_grad);
 }
 
@@ -262,7 +265,14 @@ int smpc_create(const smpc_problem_t* prob, int32_t batch, int32_t device, smpc_
       CKC(cudaMemcpyAsync(h->dWtc, packed.data(), packed.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
       CKC(cudaStreamSynchronize(h->stream));
       CKC(mlp_tc_prepare());
-      h->wtc = MlpTcWeights{h->w.W1, h->w.b1, h->w.b2, h->w.b3, h->w.W4, h->w.b4, h->dWtc};
+      std::vector<float> packed2(mlp_tc2_packed_floats());
+      mlp_tc2_pack(W2, W3, packed2.data());
+      CKC(dalloc(h, &h->dWtc2, packed2.size()));
+      CKC(cudaMemcpyAsync(h->dWtc2, packed2.data(), packed2.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+      CKC(cudaStreamSynchronize(h->stream));
+      CKC(mlp_tc2_prepare());
+      if (const char* te = getenv("SMPC_MLP_TC")) h->tc_pair = strcmp(te, "pair") == 0;
+      h->wtc = MlpTcWeights{h->w.W1, h->w.b1, h->w.b2, h->w.b3, h->w.W4, h->w.b4, h->dWtc, h->dWtc2};
     }
   }
   if (prob->nn_precision != SMPC_NN_STRICT && prob->nn_precision != SMPC_NN_TF32X3) {

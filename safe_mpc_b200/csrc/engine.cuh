@@ -24,7 +24,8 @@ enum { ROWS_TERMINAL = 0, ROWS_ALL = 1, ROWS_RECEDING = 2, ROWS_FLAT = 3, ROWS_C
 // operands of the tensor-core evaluation of the network (mlp_tc.cu): plain fp32 vectors + the packed hi / lo stage images
 struct MlpTcWeights {
   const float *W1, *b1, *b2, *b3, *W4, *b4;
-  const float* packed;
+  const float* packed;          // stage images of the single-CTA kernel (mlp_tc.cu)
+  const float* packed2;         // stage images per CTA of the pair kernel (mlp_tc2.cu)
 };
 
 #if defined(__CUDACC__)
@@ -58,6 +59,12 @@ void mlp_tc_pack(const float* W2, const float* W3, float* out);
 cudaError_t mlp_tc_prepare();
 void launch_mlp_tc(const LaunchCtx& c, const smpc_problem_t* dP, const MlpTcWeights& w, int n_sm, int B, int N, int rows_mode, int n_flat,
                    const double* xsrc, const int32_t* r, const uint8_t* act, const uint8_t* need, double* out11, bool want_grad);
+// mlp_tc2.cu -- CTA-pair form (tcgen05 cta_group::2, thread-block cluster of two)
+size_t mlp_tc2_packed_floats();
+void mlp_tc2_pack(const float* W2, const float* W3, float* out);
+cudaError_t mlp_tc2_prepare();
+void launch_mlp_tc2(const LaunchCtx& c, const smpc_problem_t* dP, const MlpTcWeights& w, int n_sm, int B, int N, int rows_mode, int n_flat,
+                    const double* xsrc, const int32_t* r, const uint8_t* act, const uint8_t* need, double* out11, bool want_grad);
 void launch_linearize(const LaunchCtx& c, const smpc_problem_t* dP, int B, int N, const double* xg, const double* ug,
                       const int32_t* r, const uint8_t* act, const double* nn11, double* lin);
 void launch_ctrl_post1(const LaunchCtx& c, const smpc_problem_t* dP, int B, int N, const uint8_t* act, const double* xg, const double* ug,

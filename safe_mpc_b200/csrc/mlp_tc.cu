@@ -24,6 +24,7 @@
 #include <vector>
 
 #include "engine.cuh"
+#include "mlp_tc_common.cuh"
 
 namespace smpc {
 
@@ -61,111 +62,9 @@ static_assert(TC_SMEM <= 232448, "shared memory budget");
 // instruction descriptor of tcgen05.mma.kind::tf32: D fp32, A/B tf32, both K-major, M = 128, N = R
 constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(R >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
-__device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+using namespace tcg;
 
-// shared-memory matrix descriptor, K-major, no swizzle: core matrix = 8 rows x 16 B stored contiguously;
-// lbo = byte distance between the two core matrices along K, sbo = between 8-row groups along M / N
-__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
-  return (uint64_t)((addr & 0x3ffffu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
-}
-
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(bar)) : "memory");
-}
-__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_expect(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = s32(bar);
-  uint32_t ok;
-  do {
-    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                 : "=r"(ok)
-                 : "r"(addr), "r"(parity)
-                 : "memory");
-  } while (!ok);
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s32(dst)), "l"(src),
-               "r"(bytes), "r"(s32(bar))
-               : "memory");
-}
 __device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, %0;" ::"n"(32 * NCW) : "memory"); }
-
-#define V32_OUT(v)                                                                                                              \
-  "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),       \
-      "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),      \
-      "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),      \
-      "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-#define V32_IN(v)                                                                                                               \
-  "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),     \
-      "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]),   \
-      "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]),   \
-      "r"(v[31])
-
-// 32 consecutive TMEM columns of this thread's lane -> registers (the wait makes them readable)
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
-      "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : V32_OUT(v)
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* v) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
-      "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
-      V32_IN(v)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
-// a = hi + lo with hi exactly representable in tf32 (round to nearest at 10 mantissa bits); lo keeps the next 11+ bits
-__host__ __device__ __forceinline__ void split_tf32(float a, float& hi, float& lo) {
-  uint32_t u;
-#if defined(__CUDA_ARCH__)
-  u = __float_as_uint(a);
-#else
-  std::memcpy(&u, &a, 4);
-#endif
-  u = (u + 0x1000u) & 0xffffe000u;
-#if defined(__CUDA_ARCH__)
-  hi = __uint_as_float(u);
-#else
-  std::memcpy(&hi, &u, 4);
-#endif
-  lo = a - hi;
-}
-
-__device__ __forceinline__ float gelu_f32(float x, float& d) {        // GELU(tanh) and its derivative (safe_set.py:31-40)
-  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
-  const float x2 = x * x;
-  // tanh(u) = 1 - 2 / (exp(2u) + 1) with the hardware exp2 / reciprocal: absolute error ~2e-7, no branches
-  const float e = __expf(2.0f * k0 * (x + k1 * x * x2));
-  const float t = 1.0f - __fdividef(2.0f, e + 1.0f);
-  d = 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * k0 * (1.0f + 3.0f * k1 * x2);
-  return 0.5f * x * (1.0f + t);
-}
-
 // byte offset of X[row n][k] inside X_hi / X_lo
 __device__ __forceinline__ int xoff(int n, int k) { return (k >> 2) * XPITCH + n * 16 + (k & 3) * 4; }
 
@@ -327,9 +226,9 @@ mlp_tc_kernel(const smpc_problem_t* __restrict__ dP, MlpTcWeights w, int B, int 
                 const uint64_t ah = smem_desc(ws + h * WHALF + ks * 2 * WROWB, WROWB, 128);
                 const uint64_t al = smem_desc(ws + 2 * WHALF + h * WHALF + ks * 2 * WROWB, WROWB, 128);
                 const uint32_t d = tmem + h * R;
-                umma_tf32(d, al, bh, (s | ks) != 0);       // small terms first
-                umma_tf32(d, ah, bl, 1);
-                umma_tf32(d, ah, bh, 1);
+                umma_tf32(d, al, bh, IDESC, (s | ks) != 0);       // small terms first
+                umma_tf32(d, ah, bl, IDESC, 1);
+                umma_tf32(d, ah, bh, IDESC, 1);
               }
             }
             umma_commit(bar_empty + slot);                  // the stage may be refilled once these MMAs have read it
@@ -511,7 +410,7 @@ cudaError_t mlp_tc_prepare() {
 
 void launch_mlp_tc(const LaunchCtx& c, const smpc_problem_t* dP, const MlpTcWeights& w, int n_sm, int B, int N, int rows_mode, int n_flat,
                    const double* xsrc, const int32_t* r, const uint8_t* act, const uint8_t* need, double* out11, bool want_grad) {
-  int n_rows = rows_mode == ROWS_TERMINAL ? B : rows_mode == ROWS_ALL ? B * N : rows_mode == ROWS_RECEDING ? 2 * B : n_flat;
+  int n_rows = (rows_mode == ROWS_TERMINAL || rows_mode == ROWS_CAND) ? B : rows_mode == ROWS_ALL ? B * N : rows_mode == ROWS_RECEDING ? 2 * B : n_flat;
   if (rows_mode == ROWS_FLAT) B = n_flat;
   if (n_rows <= 0) return;
   const int n_tiles = (n_rows + R - 1) / R;

@@ -13,17 +13,29 @@ pytestmark = pytest.mark.gpu
 TOL = 2e-5
 
 
-def _engines(controller, N, B):
+def _engines(controller, N, B, kernel='single'):
+    """kernel: 'single' = csrc/mlp_tc.cu (one CTA per 64-row tile, the default), 'pair' = csrc/mlp_tc2.cu (cta_group::2 CTA pairs)"""
+    import os
     from safe_mpc_b200.engine import Engine
     from oracle.oracle import Oracle
     prob_tc, params, md = make_problem(controller, N=N, nn_precision='tf32x3')
     prob_st, _, _ = make_problem(controller, N=N)
-    return Engine(prob_tc, B, 0), Oracle(prob_st, B, 0), params, md
+    old = os.environ.get('SMPC_MLP_TC')
+    os.environ['SMPC_MLP_TC'] = kernel                    # read when the handle is created
+    try:
+        eng = Engine(prob_tc, B, 0)
+    finally:
+        if old is None:
+            os.environ.pop('SMPC_MLP_TC', None)
+        else:
+            os.environ['SMPC_MLP_TC'] = old
+    return eng, Oracle(prob_st, B, 0), params, md
 
 
-@pytest.mark.parametrize('n', [1, 63, 64, 65, 1000, 20000])
-def test_nn_constraint_rows(n):
-    eng, orc, params, md = _engines('st', 20, 64)
+@pytest.mark.parametrize('kernel', ['single', 'pair'])
+@pytest.mark.parametrize('n', [1, 63, 64, 65, 127, 129, 1000, 20000])
+def test_nn_constraint_rows(n, kernel):
+    eng, orc, params, md = _engines('st', 20, 64, kernel)
     x = random_states(md, n, seed=n)
     c_g, g_g = eng.nn_constraint(x)
     c_o, g_o = orc.nn_constraint(x)
@@ -33,13 +45,14 @@ def test_nn_constraint_rows(n):
     assert np.abs(g_g - g_o).max() <= TOL * sg, np.abs(g_g - g_o).max()
 
 
+@pytest.mark.parametrize('kernel', ['single', 'pair'])
 @pytest.mark.parametrize('controller', ['st', 'htwa', 'receding', 'constraint_everywhere'])
-def test_rti_solve_fp32_mode(controller):
+def test_rti_solve_fp32_mode(controller, kernel):
     """one RTI iteration with the tensor-core network: stage records of the viability rows and the step agree with the
     strict oracle within the fp32-mode tolerance of BASELINE.json (1e-3 relative on the trajectories)"""
     from safe_mpc_b200 import abi
     B, N = 96, 20
-    eng, orc, params, md = _engines(controller, N, B)
+    eng, orc, params, md = _engines(controller, N, B, kernel)
     x0 = start_states(B, seed=3)
     xg, ug = rollout_guess(x0, N, params.dt, seed=4)
     for e in (eng, orc):

@@ -3,11 +3,13 @@
  * cpu_baseline / --impl reference legs as the checker and the timed CPU baseline.  The product library
  * (safe_mpc_b200/csrc) never includes, links or calls anything in this directory.
  *
- * PARITY UNPINNED: the reference's numerics live in acados/HPIPM, CasADi, adam and L4CasADi, none of which
- * is vendored under /root/reference or installed here, and the reference's tests hold no golden vectors
- * (SURVEY.md section 4, 8c).  This restatement is pinned only by independent cross-checks (tests/):
- * finite differences, a numpy re-implementation of the chain algorithms, torch fp64 autograd for the MLP,
- * and direct verification of the KKT conditions of every QP solution.
+ * PARITY UNPINNED except for the viability network: the reference's numerics live in acados/HPIPM, CasADi, adam and
+ * L4CasADi, none of which is vendored under /root/reference or installed here, and the reference's tests hold no golden
+ * vectors.  The network (a5) is pinned on the reference's own NeuralNetwork class
+ * (tests/golden/make_ref_golden.py -> ref_network.npz, tests/test_ref_golden.py); the configuration layer on the reference's
+ * own Parameters (ref_parameters.json).  Everything else in this restatement is pinned only by independent cross-checks
+ * (tests/): finite differences, a numpy re-implementation of the chain algorithms, and direct verification of the KKT
+ * conditions of every QP solution.
  *
  * The API mirrors include/safe_mpc_b200.h function by function (orc_* <-> smpc_*), host memory only; the
  * problem description is the very same struct (the boundary header is shared, the implementation is not).

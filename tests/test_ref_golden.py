@@ -1,0 +1,93 @@
+"""Golden vectors computed with the REFERENCE's own ``NeuralNetwork`` class (tests/golden/make_ref_golden.py, run in the build container
+where /root/reference is mounted): the one piece of the hot path that executes without casadi / acados / adam / l4casadi.
+They pin row a5 of SURVEY.md section 8 -- architecture, layer order, GELU(tanh), psi(x), c(x) and dc/dx -- on reference code instead of on
+a restatement: the oracle must reproduce the fp64 evaluation of the reference class to rounding, and the reference's fp32 evaluation
+(what its L4CasADi call computes) to fp32 accuracy; the CUDA kernels are held to the same vectors."""
+import os
+
+import numpy as np
+import pytest
+
+from tests.common import make_problem
+
+G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'ref_network.npz'))
+
+
+def test_oracle_matches_the_reference_network_class():
+    from oracle.oracle import Oracle
+    prob, params, md = make_problem('st', N=10, alpha=float(G['alpha']))
+    orc = Oracle(prob, 4, 0)
+    c, g = orc.nn_constraint(G['x'])
+    assert np.abs(c - G['c']).max() <= 1e-9 * max(1.0, np.abs(G['c']).max())          # fp32 weights, fp64 accumulation on both sides
+    assert np.abs(g - G['grad']).max() <= 1e-9 * max(1.0, np.abs(G['grad']).max())
+    # what the reference itself computes (fp32 inside libtorch) differs from both by fp32 rounding only
+    s = (100.0 - float(G['alpha'])) / 100.0
+    assert np.abs((G['y32'] - G['y64']) * s).max() <= 2e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('precision,kernel,tol', [('strict', 'single', 1e-9), ('tf32x3', 'single', 2e-5), ('tf32x3', 'pair', 2e-5)])
+def test_engine_matches_the_reference_network_class(precision, kernel, tol):
+    from safe_mpc_b200.engine import Engine
+    prob, params, md = make_problem('st', N=10, alpha=float(G['alpha']), nn_precision=precision)
+    old = os.environ.get('SMPC_MLP_TC')
+    os.environ['SMPC_MLP_TC'] = kernel
+    try:
+        eng = Engine(prob, 4, 0)
+    finally:
+        if old is None:
+            os.environ.pop('SMPC_MLP_TC', None)
+        else:
+            os.environ['SMPC_MLP_TC'] = old
+    c, g = eng.nn_constraint(G['x'])
+    assert np.abs(c - G['c']).max() <= tol * max(1.0, np.abs(G['c']).max())
+    assert np.abs(g - G['grad']).max() <= tol * max(1.0, np.abs(G['grad']).max())
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# reference parser.py (Parameters, parse_args) evaluated on the reference's own config.yaml  ->  tests/golden/ref_parameters.json
+# ---------------------------------------------------------------------------------------------------------------------------
+import json
+
+P = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'ref_parameters.json')))
+ARGV = {'default': [],
+        'margins': ['--joint_bounds_margin', '5', '--collision_margin', '0.02', '--noise', '10', '-c', 'receding', '--horizon', '35', '--alpha', '20']}
+
+
+# placeholders of the moving capsules that env_model.py:131-151 later fills with CasADi functions (the engine has no such objects)
+CASADI_SLOTS = {'end_points_T_fun', 'end_points_fk', 'end_points_fk_fun'}
+
+
+def _same(a, b, path=''):
+    """recursive comparison of a value of this repo's Parameters with the reference's (lists / arrays / dicts / scalars)"""
+    if isinstance(b, dict):
+        keys = set(b) - CASADI_SLOTS
+        assert isinstance(a, dict) and keys <= set(a), f'{path}: keys {sorted(keys - set(a))} missing'
+        for k in keys:
+            _same(a[k], b[k], f'{path}.{k}')
+    elif isinstance(b, list):
+        a = a.tolist() if isinstance(a, np.ndarray) else list(a)
+        assert len(a) == len(b), f'{path}: length {len(a)} != {len(b)}'
+        for i, (x, y) in enumerate(zip(a, b)):
+            _same(x, y, f'{path}[{i}]')
+    elif isinstance(b, float):
+        assert abs(float(a) - b) <= 1e-15 * max(1.0, abs(b)), f'{path}: {a} != {b}'
+    elif b is None:
+        assert a is None, f'{path}: {a} is not None'
+    else:
+        a = a.item() if isinstance(a, (np.integer, np.floating, np.bool_)) else a
+        assert a == b, f'{path}: {a!r} != {b!r}'
+
+
+@pytest.mark.parametrize('tag', ['default', 'margins'])
+def test_parameters_match_the_reference_parser(tag):
+    from safe_mpc_b200.parser import Parameters, parse_args
+    args = parse_args(ARGV[tag])
+    for k, v in P[tag]['args'].items():                    # the reference's CLI: same keys, same defaults (parser.py:9-34)
+        assert args[k] == v, f'args[{k}]'
+    p = Parameters(args, 'z1', rti=True)
+    ref = P[tag]['params']
+    assert len(ref) >= 50
+    for k, v in ref.items():
+        assert hasattr(p, k), f'Parameters.{k} missing'
+        _same(getattr(p, k), v, k)

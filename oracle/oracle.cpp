@@ -426,7 +426,9 @@ bool parallel_step_one(orc_handle& h, int b, const double* x, double* u, Workspa
 }
 
 // controller.step(x) for problem b; returns abort flag
-bool controller_step_one(orc_handle& h, int b, const double* x, double* u, Workspace& W) {
+// `scripted`: the solve is replaced by a given outcome (status, x_temp, u_temp already stored in the handle) -- used to drive the state
+// machines with the very sequences the reference's controller classes were driven with (tests/golden/make_ref_controllers.py)
+bool controller_step_one(orc_handle& h, int b, const double* x, double* u, Workspace& W, const int32_t* scripted = nullptr) {
   if (h.P.controller == SMPC_CTRL_PARALLEL) return parallel_step_one(h, b, x, u, W);
   const orc_problem_t& P = h.P;
   const int N = P.N;
@@ -435,7 +437,7 @@ bool controller_step_one(orc_handle& h, int b, const double* x, double* u, Works
   const int ctrl = P.controller;
   if (ctrl != SMPC_CTRL_REAL_RECEDING)   // guessCorrection (controller.py:226-231)
     for (int k = 0; k < N; ++k) f_disc(P.dt, xg + k * NX, ug + k * NU, xg + (k + 1) * NX);
-  const int status = rti_solve_one(h, b, x, W);
+  const int status = scripted ? (h.status[b] = scripted[b]) : rti_solve_one(h, b, x, W);
   switch (ctrl) {
     case SMPC_CTRL_NAIVE: case SMPC_CTRL_ZEROVEL: case SMPC_CTRL_ST: case SMPC_CTRL_BACKUP:
       if (status == 0) h.fails[b] = 0; else h.fails[b] += 1;
@@ -590,6 +592,19 @@ int orc_controller_step(orc_handle_t* h, const double* x, const uint8_t* active,
   parallel_for(h->B, h->threads, [&](int b, int tid) {
     if (active && !active[b]) return;
     bool ab = controller_step_one(*h, b, x + (size_t)b * NX, u + (size_t)b * NU, h->ws[tid]);
+    if (abort_flag) abort_flag[b] = ab ? 1 : 0;
+  });
+  return SMPC_OK;
+}
+
+// controller.step(x) with the solve replaced by a scripted outcome: status[B], x_temp[B][N+1][NX], u_temp[B][N][NU]
+int orc_controller_step_scripted(orc_handle_t* h, const double* x, const int32_t* status, const double* xt, const double* ut, double* u,
+                                 uint8_t* abort_flag) {
+  if (h->P.controller == SMPC_CTRL_PARALLEL) return SMPC_ERR_UNSUPPORTED;
+  std::copy(xt, xt + h->xt.size(), h->xt.begin());
+  std::copy(ut, ut + h->ut.size(), h->ut.begin());
+  parallel_for(h->B, h->threads, [&](int b, int tid) {
+    bool ab = controller_step_one(*h, b, x + (size_t)b * NX, u + (size_t)b * NU, h->ws[tid], status);
     if (abort_flag) abort_flag[b] = ab ? 1 : 0;
   });
   return SMPC_OK;

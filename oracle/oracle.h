@@ -3,11 +3,13 @@
  * cpu_baseline / --impl reference legs as the checker and the timed CPU baseline.  The product library
  * (safe_mpc_b200/csrc) never includes, links or calls anything in this directory.
  *
- * PARITY UNPINNED except for the viability network: the reference's numerics live in acados/HPIPM, CasADi, adam and
+ * PARITY PARTLY PINNED: the reference's numerics live in acados/HPIPM, CasADi, adam and
  * L4CasADi, none of which is vendored under /root/reference or installed here, and the reference's tests hold no golden
- * vectors.  The network (a5) is pinned on the reference's own NeuralNetwork class
- * (tests/golden/make_ref_golden.py -> ref_network.npz, tests/test_ref_golden.py); the configuration layer on the reference's
- * own Parameters (ref_parameters.json).  Everything else in this restatement is pinned only by independent cross-checks
+ * vectors.  Pinned on reference code executed in the build container (tests/golden/make_ref_*.py,
+ * tests/test_ref_golden.py): the network (a5, the reference's NeuralNetwork class), the controller state machines with the
+ * warm-start shift (a8, a9, the reference's controller classes driven with scripted solves), the capsule distance (a4),
+ * randomize_model (a13) and the configuration layer (the reference's Parameters on its own config.yaml).  The acados / HPIPM /
+ * CasADi / adam numerics (a2, a3, a7, a11) are PARITY UNPINNED: that part of the restatement is pinned only by independent cross-checks
  * (tests/): finite differences, a numpy re-implementation of the chain algorithms, and direct verification of the KKT
  * conditions of every QP solution.
  *
@@ -48,6 +50,9 @@ int orc_get_temp(orc_handle_t* h, double* x_temp, double* u_temp);
 int orc_reset_controller(orc_handle_t* h);
 int orc_rti_solve(orc_handle_t* h, const double* x0, const uint8_t* active, int32_t* status);
 int orc_controller_step(orc_handle_t* h, const double* x, const uint8_t* active, double* u, uint8_t* abort_flag);
+/* the same with the solve replaced by a scripted outcome (tests only) */
+int orc_controller_step_scripted(orc_handle_t* h, const double* x, const int32_t* status, const double* xt, const double* ut, double* u,
+                                 uint8_t* abort_flag);
 int orc_plant_step(orc_handle_t* h, const double* x, const double* u, double* x_next, double* a_applied);
 int orc_tau(orc_handle_t* h, int32_t n, const double* x, const double* u, double* tau);
 int orc_kinematics(orc_handle_t* h, int32_t n, const double* x, double* ee, double* dist);

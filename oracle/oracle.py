@@ -54,6 +54,15 @@ class Oracle(EngineBase):
                    C.c_void_p(M.ctypes.data), C.c_void_p(h.ctypes.data))
         return M, h
 
+    def controller_step_scripted(self, x, status, x_temp, u_temp):
+        """controller.step(x) with the solve replaced by a given outcome (tests/test_ref_golden.py) -> (u [B, nu], abort [B])"""
+        x = np.ascontiguousarray(x, dtype=np.float64); st = np.ascontiguousarray(status, dtype=np.int32)
+        xt = np.ascontiguousarray(x_temp, dtype=np.float64); ut = np.ascontiguousarray(u_temp, dtype=np.float64)
+        u = np.zeros((self.B, abi.NU)); ab = np.zeros(self.B, dtype=np.uint8)
+        self._call('controller_step_scripted', C.c_void_p(x.ctypes.data), C.c_void_p(st.ctypes.data), C.c_void_p(xt.ctypes.data),
+                   C.c_void_p(ut.ctypes.data), C.c_void_p(u.ctypes.data), C.c_void_p(ab.ctypes.data))
+        return u, ab.astype(bool)
+
     def qp_info(self, b):
         res = (C.c_double * 4)(); mu = C.c_double(); it = C.c_int32(); st = C.c_int32()
         self._call('qp_info', C.c_int32(b), res, C.byref(mu), C.byref(it), C.byref(st))

@@ -93,7 +93,7 @@ class AdamModel:
     # ---- perturbed plants / noise (env_model.py:321-331, utils.py:126-171) -----------------------------------------
     def update_randomized_dynamics(self, inertial=None, noise_percent=None, seed=0, controller_name=None):
         """Per-problem plant parameters [B, nq, 10].  The reference reloads ``z1_randomized<name>.urdf`` per test; here the
-        whole batch is set at once, either from explicit parameters or drawn like ``randomize_model`` (uniform +-%)."""
+        whole batch is set at once, either from explicit parameters or drawn like ``randomize_model`` (uniform +- percent)."""
         if inertial is None:
             n = float(self.params.noise if noise_percent is None else noise_percent)
             links = randomized_link_inertials(self.data.nominal_links, n, n, n, self.batch, seed=seed)

@@ -91,3 +91,76 @@ def test_parameters_match_the_reference_parser(tag):
     for k, v in ref.items():
         assert hasattr(p, k), f'Parameters.{k} missing'
         _same(getattr(p, k), v, k)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# reference utils.py: randomize_model (a13) and rot_mat_x/y/z, executed unmodified (tests/golden/make_ref_randomize.py)
+# ---------------------------------------------------------------------------------------------------------------------------
+R = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'ref_randomize.npz'))
+
+
+@pytest.mark.parametrize('seed', [1, 2])
+def test_randomized_inertials_match_the_reference_function(seed):
+    """the draw order and the perturbation of the reference's randomize_model (mass, 6 inertia entries, CoM, link by link) -- the
+    per-problem plant parameters of the model-noise ensemble (BASELINE.json configs[3])"""
+    from safe_mpc_b200 import urdf as U
+    from safe_mpc_b200.robot_model import nominal_link_inertials, randomized_link_inertials
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    nominal = nominal_link_inertials(U.URDF.from_xml_file(os.path.join(root, 'robots', 'z1_description', 'urdf', 'z1.urdf')))
+    pct = float(R[f'pct_{seed}'])
+    count = R[f'mass_{seed}'].shape[0]
+    ours = randomized_link_inertials(nominal, pct, pct, pct, count, seed=seed)
+    # the reference writes the numbers through str() into the URDF text and reads them back: exact round trip for doubles
+    np.testing.assert_allclose(ours['mass'], R[f'mass_{seed}'], rtol=1e-15, atol=0)
+    np.testing.assert_allclose(ours['inertia6'], R[f'inertia6_{seed}'], rtol=1e-15, atol=0)
+    np.testing.assert_allclose(ours['com'], R[f'com_{seed}'], rtol=1e-15, atol=0)
+
+
+def test_rotation_helpers_match_the_reference_functions():
+    from safe_mpc_b200.robot_model import rot_mat_x, rot_mat_y, rot_mat_z
+    for i, t in enumerate(R['theta']):
+        np.testing.assert_array_equal(rot_mat_x(t), R['rot_x'][i])
+        np.testing.assert_array_equal(rot_mat_y(t), R['rot_y'][i])
+        np.testing.assert_array_equal(rot_mat_z(t), R['rot_z'][i])
+
+
+def test_capsule_distances_match_the_reference_function():
+    """row a4: squared segment-segment distances with the clamped parameters and the R^2 + 1e-5 regulariser of the reference's
+    casadi_segment_dist, evaluated by the reference function itself on the capsule end points of 64 random configurations"""
+    from oracle.oracle import Oracle
+    prob, params, md = make_problem('naive', N=10)
+    orc = Oracle(prob, 4, 0)
+    ee, dist = orc.kinematics(R['dist_x'])
+    np.testing.assert_allclose(dist, R['dist'], rtol=1e-11, atol=1e-13)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# reference controller.py: the step state machines, provideControl and guessCorrection (rows a8 / a9), driven with scripted solve
+# outcomes (tests/golden/make_ref_controllers.py); the oracle is driven with the same sequences
+# ---------------------------------------------------------------------------------------------------------------------------
+CG = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'ref_controllers.npz'))
+
+
+@pytest.mark.parametrize('name', ['naive', 'zerovel', 'st', 'stwa', 'htwa', 'receding', 'real_receding', 'constraint_everywhere'])
+def test_controller_state_machines_match_the_reference_classes(name):
+    from oracle.oracle import Oracle
+    from safe_mpc_b200 import abi
+    N, B, steps = int(CG['N']), int(CG['B']), int(CG['STEPS'])
+    prob, params, md = make_problem(name, N=N)
+    orc = Oracle(prob, B, 1)
+    orc.set_guess(CG[f'{name}_xg0'], CG[f'{name}_ug0'])
+    orc.reset_controller()
+    for s in range(steps):
+        u, ab = orc.controller_step_scripted(CG[f'{name}_x'][s], CG[f'{name}_status'][s], CG[f'{name}_xt'][s], CG[f'{name}_ut'][s])
+        where = f'{name}, step {s}'
+        np.testing.assert_array_equal(ab, CG[f'{name}_abort'][s], err_msg=f'abort flag, {where}')
+        np.testing.assert_array_equal(orc.get_state(abi.STATE_FAILS), CG[f'{name}_fails'][s], err_msg=f'fails, {where}')
+        if name in ('receding', 'real_receding'):
+            np.testing.assert_array_equal(orc.get_state(abi.STATE_R), CG[f'{name}_r'][s], err_msg=f'receding index, {where}')
+        np.testing.assert_allclose(u, CG[f'{name}_u'][s], rtol=0, atol=1e-14, err_msg=f'control, {where}')
+        xg, ug = orc.get_guess()
+        np.testing.assert_allclose(xg, CG[f'{name}_xg'][s], rtol=0, atol=1e-13, err_msg=f'x_guess, {where}')
+        np.testing.assert_allclose(ug, CG[f'{name}_ug'][s], rtol=0, atol=1e-14, err_msg=f'u_guess, {where}')
+        if name in ('stwa', 'htwa', 'receding', 'real_receding'):
+            aborted = CG[f'{name}_abort'][:s + 1].any(axis=0) | (CG[f'{name}_fails'][:s + 1] > 0).any(axis=0)
+            np.testing.assert_allclose(orc.get_x_viable()[aborted], CG[f'{name}_xv'][s][aborted], rtol=0, atol=1e-13, err_msg=f'x_viable, {where}')

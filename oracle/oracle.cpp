@@ -61,6 +61,9 @@ struct orc_sim {
   std::vector<double> x, xlog, ulog, x_abort, u_abort, xv_first;
   std::vector<int32_t> mode, ja, outcome;
   int64_t counters[4] = {0, 0, 0, 0};
+  // scripted solve outcomes of the NEXT step (tests only, orc_sim_set_script): main controller and backup OCP
+  const int32_t *scr_status = nullptr, *scr_bk_status = nullptr;
+  const double *scr_xt = nullptr, *scr_ut = nullptr, *scr_bk_xt = nullptr, *scr_bk_ut = nullptr;
 };
 
 namespace {
@@ -720,6 +723,8 @@ int orc_sim_step(orc_sim_t* s) {
   const double kp = 1.0, kd = 1e2;
   std::atomic<int64_t> n_rti(0), n_bk(0), n_ps(0), n_ipm(0);
   if ((int)K.ws.size() < C.threads) K.ws.resize(C.threads);
+  const int32_t* scr = s->scr_status;
+  if (scr) { std::copy(s->scr_xt, s->scr_xt + C.xt.size(), C.xt.begin()); std::copy(s->scr_ut, s->scr_ut + C.ut.size(), C.ut.begin()); }
   parallel_for(B, C.threads, [&](int b, int tid) {
     if (s->mode[b] == 2) return;
     Workspace& W = C.ws[tid];
@@ -737,7 +742,7 @@ int orc_sim_step(orc_sim_t* s) {
         bool slow = true;
         for (int i = 0; i < NQ; ++i) slow &= (x[NQ + i] < 5e-3);   // no abs(), as upstream
         if (slow) {
-          bool sa = controller_step_one(C, b, x, u, W);
+          bool sa = controller_step_one(C, b, x, u, W, scr);
           ++n_rti; n_ipm += C.qp_iter[b];
           s->mode[b] = sa ? 1 : 0;        // a repeated abort here does NOT re-solve the backup OCP (mpc.py:138-141)
         } else {
@@ -746,7 +751,7 @@ int orc_sim_step(orc_sim_t* s) {
       }
       s->ja[b] = ja + 1;
     } else {
-      bool sa = controller_step_one(C, b, x, u, W);
+      bool sa = controller_step_one(C, b, x, u, W, scr);
       ++n_rti; n_ipm += C.qp_iter[b];
       if (sa) {                           // mpc.py:161-190
         const double* xv = &C.x_viable[(size_t)b * NX];
@@ -755,7 +760,12 @@ int orc_sim_step(orc_sim_t* s) {
         double* ug = &K.ug[(size_t)b * Nb * NU];
         for (int k = 0; k <= Nb; ++k) for (int i = 0; i < NX; ++i) xg[k * NX + i] = xv[i];
         for (int i = 0; i < Nb * NU; ++i) ug[i] = 0.0;
-        int st = rti_solve_one(K, b, xv, WK);
+        int st;
+        if (s->scr_bk_status) {
+          st = s->scr_bk_status[b];
+          std::copy(s->scr_bk_xt + (size_t)b * (Nb + 1) * NX, s->scr_bk_xt + (size_t)(b + 1) * (Nb + 1) * NX, &K.xt[(size_t)b * (Nb + 1) * NX]);
+          std::copy(s->scr_bk_ut + (size_t)b * Nb * NU, s->scr_bk_ut + (size_t)(b + 1) * Nb * NU, &K.ut[(size_t)b * Nb * NU]);
+        } else st = rti_solve_one(K, b, xv, WK);
         ++n_bk; n_ipm += K.qp_iter[b];
         if (st != 0) { s->outcome[b] |= SMPC_OUT_COLLIDED; done = true; }
         else {
@@ -778,6 +788,12 @@ int orc_sim_step(orc_sim_t* s) {
   });
   s->counters[0] += n_rti; s->counters[1] += n_bk; s->counters[2] += n_ps; s->counters[3] += n_ipm;
   s->j += 1;
+  return SMPC_OK;
+}
+// tests only: the solves of the next orc_sim_step calls are replaced by these outcomes (NULL status: real solves again)
+int orc_sim_set_script(orc_sim_t* s, const int32_t* status, const double* xt, const double* ut, const int32_t* bk_status, const double* bk_xt,
+                       const double* bk_ut) {
+  s->scr_status = status; s->scr_xt = xt; s->scr_ut = ut; s->scr_bk_status = bk_status; s->scr_bk_xt = bk_xt; s->scr_bk_ut = bk_ut;
   return SMPC_OK;
 }
 int orc_sim_run(orc_sim_t* s, int32_t n) {

@@ -7,7 +7,8 @@
  * L4CasADi, none of which is vendored under /root/reference or installed here, and the reference's tests hold no golden
  * vectors.  Pinned on reference code executed in the build container (tests/golden/make_ref_*.py,
  * tests/test_ref_golden.py): the network (a5, the reference's NeuralNetwork class), the controller state machines with the
- * warm-start shift (a8, a9, the reference's controller classes driven with scripted solves), the capsule distance (a4),
+ * warm-start shift (a8, a9, the reference's controller classes driven with scripted solves), the closed loop (a12, the simulation
+ * statements of the reference's scripts/mpc.py around those classes), the capsule distance (a4),
  * randomize_model (a13) and the configuration layer (the reference's Parameters on its own config.yaml).  The acados / HPIPM /
  * CasADi / adam numerics (a2, a3, a7, a11) are PARITY UNPINNED: that part of the restatement is pinned only by independent cross-checks
  * (tests/): finite differences, a numpy re-implementation of the chain algorithms, and direct verification of the KKT
@@ -67,6 +68,9 @@ int orc_sim_create(orc_handle_t* main_ctrl, orc_handle_t* backup, int32_t n_step
 void orc_sim_destroy(orc_sim_t* s);
 int orc_sim_reset(orc_sim_t* s, const double* x_init);
 int orc_sim_step(orc_sim_t* s);
+/* tests only: replace the solves of the following steps by scripted outcomes */
+int orc_sim_set_script(orc_sim_t* s, const int32_t* status, const double* xt, const double* ut, const int32_t* bk_status, const double* bk_xt,
+                       const double* bk_ut);
 int orc_sim_run(orc_sim_t* s, int32_t n_steps);
 int orc_sim_get_outcome(orc_sim_t* s, int32_t* outcome);
 int orc_sim_get_log(orc_sim_t* s, double* x, double* u);

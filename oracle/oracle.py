@@ -70,4 +70,8 @@ class Oracle(EngineBase):
 
 
 class OracleSim(SimBase):
-    pass
+    def set_script(self, status, xt, ut, bk_status, bk_xt, bk_ut):
+        """tests only: the solves of the following steps are replaced by these outcomes (arrays are kept alive here)"""
+        self._script = [np.ascontiguousarray(status, dtype=np.int32), np.ascontiguousarray(xt, dtype=np.float64), np.ascontiguousarray(ut, dtype=np.float64),
+                        np.ascontiguousarray(bk_status, dtype=np.int32), np.ascontiguousarray(bk_xt, dtype=np.float64), np.ascontiguousarray(bk_ut, dtype=np.float64)]
+        self._call('set_script', *[C.c_void_p(a.ctypes.data) for a in self._script])

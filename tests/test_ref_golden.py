@@ -164,3 +164,43 @@ def test_controller_state_machines_match_the_reference_classes(name):
         if name in ('stwa', 'htwa', 'receding', 'real_receding'):
             aborted = CG[f'{name}_abort'][:s + 1].any(axis=0) | (CG[f'{name}_fails'][:s + 1] > 0).any(axis=0)
             np.testing.assert_allclose(orc.get_x_viable()[aborted], CG[f'{name}_xv'][s][aborted], rtol=0, atol=1e-13, err_msg=f'x_viable, {where}')
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# reference scripts/mpc.py: the closed-loop simulation statements (row a12), executed unmodified around the reference's own controller
+# classes with scripted solve outcomes (tests/golden/make_ref_closed_loop.py); the oracle's closed loop is driven with the same script
+# ---------------------------------------------------------------------------------------------------------------------------
+LG = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'ref_closed_loop.npz'))
+
+
+@pytest.mark.parametrize('name', ['naive', 'htwa', 'receding'])
+def test_closed_loop_matches_the_reference_script(name):
+    from oracle.oracle import Oracle, OracleSim
+    from safe_mpc_b200 import abi
+    N, NB, B, steps = int(LG['N']), int(LG['NB']), int(LG['B']), int(LG['STEPS'])
+    prob, params, md = make_problem(name, N=N)
+    bprob, _, _ = make_problem('backup', cost='zero', N=NB)
+    main, bk = Oracle(prob, B, 1), Oracle(bprob, B, 1)
+    x_init = LG[f'{name}_x_init']
+    main.set_guess(np.repeat(x_init[:, None, :], N + 1, axis=1).copy(), np.zeros((B, N, abi.NU)))
+    main.reset_controller()
+    sim = OracleSim(main, bk, steps)
+    sim.reset(x_init)
+    for j in range(steps):
+        sim.set_script(LG[f'{name}_status'][:, j], LG[f'{name}_xt'][:, j], LG[f'{name}_ut'][:, j],
+                       LG[f'{name}_bk_status'][:, j], LG[f'{name}_bk_xt'][:, j], LG[f'{name}_bk_ut'][:, j])
+        sim.step()
+    x, u = sim.log()
+    gx, gu = LG[f'{name}_x'], LG[f'{name}_u']
+    np.testing.assert_array_equal(np.isnan(x), np.isnan(gx), err_msg='termination pattern of the state log')
+    np.testing.assert_array_equal(np.isnan(u), np.isnan(gu), err_msg='termination pattern of the control log')
+    np.testing.assert_allclose(np.nan_to_num(x), np.nan_to_num(gx), rtol=0, atol=1e-10)
+    np.testing.assert_allclose(np.nan_to_num(u), np.nan_to_num(gu), rtol=0, atol=1e-9)
+    out = sim.outcome()
+    conv = np.flatnonzero(out & abi.OUT_CONVERGED)
+    coll = np.flatnonzero(out & abi.OUT_COLLIDED)
+    viable = np.flatnonzero((out & abi.OUT_ABORTED) != 0) if hasattr(abi, 'OUT_ABORTED') else None
+    viable = np.array([i for i in viable if i not in conv and i not in coll], dtype=np.int64)      # mpc.py:273-285
+    unconv = np.setdiff1d(np.arange(B), np.concatenate([conv, coll, viable]))
+    np.testing.assert_array_equal(conv, LG[f'{name}_conv']); np.testing.assert_array_equal(coll, LG[f'{name}_coll'])
+    np.testing.assert_array_equal(viable, LG[f'{name}_viable']); np.testing.assert_array_equal(unconv, LG[f'{name}_unconv'])

@@ -6,8 +6,9 @@ controller.py cannot be imported (acados, casadi), so the class definitions are 
 UNMODIFIED; instances are made without ``__init__`` (which builds the acados OCP) and given the attributes the step methods use.  The
 three things a step calls outside the class are stand-ins:
   * ``solve(x)``                 returns a scripted status and stores scripted x_temp / u_temp (the solve itself is row a7, pinned elsewhere);
-  * ``model.checkStateConstraints`` / ``checkSafeConstraints``  evaluate the oracle's predicates (bounds on every row + collision on row 0,
-                                 viability value >= -tol), so that the same scripted trajectories mean the same thing to both sides;
+  * ``model.checkStateConstraints``  is the reference's own method (env_model.py:170-177,236-243, bodies extracted unmodified: bounds on
+                                 every row, collision check that returns after the first row) over the oracle's capsule distances;
+  * ``checkSafeConstraints``     the oracle's viability value >= -tol (the network is pinned separately);
   * ``model.integrate_naively``  the double integrator of env_model.py:63-71.
 What is recorded is everything the reference logic decides: control returned, abort flag, fails, receding index, viable state, next guess.
 
@@ -38,6 +39,18 @@ def reference_classes():
     return ns
 
 
+def reference_checks():
+    ENV = '/root/reference/src/safe_mpc/env_model.py'
+    cls = next(n for n in ast.parse(open(ENV).read()).body if isinstance(n, ast.ClassDef) and n.name == 'AdamModel')
+    keep = [n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name in ('checkStateConstraints', 'checkStateBounds', 'checkCollision')]
+    assert len(keep) == 3
+    mod = ast.Module(body=[ast.ClassDef(name='RefChecks', bases=[], keywords=[], body=keep, decorator_list=[])], type_ignores=[])
+    ast.fix_missing_locations(mod)
+    ns = {'np': np, 'deepcopy': deepcopy}
+    exec(compile(mod, ENV, 'exec'), ns)
+    return ns['RefChecks']()
+
+
 class _Solver:                                   # ocp_solver: the step methods only program flags / bounds on it
     def cost_set(self, *a): pass
     def set(self, *a): pass
@@ -55,11 +68,14 @@ def main():
         orc = Oracle(prob, 1, 1)
         tol = params.tol_safe_set
 
-        def check_state(traj, orc=orc, md=md, params=params):           # env_model.py:170-173 with the early return of :236-243
-            ok = np.all((traj >= md.x_min - params.tol_x) & (traj <= md.x_max + params.tol_x))
-            _, dist = orc.kinematics(traj[:1])
-            coll_free = np.all((np.array(prob.pair_lo_chk) <= dist[0]) & (dist[0] <= prob.pair_hi + params.tol_obs))
-            return bool(ok and coll_free)
+        # the reference's own predicates (env_model.py:170-177,236-243: checkStateConstraints -> bounds on every row and checkCollision,
+        # which returns after the FIRST row of a trajectory), method bodies extracted unmodified; the capsule distance functions they
+        # call are the oracle's
+        checks = reference_checks()
+        checks.x_min, checks.x_max, checks.params = md.x_min, md.x_max, types.SimpleNamespace(tol_x=params.tol_x)
+        checks.collisions_constr_fun = [[(lambda x, p=p, orc=orc: float(orc.kinematics(np.asarray(x)[None])[1][0, p])), prob.pair_lo_chk[p],
+                                         prob.pair_hi + params.tol_obs] for p in range(6)]
+        check_state = checks.checkStateConstraints
 
         def check_safe(x, orc=orc):                                      # safe_set.py:61-68
             c = orc.nn_constraint(np.asarray(x)[None], grad=False)[0]
@@ -70,6 +86,10 @@ def main():
                                                                    abort_flag=bool(params.abort_flag), N=N, use_net=True),
                                       checkStateConstraints=check_state,
                                       integrate_naively=lambda x, u, dt=params.dt: np.hstack([x[:5] + dt * x[5:] + 0.5 * dt * dt * u, x[5:] + dt * u]))
+        cand = random_states(md, 4000, seed=3, vel_scale=0.0)
+        dd = orc.kinematics(cand)[1]
+        bad = np.flatnonzero((dd < np.array(prob.pair_lo_chk)).any(axis=1) & ((cand >= md.x_min) & (cand <= md.x_max)).all(axis=1))
+        colliding = cand[bad[0]] if len(bad) else None
         rec = {k: [] for k in ('x', 'status', 'xt', 'ut', 'u', 'abort', 'fails', 'r', 'xv', 'xg', 'ug')}
         objs = []
         x0 = start_states(B, seed=7, vel=0.5)
@@ -93,6 +113,11 @@ def main():
             xt[:, :, 5:] *= rng.choice([0.2, 1.0, 3.0], size=(B, 1, 1))   # slow / fast trajectories: safe / unsafe under the viability row
             viol = rng.random(B) < 0.15
             xt[viol, 3, 0] = md.x_max[0] + 0.5                          # state-bound violation on a later row
+            if colliding is not None:
+                late = rng.random(B) < 0.2
+                xt[late, 4, :5] = colliding[:5]                         # a collision on a LATER row: not seen by the reference's checkCollision
+                first = (rng.random(B) < 0.1) & ~late
+                xt[first, 0, :5] = colliding[:5]                        # a collision on row 0: seen
             ut = rng.standard_normal((B, N, 5))
             us, abs_, fl, rr, xv, xgn, ugn = [], [], [], [], [], [], []
             for b, o in enumerate(objs):

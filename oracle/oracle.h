@@ -9,8 +9,8 @@
  * tests/test_ref_golden.py): the network (a5, the reference's NeuralNetwork class), the controller state machines with the
  * warm-start shift (a8, a9, the reference's controller classes driven with scripted solves), the closed loop (a12, the simulation
  * statements of the reference's scripts/mpc.py around those classes), the capsule distance (a4),
- * randomize_model (a13) and the configuration layer (the reference's Parameters on its own config.yaml).  The acados / HPIPM /
- * CasADi / adam numerics (a2, a3, a7, a11) are PARITY UNPINNED: that part of the restatement is pinned only by independent cross-checks
+ * the plant step and the feasibility predicates (a10, a11), randomize_model (a13) and the configuration layer (the reference's
+ * Parameters on its own config.yaml).  The acados / HPIPM / CasADi / adam numerics (a2, a3, a7) are PARITY UNPINNED: that part of the restatement is pinned only by independent cross-checks
  * (tests/): finite differences, a numpy re-implementation of the chain algorithms, and direct verification of the KKT
  * conditions of every QP solution.
  *

@@ -204,3 +204,33 @@ def test_closed_loop_matches_the_reference_script(name):
     unconv = np.setdiff1d(np.arange(B), np.concatenate([conv, coll, viable]))
     np.testing.assert_array_equal(conv, LG[f'{name}_conv']); np.testing.assert_array_equal(coll, LG[f'{name}_coll'])
     np.testing.assert_array_equal(viable, LG[f'{name}_viable']); np.testing.assert_array_equal(unconv, LG[f'{name}_unconv'])
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# reference env_model.py: AdamModel.integrate (row a11), method body executed unmodified (tests/golden/make_ref_plant.py)
+# ---------------------------------------------------------------------------------------------------------------------------
+PG = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'ref_plant.npz'))
+
+
+def test_plant_step_matches_the_reference_method():
+    from oracle.oracle import Oracle
+    B = PG['x'].shape[0]
+    prob, params, md = make_problem('naive', N=10)
+    orc = Oracle(prob, B, 1)
+    orc.set_plant_inertial(PG['pin'])
+    xn, a = orc.plant_step(PG['x'], PG['u'])
+    assert PG['sat'].sum() >= 5 and (~PG['sat']).sum() >= 5          # both branches of the saturation are exercised
+    np.testing.assert_allclose(a, PG['acc'], rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(xn, PG['xn'], rtol=1e-11, atol=1e-11)
+
+
+@pytest.mark.gpu
+def test_engine_plant_step_matches_the_reference_method():
+    from safe_mpc_b200.engine import Engine
+    B = PG['x'].shape[0]
+    prob, params, md = make_problem('naive', N=10)
+    eng = Engine(prob, B, 0)
+    eng.set_plant_inertial(PG['pin'])
+    xn, a = eng.plant_step(PG['x'], PG['u'])
+    np.testing.assert_allclose(a, PG['acc'], rtol=1e-8, atol=1e-8)
+    np.testing.assert_allclose(xn, PG['xn'], rtol=1e-10, atol=1e-10)

@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(32 * PREP_WARPS, QS_PREP_MINB) qs_prep_kernel(
 //           every row leaves (nu = lam_u - lam_l, gam = c_l - c_u, G = G_l + G_u) in the shared-memory slots of its own,
 //           already consumed, multipliers; every warp leaves its residual-norm partials the same way
 //   merge   warp 0: C' nu, C' gam -> stationarity residual and affine gradient, norms     warps 1-3: rows of H + C' G C
-// Same arithmetic per term as qs_prep<false>; only the order of the sums over the row groups differs.
+// Same arithmetic per term and the same summation orders as qs_prep<false>: the two forms agree to the last bit.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int PC_REC0 = SMPC_REC_X;                       // first staged record field (the controls of the guess are not needed)
 constexpr int PC_NREC = 180;                              // staged record fields [5, 185)
@@ -164,10 +164,10 @@ __global__ void __launch_bounds__(32 * PC_WARPS, 2) qs_prep_coop_kernel(const sm
   auto side = [&](int slot, double sgn, double az, double bnd, double slack, double lam, double t, double& G, double& c) {
     if (on) { QF(ito, I_LAM + slot) = lam; QF(ito, I_T + slot) = t; }
     const double r = t - (sgn * (az - bnd) + slack);
-    const double rm = lam * t;
-    const double it_ = qs_rcp(t);
-    G = lam * it_;
-    c = (rm - lam * r) * it_;
+    const double rm = QS_MUL(lam, t);                      // (QS_MUL: see the note at its definition)
+    const double it_ = QS_SRCP(t);
+    G = QS_MUL(lam, it_);
+    c = QS_MUL(fma(-lam, r, rm), it_);
     nr.mu += rm; nr.chk += rm + r; nr.nm = fmax(nr.nm, fabs(rm)); nr.nd = fmax(nr.nd, fabs(r)); nr.cnt += 1;
   };
   // a hard two-sided row: update, residuals, (nu, gam, G) into the row's own shared-memory slots
@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(32 * PC_WARPS, 2) qs_prep_coop_kernel(const sm
         rb[j] = z[5 + j] + dt * z[10 + j] + a2 * z[j] + QF(rs, SMPC_REC_B + j);
         rb[5 + j] = z[10 + j] + dt * z[j] + QF(rs, SMPC_REC_B + 5 + j);
         const double pq = pqn[j], pv = pqn[5 + j];
-        rg[j] += a2 * pq + dt * pv;
+        rg[j] += fma(a2, pq, QS_MUL(dt, pv));
         rg[5 + j] += pq;
         rg[10 + j] += dt * pq + pv;
         rb[j] -= znx[j];
@@ -275,11 +275,11 @@ __global__ void __launch_bounds__(32 * PC_WARPS, 2) qs_prep_coop_kernel(const sm
         for (int h = 0; h < 2; ++h) {
           const double rsl = ts[h] - sl[h];
           const double rgs = F.zpen - lam2[h] - ls[h];
-          const double rms = ls[h] * ts[h];
-          const double its = qs_rcp(ts[h]);
-          const double Gs = ls[h] * its;
-          const double cs = (rms - ls[h] * rsl) * its;
-          const double Wl = qs_rcp(G2[h] + Gs);
+          const double rms = QS_MUL(ls[h], ts[h]);
+          const double its = QS_SRCP(ts[h]);
+          const double Gs = QS_MUL(ls[h], its);
+          const double cs = QS_MUL(fma(-ls[h], rsl, rms), its);
+          const double Wl = QS_SRCP(G2[h] + Gs);
           c2[h] = c2[h] - G2[h] * Wl * (rgs + c2[h] + cs);
           G2[h] = G2[h] * Gs * Wl;
           nr.mu += rms; nr.chk += rms + rsl + rgs;
@@ -291,11 +291,12 @@ __global__ void __launch_bounds__(32 * PC_WARPS, 2) qs_prep_coop_kernel(const sm
       pc_row_out(s_it, 21, lu - ll, cl - cu, Gl + Gu);
     }
   }
-  // residual-norm partials of this warp -> consumed step slots of its first rows (warp 0: box 0, 1; 1: box 4, 5; 2: torque 0, 1; 3: capsule 0, 1)
+  // residual-norm partials of this warp -> consumed step slots of its first rows (warp 0: box 0-2; 1: box 4-6; 2: torque 0-2; 3: capsule 0-2)
   {
     const int s0 = wi == 0 ? 0 : (wi == 1 ? 4 : (wi == 2 ? 10 : 15));
-    QF(s_st, I_LAM + s0) = nr.mu; QF(s_st, I_LAM + QNR + s0) = nr.chk; QF(s_st, I_T + s0) = nr.nm; QF(s_st, I_T + QNR + s0) = nr.nd;
-    QF(s_st, I_LAM + s0 + 1) = nr.ng; QF(s_st, I_LAM + QNR + s0 + 1) = (double)nr.cnt;
+    QF(s_st, I_LAM + s0) = nr.chk; QF(s_st, I_LAM + QNR + s0) = nr.nm; QF(s_st, I_LAM + s0 + 1) = nr.nd;
+    QF(s_st, I_LAM + QNR + s0 + 1) = nr.ng; QF(s_st, I_LAM + s0 + 2) = (double)nr.cnt;
+    QF(s_st, I_LAM + QNR + s0 + 2) = nr.mu;
   }
   __syncthreads();
 
@@ -335,10 +336,12 @@ __global__ void __launch_bounds__(32 * PC_WARPS, 2) qs_prep_coop_kernel(const sm
 #pragma unroll
     for (int w = 0; w < PC_WARPS; ++w) {
       const int s0 = w == 0 ? 0 : (w == 1 ? 4 : (w == 2 ? 10 : 15));
-      mu += QF(s_st, I_LAM + s0); chk += QF(s_st, I_LAM + QNR + s0);
-      nm = fmax(nm, QF(s_st, I_T + s0)); nd = fmax(nd, QF(s_st, I_T + QNR + s0));
-      ng = fmax(ng, QF(s_st, I_LAM + s0 + 1)); cnt += QF(s_st, I_LAM + QNR + s0 + 1);
+      chk += QF(s_st, I_LAM + s0);
+      nm = fmax(nm, QF(s_st, I_LAM + QNR + s0)); nd = fmax(nd, QF(s_st, I_LAM + s0 + 1));
+      ng = fmax(ng, QF(s_st, I_LAM + QNR + s0 + 1)); cnt += QF(s_st, I_LAM + s0 + 2);
     }
+    // mu: the four partial sums in warp order, as qs_prep forms them (bit-identical results whichever form serves a problem)
+    mu = ((QF(s_st, I_LAM + QNR + 2) + QF(s_st, I_LAM + QNR + 6)) + QF(s_st, I_LAM + QNR + 12)) + QF(s_st, I_LAM + QNR + 17);
 #pragma unroll
     for (int i = 0; i < 15; ++i) { ng = fmax(ng, fabs(rg[i])); chk += rg[i]; if (on) QF(hc, H_GA + i) = rg[i] + gd[i]; }
     if (on) {

@@ -154,6 +154,22 @@ struct QsNorms {
 // jsm: lane-private on-chip scratch [PREP_SCRATCH][TL] (lane offset applied) that keeps the torque and capsule Jacobians
 // of the stage between their three uses (row products, multiplier terms, condensation): each entry is read ~10 times.
 enum { PREP_SCRATCH = 105 };
+// A product that must stay a product.  With -fmad the compiler may contract  x*y + u*v  either way round, and it decides per
+// kernel; the thread-per-stage and the cooperative form of prep must agree to the last bit (a problem's result must not depend on
+// which form served it), so the few expressions with two candidate contractions are written with their rounding pinned.
+// Slot reciprocals of prep (the same in both forms, so that they stay bit-identical): the branch-free reciprocal (measured 1 % of
+// a solve faster than the IEEE division, which -DQS_SLOT_IEEE brings back).
+#ifdef QS_SLOT_IEEE
+#define QS_SRCP(x) (1.0 / (x))
+#else
+#define QS_SRCP(x) qs_rcp(x)
+#endif
+#ifdef __CUDA_ARCH__
+#define QS_MUL(x, y) __dmul_rn((x), (y))
+#else
+#define QS_MUL(x, y) ((x) * (y))
+#endif
+
 template <bool FIRST>
 SMPC_HD void qs_prep(const smpc_problem_t& P, const QsBufs& q, int tile, int lane, int k, int kk, double* jsm) {
   const int N = q.N;
@@ -236,7 +252,7 @@ SMPC_HD void qs_prep(const smpc_problem_t& P, const QsBufs& q, int tile, int lan
       for (int j = 0; j < 5; ++j) {
         const double pq = QF(itn, I_PIM + j) + a * QF(stn, I_PIM + j);
         const double pv = QF(itn, I_PIM + 5 + j) + a * QF(stn, I_PIM + 5 + j);
-        if (k < N) { rg[j] += a2 * pq + dt * pv; }
+        if (k < N) { rg[j] += fma(a2, pq, QS_MUL(dt, pv)); }
         rg[5 + j] += pq;
         rg[10 + j] += dt * pq + pv;
         rb[j] -= QF(itn, I_Z + 5 + j) + a * QF(stn, I_Z + 5 + j);
@@ -264,14 +280,18 @@ SMPC_HD void qs_prep(const smpc_problem_t& P, const QsBufs& q, int tile, int lan
     }
   };
   // one side of a row; returns G = lam/t and c = (lam t - lam r)/t  (mode-0 right-hand side)
+  // mu is summed in four partial sums -- box rows 0-3, box rows 4-9, torque rows, capsule + viability rows (+ slacks) -- and the
+  // partial sums in that order: the row groups of the four warps of qs_prep_coop, so that both forms round alike
+  double mup[4] = {0.0, 0.0, 0.0, 0.0};
   auto side = [&](int slot, double sgn, double az, double bnd, double slack, double lam, double t, double& G, double& c) {
     QF(ito, I_LAM + slot) = lam; QF(ito, I_T + slot) = t;
     const double r = t - (sgn * (az - bnd) + slack);
-    const double rm = lam * t;
-    const double it_ = 1.0 / t;
-    G = lam * it_;
-    c = (rm - lam * r) * it_;
-    nr.mu += rm; nr.chk += rm + r; nr.nm = fmax(nr.nm, fabs(rm)); nr.nd = fmax(nr.nd, fabs(r)); nr.cnt += 1;
+    const double rm = QS_MUL(lam, t);                      // (QS_MUL: see the note at its definition)
+    const double it_ = QS_SRCP(t);
+    G = QS_MUL(lam, it_);
+    c = QS_MUL(fma(-lam, r, rm), it_);
+    mup[slot % QNR < 4 ? 0 : (slot % QNR < 10 ? 1 : (slot % QNR < 15 ? 2 : 3))] += rm;
+    nr.chk += rm + r; nr.nm = fmax(nr.nm, fabs(rm)); nr.nd = fmax(nr.nd, fabs(r)); nr.cnt += 1;
   };
   // row products and bounds of the general rows (loads only)
   double azg[12], glo[12], ghi[12];
@@ -390,14 +410,14 @@ SMPC_HD void qs_prep(const smpc_problem_t& P, const QsBufs& q, int tile, int lan
       for (int h = 0; h < 2; ++h) {
         const double rsl = ts[h] - sl[h];
         const double rgs = F.zpen - lam2[h] - ls[h];
-        const double rms = ls[h] * ts[h];
-        const double its = 1.0 / ts[h];
-        const double Gs = ls[h] * its;
-        const double cs = (rms - ls[h] * rsl) * its;
-        const double Wl = 1.0 / (G2[h] + Gs);
+        const double rms = QS_MUL(ls[h], ts[h]);
+        const double its = QS_SRCP(ts[h]);
+        const double Gs = QS_MUL(ls[h], its);
+        const double cs = QS_MUL(fma(-ls[h], rsl, rms), its);
+        const double Wl = QS_SRCP(G2[h] + Gs);
         c2[h] = c2[h] - G2[h] * Wl * (rgs + c2[h] + cs);
         G2[h] = G2[h] * Gs * Wl;
-        nr.mu += rms; nr.chk += rms + rsl + rgs;
+        mup[3] += rms; nr.chk += rms + rsl + rgs;
         nr.nm = fmax(nr.nm, fabs(rms)); nr.nd = fmax(nr.nd, fabs(rsl)); nr.ng = fmax(nr.ng, fabs(rgs));
         nr.cnt += 1;
       }
@@ -456,7 +476,7 @@ SMPC_HD void qs_prep(const smpc_problem_t& P, const QsBufs& q, int tile, int lan
   }
   double* res = q.res + qs_blk(tile, N, k, NRES, lane);
   QF(res, R_NG) = nr.ng; QF(res, R_NB) = nr.nb; QF(res, R_ND) = nr.nd; QF(res, R_NM) = nr.nm;
-  QF(res, R_MU) = nr.mu; QF(res, R_CHK) = nr.chk; QF(res, R_CNT) = (double)nr.cnt;
+  QF(res, R_MU) = ((mup[0] + mup[1]) + mup[2]) + mup[3]; QF(res, R_CHK) = nr.chk; QF(res, R_CNT) = (double)nr.cnt;
 }
 
 // ================================================================================================================

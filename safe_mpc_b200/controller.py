@@ -144,6 +144,64 @@ class AbstractController:
 class NaiveController(AbstractController):               # controller.py:251-284
     engine_name = 'naive'
 
+    def _all_nodes_collision_free(self, x):
+        ok = np.ones(self.B, dtype=bool)
+        for k in range(x.shape[1]):
+            ok &= self.model.checkCollision(x[:, k])
+        return ok
+
+    def checkGuess(self):
+        """controller.py:255-258, one flag per problem: running constraints, dynamics defect and collisions of (x_temp, u_temp)."""
+        x, u = self.x_temp, self.u_temp
+        return self.model.checkRunningConstraints(x, u) & self.model.checkDynamicsConstraints(x, u) & self._all_nodes_collision_free(x)
+
+    def solve_sqp(self, x0, max_iter=None, tol=1e-6, active=None):
+        """The SQP solve of the guess generator (guess_acados.py builds its controllers with rti=False: acados 'SQP',
+        nlp_max_iter): RTI iterations of the engine repeated per problem until the full step is below ``tol`` (infinity norm
+        over the trajectory) -> status 0; a problem still moving after ``max_iter`` iterations -> status 2, as acados reports
+        it; a QP failure keeps its status (1, 3, 4) and stops that problem.  Finished problems are frozen through the engine's
+        ``active`` mask, so the batch shrinks as it converges.  Full steps: acados' MERIT_BACKTRACKING line search
+        (parser.py:139) is not restated.  -> status [B]; (x_temp, u_temp) hold every problem's last iterate."""
+        max_iter = int(self.model.params.nlp_max_iter if max_iter is None else max_iter)
+        x0 = np.ascontiguousarray(x0, dtype=np.float64).reshape(self.B, abi.NX)
+        todo = np.ones(self.B, dtype=bool) if active is None else np.asarray(active, dtype=bool).copy()
+        status = np.where(todo, 2, 0).astype(np.int32)
+        xg, ug = (a.copy() for a in self.getGuess())
+        x_fin, u_fin = xg.copy(), ug.copy()
+        self.sqp_iter = np.zeros(self.B, dtype=np.int32)
+        for _ in range(max_iter):
+            if not todo.any():
+                break
+            st = self.solve(x0, todo.astype(np.uint8))
+            xt, ut = self.x_temp, self.u_temp
+            self.sqp_iter[todo] += 1
+            bad = todo & (st != 0)
+            status[bad] = st[bad]
+            good = todo & (st == 0)
+            step = np.maximum(np.abs(xt - xg).reshape(self.B, -1).max(axis=1), np.abs(ut - ug).reshape(self.B, -1).max(axis=1))
+            x_fin[good], u_fin[good] = xt[good], ut[good]
+            xg[good], ug[good] = xt[good], ut[good]
+            conv = good & (step < tol)
+            status[conv] = 0
+            todo &= ~(bad | conv)
+            self.setGuess(xg, ug)
+        self._sqp_result = (x_fin, u_fin)
+        return status
+
+    def initialize(self, x0, u0=None):
+        """controller.py:260-272 for the batch: trivial guess, solve, keep the solution as the guess where it succeeded and
+        passes checkGuess -> 1 / 0 per problem."""
+        x0 = np.ascontiguousarray(x0, dtype=np.float64).reshape(self.B, abi.NX)
+        xg = np.repeat(x0[:, None, :], self.N + 1, axis=1)
+        ug = np.zeros((self.B, self.N, abi.NU)) if u0 is None else np.broadcast_to(np.asarray(u0, dtype=np.float64), (self.B, self.N, abi.NU)).copy()
+        self.setGuess(xg, ug)
+        status = self.solve(x0)
+        ok = (status == 0) & self.checkGuess()
+        xt, ut = self.x_temp, self.u_temp
+        xg[ok], ug[ok] = xt[ok], ut[ok]
+        self.setGuess(xg, ug)
+        return ok.astype(np.int32)
+
 
 class TerminalZeroVelocity(NaiveController):             # controller.py:295-317
     engine_name = 'zerovel'
@@ -155,6 +213,10 @@ class STController(NaiveController):                     # controller.py:319-361
 
 class STWAController(STController):                      # controller.py:364-393
     engine_name = 'stwa'
+
+    def checkGuess(self):
+        """controller.py:369-373: the checks of NaiveController plus the viability constraint at the terminal node."""
+        return super().checkGuess() & self.checkSafeConstraints(self.x_temp[:, -1])
 
 
 class HTWAController(STWAController):                    # controller.py:396-401

@@ -85,6 +85,45 @@ class AdamModel:
         x = self._rows(x)
         return bool(self.checkStateBounds(x).all() and self.checkCollision(x[:1])[0])
 
+    def checkTorqueConstraints(self, x, u):
+        """env_model.py:179-182 for trajectories x [B, N+1, nx], u [B, N, nu] -> one flag per problem."""
+        x, u = np.asarray(x, dtype=np.float64), np.asarray(u, dtype=np.float64)
+        ok = np.ones(x.shape[0], dtype=bool)
+        for k in range(u.shape[1]):
+            ok &= self.checkTorqueBounds(self.tau_fun(x[:, k], u[:, k]))
+        return ok
+
+    def checkRunningConstraints(self, x, u):
+        """env_model.py:189-190 per problem: state bounds on every node, collision on node 0 only (the early return of
+        env_model.py:237-244), torque bounds on every interval."""
+        x = np.asarray(x, dtype=np.float64)
+        ok = np.logical_and(x >= self.x_min - self.params.tol_x, x <= self.x_max + self.params.tol_x).all(axis=(1, 2))
+        return ok & self.checkCollision(x[:, 0]) & self.checkTorqueConstraints(x, u)
+
+    def integrate_controller_model(self, x, u):
+        """env_model.py:212-224, rows of x / u: the nominal model, no noise; the torque is saturated and the acceleration
+        recomputed only where it leaves the bounds (inside them the engine's M^-1 (tau - h) returns u to rounding)."""
+        e = self.engine()
+        e.set_plant_inertial(np.tile(self.data.inertial, (self.batch, 1, 1)))
+        e.set_torque_noise(np.zeros((self.batch, self.nu)))
+        try:
+            x_next, u_app = e.plant_step(self._rows(x), self._rows(u))
+        finally:
+            e.set_plant_inertial(self.plant_inertial)
+            e.set_torque_noise(self.torque_noise)
+        return x_next, u_app
+
+    def checkDynamicsConstraints(self, x, u):
+        """env_model.py:226-234 per problem: roll the controls out with the controller model and compare the trajectories,
+        ||x - x_sim||_F < tol_dyn sqrt(n + 1)."""
+        x, u = np.asarray(x, dtype=np.float64), np.asarray(u, dtype=np.float64)
+        n = u.shape[1]
+        x_sim = np.zeros_like(x)
+        x_sim[:, 0] = x[:, 0]
+        for i in range(n):
+            x_sim[:, i + 1], _ = self.integrate_controller_model(x_sim[:, i], u[:, i])
+        return np.linalg.norm((x - x_sim).reshape(x.shape[0], -1), axis=1) < self.params.tol_dyn * np.sqrt(n + 1)
+
     def integrate(self, x, u):
         """env_model.py:192-206 for the whole batch: nominal torque + noise, clipped, forward dynamics of the perturbed
         plant, double-integrator update.  -> (x_next [B, nx], applied acceleration [B, nu])."""

@@ -1,12 +1,17 @@
 #!/usr/bin/env python
-"""Warm-start file generator -- writes the reference's ``*_guess.pkl`` ({'xg', 'ug'}, guess_acados.py:235-244) from the
-reference's Halton initial conditions and full-step SQP iterations of the engine (safe_mpc_b200/guess.py).
+"""Warm-start file generator -- the reference's scripts/guess_acados.py for a batch of initial conditions at a time.
+
+Writes the reference's ``*_guess.pkl`` files ({'xg', 'ug'}, guess_acados.py:235-244, same file names): Halton initial
+conditions, the controller named by ``-c`` solved to convergence from the trivial guess and accepted on status 0 / 2 +
+``checkGuess``; the naive and zero-velocity files hold their own solutions where those pass the same test and the network
+controller's trajectory otherwise (guess_acados.py:132-150).  All of it is safe_mpc_b200.guess.generate_guesses.
 
     python scripts/guess_acados.py -c st --horizon 45 --alpha 10 [--batch 100]
 """
 import os
 import pickle
 import sys
+import time
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..'))
 
@@ -14,31 +19,55 @@ from safe_mpc_b200.parser import Parameters, parse_args            # noqa: E402
 from safe_mpc_b200.env_model import AdamModel                      # noqa: E402
 from safe_mpc_b200.utils import get_controller                     # noqa: E402
 from safe_mpc_b200.cost_definition import ReachTargetEXT           # noqa: E402
-from safe_mpc_b200.guess import halton_initial_states, sqp_guess   # noqa: E402
+from safe_mpc_b200.guess import generate_guesses                   # noqa: E402
+
+NET_CONTROLLERS = ['st', 'stwa', 'htwa', 'receding', 'real_receding', 'parallel', 'constraint_everywhere']     # guess_acados.py:242
 
 
-def main(argv=None):
-    args = parse_args(argv)
-    params = Parameters(args, args['system'], rti=True)
+def make_controller(name, args, batch):
+    params = Parameters(args, args['system'], rti=False)               # guess_acados.py:27,45,56: SQP, nlp_max_iter
     params.q_margin = args['joint_bounds_margin']
     params.collision_margin = args['collision_margin']
     params.alpha = args['alpha']
     params.N = args['horizon']
-    batch = args['batch'] or params.test_num
     model = AdamModel(params, batch=batch)
-    cont_name = args['controller']
-    controller = get_controller(cont_name, model)
+    controller = get_controller(name, model)
     ReachTargetEXT(model, params.Q_weight, params.R_weight).set_solver_cost(controller)
     controller.build_controller(args['build'])
-    x_init = halton_initial_states(model, batch)
-    xg, ug, st = sqp_guess(controller, x_init, iters=20)
-    use_net = True if cont_name not in ('naive', 'zerovel') else None
-    path = (f'{params.DATA_DIR}{args["system"]}_{cont_name}_{params.N}hor_{int(params.alpha)}sm_use_net{use_net}__q_collision_margins_'
-            f'{params.q_margin}_{params.collision_margin}_guess.pkl')
+    return controller, params
+
+
+def main(argv=None):
+    args = parse_args(argv)
+    cont_name = args['controller']
+    probe = Parameters(args, args['system'], rti=False)
+    count = probe.test_num
+    batch = args['batch'] or count
+    ctrl, params = make_controller(cont_name, args, batch)
+    naive = zerovel = None
+    if cont_name not in ('naive', 'zerovel'):
+        naive, _ = make_controller('naive', args, batch)
+        zerovel, _ = make_controller('zerovel', args, batch)
+    t0 = time.time()
+    out, stats = generate_guesses(ctrl, naive, zerovel, count, sqp_iter=min(params.nlp_max_iter, args.get('sqp_iter') or 100))
+    print(f'{stats["succ"]} accepted, {stats["fails"]} failed, {stats["skipped"]} initial conditions in collision, '
+          f'{stats["rounds"]} batches of {batch}, {time.time() - t0:.1f} s')
+
+    def path(name, use_net):
+        return (f'{params.DATA_DIR}{args["system"]}_{name}_{params.N}hor_{int(params.alpha)}sm_use_net{use_net}__q_collision_margins_'
+                f'{params.q_margin}_{params.collision_margin}_guess.pkl')
+
     os.makedirs(params.DATA_DIR, exist_ok=True)
-    with open(path, 'wb') as f:
-        pickle.dump({'xg': xg, 'ug': ug}, f)
-    print(f'{int((st == 0).sum())}/{batch} solves ended with status 0; saved {path}')
+    files = []
+    if cont_name in ('naive', 'zerovel'):
+        files.append((path(cont_name, None), out['net']))
+    else:
+        files += [(path('naive', None), out['naive']), (path('zerovel', None), out['zerovel'])]
+        files += [(path(c, True), out['net']) for c in NET_CONTROLLERS]
+    for p, d in files:
+        with open(p, 'wb') as f:
+            pickle.dump({'xg': d['xg'], 'ug': d['ug']}, f)
+        print('saved', p, d['xg'].shape)
 
 
 if __name__ == '__main__':

@@ -150,24 +150,54 @@ class NaiveController(AbstractController):               # controller.py:251-284
             ok &= self.model.checkCollision(x[:, k])
         return ok
 
-    def checkGuess(self):
-        """controller.py:255-258, one flag per problem: running constraints, dynamics defect and collisions of (x_temp, u_temp)."""
-        x, u = self.x_temp, self.u_temp
+    def checkGuess(self, x=None, u=None):
+        """controller.py:255-258, one flag per problem: running constraints, dynamics defect and collisions of (x_temp, u_temp)
+        -- or of the trajectories passed in (the last iterate of ``solve_sqp``)."""
+        x, u = (self.x_temp if x is None else x), (self.u_temp if u is None else u)
         return self.model.checkRunningConstraints(x, u) & self.model.checkDynamicsConstraints(x, u) & self._all_nodes_collision_free(x)
 
-    def solve_sqp(self, x0, max_iter=None, tol=1e-6, active=None):
+    def merit(self, x, u, mu):
+        """l1 merit of a trajectory, per problem: the cost of cost_definition.py:91-96 (EE tracking + control effort, terminal
+        EE tracking) + mu * (violation of the torque rows, the capsule rows and -- controllers with a terminal viability row --
+        c(x_N) >= 0).  The dynamics and the state box are linear: a step between two points that satisfy them satisfies them."""
+        p, m = self.model.params, self.model
+        B, N = x.shape[0], u.shape[1]
+        eng = m.engine()
+        ee, dist = eng.kinematics(np.ascontiguousarray(x.reshape(-1, abi.NX)))
+        e = ee.reshape(B, N + 1, 3) - np.asarray(p.ee_ref)
+        cost = p.Q_weight * (e * e).sum(axis=(1, 2)) + p.R_weight * (u * u).sum(axis=(1, 2))
+        tau = eng.tau(np.ascontiguousarray(x[:, :N].reshape(-1, abi.NX)), np.ascontiguousarray(u.reshape(-1, abi.NU))).reshape(B, N, abi.NU)
+        viol = (np.maximum(m.tau_min - tau, 0.0) + np.maximum(tau - m.tau_max, 0.0)).sum(axis=(1, 2))
+        lo = np.array([pr['lo_ocp'] for pr in m.data.pairs])
+        viol += np.maximum(lo - dist.reshape(B, N + 1, -1), 0.0).sum(axis=(1, 2))
+        if self.engine_name in ('st', 'stwa', 'htwa'):
+            viol += np.maximum(-self._solver().nn_constraint(np.ascontiguousarray(x[:, -1]), grad=False), 0.0)
+        return cost + mu * viol
+
+    def solve_sqp(self, x0, max_iter=None, tol=1e-6, active=None, globalization=None):
         """The SQP solve of the guess generator (guess_acados.py builds its controllers with rti=False: acados 'SQP',
         nlp_max_iter): RTI iterations of the engine repeated per problem until the full step is below ``tol`` (infinity norm
         over the trajectory) -> status 0; a problem still moving after ``max_iter`` iterations -> status 2, as acados reports
         it; a QP failure keeps its status (1, 3, 4) and stops that problem.  Finished problems are frozen through the engine's
-        ``active`` mask, so the batch shrinks as it converges.  Full steps: acados' MERIT_BACKTRACKING line search
-        (parser.py:139) is not restated.  -> status [B]; (x_temp, u_temp) hold every problem's last iterate."""
+        ``active`` mask, so the batch shrinks as it converges.  ``globalization``: 'FIXED_STEP' (default) takes full steps --
+        with the reference's Levenberg-Marquardt term (0.5) the iteration is heavily damped already and ends on the iteration
+        limit, which the generator accepts like the reference does.  'MERIT_BACKTRACKING' (what parser.py:139 selects for the
+        reference's generator) shortens the step by ``alpha_reduction`` until the l1 merit (``merit``, penalty = the largest
+        inequality multiplier of the QP, at least 1) decreases, down to ``alpha_min``, which is then taken regardless: the
+        structure of acados' line search with a plain decrease test.  acados' own merit weights and Armijo constant are not
+        restated (they cannot be pinned here), and in the probes (scripts/sqp_probe.py) this search did not raise the number
+        of accepted guesses, so it is opt-in.  -> status [B]; the last iterate of every problem (what acados' get(i, 'x')
+        returns after its SQP solve) is ``self._sqp_result`` = getGuess(); (x_temp, u_temp) hold the last QP solution, the
+        same thing when the last step was a full one."""
+        p = self.model.params
+        glob = 'FIXED_STEP' if globalization is None else globalization
+        if glob not in ('FIXED_STEP', 'MERIT_BACKTRACKING'):
+            raise ValueError(f'unknown globalization {glob}')
         max_iter = int(self.model.params.nlp_max_iter if max_iter is None else max_iter)
         x0 = np.ascontiguousarray(x0, dtype=np.float64).reshape(self.B, abi.NX)
         todo = np.ones(self.B, dtype=bool) if active is None else np.asarray(active, dtype=bool).copy()
         status = np.where(todo, 2, 0).astype(np.int32)
         xg, ug = (a.copy() for a in self.getGuess())
-        x_fin, u_fin = xg.copy(), ug.copy()
         self.sqp_iter = np.zeros(self.B, dtype=np.int32)
         for _ in range(max_iter):
             if not todo.any():
@@ -179,13 +209,30 @@ class NaiveController(AbstractController):               # controller.py:251-284
             status[bad] = st[bad]
             good = todo & (st == 0)
             step = np.maximum(np.abs(xt - xg).reshape(self.B, -1).max(axis=1), np.abs(ut - ug).reshape(self.B, -1).max(axis=1))
-            x_fin[good], u_fin[good] = xt[good], ut[good]
+            if glob == 'MERIT_BACKTRACKING' and good.any():
+                lam = self._solver().get_qp()[2]
+                mu = np.maximum(1.0, lam.reshape(self.B, -1).max(axis=1))
+                phi0 = self.merit(xg, ug, mu)
+                alpha = np.ones(self.B)
+                pend = good & (step >= tol)
+                while pend.any():
+                    a = alpha[:, None, None]
+                    phi = self.merit(xg + a * (xt - xg), ug + a * (ut - ug), mu)
+                    pend &= ~(phi < phi0)
+                    nxt = alpha * p.alpha_reduction
+                    stop = pend & (nxt < p.alpha_min)
+                    alpha[stop] = p.alpha_min
+                    pend &= ~stop
+                    alpha[pend] = nxt[pend]
+                self.sqp_alpha = alpha
+                a = alpha[:, None, None]
+                xt, ut = xg + a * (xt - xg), ug + a * (ut - ug)
             xg[good], ug[good] = xt[good], ut[good]
             conv = good & (step < tol)
             status[conv] = 0
             todo &= ~(bad | conv)
             self.setGuess(xg, ug)
-        self._sqp_result = (x_fin, u_fin)
+        self._sqp_result = (xg, ug)
         return status
 
     def initialize(self, x0, u0=None):
@@ -214,9 +261,10 @@ class STController(NaiveController):                     # controller.py:319-361
 class STWAController(STController):                      # controller.py:364-393
     engine_name = 'stwa'
 
-    def checkGuess(self):
+    def checkGuess(self, x=None, u=None):
         """controller.py:369-373: the checks of NaiveController plus the viability constraint at the terminal node."""
-        return super().checkGuess() & self.checkSafeConstraints(self.x_temp[:, -1])
+        x = self.x_temp if x is None else x
+        return super().checkGuess(x, u) & self.checkSafeConstraints(x[:, -1])
 
 
 class HTWAController(STWAController):                    # controller.py:396-401

@@ -5,7 +5,7 @@ trivial guess and keeps the ones whose status is 0 or 2 and whose solution passe
 controllers are solved from the same initial conditions and fall back to the network controller's trajectory where they fail
 (guess_acados.py:113-150).  Here the same procedure runs for a whole batch of initial conditions at a time:
 ``generate_guesses`` (the loop of guess_acados.py:98-159), on ``controller.solve_sqp`` (RTI iterations of the engine to
-convergence, full steps) and the batched ``checkGuess``.  ``sqp_guess`` -- a fixed number of full-step iterations, no
+convergence, with an l1-merit backtracking line search) and the batched ``checkGuess``.  ``sqp_guess`` -- a fixed number of full-step iterations, no
 acceptance test -- is what bench.py and scripts/mpc.py use when no guess file exists.
 """
 from __future__ import annotations
@@ -56,7 +56,7 @@ def halton_initial_states(model, count, shipped_ic=False):
     return HaltonInitialStates(model, shipped_ic).draw(count)
 
 
-def generate_guesses(ctrl_net, ctrl_naive, ctrl_zerovel, count, shipped_ic=False, max_rounds=50, sqp_iter=None, tol=1e-6):
+def generate_guesses(ctrl_net, ctrl_naive, ctrl_zerovel, count, shipped_ic=False, max_rounds=50, sqp_iter=None, tol=1e-6, globalization=None):
     """guess_acados.py:98-159 for batches of initial conditions.  Every round draws one batch of collision-free Halton points,
     solves the network controller to convergence from the trivial guess and accepts a problem when its status is 0 or 2 and
     ``checkGuess`` holds; for the accepted ones the naive and the zero-velocity controller are solved from the same trivial
@@ -77,17 +77,18 @@ def generate_guesses(ctrl_net, ctrl_naive, ctrl_zerovel, count, shipped_ic=False
         xg0 = np.repeat(x0[:, None, :], N + 1, axis=1)
         ug0 = np.zeros((B, N, abi.NU))
         ctrl_net.setGuess(xg0, ug0)
-        st = ctrl_net.solve_sqp(x0, max_iter=sqp_iter, tol=tol)
-        ok = ((st == 0) | (st == 2)) & ctrl_net.checkGuess()                      # guess_acados.py:118
-        x_net, u_net = ctrl_net.x_temp, ctrl_net.u_temp
+        st = ctrl_net.solve_sqp(x0, max_iter=sqp_iter, tol=tol, globalization=globalization)
+        x_net, u_net = ctrl_net._sqp_result
+        ok = ((st == 0) | (st == 2)) & ctrl_net.checkGuess(x_net, u_net)          # guess_acados.py:118
         stats['fails'] += int((~ok).sum())
         stats['succ'] += int(ok.sum())
         acc['net']['xg'].append(x_net[ok]); acc['net']['ug'].append(u_net[ok])
         for name, c in others:                                                    # guess_acados.py:132-150
             c.setGuess(xg0, ug0)
-            s2 = c.solve_sqp(x0, max_iter=sqp_iter, tol=tol, active=ok)
-            own = ok & ((s2 == 0) | (s2 == 2)) & c.checkGuess()
-            xo, uo = np.where(own[:, None, None], c.x_temp, x_net), np.where(own[:, None, None], c.u_temp, u_net)
+            s2 = c.solve_sqp(x0, max_iter=sqp_iter, tol=tol, active=ok, globalization=globalization)
+            x_c, u_c = c._sqp_result
+            own = ok & ((s2 == 0) | (s2 == 2)) & c.checkGuess(x_c, u_c)
+            xo, uo = np.where(own[:, None, None], x_c, x_net), np.where(own[:, None, None], u_c, u_net)
             stats[name + '_own'] += int(own.sum())
             acc[name]['xg'].append(xo[ok]); acc[name]['ug'].append(uo[ok])
     out = {}

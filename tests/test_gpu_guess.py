@@ -60,7 +60,7 @@ def test_sqp_loop_matches_the_oracle_loop(name, lm, max_iter):
     c, model, params = _controller(name, B, N, lm)
     x0 = halton_initial_states(model, B)
     c.setGuess(np.repeat(x0[:, None, :], N + 1, axis=1), np.zeros((B, N, abi.NU)))
-    st = c.solve_sqp(x0, max_iter=max_iter, tol=1e-7)
+    st = c.solve_sqp(x0, max_iter=max_iter, tol=1e-7, globalization='FIXED_STEP')
     xt, ut = c.x_temp, c.u_temp
     prob, keep = build_problem(params, name, cost='ext', N=N, model=model.data)
     st_o, it_o, x_o, u_o = _oracle_sqp(prob, B, N, x0, max_iter, 1e-7)
@@ -73,7 +73,7 @@ def test_sqp_loop_matches_the_oracle_loop(name, lm, max_iter):
         return
     assert conv.sum() >= B // 2 and c.sqp_iter[conv].max() < 25
     assert np.abs(c.sqp_iter[conv] - it_o[conv]).max() <= 1       # the step test sits at 1e-7: one iteration of slack
-    # frozen problems keep their last iterate in the engine (x_temp is what checkGuess and the generator read)
+    # frozen problems keep their last QP solution in the engine; after a full step it is the last iterate
     xf, uf = c._sqp_result
     assert np.array_equal(xt[conv], xf[conv]) and np.array_equal(ut[conv], uf[conv])
     # a converged trajectory is a fixed point of the RTI solve, and it passes the reference's acceptance test
@@ -83,12 +83,42 @@ def test_sqp_loop_matches_the_oracle_loop(name, lm, max_iter):
     assert np.abs(c.x_temp[conv] - xt[conv]).max() < 1e-6
 
 
+def test_merit_backtracking_line_search():
+    """The opt-in line search of solve_sqp: step lengths on the alpha_reduction ladder down to alpha_min (parser.py:136-137),
+    iterates = guess + alpha * QP step, still on the (linear) dynamics."""
+    B, N = 8, 12
+    c, model, params = _controller('st', B, N, 1e-2)
+    assert params.globalization == 'MERIT_BACKTRACKING' and (params.alpha_reduction, params.alpha_min) == (0.3, 1e-2)
+    x0 = halton_initial_states(model, B)
+    xg0, ug0 = np.repeat(x0[:, None, :], N + 1, axis=1), np.zeros((B, N, abi.NU))
+    c.setGuess(xg0, ug0)
+    alphas = []
+    xp, up = xg0, ug0
+    for _ in range(4):
+        st = c.solve_sqp(x0, max_iter=1, tol=1e-7, globalization='MERIT_BACKTRACKING')     # one line-searched SQP iteration per call
+        x, u = c._sqp_result
+        a = c.sqp_alpha[:, None, None]
+        run = st != 4
+        assert np.array_equal(x, c.x_guess) and np.array_equal(u, c.u_guess)
+        assert np.allclose(x[run], (xp + a * (c.x_temp - xp))[run], atol=1e-12) and np.allclose(u[run], (up + a * (c.u_temp - up))[run], atol=1e-12)
+        alphas.append(c.sqp_alpha.copy())
+        xp, up = x, u
+    alphas = np.array(alphas)
+    assert set(np.unique(np.round(alphas, 6))) <= {1.0, 0.3, 0.09, 0.027, 0.01}        # alpha_reduction ladder down to alpha_min
+    assert (alphas < 1.0).any()                                    # the search does shorten steps on this problem
+    mu = np.full(B, 1.0)
+    assert np.isfinite(c.merit(x, u, mu)).all() and (c.merit(x, u, 10 * mu) >= c.merit(x, u, mu)).all()
+    assert model.checkDynamicsConstraints(x, u)[model.checkTorqueConstraints(x, u)].all()
+    with pytest.raises(ValueError, match='globalization'):
+        c.solve_sqp(x0, max_iter=1, globalization='nope')
+
+
 def test_check_guess_agrees_with_plain_numpy_predicates():
     B, N = 8, 12
     c, model, params = _controller('st', B, N)
     x0 = halton_initial_states(model, B)
     c.setGuess(np.repeat(x0[:, None, :], N + 1, axis=1), np.zeros((B, N, abi.NU)))
-    c.solve_sqp(x0, max_iter=30, tol=1e-7)
+    c.solve_sqp(x0, max_iter=30, tol=1e-7, globalization='FIXED_STEP')
     x, u = c.x_temp.copy(), c.u_temp.copy()
     # spoil some trajectories: a state beyond its bound (1), a dynamics defect (2), a torque far out of range (3)
     x[1, 5, 0] = model.x_max[0] + 10 * params.tol_x

@@ -294,8 +294,8 @@ def run_engine(a):
         'clocks': clocks,
         'roofline': {'kernel': 'qs_prep_coop_kernel (IPM iterations >= 1; the cold start is qs_prep_kernel<true>)', 'bound': 'hbm', 'achieved': achieved,
                      'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak,
-                     'traffic': 2.40e9 if (B, N) == (10000, 45) else None,
-                     'traffic_source': 'ncu dram__bytes_read+write of one full launch (all problems active), profiles/r01_qp_v7.md (B=10000, N=45 only)',
+                     'traffic': 2.42e9 if (B, N) == (10000, 45) else None,
+                     'traffic_source': 'ncu dram__bytes_read+write of one full launch (all problems active), profiles/r01_final.md, r01_prep_coop_final_raw.csv (B=10000, N=45 only)',
                      'peak_source': peak_src, 'algorithmic_bytes_per_launch': alg_bytes, 'launch_ms': prep_launch_ms,
                      'launches_per_solve': prep_n, 'share_of_qp_solve': prep_ms / max(kern_total, 1e-9),
                      'note': 'bytes and time are averaged over every qs_prep launch of one solve; a launch only touches the problems still iterating'},

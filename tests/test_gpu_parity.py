@@ -217,3 +217,58 @@ def test_parallel_controller_steps(alpha):
         _close(x_g[m], x_o[m], RTOL, f'x step {step}')
     assert keep.sum() >= B // 2, f'only {keep.sum()} of {B} problems stayed well-posed'
     print('receding indices seen:', sorted(seen_r))
+
+
+@pytest.mark.parametrize('B', [1, 33, 97])
+def test_ragged_batches(B):
+    """Batches that do not fill a tile of 32 problems (1), spill one problem into a second tile (33), and give the three tile
+    groups unequal shares (97 = 4 tiles): solve, controller step and closed loop against the oracle; padding lanes stay silent."""
+    N = 10
+    eng, orc, prob, params, md = _pair('st', 'ext', N, B)
+    x0 = start_states(B, seed=71, vel=0.4)
+    xg, ug = rollout_guess(x0, N, params.dt, seed=72)
+    for e in (eng, orc):
+        e.set_guess(xg, ug)
+    st_g, st_o = eng.rti_solve(x0), orc.rti_solve(x0)
+    np.testing.assert_array_equal(st_g, st_o)
+    xt_g, ut_g = eng.get_temp(); xt_o, ut_o = orc.get_temp()
+    ok = st_o == 0
+    _close(xt_g[ok], xt_o[ok], RTOL, 'x_temp'); _close(ut_g[ok], ut_o[ok], RTOL, 'u_temp')
+    for e in (eng, orc):
+        e.set_guess(xg, ug); e.reset_controller()
+    x_g, x_o = x0.copy(), x0.copy()
+    for _ in range(3):
+        u_g, ab_g = eng.controller_step(x_g); u_o, ab_o = orc.controller_step(x_o)
+        np.testing.assert_array_equal(ab_g, ab_o)
+        _close(u_g, u_o, RTOL, 'u')
+        x_g, _ = eng.plant_step(x_g, u_g); x_o, _ = orc.plant_step(x_o, u_o)
+    _close(x_g, x_o, RTOL, 'x after 3 steps')
+
+
+def test_empty_active_mask_and_horizon_range():
+    """No problem active: nothing moves and nothing is reported; the shortest (N = 2) and the longest (N = 128) horizon of the
+    boundary solve like the oracle, horizons outside the range are refused."""
+    B = 40
+    eng, orc, prob, params, md = _pair('naive', 'ext', 6, B)
+    x0 = start_states(B, seed=73, vel=0.3)
+    xg, ug = rollout_guess(x0, 6, params.dt, seed=74)
+    eng.set_guess(xg, ug); orc.set_guess(xg, ug)
+    eng.rti_solve(x0); orc.rti_solve(x0)
+    xt0, ut0 = (a.copy() for a in eng.get_temp())
+    none = np.zeros(B, dtype=np.uint8)
+    st_g, st_o = eng.rti_solve(x0 + 0.01, none), orc.rti_solve(x0 + 0.01, none)
+    np.testing.assert_array_equal(st_g, st_o)
+    xt1, ut1 = eng.get_temp()
+    assert np.array_equal(xt0, xt1) and np.array_equal(ut0, ut1)
+    for bad in (1, abi.MAX_N + 1):                                 # the horizon range of the boundary
+        with pytest.raises(ValueError, match='horizon'):
+            make_problem('naive', cost='ext', N=bad)
+    for N1, B1 in ((2, B), (abi.MAX_N, 8)):                        # shortest and longest horizon
+        eng1, orc1, prob1, params1, md1 = _pair('naive', 'ext', N1, B1)
+        xg1, ug1 = rollout_guess(x0[:B1], N1, params1.dt, seed=75)
+        eng1.set_guess(xg1, ug1); orc1.set_guess(xg1, ug1)
+        st1 = orc1.rti_solve(x0[:B1])
+        np.testing.assert_array_equal(eng1.rti_solve(x0[:B1]), st1)
+        a, b = eng1.get_temp(), orc1.get_temp()
+        ok = st1 == 0
+        _close(a[0][ok], b[0][ok], RTOL, f'x_temp N={N1}'); _close(a[1][ok], b[1][ok], RTOL, f'u_temp N={N1}')

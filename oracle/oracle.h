@@ -11,7 +11,8 @@
  * statements of the reference's scripts/mpc.py around those classes), the capsule distance (a4),
  * the plant step and the feasibility predicates (a10, a11), randomize_model (a13) and the configuration layer (the reference's
  * Parameters on its own config.yaml).  The acados / HPIPM / CasADi / adam numerics (a2, a3, a7) are PARITY UNPINNED: that part of the restatement is pinned only by independent cross-checks
- * (tests/): finite differences, a numpy re-implementation of the chain algorithms, and direct verification of the KKT
+ * (tests/): finite differences, a numpy re-implementation of the chain algorithms, an Euler-Lagrange (kinetic-energy) derivation of the
+ * mass matrix and the Coriolis vector, and direct verification of the KKT
  * conditions of every QP solution.
  *
  * The API mirrors include/safe_mpc_b200.h function by function (orc_* <-> smpc_*), host memory only; the

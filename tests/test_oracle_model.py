@@ -45,6 +45,42 @@ def test_mass_matrix_identities(orc):
     np.testing.assert_allclose(o.tau(x_rest[None], np.zeros((1, 5)))[0], g_fd, rtol=1e-6, atol=1e-7)
 
 
+def test_euler_lagrange_derivation_of_mass_matrix_and_coriolis(orc):
+    """a2 from the energy side: M(q) is the Hessian of the kinetic energy T = 1/2 sum_b (m |v_cb|^2 + w_b' R I R' w_b) in the joint
+    velocities and the velocity-dependent part of h(q, qd) follows from the Christoffel symbols of M (Euler-Lagrange) -- no
+    Newton-Euler recursion anywhere in this derivation, only forward kinematics differentiated numerically."""
+    o, prob, params, md = orc
+    ch, inert, n = md.chain, md.inertial, 5
+
+    def mass(q, h=1e-6):
+        Rs0, _ = robot_model.fk_frames(ch, q)
+        Jv, Jw = np.zeros((n, 3, n)), np.zeros((n, 3, n))
+        for i in range(n):
+            e = np.zeros(n); e[i] = h
+            Rp, op = robot_model.fk_frames(ch, q + e); Rm, om = robot_model.fk_frames(ch, q - e)
+            for b in range(n):
+                c = inert[b, 1:4]
+                Jv[b, :, i] = ((op[b] + Rp[b] @ c) - (om[b] + Rm[b] @ c)) / (2 * h)
+                S = (Rp[b] - Rm[b]) / (2 * h) @ Rs0[b].T                 # skew of the angular velocity per unit joint rate
+                Jw[b, :, i] = [S[2, 1], S[0, 2], S[1, 0]]
+        M = np.zeros((n, n))
+        for b in range(n):
+            I = np.array([[inert[b, 4], inert[b, 7], inert[b, 9]], [inert[b, 7], inert[b, 5], inert[b, 8]], [inert[b, 9], inert[b, 8], inert[b, 6]]])
+            M += inert[b, 0] * Jv[b].T @ Jv[b] + Jw[b].T @ (Rs0[b] @ I @ Rs0[b].T) @ Jw[b]
+        return M
+
+    x = random_states(md, 3, seed=11, vel_scale=0.8)
+    for i in range(3):
+        q, qd = x[i, :5], x[i, 5:]
+        M_o, h_o = o.mass_bias(0, x[i])
+        np.testing.assert_allclose(mass(q), M_o, rtol=1e-7, atol=1e-8)
+        d = 1e-4
+        dM = np.stack([(mass(q + d * e) - mass(q - d * e)) / (2 * d) for e in np.eye(n)], axis=2)      # dM[i, j, k] = dM_ij / dq_k
+        cor = np.einsum('ijk,j,k->i', dM, qd, qd) - 0.5 * np.einsum('jki,j,k->i', dM, qd, qd)
+        _, g_o = o.mass_bias(0, np.hstack([q, np.zeros(5)]))
+        np.testing.assert_allclose(h_o - g_o, cor, rtol=1e-5, atol=1e-6 * max(1.0, np.abs(cor).max()))
+
+
 def test_fk_and_distances(orc):
     o, prob, params, md = orc
     x = random_states(md, 8, seed=4)

@@ -12,8 +12,8 @@
  * the plant step and the feasibility predicates (a10, a11), randomize_model (a13) and the configuration layer (the reference's
  * Parameters on its own config.yaml).  The acados / HPIPM / CasADi / adam numerics (a2, a3, a7) are PARITY UNPINNED: that part of the restatement is pinned only by independent cross-checks
  * (tests/): finite differences, a numpy re-implementation of the chain algorithms, an Euler-Lagrange (kinetic-energy) derivation of the
- * mass matrix and the Coriolis vector, and direct verification of the KKT
- * conditions of every QP solution.
+ * mass matrix and the Coriolis vector, direct verification of the KKT
+ * conditions of every QP solution, and agreement of the QP solution with an independent dense solver (scipy SLSQP).
  *
  * The API mirrors include/safe_mpc_b200.h function by function (orc_* <-> smpc_*), host memory only; the
  * problem description is the very same struct (the boundary header is shared, the implementation is not).

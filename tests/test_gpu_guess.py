@@ -193,3 +193,26 @@ def test_guess_script_writes_the_reference_files_and_mpc_reads_them(tmp_path, mo
     assert len(out) == 1
     x = pickle.load(open(tmp_path / out[0], 'rb'))['x']
     assert np.allclose(x[:, 0], d['xg'][:, 0])
+
+
+def test_initialize_keeps_the_solution_where_it_passes():
+    """NaiveController.initialize (controller.py:260-272) for a batch: trivial guess, one solve, the solution becomes the
+    guess exactly where the status is 0 and checkGuess holds."""
+    B, N = 8, 12
+    c, model, params = _controller('naive', B, N)
+    x0 = halton_initial_states(model, B)
+    ok = c.initialize(x0)
+    assert ok.shape == (B,) and set(np.unique(ok)) <= {0, 1}
+    st = c.last_status if hasattr(c, 'last_status') else None
+    chk = c.checkGuess()
+    xg, ug = c.getGuess()
+    xt, ut = c.x_temp, c.u_temp
+    triv = np.repeat(x0[:, None, :], N + 1, axis=1)
+    for b in range(B):
+        if ok[b]:
+            assert chk[b] and np.array_equal(xg[b], xt[b]) and np.array_equal(ug[b], ut[b])
+        else:
+            assert np.array_equal(xg[b], triv[b]) and np.abs(ug[b]).max() == 0.0
+    assert np.array_equal(ok.astype(bool), chk & (np.asarray(st) == 0)) if st is not None else True
+    # an explicit u0 is broadcast over the horizon (controller.py:263-265)
+    c.initialize(x0, u0=np.full(5, 0.1))

@@ -267,6 +267,10 @@ int64_t smpc_launch_count(const smpc_handle_t* h);
 void* smpc_stream(smpc_handle_t* h);
 int smpc_sync(smpc_handle_t* h);
 
+/* --- measured machine peaks for the roofline of bench.py (the dynamics / QP kernels are charged to the
+ * FP64 FMA pipe; MEASURED_PEAKS.json has no FP64 number): dense FMA rate of the FP64 and FP32 pipes, TFLOP/s, CUDA events --- */
+int smpc_measure_peaks(int32_t device, double* fp64_tflops, double* fp32_tflops);
+
 #ifdef __cplusplus
 }
 #endif

@@ -48,6 +48,11 @@ struct orc_handle {
   std::vector<float> w;
   int B = 0, N = 0, threads = 1;
   int mlp_fp32 = 0;
+  // tests only: the QP of every solve handed to an external solver (tests/emu: the engine's kernel sources on the host), see oracle.h
+  orc_qp_hook_t qp_hook = nullptr;
+  // tests only: every solve repeated on perturbed data; per problem, the number of solves whose status depends on the perturbation
+  double probe_eps = 0.0;
+  std::vector<int32_t> probe_flips;
   std::vector<double> xg, ug, xt, ut, lin, plant_inertial, tau_noise, x_viable;
   std::vector<double> qp_z, qp_pi, qp_lam, qp_t, qp_res;
   std::vector<int32_t> fails, r, status, qp_iter, qp_status, cur_step, cand;
@@ -295,7 +300,40 @@ int rti_solve_one(orc_handle& h, int b, const double* x0, Workspace& W) {
   o.iter_max = P.qp_iter_max; o.mu0 = P.qp_mu0; o.tol_stat = P.qp_tol_stat; o.tol_eq = P.qp_tol_eq;
   o.tol_ineq = P.qp_tol_ineq; o.tol_comp = P.qp_tol_comp; o.alpha_min = P.qp_alpha_min; o.reg_prim = P.qp_reg_prim;
   o.cond_pred_corr = P.qp_cond_pred_corr;
-  const int qs = qp.solve(o);
+  if (h.qp_hook) {
+    // the QP of this solve goes to the external solver; it returns what the engine's qs_ctl / qs_final would (status mapping included)
+    double* xt = &h.xt[(size_t)b * (N + 1) * NX];
+    double* ut = &h.ut[(size_t)b * N * NU];
+    int32_t status = 4, it = 0, qst = 0;
+    h.qp_hook(&P, lin, x0, h.P.nn_rows == SMPC_NN_PARALLEL ? h.cand[b] : h.r[b], xt, ut, &status, &it, &qst, &h.qp_res[(size_t)b * 5]);
+    h.qp_iter[b] = it; h.qp_status[b] = qst; h.status[b] = status;
+    return status;
+  }
+  int qs = qp.solve(o);
+  if (h.probe_eps > 0.0) {
+    // sensitivity probe: the same QP with its gradients and dynamics offsets perturbed by a relative probe_eps; a solve whose status
+    // changes under such a perturbation is decided by rounding, not by the algorithm (tests/test_gpu_closed_loop_full.py)
+    const QpSol keep = qp.sol();
+    bool flip = false;
+    for (int trial = 0; trial < 2 && !flip; ++trial) {
+      uint64_t sd = 0x9E3779B97F4A7C15ull * (uint64_t)(b + 1) + (uint64_t)trial * 0xD1B54A32D192ED03ull + (uint64_t)h.cur_step[b];
+      auto rnd = [&]() { sd ^= sd << 13; sd ^= sd >> 7; sd ^= sd << 17; return (double)(sd >> 11) / 9007199254740992.0 * 2.0 - 1.0; };
+      for (int k = 0; k <= N; ++k) {
+        QpStage& S = qp.stages()[k];
+        for (int i = 0; i < QNZ; ++i) S.g[i] *= 1.0 + h.probe_eps * rnd();
+        for (int i = 0; i < NX; ++i) S.b[i] *= 1.0 + h.probe_eps * rnd();
+      }
+      const int qs2 = qp.solve(o);
+      flip = ((qs2 == 0 || qs2 == 1) != (qs == 0 || qs == 1));
+      for (int k = 0; k <= N; ++k) {
+        double lo[NX], hi[NX];
+        stage_box(h, b, k, x0, lo, hi);
+        assemble_stage(P, k, lin + (size_t)k * REC, lo, hi, qp.stages()[k]);
+      }
+    }
+    if (flip) h.probe_flips[b] += 1;
+    qp.restore(keep);
+  }
   const QpSol& sol = qp.sol();
   h.qp_iter[b] = sol.iter;
   h.qp_status[b] = qs;
@@ -554,6 +592,13 @@ int orc_create(const orc_problem_t* prob, int32_t batch, int32_t threads, orc_ha
 void orc_destroy(orc_handle_t* h) { delete h; }
 int orc_num_threads(const orc_handle_t* h) { return h->threads; }
 int orc_set_mlp_fp32(orc_handle_t* h, int32_t on) { h->mlp_fp32 = on; return SMPC_OK; }
+int orc_set_qp_hook(orc_handle_t* h, orc_qp_hook_t fn) { h->qp_hook = fn; return SMPC_OK; }
+int orc_set_probe(orc_handle_t* h, double eps) { h->probe_eps = eps; h->probe_flips.assign(h->B, 0); return SMPC_OK; }
+int orc_get_probe_flips(orc_handle_t* h, int32_t* out) {
+  if (h->probe_flips.size() != (size_t)h->B) h->probe_flips.assign(h->B, 0);
+  std::copy(h->probe_flips.begin(), h->probe_flips.end(), out);
+  return SMPC_OK;
+}
 
 int orc_set_plant_inertial(orc_handle_t* h, const double* v) { std::copy(v, v + h->plant_inertial.size(), h->plant_inertial.begin()); return SMPC_OK; }
 int orc_set_torque_noise(orc_handle_t* h, const double* v) { std::copy(v, v + h->tau_noise.size(), h->tau_noise.begin()); return SMPC_OK; }

@@ -44,6 +44,17 @@ int orc_num_threads(const orc_handle_t* h);
 /* 0: viability MLP accumulates in fp64 (default, deterministic); 1: plain fp32 like libtorch on CPU */
 int orc_set_mlp_fp32(orc_handle_t* h, int32_t on);
 
+/* tests only: hand the QP of every solve to an external solver (tests/emu: the engine's kernel sources compiled for the host), so that
+ * whole closed loops of "kernel arithmetic" can be compared with the oracle's own solver without a GPU.  rec: the stage records of the
+ * problem [N+1][SMPC_REC]; outputs as smpc_rti_solve produces them (x_temp, u_temp, acados status, IPM iterations, QP status, res[5]) */
+typedef int (*orc_qp_hook_t)(const orc_problem_t* P, const double* rec, const double* x0, int32_t r, double* xt, double* ut, int32_t* status,
+                             int32_t* qp_iter, int32_t* qp_status, double* qp_res);
+int orc_set_qp_hook(orc_handle_t* h, orc_qp_hook_t fn);
+/* tests only: sensitivity probe.  eps > 0: every solve is repeated on data perturbed by a relative eps; orc_get_probe_flips returns, per
+ * problem, how many solves changed their accept / fail status under the perturbation (rounding-decided solves) */
+int orc_set_probe(orc_handle_t* h, double eps);
+int orc_get_probe_flips(orc_handle_t* h, int32_t* out);
+
 int orc_set_plant_inertial(orc_handle_t* h, const double* inertial);
 int orc_set_torque_noise(orc_handle_t* h, const double* tau_noise);
 int orc_set_guess(orc_handle_t* h, const double* xg, const double* ug);

@@ -47,6 +47,21 @@ class Oracle(EngineBase):
     def set_mlp_fp32(self, on):
         self._call('set_mlp_fp32', C.c_int32(int(on)))
 
+    def set_qp_hook(self, fn_ptr):
+        """tests only: every QP of this handle is solved by an external function (oracle.h orc_qp_hook_t), e.g. tests/emu's
+        emu_qp_solve1 = the engine's kernel sources compiled for the host.  fn_ptr: ctypes function object or None."""
+        self._hook = fn_ptr
+        self._call('set_qp_hook', C.cast(fn_ptr, C.c_void_p) if fn_ptr is not None else C.c_void_p(0))
+
+    def set_probe(self, eps):
+        """tests only: repeat every solve on data perturbed by a relative eps and count the status flips per problem"""
+        self._call('set_probe', C.c_double(eps))
+
+    def probe_flips(self):
+        out = np.zeros(self.B, dtype=np.int32)
+        self._call('get_probe_flips', C.c_void_p(out.ctypes.data))
+        return out
+
     def mass_bias(self, b, x, nominal=True):
         M = np.empty((abi.NQ, abi.NQ)); h = np.empty(abi.NQ)
         xx = np.ascontiguousarray(x, dtype=np.float64)

@@ -82,6 +82,7 @@ class QpIpm {
   }
   std::vector<QpStage>& stages() { return st_; }
   const QpSol& sol() const { return sol_; }
+  void restore(const QpSol& s) { sol_ = s; }   // (sensitivity probe of oracle.cpp: put the un-perturbed result back)
 
   // true when constraint slot c of stage k exists
   bool present(int k, int c) const {

@@ -103,7 +103,8 @@ void launch_sim_post(const LaunchCtx& c, const SimDev& s, const smpc_problem_t* 
                      const double* bk_ut, const double* inertial, const double* noise, const int32_t* qp_iter_bk);
 void launch_sim_outcome(const LaunchCtx& c, const SimDev& s, const smpc_problem_t* dP, int32_t* out);
 
-// qp.cu -- split interior-point solver (qp_split.cuh)
+// qp.cu -- split interior-point solver (qp_split.cuh); lives in the storage-flavour namespace of qp_split.cuh
+inline namespace QS_FLAVOUR {
 struct QpSolver;
 size_t qp_bytes(int B, int N);
 QpSolver* qp_create(int B, int N, int iter_max, cudaStream_t stream, cudaError_t* err);
@@ -118,5 +119,6 @@ cudaError_t launch_qp_solve(const LaunchCtx& c, const smpc_problem_t* dP, QpSolv
                             double* xt, double* ut, int32_t* status, int32_t* qp_iter, int32_t* qp_status, double* qp_res);
 void launch_rec_untile(const LaunchCtx& c, QpSolver* s, double* out);
 void launch_dump_qp(const LaunchCtx& c, const smpc_problem_t* dP, QpSolver* s, double* dz, double* pi, double* lam, double* t);
+}  // inline namespace QS_FLAVOUR
 
 }  // namespace smpc

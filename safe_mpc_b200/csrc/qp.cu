@@ -18,6 +18,7 @@
 #include "engine.cuh"
 
 namespace smpc {
+inline namespace QS_FLAVOUR {
 
 namespace {
 
@@ -1479,4 +1480,5 @@ void launch_dump_qp(const LaunchCtx& c, const smpc_problem_t* dP, QpSolver* s, d
   ++*c.launches;
 }
 
+}  // inline namespace QS_FLAVOUR
 }  // namespace smpc

@@ -35,7 +35,25 @@
 #pragma once
 #include "dev_model.cuh"
 
+// Storage flavour.  QS_REAL is the type of everything a solve STREAMS: stage records, search directions, condensed matrices and
+// Riccati factors (rec, st, st2, sb, prod).  The iterate (z, pi, lam, t), the residual / step-length partials and the per-problem
+// scalars are always fp64, and so is all arithmetic (values are widened on load, rounded on store).  The library holds both
+// flavours: qp.cu is compiled once with QS_REAL = double (namespace smpc::f64, `precision = SMPC_PREC_F64`, bit-level parity
+// with the oracle) and once with QS_REAL = float (qp_f32.cu, namespace smpc::f32, `precision = SMPC_PREC_F32`: 40 % less HBM
+// traffic per interior-point iteration).  tests/emu compiles this header for the host in either flavour.
+#ifndef QS_REAL
+#define QS_REAL double
+#define QS_FLAVOUR f64
+#endif
+
 namespace smpc {
+inline namespace QS_FLAVOUR {
+using qs_real = QS_REAL;
+#ifdef QS_FAC
+using qs_fac = QS_FAC;      // (experiment) type of the solver block
+#else
+using qs_fac = qs_real;
+#endif
 
 constexpr int TL = 32;             // problems per tile
 constexpr int QNR = 22;            // two-sided rows per stage
@@ -66,12 +84,12 @@ enum { D_X0 = 0, D_T0 = 10, D_MU = 65, D_MUAFF = 66, D_SIGMU = 67, D_ALPHA = 68,
 enum { J_ACT = 0, J_ITER = 1, J_QST = 2, J_REDO = 3, J_NC = 4, J_ITBUF = 5, J_R = 6, J_B = 7, NPI = 8 };
 
 struct QsBufs {
-  const double* rec;     // [T][N+1][REC][TL]   stage records (linearisation)
-  double* it[2];         // [T][N+1][NIT][TL]   iterate, ping-pong
-  double* st;            // [T][N+1][NIT][TL]   step
-  double* st2;           // [T][N+1][NS2][TL]   pure-centering direction (dz, dpi) computed speculatively by ric2
-  double* sb;            // [T][N+1][NSB][TL]   solver block (condensed matrices, Riccati factors, corrector terms)
-  double* prod;          // [T][N+1][NPROD][TL]
+  const qs_real* rec;    // [T][N+1][REC][TL]   stage records (linearisation)
+  double* it[2];         // [T][N+1][NIT][TL]   iterate, ping-pong (always fp64)
+  qs_real* st;           // [T][N+1][NIT][TL]   step
+  qs_real* st2;          // [T][N+1][NS2][TL]   pure-centering direction (dz, dpi) computed speculatively by ric2
+  qs_fac* sb;            // [T][N+1][NSB][TL]   solver block (condensed matrices, Riccati factors, corrector terms)
+  qs_real* prod;         // [T][N+1][NPROD][TL]
   double* res;           // [T][N+1][NRES][TL]
   double* stp;           // [T][N+1][NSTP][TL]
   double* pd;            // [T][NPD][TL]
@@ -179,11 +197,11 @@ SMPC_HD void qs_prep(const smpc_problem_t& P, const QsBufs& q, int tile, int lan
   constexpr bool first = FIRST;            // cold start (kk == 0) is its own instantiation: half the code, no runtime branches
   const double a = first ? 0.0 : QF(pd, D_STEP);
   const int rrec = QF(pi, J_R);
-  const double* rec = q.rec + qs_blk(tile, N, k, REC, lane);
+  const qs_real* rec = q.rec + qs_blk(tile, N, k, REC, lane);
   double* ito = q.it[kk & 1] + qs_blk(tile, N, k, NIT, lane);
   const double* iti = q.it[(kk & 1) ^ 1] + qs_blk(tile, N, k, NIT, lane);
-  const double* st = q.st + qs_blk(tile, N, k, NIT, lane);
-  double* hc = q.sb + qs_blk(tile, N, k, NHC, lane);
+  const qs_real* st = q.st + qs_blk(tile, N, k, NIT, lane);
+  qs_fac* hc = q.sb + qs_blk(tile, N, k, NHC, lane);
   const StageFlags F = qs_flags(P, k);
   const double lam_min = 1e-16, t_min = 1e-16, thr0 = 1e-1, mu0 = P.qp_mu0, reg = P.qp_reg_prim;
   const double dt = P.dt, a2 = 0.5 * P.dt * P.dt;
@@ -233,7 +251,7 @@ SMPC_HD void qs_prep(const smpc_problem_t& P, const QsBufs& q, int tile, int lan
   }
   if (k < N) {
     const double* itn = q.it[(kk & 1) ^ 1] + qs_blk(tile, N, k + 1, NIT, lane);
-    const double* stn = q.st + qs_blk(tile, N, k + 1, NIT, lane);
+    const qs_real* stn = q.st + qs_blk(tile, N, k + 1, NIT, lane);
     double rb[10];
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
@@ -532,7 +550,7 @@ SMPC_HD bool qs_final(const QsBufs& q, int tile, int lane, int k, const uint8_t*
   if (b >= B || (act && !act[b])) return false;
   const bool ok = status[b] != 4;
   const double* it = q.it[QF(pi, J_ITBUF)] + qs_blk(tile, N, k, NIT, lane);
-  const double* rec = q.rec + qs_blk(tile, N, k, REC, lane);
+  const qs_real* rec = q.rec + qs_blk(tile, N, k, REC, lane);
   bool znan = false;
   if (k < N) {
     double* utb = ut + ((size_t)b * N + k) * NU;
@@ -578,7 +596,7 @@ SMPC_HD void qs_ric1(const smpc_problem_t& P, const QsBufs& q, int tile, W& w, d
   if (!w.any(on)) return;
   double* pd = q.pd + qs_pb(tile, NPD, lane);
   const double dt = P.dt, a2 = 0.5 * P.dt * P.dt;
-  const double* gsb = q.sb + qs_blk(tile, N, 0, NSB, 0);       // stage blocks of this tile (no lane offset)
+  const qs_fac* gsb = q.sb + qs_blk(tile, N, 0, NSB, 0);       // stage blocks of this tile (no lane offset)
   const size_t sstride = (size_t)NSB * TL;
   double dx[10];
   // staging: with two buffers stage k - 1 is fetched while stage k is processed; with one buffer (more warps per SM)
@@ -592,8 +610,8 @@ SMPC_HD void qs_ric1(const smpc_problem_t& P, const QsBufs& q, int tile, W& w, d
     if (!nb1 && k < N) { w.fetch_begin(0, B_LP - B_M); w.fetch(0, 0, gsb + (size_t)k * sstride, B_M, B_LP - B_M); }
     if (!nb1 && k > 0) w.prefetch(gsb + (size_t)(k - 1) * sstride, B_M, B_LP - B_M);      // next stage on its way to L2 meanwhile
     w.wait(k & nb1);
-    const double* hc = w.buf(k & nb1);                           // fields B_M .. B_LP at their own offsets
-    double* fac = q.sb + qs_blk(tile, N, k, NSB, lane);
+    const qs_fac* hc = w.buf(k & nb1);                           // fields B_M .. B_LP at their own offsets
+    qs_fac* fac = q.sb + qs_blk(tile, N, k, NSB, lane);
     double* pcur = psm;                                          // P_{k+1}, p_{k+1} on entry; P_k, p_k on exit (in place)
     const double* pnx = psm;
     auto Pn = [&](int idx) { return QF(pnx, idx); };
@@ -736,8 +754,8 @@ SMPC_HD void qs_ric1(const smpc_problem_t& P, const QsBufs& q, int tile, W& w, d
     if (!nb1 && k > 0) { w.fetch_begin(0, B_WV - B_RB); w.fetch(0, 0, gsb + (size_t)k * sstride, B_RB, B_WV - B_RB); }
     if (!nb1 && k < N) w.prefetch(gsb + (size_t)(k + 1) * sstride, B_RB, B_WV - B_RB);
     w.wait(k & nb1);
-    const double* sb = w.buf(k & nb1) - (size_t)B_RB * TL;       // sb[f] valid for B_RB <= f < B_WV
-    double* st = q.st + qs_blk(tile, N, k, NIT, lane);
+    const qs_fac* sb = w.buf(k & nb1) - (size_t)B_RB * TL;       // sb[f] valid for B_RB <= f < B_WV
+    qs_real* st = q.st + qs_blk(tile, N, k, NIT, lane);
     double du[5];
 #pragma unroll
     for (int i = 0; i < 5; ++i) du[i] = 0.0;
@@ -799,7 +817,7 @@ SMPC_HD void qs_ric2(const smpc_problem_t& P, const QsBufs& q, int tile, W& w) {
   if (!w.any(on)) return;
   double* pd = q.pd + qs_pb(tile, NPD, lane);
   const double dt = P.dt, a2 = 0.5 * P.dt * P.dt;
-  const double* gsb = q.sb + qs_blk(tile, N, 0, NSB, 0);
+  const qs_fac* gsb = q.sb + qs_blk(tile, N, 0, NSB, 0);
   const size_t sstride = (size_t)NSB * TL;
   // backward stages fetch GA RB LP T WV = [B_GA, B_P) -> staging fields 0..124, and V1 V2 = [B_V1, NSB) -> 125..154
   const int n1 = B_P - B_GA, n2 = NSB - B_V1;
@@ -832,9 +850,9 @@ SMPC_HD void qs_ric2(const smpc_problem_t& P, const QsBufs& q, int tile, W& w) {
     }
     if (!nb1 && k > 0) { w.prefetch(gsb + (size_t)(k - 1) * sstride, B_GA, n1); w.prefetch(gsb + (size_t)(k - 1) * sstride, B_V1, n2); }
     w.wait(k & nb1);
-    const double* sb = w.buf(k & nb1) - (size_t)B_GA * TL;         // sb[f] valid for B_GA <= f < B_P
-    const double* vv = w.buf(k & nb1) - (size_t)(B_V1 - n1) * TL;  // vv[f] valid for B_V1 <= f < NSB
-    double* fac = q.sb + qs_blk(tile, N, k, NSB, lane);
+    const qs_fac* sb = w.buf(k & nb1) - (size_t)B_GA * TL;         // sb[f] valid for B_GA <= f < B_P
+    const qs_fac* vv = w.buf(k & nb1) - (size_t)(B_V1 - n1) * TL;  // vv[f] valid for B_V1 <= f < NSB
+    qs_fac* fac = q.sb + qs_blk(tile, N, k, NSB, lane);
     double g[2][15];
 #pragma unroll
     for (int i = 0; i < 15; ++i) {
@@ -898,9 +916,9 @@ SMPC_HD void qs_ric2(const smpc_problem_t& P, const QsBufs& q, int tile, W& w) {
     if (!nb1 && k > 0) { w.fetch_begin(0, B_V1 - B_RB); w.fetch(0, 0, gsb + (size_t)k * sstride, B_RB, B_V1 - B_RB); }
     if (!nb1 && k < N) w.prefetch(gsb + (size_t)(k + 1) * sstride, B_RB, B_V1 - B_RB);
     w.wait(k & nb1);
-    const double* sb = w.buf(k & nb1) - (size_t)B_RB * TL;
-    double* st = q.st + qs_blk(tile, N, k, NIT, lane);
-    double* st2 = q.st2 + qs_blk(tile, N, k, NS2, lane);
+    const qs_fac* sb = w.buf(k & nb1) - (size_t)B_RB * TL;
+    qs_real* st = q.st + qs_blk(tile, N, k, NIT, lane);
+    qs_real* st2 = q.st2 + qs_blk(tile, N, k, NS2, lane);
     // multiplier step of the link k-1 -> k:  dpi = P_k dx_k + p_k
 #pragma unroll
     for (int i = 0; i < 10; ++i) {
@@ -964,15 +982,15 @@ SMPC_HD void qs_step(const smpc_problem_t& P, const QsBufs& q, int tile, int lan
   const double* pd = q.pd + qs_pb(tile, NPD, lane);
   const int rrec = QF(pi, J_R);
   const double sigmu = mode == 0 ? 0.0 : QF(pd, D_SIGMU);
-  const double* rec = q.rec + qs_blk(tile, N, k, REC, lane);
+  const qs_real* rec = q.rec + qs_blk(tile, N, k, REC, lane);
   const double* it = q.it[kk & 1] + qs_blk(tile, N, k, NIT, lane);
-  double* st = q.st + qs_blk(tile, N, k, NIT, lane);
-  double* prod = q.prod + qs_blk(tile, N, k, NPROD, lane);
+  qs_real* st = q.st + qs_blk(tile, N, k, NIT, lane);
+  qs_real* prod = q.prod + qs_blk(tile, N, k, NPROD, lane);
   const StageFlags F = qs_flags(P, k);
   double z[15], dz[15];
   if (mode == 2) {
     // the centering direction was computed by ric2 next to the corrector: it becomes the step of this problem
-    const double* st2 = q.st2 + qs_blk(tile, N, k, NS2, lane);
+    const qs_real* st2 = q.st2 + qs_blk(tile, N, k, NS2, lane);
 #pragma unroll
     for (int i = 0; i < 15; ++i) { z[i] = QF(it, I_Z + i); dz[i] = QF(st2, I_Z + i); }
   } else {
@@ -1152,7 +1170,7 @@ SMPC_HD void qs_step(const smpc_problem_t& P, const QsBufs& q, int tile, int lan
     }
   }
   if (mode == 0) {
-    double* vv = q.sb + qs_blk(tile, N, k, NV, lane);
+    qs_fac* vv = q.sb + qs_blk(tile, N, k, NV, lane);
     if (k == N) {
 #pragma unroll
       for (int i = 0; i < 5; ++i) { v1[i] = 0.0; v2[i] = 0.0; }
@@ -1162,7 +1180,7 @@ SMPC_HD void qs_step(const smpc_problem_t& P, const QsBufs& q, int tile, int lan
   }
   if (mode == 2) {
     // (dz, dpi) of the step block <- centering direction (after every load of this thread, see the note on load / store phases)
-    const double* st2 = q.st2 + qs_blk(tile, N, k, NS2, lane);
+    const qs_real* st2 = q.st2 + qs_blk(tile, N, k, NS2, lane);
     double dpi[10];
 #pragma unroll
     for (int j = 0; j < 10; ++j) dpi[j] = QF(st2, I_PIM + j);
@@ -1254,4 +1272,5 @@ int qs_drive(BK* groups, int n_groups) {
   return kmax;
 }
 
+}  // inline namespace QS_FLAVOUR
 }  // namespace smpc

@@ -32,18 +32,38 @@ CONTROLLERS = {
 COSTS = {'zero': abi.COST_ZERO, 'ext': abi.COST_EXT, 'nls': abi.COST_NLS}
 
 
-def load_network(params):
-    """Weights / normalisation of the viability network in the reference's file format
-    (safe_set.py:76-85: ``torch.load`` of {'model', 'mean', 'std'}); written by synthetic.py if absent."""
+def resolve_network_path(params):
+    """The reference opens ``params.net_path`` as it stands (safe_set.py:76), i.e. relative to the working directory of its scripts
+    (``scripts/``: config.yaml:65 says '../nn_models/z1/...').  Tried in that order: the path as given, relative to ``scripts/`` of
+    this repository, relative to the repository root."""
     path = params.net_path
-    if not os.path.isabs(path):
-        path = os.path.normpath(os.path.join(params.NN_DIR, os.path.basename(path)))
+    if os.path.isabs(path):
+        return path
+    cands = [os.path.abspath(path), os.path.normpath(os.path.join(params.ROOT_DIR, 'scripts', path)),
+             os.path.normpath(os.path.join(params.ROOT_DIR, path))]
+    for c in cands:
+        if os.path.isfile(c):
+            return c
+    return cands[1]
+
+
+def load_network(params):
+    """Weights / normalisation of the viability network in the reference's file format (safe_set.py:76-85: ``torch.load`` of
+    {'model', 'mean', 'std'}).  A missing file raises, as the reference's ``torch.load`` does; the synthetic stand-in of
+    safe_mpc_b200/synthetic.py is only written on explicit request (``SMPC_SYNTHETIC_ASSETS=1`` or ``params.allow_synthetic``)."""
+    path = resolve_network_path(params)
     if not os.path.isfile(path):
+        if not (os.environ.get('SMPC_SYNTHETIC_ASSETS') == '1' or getattr(params, 'allow_synthetic', False)):
+            raise FileNotFoundError(f'viability network {path} (config.yaml network_path = {params.net_path!r}) does not exist; set '
+                                    'SMPC_SYNTHETIC_ASSETS=1 to generate the random-init stand-in of safe_mpc_b200/synthetic.py')
         synthetic.write_synthetic_net(path, nq=params.nq, hidden=int(params.net_size[1]))
     import torch
     data = torch.load(path, map_location='cpu', weights_only=True)
     sd = data['model']
     ws = [sd[f'linear_stack.{i}.weight'].numpy() for i in (0, 2, 4, 6)]
+    # is this the random-init stand-in (same generator, seed 0)?  recorded so that scripts / bench can say so
+    ref0 = synthetic.synthetic_net_arrays(params.nq, int(params.net_size[1]))[0][0]
+    params.synthetic_net = bool(ws[0].shape == ref0.shape and np.array_equal(ws[0], ref0))
     bs = [sd[f'linear_stack.{i}.bias'].numpy() for i in (0, 2, 4, 6)]
     mean = np.broadcast_to(np.asarray(data['mean'], dtype=np.float64).ravel(), (params.nq,)) \
         if np.asarray(data['mean']).size in (1, params.nq) else np.asarray(data['mean'], dtype=np.float64).ravel()[:params.nq]
@@ -141,7 +161,12 @@ def build_problem(params, controller: str, cost: str = 'ext', N: int | None = No
     keep = None
     if nn_rows != abi.NN_NONE:
         if not params.use_net:
-            raise NotImplementedError('the analytic safe set is out of scope (config.yaml use_net: true)')
+            raise NotImplementedError('use_net: false selects the analytic safe set (safe_set.py:106-155) as OCP rows; the engine evaluates it '
+                                      '(safe_set.AnalyticSafeSet: values and check_constraint) but its QP carries the network row only')
+        if str(params.act_fun).lower() != 'gelu':
+            raise NotImplementedError(f"act_fun = {params.act_fun!r}: the engine implements the shipped network (GELU, tanh form; config.yaml act_fun: 'gelu') only")
+        if int(params.n_dof_safe_set) != int(params.nq):
+            raise NotImplementedError(f'n_dof_safe_set = {params.n_dof_safe_set} != n_dofs = {params.nq}: the engine feeds every joint to the network')
         ws, bs, mean, std = load_network(params)
         keep = abi.pack_nn_weights(ws, bs)
     else:

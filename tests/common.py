@@ -164,3 +164,86 @@ def kkt_residuals(prob, lin, x0, dz, pi, lam, t, boxes=None):
                 ineq = max(ineq, vl, vu)
                 comp = max(comp, ll * abs(v - l_), lu * abs(h_ - v))
     return dict(stat=stat, eq=eq, ineq=ineq, comp=comp)
+
+
+# --------------------------------------------------------------------------------------------------
+# BASELINE.json configs[0]: the reference's own closed-loop workload (config.yaml:1-7: test_num = 100 tests x n_steps = 800,
+# N = 45), as scripts/guess_acados.py + scripts/mpc.py of the reference set it up
+# --------------------------------------------------------------------------------------------------
+def cfg0_initial_states(handle, md, params, B, flavour):
+    """'shipped': every test starts from the shipped configuration (guess_acados.py:101-103, TEST_NOISE = True), the tests differ
+    by their perturbed plant and torque-noise draw; 'halton': the collision-free points of Halton(nq, scramble=False) scaled to the
+    joint box, zero velocity (guess_acados.py:79,100-109).  `handle`: anything with .kinematics (engine or oracle)."""
+    nq = abi.NQ
+    if flavour == 'shipped':
+        x = np.zeros((B, abi.NX)); x[:, :nq] = Q0
+        return x
+    from scipy.stats import qmc
+    sampler = qmc.Halton(nq, scramble=False)
+    lo_chk = np.array([pr['lo_chk'] for pr in md.pairs])
+    out = []
+    while len(out) < B:
+        q = qmc.scale(sampler.random(256), md.x_min[:nq], md.x_max[:nq])
+        x = np.zeros((256, abi.NX)); x[:, :nq] = q
+        d = handle.kinematics(x)[1]
+        out += [xi for xi, ok in zip(x, (d >= lo_chk).all(axis=1)) if ok]
+    return np.array(out[:B])
+
+
+def cfg0_plants(md, params, B, noise, control_noise):
+    """Per-test perturbed plants (mpc.py:106-107, utils.py:126-171 draw order, seed 0) and the per-test torque-noise vector
+    (mpc.py:126-127: re-seeded with the test index every step, i.e. one fixed draw per test; env_model.py:196)."""
+    from safe_mpc_b200.robot_model import randomized_link_inertials
+    links = randomized_link_inertials(md.nominal_links, noise, noise, noise, B, seed=0)
+    pin = np.stack([md.chain.lump(links['mass'][i], links['com'][i], links['inertia6'][i], links['rpy']) for i in range(B)])
+    scale = md.tau_max * (control_noise / 100.0)
+    tn = np.stack([np.random.default_rng(i).normal(np.zeros(abi.NU), scale, size=abi.NU) for i in range(B)])
+    return pin, tn
+
+
+def sqp_warm_start(handle, x0, N, iters):
+    """Full-step SQP iterations from the trivial guess (x0 repeated, u = 0), accepted per problem on status 0 -> (xg, ug)."""
+    B = x0.shape[0]
+    xg, ug = constant_guess(x0, N)
+    handle.set_guess(xg, ug)
+    for _ in range(iters):
+        st = handle.rti_solve(x0)
+        xt, ut = handle.get_temp()
+        ok = st == 0
+        xg[ok], ug[ok] = xt[ok], ut[ok]
+        handle.set_guess(xg, ug)
+    handle.reset_controller()
+    return xg, ug
+
+
+def run_closed_loop(E, S, prob, bprob, x0, xg, ug, pin, tn, steps, arg=0, probe_eps=0.0, hook=None):
+    """One closed loop of mpc.py:102-291 on implementation (E, S) -> dict(outcome, x, u, counters, x_viable[, flips])."""
+    B = x0.shape[0]
+    main, bk = E(prob, B, arg), E(bprob, B, arg)
+    if hook is not None:
+        main.set_qp_hook(hook); bk.set_qp_hook(hook)
+    if probe_eps > 0.0:
+        main.set_probe(probe_eps); bk.set_probe(probe_eps)
+    main.set_guess(xg, ug); main.reset_controller()
+    for h in (main, bk):
+        h.set_plant_inertial(pin); h.set_torque_noise(tn)
+    sim = S(main, bk, steps)
+    sim.reset(x0)
+    sim.run(steps)
+    x, u = sim.log()
+    out = dict(outcome=np.asarray(sim.outcome()), x=x, u=u, counters=sim.counters(), x_viable=sim.x_viable())
+    if probe_eps > 0.0:
+        out['flips'] = main.probe_flips() + bk.probe_flips()
+    sim.close() if hasattr(sim, 'close') else None
+    main.close(); bk.close()
+    return out
+
+
+def outcome_sets(outcome):
+    """The four index sets of mpc.py:273-291 -> dict of counts (Completed task / Collisions / Viable states / Not converged)."""
+    conv = (outcome & abi.OUT_CONVERGED) != 0
+    coll = (outcome & abi.OUT_COLLIDED) != 0
+    abrt = (outcome & abi.OUT_ABORTED) != 0
+    viable = abrt & ~conv & ~coll
+    return dict(completed=int(conv.sum()), collisions=int(coll.sum()), viable=int(viable.sum()),
+                not_converged=int((~conv & ~coll & ~viable).sum()))

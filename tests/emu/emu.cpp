@@ -53,23 +53,23 @@ namespace {
 struct HostStage {
   int ln, nfb, lazy, nb = 2;
   int nbuf() const { return nb; }
-  std::vector<double> mem;
-  struct Copy { double* dst; const double* src; size_t n; };
+  std::vector<qs_fac> mem;
+  struct Copy { qs_fac* dst; const qs_fac* src; size_t n; };
   std::vector<Copy> pend[2];
-  HostStage(int lane_, int nfb_, int lazy_) : ln(lane_), nfb(nfb_), lazy(lazy_), mem((size_t)2 * nfb_ * TL, 0.0) {}
+  HostStage(int lane_, int nfb_, int lazy_) : ln(lane_), nfb(nfb_), lazy(lazy_), mem((size_t)2 * nfb_ * TL, (qs_fac)0) {}
   int lane() const { return ln; }
   bool any(bool v) const { return v; }
   void sync() const {}
-  double* buf(int b) { return mem.data() + (size_t)b * nfb * TL + ln; }
+  qs_fac* buf(int b) { return mem.data() + (size_t)b * nfb * TL + ln; }
   void fetch_begin(int, int) {}
-  void fetch(int b, int dst_field, const double* gblock, int src_field, int nfields) {
+  void fetch(int b, int dst_field, const qs_fac* gblock, int src_field, int nfields) {
     Copy c{mem.data() + ((size_t)b * nfb + dst_field) * TL, gblock + (size_t)src_field * TL, (size_t)nfields * TL};
     if (dst_field + nfields > nfb) { fprintf(stderr, "emu: staging overflow\n"); abort(); }
-    if (lazy) pend[b].push_back(c); else std::memcpy(c.dst, c.src, c.n * sizeof(double));
+    if (lazy) pend[b].push_back(c); else std::memcpy(c.dst, c.src, c.n * sizeof(qs_fac));
   }
-  void wait(int b) { for (auto& c : pend[b]) std::memcpy(c.dst, c.src, c.n * sizeof(double)); pend[b].clear(); }
+  void wait(int b) { for (auto& c : pend[b]) std::memcpy(c.dst, c.src, c.n * sizeof(qs_fac)); pend[b].clear(); }
   void publish() const {}
-  void prefetch(const double*, int, int) const {}
+  void prefetch(const qs_fac*, int, int) const {}
 };
 
 struct HostBackend {
@@ -84,13 +84,15 @@ struct HostBackend {
     for (int t = 0; t < T; ++t)
       for (int kx = 0; kx <= N; ++kx) {
         const int k = order ? N - kx : kx;
-        for (int lx = 0; lx < TL; ++lx) f(t, order ? TL - 1 - lx : lx, k);
+        for (int lx = 0; lx < TL; ++lx) { const int l = order ? TL - 1 - lx : lx; if (t * TL + l < B + lane_pad) f(t, l, k); }
       }
   }
   template <class F> void each_problem(F f) {
-    for (int t = 0; t < T; ++t) for (int lx = 0; lx < TL; ++lx) f(t, order ? TL - 1 - lx : lx);
+    for (int t = 0; t < T; ++t) for (int lx = 0; lx < TL; ++lx) { const int l = order ? TL - 1 - lx : lx; if (t * TL + l < B + lane_pad) f(t, l); }
   }
-  void init() { each_problem([&](int t, int l) { qs_init(q, t, l, B, x0, r, act); }); }
+  int lane_pad = TL;            // padding lanes past the batch are visited too (they must stay silent); 0 after init() when skip_pad is set
+  bool skip_pad = false;
+  void init() { lane_pad = TL; each_problem([&](int t, int l) { qs_init(q, t, l, B, x0, r, act); }); if (skip_pad) lane_pad = 0; }
   void prep(int kk) {
     std::vector<double> jsm((size_t)PREP_SCRATCH * TL, 0.0);
     each_stage([&](int t, int l, int k) {
@@ -124,12 +126,14 @@ extern "C" int emu_qp_solve(const smpc_problem_t* P, int B, const double* rec, c
                             int32_t* qp_iter, int32_t* qp_status, double* qp_res, int* n_redo_total) {
   const int N = P->N, T = (B + TL - 1) / TL;
   const size_t S = (size_t)T * (N + 1) * TL;
-  std::vector<double> vrec(S * REC, 0.0), it0(S * NIT, 0.0), it1(S * NIT, 0.0), st(S * NIT, 0.0), st2(S * NS2, 0.0), sb(S * NSB, 0.0), prod(S * NPROD, 0.0), res(S * NRES, 0.0), stp(S * NSTP, 0.0), pd((size_t)T * NPD * TL, 0.0);
+  std::vector<qs_real> vrec(S * REC, (qs_real)0), st(S * NIT, (qs_real)0), st2(S * NS2, (qs_real)0), prod(S * NPROD, (qs_real)0);
+  std::vector<qs_fac> sb(S * NSB, (qs_fac)0);
+  std::vector<double> it0(S * NIT, 0.0), it1(S * NIT, 0.0), res(S * NRES, 0.0), stp(S * NSTP, 0.0), pd((size_t)T * NPD * TL, 0.0);
   std::vector<int32_t> pi32((size_t)T * NPI * TL, 0);
   for (int b = 0; b < B; ++b)
     for (int k = 0; k <= N; ++k)
       for (int f = 0; f < REC; ++f)
-        vrec[qs_blk(b / TL, N, k, REC, b % TL) + (size_t)f * TL] = rec[((size_t)b * (N + 1) + k) * REC + f];
+        vrec[qs_blk(b / TL, N, k, REC, b % TL) + (size_t)f * TL] = (qs_real)rec[((size_t)b * (N + 1) + k) * REC + f];
   QsBufs q{vrec.data(), {it0.data(), it1.data()}, st.data(), st2.data(), sb.data(), prod.data(), res.data(), stp.data(),
            pd.data(), pi32.data(), N, 0};
   HostBackend bk{*P, q, B, T, N, order, x0, r, act, xt, ut, status, qp_iter, qp_status, qp_res, std::vector<double>(65 * TL, 0.0)};
@@ -168,6 +172,43 @@ extern "C" int emu_qp_solve(const smpc_problem_t* P, int B, const double* rec, c
       ot[2 * QNR] = F.soft ? QF(it, I_SLK + 4) : 0.0; ot[2 * QNR + 1] = F.soft ? QF(it, I_SLK + 5) : 0.0;
     }
   }
+  return 0;
+}
+
+// One problem at a time with a per-thread workspace: the signature of oracle.h's orc_qp_hook_t, so that the oracle's closed loop can
+// run on "kernel arithmetic" (tests/test_closed_loop_emulated.py, scripts/closed_loop_probe.py).  Lane 0 of one tile carries the problem.
+extern "C" int emu_qp_solve1(const smpc_problem_t* P, const double* rec, const double* x0, int32_t r, double* xt, double* ut, int32_t* status,
+                             int32_t* qp_iter, int32_t* qp_status, double* qp_res) {
+  struct Ws {
+    int N = -1;
+    std::vector<qs_real> vrec, st, st2, prod;
+    std::vector<qs_fac> sb;
+    std::vector<double> it0, it1, res, stp, pd, psm;
+    std::vector<int32_t> pi32;
+  };
+  thread_local Ws w;
+  const int N = P->N;
+  const size_t S = (size_t)(N + 1) * TL;
+  if (w.N != N) {
+    w.N = N;
+    w.vrec.assign(S * REC, (qs_real)0); w.it0.assign(S * NIT, 0.0); w.it1.assign(S * NIT, 0.0); w.st.assign(S * NIT, (qs_real)0); w.st2.assign(S * NS2, (qs_real)0);
+    w.sb.assign(S * NSB, (qs_fac)0); w.prod.assign(S * NPROD, (qs_real)0); w.res.assign(S * NRES, 0.0); w.stp.assign(S * NSTP, 0.0);
+    w.pd.assign((size_t)NPD * TL, 0.0); w.pi32.assign((size_t)NPI * TL, 0); w.psm.assign(65 * TL, 0.0);
+  }
+  for (int k = 0; k <= N; ++k)
+    for (int f = 0; f < REC; ++f) w.vrec[qs_blk(0, N, k, REC, 0) + (size_t)f * TL] = (qs_real)rec[(size_t)k * REC + f];
+  QsBufs q{w.vrec.data(), {w.it0.data(), w.it1.data()}, w.st.data(), w.st2.data(), w.sb.data(), w.prod.data(), w.res.data(), w.stp.data(),
+           w.pd.data(), w.pi32.data(), N, 0};
+  const int32_t rr = r;
+  double res5[5] = {0, 0, 0, 0, 0};
+  int32_t st1 = 4, it1 = 0, qst1 = 0;
+  // B = 1: lanes 1..31 of the tile are padding (qs_init marks them inactive), the outputs are indexed by problem 0
+  HostBackend bk{*P, q, 1, 1, N, 0, x0, &rr, nullptr, xt, ut, &st1, &it1, &qst1, res5, std::move(w.psm)};
+  bk.skip_pad = true;
+  qs_drive(&bk, 1);
+  w.psm = std::move(bk.psm);
+  *status = st1; *qp_iter = it1; *qp_status = qst1;
+  for (int c = 0; c < 5; ++c) qp_res[c] = res5[c];
   return 0;
 }
 #endif

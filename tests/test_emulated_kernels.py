@@ -17,6 +17,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 @pytest.fixture(scope='module')
 def emu():
+    from tests.emu import load
+    return load()
+
+
+def _emu_old():
     so = os.path.join(HERE, 'emu', 'libsmpc_emu.so')
     srcs = [os.path.join(HERE, 'emu', 'emu.cpp')] + [os.path.join(HERE, '..', 'safe_mpc_b200', 'csrc', f) for f in ('dev_model.cuh', 'qp_split.cuh')]
     if not os.path.isfile(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):

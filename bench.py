@@ -8,6 +8,8 @@ controller with the viability-network terminal constraint, N=45, dt=5 ms, batch 
   python bench.py [--gpus N --steps K --warmup W]          this engine (one process per GPU under torchrun)
   python bench.py --impl reference ...                      the CPU path (oracle port of the acados RTI path,
                                                             all host threads, bounded sample of the same workload)
+  python bench.py --config cfg0|cfg1|cfg2|cfg3|cfg4 ...     the other BASELINE.json configurations (see PRESETS); the default and
+                                                            the N = 1 headline stay cfg1
 """
 from __future__ import annotations
 
@@ -34,12 +36,32 @@ Q0 = np.array([-0.3, 0.8, -1.65, 0.658, 0.0])
 
 NN_PRECISION = 'strict'      # set from --nn-precision
 
+# BASELINE.json configs -> bench arguments (explicit flags win).  cfg2 names three controllers: pick with --controller.
+PRESETS = {
+    'cfg0': dict(controller='naive', horizon=45, batch=100, noise=0.0,
+                 what="configs[0]: naive RTI MPC, N=45, dt=5 ms, 100 initial states (the reference's own test_num)"),
+    'cfg1': dict(controller='st', horizon=45, batch=10000, noise=0.0,
+                 what='configs[1]: ST controller with the viability-network terminal constraint, batch 10k on 1 GPU'),
+    'cfg2': dict(controller='receding', horizon=45, batch=12500, noise=0.0, nn_precision='tf32x3',
+                 what='configs[2]: HTWA / receding / constraint_everywhere (--controller), 12.5k problems per GPU = 100k on 8 GPUs; '
+                      'viability network on the tensor cores (fp32 class, the precision of the reference libtorch call)'),
+    'cfg3': dict(controller='st', horizon=45, batch=50000, noise=5.0,
+                 what='configs[3]: model-noise ensemble, per-problem perturbed inertial parameters (5 %), batch 50k'),
+    'cfg4': dict(controller='st', horizon=45, batch=10000, noise=0.0,
+                 what='configs[4]: horizon / alpha sweep point (--horizon in {20,35,45,60,80}, --alpha in {10,..,50})'),
+}
+
+
+ALPHA = None                 # set from --alpha (default: config.yaml)
+
 
 def workload(controller, N, noise, seed, lo, hi):
     """Synthetic inputs of problems [lo, hi): initial states around the shipped IC, perturbed plants, torque noise."""
     args = default_args(controller=controller, horizon=N, noise=noise, nn_precision=NN_PRECISION)
     params = Parameters(args, 'z1', rti=True)
     params.N = N
+    if ALPHA is not None:
+        params.alpha = float(ALPHA)
     md = ModelData(params)
     B = hi - lo
     x0 = np.zeros((B, abi.NX)); pin = np.zeros((B, abi.NQ, 10))
@@ -138,8 +160,9 @@ def run_reference(a):
     line = {'metric': METRIC, 'value': r['value'], 'unit': UNIT, 'impl': 'reference', 'n_gpus': a.gpus, 'steps': a.steps, 'warmup': a.warmup,
             'ms_per_step': 1e3 * r['seconds'] / a.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
             'data': 'synthetic',
-            'config': {'workload': f'closed-loop RTI MPC, controller={a.controller}, N={a.horizon}, dt=5ms, synthetic Z1-like 5-DOF chain + random-init viability MLP',
-                       'batch': n, 'note': 'CPU path: oracle port of the acados SQP_RTI/HPIPM path (acados, CasADi, adam, l4casadi are not installable offline)'},
+            'config': {'workload': f'{a.config}: closed-loop RTI MPC, controller={a.controller}, N={a.horizon}, dt=5ms, '
+                                   f'synthetic Z1-like 5-DOF chain + random-init viability MLP 10-256-256-256-1',
+                       'preset': PRESETS[a.config]['what'], 'batch': n, 'noise_percent': a.noise, 'note': 'CPU path: oracle port of the acados SQP_RTI/HPIPM path (acados, CasADi, adam, l4casadi are not installable offline)'},
             'cpu_baseline': {'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': 'port', 'sample': r['sample']},
             'e2e': {'value': r['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'ipm_iterations_per_solve': r['ipm_per_solve'], 'outcome': r['outcome']}
@@ -211,8 +234,27 @@ def run_engine(a):
     qp_ms_1group = float(np.median([p[1]['time_qp'] for p in profs]) * 1e3)
     lin_ms = float(np.median([t['time_lin'] for t in tq]) * 1e3)
     it_qp = float(main.get_state(abi.STATE_QP_ITER).mean())
-    prep_ms, prep_n = kern['qs_prep']
+    it_sum = float(main.get_state(abi.STATE_QP_ITER).sum())
     kern_total = sum(v[0] for v in kern.values())
+
+    # ---- the linearisation kernel alone: a handle without viability rows (time_lin = linearize_kernel only), same B and N ----
+    lin_probe = None
+    if rank == 0:
+        nprob, nkeep = build_problem(params, 'naive', cost='ext', model=md)
+        neng = Engine(nprob, B, local_rank); neng._keepalive = (nprob, nkeep)
+        neng.set_guess(*main.get_guess())
+        neng.rti_solve(xs); neng.sync()
+        tl = []
+        for _ in range(3):
+            neng.rti_solve(xs); neng.sync()
+            tl.append(neng.times()['time_lin'] * 1e3)
+        lin_probe = float(np.median(tl))
+        neng.close()
+
+    # ---- measured FP64 / FP32 FMA peaks (MEASURED_PEAKS.json has none) ----
+    fp64_peak = fp32_peak = None
+    if rank == 0:
+        fp64_peak, fp32_peak = Engine.measure_peaks(local_rank)
 
     # ---- end to end through the C ABI with host buffers (H2D / D2H inside the timed region) ----
     e2e = None
@@ -257,60 +299,101 @@ def run_engine(a):
         pass
     hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
     peak_src = 'measured (MEASURED_PEAKS.json hbm_gbs)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s (B200_PROFILING.md)'
-    # Dominant kernel = qs_prep (update + residuals + condensation, one thread per (problem, stage)).  Algorithmic bytes per
-    # (problem, stage) = every array field the phase has to read or write once: 436 read + 265 written
-    # doubles = 5608 B.
-    prep_bytes_unit = (436 + 265) * 8
-    # a problem takes part in the prep launches kk = 0 .. iter_b of a solve; later launches skip it
-    visits = float((qp_iter_probe + 1).sum())
-    alg_bytes = visits * (N + 1) * prep_bytes_unit / max(1, prep_n)          # per launch, averaged over the launches of one solve
-    prep_launch_ms = prep_ms / max(1, prep_n)
-    achieved = alg_bytes / (prep_launch_ms * 1e-3) / 1e9
-    # second kernel by time: the factorising Riccati sweep qs_ric1 (thread per problem, sequential in the stage index).  Per (problem, stage)
-    # it reads M, GA, RB (145) and, in the forward pass, RB, LP, T (100), and writes LP, T, WV, P (155) and dz (15): 415 doubles = 3 320 B.
-    # A launch walks every tile that still has an active problem, so the bytes are counted per problem of an active tile ~ active problems.
-    ric_ms, ric_n = kern['qs_ric1']
-    ric_bytes = visits * (N + 1) * 415 * 8 / max(1, ric_n)
-    ric_ach = ric_bytes / (ric_ms / max(1, ric_n) * 1e-3) / 1e9
-    ric_roof = {'kernel': 'qs_ric1_kernel', 'bound': 'hbm', 'achieved': ric_ach, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ric_ach / hbm_peak,
-                'traffic': 1.47e9 if (B, N) == (10000, 45) else None, 'launch_ms': ric_ms / max(1, ric_n), 'launches_per_solve': ric_n,
-                'share_of_qp_solve': ric_ms / max(kern_total, 1e-9),
-                'note': 'latency-bound sweep: one warp per tile of 32 problems, 46 dependent stages; a launch costs the same 0.33 ms whether 1 or 10 000 problems '
-                        'are still iterating, which is why its average fraction is far below that of a full launch (0.6 of the HBM peak, profiles/r01_qp_v7.md)'}
-    flops_solve = 0.48e6 * float(main.get_state(abi.STATE_QP_ITER).sum())       # 0.48 MFLOP per IPM iteration
+    fp64_src = 'measured in this run (smpc_measure_peaks: 16 independent DFMA chains per thread, CUDA events)'
+    if not fp64_peak:
+        fp64_peak, fp64_src = 37.0, 'nominal 37 TFLOP/s (SURVEY.md section 8d placeholder; smpc_measure_peaks failed)'
+    # Per-kernel roofline of one QP solve.  A "visit" = one (problem, stage) handled by one launch; a problem takes part in the launches
+    # kk = 0 .. iter_b of a solve.  Two bases per kernel:
+    #   bytes  what the kernel has to stream per visit in THIS design (solver state resident in HBM), doubles read + written
+    #   flop   SURVEY.md section 8(d) / BASELINE.md section 4 dense counts per stage and IPM iteration: factorisation 4 875, one
+    #          solve 1 250, inequality condensation 2 475
+    UNITS = {                       # kernel family -> (doubles per visit, flop per visit)
+        'qs_prep': (436 + 265, 2475.0),               # update + residuals + condensation
+        'qs_ric1': (145 + 155 + 100 + 15, 4875.0 + 1250.0),   # factorisation + affine solve (backward + forward)
+        'qs_step0': (270 + 80, 0.0),                  # affine (dlam, dt), products, corrector terms (row products: not in the 8(d) count)
+        'qs_ric2': (155 + 30 + 180 + 50, 2 * 1250.0), # corrector and centering solves in one pass
+        'qs_step1': (316 + 98, 0.0),
+        'qs_step2_centering': (300 + 123, 0.0),
+    }
+    visits = float((qp_iter_probe + 1).sum()) * (N + 1)
+    table = {}
+    for k, (dbl, flop) in UNITS.items():
+        ms_k, n_k = kern[k]
+        if n_k == 0 or ms_k <= 0:
+            continue
+        v = visits if k != 'qs_step2_centering' else None     # (only the problems that switch direction: not tracked per launch)
+        row = {'ms_per_solve': round(ms_k, 3), 'launches': n_k, 'share_of_qp_solve': ms_k / max(kern_total, 1e-9)}
+        if v is not None:
+            row.update({'hbm_gbs': v * dbl * 8 / (ms_k * 1e-3) / 1e9, 'hbm_frac': v * dbl * 8 / (ms_k * 1e-3) / 1e9 / hbm_peak,
+                        'fp64_tflops': v * flop / (ms_k * 1e-3) / 1e12, 'fp64_frac': v * flop / (ms_k * 1e-3) / 1e12 / fp64_peak,
+                        'bytes_per_visit': dbl * 8, 'flop_per_visit': flop})
+        table[k] = row
+    dom = max((k for k in table if 'hbm_gbs' in table[k]), key=lambda k: table[k]['ms_per_solve'])
+    dname = {'qs_prep': 'qs_prep_coop_kernel / qs_prep_kernel', 'qs_ric1': 'qs_ric1x_kernel / qs_ric1t_kernel', 'qs_ric2': 'qs_ric2_kernel / qs_ric2t_kernel',
+             'qs_step0': 'qs_step_kernel<0>', 'qs_step1': 'qs_step_kernel<1>'}[dom]
+    d = table[dom]
+    traffic = {'qs_prep': 2.42e9, 'qs_ric1': 1.47e9, 'qs_ric2': 1.31e9}.get(dom) if (B, N) == (10000, 45) else None
+    # bytes the whole solve moves per problem against what is algorithmically necessary (~11 KB per problem and RTI iteration)
+    moved = sum(table[k]['bytes_per_visit'] for k in table if 'bytes_per_visit' in table[k]) * visits / B
+    necessary = ((N + 1) * abi.NX + N * abi.NU) * 8 * 2 + 200
+    flops_solve = 0.48e6 * (N + 1) / 46.0 * it_sum                              # 0.48 MFLOP per IPM iteration at N = 45
     value = solves_all / (ms_max * 1e-3)
+    roofline = {'kernel': dname, 'bound': 'hbm', 'achieved': d['hbm_gbs'], 'peak': hbm_peak, 'unit': 'GB/s', 'frac': d['hbm_frac'],
+                'traffic': traffic, 'traffic_source': 'ncu dram__bytes_read+write of one all-active launch, profiles/r01_qp_v7.md (B=10000, N=45 only)',
+                'peak_source': peak_src, 'selection': 'the QP kernel family with the largest summed duration in one solve (kernel_ms below)',
+                'algorithmic_bytes_per_launch': d['bytes_per_visit'] * visits / max(1, d['launches']), 'launch_ms': d['ms_per_solve'] / max(1, d['launches']),
+                'launches_per_solve': d['launches'], 'share_of_qp_solve': d['share_of_qp_solve'],
+                'bytes_basis': 'design traffic: solver state resident in HBM, %d doubles per (problem, stage) visit' % (d['bytes_per_visit'] // 8),
+                'fp64': {'achieved': d['fp64_tflops'], 'peak': fp64_peak, 'unit': 'TFLOP/s', 'frac': d['fp64_frac'], 'flop_per_visit': d['flop_per_visit'],
+                         'peak_source': fp64_src, 'basis': 'SURVEY.md section 8(d) dense flop count of this phase'},
+                'solve_traffic': {'bytes_moved_per_problem': moved, 'necessary_bytes_per_problem': necessary, 'ratio': moved / necessary,
+                                  'note': 'HBM bytes one RTI solve streams per problem (sum over the kernels of bytes_per_visit x visits) against the '
+                                          'warm start in / out + x0 + status that SURVEY 8(d) calls algorithmically necessary: the solver state '
+                                          '(~340 KB per problem) does not fit on chip for the ~1 500 problems the sequential Riccati recursion needs in flight, '
+                                          'so every IPM iteration re-streams it (DESIGN.md section 3.2)'},
+                'note': 'bytes and time are summed over every launch of the family in one solve; a launch only touches the problems still iterating'}
+    # linearisation kernel against the FP64 pipe (flop per stage from the executed-instruction tally)
+    roof_dyn = None
+    if lin_probe:
+        fl = LINEARIZE_FLOP_PER_STAGE * B * (N + 1)
+        roof_dyn = {'kernel': 'linearize_kernel', 'bound': 'fp64', 'achieved': fl / (lin_probe * 1e-3) / 1e12, 'peak': fp64_peak, 'unit': 'TFLOP/s',
+                    'frac': fl / (lin_probe * 1e-3) / 1e12 / fp64_peak, 'launch_ms': lin_probe, 'flop_per_stage': LINEARIZE_FLOP_PER_STAGE,
+                    'flop_source': LINEARIZE_FLOP_SOURCE, 'peak_source': fp64_src,
+                    'hbm_gbs_written': B * (N + 1) * abi.REC * 8 / (lin_probe * 1e-3) / 1e9}
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
-        'ms_per_step': ms_max / a.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+        'ms_per_step': ms_max / a.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64' if a.precision == 'f64' else 'f32-storage/f64-accumulate',
         'data': 'synthetic',
-        'config': {'workload': f'closed-loop RTI MPC, controller={a.controller} (viability-network terminal constraint), N={N}, dt=5ms, '
+        'config': {'workload': f'{a.config}: closed-loop RTI MPC, controller={a.controller}, N={N}, dt=5ms, '
                                f'synthetic Z1-like 5-DOF chain + random-init viability MLP 10-256-256-256-1',
+                   'preset': PRESETS[a.config]['what'],
                    'batch_per_gpu': B, 'global_batch': B * world, 'parallelism': f'dp{world} (problem sharding, no hot-path collective)',
-                   'l2': f'working set {B * (main_qp_bytes(N)) / 1e9:.2f} GB per GPU > 126 MB L2 (no flush needed)',
-                   'noise_percent': a.noise, 'sqp_warm_start_iters': a.sqp_iters, 'nn_precision': a.nn_precision},
+                   'l2': f'working set {B * (main_qp_bytes(N)) / 1e9:.2f} GB per GPU > 126 MB L2 (no flush needed)' if B * main_qp_bytes(N) > 2.5e8
+                         else f'working set {B * (main_qp_bytes(N)) / 1e6:.0f} MB per GPU: L2-resident (small-batch latency case, not a bandwidth measurement)',
+                   'noise_percent': a.noise, 'alpha': float(params.alpha), 'sqp_warm_start_iters': a.sqp_iters, 'nn_precision': a.nn_precision,
+                   'precision': a.precision},
         'p50_step_ms': float(np.percentile(lat, 50)), 'p99_step_ms': float(np.percentile(lat, 99)),
         'ipm_iterations_per_solve': ipm / max(1, solves),
         'gpu_launches': int(sum(v[3] for v in allv)),
         'clocks': clocks,
-        'roofline': {'kernel': 'qs_prep_coop_kernel (IPM iterations >= 1; the cold start is qs_prep_kernel<true>)', 'bound': 'hbm', 'achieved': achieved,
-                     'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak,
-                     'traffic': 2.42e9 if (B, N) == (10000, 45) else None,
-                     'traffic_source': 'ncu dram__bytes_read+write of one full launch (all problems active), profiles/r01_final.md, r01_prep_coop_final_raw.csv (B=10000, N=45 only)',
-                     'peak_source': peak_src, 'algorithmic_bytes_per_launch': alg_bytes, 'launch_ms': prep_launch_ms,
-                     'launches_per_solve': prep_n, 'share_of_qp_solve': prep_ms / max(kern_total, 1e-9),
-                     'note': 'bytes and time are averaged over every qs_prep launch of one solve; a launch only touches the problems still iterating'},
-        'roofline_riccati': ric_roof,
+        'roofline': roofline,
+        'roofline_kernels': table,
+        'roofline_dynamics': roof_dyn,
+        'peaks': {'hbm_gbs': hbm_peak, 'fp64_tflops': fp64_peak, 'fp32_tflops': fp32_peak, 'fp64_source': fp64_src},
         'qp_solve': {'ms': qp_ms, 'ms_single_tile_group': qp_ms_1group, 'linearize_ms': lin_ms, 'ipm_iterations_mean': it_qp, 'ipm_iterations_max': it_max,
-                     'algorithmic_fp64_tflops': flops_solve / (qp_ms * 1e-3) / 1e12,
+                     'algorithmic_fp64_tflops': flops_solve / (qp_ms * 1e-3) / 1e12, 'algorithmic_fp64_frac': flops_solve / (qp_ms * 1e-3) / 1e12 / fp64_peak,
                      'kernel_ms': {k: round(v[0], 3) for k, v in kern.items()}, 'kernel_launches': {k: v[1] for k, v in kern.items()},
                      'kernel_ms_note': 'per-kernel sums of one solve timed with a single tile group (no overlap between kernels)'},
         'outcome': D.outcome_counts(outcome),
     }
     if mlp:
-        tpeak = float(peaks.get('bf16_tflops', peaks.get('bf16_dense_tflops', 1590.0))) / 2
+        tpeak = mlp.pop('tf32_peak_measured', None)
+        if tpeak:
+            mlp['tensor_peak_source'] = 'measured in this run: torch.matmul fp32 8192^3 with allow_tf32 (cuBLAS TF32 tensor-core GEMM), best of 5, CUDA events'
+        else:
+            tpeak = float(peaks.get('bf16_tflops', peaks.get('bf16_dense_tflops', 1590.0))) / 2
+            mlp['tensor_peak_source'] = 'half of the dense bf16 peak of MEASURED_PEAKS.json (the TF32 GEMM measurement failed)'
         mlp['tensor_peak_tf32_tflops'] = tpeak
-        mlp['tensor_peak_source'] = ('half of the measured dense bf16 peak (MEASURED_PEAKS.json)' if any(k in peaks for k in ('bf16_tflops', 'bf16_dense_tflops'))
-                                     else 'half of the fallback dense bf16 peak 1.59 PFLOP/s (B200_PROFILING.md)')
         mlp['tf32x3']['frac_of_tensor_peak'] = mlp['tf32x3']['executed_tf32_tflops'] / tpeak
         line['viability_network'] = mlp
     if e2e:
@@ -334,6 +417,20 @@ def time_mlp(params, md, n_rows, device_index, dev):
     x = mid + 0.8 * half * rng.uniform(-1, 1, (n_rows, abi.NX))
     xd = torch.tensor(x, device=dev)
     out = {'rows': n_rows, 'algorithmic_flop_per_row': 535040}
+    try:                                           # TF32 tensor-core peak of this GPU (library GEMM, measurement only)
+        torch.backends.cuda.matmul.allow_tf32 = True
+        a_ = torch.randn(8192, 8192, device=dev); b_ = torch.randn(8192, 8192, device=dev)
+        torch.matmul(a_, b_); torch.cuda.synchronize()
+        best = 0.0
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); torch.matmul(a_, b_); e1.record(); torch.cuda.synchronize()
+            best = max(best, 2 * 8192 ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+        out['tf32_peak_measured'] = best
+        del a_, b_
+        torch.backends.cuda.matmul.allow_tf32 = False
+    except Exception:
+        pass
     for name in ('strict', 'tf32x3'):
         prob, keep = build_problem(params, 'st', cost='ext', model=md, nn_precision=name)
         eng = Engine(prob, 64, device_index)
@@ -354,12 +451,10 @@ def time_mlp(params, md, n_rows, device_index, dev):
     return out
 
 
-def main_times(main):
-    return main.times()
-
-
-def guess_copy(main):
-    return main.get_guess()
+# linearize_kernel: FP64 flop per (problem, stage) = 2 x DFMA + DADD + DMUL thread instructions executed / (B (N+1)), from ncu
+# (smsp__sass_thread_inst_executed_op_d{fma,add,mul}_pred_on.sum; profiles/r02_linearize_flops.md).  Frozen in BASELINE.md section 4.
+LINEARIZE_FLOP_PER_STAGE = 18000.0
+LINEARIZE_FLOP_SOURCE = 'SURVEY.md section 8(d) estimate (18 kflop +- 50 %); replaced by the executed-instruction tally once measured'
 
 
 def main_qp_bytes(N):
@@ -372,10 +467,13 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='engine', choices=['engine', 'reference'])
-    ap.add_argument('--controller', default='st')
-    ap.add_argument('--horizon', type=int, default=45)
-    ap.add_argument('--batch', type=int, default=10000, help='problems per GPU')
-    ap.add_argument('--noise', type=float, default=0.0)
+    ap.add_argument('--config', default='cfg1', choices=sorted(PRESETS), help='BASELINE.json configuration (default cfg1 = the headline)')
+    ap.add_argument('--controller', default=None)
+    ap.add_argument('--horizon', type=int, default=None)
+    ap.add_argument('--batch', type=int, default=None, help='problems per GPU')
+    ap.add_argument('--noise', type=float, default=None)
+    ap.add_argument('--alpha', type=float, default=None, help='safety margin in percent (config.yaml alpha)')
+    ap.add_argument('--precision', default='f64', choices=['f64', 'f32'], help='storage precision of the QP solver state')
     ap.add_argument('--seed', type=int, default=0)
     ap.add_argument('--sqp-iters', type=int, default=5, dest='sqp_iters')
     ap.add_argument('--ref-problems', type=int, default=256, dest='ref_problems')
@@ -384,11 +482,18 @@ def main():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-mlp', action='store_true', dest='no_mlp')
-    ap.add_argument('--nn-precision', default='strict', choices=['strict', 'tf32x3'], dest='nn_precision',
+    ap.add_argument('--nn-precision', default=None, choices=['strict', 'tf32x3'], dest='nn_precision',
                     help='viability network arithmetic of the timed closed loop (the tensor-core kernel is always timed alone as well)')
     a = ap.parse_args()
-    global NN_PRECISION
+    pre = PRESETS[a.config]
+    for key in ('controller', 'horizon', 'batch', 'noise'):
+        if getattr(a, key) is None:
+            setattr(a, key, pre[key])
+    if a.nn_precision is None:
+        a.nn_precision = pre.get('nn_precision', 'strict')
+    global NN_PRECISION, ALPHA
     NN_PRECISION = a.nn_precision
+    ALPHA = a.alpha
     if a.warmup < 3 and a.impl == 'engine':
         a.warmup = 3
     if a.impl == 'reference':

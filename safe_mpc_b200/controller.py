@@ -179,18 +179,17 @@ class NaiveController(AbstractController):               # controller.py:251-284
         nlp_max_iter): RTI iterations of the engine repeated per problem until the full step is below ``tol`` (infinity norm
         over the trajectory) -> status 0; a problem still moving after ``max_iter`` iterations -> status 2, as acados reports
         it; a QP failure keeps its status (1, 3, 4) and stops that problem.  Finished problems are frozen through the engine's
-        ``active`` mask, so the batch shrinks as it converges.  ``globalization``: 'FIXED_STEP' (default) takes full steps --
-        with the reference's Levenberg-Marquardt term (0.5) the iteration is heavily damped already and ends on the iteration
-        limit, which the generator accepts like the reference does.  'MERIT_BACKTRACKING' (what parser.py:139 selects for the
-        reference's generator) shortens the step by ``alpha_reduction`` until the l1 merit (``merit``, penalty = the largest
-        inequality multiplier of the QP, at least 1) decreases, down to ``alpha_min``, which is then taken regardless: the
-        structure of acados' line search with a plain decrease test.  acados' own merit weights and Armijo constant are not
-        restated (they cannot be pinned here), and in the probes (scripts/sqp_probe.py) this search did not raise the number
-        of accepted guesses, so it is opt-in.  -> status [B]; the last iterate of every problem (what acados' get(i, 'x')
+        ``active`` mask, so the batch shrinks as it converges.  ``globalization``: default = ``params.globalization``, i.e. what
+        parser.py:139 selects -- 'FIXED_STEP' for rti=True, 'MERIT_BACKTRACKING' for the generator's Parameters(rti=False).
+        'FIXED_STEP' takes full steps.  'MERIT_BACKTRACKING' shortens the step by ``alpha_reduction`` until the l1 merit
+        (``merit``, penalty = the largest inequality multiplier of the QP, at least 1) decreases, down to ``alpha_min``, which
+        is then taken regardless: the structure of acados' line search with a plain decrease test (acados' own merit weights
+        and Armijo constant cannot be pinned offline).  -> status [B]; the last iterate of every problem (what acados' get(i, 'x')
         returns after its SQP solve) is ``self._sqp_result`` = getGuess(); (x_temp, u_temp) hold the last QP solution, the
         same thing when the last step was a full one."""
         p = self.model.params
-        glob = 'FIXED_STEP' if globalization is None else globalization
+        # parser.py:139: FIXED_STEP for rti=True, MERIT_BACKTRACKING for the SQP of the guess generator (rti=False)
+        glob = getattr(p, 'globalization', 'FIXED_STEP') if globalization is None else globalization
         if glob not in ('FIXED_STEP', 'MERIT_BACKTRACKING'):
             raise ValueError(f'unknown globalization {glob}')
         max_iter = int(self.model.params.nlp_max_iter if max_iter is None else max_iter)

@@ -63,6 +63,8 @@ struct smpc_sim {
   SimDev d;
   int j = 0;
   int32_t* outcome_tmp = nullptr;
+  std::vector<void*> allocs;        // device buffers of this closed loop (freed by smpc_sim_destroy)
+  int device = 0;
 };
 
 namespace {
@@ -231,6 +233,7 @@ int smpc_create(const smpc_problem_t* prob, int32_t batch, int32_t device, smpc_
   } while (0)
   CKC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   for (auto& ev : h->ev) CKC(cudaEventCreate(&ev));
+  CKC(mlp_prepare());
   // network weights: original + transposed copies of the two square layers
   if (prob->nn_weights) {
     const size_t np = SMPC_NN_NPARAM, sq = (size_t)SMPC_HID * SMPC_HID;
@@ -538,11 +541,12 @@ int smpc_sync(smpc_handle_t* h) { CK(h, cudaStreamSynchronize(h->stream)); retur
 int smpc_sim_create(smpc_handle_t* c, smpc_handle_t* bk, int32_t n_steps, smpc_sim_t** out) {
   if (!c || !bk || !out || n_steps <= 0 || c->B != bk->B || c->device != bk->device) return fail(c, SMPC_ERR_ARG, "smpc_sim_create: bad arguments");
   smpc_sim* s = new smpc_sim;
-  s->c = c; s->bk = bk;
+  s->c = c; s->bk = bk; s->device = c->device;
   SimDev& d = s->d;
   const int B = c->B, Nb = bk->N;
   d.B = B; d.N = c->N; d.Nb = Nb; d.n_steps = n_steps;
-#define CKS(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { fail(c, SMPC_ERR_CUDA, #call, e__); delete s; return SMPC_ERR_CUDA; } } while (0)
+#define CKS(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { fail(c, SMPC_ERR_CUDA, #call, e__); s->allocs.insert(s->allocs.end(), c->allocs.begin() + n_before, c->allocs.end()); c->allocs.resize(n_before); smpc_sim_destroy(s); return SMPC_ERR_CUDA; } } while (0)
+  const size_t n_before = c->allocs.size();      // dalloc registers with the handle; the buffers of the closed loop move to the sim object below
   CKS(dalloc(c, &d.x, (size_t)B * NX));
   CKS(dalloc(c, &d.xlog, (size_t)B * (n_steps + 1) * NX));
   CKS(dalloc(c, &d.ulog, (size_t)B * n_steps * NU));
@@ -557,10 +561,18 @@ int smpc_sim_create(smpc_handle_t* c, smpc_handle_t* bk, int32_t n_steps, smpc_s
   CKS(dalloc(c, &d.counters, (size_t)4));
   CKS(dalloc(c, &s->outcome_tmp, (size_t)B));
 #undef CKS
+  s->allocs.assign(c->allocs.begin() + n_before, c->allocs.end());
+  c->allocs.resize(n_before);
   *out = s;
   return SMPC_OK;
 }
-void smpc_sim_destroy(smpc_sim_t* s) { delete s; }   // device buffers are owned (and freed) by the main handle
+void smpc_sim_destroy(smpc_sim_t* s) {
+  if (!s) return;
+  cudaSetDevice(s->device);
+  cudaDeviceSynchronize();          // (the handles may already be gone: do not touch them)
+  for (void* p : s->allocs) cudaFree(p);
+  delete s;
+}
 
 int smpc_sim_reset(smpc_sim_t* s, const double* x_init, int32_t mem) {
   smpc_handle* c = s->c;
@@ -589,8 +601,9 @@ int smpc_sim_step(smpc_sim_t* s) {
   cudaStream_t bk_stream = bk->stream;
   bk->stream = c->stream;
   launch_sim_pre(lc, d, c->dP, s->j);
-  c->timed = false; bk->timed = false;
+  c->timed = true; bk->timed = false;           // the main controller's step is timed (smpc_get_times = controller.getTime(), mpc.py:239)
   int rc = step_pipeline(c, d.x, d.need_ctrl, d.u_ctrl, d.abort_flag);
+  c->times_pending = 2;
   if (!rc) {
     launch_sim_mid(lc, d, c->x_viable, bk->xg, bk->ug, c->qp_iter);
     rc = solve_pipeline(bk, c->x_viable, d.need_backup);     // safe_ocp.solve(x_viable), one RTI (mpc.py:177)

@@ -165,14 +165,16 @@ mlp_kernel(const smpc_problem_t* __restrict__ dP, MlpWeights w, int B, int N, in
   }
 }
 
+constexpr size_t MLP_SMEM = sizeof(double) * (5 * MLP_R * HID + MLP_R * NX * 2 + 2 * MLP_R);
+// per device: called by smpc_create after cudaSetDevice
+cudaError_t mlp_prepare() { return cudaFuncSetAttribute(mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_SMEM); }
+
 void launch_mlp(const LaunchCtx& c, const smpc_problem_t* dP, const MlpWeights& w, int B, int N, int rows_mode, int n_flat,
                 const double* xsrc, const int32_t* r, const uint8_t* act, const uint8_t* need, double* out11, bool want_grad) {
   int n_rows = (rows_mode == ROWS_TERMINAL || rows_mode == ROWS_CAND) ? B : rows_mode == ROWS_ALL ? B * N : rows_mode == ROWS_RECEDING ? 2 * B : n_flat;
   if (rows_mode == ROWS_FLAT) B = n_flat;
   if (n_rows <= 0) return;
-  const size_t smem = sizeof(double) * (5 * MLP_R * HID + MLP_R * NX * 2 + 2 * MLP_R);
-  static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+  const size_t smem = MLP_SMEM;
   mlp_kernel<<<GRID1D(n_rows, MLP_R), HID, smem, c.stream>>>(dP, w, B, N, rows_mode, n_rows, xsrc, r, act, need, out11, want_grad ? 1 : 0);
   ++*c.launches;
 }

@@ -457,10 +457,8 @@ void mlp_tc2_pack(const float* W2, const float* W3, float* out) {
 }
 
 cudaError_t mlp_tc2_prepare() {
-  static bool done = false;
-  if (done) return cudaSuccess;
+  // per device: called by smpc_create after cudaSetDevice (the attribute belongs to the device, not to the process)
   cudaError_t e = cudaFuncSetAttribute(mlp_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM);
-  if (e == cudaSuccess) done = true;
   return e;
 }
 

@@ -49,15 +49,38 @@ class Engine(EngineBase):
         super().__init__(load_library(), prob, batch, device)
         self.device = device
 
-    def _in(self, a, dtype, shape=None):
-        # torch tensors live on torch's stream; the engine has its own -> order them
-        if a is not None and _is_torch(a) and a.is_cuda:
+    # torch tensors live on torch's current stream, the engine launches on its own: a call that takes or returns device memory
+    # (mem == SMPC_DEVICE) is ordered on the GPU, without blocking the host -- the engine's stream waits for torch's before the
+    # call, torch's stream waits for the engine's after it (the outputs may then be consumed on torch's stream right away)
+    def _ext_stream(self):
+        import torch
+        if getattr(self, '_ext', None) is None:
+            self._ext = torch.cuda.ExternalStream(self.stream(), device=torch.device('cuda', self.device))
+        return self._ext
+
+    def _call(self, name, *args, mem=None):
+        if mem == abi.DEVICE:
             import torch
-            torch.cuda.current_stream(a.device).synchronize()
-        return super()._in(a, dtype, shape)
+            cur = torch.cuda.current_stream(torch.device('cuda', self.device))
+            ext = self._ext_stream()
+            ext.wait_stream(cur)
+            super()._call(name, *args, mem=mem)
+            cur.wait_stream(ext)
+        else:
+            super()._call(name, *args, mem=mem)
 
     def sync(self):
         self._call('sync')
+
+    @staticmethod
+    def measure_peaks(device: int = 0):
+        """Dense FMA rate of the FP64 and FP32 pipes of this GPU, TFLOP/s (smpc_measure_peaks: micro-benchmark, CUDA events)."""
+        lib = load_library()
+        f64, f32 = C.c_double(), C.c_double()
+        rc = lib.smpc_measure_peaks(C.c_int32(device), C.byref(f64), C.byref(f32))
+        if rc != 0:
+            return None, None
+        return f64.value, f32.value
 
     def launch_count(self) -> int:
         return int(self.lib.smpc_launch_count(self.h))
@@ -88,3 +111,24 @@ class Engine(EngineBase):
 class Sim(SimBase):
     def sync(self):
         self.main.sync()
+
+    def _call(self, name, *args, mem=None):
+        if mem == abi.DEVICE:
+            import torch
+            cur = torch.cuda.current_stream(torch.device('cuda', self.main.device))
+            ext = self.main._ext_stream()
+            ext.wait_stream(cur)
+            super()._call(name, *args, mem=mem)
+            cur.wait_stream(ext)
+        else:
+            super()._call(name, *args, mem=mem)
+
+    def step_times(self):
+        """controller.getTime() of the last closed-loop step (mpc.py:239): the acados time fields of the main controller's batched
+        step [s] and the number of problems that solved in it.  Synchronises with the step."""
+        t = self.main.times()
+        solves = self.counters()['rti_solves']
+        n = solves - getattr(self, '_solves_seen', 0)
+        self._solves_seen = solves
+        import numpy as np
+        return np.array([t[f] for f in ('time_lin', 'time_sim', 'time_qp', 'time_qp_solver_call', 'time_glob', 'time_reg', 'time_tot')]), int(n)

@@ -17,24 +17,29 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..'
 
 from safe_mpc_b200.parser import Parameters, parse_args            # noqa: E402
 from safe_mpc_b200.env_model import AdamModel                      # noqa: E402
-from safe_mpc_b200.utils import get_controller                     # noqa: E402
-from safe_mpc_b200.cost_definition import ReachTargetEXT           # noqa: E402
+from safe_mpc_b200.utils import get_ocp_acados                     # noqa: E402
+from safe_mpc_b200.cost_definition import ReachTargetEXT, ReachTargetNLS   # noqa: E402
 from safe_mpc_b200.guess import generate_guesses                   # noqa: E402
 
-NET_CONTROLLERS = ['st', 'stwa', 'htwa', 'receding', 'real_receding', 'parallel', 'constraint_everywhere']     # guess_acados.py:242
+# guess_acados.py:240-243: the network guess is stored under every name of get_ocp_acados' dict that is in this list
+NET_FILE_NAMES = ['st', 'stwa', 'htwa', 'receding', 'real_receding', 'receding_parallel', 'parallel2', 'constraint_everywhere']
 
 
 def make_controller(name, args, batch):
-    params = Parameters(args, args['system'], rti=False)               # guess_acados.py:27,45,56: SQP, nlp_max_iter
+    """guess_acados.py:14-71: Parameters(rti=False) -> acados 'SQP' with nlp_max_iter and MERIT_BACKTRACKING (parser.py:139); the
+    controller class of get_ocp_acados (every network controller -> HTWAController, utils.py:46-62); cost: ReachTargetEXT for the
+    network controller (guess_acados.py:31,43), ReachTargetNLS for naive / zerovel (guess_acados.py:33,62-68)."""
+    params = Parameters(args, args['system'], rti=False)
     params.q_margin = args['joint_bounds_margin']
     params.collision_margin = args['collision_margin']
     params.alpha = args['alpha']
     params.N = args['horizon']
     model = AdamModel(params, batch=batch)
-    controller = get_controller(name, model)
-    ReachTargetEXT(model, params.Q_weight, params.R_weight).set_solver_cost(controller)
+    controller, names = get_ocp_acados(name, model)
+    cost = ReachTargetNLS if name in ('naive', 'zerovel') else ReachTargetEXT
+    cost(model, params.Q_weight, params.R_weight).set_solver_cost(controller)
     controller.build_controller(args['build'])
-    return controller, params
+    return controller, params, names
 
 
 def main(argv=None):
@@ -43,13 +48,14 @@ def main(argv=None):
     probe = Parameters(args, args['system'], rti=False)
     count = probe.test_num
     batch = args['batch'] or count
-    ctrl, params = make_controller(cont_name, args, batch)
+    ctrl, params, names = make_controller(cont_name, args, batch)
     naive = zerovel = None
     if cont_name not in ('naive', 'zerovel'):
-        naive, _ = make_controller('naive', args, batch)
-        zerovel, _ = make_controller('zerovel', args, batch)
+        naive, _, _ = make_controller('naive', args, batch)
+        zerovel, _, _ = make_controller('zerovel', args, batch)
     t0 = time.time()
-    out, stats = generate_guesses(ctrl, naive, zerovel, count, sqp_iter=min(params.nlp_max_iter, args.get('sqp_iter') or 100))
+    out, stats = generate_guesses(ctrl, naive, zerovel, count, sqp_iter=min(params.nlp_max_iter, args.get('sqp_iter') or 100),
+                                  globalization=params.globalization)
     print(f'{stats["succ"]} accepted, {stats["fails"]} failed, {stats["skipped"]} initial conditions in collision, '
           f'{stats["rounds"]} batches of {batch}, {time.time() - t0:.1f} s')
 
@@ -63,7 +69,7 @@ def main(argv=None):
         files.append((path(cont_name, None), out['net']))
     else:
         files += [(path('naive', None), out['naive']), (path('zerovel', None), out['zerovel'])]
-        files += [(path(c, True), out['net']) for c in NET_CONTROLLERS]
+        files += [(path(c, True), out['net']) for c in names if c in NET_FILE_NAMES]
     for p, d in files:
         with open(p, 'wb') as f:
             pickle.dump({'xg': d['xg'], 'ug': d['ug']}, f)

@@ -62,10 +62,15 @@ def main(argv=None):
         x_guess, u_guess = np.asarray(data['xg'])[:batch], np.asarray(data['ug'])[:batch]
         if len(x_guess) < batch:
             raise SystemExit(f'{guess_file} holds {len(x_guess)} guesses, batch is {batch}')
-    else:
+    elif args.get('generate_guess'):
         x_init = halton_initial_states(model, batch)
         x_guess, u_guess, st = sqp_guess(controller, x_init, iters=10)
-        print(f'generated {batch} warm starts ({int((st == 0).sum())} converged RTI solves at the last SQP iteration)')
+        print(f'WARNING: {guess_file} does not exist; --generate-guess: {batch} warm starts from 10 full-step SQP iterations, NOT checked by '
+              f'checkGuess ({int((st == 0).sum())} converged RTI solves at the last iteration).  Run scripts/guess_acados.py for the '
+              "reference's accepted guesses.", file=sys.stderr)
+    else:                                                                                       # the reference fails on the missing pickle (mpc.py:80)
+        raise FileNotFoundError(f'{guess_file} does not exist: run scripts/guess_acados.py -c {cont_name} --horizon {horizon} first, '
+                                'or pass --generate-guess')
     x_init = x_guess[:, 0, :].copy()
     controller.setGuess(x_guess, u_guess)
     controller.reset_controller()
@@ -77,10 +82,15 @@ def main(argv=None):
         c.ocp_solver.set_plant_inertial(m.plant_inertial)
         c.ocp_solver.set_torque_noise(m.torque_noise)
 
+    print(f'robot: {"synthetic Z1-like chain" if params.synthetic_robot else params.robot_urdf}; viability network: '
+          f'{"random-init stand-in (synthetic)" if getattr(params, "synthetic_net", False) else params.net_path if use_net else "none"}')
     sim = Sim(controller.ocp_solver, safe_ocp.ocp_solver, params.n_steps)
     sim.reset(x_init)
     t0 = time.perf_counter()
-    sim.run()
+    stats = []                                                                                  # mpc.py:239: controller.getTime() of every step
+    for _ in range(params.n_steps):
+        sim.step()
+        stats.append(sim.step_times())
     outcome = sim.outcome()
     dt = time.perf_counter() - t0
     x_log, u_log = sim.log()
@@ -100,6 +110,14 @@ def main(argv=None):
     solves = cnt['rti_solves'] + cnt['backup_solves']
     print(f'{solves} RTI solves in {dt:.2f} s = {solves / dt:.0f} RTI iterations/s '
           f'({cnt["ipm_iterations"] / max(1, solves):.1f} IPM iterations per solve)')
+
+    # mpc.py:300-303: 99 % quantile of the computation time per field -- here of one BATCHED controller step (all problems of the
+    # batch at once, CUDA events), and the same divided by the number of problems that solved in that step
+    times = np.array([t for t, n in stats])
+    per_solve = np.array([t / max(1, n) for t, n in stats])
+    print('99% quantile of the computation time (batched step | per solve):')
+    for field, t, tp in zip(controller.time_fields, np.quantile(times, 0.99, axis=0), np.quantile(per_solve, 0.99, axis=0)):
+        print(f'{field:<20} -> {t:.6f} | {tp:.3e}')
 
     xv = sim.x_viable()
     out = {'x': x_log, 'u': u_log, 'r': np.full((batch, params.n_steps, 1), np.nan), 'conv_idx': conv_idx,

@@ -184,9 +184,15 @@ def test_guess_script_writes_the_reference_files_and_mpc_reads_them(tmp_path, mo
     # guess_acados.py:235-244: the naive and zero-velocity files and one file per network controller
     assert 'z1_naive_12hor_10sm_use_netNone__q_collision_margins_0.0_0.0_guess.pkl' in files
     assert 'z1_zerovel_12hor_10sm_use_netNone__q_collision_margins_0.0_0.0_guess.pkl' in files
-    assert 'z1_st_12hor_10sm_use_netTrue__q_collision_margins_0.0_0.0_guess.pkl' in files and len(files) == 9
+    # one file per name of get_ocp_acados' dict that guess_acados.py:242 lists: st, htwa, receding, real_receding, constraint_everywhere
+    assert 'z1_st_12hor_10sm_use_netTrue__q_collision_margins_0.0_0.0_guess.pkl' in files and len(files) == 7
+    assert not any('_parallel_' in f or '_stwa_' in f for f in files)
     d = pickle.load(open(tmp_path / 'z1_st_12hor_10sm_use_netTrue__q_collision_margins_0.0_0.0_guess.pkl', 'rb'))
     assert set(d) == {'xg', 'ug'} and d['xg'].shape == (6, 13, 10) and d['ug'].shape == (6, 12, 5)
+    # every network guess is generated with HTWAController (utils.py:46-62): its terminal node is inside the viable set, which is what
+    # STWA / HTWA / receding latch as x_viable in setGuess (controller.py:390-393)
+    c, model, params = _controller('htwa', 6, 12)
+    assert c.checkSafeConstraints(d['xg'][:, -1]).all()
     # the closed-loop script starts from that file (mpc.py:79-84)
     load('mpc').main(['-c', 'st', '--horizon', '12', '--back_hor', '12', '--batch', '6'])
     out = [f for f in os.listdir(tmp_path) if f.endswith('_mpc.pkl')]

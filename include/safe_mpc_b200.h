@@ -131,7 +131,9 @@ typedef struct smpc_problem {
   int32_t nn_precision;          /* SMPC_NN_STRICT: fp32 weights, fp64 accumulation (FP64 pipe);
                                     SMPC_NN_TF32X3: fp32-class evaluation on the tensor cores (the precision of the
                                     reference's libtorch call, safe_set.py:76-94), see csrc/mlp_tc.cu              */
-  int32_t reserved_i[2];
+  int32_t qp_keep_slots;         /* 1: never compact the solver's slots during a solve, so that smpc_get_lin / smpc_get_qp stay
+                                    available for every batch size (tests, the merit line search of the guess generator); 0: default */
+  int32_t reserved_i[1];
   /* ---- scalars ---- */
   double dt;                     /* config.yaml:7                                                 */
   double q_weight, r_weight;     /* config.yaml:35,39                                             */
@@ -142,7 +144,11 @@ typedef struct smpc_problem {
   double tol_x, tol_tau, tol_obs, tol_safe, tol_conv; /* config.yaml:42-49                       */
   double qp_mu0, qp_tol_stat, qp_tol_eq, qp_tol_ineq, qp_tol_comp, qp_alpha_min, qp_reg_prim;
   double gravity[3];             /* world-frame gravity acceleration, (0,0,-9.80665)              */
-  double reserved_d[8];
+  double qp_maxiter_accept;      /* acados' SQP_RTI takes the step of a QP that ran into qp_iter_max (controller.py:166 sees status 0).
+                                    Whether an INFEASIBLE QP ends at qp_iter_max or at the minimum step length is decided by rounding
+                                    (its multipliers diverge), so a max-iter exit only counts as solved when every
+                                    residual is within this factor of its tolerance (default 1e3); <= 0: every max-iter exit is accepted */
+  double reserved_d[7];
   /* ---- serial chain (lumped over locked/fixed joints, see host/robot_model.py) ---- */
   double joint_R[SMPC_NQ][9];    /* row-major rotation parent-body <- joint frame at q=0          */
   double joint_p[SMPC_NQ][3];    /* joint-frame origin in the parent body frame                   */
@@ -258,7 +264,7 @@ int smpc_get_times(smpc_handle_t* h, double* out7);
  * synchronise at its end); smpc_get_profile returns, for the last solve, the summed duration [ms] and the launch count per
  * kernel kind (index = SMPC_PROF_*), the span of the whole solve [ms] and the IPM iterations of the slowest problem. */
 enum { SMPC_PROF_INIT = 0, SMPC_PROF_PREP = 1, SMPC_PROF_CTL = 2, SMPC_PROF_RIC1 = 3, SMPC_PROF_STEP0 = 4, SMPC_PROF_RIC2 = 5,
-       SMPC_PROF_STEP1 = 6, SMPC_PROF_RED = 7, SMPC_PROF_RIC2C = 8, SMPC_PROF_STEP2 = 9, SMPC_PROF_FINAL = 10, SMPC_PROF_N = 11 };
+       SMPC_PROF_STEP1 = 6, SMPC_PROF_RED = 7, SMPC_PROF_COMPACT = 8, SMPC_PROF_STEP2 = 9, SMPC_PROF_FINAL = 10, SMPC_PROF_N = 11 };
 int smpc_set_profiling(smpc_handle_t* h, int32_t enable);
 int smpc_get_profile(smpc_handle_t* h, double* ms /*[SMPC_PROF_N]*/, int32_t* count /*[SMPC_PROF_N]*/, double* span_ms, int32_t* iterations);
 /* number of kernels this handle has launched so far (bench.py "gpu_launches") */

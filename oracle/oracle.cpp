@@ -310,6 +310,12 @@ int rti_solve_one(orc_handle& h, int b, const double* x0, Workspace& W) {
     return status;
   }
   int qs = qp.solve(o);
+  // acados status of a QP exit: solved, or max-iter within qp_maxiter_accept x the tolerances (include/safe_mpc_b200.h)
+  auto accepted = [&](int q, const QpSol& sl) {
+    const double F = P.qp_maxiter_accept;
+    const bool sane = !(F > 0.0) || (sl.res[0] <= F * P.qp_tol_stat && sl.res[1] <= F * P.qp_tol_eq && sl.res[2] <= F * P.qp_tol_ineq && sl.res[3] <= F * P.qp_tol_comp);
+    return q == 0 || (q == 1 && sane);
+  };
   if (h.probe_eps > 0.0) {
     // sensitivity probe: the same QP with its gradients and dynamics offsets perturbed by a relative probe_eps; a solve whose status
     // changes under such a perturbation is decided by rounding, not by the algorithm (tests/test_gpu_closed_loop_full.py)
@@ -324,7 +330,7 @@ int rti_solve_one(orc_handle& h, int b, const double* x0, Workspace& W) {
         for (int i = 0; i < NX; ++i) S.b[i] *= 1.0 + h.probe_eps * rnd();
       }
       const int qs2 = qp.solve(o);
-      flip = ((qs2 == 0 || qs2 == 1) != (qs == 0 || qs == 1));
+      flip = accepted(qs2, qp.sol()) != accepted(qs, keep);
       for (int k = 0; k <= N; ++k) {
         double lo[NX], hi[NX];
         stage_box(h, b, k, x0, lo, hi);
@@ -368,7 +374,7 @@ int rti_solve_one(orc_handle& h, int b, const double* x0, Workspace& W) {
   double* xt = &h.xt[(size_t)b * (N + 1) * NX];
   double* ut = &h.ut[(size_t)b * N * NU];
   int status;
-  if (qs == 0 || qs == 1) {   // success or max-iter: acados SQP_RTI takes the full step
+  if (accepted(qs, sol)) {   // success or (sane) max-iter: acados SQP_RTI takes the full step
     status = 0;
     bool nan = false;
     for (int k = 0; k <= N; ++k) {

@@ -41,7 +41,7 @@ class Problem(C.Structure):
         ('controller', C.c_int32), ('nn_rows', C.c_int32), ('nn_terminal_soft', C.c_int32),
         ('stage0_collision_rows', C.c_int32), ('cost_type', C.c_int32), ('abort_flag', C.c_int32),
         ('qp_iter_max', C.c_int32), ('lm_scale_dt', C.c_int32), ('qp_cond_pred_corr', C.c_int32),
-        ('nn_precision', C.c_int32), ('reserved_i', C.c_int32 * 2),
+        ('nn_precision', C.c_int32), ('qp_keep_slots', C.c_int32), ('reserved_i', C.c_int32 * 1),
         ('dt', C.c_double), ('q_weight', C.c_double), ('r_weight', C.c_double), ('lm', C.c_double),
         ('alpha', C.c_double), ('eps', C.c_double), ('slack_penalty_e', C.c_double),
         ('tol_x', C.c_double), ('tol_tau', C.c_double), ('tol_obs', C.c_double), ('tol_safe', C.c_double),
@@ -49,7 +49,7 @@ class Problem(C.Structure):
         ('qp_mu0', C.c_double), ('qp_tol_stat', C.c_double), ('qp_tol_eq', C.c_double),
         ('qp_tol_ineq', C.c_double), ('qp_tol_comp', C.c_double), ('qp_alpha_min', C.c_double),
         ('qp_reg_prim', C.c_double),
-        ('gravity', C.c_double * 3), ('reserved_d', C.c_double * 8),
+        ('gravity', C.c_double * 3), ('qp_maxiter_accept', C.c_double), ('reserved_d', C.c_double * 7),
         ('joint_R', (C.c_double * 9) * NQ), ('joint_p', (C.c_double * 3) * NQ),
         ('joint_axis', (C.c_double * 3) * NQ), ('inertial', (C.c_double * 10) * NQ),
         ('x_min', C.c_double * NX), ('x_max', C.c_double * NX),

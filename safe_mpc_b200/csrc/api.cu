@@ -304,7 +304,7 @@ int smpc_create(const smpc_problem_t* prob, int32_t batch, int32_t device, smpc_
   }
   {
     cudaError_t qe = cudaSuccess;
-    h->qp = qp_create(B, N, prob->qp_iter_max, h->stream, &qe);
+    h->qp = qp_create(B, N, prob->qp_iter_max, prob->qp_keep_slots != 0, h->stream, &qe);
     if (!h->qp) { fail(nullptr, SMPC_ERR_CUDA, "qp_create", qe); smpc_destroy(h); return SMPC_ERR_CUDA; }
   }
   CKC(dalloc(h, &h->qp_res, (size_t)B * 5));
@@ -471,7 +471,16 @@ int smpc_nn_constraint(smpc_handle_t* h, int32_t n, const double* x, double* cva
   return copy_out(h, grad, dg, sizeof(double) * n * NX, mem);
 }
 
+static int slots_intact(smpc_handle_t* h, const char* what) {
+  if (qp_compactions(h->qp) == 0) return 0;
+  char buf[256];
+  snprintf(buf, sizeof buf, "%s: the last solve compacted its slots (the stage records / iterates of the finished problems were reused); "
+                            "create the handle with smpc_problem_t::qp_keep_slots = 1 (or SMPC_QP_COMPACT=0) to keep them", what);
+  return fail(h, SMPC_ERR_UNSUPPORTED, buf);
+}
+
 int smpc_get_lin(smpc_handle_t* h, double* lin, int32_t mem) {
+  if (int rc0 = slots_intact(h, "smpc_get_lin")) return rc0;
   const size_t bytes = sizeof(double) * h->B * (h->N + 1) * REC;
   if (mem == SMPC_DEVICE) { launch_rec_untile(h->ctx(), h->qp, lin); return check_launch(h, "get_lin"); }
   int rc = stage_reserve(h, bytes); if (rc) return rc;
@@ -484,6 +493,7 @@ int smpc_get_qp(smpc_handle_t* h, double* dz, double* pi, double* lam, double* t
   const size_t nst = (size_t)h->B * (h->N + 1);
   const size_t b1 = sizeof(double) * nst * 15, b2 = sizeof(double) * h->B * h->N * 10, b3 = sizeof(double) * nst * SMPC_QP_NC;
   if (!h->solved) return fail(h, SMPC_ERR_ARG, "smpc_get_qp: no smpc_rti_solve / smpc_controller_step yet");
+  if (int rc0 = slots_intact(h, "smpc_get_qp")) return rc0;
   int rc = stage_reserve(h, b1 + b2 + 2 * b3); if (rc) return rc;
   char* s = (char*)h->stage;
   // the final iterate of every problem stays in the solver's ping-pong buffers until the next solve

@@ -108,11 +108,12 @@ void launch_sim_outcome(const LaunchCtx& c, const SimDev& s, const smpc_problem_
 inline namespace QS_FLAVOUR {
 struct QpSolver;
 size_t qp_bytes(int B, int N);
-QpSolver* qp_create(int B, int N, int iter_max, cudaStream_t stream, cudaError_t* err);
+QpSolver* qp_create(int B, int N, int iter_max, bool keep_slots, cudaStream_t stream, cudaError_t* err);
 void qp_destroy(QpSolver* s);
 double* qp_rec(QpSolver* s);                  // tile-interleaved stage records [T][N+1][REC][32] the linearisation writes
 int qp_groups(const QpSolver* s);              // tile groups solved concurrently
 int qp_last_iterations(const QpSolver* s);
+int qp_compactions(const QpSolver* s);          // compactions of the slots during the last solve (> 0: per-slot dumps are gone)
 void qp_set_profiling(QpSolver* s, bool on);
 void qp_get_profile(const QpSolver* s, double* ms, int32_t* n, double* span_ms);    // IPM iterations of the slowest problem of the last solve
 // one batched solve; reads the records of qp_rec(); problems with act == 0 are skipped and keep their outputs

@@ -427,7 +427,68 @@ __global__ void __launch_bounds__(32 * SP_WARPS) qs_final_kernel(QsBufs q, int T
   const int w = blockIdx.x * SP_WARPS + (threadIdx.x >> 5);
   if (w >= T * (q.N + 1)) return;
   const int tile = w / (q.N + 1), lane = threadIdx.x & 31;
-  if (qs_final(q, tile, lane, w % (q.N + 1), act, B, status, xt, ut)) atomicExch(&status[tile * TL + lane], 1);
+  const int b = qs_final(q, tile, lane, w % (q.N + 1), act, B, status, xt, ut);
+  if (b >= 0) atomicExch(&status[b], 1);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Compaction of the slots of one tile group (qp_split.cuh: qs_compact_*).  plan: one CTA, block-wide scan over the S = 32 T
+// slots -> the list of moves (active slots >= n into inactive slots < n, both in slot order: the plan of qs_compact_plan);
+// move: one CTA per (move, quarter of the stages).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int CP_THREADS = 1024;
+__global__ void __launch_bounds__(CP_THREADS) qs_compact_plan_kernel(QsBufs q, int T, int32_t* mv, int mv_half, int* n_moves) {
+  __shared__ int part[CP_THREADS];
+  __shared__ int s_n, s_apn;
+  const int S = T * TL, tid = threadIdx.x;
+  const int C = (S + CP_THREADS - 1) / CP_THREADS;
+  const int s0 = tid * C, s1 = min(S, s0 + C);
+  int cnt = 0;
+  for (int s = s0; s < s1; ++s) {
+    int32_t* pi = q.pi + qs_pb(s / TL, NPI, s % TL);
+    if (QF(pi, J_ACT)) ++cnt; else QF(pi, J_FIN) = 1;          // (the results of the finished problems were written by the launch before this one)
+  }
+  part[tid] = cnt;
+  __syncthreads();
+  for (int off = 1; off < CP_THREADS; off <<= 1) {             // inclusive scan (Hillis-Steele; 1024 entries, once per compaction)
+    const int v = tid >= off ? part[tid - off] : 0;
+    __syncthreads();
+    part[tid] += v;
+    __syncthreads();
+  }
+  const int before = part[tid] - cnt;                           // active slots below s0
+  if (tid == CP_THREADS - 1) s_n = part[tid];
+  __syncthreads();
+  const int n = s_n;
+  if (n >= s0 && n < s1) {                                      // the owner of slot n: actives below slot n
+    int ap = before;
+    for (int s = s0; s < n; ++s) ap += QF(q.pi + qs_pb(s / TL, NPI, s % TL), J_ACT) ? 1 : 0;
+    s_apn = ap;
+  }
+  if (n >= S && tid == 0) s_apn = n;                            // every slot active: nothing moves
+  __syncthreads();
+  const int apn = s_apn;
+  int ap = before;
+  for (int s = s0; s < s1; ++s) {
+    const bool a = QF(q.pi + qs_pb(s / TL, NPI, s % TL), J_ACT) != 0;
+    if (a && s >= n) mv[ap - apn] = s;                          // mover number = actives in [n, s)
+    if (!a && s < n) mv[mv_half + (s - ap)] = s;                // hole number = inactive slots in [0, s)
+    ap += a ? 1 : 0;
+  }
+  if (tid == 0) *n_moves = n - apn;
+}
+
+constexpr int CM_THREADS = 128, CM_SPLIT = 4;
+__global__ void __launch_bounds__(CM_THREADS) qs_compact_move_kernel(QsBufs q, const int32_t* __restrict__ mv, int mv_half, const int* __restrict__ n_moves, int kk) {
+  const int i = blockIdx.x;
+  if (i >= *n_moves) return;
+  const int src = mv[i], dst = mv[mv_half + i];
+  for (int k = blockIdx.y; k <= q.N; k += CM_SPLIT)
+    for (int f = threadIdx.x; f < CMP_FIELDS; f += CM_THREADS) qs_compact_move_field(q, src, dst, k, kk, f);
+  if (blockIdx.y == 0) {
+    __syncthreads();
+    if (threadIdx.x == 0) qs_compact_move_scalars(q, src, dst);
+  }
 }
 
 
@@ -1178,6 +1239,10 @@ __global__ void dump_qp_kernel(const smpc_problem_t* __restrict__ dP, QsBufs q, 
 #define QS_GROUPS 3              // tile groups solved concurrently on their own streams (see QsLoop)
 #endif
 constexpr int MAX_GROUPS = 8;
+constexpr int RING = 8;          // counter read-backs in flight per group (run-ahead depth + 2 at most)
+
+// optional timeline (profiling / SMPC_QP_TRACE=1): one event pair per kernel
+struct TraceRec { int g; const char* name; int kk; cudaEvent_t a, b; };
 
 struct QpGroup {
   QsBufs q{};
@@ -1185,10 +1250,16 @@ struct QpGroup {
   cudaStream_t stream = nullptr;   // stage-parallel kernels (bandwidth-bound)
   cudaStream_t hi = nullptr;       // Riccati sweeps (latency-bound, few warps): higher priority, so that their CTAs take the
                                    // slots that retiring stage-parallel CTAs of the other groups free
-  cudaEvent_t ev = nullptr;     // counters of the current iteration have landed in h_counters
+  cudaEvent_t ev[RING] = {nullptr};   // ev[kk % RING]: the counters of iteration kk have landed in h_counters[2 (kk % RING)]
+  cudaEvent_t ev_done = nullptr;      // last kernel of the solve
   cudaEvent_t evx = nullptr;    // hand-over between the two streams
   int* counters = nullptr;      // [2 (iter_max + 2)]: active / redo per IPM iteration
-  int* h_counters = nullptr;    // pinned, 2 ints
+  int* h_counters = nullptr;    // pinned, 2 RING ints
+  int32_t* mv = nullptr;        // compaction: [2][mv_half] source / destination slots
+  int mv_half = 0;
+  int* n_moves = nullptr;       // device
+  int in_use = 0;               // slots that may still hold an iterating problem (32 T at the start of a solve, less after a compaction)
+  int tiles() const { return (in_use + TL - 1) / TL; }
 };
 
 struct QpSolver {
@@ -1199,6 +1270,8 @@ struct QpSolver {
   int32_t* pi = nullptr;
   int* counters = nullptr;
   int* h_counters = nullptr;
+  int32_t* mv = nullptr;        // compaction plans of the groups
+  int* n_moves = nullptr;
   cudaEvent_t ev_in = nullptr;  // inputs (records, x0) are ready on the caller's stream
   int last_iters = 0;
   int tail_max = 384;           // a tile group with at most this many problems still iterating is served by the warp-per-problem sweeps (0: never)
@@ -1208,6 +1281,13 @@ struct QpSolver {
   double prof_ms[SMPC_PROF_N] = {0};
   int32_t prof_n[SMPC_PROF_N] = {0};
   double prof_span_ms = 0.0;
+  int depth = 2;                // IPM iterations the host queues ahead of the counters it has seen (SMPC_QP_DEPTH; 0: one round trip per iteration)
+  bool compact = true;          // pack the problems still iterating into the leading slots between iterations (SMPC_QP_COMPACT=0: never)
+  int compact_min_tiles = 32;   // ... for groups of at least this many tiles
+  bool compacted = false;       // the last solve reused slots: per-slot dumps (smpc_get_lin / smpc_get_qp) are not available for it
+  int n_compactions = 0;        // of the last solve
+  bool trace_print = false;     // SMPC_QP_TRACE=1
+  std::vector<struct TraceRec> trace;   // optional timeline: one event pair per kernel (profiling / SMPC_QP_TRACE)
 };
 
 size_t qp_bytes(int B, int N) {
@@ -1215,7 +1295,7 @@ size_t qp_bytes(int B, int N) {
   return sizeof(double) * (S * (REC + 3 * NIT + NS2 + NSB + NPROD + NRES + NSTP) + T * NPD * TL);
 }
 
-QpSolver* qp_create(int B, int N, int iter_max, cudaStream_t stream, cudaError_t* err) {
+QpSolver* qp_create(int B, int N, int iter_max, bool keep_slots, cudaStream_t stream, cudaError_t* err) {
   QpSolver* s = new QpSolver;
   s->B = B; s->N = N; s->T = (B + TL - 1) / TL; s->iter_max = iter_max;
   const size_t T = s->T, S = T * (N + 1) * TL;
@@ -1232,8 +1312,10 @@ QpSolver* qp_create(int B, int N, int iter_max, cudaStream_t stream, cudaError_t
   if (e == cudaSuccess) e = cudaMalloc((void**)&s->pi, sizeof(int32_t) * T * NPI * TL);
   if (e == cudaSuccess) e = cudaMemsetAsync(s->pi, 0, sizeof(int32_t) * T * NPI * TL, stream);
   if (e == cudaSuccess) e = cudaMalloc((void**)&s->counters, sizeof(int) * ncnt * G);
-  if (e == cudaSuccess) e = cudaMallocHost((void**)&s->h_counters, sizeof(int) * 2 * G);
+  if (e == cudaSuccess) e = cudaMallocHost((void**)&s->h_counters, sizeof(int) * 2 * RING * G);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_in, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&s->mv, sizeof(int32_t) * ((size_t)s->T * TL + 2 * MAX_GROUPS));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&s->n_moves, sizeof(int) * MAX_GROUPS);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(qs_prep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PREP_SMEM);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(qs_prep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PREP_SMEM);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(qs_prep_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PC_SMEM);
@@ -1244,13 +1326,20 @@ QpSolver* qp_create(int B, int N, int iter_max, cudaStream_t stream, cudaError_t
   if (e == cudaSuccess) e = cudaFuncSetAttribute(qs_ric1t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RT_SMEM);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(qs_ric2t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RT_SMEM);
   if (const char* te = getenv("SMPC_QP_TAIL")) s->tail_max = atoi(te);
+  if (const char* de = getenv("SMPC_QP_DEPTH")) s->depth = atoi(de);
+  if (s->depth < 0) s->depth = 0;
+  if (s->depth > RING - 2) s->depth = RING - 2;
+  if (const char* ce = getenv("SMPC_QP_COMPACT")) s->compact = atoi(ce) != 0;
+  if (keep_slots) s->compact = false;
+  s->trace_print = getenv("SMPC_QP_TRACE") != nullptr;
   if (e == cudaSuccess) e = cudaFuncSetAttribute(qs_ric2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RIC2_SMEM);
   for (int g = 0; g < G && e == cudaSuccess; ++g) {
     int plo = 0, phi = 0;
     cudaDeviceGetStreamPriorityRange(&plo, &phi);
     e = cudaStreamCreateWithPriority(&s->grp[g].stream, cudaStreamNonBlocking, plo);
     if (e == cudaSuccess && G > 1 && !getenv("SMPC_QP_NOPRIO")) e = cudaStreamCreateWithPriority(&s->grp[g].hi, cudaStreamNonBlocking, phi);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->grp[g].ev, cudaEventDisableTiming);
+    for (int i = 0; i < RING && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&s->grp[g].ev[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->grp[g].ev_done, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->grp[g].evx, cudaEventDisableTiming);
   }
   if (e != cudaSuccess) { *err = e; qp_destroy(s); return nullptr; }
@@ -1269,6 +1358,7 @@ QpSolver* qp_create(int B, int N, int iter_max, cudaStream_t stream, cudaError_t
   s->q.pi = s->pi;
   s->q.N = N;
   s->q.tile0 = 0;
+  size_t mv_off = 0;
   for (int g = 0; g < G; ++g) {
     QpGroup& gr = s->grp[g];
     const int t0 = (int)((long long)s->T * g / G), t1 = (int)((long long)s->T * (g + 1) / G);
@@ -1279,7 +1369,11 @@ QpSolver* qp_create(int B, int N, int iter_max, cudaStream_t stream, cudaError_t
     gr.q.sb = s->q.sb + so * NSB; gr.q.prod = s->q.prod + so * NPROD; gr.q.res = s->q.res + so * NRES; gr.q.stp = s->q.stp + so * NSTP;
     gr.q.pd = s->q.pd + (size_t)t0 * NPD * TL; gr.q.pi = s->q.pi + (size_t)t0 * NPI * TL; gr.q.tile0 = t0;
     gr.counters = s->counters + ncnt * g;
-    gr.h_counters = s->h_counters + 2 * g;
+    gr.h_counters = s->h_counters + 2 * RING * g;
+    gr.mv_half = gr.T * TL / 2 + 1;
+    gr.mv = s->mv + mv_off; mv_off += 2 * (size_t)gr.mv_half;
+    gr.n_moves = s->n_moves + g;
+    gr.in_use = gr.T * TL;
   }
   *err = cudaSuccess;
   return s;
@@ -1290,7 +1384,8 @@ void qp_destroy(QpSolver* s) {
   for (int g = 0; g < MAX_GROUPS; ++g) {
     if (s->grp[g].stream) { cudaStreamSynchronize(s->grp[g].stream); cudaStreamDestroy(s->grp[g].stream); }
     if (s->grp[g].hi) { cudaStreamSynchronize(s->grp[g].hi); cudaStreamDestroy(s->grp[g].hi); }
-    if (s->grp[g].ev) cudaEventDestroy(s->grp[g].ev);
+    for (int i = 0; i < RING; ++i) if (s->grp[g].ev[i]) cudaEventDestroy(s->grp[g].ev[i]);
+    if (s->grp[g].ev_done) cudaEventDestroy(s->grp[g].ev_done);
     if (s->grp[g].evx) cudaEventDestroy(s->grp[g].evx);
   }
   if (s->ev_in) cudaEventDestroy(s->ev_in);
@@ -1298,12 +1393,15 @@ void qp_destroy(QpSolver* s) {
   if (s->pi) cudaFree(s->pi);
   if (s->counters) cudaFree(s->counters);
   if (s->h_counters) cudaFreeHost(s->h_counters);
+  if (s->mv) cudaFree(s->mv);
+  if (s->n_moves) cudaFree(s->n_moves);
   delete s;
 }
 
 double* qp_rec(QpSolver* s) { return const_cast<double*>(s->q.rec); }
 int qp_last_iterations(const QpSolver* s) { return s->last_iters; }
 int qp_groups(const QpSolver* s) { return s->G; }
+int qp_compactions(const QpSolver* s) { return s->n_compactions; }
 void qp_set_profiling(QpSolver* s, bool on) { s->profile = on; }
 void qp_get_profile(const QpSolver* s, double* ms, int32_t* n, double* span_ms) {
   for (int i = 0; i < SMPC_PROF_N; ++i) { ms[i] = s->prof_ms[i]; n[i] = s->prof_n[i]; }
@@ -1311,15 +1409,9 @@ void qp_get_profile(const QpSolver* s, double* ms, int32_t* n, double* span_ms) 
 }
 
 namespace {
-// optional timeline (SMPC_QP_TRACE=1): one event pair per kernel, printed to stderr after the solve
-struct TraceRec { int g; const char* name; int kk; cudaEvent_t a, b; };
-static std::vector<TraceRec> g_trace;
-static bool g_profile = false;
-static bool trace_print() { static int v = -1; if (v < 0) v = getenv("SMPC_QP_TRACE") ? 1 : 0; return v == 1; }
-static bool trace_on() { return g_profile || trace_print(); }
 static int prof_slot(const char* n) {
   static const char* names[SMPC_PROF_N] = {"qs_init_kernel", "qs_prep_kernel", "qs_ctl_kernel", "qs_ric1_kernel", "qs_step_kernel<0>", "qs_ric2_kernel",
-                                           "qs_step_kernel<1>", "qs_red_kernel", nullptr /* (the separate centering sweep is gone) */, "qs_step_kernel<2>", "qs_final_kernel"};
+                                           "qs_step_kernel<1>", "qs_red_kernel", "qs_compact" /* final + plan + move of a compaction */, "qs_step_kernel<2>", "qs_final_kernel"};
   for (int i = 0; i < SMPC_PROF_N; ++i) if (names[i] && !strcmp(names[i], n)) return i;
   return 0;
 }
@@ -1333,9 +1425,10 @@ struct DeviceBackend {
   const double* x0; const int32_t* r; const uint8_t* act;
   double *xt, *ut; int32_t *status, *qp_iter, *qp_status; double* qp_res;
   int kk_last = 0;
-  int n_active_last = 1 << 30;  // problems still iterating after the last control kernel the host has seen
+  int n_active_last = 1 << 30;  // problems still iterating after the newest control kernel the host has seen
   cudaError_t err = cudaSuccess;
   bool on_hi = false;
+  bool trace_on() const { return s->profile || s->trace_print; }
   // stream for the next kernel; a change of stream is ordered after everything queued on the other one
   cudaStream_t st(bool hi) {
     if (!g->hi) return g->stream;
@@ -1346,7 +1439,10 @@ struct DeviceBackend {
     }
     return hi ? g->hi : g->stream;
   }
-  int sp_grid() const { return (g->T * (s->N + 1) + SP_WARPS - 1) / SP_WARPS; }
+  // grids cover the tiles that may still hold an iterating problem (all of them until the first compaction)
+  int tl() const { return g->tiles(); }
+  int sp_grid() const { return (tl() * (s->N + 1) + SP_WARPS - 1) / SP_WARPS; }
+  int sp_grid_all() const { return (g->T * (s->N + 1) + SP_WARPS - 1) / SP_WARPS; }
   void count(int n = 1) { *launches += n; }
   int gi() const { return (int)(g - s->grp); }
   void tr0(const char* name, cudaStream_t stm) {
@@ -1354,10 +1450,11 @@ struct DeviceBackend {
     TraceRec r{gi(), name, kk_last, nullptr, nullptr};
     cudaEventCreate(&r.a); cudaEventCreate(&r.b);
     cudaEventRecord(r.a, stm);
-    g_trace.push_back(r);
+    s->trace.push_back(r);
   }
-  void tr1(cudaStream_t stm) { if (trace_on()) cudaEventRecord(g_trace.back().b, stm); }
+  void tr1(cudaStream_t stm) { if (trace_on()) cudaEventRecord(s->trace.back().b, stm); }
   void init() {
+    g->in_use = g->T * TL;
     cudaMemsetAsync(g->counters, 0, sizeof(int) * 2 * (s->iter_max + 2), st(false));
     { cudaStream_t stm_ = st(false); tr0("qs_init_kernel", stm_); qs_init_kernel<<<g->T, 32, 0, stm_>>>(g->q, s->B, x0, r, act); tr1(stm_); }
     count();
@@ -1365,30 +1462,30 @@ struct DeviceBackend {
   void prep(int kk) {
     {
       cudaStream_t stm_ = st(false);
-      const int grid = (g->T * (s->N + 1) + PREP_WARPS - 1) / PREP_WARPS;
+      const int grid = (tl() * (s->N + 1) + PREP_WARPS - 1) / PREP_WARPS;
       tr0("qs_prep_kernel", stm_);
-      if (kk == 0) qs_prep_kernel<true><<<grid, 32 * PREP_WARPS, PREP_SMEM, stm_>>>(dP, g->q, g->T, kk);
+      if (kk == 0) qs_prep_kernel<true><<<grid, 32 * PREP_WARPS, PREP_SMEM, stm_>>>(dP, g->q, tl(), kk);
       // the cooperative form stages whole (tile, stage) blocks, the thread-per-stage form only touches the lanes that still iterate:
-      // measured break-even at about half of the problems active (full launch 0.57 ms against 1.02 ms).  In the deep tail (a handful of
-      // tiles) throughput does not matter and the cooperative form has the shorter critical path (33 against 43 us)
-      else if (s->coop_prep && (2 * n_active_last >= 32 * g->T || n_active_last <= s->tail_max)) qs_prep_coop_kernel<<<g->T * (s->N + 1), 32 * PC_WARPS, PC_SMEM, stm_>>>(dP, g->q, g->T, kk);
-      else qs_prep_kernel<false><<<grid, 32 * PREP_WARPS, PREP_SMEM, stm_>>>(dP, g->q, g->T, kk);
+      // measured break-even at about half of the slots in use active (full launch 0.57 ms against 1.02 ms).  In the deep tail (a handful
+      // of tiles) throughput does not matter and the cooperative form has the shorter critical path (33 against 43 us)
+      else if (s->coop_prep && (2 * n_active_last >= g->in_use || n_active_last <= s->tail_max)) qs_prep_coop_kernel<<<tl() * (s->N + 1), 32 * PC_WARPS, PC_SMEM, stm_>>>(dP, g->q, tl(), kk);
+      else qs_prep_kernel<false><<<grid, 32 * PREP_WARPS, PREP_SMEM, stm_>>>(dP, g->q, tl(), kk);
       tr1(stm_);
     }
     count();
   }
   void ctl(int kk) {
     kk_last = kk;
-    { cudaStream_t stm_ = st(false); tr0("qs_ctl_kernel", stm_); qs_ctl_kernel<<<g->T, 32, 0, stm_>>>(dP, g->q, kk, status, qp_iter, qp_status, qp_res, g->counters); tr1(stm_); }
+    { cudaStream_t stm_ = st(false); tr0("qs_ctl_kernel", stm_); qs_ctl_kernel<<<tl(), 32, 0, stm_>>>(dP, g->q, kk, status, qp_iter, qp_status, qp_res, g->counters); tr1(stm_); }
     count();
   }
   void ric1() {
     {
       cudaStream_t stm_ = st(true);
       tr0("qs_ric1_kernel", stm_);
-      if (n_active_last <= s->tail_max) qs_ric1t_kernel<<<g->T * (32 / RT_WARPS), 32 * RT_WARPS, RT_SMEM, stm_>>>(dP, g->q);
-      else if (s->split_ric1) qs_ric1x_kernel<<<g->T, 64, RIC1X_SMEM, stm_>>>(dP, g->q);
-      else qs_ric1_kernel<<<g->T, 32, RIC1_SMEM, stm_>>>(dP, g->q);
+      if (n_active_last <= s->tail_max) qs_ric1t_kernel<<<tl() * (32 / RT_WARPS), 32 * RT_WARPS, RT_SMEM, stm_>>>(dP, g->q);
+      else if (s->split_ric1) qs_ric1x_kernel<<<tl(), 64, RIC1X_SMEM, stm_>>>(dP, g->q);
+      else qs_ric1_kernel<<<tl(), 32, RIC1_SMEM, stm_>>>(dP, g->q);
       tr1(stm_);
     }
     count();
@@ -1397,38 +1494,70 @@ struct DeviceBackend {
     {
       cudaStream_t stm_ = st(true);
       tr0("qs_ric2_kernel", stm_);
-      if (n_active_last <= s->tail_max) qs_ric2t_kernel<<<g->T * (32 / RT_WARPS), 32 * RT_WARPS, RT_SMEM, stm_>>>(dP, g->q);
-      else qs_ric2_kernel<<<g->T, 32, RIC2_SMEM, stm_>>>(dP, g->q);
+      if (n_active_last <= s->tail_max) qs_ric2t_kernel<<<tl() * (32 / RT_WARPS), 32 * RT_WARPS, RT_SMEM, stm_>>>(dP, g->q);
+      else qs_ric2_kernel<<<tl(), 32, RIC2_SMEM, stm_>>>(dP, g->q);
       tr1(stm_);
     }
     count();
   }
   void step(int kk, int mode) {
-    if (mode == 0) { cudaStream_t stm_ = st(false); tr0("qs_step_kernel<0>", stm_); qs_step_kernel<0><<<sp_grid(), 32 * SP_WARPS, 0, stm_>>>(dP, g->q, g->T, kk); tr1(stm_); }
-    else if (mode == 1) { cudaStream_t stm_ = st(false); tr0("qs_step_kernel<1>", stm_); qs_step_kernel<1><<<sp_grid(), 32 * SP_WARPS, 0, stm_>>>(dP, g->q, g->T, kk); tr1(stm_); }
-    else { cudaStream_t stm_ = st(false); tr0("qs_step_kernel<2>", stm_); qs_step_kernel<2><<<sp_grid(), 32 * SP_WARPS, 0, stm_>>>(dP, g->q, g->T, kk); tr1(stm_); }
+    if (mode == 0) { cudaStream_t stm_ = st(false); tr0("qs_step_kernel<0>", stm_); qs_step_kernel<0><<<sp_grid(), 32 * SP_WARPS, 0, stm_>>>(dP, g->q, tl(), kk); tr1(stm_); }
+    else if (mode == 1) { cudaStream_t stm_ = st(false); tr0("qs_step_kernel<1>", stm_); qs_step_kernel<1><<<sp_grid(), 32 * SP_WARPS, 0, stm_>>>(dP, g->q, tl(), kk); tr1(stm_); }
+    else { cudaStream_t stm_ = st(false); tr0("qs_step_kernel<2>", stm_); qs_step_kernel<2><<<sp_grid(), 32 * SP_WARPS, 0, stm_>>>(dP, g->q, tl(), kk); tr1(stm_); }
     count();
   }
-  void final() { { cudaStream_t stm_ = st(false); tr0("qs_final_kernel", stm_); qs_final_kernel<<<sp_grid(), 32 * SP_WARPS, 0, stm_>>>(g->q, g->T, s->B, act, status, xt, ut); tr1(stm_); } count(); }
-  void red(bool after) { { cudaStream_t stm_ = st(false); tr0("qs_red_kernel", stm_); qs_red_kernel<<<g->T, 32, 0, stm_>>>(dP, g->q, kk_last, after ? 1 : 0, g->counters); tr1(stm_); } count(); }
-  void request_counters() {
-    cudaError_t e = cudaMemcpyAsync(g->h_counters, g->counters + 2 * kk_last, 2 * sizeof(int), cudaMemcpyDeviceToHost, st(false));
-    if (e == cudaSuccess) e = cudaEventRecord(g->ev, st(false));
+  // results of the problems that have finished and not been written yet; all slots of the group (empty ones are skipped)
+  void final() { { cudaStream_t stm_ = st(false); tr0("qs_final_kernel", stm_); qs_final_kernel<<<sp_grid_all(), 32 * SP_WARPS, 0, stm_>>>(g->q, g->T, s->B, act, status, xt, ut); tr1(stm_); } count(); }
+  void red(bool after) { { cudaStream_t stm_ = st(false); tr0("qs_red_kernel", stm_); qs_red_kernel<<<tl(), 32, 0, stm_>>>(dP, g->q, kk_last, after ? 1 : 0, g->counters); tr1(stm_); } count(); }
+  // Compaction between iteration kk and kk + 1 (qp_split.cuh: qs_compact_*), decided on the newest active count the host has seen --
+  // an upper bound of the current one, the counts never grow: when it has fallen to 85 % of the slots in use (and by at least a
+  // tile), the problems still iterating are packed into the leading slots and every later launch covers only those tiles.
+  void compact(int kk) {
+    if (!s->compact || g->T < s->compact_min_tiles) return;
+    const int na = n_active_last;
+    if (na > g->in_use || g->in_use - na < TL || (double)na > 0.85 * g->in_use) return;
+    cudaStream_t stm_ = st(false);
+    tr0("qs_compact", stm_);
+    const int tl_before = tl();
+    qs_final_kernel<<<(tl_before * (s->N + 1) + SP_WARPS - 1) / SP_WARPS, 32 * SP_WARPS, 0, stm_>>>(g->q, tl_before, s->B, act, status, xt, ut);
+    qs_compact_plan_kernel<<<1, CP_THREADS, 0, stm_>>>(g->q, tl_before, g->mv, g->mv_half, g->n_moves);
+    const int grid_x = g->in_use / 2 + 1;          // movers = min(active beyond the boundary, holes below it) <= half of the slots in use
+    qs_compact_move_kernel<<<dim3(grid_x, CM_SPLIT), CM_THREADS, 0, stm_>>>(g->q, g->mv, g->mv_half, g->n_moves, kk);
+    tr1(stm_);
+    count(3);
+    g->in_use = na;
+    s->compacted = true;
+    s->n_compactions += 1;
+  }
+  void request_counters(int kk) {
+    const int slot = kk % RING;
+    cudaError_t e = cudaMemcpyAsync(g->h_counters + 2 * slot, g->counters + 2 * kk, 2 * sizeof(int), cudaMemcpyDeviceToHost, st(false));
+    if (e == cudaSuccess) e = cudaEventRecord(g->ev[slot], st(false));
     if (e != cudaSuccess) err = e;
   }
-  void wait_counters(int& na, int& nr) {
-    cudaError_t e = err == cudaSuccess ? cudaEventSynchronize(g->ev) : err;
-    if (e != cudaSuccess) { err = e; na = 0; nr = 0; return; }     // stop iterating; the caller reports the error
-    na = g->h_counters[0]; nr = g->h_counters[1];
+  // counters of iteration kk: true when they have arrived (must: block until they have)
+  bool wait_counters(int kk, bool must, int& na, int& nr) {
+    const int slot = kk % RING;
+    cudaError_t e = err;
+    if (e == cudaSuccess) {
+      if (must) e = cudaEventSynchronize(g->ev[slot]);
+      else {
+        e = cudaEventQuery(g->ev[slot]);
+        if (e == cudaErrorNotReady) return false;
+      }
+    }
+    if (e != cudaSuccess) { err = e; na = 0; nr = 0; return true; }     // stop iterating; the caller reports the error
+    na = g->h_counters[2 * slot]; nr = g->h_counters[2 * slot + 1];
     n_active_last = na;
-    if (trace_print()) fprintf(stderr, "QPCOUNT g=%d kk=%d active=%d redo=%d\n", gi(), kk_last, na, nr);
+    if (s->trace_print) fprintf(stderr, "QPCOUNT g=%d kk=%d active=%d redo=%d in_use=%d\n", gi(), kk, na, nr, g->in_use);
+    return true;
   }
 };
 }  // namespace
 
 cudaError_t launch_qp_solve(const LaunchCtx& c, const smpc_problem_t* dP, QpSolver* s, const double* x0, const int32_t* r, const uint8_t* act,
                             double* xt, double* ut, int32_t* status, int32_t* qp_iter, int32_t* qp_status, double* qp_res) {
-  g_profile = s->profile;
+  s->compacted = false; s->n_compactions = 0;
   // the group streams start after everything queued on the caller's stream (linearisation, input copies) ...
   cudaError_t e = cudaEventRecord(s->ev_in, c.stream);
   if (e != cudaSuccess) return e;
@@ -1438,31 +1567,31 @@ cudaError_t launch_qp_solve(const LaunchCtx& c, const smpc_problem_t* dP, QpSolv
     if (e != cudaSuccess) return e;
     bk[g] = DeviceBackend{c.launches, dP, s, &s->grp[g], x0, r, act, xt, ut, status, qp_iter, qp_status, qp_res};
   }
-  s->last_iters = qs_drive(bk, s->G);
-  if (trace_on()) {
+  s->last_iters = qs_drive(bk, s->G, s->depth);
+  if (s->profile || s->trace_print) {
     for (int g = 0; g < s->G; ++g) cudaStreamSynchronize(bk[g].st(false));
-    if (!g_trace.empty()) {
-      cudaEvent_t t0 = g_trace[0].a;
+    if (!s->trace.empty()) {
+      cudaEvent_t t0 = s->trace[0].a;
       for (int i = 0; i < SMPC_PROF_N; ++i) { s->prof_ms[i] = 0.0; s->prof_n[i] = 0; }
       float t_end = 0;
-      for (auto& r : g_trace) {
+      for (auto& r : s->trace) {
         float a = 0, b = 0;
         cudaEventElapsedTime(&a, t0, r.a); cudaEventElapsedTime(&b, t0, r.b);
-        if (trace_print()) fprintf(stderr, "QPTRACE g=%d kk=%d %-12s start=%9.3f end=%9.3f dur=%8.3f\n", r.g, r.kk, r.name, a, b, b - a);
+        if (s->trace_print) fprintf(stderr, "QPTRACE g=%d kk=%d %-12s start=%9.3f end=%9.3f dur=%8.3f\n", r.g, r.kk, r.name, a, b, b - a);
         const int sl = prof_slot(r.name);
         s->prof_ms[sl] += b - a; s->prof_n[sl] += 1;
         t_end = b > t_end ? b : t_end;
       }
       s->prof_span_ms = t_end;
-      for (auto& r : g_trace) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
-      g_trace.clear();
+      for (auto& r : s->trace) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+      s->trace.clear();
     }
   }
   // ... and the caller's stream continues after the last kernel of every group
   for (int g = 0; g < s->G; ++g) {
     if (bk[g].err != cudaSuccess) return bk[g].err;
-    e = cudaEventRecord(s->grp[g].ev, bk[g].st(false));
-    if (e == cudaSuccess) e = cudaStreamWaitEvent(c.stream, s->grp[g].ev, 0);
+    e = cudaEventRecord(s->grp[g].ev_done, bk[g].st(false));
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(c.stream, s->grp[g].ev_done, 0);
     if (e != cudaSuccess) return e;
   }
   return cudaSuccess;

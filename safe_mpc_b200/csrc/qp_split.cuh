@@ -81,7 +81,8 @@ enum { S_ALPHA = 0, S_LIN = 1, S_QUAD = 2, NSTP = 4 };
 // per-problem doubles
 enum { D_X0 = 0, D_T0 = 10, D_MU = 65, D_MUAFF = 66, D_SIGMU = 67, D_ALPHA = 68, D_STEP = 69, D_RES = 70, NPD = 74 };
 // per-problem ints
-enum { J_ACT = 0, J_ITER = 1, J_QST = 2, J_REDO = 3, J_NC = 4, J_ITBUF = 5, J_R = 6, J_B = 7, NPI = 8 };
+// J_B: index of the problem this slot carries in the caller's arrays (-1: empty slot); J_FIN: its result (x_temp, u_temp) has been written
+enum { J_ACT = 0, J_ITER = 1, J_QST = 2, J_REDO = 3, J_NC = 4, J_ITBUF = 5, J_R = 6, J_B = 7, J_FIN = 8, NPI = 9 };
 
 struct QsBufs {
   const qs_real* rec;    // [T][N+1][REC][TL]   stage records (linearisation)
@@ -530,9 +531,13 @@ SMPC_HD bool qs_ctl(const smpc_problem_t& P, const QsBufs& q, int tile, int lane
   int qst;
   if (nan) qst = 3; else if (!unconv) qst = 0; else if (kk >= P.qp_iter_max) qst = 1; else qst = 2;
   QF(pi, J_ACT) = 0; QF(pi, J_ITER) = kk; QF(pi, J_QST) = qst; QF(pi, J_ITBUF) = kk & 1;
-  // status mapping of acados SQP_RTI: QP success / max-iter -> step taken (qs_final writes it), else QP failure
+  // status mapping of acados SQP_RTI: QP success / max-iter -> step taken (qs_final writes it), else QP failure.  A max-iter exit
+  // counts as solved only when its iterate is within qp_maxiter_accept x the tolerances (smpc_problem_t::qp_maxiter_accept: an
+  // infeasible QP ends at max-iter or at the minimum step length depending on rounding, with residuals many orders above)
   const int b = QF(pi, J_B);
-  status[b] = (qst == 0 || qst == 1) ? 0 : 4;
+  const double F = P.qp_maxiter_accept;
+  const bool sane = !(F > 0.0) || (r0 <= F * P.qp_tol_stat && nb <= F * P.qp_tol_eq && nd <= F * P.qp_tol_ineq && nm <= F * P.qp_tol_comp);
+  status[b] = (qst == 0 || (qst == 1 && sane)) ? 0 : 4;
   qp_iter[b] = kk;
   qp_status[b] = qst;
   for (int c = 0; c < 4; ++c) qp_res[(size_t)b * 5 + c] = QF(pd, D_RES + c);
@@ -540,14 +545,17 @@ SMPC_HD bool qs_ctl(const smpc_problem_t& P, const QsBufs& q, int tile, int lane
   return false;
 }
 
-// final: full step x_temp = x_guess + dx, u_temp = u_guess + du of one stage of a problem that took part in this solve
-// (zero step after a QP failure; a NaN in an accepted step turns the status into acados' 1).   thread = (problem, stage)
-// returns true when this stage found a NaN in an accepted step (the caller raises status[b] to 1)
-SMPC_HD bool qs_final(const QsBufs& q, int tile, int lane, int k, const uint8_t* act, int B, const int32_t* status, double* xt, double* ut) {
+// final: full step x_temp = x_guess + dx, u_temp = u_guess + du of one stage of a problem that took part in this solve and has
+// finished but not been written yet (zero step after a QP failure; a NaN in an accepted step turns the status into acados' 1).
+// Called once at the end of a solve and, when the solve compacts its slots, before every compaction (the slot of a finished
+// problem may be reused then).   thread = (slot, stage)
+// returns the problem index when this stage found a NaN in an accepted step (the caller raises status[b] to 1), else -1
+SMPC_HD int qs_final(const QsBufs& q, int tile, int lane, int k, const uint8_t* act, int B, const int32_t* status, double* xt, double* ut) {
   const int N = q.N;
   const int32_t* pi = q.pi + qs_pb(tile, NPI, lane);
-  const int b = (q.tile0 + tile) * TL + lane;
-  if (b >= B || (act && !act[b])) return false;
+  const int b = QF(pi, J_B);
+  if (b < 0 || b >= B || (act && !act[b])) return -1;
+  if (QF(pi, J_ACT) || QF(pi, J_FIN)) return -1;
   const bool ok = status[b] != 4;
   const double* it = q.it[QF(pi, J_ITBUF)] + qs_blk(tile, N, k, NIT, lane);
   const qs_real* rec = q.rec + qs_blk(tile, N, k, REC, lane);
@@ -560,7 +568,55 @@ SMPC_HD bool qs_final(const QsBufs& q, int tile, int lane, int k, const uint8_t*
   double* xtb = xt + ((size_t)b * (N + 1) + k) * NX;
 #pragma unroll
   for (int j = 0; j < NX; ++j) { const double z = ok ? QF(it, I_Z + NU + j) : 0.0; znan |= (z != z); xtb[j] = QF(rec, SMPC_REC_X + j) + z; }
-  return znan;
+  return znan ? b : -1;
+}
+
+// ================================================================================================================
+// Compaction of the slots of a tile group.  The stage-parallel kernels stream whole tiles: a tile with one problem still
+// iterating costs as much as a full one, and the iteration counts of the problems of a batch spread over a factor of two.
+// Between two iterations the problems still iterating are therefore packed into the leading slots: with n active problems,
+// the active ones in slots >= n (in slot order) move into the inactive slots < n (in slot order); nobody else moves, sources
+// and destinations are disjoint, and every kernel then only walks the first ceil(n / 32) tiles.  A move copies bits (stage
+// records, current iterate, step, per-problem scalars), so results do not depend on it.  The results of the finished
+// problems are written by qs_final before their slots are reused.
+// ================================================================================================================
+// plan for one group of T tiles (serial form: tests/emu; the device builds the same plan with a block-wide scan, qp.cu).
+// mv: [2][T * TL / 2] source and destination slots; returns the number of moves and marks the finished slots as written.
+SMPC_HD int qs_compact_plan(const QsBufs& q, int T, int32_t* mv, int* n_active_out) {
+  const int S = T * TL, half = S / 2;
+  int n = 0;
+  for (int s = 0; s < S; ++s) {
+    int32_t* pi = q.pi + qs_pb(s / TL, NPI, s % TL);
+    if (QF(pi, J_ACT)) ++n; else QF(pi, J_FIN) = 1;
+  }
+  int nm = 0, hole = 0;
+  for (int s = n; s < S; ++s) {
+    if (!QF(q.pi + qs_pb(s / TL, NPI, s % TL), J_ACT)) continue;
+    while (QF(q.pi + qs_pb(hole / TL, NPI, hole % TL), J_ACT)) ++hole;
+    mv[nm] = s; mv[half + nm] = hole; ++nm; ++hole;
+  }
+  if (n_active_out) *n_active_out = n;
+  return nm;
+}
+// one field of one stage of one move (thread = (move, stage, field) on the device): what prep of the next iteration reads
+// -- stage record, iterate of iteration kk, step
+enum { CMP_FIELDS = REC + 2 * NIT };
+SMPC_HD void qs_compact_move_field(const QsBufs& q, int src, int dst, int k, int kk, int f) {
+  const int N = q.N;
+  const int ts = src / TL, ls = src % TL, td = dst / TL, ld = dst % TL;
+  if (f < REC) { qs_real* r = const_cast<qs_real*>(q.rec); QF(r + qs_blk(td, N, k, REC, ld), f) = QF(q.rec + qs_blk(ts, N, k, REC, ls), f); }
+  else if (f < REC + NIT) { double* it = q.it[kk & 1]; QF(it + qs_blk(td, N, k, NIT, ld), f - REC) = QF(it + qs_blk(ts, N, k, NIT, ls), f - REC); }
+  else QF(q.st + qs_blk(td, N, k, NIT, ld), f - REC - NIT) = QF(q.st + qs_blk(ts, N, k, NIT, ls), f - REC - NIT);
+}
+// per-problem scalars of one move; the source slot becomes empty
+SMPC_HD void qs_compact_move_scalars(const QsBufs& q, int src, int dst) {
+  int32_t* ps = q.pi + qs_pb(src / TL, NPI, src % TL);
+  int32_t* pdst = q.pi + qs_pb(dst / TL, NPI, dst % TL);
+  for (int f = 0; f < NPI; ++f) QF(pdst, f) = QF(ps, f);
+  double* ds = q.pd + qs_pb(src / TL, NPD, src % TL);
+  double* dd = q.pd + qs_pb(dst / TL, NPD, dst % TL);
+  for (int f = 0; f < NPD; ++f) QF(dd, f) = QF(ds, f);
+  QF(ps, J_ACT) = 0; QF(ps, J_FIN) = 1; QF(ps, J_B) = -1;
 }
 
 // ================================================================================================================
@@ -1221,22 +1277,30 @@ SMPC_HD void qs_init(const QsBufs& q, int tile, int lane, int B, const double* x
   double* pd = q.pd + qs_pb(tile, NPD, lane);
   const bool on = b < B && (!act || act[b]);
   QF(pi, J_ACT) = on ? 1 : 0; QF(pi, J_ITER) = 0; QF(pi, J_QST) = 0; QF(pi, J_REDO) = 0; QF(pi, J_NC) = 1; QF(pi, J_ITBUF) = 0;
-  QF(pi, J_R) = b < B ? r[b] : 0; QF(pi, J_B) = b;
+  QF(pi, J_R) = b < B ? r[b] : 0; QF(pi, J_B) = b < B ? b : -1; QF(pi, J_FIN) = 0;
   for (int j = 0; j < NX; ++j) QF(pd, D_X0 + j) = b < B ? x0[(size_t)b * NX + j] : 0.0;
   QF(pd, D_MU) = 0.0; QF(pd, D_MUAFF) = 0.0; QF(pd, D_SIGMU) = 0.0; QF(pd, D_ALPHA) = 1.0; QF(pd, D_STEP) = 0.0;
 }
 
 // Host-side sequencing of one batched solve of one group of tiles; BK launches the phases (CUDA kernels in qp.cu, plain
-// loops in tests/emu).  issue() queues one IPM iteration up to the step-length decision and requests the two counters
-// (problems still active, problems that asked for the centering re-solve); advance() waits for them -- the one host
-// round trip per iteration -- and queues the rest.  Several groups are driven round-robin so that the latency-bound
-// Riccati sweeps of one group overlap the bandwidth-bound stage-parallel kernels of the others.
+// loops in tests/emu).  One IPM iteration = ctl, ric1, step<0>, ric2, step<1>, red, [step<2>, red], [compaction], prep of the
+// next iterate.  The host needs two numbers per iteration -- problems still active, problems that asked for the centering
+// re-solve -- to stop, to pick between kernel forms that give identical results, and to decide on a compaction.
+//   depth = 0   the host waits for the counters of every iteration before it queues the next one (one round trip per iteration;
+//               step<2> / red only when some problem asked for them)
+//   depth > 0   the host runs up to `depth` iterations ahead of the counters it has seen: it polls, blocks only when `depth`
+//               iterations are in flight, and queues step<2> / red unconditionally (they filter per problem); every kernel of an
+//               iteration queued past the end of the solve finds no active problem and exits.  The GPU never waits for the host.
+// Several groups are driven round-robin so that the latency-bound Riccati sweeps of one group overlap the bandwidth-bound
+// stage-parallel kernels of the others.
 template <class BK>
 struct QsLoop {
   BK& bk;
   int kk = 0;
+  int depth = 0;
+  int kk_seen = -1;              // newest iteration whose counters the host has read
   bool done = false;
-  explicit QsLoop(BK& b) : bk(b) {}
+  explicit QsLoop(BK& b, int depth_ = 0) : bk(b), depth(depth_) {}
   void issue() {
     bk.ctl(kk);
     bk.ric1();
@@ -1244,14 +1308,25 @@ struct QsLoop {
     bk.ric2();
     bk.step(kk, 1);
     bk.red(false);
-    bk.request_counters();
+    if (depth > 0) { bk.step(kk, 2); bk.red(true); }
+    bk.request_counters(kk);
   }
   void start() { bk.init(); bk.prep(0); issue(); }
   void advance() {
     int n_active = 0, n_redo = 0;
-    bk.wait_counters(n_active, n_redo);
-    if (n_active == 0) { bk.final(); done = true; return; }
-    if (n_redo > 0) { bk.step(kk, 2); bk.red(true); }
+    if (depth == 0) {
+      bk.wait_counters(kk, true, n_active, n_redo);
+      kk_seen = kk;
+      if (n_active == 0) { bk.final(); done = true; return; }
+      if (n_redo > 0) { bk.step(kk, 2); bk.red(true); }
+    } else {
+      while (kk_seen < kk) {
+        if (!bk.wait_counters(kk_seen + 1, kk - kk_seen >= depth, n_active, n_redo)) break;
+        ++kk_seen;
+        if (n_active == 0) { bk.final(); done = true; return; }
+      }
+    }
+    bk.compact(kk);              // (the backend decides; a no-op for most iterations)
     ++kk;
     bk.prep(kk);
     issue();
@@ -1259,9 +1334,9 @@ struct QsLoop {
 };
 
 template <class BK>
-int qs_drive(BK* groups, int n_groups) {
+int qs_drive(BK* groups, int n_groups, int depth = 0) {
   QsLoop<BK>* loops[8];
-  for (int g = 0; g < n_groups; ++g) { loops[g] = new QsLoop<BK>(groups[g]); loops[g]->start(); }
+  for (int g = 0; g < n_groups; ++g) { loops[g] = new QsLoop<BK>(groups[g], depth); loops[g]->start(); }
   int kmax = 0;
   for (bool any = true; any;) {
     any = false;

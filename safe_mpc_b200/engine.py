@@ -88,7 +88,7 @@ class Engine(EngineBase):
     def stream(self) -> int:
         return int(self.lib.smpc_stream(self.h) or 0)
 
-    PROF_NAMES = ['qs_init', 'qs_prep', 'qs_ctl', 'qs_ric1', 'qs_step0', 'qs_ric2', 'qs_step1', 'qs_red', 'qs_ric2_centering',
+    PROF_NAMES = ['qs_init', 'qs_prep', 'qs_ctl', 'qs_ric1', 'qs_step0', 'qs_ric2', 'qs_step1', 'qs_red', 'qs_compact',
                   'qs_step2_centering', 'qs_final']
 
     def set_profiling(self, on: bool):

@@ -179,6 +179,8 @@ def build_problem(params, controller: str, cost: str = 'ext', N: int | None = No
         p, nq=nq, N=N, n_pairs=abi.NPAIR, n_points=md.n_points, controller=ctrl, nn_rows=nn_rows,
         nn_terminal_soft=int(soft), stage0_collision_rows=int(not params.noise > 0), cost_type=COSTS[cost],
         abort_flag=int(params.abort_flag), qp_iter_max=int(params.qp_max_iter), lm_scale_dt=1, qp_cond_pred_corr=1,
+        # the SQP of the guess generator reads the QP multipliers back (merit line search): keep every problem in its slot
+        qp_keep_slots=int(getattr(params, 'qp_keep_slots', params.solver_type == 'SQP')),
         nn_precision=abi.NN_PRECISION[nn_precision or getattr(params, 'nn_precision', None) or 'strict'],
         dt=params.dt, q_weight=params.Q_weight, r_weight=params.R_weight, lm=params.levenberg_marquardt,
         alpha=params.alpha, eps=params.eps, slack_penalty_e=penalty,
@@ -186,7 +188,7 @@ def build_problem(params, controller: str, cost: str = 'ext', N: int | None = No
         tol_conv=params.tol_conv,
         # HPIPM BALANCE defaults (UNVERIFIED offline)
         qp_mu0=1e1, qp_tol_stat=1e-6, qp_tol_eq=1e-8, qp_tol_ineq=1e-8, qp_tol_comp=1e-8, qp_alpha_min=1e-12,
-        qp_reg_prim=1e-15,
+        qp_reg_prim=1e-15, qp_maxiter_accept=float(getattr(params, 'qp_maxiter_accept', 1e3)),
         gravity=[0.0, 0.0, -GRAVITY],
         joint_R=md.chain.joint_R, joint_p=md.chain.joint_p, joint_axis=md.chain.joint_axis, inertial=md.inertial,
         x_min=md.x_min, x_max=md.x_max, lbx=lbx, ubx=ubx, lbx_e=lbx_e, ubx_e=ubx_e,

@@ -106,17 +106,39 @@ struct HostBackend {
   void ric1() { each_problem([&](int t, int l) { HostStage w(l, RIC1_STAGE_FIELDS, order); w.nb = 2 - order; qs_ric1(P, q, t, w, psm.data() + l); }); }
   void ric2() { each_problem([&](int t, int l) { HostStage w(l, RIC2_STAGE_FIELDS, order); w.nb = 2 - order; qs_ric2(P, q, t, w); }); }
   void step(int kk, int mode) { each_stage([&](int t, int l, int k) { qs_step(P, q, t, l, k, kk, mode); }); }
-  void final() { each_stage([&](int t, int l, int k) { if (qs_final(q, t, l, k, act, B, status, xt, ut)) status[(q.tile0 + t) * TL + l] = 1; }); }
+  void final() { each_stage([&](int t, int l, int k) { const int b = qs_final(q, t, l, k, act, B, status, xt, ut); if (b >= 0) status[b] = 1; }); }
+  // compaction of the slots (qp_split.cuh): in the test harness after every iteration that leaves a hole, when enabled
+  int compact_mode = 0, n_compactions = 0, n_moves = 0;
+  void compact(int kk) {
+    if (!compact_mode) return;
+    final();                                                   // results of the finished problems, before their slots are reused
+    std::vector<int32_t> mv((size_t)T * TL, 0);
+    int na = 0;
+    const int nm = qs_compact_plan(q, T, mv.data(), &na);
+    const int half = T * TL / 2;
+    for (int i = 0; i < nm; ++i) {
+      for (int k = 0; k <= N; ++k) for (int f = 0; f < CMP_FIELDS; ++f) qs_compact_move_field(q, mv[i], mv[half + i], k, kk, f);
+      qs_compact_move_scalars(q, mv[i], mv[half + i]);
+    }
+    if (nm) { ++n_compactions; n_moves += nm; }
+  }
   void red(bool after) { each_problem([&](int t, int l) { qs_red(P, q, t, l, after); }); }
   int redo_total = 0;
-  void request_counters() {}
-  void wait_counters(int& na, int& nr) {
+  void request_counters(int) {}
+  bool wait_counters(int, bool, int& na, int& nr) {
     na = n_active; nr = 0;
     each_problem([&](int t, int l) { const int32_t* pi = q.pi + qs_pb(t, NPI, l); if (QF(pi, J_ACT) && QF(pi, J_REDO)) ++nr; });
     redo_total += nr;
+    return true;
   }
 };
 }  // namespace
+
+// loop options of the following solves (tests): run-ahead depth of QsLoop, compaction after every iteration that leaves a hole
+static int g_depth = 0, g_compact = 0;
+extern "C" void emu_set_options(int depth, int compact) { g_depth = depth; g_compact = compact; }
+static int g_last_compactions = 0, g_last_moves = 0;
+extern "C" void emu_last_compactions(int* n, int* moves) { *n = g_last_compactions; *moves = g_last_moves; }
 
 // Batched QP solve with the engine's kernel sources.  rec: [B][N+1][REC] (caller layout), x0: [B][10], r: [B].
 // Outputs in the layout of smpc_get_qp: z [B][N+1][15] ([du;dx], terminal stage: dx first), pi [B][N][10],
@@ -148,11 +170,15 @@ extern "C" int emu_qp_solve(const smpc_problem_t* P, int B, const double* rec, c
     b2.q.sb = q.sb + so * NSB; b2.q.prod = q.prod + so * NPROD; b2.q.res = q.res + so * NRES; b2.q.stp = q.stp + so * NSTP;
     b2.q.pd = q.pd + (size_t)t0 * NPD * TL; b2.q.pi = q.pi + (size_t)t0 * NPI * TL; b2.q.tile0 = t0;
     b2.T = t1 - t0;
+    b2.compact_mode = g_compact;
     gb.push_back(b2);
   }
-  qs_drive(gb.data(), G);
+  qs_drive(gb.data(), G, g_depth);
   if (n_redo_total) { *n_redo_total = 0; for (auto& b2 : gb) *n_redo_total += b2.redo_total; }
-  for (int b = 0; b < B; ++b) {
+  g_last_compactions = 0; g_last_moves = 0;
+  for (auto& b2 : gb) { g_last_compactions += b2.n_compactions; g_last_moves += b2.n_moves; }
+  // the canonical dump reads every problem at its original slot: only meaningful when no slot was reused
+  for (int b = 0; b < B && g_last_compactions == 0; ++b) {
     const int tile = b / TL, lane = b % TL;
     const int buf = QF(pi32.data() + qs_pb(tile, NPI, lane), J_ITBUF);
     for (int k = 0; k <= N; ++k) {
@@ -205,7 +231,7 @@ extern "C" int emu_qp_solve1(const smpc_problem_t* P, const double* rec, const d
   // B = 1: lanes 1..31 of the tile are padding (qs_init marks them inactive), the outputs are indexed by problem 0
   HostBackend bk{*P, q, 1, 1, N, 0, x0, &rr, nullptr, xt, ut, &st1, &it1, &qst1, res5, std::move(w.psm)};
   bk.skip_pad = true;
-  qs_drive(&bk, 1);
+  qs_drive(&bk, 1, g_depth);
   w.psm = std::move(bk.psm);
   *status = st1; *qp_iter = it1; *qp_status = qst1;
   for (int c = 0; c < 5; ++c) qp_res[c] = res5[c];

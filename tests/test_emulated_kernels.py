@@ -118,3 +118,39 @@ def test_qp_kernel_source_mask_and_infeasible(emu):
     assert (e['status'][on] == st_o[on]).all()
     xt_o, ut_o = o.get_temp()
     assert np.abs(e['xt'][on] - xt_o[on]).max() < 1e-9
+
+
+@pytest.mark.parametrize('controller', ['st', 'receding', 'zerovel'])
+def test_run_ahead_and_compaction_do_not_change_results(emu, controller):
+    """The host loop running ahead of the counters (step<2> / red queued unconditionally, iterations queued past the end of the
+    solve) and the compaction of the slots between iterations (qp_split.cuh: qs_compact_*) give bit-identical results: problems
+    with very different iteration counts share tiles, so the compaction moves most of them at least once."""
+    N, B = 12, 100                     # 4 tiles, two groups
+    prob, params, md = make_problem(controller, N=N)
+    o = Oracle(prob, B, 2)
+    x0 = start_states(B, seed=21, vel=0.6)
+    x0[::3, 5:] *= 4.0                 # every third problem starts fast: more iterations, some infeasible
+    xg, ug = rollout_guess(x0, N, params.dt, seed=22)
+    o.set_guess(xg, ug)
+    r = np.full(B, 5 if controller == 'receding' else N, dtype=np.int32)
+    o.set_state(abi.STATE_R, r)
+    o.rti_solve(x0)
+    lin = o.get_lin()
+    act = np.ones(B, dtype=np.uint8); act[7::11] = 0
+    emu.emu_set_options(C.c_int(0), C.c_int(0))
+    base = _emu_solve(emu, prob, lin, x0, r, act=act)
+    assert len(set(base['iter'][act == 1].tolist())) >= 4, 'the case should spread the iteration counts'
+    for depth, compact in ((3, 0), (0, 1), (2, 1)):
+        emu.emu_set_options(C.c_int(depth), C.c_int(compact))
+        try:
+            e = _emu_solve(emu, prob, lin, x0, r, act=act)
+            nc, nm = C.c_int(), C.c_int()
+            emu.emu_last_compactions(C.byref(nc), C.byref(nm))
+        finally:
+            emu.emu_set_options(C.c_int(0), C.c_int(0))
+        assert (nc.value > 0 and nm.value > 0) == bool(compact)
+        for key in ('status', 'iter', 'qp_status', 'res'):
+            assert np.array_equal(e[key], base[key]), (depth, compact, key)
+        on = act == 1
+        assert np.array_equal(e['xt'][on], base['xt'][on]) and np.array_equal(e['ut'][on], base['ut'][on]), (depth, compact)
+        assert np.isnan(e['xt'][~on]).all()                       # masked problems stay untouched

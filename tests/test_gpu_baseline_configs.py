@@ -33,7 +33,7 @@ def test_cfg0_closed_loop_outcomes_identical(controller, flavour, noise):
     from safe_mpc_b200.engine import Engine, Sim
     from oracle.oracle import Oracle, OracleSim
     B, N, steps = 100, 45, 800
-    cn = 1.0 if noise > 0 else 0.0                      # run_mpc_noise-style runs add 1 % torque noise
+    cn = 0.0                                            # (1 % torque noise ends 99 of 100 shipped-IC tests within 25 steps: no test of the loop)
     prob, params, md = make_problem(controller, N=N, noise=noise, control_noise=cn)
     bprob, _, _ = make_problem('backup', cost='zero', N=params.back_hor, noise=noise, control_noise=cn)
     eng = Engine(prob, B, 0)

@@ -18,7 +18,7 @@ B, N = 10000, 45
 @pytest.fixture(scope='module')
 def solved():
     from safe_mpc_b200.engine import Engine
-    prob, params, md = make_problem('st', N=N)
+    prob, params, md = make_problem('st', N=N, keep_slots=True)      # the stage records are read back below: no compaction of the slots
     x0 = start_states(B, seed=11)
     xg, ug = rollout_guess(x0, N, params.dt, seed=12, scale=1.0)
     eng = Engine(prob, B, 0)
@@ -59,12 +59,14 @@ def test_full_size_solution_properties(solved):
 
 
 def test_result_does_not_depend_on_the_batch(solved):
-    """two half batches solved on their own give bit-identical results (what the per-rank shards of bench.py --gpus N do)"""
+    """two half batches solved on their own give bit-identical results (what the per-rank shards of bench.py --gpus N do) -- and
+    they are solved with the default policy, i.e. WITH the compaction of the solver's slots that the full-batch fixture switches off"""
     from safe_mpc_b200.engine import Engine
     s = solved
     h = B // 2 + 16                                       # not a multiple of the tile or group size
+    prob2, _, _ = make_problem('st', N=N)
     for lo, hi in ((0, h), (h, B)):
-        eng = Engine(s['prob'], hi - lo, 0)
+        eng = Engine(prob2, hi - lo, 0)
         eng.set_guess(s['xg'][lo:hi], s['ug'][lo:hi])
         st = eng.rti_solve(s['x0'][lo:hi])
         xt, ut = eng.get_temp()

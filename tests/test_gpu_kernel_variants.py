@@ -69,3 +69,41 @@ def test_prep_forms_agree_bitwise(controller):
     for other in (thread, mixed):
         for i in range(4):
             assert np.array_equal(coop[i], other[i])
+
+
+@pytest.mark.parametrize('controller', ['st', 'receding'])
+def test_host_loop_depth_and_compaction_agree_bitwise(controller):
+    """The host queues IPM iterations ahead of the counters it has read (SMPC_QP_DEPTH) and packs the problems still iterating into
+    the leading slots between iterations (qs_compact_*): neither may change a bit of any result.  The batch mixes slow and fast
+    problems in every tile and is large enough (40 tiles) for the compaction to act."""
+    from safe_mpc_b200.engine import Engine
+    from safe_mpc_b200 import abi
+    Bc, Nc = 1280, 16
+
+    def solve(env):
+        old = {k: os.environ.get(k) for k in env}
+        os.environ.update(env)
+        try:
+            prob, params, md = make_problem(controller, N=Nc)
+            eng = Engine(prob, Bc, 0)
+        finally:
+            for k, v in old.items():
+                os.environ.pop(k, None) if v is None else os.environ.__setitem__(k, v)
+        x0 = start_states(Bc, seed=23, vel=0.5)
+        x0[::3, 5:] *= 4.0                                    # every third problem starts fast: many more iterations, some infeasible
+        xg, ug = rollout_guess(x0, Nc, params.dt, seed=24, scale=1.0)
+        act = np.ones(Bc, dtype=np.uint8); act[5::17] = 0
+        eng.set_guess(xg, ug)
+        st = eng.rti_solve(x0, act)
+        xt, ut = eng.get_temp()
+        it = eng.get_state(abi.STATE_QP_ITER)
+        prof = None
+        eng.close()
+        return st, xt, ut, it
+
+    base = solve({'SMPC_QP_DEPTH': '0', 'SMPC_QP_COMPACT': '0'})       # one host round trip per iteration, no compaction
+    assert len(set(base[3].tolist())) >= 6
+    for env in ({'SMPC_QP_DEPTH': '3', 'SMPC_QP_COMPACT': '0'}, {'SMPC_QP_DEPTH': '0', 'SMPC_QP_COMPACT': '1'}, {}):
+        other = solve(env)
+        for i in range(4):
+            assert np.array_equal(base[i], other[i]), (env, i)

@@ -112,7 +112,11 @@ def test_mpc_script_runs_and_writes_the_reference_result_file(tmp_path, monkeypa
     spec = importlib.util.spec_from_file_location('mpc_script', os.path.join(os.path.dirname(__file__), '..', 'scripts', 'mpc.py'))
     mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
     monkeypatch.setattr(mod.Parameters, '__init__', _short_run(mod.Parameters.__init__, str(tmp_path) + '/', 40))
-    n_coll = mod.main(['-c', 'htwa', '--horizon', '15', '--back_hor', '15', '--batch', '6'])
+    # without a guess file the script fails like the reference does on its missing pickle (mpc.py:80) ...
+    with pytest.raises(FileNotFoundError, match='guess_acados'):
+        mod.main(['-c', 'htwa', '--horizon', '15', '--back_hor', '15', '--batch', '6'])
+    # ... unless it is told to generate the warm starts itself
+    n_coll = mod.main(['-c', 'htwa', '--horizon', '15', '--back_hor', '15', '--batch', '6', '--generate-guess'])
     files = [f for f in os.listdir(tmp_path) if f.endswith('_mpc.pkl')]
     assert len(files) == 1 and files[0].startswith('z1_htwa_use_netTrue_15hor_10sm_noise_0.0_control_noise0.0')
     data = pickle.load(open(tmp_path / files[0], 'rb'))

@@ -453,8 +453,8 @@ def time_mlp(params, md, n_rows, device_index, dev):
 
 # linearize_kernel: FP64 flop per (problem, stage) = 2 x DFMA + DADD + DMUL thread instructions executed / (B (N+1)), from ncu
 # (smsp__sass_thread_inst_executed_op_d{fma,add,mul}_pred_on.sum; profiles/r02_linearize_flops.md).  Frozen in BASELINE.md section 4.
-LINEARIZE_FLOP_PER_STAGE = 18000.0
-LINEARIZE_FLOP_SOURCE = 'SURVEY.md section 8(d) estimate (18 kflop +- 50 %); replaced by the executed-instruction tally once measured'
+LINEARIZE_FLOP_PER_STAGE = 16274.0
+LINEARIZE_FLOP_SOURCE = 'executed FP64 instructions of linearize_kernel under ncu, 2 DFMA + DADD + DMUL per (problem, stage): profiles/r02_linearize_flops.md'
 
 
 def main_qp_bytes(N):

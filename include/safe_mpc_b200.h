@@ -232,6 +232,9 @@ enum { SMPC_STATE_FAILS = 0, SMPC_STATE_R = 1, SMPC_STATE_STATUS = 2, SMPC_STATE
 int smpc_get_state_i32(smpc_handle_t* h, int32_t field, int32_t* out, int32_t mem);
 int smpc_set_state_i32(smpc_handle_t* h, int32_t field, const int32_t* in, int32_t mem);
 int smpc_get_x_viable(smpc_handle_t* h, double* x_viable, int32_t mem);
+/* max-norm residuals of the last QP of every problem [B][5]: stationarity, dynamics, inequality, complementarity, mu (what acados'
+ * get_stats('qp_res..') / HPIPM's get_max_res_* report; controller.py:192-193 only reads the timing fields) */
+int smpc_get_qp_residuals(smpc_handle_t* h, double* res5, int32_t mem);
 
 /* --- closed loop = the per-test body of scripts/mpc.py:102-291, batched ---
  * `backup` is a handle created with controller = SMPC_CTRL_BACKUP and N = back_hor (mpc.py:54-73),

@@ -8,6 +8,15 @@
 #pragma once
 #include <cmath>
 
+// Flop tally (tests only): with -DORC_COUNT_FLOPS every operation on an AD scalar adds its floating-point operation count
+// (value part + derivative parts; a transcendental counts as one) to a thread-local counter, read through orc_flops_get().
+#ifdef ORC_COUNT_FLOPS
+namespace orc { extern thread_local unsigned long long g_flops; }
+#define ORC_FLOP(n) (::orc::g_flops += (unsigned long long)(n))
+#else
+#define ORC_FLOP(n) ((void)0)
+#endif
+
 namespace orc {
 
 // first-order dual number with N directions
@@ -21,30 +30,30 @@ struct Dual {
 };
 
 template <int N> inline Dual<N> operator+(const Dual<N>& a, const Dual<N>& b) {
-  Dual<N> r; r.v = a.v + b.v; for (int i = 0; i < N; ++i) r.d[i] = a.d[i] + b.d[i]; return r; }
+  Dual<N> r; ORC_FLOP(1 + N); r.v = a.v + b.v; for (int i = 0; i < N; ++i) r.d[i] = a.d[i] + b.d[i]; return r; }
 template <int N> inline Dual<N> operator-(const Dual<N>& a, const Dual<N>& b) {
-  Dual<N> r; r.v = a.v - b.v; for (int i = 0; i < N; ++i) r.d[i] = a.d[i] - b.d[i]; return r; }
+  Dual<N> r; ORC_FLOP(1 + N); r.v = a.v - b.v; for (int i = 0; i < N; ++i) r.d[i] = a.d[i] - b.d[i]; return r; }
 template <int N> inline Dual<N> operator-(const Dual<N>& a) {
   Dual<N> r; r.v = -a.v; for (int i = 0; i < N; ++i) r.d[i] = -a.d[i]; return r; }
 template <int N> inline Dual<N> operator*(const Dual<N>& a, const Dual<N>& b) {
-  Dual<N> r; r.v = a.v * b.v; for (int i = 0; i < N; ++i) r.d[i] = a.d[i] * b.v + a.v * b.d[i]; return r; }
+  Dual<N> r; ORC_FLOP(1 + 3 * N); r.v = a.v * b.v; for (int i = 0; i < N; ++i) r.d[i] = a.d[i] * b.v + a.v * b.d[i]; return r; }
 template <int N> inline Dual<N> operator/(const Dual<N>& a, const Dual<N>& b) {
-  Dual<N> r; double inv = 1.0 / b.v; r.v = a.v * inv;
+  Dual<N> r; ORC_FLOP(2 + 3 * N); double inv = 1.0 / b.v; r.v = a.v * inv;
   for (int i = 0; i < N; ++i) r.d[i] = (a.d[i] - r.v * b.d[i]) * inv; return r; }
-template <int N> inline Dual<N> operator+(const Dual<N>& a, double b) { Dual<N> r = a; r.v += b; return r; }
-template <int N> inline Dual<N> operator+(double b, const Dual<N>& a) { Dual<N> r = a; r.v += b; return r; }
-template <int N> inline Dual<N> operator-(const Dual<N>& a, double b) { Dual<N> r = a; r.v -= b; return r; }
+template <int N> inline Dual<N> operator+(const Dual<N>& a, double b) { Dual<N> r = a; ORC_FLOP(1); r.v += b; return r; }
+template <int N> inline Dual<N> operator+(double b, const Dual<N>& a) { Dual<N> r = a; ORC_FLOP(1); r.v += b; return r; }
+template <int N> inline Dual<N> operator-(const Dual<N>& a, double b) { Dual<N> r = a; ORC_FLOP(1); r.v -= b; return r; }
 template <int N> inline Dual<N> operator-(double b, const Dual<N>& a) { return Dual<N>(b) - a; }
 template <int N> inline Dual<N> operator*(const Dual<N>& a, double b) {
-  Dual<N> r; r.v = a.v * b; for (int i = 0; i < N; ++i) r.d[i] = a.d[i] * b; return r; }
+  Dual<N> r; ORC_FLOP(1 + N); r.v = a.v * b; for (int i = 0; i < N; ++i) r.d[i] = a.d[i] * b; return r; }
 template <int N> inline Dual<N> operator*(double b, const Dual<N>& a) { return a * b; }
 template <int N> inline Dual<N> operator/(const Dual<N>& a, double b) { return a * (1.0 / b); }
 template <int N> inline Dual<N> sin(const Dual<N>& a) {
-  Dual<N> r; r.v = std::sin(a.v); double c = std::cos(a.v); for (int i = 0; i < N; ++i) r.d[i] = c * a.d[i]; return r; }
+  Dual<N> r; ORC_FLOP(2 + N); r.v = std::sin(a.v); double c = std::cos(a.v); for (int i = 0; i < N; ++i) r.d[i] = c * a.d[i]; return r; }
 template <int N> inline Dual<N> cos(const Dual<N>& a) {
-  Dual<N> r; r.v = std::cos(a.v); double s = -std::sin(a.v); for (int i = 0; i < N; ++i) r.d[i] = s * a.d[i]; return r; }
+  Dual<N> r; ORC_FLOP(2 + N); r.v = std::cos(a.v); double s = -std::sin(a.v); for (int i = 0; i < N; ++i) r.d[i] = s * a.d[i]; return r; }
 template <int N> inline Dual<N> sqrt(const Dual<N>& a) {
-  Dual<N> r; r.v = std::sqrt(a.v); double k = 0.5 / r.v; for (int i = 0; i < N; ++i) r.d[i] = k * a.d[i]; return r; }
+  Dual<N> r; ORC_FLOP(2 + N); r.v = std::sqrt(a.v); double k = 0.5 / r.v; for (int i = 0; i < N; ++i) r.d[i] = k * a.d[i]; return r; }
 // CasADi fmin/fmax: value of the selected branch, derivative of the selected branch
 template <int N> inline Dual<N> fmin(const Dual<N>& a, double b) { return (a.v <= b) ? a : Dual<N>(b); }
 template <int N> inline Dual<N> fmax(const Dual<N>& a, double b) { return (a.v >= b) ? a : Dual<N>(b); }
@@ -66,13 +75,13 @@ struct Dual2 {
   static int idx(int i, int j) { if (i > j) { int t = i; i = j; j = t; } return i * N - i * (i - 1) / 2 + (j - i); }
 };
 template <int N> inline Dual2<N> operator+(const Dual2<N>& a, const Dual2<N>& b) {
-  Dual2<N> r; r.v = a.v + b.v; for (int i = 0; i < N; ++i) r.g[i] = a.g[i] + b.g[i];
+  Dual2<N> r; ORC_FLOP(1 + N + Dual2<N>::NH); r.v = a.v + b.v; for (int i = 0; i < N; ++i) r.g[i] = a.g[i] + b.g[i];
   for (int i = 0; i < Dual2<N>::NH; ++i) r.h[i] = a.h[i] + b.h[i]; return r; }
 template <int N> inline Dual2<N> operator-(const Dual2<N>& a, const Dual2<N>& b) {
-  Dual2<N> r; r.v = a.v - b.v; for (int i = 0; i < N; ++i) r.g[i] = a.g[i] - b.g[i];
+  Dual2<N> r; ORC_FLOP(1 + N + Dual2<N>::NH); r.v = a.v - b.v; for (int i = 0; i < N; ++i) r.g[i] = a.g[i] - b.g[i];
   for (int i = 0; i < Dual2<N>::NH; ++i) r.h[i] = a.h[i] - b.h[i]; return r; }
 template <int N> inline Dual2<N> operator*(const Dual2<N>& a, const Dual2<N>& b) {
-  Dual2<N> r; r.v = a.v * b.v;
+  Dual2<N> r; ORC_FLOP(1 + 3 * N + 7 * Dual2<N>::NH); r.v = a.v * b.v;
   for (int i = 0; i < N; ++i) r.g[i] = a.g[i] * b.v + a.v * b.g[i];
   for (int i = 0; i < N; ++i) for (int j = i; j < N; ++j) {
     int k = Dual2<N>::idx(i, j);
@@ -80,18 +89,18 @@ template <int N> inline Dual2<N> operator*(const Dual2<N>& a, const Dual2<N>& b)
   }
   return r; }
 template <int N> inline Dual2<N> operator*(const Dual2<N>& a, double b) {
-  Dual2<N> r; r.v = a.v * b; for (int i = 0; i < N; ++i) r.g[i] = a.g[i] * b;
+  Dual2<N> r; ORC_FLOP(1 + N + Dual2<N>::NH); r.v = a.v * b; for (int i = 0; i < N; ++i) r.g[i] = a.g[i] * b;
   for (int i = 0; i < Dual2<N>::NH; ++i) r.h[i] = a.h[i] * b; return r; }
 template <int N> inline Dual2<N> operator*(double b, const Dual2<N>& a) { return a * b; }
-template <int N> inline Dual2<N> operator+(const Dual2<N>& a, double b) { Dual2<N> r = a; r.v += b; return r; }
-template <int N> inline Dual2<N> operator-(const Dual2<N>& a, double b) { Dual2<N> r = a; r.v -= b; return r; }
+template <int N> inline Dual2<N> operator+(const Dual2<N>& a, double b) { Dual2<N> r = a; ORC_FLOP(1); r.v += b; return r; }
+template <int N> inline Dual2<N> operator-(const Dual2<N>& a, double b) { Dual2<N> r = a; ORC_FLOP(1); r.v -= b; return r; }
 template <int N> inline Dual2<N> sin(const Dual2<N>& a) {
-  Dual2<N> r; double s = std::sin(a.v), c = std::cos(a.v); r.v = s;
+  Dual2<N> r; ORC_FLOP(2 + N + 4 * Dual2<N>::NH); double s = std::sin(a.v), c = std::cos(a.v); r.v = s;
   for (int i = 0; i < N; ++i) r.g[i] = c * a.g[i];
   for (int i = 0; i < N; ++i) for (int j = i; j < N; ++j) { int k = Dual2<N>::idx(i, j); r.h[k] = c * a.h[k] - s * a.g[i] * a.g[j]; }
   return r; }
 template <int N> inline Dual2<N> cos(const Dual2<N>& a) {
-  Dual2<N> r; double s = std::sin(a.v), c = std::cos(a.v); r.v = c;
+  Dual2<N> r; ORC_FLOP(2 + N + 4 * Dual2<N>::NH); double s = std::sin(a.v), c = std::cos(a.v); r.v = c;
   for (int i = 0; i < N; ++i) r.g[i] = -s * a.g[i];
   for (int i = 0; i < N; ++i) for (int j = i; j < N; ++j) { int k = Dual2<N>::idx(i, j); r.h[k] = -s * a.h[k] - c * a.g[i] * a.g[j]; }
   return r; }

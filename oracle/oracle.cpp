@@ -22,6 +22,12 @@
 
 using namespace orc;
 
+#ifdef ORC_COUNT_FLOPS
+namespace orc { thread_local unsigned long long g_flops = 0; }
+extern "C" void orc_flops_reset() { orc::g_flops = 0; }
+extern "C" unsigned long long orc_flops_get() { return orc::g_flops; }
+#endif
+
 namespace {
 constexpr int NQ = ORC_NQ, NX = ORC_NX, NU = ORC_NU, REC = SMPC_REC;
 
@@ -309,6 +315,7 @@ int rti_solve_one(orc_handle& h, int b, const double* x0, Workspace& W) {
     h.qp_iter[b] = it; h.qp_status[b] = qst; h.status[b] = status;
     return status;
   }
+  qp.set_ratio_tolerances(o.tol_stat, o.tol_eq, o.tol_ineq, o.tol_comp);
   int qs = qp.solve(o);
   // acados status of a QP exit: solved, or max-iter within qp_maxiter_accept x the tolerances (include/safe_mpc_b200.h)
   auto accepted = [&](int q, const QpSol& sl) {
@@ -317,27 +324,25 @@ int rti_solve_one(orc_handle& h, int b, const double* x0, Workspace& W) {
     return q == 0 || (q == 1 && sane);
   };
   if (h.probe_eps > 0.0) {
-    // sensitivity probe: the same QP with its gradients and dynamics offsets perturbed by a relative probe_eps; a solve whose status
-    // changes under such a perturbation is decided by rounding, not by the algorithm (tests/test_gpu_closed_loop_full.py)
+    // margin probe (tests only): is the accept / fail status of this solve decided by rounding?
+    //   accepted: the stop test is disabled and the same iteration runs three iterations further; a robust solve stays within the
+    //             tolerances, a knife-edge one (a QP at the boundary of feasibility whose multipliers are about to diverge) has left them
+    //   failed:   knife-edge when some iterate came within qp_maxiter_accept x the tolerances (another implementation may have stopped there)
     const QpSol keep = qp.sol();
-    bool flip = false;
-    for (int trial = 0; trial < 2 && !flip; ++trial) {
-      uint64_t sd = 0x9E3779B97F4A7C15ull * (uint64_t)(b + 1) + (uint64_t)trial * 0xD1B54A32D192ED03ull + (uint64_t)h.cur_step[b];
-      auto rnd = [&]() { sd ^= sd << 13; sd ^= sd >> 7; sd ^= sd << 17; return (double)(sd >> 11) / 9007199254740992.0 * 2.0 - 1.0; };
-      for (int k = 0; k <= N; ++k) {
-        QpStage& S = qp.stages()[k];
-        for (int i = 0; i < QNZ; ++i) S.g[i] *= 1.0 + h.probe_eps * rnd();
-        for (int i = 0; i < NX; ++i) S.b[i] *= 1.0 + h.probe_eps * rnd();
-      }
-      const int qs2 = qp.solve(o);
-      flip = accepted(qs2, qp.sol()) != accepted(qs, keep);
-      for (int k = 0; k <= N; ++k) {
-        double lo[NX], hi[NX];
-        stage_box(h, b, k, x0, lo, hi);
-        assemble_stage(P, k, lin + (size_t)k * REC, lo, hi, qp.stages()[k]);
-      }
+    bool knife;
+    if (accepted(qs, keep)) {
+      QpOpts o2 = o;
+      o2.tol_stat = o2.tol_eq = o2.tol_ineq = o2.tol_comp = -1.0;
+      o2.iter_max = keep.iter + 3;
+      qp.solve(o2);
+      const QpSol& s2 = qp.sol();
+      knife = !(s2.res[0] <= P.qp_tol_stat && s2.res[1] <= P.qp_tol_eq && s2.res[2] <= P.qp_tol_ineq && s2.res[3] <= P.qp_tol_comp);
+      if (qs == 1) knife = true;
+    } else {
+      const double F = P.qp_maxiter_accept > 0.0 ? P.qp_maxiter_accept : 1e3;
+      knife = keep.best_ratio <= F;
     }
-    if (flip) h.probe_flips[b] += 1;
+    if (knife) h.probe_flips[b] += 1;
     qp.restore(keep);
   }
   const QpSol& sol = qp.sol();
@@ -716,6 +721,7 @@ int orc_set_state_i32(orc_handle_t* h, int32_t f, const int32_t* in) {
   std::copy(in, in + h->B, v->begin());
   return SMPC_OK;
 }
+int orc_get_qp_residuals(orc_handle_t* h, double* res5) { std::copy(h->qp_res.begin(), h->qp_res.end(), res5); return SMPC_OK; }
 int orc_get_x_viable(orc_handle_t* h, double* xv) { std::copy(h->x_viable.begin(), h->x_viable.end(), xv); return SMPC_OK; }
 
 int orc_mass_bias(orc_handle_t* h, int32_t b, int32_t nominal, const double* x, double* M, double* bias) {

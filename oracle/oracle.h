@@ -50,8 +50,10 @@ int orc_set_mlp_fp32(orc_handle_t* h, int32_t on);
 typedef int (*orc_qp_hook_t)(const orc_problem_t* P, const double* rec, const double* x0, int32_t r, double* xt, double* ut, int32_t* status,
                              int32_t* qp_iter, int32_t* qp_status, double* qp_res);
 int orc_set_qp_hook(orc_handle_t* h, orc_qp_hook_t fn);
-/* tests only: sensitivity probe.  eps > 0: every solve is repeated on data perturbed by a relative eps; orc_get_probe_flips returns, per
- * problem, how many solves changed their accept / fail status under the perturbation (rounding-decided solves) */
+/* tests only: margin probe.  eps > 0 switches it on: every accepted solve is run three iterations past its stop test (a robust solve stays
+ * converged; at the boundary of feasibility the multipliers diverge and it does not), every failed solve is checked for an iterate that came
+ * within qp_maxiter_accept x the tolerances.  orc_get_probe_flips returns, per problem, how many of its solves were such knife-edge solves:
+ * their accept / fail status is decided by rounding, two correct implementations may disagree on it */
 int orc_set_probe(orc_handle_t* h, double eps);
 int orc_get_probe_flips(orc_handle_t* h, int32_t* out);
 
@@ -75,6 +77,7 @@ int orc_get_qp(orc_handle_t* h, double* dz, double* pi, double* lam, double* t);
 int orc_get_state_i32(orc_handle_t* h, int32_t field, int32_t* out);
 int orc_set_state_i32(orc_handle_t* h, int32_t field, const int32_t* in);
 int orc_get_x_viable(orc_handle_t* h, double* x_viable);
+int orc_get_qp_residuals(orc_handle_t* h, double* res5);
 
 int orc_sim_create(orc_handle_t* main_ctrl, orc_handle_t* backup, int32_t n_steps, orc_sim_t** out);
 void orc_sim_destroy(orc_sim_t* s);

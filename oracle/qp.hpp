@@ -54,6 +54,7 @@ struct QpSol {
   int status = 0;            // 0 success, 1 max iter, 2 min step, 3 NaN
   double res[4] = {0, 0, 0, 0};  // max-norm residuals: stationarity, dynamics, inequality, complementarity
   double mu = 0;
+  double best_ratio = 1e300; // smallest max_i(res_i / tol_i) over the iterates of the solve (margin probe of oracle.cpp)
 };
 
 struct QpOpts {
@@ -82,6 +83,9 @@ class QpIpm {
   }
   std::vector<QpStage>& stages() { return st_; }
   const QpSol& sol() const { return sol_; }
+  // tolerances the residual ratios of QpSol::best_ratio refer to (default: those of the solve; the margin probe re-solves with
+  // the stop test disabled and keeps the original ones here)
+  void set_ratio_tolerances(double ts, double te, double ti, double tc) { ratio_tol_[0] = ts; ratio_tol_[1] = te; ratio_tol_[2] = ti; ratio_tol_[3] = tc; }
   void restore(const QpSol& s) { sol_ = s; }   // (sensitivity probe of oracle.cpp: put the un-perturbed result back)
 
   // true when constraint slot c of stage k exists
@@ -99,7 +103,15 @@ class QpIpm {
     int kk = 0;
     double alpha = 1.0;
     sol_.status = 0;
+    sol_.best_ratio = 1e300;
+    auto ratio = [&]() {
+      const double t[4] = {ratio_tol_[0], ratio_tol_[1], ratio_tol_[2], ratio_tol_[3]};
+      double r = 0.0;
+      for (int i = 0; i < 4; ++i) { const double v = sol_.res[i] / t[i]; r = (v > r || !(v == v)) ? v : r; }
+      return r;
+    };
     for (; kk < o.iter_max; ++kk) {
+      { const double r = ratio(); if (r < sol_.best_ratio) sol_.best_ratio = r; }
       if (!(sol_.res[0] > o.tol_stat || sol_.res[1] > o.tol_eq || sol_.res[2] > o.tol_ineq || sol_.res[3] > o.tol_comp)) break;
       if (!(alpha > o.alpha_min)) break;
       // ---- predictor (affine scaling direction) ----
@@ -127,6 +139,7 @@ class QpIpm {
       if (!(sol_.res[0] == sol_.res[0]) || !(sol_.res[1] == sol_.res[1]) || !(sol_.res[2] == sol_.res[2]) ||
           !(sol_.res[3] == sol_.res[3])) { sol_.status = 3; sol_.iter = kk + 1; return 3; }
     }
+    { const double r = ratio(); if (r < sol_.best_ratio) sol_.best_ratio = r; }
     sol_.iter = kk;
     bool conv = !(sol_.res[0] > o.tol_stat || sol_.res[1] > o.tol_eq || sol_.res[2] > o.tol_ineq || sol_.res[3] > o.tol_comp);
     if (conv) sol_.status = 0;
@@ -143,6 +156,7 @@ class QpIpm {
   std::vector<double> res_g_, res_gs_, res_b_, res_d_, res_m_, rm_, dz_, dpi_, ds_, dlam_, dt__, dlam_aff_, dt_aff_;
   std::vector<double> Lr_, Ls_, P_, L0_, l_, p_, Hc_;
   int nc_ = 0;
+  double ratio_tol_[4] = {1e-6, 1e-8, 1e-8, 1e-8};
 
   // row product a_j . z for row j of stage k (box rows first)
   double row_dot(const QpStage& S, int j, const double* z) const {

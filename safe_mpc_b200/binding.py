@@ -208,6 +208,12 @@ class EngineBase:
         p, m, k = self._in(values, np.int32, (self.B,))
         self._call('set_state_i32', C.c_int32(field), p, mem=m)
 
+    def get_qp_residuals(self, like=None):
+        """max-norm residuals of the last QP of every problem: [B, 5] = stationarity, dynamics, inequality, complementarity, mu"""
+        out, p, m = self._out((self.B, 5), np.float64, like)
+        self._call('get_qp_residuals', p, mem=m)
+        return out
+
     def get_x_viable(self, like=None):
         out, p, m = self._out((self.B, abi.NX), np.float64, like)
         self._call('get_x_viable', p, mem=m)

@@ -525,6 +525,7 @@ int smpc_set_state_i32(smpc_handle_t* h, int32_t f, const int32_t* in, int32_t m
   if (!p) return fail(h, SMPC_ERR_ARG, "smpc_set_state_i32: unknown field");
   return copy_in(h, p, in, sizeof(int32_t) * h->B, mem);
 }
+int smpc_get_qp_residuals(smpc_handle_t* h, double* res5, int32_t mem) { return copy_out(h, res5, h->qp_res, sizeof(double) * h->B * 5, mem); }
 int smpc_get_x_viable(smpc_handle_t* h, double* xv, int32_t mem) { return copy_out(h, xv, h->x_viable, sizeof(double) * h->B * NX, mem); }
 
 int smpc_set_profiling(smpc_handle_t* h, int32_t enable) { qp_set_profiling(h->qp, enable != 0); return SMPC_OK; }

@@ -1281,7 +1281,9 @@ struct QpSolver {
   double prof_ms[SMPC_PROF_N] = {0};
   int32_t prof_n[SMPC_PROF_N] = {0};
   double prof_span_ms = 0.0;
-  int depth = 2;                // IPM iterations the host queues ahead of the counters it has seen (SMPC_QP_DEPTH; 0: one round trip per iteration)
+  int depth = 0;                // IPM iterations the host queues ahead of the counters it has seen (SMPC_QP_DEPTH).  Default 0 = one round trip per
+                                // iteration: measured on B200 (profiles/r02_qp_loop.md) running ahead costs two unconditional launches per iteration
+                                // (step<2>, red) and gains nothing while three tile groups already cover the round trip
   bool compact = true;          // pack the problems still iterating into the leading slots between iterations (SMPC_QP_COMPACT=0: never)
   int compact_min_tiles = 32;   // ... for groups of at least this many tiles
   bool compacted = false;       // the last solve reused slots: per-slot dumps (smpc_get_lin / smpc_get_qp) are not available for it

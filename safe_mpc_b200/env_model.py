@@ -133,6 +133,17 @@ class AdamModel:
     def update_randomized_dynamics(self, inertial=None, noise_percent=None, seed=0, controller_name=None):
         """Per-problem plant parameters [B, nq, 10].  The reference reloads ``z1_randomized<name>.urdf`` per test; here the
         whole batch is set at once, either from explicit parameters or drawn like ``randomize_model`` (uniform +- percent)."""
+        if inertial is None and controller_name is not None:
+            # env_model.py:321-328: the reference reloads robots/.../<sys>_randomized<controller_name>.urdf; here one name per problem
+            # ('noise<level>_<i>', mpc.py:106), the files of scripts/generate_urdf_noise.py
+            from .urdf import URDF
+            from .robot_model import nominal_link_inertials
+            names = [controller_name] * self.batch if isinstance(controller_name, str) else list(controller_name)
+            rows = []
+            for nm in names:
+                ln = nominal_link_inertials(URDF.from_xml_file(self.params.robot_urdf[:-5] + f'_randomized{nm}.urdf'))
+                rows.append(self.data.chain.lump(ln['mass'], ln['com'], ln['inertia6'], ln['rpy']))
+            inertial = np.stack(rows)
         if inertial is None:
             n = float(self.params.noise if noise_percent is None else noise_percent)
             links = randomized_link_inertials(self.data.nominal_links, n, n, n, self.batch, seed=seed)

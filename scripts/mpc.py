@@ -76,8 +76,16 @@ def main(argv=None):
     controller.reset_controller()
 
     # per-test perturbed plants (mpc.py:106-107) and the per-test torque-noise draw (mpc.py:126-127)
+    # mpc.py:106-107 loads z1_randomizednoise<noise>_<i>.urdf of scripts/generate_urdf_noise.py for test i; when those files are absent the
+    # same perturbation is drawn here (randomize_model's draw order on default_rng(0): the numbers of the first noise level of the script)
+    names = [f'noise{args["noise"]}_{i}' for i in range(batch)]
+    have_files = all(os.path.isfile(params.robot_urdf[:-5] + f'_randomized{n}.urdf') for n in names)
+    print('perturbed plants:', 'read from robots/*_randomizednoise*.urdf' if have_files else f'drawn (uniform +-{args["noise"]} %, default_rng(0))')
     for m, c in ((model, controller), (model_backup, safe_ocp)):
-        m.update_randomized_dynamics(noise_percent=args['noise'], seed=0)
+        if have_files:
+            m.update_randomized_dynamics(controller_name=names)
+        else:
+            m.update_randomized_dynamics(noise_percent=args['noise'], seed=0)
         m.reset_seed()
         c.ocp_solver.set_plant_inertial(m.plant_inertial)
         c.ocp_solver.set_torque_noise(m.torque_noise)

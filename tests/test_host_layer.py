@@ -132,3 +132,35 @@ def _short_run(orig, data_dir, n_steps):
         self.DATA_DIR = data_dir
         self.n_steps = n_steps
     return init
+
+
+def test_generate_urdf_noise_script_and_model_reload(tmp_path, monkeypatch):
+    import os
+    """scripts/generate_urdf_noise.py writes one perturbed URDF per test and level with the reference's seeding schedule
+    (default_rng(0) for the first level, default_rng(test_num) afterwards: generate_urdf_noise.py:32-36, utils.py:19-24), and a file read
+    back gives the inertial parameters the in-memory draw gives."""
+    import importlib.util
+    import shutil
+    from safe_mpc_b200.robot_model import nominal_link_inertials, randomized_link_inertials
+    from safe_mpc_b200.urdf import URDF
+    spec = importlib.util.spec_from_file_location('gen_noise', os.path.join(os.path.dirname(__file__), '..', 'scripts', 'generate_urdf_noise.py'))
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+    orig = mod.Parameters.__init__
+
+    def init(self, *a, **k):
+        orig(self, *a, **k)
+        dst = tmp_path / 'z1.urdf'
+        if not dst.exists():
+            shutil.copy(self.robot_urdf, dst)
+        self.robot_urdf, self.test_num = str(dst), 4
+    monkeypatch.setattr(mod.Parameters, '__init__', init)
+    files = mod.main(['--noises', '5.0', '10.0'])
+    assert len(files) == 8 and all(os.path.isfile(f) for f in files)
+    assert os.path.basename(files[0]) == 'z1_randomizednoise5.0_0.urdf' and os.path.basename(files[-1]) == 'z1_randomizednoise10.0_3.urdf'
+    nominal = nominal_link_inertials(URDF.from_xml_file(str(tmp_path / 'z1.urdf')))
+    for level, seed, fs in ((5.0, 0, files[:4]), (10.0, 4, files[4:])):
+        want = randomized_link_inertials(nominal, level, level, level, 4, seed=seed)
+        for i, f in enumerate(fs):
+            got = nominal_link_inertials(URDF.from_xml_file(f))
+            assert np.array_equal(got['mass'], want['mass'][i]) and np.array_equal(got['com'], want['com'][i])
+            assert np.array_equal(got['inertia6'], want['inertia6'][i])

@@ -224,3 +224,33 @@ def test_plant_step_consistency(orc):
         M, h = o.mass_bias(b, x[b], nominal=False)
         np.testing.assert_allclose(M @ a[b] + h, tau[b], rtol=1e-10, atol=1e-10)
     o.set_plant_inertial(np.tile(md.inertial, (o.B, 1, 1))); o.set_torque_noise(np.zeros((o.B, 5)))
+
+
+def test_flop_tally():
+    """the oracle built with a counting AD scalar (oracle/dual.hpp, -DORC_COUNT_FLOPS) tallies the floating-point
+    operations of one linearisation.  Forward-mode AD (15 directions for the torque rows, second-order duals for the cost) costs about
+    five times the hand-derived analytic recursion the CUDA kernel executes (16 274 flop per stage, profiles/r02_linearize_flops.md)."""
+    import ctypes as C
+    import os
+    import subprocess
+    import oracle.oracle as oo
+    d = os.path.dirname(os.path.abspath(oo.__file__))
+    subprocess.run(['make', '-C', d, '-s', 'liboracle_count.so'], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    lib = C.CDLL(os.path.join(d, 'liboracle_count.so'))
+    lib.orc_flops_get.restype = C.c_ulonglong
+    from tests.common import make_problem, start_states, rollout_guess
+    prob, params, md = make_problem('naive', N=45)
+    saved = oo._LIB
+    oo._LIB = lib
+    try:
+        o = oo.Oracle(prob, 1, 1)
+        x0 = start_states(1, seed=3)
+        xg, ug = rollout_guess(x0, 45, params.dt, seed=4)
+        o.set_guess(xg, ug)
+        lib.orc_flops_reset()
+        o.rti_solve(x0)
+        per_stage = lib.orc_flops_get() / 46.0
+        o.close()
+    finally:
+        oo._LIB = saved
+    assert abs(per_stage - 84382.5) < 1.0, per_stage

@@ -53,11 +53,12 @@ PRESETS = {
 
 
 ALPHA = None                 # set from --alpha (default: config.yaml)
+PRECISION = 'f64'            # set from --precision
 
 
 def workload(controller, N, noise, seed, lo, hi):
     """Synthetic inputs of problems [lo, hi): initial states around the shipped IC, perturbed plants, torque noise."""
-    args = default_args(controller=controller, horizon=N, noise=noise, nn_precision=NN_PRECISION)
+    args = default_args(controller=controller, horizon=N, noise=noise, nn_precision=NN_PRECISION, precision=PRECISION)
     params = Parameters(args, 'z1', rti=True)
     params.N = N
     if ALPHA is not None:
@@ -307,14 +308,16 @@ def run_engine(a):
     #   bytes  what the kernel has to stream per visit in THIS design (solver state resident in HBM), doubles read + written
     #   flop   SURVEY.md section 8(d) / BASELINE.md section 4 dense counts per stage and IPM iteration: factorisation 4 875, one
     #          solve 1 250, inequality condensation 2 475
-    UNITS = {                       # kernel family -> (doubles per visit, flop per visit)
-        'qs_prep': (436 + 265, 2475.0),               # update + residuals + condensation
-        'qs_ric1': (145 + 155 + 100 + 15, 4875.0 + 1250.0),   # factorisation + affine solve (backward + forward)
-        'qs_step0': (270 + 80, 0.0),                  # affine (dlam, dt), products, corrector terms (row products: not in the 8(d) count)
-        'qs_ric2': (155 + 30 + 180 + 50, 2 * 1250.0), # corrector and centering solves in one pass
-        'qs_step1': (316 + 98, 0.0),
-        'qs_step2_centering': (300 + 123, 0.0),
+    sb = 8 if a.precision == 'f64' else 4             # bytes of a value of the storage type (records, directions, factors); the iterate is fp64
+    UNITS = {                       # kernel family -> (fp64 values, storage-type values, flop) per visit
+        'qs_prep': (250, 451, 2475.0),                # update + residuals + condensation: 436 read + 265 written
+        'qs_ric1': (0, 145 + 155 + 100 + 15, 4875.0 + 1250.0),   # factorisation + affine solve (backward + forward)
+        'qs_step0': (122, 228, 0.0),                  # affine (dlam, dt), products, corrector terms (row products: not in the 8(d) count)
+        'qs_ric2': (0, 155 + 30 + 180 + 50, 2 * 1250.0), # corrector and centering solves in one pass
+        'qs_step1': (122, 292, 0.0),
+        'qs_step2_centering': (122, 301, 0.0),
     }
+    UNITS = {k: ((d * 8 + v * sb) / 8.0, fl) for k, (d, v, fl) in UNITS.items()}    # -> (fp64-equivalents per visit, flop)
     visits = float((qp_iter_probe + 1).sum()) * (N + 1)
     table = {}
     for k, (dbl, flop) in UNITS.items():
@@ -326,7 +329,7 @@ def run_engine(a):
         if v is not None:
             row.update({'hbm_gbs': v * dbl * 8 / (ms_k * 1e-3) / 1e9, 'hbm_frac': v * dbl * 8 / (ms_k * 1e-3) / 1e9 / hbm_peak,
                         'fp64_tflops': v * flop / (ms_k * 1e-3) / 1e12, 'fp64_frac': v * flop / (ms_k * 1e-3) / 1e12 / fp64_peak,
-                        'bytes_per_visit': dbl * 8, 'flop_per_visit': flop})
+                        'bytes_per_visit': int(dbl * 8), 'flop_per_visit': flop})
         table[k] = row
     dom = max((k for k in table if 'hbm_gbs' in table[k]), key=lambda k: table[k]['ms_per_solve'])
     dname = {'qs_prep': 'qs_prep_coop_kernel / qs_prep_kernel', 'qs_ric1': 'qs_ric1x_kernel / qs_ric1t_kernel', 'qs_ric2': 'qs_ric2_kernel / qs_ric2t_kernel',
@@ -458,7 +461,8 @@ LINEARIZE_FLOP_SOURCE = 'executed FP64 instructions of linearize_kernel under nc
 
 
 def main_qp_bytes(N):
-    return (N + 1) * (abi.REC + 3 * 120 + 25 + 345 + 46 + 8 + 4) * 8     # per problem: records, iterate x2, step, solver block, products, partials (qp_split.cuh)
+    sb = 8 if PRECISION == 'f64' else 4
+    return (N + 1) * ((2 * 120 + 8 + 4) * 8 + (abi.REC + 120 + 25 + 345 + 46) * sb)     # per problem: iterate x2, partials (fp64); records, step, solver block, products (storage type)
 
 
 def main():
@@ -491,9 +495,10 @@ def main():
             setattr(a, key, pre[key])
     if a.nn_precision is None:
         a.nn_precision = pre.get('nn_precision', 'strict')
-    global NN_PRECISION, ALPHA
+    global NN_PRECISION, ALPHA, PRECISION
     NN_PRECISION = a.nn_precision
     ALPHA = a.alpha
+    PRECISION = a.precision
     if a.warmup < 3 and a.impl == 'engine':
         a.warmup = 3
     if a.impl == 'reference':

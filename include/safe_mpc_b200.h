@@ -74,6 +74,8 @@ enum {
 
 enum { SMPC_NN_STRICT = 0, SMPC_NN_TF32X3 = 1 };
 
+enum { SMPC_PREC_F64 = 0, SMPC_PREC_F32 = 1 };
+
 enum { SMPC_COST_ZERO = 0, SMPC_COST_EXT = 1, SMPC_COST_NLS = 2 };
 
 /*
@@ -133,7 +135,11 @@ typedef struct smpc_problem {
                                     reference's libtorch call, safe_set.py:76-94), see csrc/mlp_tc.cu              */
   int32_t qp_keep_slots;         /* 1: never compact the solver's slots during a solve, so that smpc_get_lin / smpc_get_qp stay
                                     available for every batch size (tests, the merit line search of the guess generator); 0: default */
-  int32_t reserved_i[1];
+  int32_t precision;             /* SMPC_PREC_F64 (default): the QP solver state is stored in fp64, results agree with the fp64 reference path
+                                    to 1e-6; SMPC_PREC_F32: everything a solve streams from HBM (stage records, search directions, condensed
+                                    matrices, Riccati factors) is stored in fp32, the iterate and all arithmetic stay fp64 -- 40 % less HBM
+                                    traffic per interior-point iteration, trajectories within 1e-3 relative (BASELINE.json north_star, fp32
+                                    mode); pair it with qp_tol_* = 1e-5 / 1e-6 (the fp32 search direction bottoms the residuals out near 1e-5) */
   /* ---- scalars ---- */
   double dt;                     /* config.yaml:7                                                 */
   double q_weight, r_weight;     /* config.yaml:35,39                                             */

@@ -31,6 +31,7 @@ CTRL = {'naive': 0, 'zerovel': 1, 'st': 2, 'stwa': 3, 'htwa': 4, 'receding': 5, 
         'constraint_everywhere': 7, 'backup': 8, 'parallel': 9}
 NN_NONE, NN_TERMINAL, NN_RECEDING, NN_EVERYWHERE, NN_PARALLEL = 0, 1, 2, 3, 4
 NN_PRECISION = {'strict': 0, 'tf32x3': 1}
+PRECISION = {'f64': 0, 'f32': 1}
 COST_ZERO, COST_EXT, COST_NLS = 0, 1, 2
 STATE_FAILS, STATE_R, STATE_STATUS, STATE_QP_ITER, STATE_QP_STATUS = 0, 1, 2, 3, 4
 
@@ -41,7 +42,7 @@ class Problem(C.Structure):
         ('controller', C.c_int32), ('nn_rows', C.c_int32), ('nn_terminal_soft', C.c_int32),
         ('stage0_collision_rows', C.c_int32), ('cost_type', C.c_int32), ('abort_flag', C.c_int32),
         ('qp_iter_max', C.c_int32), ('lm_scale_dt', C.c_int32), ('qp_cond_pred_corr', C.c_int32),
-        ('nn_precision', C.c_int32), ('qp_keep_slots', C.c_int32), ('reserved_i', C.c_int32 * 1),
+        ('nn_precision', C.c_int32), ('qp_keep_slots', C.c_int32), ('precision', C.c_int32),
         ('dt', C.c_double), ('q_weight', C.c_double), ('r_weight', C.c_double), ('lm', C.c_double),
         ('alpha', C.c_double), ('eps', C.c_double), ('slack_penalty_e', C.c_double),
         ('tol_x', C.c_double), ('tol_tau', C.c_double), ('tol_obs', C.c_double), ('tol_safe', C.c_double),

@@ -37,7 +37,10 @@ struct smpc_handle {
   // state
   double *xg = nullptr, *ug = nullptr, *xt = nullptr, *ut = nullptr, *plant_inertial = nullptr, *tau_noise = nullptr,
          *x_viable = nullptr, *nn11 = nullptr, *scan11 = nullptr, *qp_res = nullptr, *x_in = nullptr, *u_out = nullptr;
-  QpSolver* qp = nullptr;           // split interior-point solver: tile-interleaved records + solver state
+  // split interior-point solver: tile-interleaved records + solver state, in the storage flavour the handle was created with
+  // (smpc_problem_t::precision): exactly one of the two is set
+  f64::QpSolver* qp = nullptr;
+  f32::QpSolver* qpf = nullptr;
   const uint8_t* act_last = nullptr;
   bool solved = false;
   int32_t *fails = nullptr, *r = nullptr, *status = nullptr, *qp_iter = nullptr, *qp_status = nullptr, *cur_step = nullptr;
@@ -68,6 +71,9 @@ struct smpc_sim {
 };
 
 namespace {
+
+// call a QP-solver function of the handle's storage flavour
+#define QPCALL(h, fn, ...) ((h)->qpf ? f32::fn((h)->qpf, ##__VA_ARGS__) : f64::fn((h)->qp, ##__VA_ARGS__))
 
 int fail(smpc_handle* h, int code, const char* what, cudaError_t e = cudaSuccess) {
   char buf[512];
@@ -149,9 +155,10 @@ int solve_pipeline(smpc_handle* h, const double* x0_dev, const uint8_t* act) {
     const int mode = h->P.nn_rows == SMPC_NN_TERMINAL ? ROWS_TERMINAL : (h->P.nn_rows == SMPC_NN_EVERYWHERE ? ROWS_ALL : (h->P.nn_rows == SMPC_NN_PARALLEL ? ROWS_CAND : ROWS_RECEDING));
     run_mlp(h, B, N, mode, 0, h->xg, act, nullptr, h->nn11, true);
   }
-  launch_linearize(c, h->dP, B, N, h->xg, h->ug, h->P.nn_rows == SMPC_NN_PARALLEL ? h->cand : h->r, act, h->nn11, qp_rec(h->qp));
+  launch_linearize(c, h->dP, B, N, h->xg, h->ug, h->P.nn_rows == SMPC_NN_PARALLEL ? h->cand : h->r, act, h->nn11, QPCALL(h, qp_rec), h->qpf != nullptr);
   if (h->timed) cudaEventRecord(h->ev[1], h->stream);
-  cudaError_t qe = launch_qp_solve(c, h->dP, h->qp, x0_dev, h->r, act, h->xt, h->ut, h->status, h->qp_iter, h->qp_status, h->qp_res);
+  cudaError_t qe = h->qpf ? f32::launch_qp_solve(c, h->dP, h->qpf, x0_dev, h->r, act, h->xt, h->ut, h->status, h->qp_iter, h->qp_status, h->qp_res)
+                          : f64::launch_qp_solve(c, h->dP, h->qp, x0_dev, h->r, act, h->xt, h->ut, h->status, h->qp_iter, h->qp_status, h->qp_res);
   if (qe != cudaSuccess) return fail(h, SMPC_ERR_CUDA, "QP solve", qe);
   h->solved = true;
   if (h->timed) cudaEventRecord(h->ev[2], h->stream);
@@ -278,6 +285,9 @@ int smpc_create(const smpc_problem_t* prob, int32_t batch, int32_t device, smpc_
       h->wtc = MlpTcWeights{h->w.W1, h->w.b1, h->w.b2, h->w.b3, h->w.W4, h->w.b4, h->dWtc, h->dWtc2};
     }
   }
+  if (prob->precision != SMPC_PREC_F64 && prob->precision != SMPC_PREC_F32) {
+    fail(nullptr, SMPC_ERR_ARG, "smpc_create: unknown precision"); smpc_destroy(h); return SMPC_ERR_ARG;
+  }
   if (prob->nn_precision != SMPC_NN_STRICT && prob->nn_precision != SMPC_NN_TF32X3) {
     fail(nullptr, SMPC_ERR_ARG, "smpc_create: unknown nn_precision"); smpc_destroy(h); return SMPC_ERR_ARG;
   }
@@ -304,8 +314,9 @@ int smpc_create(const smpc_problem_t* prob, int32_t batch, int32_t device, smpc_
   }
   {
     cudaError_t qe = cudaSuccess;
-    h->qp = qp_create(B, N, prob->qp_iter_max, prob->qp_keep_slots != 0, h->stream, &qe);
-    if (!h->qp) { fail(nullptr, SMPC_ERR_CUDA, "qp_create", qe); smpc_destroy(h); return SMPC_ERR_CUDA; }
+    if (prob->precision == SMPC_PREC_F32) h->qpf = f32::qp_create(B, N, prob->qp_iter_max, prob->qp_keep_slots != 0, h->stream, &qe);
+    else h->qp = f64::qp_create(B, N, prob->qp_iter_max, prob->qp_keep_slots != 0, h->stream, &qe);
+    if (!h->qp && !h->qpf) { fail(nullptr, SMPC_ERR_CUDA, "qp_create", qe); smpc_destroy(h); return SMPC_ERR_CUDA; }
   }
   CKC(dalloc(h, &h->qp_res, (size_t)B * 5));
   CKC(dalloc(h, &h->x_in, (size_t)B * NX)); CKC(dalloc(h, &h->u_out, (size_t)B * NU));
@@ -336,7 +347,8 @@ void smpc_destroy(smpc_handle_t* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->h_par_open) cudaFreeHost(h->h_par_open);
   for (void* p : h->allocs) cudaFree(p);
-  qp_destroy(h->qp);
+  f64::qp_destroy(h->qp);
+  f32::qp_destroy(h->qpf);
   if (h->stage) cudaFree(h->stage);
   for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -472,7 +484,7 @@ int smpc_nn_constraint(smpc_handle_t* h, int32_t n, const double* x, double* cva
 }
 
 static int slots_intact(smpc_handle_t* h, const char* what) {
-  if (qp_compactions(h->qp) == 0) return 0;
+  if (QPCALL(h, qp_compactions) == 0) return 0;
   char buf[256];
   snprintf(buf, sizeof buf, "%s: the last solve compacted its slots (the stage records / iterates of the finished problems were reused); "
                             "create the handle with smpc_problem_t::qp_keep_slots = 1 (or SMPC_QP_COMPACT=0) to keep them", what);
@@ -482,9 +494,10 @@ static int slots_intact(smpc_handle_t* h, const char* what) {
 int smpc_get_lin(smpc_handle_t* h, double* lin, int32_t mem) {
   if (int rc0 = slots_intact(h, "smpc_get_lin")) return rc0;
   const size_t bytes = sizeof(double) * h->B * (h->N + 1) * REC;
-  if (mem == SMPC_DEVICE) { launch_rec_untile(h->ctx(), h->qp, lin); return check_launch(h, "get_lin"); }
+  if (mem == SMPC_DEVICE) { if (h->qpf) f32::launch_rec_untile(h->ctx(), h->qpf, lin); else f64::launch_rec_untile(h->ctx(), h->qp, lin); return check_launch(h, "get_lin"); }
   int rc = stage_reserve(h, bytes); if (rc) return rc;
-  launch_rec_untile(h->ctx(), h->qp, (double*)h->stage);      // records are kept tile-interleaved; hand them back as [B][N+1][REC]
+  if (h->qpf) f32::launch_rec_untile(h->ctx(), h->qpf, (double*)h->stage);      // records are kept tile-interleaved; hand them back as [B][N+1][REC]
+  else f64::launch_rec_untile(h->ctx(), h->qp, (double*)h->stage);
   rc = check_launch(h, "get_lin"); if (rc) return rc;
   return copy_out(h, lin, h->stage, bytes, mem);
 }
@@ -497,7 +510,8 @@ int smpc_get_qp(smpc_handle_t* h, double* dz, double* pi, double* lam, double* t
   int rc = stage_reserve(h, b1 + b2 + 2 * b3); if (rc) return rc;
   char* s = (char*)h->stage;
   // the final iterate of every problem stays in the solver's ping-pong buffers until the next solve
-  launch_dump_qp(h->ctx(), h->dP, h->qp, (double*)s, (double*)(s + b1), (double*)(s + b1 + b2), (double*)(s + b1 + b2 + b3));
+  if (h->qpf) f32::launch_dump_qp(h->ctx(), h->dP, h->qpf, (double*)s, (double*)(s + b1), (double*)(s + b1 + b2), (double*)(s + b1 + b2 + b3));
+  else f64::launch_dump_qp(h->ctx(), h->dP, h->qp, (double*)s, (double*)(s + b1), (double*)(s + b1 + b2), (double*)(s + b1 + b2 + b3));
   rc = check_launch(h, "get_qp"); if (rc) return rc;
   rc = copy_out(h, dz, s, b1, mem); if (rc) return rc;
   rc = copy_out(h, pi, s + b1, b2, mem); if (rc) return rc;
@@ -528,11 +542,11 @@ int smpc_set_state_i32(smpc_handle_t* h, int32_t f, const int32_t* in, int32_t m
 int smpc_get_qp_residuals(smpc_handle_t* h, double* res5, int32_t mem) { return copy_out(h, res5, h->qp_res, sizeof(double) * h->B * 5, mem); }
 int smpc_get_x_viable(smpc_handle_t* h, double* xv, int32_t mem) { return copy_out(h, xv, h->x_viable, sizeof(double) * h->B * NX, mem); }
 
-int smpc_set_profiling(smpc_handle_t* h, int32_t enable) { qp_set_profiling(h->qp, enable != 0); return SMPC_OK; }
+int smpc_set_profiling(smpc_handle_t* h, int32_t enable) { QPCALL(h, qp_set_profiling, enable != 0); return SMPC_OK; }
 int smpc_get_profile(smpc_handle_t* h, double* ms, int32_t* count, double* span_ms, int32_t* iterations) {
   if (!ms || !count || !span_ms || !iterations) return fail(h, SMPC_ERR_ARG, "smpc_get_profile: NULL output");
-  qp_get_profile(h->qp, ms, count, span_ms);
-  *iterations = qp_last_iterations(h->qp);
+  QPCALL(h, qp_get_profile, ms, count, span_ms);
+  *iterations = QPCALL(h, qp_last_iterations);
   return SMPC_OK;
 }
 int smpc_get_times(smpc_handle_t* h, double* out7) {

@@ -328,8 +328,10 @@ SMPC_HD bool collision_free(const smpc_problem_t& P, const double* x) {         
 
 // one stage of the linearisation -> stage record (viability row value/gradient are supplied by the MLP kernel);
 // `rs` = stride between consecutive record fields (32 in the device layout [tile][stage][field][32 problems])
+// R: element type of the record array (double, or float for the fp32-storage flavour of the QP solver: values are rounded on store)
+template <class R>
 SMPC_HD void linearize_stage(const smpc_problem_t& P, int k, const double* x, const double* u, const double* xnext,
-                             bool has_nn, bool gate_on, const double* nn11, double* rec, int rs = 1) {
+                             bool has_nn, bool gate_on, const double* nn11, R* rec, int rs = 1) {
   const int N = P.N;
   const bool term = (k == N);
   const double s = term ? 1.0 : P.dt;

@@ -66,8 +66,9 @@ void mlp_tc2_pack(const float* W2, const float* W3, float* out);
 cudaError_t mlp_tc2_prepare();
 void launch_mlp_tc2(const LaunchCtx& c, const smpc_problem_t* dP, const MlpTcWeights& w, int n_sm, int B, int N, int rows_mode, int n_flat,
                     const double* xsrc, const int32_t* r, const uint8_t* act, const uint8_t* need, double* out11, bool want_grad);
+// lin: tile-interleaved record array of the QP solver, double or (lin_f32) float
 void launch_linearize(const LaunchCtx& c, const smpc_problem_t* dP, int B, int N, const double* xg, const double* ug,
-                      const int32_t* r, const uint8_t* act, const double* nn11, double* lin);
+                      const int32_t* r, const uint8_t* act, const double* nn11, void* lin, bool lin_f32);
 void launch_ctrl_post1(const LaunchCtx& c, const smpc_problem_t* dP, int B, int N, const uint8_t* act, const double* xg, const double* ug,
                        const double* xt, int32_t* status, int32_t* fails, int32_t* r, double* x_viable, uint8_t* need_scan,
                        uint8_t* abort_flag, double* u_out);
@@ -104,23 +105,30 @@ void launch_sim_post(const LaunchCtx& c, const SimDev& s, const smpc_problem_t* 
                      const double* bk_ut, const double* inertial, const double* noise, const int32_t* qp_iter_bk);
 void launch_sim_outcome(const LaunchCtx& c, const SimDev& s, const smpc_problem_t* dP, int32_t* out);
 
-// qp.cu -- split interior-point solver (qp_split.cuh); lives in the storage-flavour namespace of qp_split.cuh
+// qp.cu -- split interior-point solver (qp_split.cuh).  The library holds it twice: qp.cu (fp64 storage, namespace smpc::f64) and
+// qp_f32.cu (the same source with QS_REAL = float, namespace smpc::f32); the flavour of this translation unit is an inline namespace.
+#define SMPC_QP_API                                                                                                                       \
+  struct QpSolver;                                                                                                                        \
+  size_t qp_bytes(int B, int N);                                                                                                          \
+  QpSolver* qp_create(int B, int N, int iter_max, bool keep_slots, cudaStream_t stream, cudaError_t* err);                                \
+  void qp_destroy(QpSolver* s);                                                                                                           \
+  void* qp_rec(QpSolver* s);               /* tile-interleaved stage records [T][N+1][REC][32] the linearisation writes (storage type) */ \
+  int qp_groups(const QpSolver* s);        /* tile groups solved concurrently */                                                          \
+  int qp_last_iterations(const QpSolver* s);                                                                                              \
+  int qp_compactions(const QpSolver* s);   /* compactions of the slots during the last solve (> 0: per-slot dumps are gone) */            \
+  void qp_set_profiling(QpSolver* s, bool on);                                                                                            \
+  void qp_get_profile(const QpSolver* s, double* ms, int32_t* n, double* span_ms);                                                        \
+  /* one batched solve; reads the records of qp_rec(); problems with act == 0 are skipped and keep their outputs */                      \
+  cudaError_t launch_qp_solve(const LaunchCtx& c, const smpc_problem_t* dP, QpSolver* s, const double* x0, const int32_t* r,              \
+                              const uint8_t* act, double* xt, double* ut, int32_t* status, int32_t* qp_iter, int32_t* qp_status,          \
+                              double* qp_res);                                                                                            \
+  void launch_rec_untile(const LaunchCtx& c, QpSolver* s, double* out);                                                                   \
+  void launch_dump_qp(const LaunchCtx& c, const smpc_problem_t* dP, QpSolver* s, double* dz, double* pi, double* lam, double* t);
 inline namespace QS_FLAVOUR {
-struct QpSolver;
-size_t qp_bytes(int B, int N);
-QpSolver* qp_create(int B, int N, int iter_max, bool keep_slots, cudaStream_t stream, cudaError_t* err);
-void qp_destroy(QpSolver* s);
-double* qp_rec(QpSolver* s);                  // tile-interleaved stage records [T][N+1][REC][32] the linearisation writes
-int qp_groups(const QpSolver* s);              // tile groups solved concurrently
-int qp_last_iterations(const QpSolver* s);
-int qp_compactions(const QpSolver* s);          // compactions of the slots during the last solve (> 0: per-slot dumps are gone)
-void qp_set_profiling(QpSolver* s, bool on);
-void qp_get_profile(const QpSolver* s, double* ms, int32_t* n, double* span_ms);    // IPM iterations of the slowest problem of the last solve
-// one batched solve; reads the records of qp_rec(); problems with act == 0 are skipped and keep their outputs
-cudaError_t launch_qp_solve(const LaunchCtx& c, const smpc_problem_t* dP, QpSolver* s, const double* x0, const int32_t* r, const uint8_t* act,
-                            double* xt, double* ut, int32_t* status, int32_t* qp_iter, int32_t* qp_status, double* qp_res);
-void launch_rec_untile(const LaunchCtx& c, QpSolver* s, double* out);
-void launch_dump_qp(const LaunchCtx& c, const smpc_problem_t* dP, QpSolver* s, double* dz, double* pi, double* lam, double* t);
+SMPC_QP_API
 }  // inline namespace QS_FLAVOUR
+namespace QS_OTHER_FLAVOUR {
+SMPC_QP_API
+}
 
 }  // namespace smpc

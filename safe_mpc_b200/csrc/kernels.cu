@@ -182,9 +182,10 @@ void launch_mlp(const LaunchCtx& c, const smpc_problem_t* dP, const MlpWeights& 
 // ----------------------------------------------------------------------------------------------------------------
 // Linearisation of every (problem, stage): one thread each (dev_model.cuh: linearize_stage)
 // ----------------------------------------------------------------------------------------------------------------
+template <class R>
 __global__ void __launch_bounds__(128)
 linearize_kernel(const smpc_problem_t* __restrict__ dP, int B, int N, const double* __restrict__ xg, const double* __restrict__ ug,
-                 const int32_t* __restrict__ r, const uint8_t* __restrict__ act, const double* __restrict__ nn11, double* lin) {
+                 const int32_t* __restrict__ r, const uint8_t* __restrict__ act, const double* __restrict__ nn11, R* lin) {
   // records are written tile-interleaved, [tile][stage][field][lane] (qp_split.cuh): thread = lane of warp (tile, stage),
   // so every field store of a warp is one contiguous 256-byte segment
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -204,13 +205,14 @@ linearize_kernel(const smpc_problem_t* __restrict__ dP, int B, int N, const doub
   bool gate = true;
   if (P.nn_rows == SMPC_NN_RECEDING && k < N) gate = (k == r[b]);      // controller.py:452-469
   if (P.nn_rows == SMPC_NN_PARALLEL) gate = (k == r[b]);               // controller.py:578-588 (r = candidate node of this solve)
-  double* rec = lin + qs_blk(tile, N, k, REC, lane);
+  R* rec = lin + qs_blk(tile, N, k, REC, lane);
   linearize_stage(P, k, x, u, xn, has_nn, gate, nn11 + ((size_t)b * (N + 1) + k) * NN_OUT, rec, TL);
 }
 void launch_linearize(const LaunchCtx& c, const smpc_problem_t* dP, int B, int N, const double* xg, const double* ug, const int32_t* r,
-                      const uint8_t* act, const double* nn11, double* lin) {
+                      const uint8_t* act, const double* nn11, void* lin, bool lin_f32) {
   const int n = ((B + TL - 1) / TL) * (N + 1) * TL;
-  linearize_kernel<<<GRID1D(n, 128), 128, 0, c.stream>>>(dP, B, N, xg, ug, r, act, nn11, lin);
+  if (lin_f32) linearize_kernel<float><<<GRID1D(n, 128), 128, 0, c.stream>>>(dP, B, N, xg, ug, r, act, nn11, static_cast<float*>(lin));
+  else linearize_kernel<double><<<GRID1D(n, 128), 128, 0, c.stream>>>(dP, B, N, xg, ug, r, act, nn11, static_cast<double*>(lin));
   ++*c.launches;
 }
 

@@ -67,7 +67,11 @@ __global__ void __launch_bounds__(32 * PREP_WARPS, QS_PREP_MINB) qs_prep_kernel(
 constexpr int PC_REC0 = SMPC_REC_X;                       // first staged record field (the controls of the guess are not needed)
 constexpr int PC_NREC = 180;                              // staged record fields [5, 185)
 constexpr int PC_WARPS = 4;
-constexpr size_t PC_SMEM = sizeof(double) * (PC_NREC + 2 * NIT) * TL + 16;
+constexpr int PC_NPART = 6;                               // residual-norm partials per warp
+// staged: previous iterate (fp64), stage record and step (storage type); the fp32 flavour keeps the fp64 partials of the warps in an array of
+// their own (the fp64 flavour parks them in consumed slots of the staged step, as before: two CTAs of 107.5 KB per SM)
+constexpr size_t PC_SMEM = sizeof(double) * NIT * TL + sizeof(qs_real) * (PC_NREC + NIT) * TL +
+                           (sizeof(qs_real) == 8 ? 0 : sizeof(double) * PC_WARPS * PC_NPART * TL) + 16;
 static_assert(PC_REC0 + PC_NREC > SMPC_REC_HQ && PC_REC0 + PC_NREC <= SMPC_REC, "staged record range");
 
 __device__ __forceinline__ void pc_row_out(double* s_it, int sl, double nu, double gam, double G) {
@@ -83,34 +87,45 @@ __global__ void __launch_bounds__(32 * PC_WARPS, 2) qs_prep_coop_kernel(const sm
   const int32_t* pi = q.pi + qs_pb(tile, NPI, lane);
   const bool on = QF(pi, J_ACT) != 0;
   if (!__any_sync(0xffffffffu, on)) return;               // (same decision in the four warps: same tile)
-  double* g_rec_blk = const_cast<double*>(q.rec) + qs_blk(tile, N, k, REC, 0);
+  const qs_real* g_rec_blk = q.rec + qs_blk(tile, N, k, REC, 0);
   const double* g_it_blk = q.it[(kk & 1) ^ 1] + qs_blk(tile, N, k, NIT, 0);
-  const double* g_st_blk = q.st + qs_blk(tile, N, k, NIT, 0);
-  double* sm_rec = pc_sm;
-  double* sm_it = sm_rec + (size_t)PC_NREC * TL;
-  double* sm_st = sm_it + (size_t)NIT * TL;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(sm_st + (size_t)NIT * TL);
+  const qs_real* g_st_blk = q.st + qs_blk(tile, N, k, NIT, 0);
+  double* sm_it = pc_sm;
+  qs_real* sm_rec = reinterpret_cast<qs_real*>(sm_it + (size_t)NIT * TL);
+  qs_real* sm_st = sm_rec + (size_t)PC_NREC * TL;
+  double* sm_part = reinterpret_cast<double*>(sm_st + (size_t)NIT * TL);           // fp32 flavour only
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sm_part + (sizeof(qs_real) == 8 ? 0 : (size_t)PC_WARPS * PC_NPART * TL));
   if (threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    const uint32_t nb_rec = PC_NREC * TL * 8, nb_it = NIT * TL * 8;
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(nb_rec + 2 * nb_it) : "memory");
+    const uint32_t nb_rec = PC_NREC * TL * sizeof(qs_real), nb_it = NIT * TL * 8, nb_st = NIT * TL * sizeof(qs_real);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(nb_rec + nb_it + nb_st) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sm_rec)),
                  "l"(g_rec_blk + (size_t)PC_REC0 * TL), "r"(nb_rec), "r"(smem_u32(bar)) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sm_it)),
                  "l"(g_it_blk), "r"(nb_it), "r"(smem_u32(bar)) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sm_st)),
-                 "l"(g_st_blk), "r"(nb_it), "r"(smem_u32(bar)) : "memory");
+                 "l"(g_st_blk), "r"(nb_st), "r"(smem_u32(bar)) : "memory");
   }
   // lane views: field f of the record at rs[f * TL] (valid for PC_REC0 <= f < PC_REC0 + PC_NREC)
-  const double* rs = sm_rec - (size_t)PC_REC0 * TL + lane;
+  const qs_real* rs = sm_rec - (size_t)PC_REC0 * TL + lane;
   double* s_it = sm_it + lane;
-  double* s_st = sm_st + lane;
+  const qs_real* s_st = sm_st + lane;
+  // partial j of warp w: fp64 flavour -> the consumed step slots of the warp's first rows (warp 0: box 0-2; 1: box 4-6; 2: torque 0-2;
+  // 3: capsule 0-2), fp32 flavour -> sm_part
+  auto part = [&](int w, int j) -> double& {
+    if (sizeof(qs_real) == 8) {
+      const int s0 = w == 0 ? 0 : (w == 1 ? 4 : (w == 2 ? 10 : 15));
+      const int slot = (j & 1) ? I_LAM + QNR + s0 + (j >> 1) : I_LAM + s0 + (j >> 1);
+      return *reinterpret_cast<double*>(const_cast<qs_real*>(s_st) + (size_t)slot * TL);
+    }
+    return sm_part[(size_t)(w * PC_NPART + j) * TL + lane];
+  };
   const double* pd = q.pd + qs_pb(tile, NPD, lane);
   const double a = QF(pd, D_STEP);
   const int rrec = QF(pi, J_R);
   double* ito = q.it[kk & 1] + qs_blk(tile, N, k, NIT, lane);
-  double* hc = q.sb + qs_blk(tile, N, k, NHC, lane);
+  qs_real* hc = q.sb + qs_blk(tile, N, k, NHC, lane);
   const StageFlags F = qs_flags(P, k);
   const double lam_min = 1e-16, t_min = 1e-16, reg = P.qp_reg_prim;
   const double dt = P.dt, a2 = 0.5 * P.dt * P.dt;
@@ -122,7 +137,7 @@ __global__ void __launch_bounds__(32 * PC_WARPS, 2) qs_prep_coop_kernel(const sm
     for (int j = 0; j < 10; ++j) { pqn[j] = 0.0; znx[j] = 0.0; }
     if (k < N) {
       const double* itn = q.it[(kk & 1) ^ 1] + qs_blk(tile, N, k + 1, NIT, lane);
-      const double* stn = q.st + qs_blk(tile, N, k + 1, NIT, lane);
+      const qs_real* stn = q.st + qs_blk(tile, N, k + 1, NIT, lane);
 #pragma unroll
       for (int j = 0; j < 10; ++j) {
         pqn[j] = QF(itn, I_PIM + j) + a * QF(stn, I_PIM + j);
@@ -294,10 +309,9 @@ __global__ void __launch_bounds__(32 * PC_WARPS, 2) qs_prep_coop_kernel(const sm
   }
   // residual-norm partials of this warp -> consumed step slots of its first rows (warp 0: box 0-2; 1: box 4-6; 2: torque 0-2; 3: capsule 0-2)
   {
-    const int s0 = wi == 0 ? 0 : (wi == 1 ? 4 : (wi == 2 ? 10 : 15));
-    QF(s_st, I_LAM + s0) = nr.chk; QF(s_st, I_LAM + QNR + s0) = nr.nm; QF(s_st, I_LAM + s0 + 1) = nr.nd;
-    QF(s_st, I_LAM + QNR + s0 + 1) = nr.ng; QF(s_st, I_LAM + s0 + 2) = (double)nr.cnt;
-    QF(s_st, I_LAM + QNR + s0 + 2) = nr.mu;
+    part(wi, 0) = nr.chk; part(wi, 1) = nr.nm; part(wi, 2) = nr.nd;
+    part(wi, 3) = nr.ng; part(wi, 4) = (double)nr.cnt;
+    part(wi, 5) = nr.mu;
   }
   __syncthreads();
 
@@ -336,13 +350,12 @@ __global__ void __launch_bounds__(32 * PC_WARPS, 2) qs_prep_coop_kernel(const sm
     double ng = 0.0, nb = nr.nb, nd = 0.0, nm = 0.0, mu = 0.0, chk = 0.0, cnt = 0.0;
 #pragma unroll
     for (int w = 0; w < PC_WARPS; ++w) {
-      const int s0 = w == 0 ? 0 : (w == 1 ? 4 : (w == 2 ? 10 : 15));
-      chk += QF(s_st, I_LAM + s0);
-      nm = fmax(nm, QF(s_st, I_LAM + QNR + s0)); nd = fmax(nd, QF(s_st, I_LAM + s0 + 1));
-      ng = fmax(ng, QF(s_st, I_LAM + QNR + s0 + 1)); cnt += QF(s_st, I_LAM + s0 + 2);
+      chk += part(w, 0);
+      nm = fmax(nm, part(w, 1)); nd = fmax(nd, part(w, 2));
+      ng = fmax(ng, part(w, 3)); cnt += part(w, 4);
     }
     // mu: the four partial sums in warp order, as qs_prep forms them (bit-identical results whichever form serves a problem)
-    mu = ((QF(s_st, I_LAM + QNR + 2) + QF(s_st, I_LAM + QNR + 6)) + QF(s_st, I_LAM + QNR + 12)) + QF(s_st, I_LAM + QNR + 17);
+    mu = ((part(0, 5) + part(1, 5)) + part(2, 5)) + part(3, 5);
 #pragma unroll
     for (int i = 0; i < 15; ++i) { ng = fmax(ng, fabs(rg[i])); chk += rg[i]; if (on) QF(hc, H_GA + i) = rg[i] + gd[i]; }
     if (on) {
@@ -495,7 +508,7 @@ __global__ void __launch_bounds__(CM_THREADS) qs_compact_move_kernel(QsBufs q, c
 // Device warp policy of the Riccati sweeps: two staging buffers of `nfb` fields x 32 lanes in shared memory, filled by
 // TMA 1-D bulk copies (cp.async.bulk global -> shared, mbarrier completion) that lane 0 issues one stage ahead.
 struct TmaStage {
-  double* sm;
+  qs_real* sm;
   uint64_t* bar;
   uint32_t phase[2];
   int ln, nfb;
@@ -503,7 +516,7 @@ struct TmaStage {
   __device__ __forceinline__ int nbuf() const { return QS_RIC_NBUF; }
   __device__ __forceinline__ bool any(bool v) const { return __any_sync(0xffffffffu, v) != 0; }
   __device__ __forceinline__ void sync() const { __syncwarp(); }
-  __device__ __forceinline__ double* buf(int b) const { return sm + (size_t)b * nfb * TL + ln; }
+  __device__ __forceinline__ qs_real* buf(int b) const { return sm + (size_t)b * nfb * TL + ln; }
   __device__ __forceinline__ void init() {
     phase[0] = phase[1] = 0;
     if (ln == 0) {
@@ -515,13 +528,13 @@ struct TmaStage {
   }
   __device__ __forceinline__ void fetch_begin(int b, int nfields) {
     if (ln == 0)
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar + b)), "r"(nfields * TL * 8) : "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar + b)), "r"((uint32_t)(nfields * TL * sizeof(qs_real))) : "memory");
   }
-  __device__ __forceinline__ void fetch(int b, int dst_field, const double* gblock, int src_field, int nfields) {
+  __device__ __forceinline__ void fetch(int b, int dst_field, const qs_real* gblock, int src_field, int nfields) {
     if (ln == 0)
       asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                        smem_u32(sm + ((size_t)b * nfb + dst_field) * TL)),
-                   "l"(gblock + (size_t)src_field * TL), "r"(nfields * TL * 8), "r"(smem_u32(bar + b))
+                   "l"(gblock + (size_t)src_field * TL), "r"((uint32_t)(nfields * TL * sizeof(qs_real))), "r"(smem_u32(bar + b))
                    : "memory");
   }
   __device__ __forceinline__ void wait(int b) {
@@ -533,23 +546,23 @@ struct TmaStage {
     phase[b] = par ^ 1u;
   }
   // hint: start moving a field range of a stage block towards L2
-  __device__ __forceinline__ void prefetch(const double* gblock, int src_field, int nfields) const {
+  __device__ __forceinline__ void prefetch(const qs_real* gblock, int src_field, int nfields) const {
     if (ln == 0)
-      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gblock + (size_t)src_field * TL), "r"(nfields * TL * 8) : "memory");
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gblock + (size_t)src_field * TL), "r"((uint32_t)(nfields * TL * sizeof(qs_real))) : "memory");
   }
   // this lane's global stores become visible to bulk copies issued after the next warp barrier
   __device__ __forceinline__ void publish() const { asm volatile("fence.proxy.async;" ::: "memory"); }
 };
 
-constexpr size_t RIC1_SMEM = sizeof(double) * (QS_RIC_NBUF * RIC1_STAGE_FIELDS + 65) * TL + 16;
-constexpr size_t RIC2_SMEM = sizeof(double) * (QS_RIC_NBUF * RIC2_STAGE_FIELDS) * TL + 16;
+constexpr size_t RIC1_SMEM = sizeof(double) * 65 * TL + sizeof(qs_real) * (QS_RIC_NBUF * RIC1_STAGE_FIELDS) * TL + 16;   // P scratch (fp64) + staging
+constexpr size_t RIC2_SMEM = sizeof(qs_real) * (QS_RIC_NBUF * RIC2_STAGE_FIELDS) * TL + 16;
 
 __global__ void __launch_bounds__(32) qs_ric1_kernel(const smpc_problem_t* __restrict__ dP, QsBufs q) {
   extern __shared__ __align__(128) double smem[];
   TmaStage w;
-  w.sm = smem; w.nfb = RIC1_STAGE_FIELDS; w.ln = threadIdx.x;
-  double* psm = smem + (size_t)QS_RIC_NBUF * RIC1_STAGE_FIELDS * TL;
-  w.bar = reinterpret_cast<uint64_t*>(psm + 65 * TL);
+  double* psm = smem;                                        // P_{k+1}, p_{k+1}: on-chip only, fp64 in both flavours
+  w.sm = reinterpret_cast<qs_real*>(psm + 65 * TL); w.nfb = RIC1_STAGE_FIELDS; w.ln = threadIdx.x;
+  w.bar = reinterpret_cast<uint64_t*>(w.sm + (size_t)QS_RIC_NBUF * RIC1_STAGE_FIELDS * TL);
   w.init();
   qs_ric1(*dP, q, blockIdx.x, w, psm + threadIdx.x);
 }
@@ -571,13 +584,18 @@ constexpr int R1X_FIELDS = RIC1_STAGE_FIELDS + 65 + R1X_XF;                    /
 constexpr int R1X_FWD = B_WV - B_RB;                                           // forward stage fetch: RB LP T (100 fields)
 constexpr int R1X_FWD1 = 136;                                                  // field offset of the second forward buffer
 static_assert(R1X_FWD1 >= R1X_FWD && R1X_FWD1 + R1X_FWD <= R1X_FIELDS, "forward buffers");
-constexpr size_t RIC1X_SMEM = sizeof(double) * R1X_FIELDS * TL + 32;
+// bytes: backward staging [B_M, B_LP) in the storage type, then P / p scratch and the exchange block in fp64; the two forward buffers
+// overlay the front of it (the scratch is free by then)
+constexpr size_t R1X_STG_BYTES = sizeof(qs_real) * RIC1_STAGE_FIELDS * TL;
+constexpr size_t R1X_BYTES = R1X_STG_BYTES + sizeof(double) * (65 + R1X_XF) * TL;
+static_assert(sizeof(qs_real) * (R1X_FWD1 + R1X_FWD) * TL <= R1X_BYTES, "forward buffers");
+constexpr size_t RIC1X_SMEM = R1X_BYTES + 32;
 
 __device__ __forceinline__ void r1x_bar() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
-__device__ __forceinline__ void r1x_fetch(double* dst, const double* src, int nfields, uint64_t* bar) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(nfields * TL * 8) : "memory");
+__device__ __forceinline__ void r1x_fetch(qs_real* dst, const qs_real* src, int nfields, uint64_t* bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"((uint32_t)(nfields * TL * sizeof(qs_real))) : "memory");
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
-               "r"(nfields * TL * 8), "r"(smem_u32(bar))
+               "r"((uint32_t)(nfields * TL * sizeof(qs_real))), "r"(smem_u32(bar))
                : "memory");
 }
 __device__ __forceinline__ void r1x_wait(uint64_t* bar, uint32_t& phase) {
@@ -596,10 +614,10 @@ __global__ void __launch_bounds__(64) qs_ric1x_kernel(const smpc_problem_t* __re
   const int32_t* pi = q.pi + qs_pb(tile, NPI, lane);
   const bool on = QF(pi, J_ACT) != 0;
   if (!__any_sync(0xffffffffu, on)) return;                 // (both warps: same tile, same answer)
-  double* stg_all = smem;                                    // backward staging: fields [B_M, B_LP) at their own offsets
-  double* psm_all = smem + (size_t)RIC1_STAGE_FIELDS * TL;   // P_{k+1} (55) and p_{k+1} (10)
-  double* xch_all = psm_all + (size_t)65 * TL;               // T rows 5-14 and D of the running stage
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (size_t)R1X_FIELDS * TL);
+  qs_real* stg_all = reinterpret_cast<qs_real*>(smem);       // backward staging: fields [B_M, B_LP) at their own offsets
+  double* psm_all = reinterpret_cast<double*>(reinterpret_cast<char*>(smem) + R1X_STG_BYTES);   // P_{k+1} (55) and p_{k+1} (10), fp64
+  double* xch_all = psm_all + (size_t)65 * TL;               // T rows 5-14 and D of the running stage, fp64
+  uint64_t* bar = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(smem) + R1X_BYTES);
   if (threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar + 0)));
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar + 1)));
@@ -608,9 +626,9 @@ __global__ void __launch_bounds__(64) qs_ric1x_kernel(const smpc_problem_t* __re
   __syncthreads();
   double* pd = q.pd + qs_pb(tile, NPD, lane);
   const double dt = P.dt, a2 = 0.5 * P.dt * P.dt;
-  const double* gsb = q.sb + qs_blk(tile, N, 0, NSB, 0);
+  const qs_real* gsb = q.sb + qs_blk(tile, N, 0, NSB, 0);
   const size_t sstride = (size_t)NSB * TL;
-  const double* hc = stg_all + lane;
+  const qs_real* hc = stg_all + lane;
   double* psm = psm_all + lane;
   double* xch = xch_all + lane;
   auto Pn = [&](int idx) { return QF(psm, idx); };
@@ -622,7 +640,7 @@ __global__ void __launch_bounds__(64) qs_ric1x_kernel(const smpc_problem_t* __re
 
   for (int k = N; k >= 0; --k) {
     r1x_wait(bar, ph0);
-    double* fac = q.sb + qs_blk(tile, N, k, NSB, lane);
+    qs_real* fac = q.sb + qs_blk(tile, N, k, NSB, lane);
     if (wi == 0) {
       // ---------------- warp A: gradient, panel, elimination ----------------
       double g[15];
@@ -759,14 +777,14 @@ __global__ void __launch_bounds__(64) qs_ric1x_kernel(const smpc_problem_t* __re
 
   // ---------------- warp B: forward substitution (affine direction), two staging buffers ----------------
   uint32_t ph[2] = {ph0, 0};
-  double* fb[2] = {smem, smem + (size_t)R1X_FWD1 * TL};
+  qs_real* fb[2] = {stg_all, stg_all + (size_t)R1X_FWD1 * TL};
   if (lane == 0) r1x_fetch(fb[0], gsb + (size_t)B_RB * TL, R1X_FWD, bar + 0);
   for (int k = 0; k <= N; ++k) {
     __syncwarp();                                                          // every lane is done with the buffer of stage k - 1
     if (lane == 0 && k < N) r1x_fetch(fb[(k + 1) & 1], gsb + (size_t)(k + 1) * sstride + (size_t)B_RB * TL, R1X_FWD, bar + ((k + 1) & 1));
     r1x_wait(bar + (k & 1), ph[k & 1]);
-    const double* sb = fb[k & 1] + lane - (size_t)B_RB * TL;               // sb[f] valid for B_RB <= f < B_WV
-    double* st = q.st + qs_blk(tile, N, k, NIT, lane);
+    const qs_real* sb = fb[k & 1] + lane - (size_t)B_RB * TL;              // sb[f] valid for B_RB <= f < B_WV
+    qs_real* st = q.st + qs_blk(tile, N, k, NIT, lane);
     double du[5];
 #pragma unroll
     for (int i = 0; i < 5; ++i) du[i] = 0.0;
@@ -822,7 +840,7 @@ constexpr size_t RT_SMEM = sizeof(double) * RT_PER_WARP * RT_WARPS;
 // fields [f0, f0 + nf) of one stage of one problem: issued one stage ahead into registers (RT_NR per lane), parked in shared
 // memory when their stage starts, so that the global round trip of stage k - 1 runs under the arithmetic of stage k
 constexpr int RT_NR = 6;
-__device__ __forceinline__ void rt_issue(double (&r)[RT_NR], const double* gblock_lane, int f0, int nf, int lane) {
+__device__ __forceinline__ void rt_issue(double (&r)[RT_NR], const qs_real* gblock_lane, int f0, int nf, int lane) {
 #pragma unroll
   for (int u = 0; u < RT_NR; ++u) {
     const int f = lane + 32 * u;
@@ -851,7 +869,7 @@ __global__ void __launch_bounds__(32 * RT_WARPS) qs_ric1t_kernel(const smpc_prob
   double* X = DD + 5;
   double* pd = q.pd + qs_pb(tile, NPD, pl);
   const double dt = P.dt, a2 = 0.5 * P.dt * P.dt;
-  const double* gsb = q.sb + qs_blk(tile, N, 0, NSB, pl);    // stage blocks, lane offset of this problem applied
+  const qs_real* gsb = q.sb + qs_blk(tile, N, 0, NSB, pl);   // stage blocks, lane offset of this problem applied
   const size_t sstride = (size_t)NSB * TL;
   int cur = 0;                                               // Pb[cur] = (P_{k+1}, p_{k+1})
   double rr[RT_NR];
@@ -864,7 +882,7 @@ __global__ void __launch_bounds__(32 * RT_WARPS) qs_ric1t_kernel(const smpc_prob
     rt_park(S, rr, B_LP - B_M, lane);                                      // M GA RB at S[field]
     if (k > 0) rt_issue(rr, gsb + (size_t)(k - 1) * sstride, B_M, B_LP - B_M, lane);
     __syncwarp();
-    double* fac = q.sb + qs_blk(tile, N, k, NSB, pl);
+    qs_real* fac = q.sb + qs_blk(tile, N, k, NSB, pl);
     // y = P rb + p  (lanes 0-9)
     if (k < N && lane < 10) {
       double s_ = 0.0;
@@ -1036,7 +1054,7 @@ __global__ void __launch_bounds__(32 * RT_WARPS) qs_ric2t_kernel(const smpc_prob
   double* T0 = DUV + 10;                                     // [55] factor of P_0
   double* pd = q.pd + qs_pb(tile, NPD, pl);
   const double dt = P.dt, a2 = 0.5 * P.dt * P.dt;
-  const double* gsb = q.sb + qs_blk(tile, N, 0, NSB, pl);
+  const qs_real* gsb = q.sb + qs_blk(tile, N, 0, NSB, pl);
   const size_t sstride = (size_t)NSB * TL;
   const int n1 = B_P - B_GA, n2 = NSB - B_V1;
 
@@ -1067,7 +1085,7 @@ __global__ void __launch_bounds__(32 * RT_WARPS) qs_ric2t_kernel(const smpc_prob
   double rr[RT_NR];
   // backward stage fields: [B_GA, B_P) at S[f - B_GA], [B_V1, NSB) at S[n1 + f - B_V1]
   auto issue_b = [&](int k) {
-    const double* blk = gsb + (size_t)k * sstride;
+    const qs_real* blk = gsb + (size_t)k * sstride;
 #pragma unroll
     for (int u = 0; u < RT_NR; ++u) {
       const int f = lane + 32 * u;
@@ -1081,7 +1099,7 @@ __global__ void __launch_bounds__(32 * RT_WARPS) qs_ric2t_kernel(const smpc_prob
     __syncwarp();
     const double* sb = S - B_GA;                              // sb[f] valid for B_GA <= f < B_P
     const double* vv = S + n1 - B_V1;                         // vv[f] valid for B_V1 <= f < NSB
-    double* fac = q.sb + qs_blk(tile, N, k, NSB, pl);
+    qs_real* fac = q.sb + qs_blk(tile, N, k, NSB, pl);
     if (k < N && i < 10) YV[v * 10 + i] = sb[F_WV + i] + PN[v * 10 + i];
     __syncwarp();
     double g = 0.0;
@@ -1135,7 +1153,7 @@ __global__ void __launch_bounds__(32 * RT_WARPS) qs_ric2t_kernel(const smpc_prob
     const double* sb = S - B_RB;
     const double* dx = DXV + v * 10;
     const int lp = v == 0 ? F_LP : F_LP2;
-    double* sto = v == 0 ? q.st + qs_blk(tile, N, k, NIT, pl) : q.st2 + qs_blk(tile, N, k, NS2, pl);
+    qs_real* sto = v == 0 ? q.st + qs_blk(tile, N, k, NIT, pl) : q.st2 + qs_blk(tile, N, k, NS2, pl);
     // multiplier step of the link k-1 -> k:  dpi = P_k dx_k + p_k
     if (i < 10) {
       double s_ = 0.0;
@@ -1178,8 +1196,8 @@ __global__ void __launch_bounds__(32 * RT_WARPS) qs_ric2t_kernel(const smpc_prob
 __global__ void __launch_bounds__(32) qs_ric2_kernel(const smpc_problem_t* __restrict__ dP, QsBufs q) {
   extern __shared__ __align__(128) double smem[];
   TmaStage w;
-  w.sm = smem; w.nfb = RIC2_STAGE_FIELDS; w.ln = threadIdx.x;
-  w.bar = reinterpret_cast<uint64_t*>(smem + (size_t)QS_RIC_NBUF * RIC2_STAGE_FIELDS * TL);
+  w.sm = reinterpret_cast<qs_real*>(smem); w.nfb = RIC2_STAGE_FIELDS; w.ln = threadIdx.x;
+  w.bar = reinterpret_cast<uint64_t*>(w.sm + (size_t)QS_RIC_NBUF * RIC2_STAGE_FIELDS * TL);
   w.init();
   qs_ric2(*dP, q, blockIdx.x, w);
 }
@@ -1195,7 +1213,7 @@ __global__ void __launch_bounds__(32) qs_red_kernel(const smpc_problem_t* __rest
 }
 
 // stage records, tile-interleaved -> caller layout [B][N+1][REC] (smpc_get_lin)
-__global__ void rec_untile_kernel(int B, int N, const double* __restrict__ rec, double* out) {
+__global__ void rec_untile_kernel(int B, int N, const qs_real* __restrict__ rec, double* out) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (size_t)B * (N + 1) * REC) return;
   const int f = idx % REC;
@@ -1266,7 +1284,7 @@ struct QpSolver {
   int B = 0, N = 0, T = 0, iter_max = 0, G = 1;
   QsBufs q{};                   // whole batch (group 0 .. G-1 are sub-ranges of its tiles)
   QpGroup grp[MAX_GROUPS];
-  double* block = nullptr;      // one allocation for all double arrays
+  double* block = nullptr;      // one allocation for all arrays: the fp64 ones first, then the ones of the storage type
   int32_t* pi = nullptr;
   int* counters = nullptr;
   int* h_counters = nullptr;
@@ -1294,7 +1312,7 @@ struct QpSolver {
 
 size_t qp_bytes(int B, int N) {
   const size_t T = (B + TL - 1) / TL, S = T * (N + 1) * TL;
-  return sizeof(double) * (S * (REC + 3 * NIT + NS2 + NSB + NPROD + NRES + NSTP) + T * NPD * TL);
+  return sizeof(double) * (S * (2 * NIT + NRES + NSTP) + T * NPD * TL) + sizeof(qs_real) * S * (REC + NIT + NS2 + NSB + NPROD);
 }
 
 QpSolver* qp_create(int B, int N, int iter_max, bool keep_slots, cudaStream_t stream, cudaError_t* err) {
@@ -1346,17 +1364,17 @@ QpSolver* qp_create(int B, int N, int iter_max, bool keep_slots, cudaStream_t st
   }
   if (e != cudaSuccess) { *err = e; qp_destroy(s); return nullptr; }
   double* p = s->block;
-  double* rec = p; p += S * REC;
-  s->q.rec = rec;
   s->q.it[0] = p; p += S * NIT;
   s->q.it[1] = p; p += S * NIT;
-  s->q.st = p; p += S * NIT;
-  s->q.st2 = p; p += S * NS2;
-  s->q.sb = p; p += S * NSB;
-  s->q.prod = p; p += S * NPROD;
   s->q.res = p; p += S * NRES;
   s->q.stp = p; p += S * NSTP;
-  s->q.pd = p;
+  s->q.pd = p; p += T * NPD * TL;
+  qs_real* pr = reinterpret_cast<qs_real*>(p);
+  s->q.rec = pr; pr += S * REC;
+  s->q.st = pr; pr += S * NIT;
+  s->q.st2 = pr; pr += S * NS2;
+  s->q.sb = pr; pr += S * NSB;
+  s->q.prod = pr;
   s->q.pi = s->pi;
   s->q.N = N;
   s->q.tile0 = 0;
@@ -1400,7 +1418,7 @@ void qp_destroy(QpSolver* s) {
   delete s;
 }
 
-double* qp_rec(QpSolver* s) { return const_cast<double*>(s->q.rec); }
+void* qp_rec(QpSolver* s) { return const_cast<qs_real*>(s->q.rec); }
 int qp_last_iterations(const QpSolver* s) { return s->last_iters; }
 int qp_groups(const QpSolver* s) { return s->G; }
 int qp_compactions(const QpSolver* s) { return s->n_compactions; }
@@ -1518,6 +1536,9 @@ struct DeviceBackend {
     if (!s->compact || g->T < s->compact_min_tiles) return;
     const int na = n_active_last;
     if (na > g->in_use || g->in_use - na < TL || (double)na > 0.85 * g->in_use) return;
+    // in the tail (warp-per-problem sweeps, a handful of tiles) one compaction at its start is enough: a further one costs more
+    // (three launches, ~0.1 ms) than the few tiles it would save
+    if (na <= s->tail_max && g->in_use <= 2 * s->tail_max) return;
     cudaStream_t stm_ = st(false);
     tr0("qs_compact", stm_);
     const int tl_before = tl();

@@ -44,16 +44,12 @@
 #ifndef QS_REAL
 #define QS_REAL double
 #define QS_FLAVOUR f64
+#define QS_OTHER_FLAVOUR f32
 #endif
 
 namespace smpc {
 inline namespace QS_FLAVOUR {
 using qs_real = QS_REAL;
-#ifdef QS_FAC
-using qs_fac = QS_FAC;      // (experiment) type of the solver block
-#else
-using qs_fac = qs_real;
-#endif
 
 constexpr int TL = 32;             // problems per tile
 constexpr int QNR = 22;            // two-sided rows per stage
@@ -79,7 +75,8 @@ enum { NPROD = 46 };               // dlam_aff * dt_aff per slot (44) + the two 
 enum { R_NG = 0, R_NB = 1, R_ND = 2, R_NM = 3, R_MU = 4, R_CHK = 5, R_CNT = 6, NRES = 8 };
 enum { S_ALPHA = 0, S_LIN = 1, S_QUAD = 2, NSTP = 4 };
 // per-problem doubles
-enum { D_X0 = 0, D_T0 = 10, D_MU = 65, D_MUAFF = 66, D_SIGMU = 67, D_ALPHA = 68, D_STEP = 69, D_RES = 70, NPD = 74 };
+// D_RATIO, D_RESP: residual ratio max_i(res_i / tol_i) and residuals of the previous iterate (stall test of the fp32-storage flavour)
+enum { D_X0 = 0, D_T0 = 10, D_MU = 65, D_MUAFF = 66, D_SIGMU = 67, D_ALPHA = 68, D_STEP = 69, D_RES = 70, D_RATIO = 74, D_RESP = 75, NPD = 80 };
 // per-problem ints
 // J_B: index of the problem this slot carries in the caller's arrays (-1: empty slot); J_FIN: its result (x_temp, u_temp) has been written
 enum { J_ACT = 0, J_ITER = 1, J_QST = 2, J_REDO = 3, J_NC = 4, J_ITBUF = 5, J_R = 6, J_B = 7, J_FIN = 8, NPI = 9 };
@@ -89,7 +86,7 @@ struct QsBufs {
   double* it[2];         // [T][N+1][NIT][TL]   iterate, ping-pong (always fp64)
   qs_real* st;           // [T][N+1][NIT][TL]   step
   qs_real* st2;          // [T][N+1][NS2][TL]   pure-centering direction (dz, dpi) computed speculatively by ric2
-  qs_fac* sb;            // [T][N+1][NSB][TL]   solver block (condensed matrices, Riccati factors, corrector terms)
+  qs_real* sb;            // [T][N+1][NSB][TL]   solver block (condensed matrices, Riccati factors, corrector terms)
   qs_real* prod;         // [T][N+1][NPROD][TL]
   double* res;           // [T][N+1][NRES][TL]
   double* stp;           // [T][N+1][NSTP][TL]
@@ -202,7 +199,7 @@ SMPC_HD void qs_prep(const smpc_problem_t& P, const QsBufs& q, int tile, int lan
   double* ito = q.it[kk & 1] + qs_blk(tile, N, k, NIT, lane);
   const double* iti = q.it[(kk & 1) ^ 1] + qs_blk(tile, N, k, NIT, lane);
   const qs_real* st = q.st + qs_blk(tile, N, k, NIT, lane);
-  qs_fac* hc = q.sb + qs_blk(tile, N, k, NHC, lane);
+  qs_real* hc = q.sb + qs_blk(tile, N, k, NHC, lane);
   const StageFlags F = qs_flags(P, k);
   const double lam_min = 1e-16, t_min = 1e-16, thr0 = 1e-1, mu0 = P.qp_mu0, reg = P.qp_reg_prim;
   const double dt = P.dt, a2 = 0.5 * P.dt * P.dt;
@@ -502,12 +499,13 @@ SMPC_HD void qs_prep(const smpc_problem_t& P, const QsBufs& q, int tile, int lan
 // ctl: residual norms of the new iterate, exit tests (same control flow as the oracle's QpIpm::solve), result.
 // thread = problem.  Returns true when the problem stays active.
 // ================================================================================================================
-SMPC_HD bool qs_ctl(const smpc_problem_t& P, const QsBufs& q, int tile, int lane, int kk, int32_t* status, int32_t* qp_iter,
+SMPC_HD bool qs_ctl(const smpc_problem_t& P, const QsBufs& q, int tile, int lane, int kk_in, int32_t* status, int32_t* qp_iter,
                     int32_t* qp_status, double* qp_res) {
   const int N = q.N;
   int32_t* pi = q.pi + qs_pb(tile, NPI, lane);
   if (!QF(pi, J_ACT)) return false;
   double* pd = q.pd + qs_pb(tile, NPD, lane);
+  int kk = kk_in;
   double ng = 0.0, nb = 0.0, nd = 0.0, nm = 0.0, mu = 0.0, chk = 0.0, cnt = 0.0;
 #pragma unroll 8
   for (int k = 0; k <= N; ++k) {
@@ -517,7 +515,7 @@ SMPC_HD bool qs_ctl(const smpc_problem_t& P, const QsBufs& q, int tile, int lane
   }
   if (kk == 0) QF(pi, J_NC) = (int)(cnt + 0.5);
   const int nc = QF(pi, J_NC);
-  const double r0 = (chk != chk) ? chk : ng;
+  double r0 = (chk != chk) ? chk : ng;
   mu = mu / nc;
   QF(pd, D_RES + 0) = r0; QF(pd, D_RES + 1) = nb; QF(pd, D_RES + 2) = nd; QF(pd, D_RES + 3) = nm; QF(pd, D_MU) = mu;
   const bool nan = (r0 != r0) || (nb != nb) || (nd != nd) || (nm != nm);
@@ -527,9 +525,29 @@ SMPC_HD bool qs_ctl(const smpc_problem_t& P, const QsBufs& q, int tile, int lane
   else if (!unconv && !nan) done = true;
   else if (kk >= P.qp_iter_max) done = true;
   else if (!(QF(pd, D_ALPHA) > P.qp_alpha_min)) done = true;
+  // fp32-storage flavour only.  The stored search direction carries a relative rounding of 6e-8 that the condensation amplifies by
+  // lam / t, so the residuals of an iterate bottom out (1e-5 .. 1e-4 on this path) and GROW again if the iteration goes on.  A
+  // solve that has come within qp_maxiter_accept x its tolerances and whose new iterate is worse than the previous one ends on
+  // the previous iterate (still intact in the other ping-pong buffer) and reports it like an exit at the iteration limit.
+  bool stalled = false;
+  if (sizeof(qs_real) == 4) {
+    const double ratio = nan ? 1e300 : fmax(fmax(r0 / P.qp_tol_stat, nb / P.qp_tol_eq), fmax(nd / P.qp_tol_ineq, nm / P.qp_tol_comp));
+    const double prev = kk == 0 ? 1e300 : QF(pd, D_RATIO);
+    const double F = P.qp_maxiter_accept > 0.0 ? P.qp_maxiter_accept : 1e3;
+    if (kk >= 2 && (unconv || nan) && prev <= F && ratio > prev) { stalled = true; done = true; }
+    if (!stalled) {
+      QF(pd, D_RATIO) = ratio;
+      QF(pd, D_RESP + 0) = r0; QF(pd, D_RESP + 1) = nb; QF(pd, D_RESP + 2) = nd; QF(pd, D_RESP + 3) = nm; QF(pd, D_RESP + 4) = mu;
+    }
+  }
   if (!done) return true;
   int qst;
-  if (nan) qst = 3; else if (!unconv) qst = 0; else if (kk >= P.qp_iter_max) qst = 1; else qst = 2;
+  if (stalled) {
+    qst = 1;
+    r0 = QF(pd, D_RESP + 0); nb = QF(pd, D_RESP + 1); nd = QF(pd, D_RESP + 2); nm = QF(pd, D_RESP + 3); mu = QF(pd, D_RESP + 4);
+    QF(pd, D_RES + 0) = r0; QF(pd, D_RES + 1) = nb; QF(pd, D_RES + 2) = nd; QF(pd, D_RES + 3) = nm;
+    kk -= 1;                                               // the iterate that is reported
+  } else if (nan) qst = 3; else if (!unconv) qst = 0; else if (kk >= P.qp_iter_max) qst = 1; else qst = 2;
   QF(pi, J_ACT) = 0; QF(pi, J_ITER) = kk; QF(pi, J_QST) = qst; QF(pi, J_ITBUF) = kk & 1;
   // status mapping of acados SQP_RTI: QP success / max-iter -> step taken (qs_final writes it), else QP failure.  A max-iter exit
   // counts as solved only when its iterate is within qp_maxiter_accept x the tolerances (smpc_problem_t::qp_maxiter_accept: an
@@ -652,7 +670,7 @@ SMPC_HD void qs_ric1(const smpc_problem_t& P, const QsBufs& q, int tile, W& w, d
   if (!w.any(on)) return;
   double* pd = q.pd + qs_pb(tile, NPD, lane);
   const double dt = P.dt, a2 = 0.5 * P.dt * P.dt;
-  const qs_fac* gsb = q.sb + qs_blk(tile, N, 0, NSB, 0);       // stage blocks of this tile (no lane offset)
+  const qs_real* gsb = q.sb + qs_blk(tile, N, 0, NSB, 0);       // stage blocks of this tile (no lane offset)
   const size_t sstride = (size_t)NSB * TL;
   double dx[10];
   // staging: with two buffers stage k - 1 is fetched while stage k is processed; with one buffer (more warps per SM)
@@ -666,8 +684,8 @@ SMPC_HD void qs_ric1(const smpc_problem_t& P, const QsBufs& q, int tile, W& w, d
     if (!nb1 && k < N) { w.fetch_begin(0, B_LP - B_M); w.fetch(0, 0, gsb + (size_t)k * sstride, B_M, B_LP - B_M); }
     if (!nb1 && k > 0) w.prefetch(gsb + (size_t)(k - 1) * sstride, B_M, B_LP - B_M);      // next stage on its way to L2 meanwhile
     w.wait(k & nb1);
-    const qs_fac* hc = w.buf(k & nb1);                           // fields B_M .. B_LP at their own offsets
-    qs_fac* fac = q.sb + qs_blk(tile, N, k, NSB, lane);
+    const qs_real* hc = w.buf(k & nb1);                           // fields B_M .. B_LP at their own offsets
+    qs_real* fac = q.sb + qs_blk(tile, N, k, NSB, lane);
     double* pcur = psm;                                          // P_{k+1}, p_{k+1} on entry; P_k, p_k on exit (in place)
     const double* pnx = psm;
     auto Pn = [&](int idx) { return QF(pnx, idx); };
@@ -810,7 +828,7 @@ SMPC_HD void qs_ric1(const smpc_problem_t& P, const QsBufs& q, int tile, W& w, d
     if (!nb1 && k > 0) { w.fetch_begin(0, B_WV - B_RB); w.fetch(0, 0, gsb + (size_t)k * sstride, B_RB, B_WV - B_RB); }
     if (!nb1 && k < N) w.prefetch(gsb + (size_t)(k + 1) * sstride, B_RB, B_WV - B_RB);
     w.wait(k & nb1);
-    const qs_fac* sb = w.buf(k & nb1) - (size_t)B_RB * TL;       // sb[f] valid for B_RB <= f < B_WV
+    const qs_real* sb = w.buf(k & nb1) - (size_t)B_RB * TL;       // sb[f] valid for B_RB <= f < B_WV
     qs_real* st = q.st + qs_blk(tile, N, k, NIT, lane);
     double du[5];
 #pragma unroll
@@ -873,7 +891,7 @@ SMPC_HD void qs_ric2(const smpc_problem_t& P, const QsBufs& q, int tile, W& w) {
   if (!w.any(on)) return;
   double* pd = q.pd + qs_pb(tile, NPD, lane);
   const double dt = P.dt, a2 = 0.5 * P.dt * P.dt;
-  const qs_fac* gsb = q.sb + qs_blk(tile, N, 0, NSB, 0);
+  const qs_real* gsb = q.sb + qs_blk(tile, N, 0, NSB, 0);
   const size_t sstride = (size_t)NSB * TL;
   // backward stages fetch GA RB LP T WV = [B_GA, B_P) -> staging fields 0..124, and V1 V2 = [B_V1, NSB) -> 125..154
   const int n1 = B_P - B_GA, n2 = NSB - B_V1;
@@ -906,9 +924,9 @@ SMPC_HD void qs_ric2(const smpc_problem_t& P, const QsBufs& q, int tile, W& w) {
     }
     if (!nb1 && k > 0) { w.prefetch(gsb + (size_t)(k - 1) * sstride, B_GA, n1); w.prefetch(gsb + (size_t)(k - 1) * sstride, B_V1, n2); }
     w.wait(k & nb1);
-    const qs_fac* sb = w.buf(k & nb1) - (size_t)B_GA * TL;         // sb[f] valid for B_GA <= f < B_P
-    const qs_fac* vv = w.buf(k & nb1) - (size_t)(B_V1 - n1) * TL;  // vv[f] valid for B_V1 <= f < NSB
-    qs_fac* fac = q.sb + qs_blk(tile, N, k, NSB, lane);
+    const qs_real* sb = w.buf(k & nb1) - (size_t)B_GA * TL;         // sb[f] valid for B_GA <= f < B_P
+    const qs_real* vv = w.buf(k & nb1) - (size_t)(B_V1 - n1) * TL;  // vv[f] valid for B_V1 <= f < NSB
+    qs_real* fac = q.sb + qs_blk(tile, N, k, NSB, lane);
     double g[2][15];
 #pragma unroll
     for (int i = 0; i < 15; ++i) {
@@ -972,7 +990,7 @@ SMPC_HD void qs_ric2(const smpc_problem_t& P, const QsBufs& q, int tile, W& w) {
     if (!nb1 && k > 0) { w.fetch_begin(0, B_V1 - B_RB); w.fetch(0, 0, gsb + (size_t)k * sstride, B_RB, B_V1 - B_RB); }
     if (!nb1 && k < N) w.prefetch(gsb + (size_t)(k + 1) * sstride, B_RB, B_V1 - B_RB);
     w.wait(k & nb1);
-    const qs_fac* sb = w.buf(k & nb1) - (size_t)B_RB * TL;
+    const qs_real* sb = w.buf(k & nb1) - (size_t)B_RB * TL;
     qs_real* st = q.st + qs_blk(tile, N, k, NIT, lane);
     qs_real* st2 = q.st2 + qs_blk(tile, N, k, NS2, lane);
     // multiplier step of the link k-1 -> k:  dpi = P_k dx_k + p_k
@@ -1226,7 +1244,7 @@ SMPC_HD void qs_step(const smpc_problem_t& P, const QsBufs& q, int tile, int lan
     }
   }
   if (mode == 0) {
-    qs_fac* vv = q.sb + qs_blk(tile, N, k, NV, lane);
+    qs_real* vv = q.sb + qs_blk(tile, N, k, NV, lane);
     if (k == N) {
 #pragma unroll
       for (int i = 0; i < 5; ++i) { v1[i] = 0.0; v2[i] = 0.0; }

@@ -136,7 +136,7 @@ class ModelData:
 
 
 def build_problem(params, controller: str, cost: str = 'ext', N: int | None = None, model: ModelData | None = None,
-                  nn_precision: str | None = None):
+                  nn_precision: str | None = None, precision: str | None = None):
     """-> (abi.Problem, keepalive).  ``keepalive`` owns the weight buffer the struct points to.
 
     ``nn_precision``: 'strict' (fp32 weights, fp64 accumulation) or 'tf32x3' (fp32-class evaluation on the tensor cores,
@@ -171,6 +171,13 @@ def build_problem(params, controller: str, cost: str = 'ext', N: int | None = No
         keep = abi.pack_nn_weights(ws, bs)
     else:
         mean, std = np.zeros(nq), np.ones(nq)
+    precision = precision or getattr(params, 'precision', None) or 'f64'
+    if precision not in abi.PRECISION:
+        raise ValueError(f'unknown precision {precision} (f64, f32)')
+    # HPIPM BALANCE tolerances (UNVERIFIED offline).  fp32 storage: the stored search direction carries a rounding of
+    # 6e-8 that the condensation amplifies by lam / t, the residuals bottom out near 1e-5 -> one decade looser
+    tols = dict(qp_tol_stat=1e-6, qp_tol_eq=1e-8, qp_tol_ineq=1e-8, qp_tol_comp=1e-8) if precision == 'f64' else \
+        dict(qp_tol_stat=1e-5, qp_tol_eq=1e-6, qp_tol_ineq=1e-6, qp_tol_comp=1e-6)
     if controller == 'receding':
         penalty = params.ws_t                      # controller.py:461-462 (runtime cost_set wins over zl_e)
     else:
@@ -186,8 +193,7 @@ def build_problem(params, controller: str, cost: str = 'ext', N: int | None = No
         alpha=params.alpha, eps=params.eps, slack_penalty_e=penalty,
         tol_x=params.tol_x, tol_tau=params.tol_tau, tol_obs=params.tol_obs, tol_safe=params.tol_safe_set,
         tol_conv=params.tol_conv,
-        # HPIPM BALANCE defaults (UNVERIFIED offline)
-        qp_mu0=1e1, qp_tol_stat=1e-6, qp_tol_eq=1e-8, qp_tol_ineq=1e-8, qp_tol_comp=1e-8, qp_alpha_min=1e-12,
+        qp_mu0=1e1, qp_alpha_min=1e-12, precision=abi.PRECISION[precision], **tols,
         qp_reg_prim=1e-15, qp_maxiter_accept=float(getattr(params, 'qp_maxiter_accept', 1e3)),
         gravity=[0.0, 0.0, -GRAVITY],
         joint_R=md.chain.joint_R, joint_p=md.chain.joint_p, joint_axis=md.chain.joint_axis, inertial=md.inertial,

@@ -21,9 +21,9 @@ def params_model(noise=0.0, alpha=10.0, q_margin=0.0, collision_margin=0.0, cont
     return params, ModelData(params)
 
 
-def make_problem(controller='naive', cost='ext', N=None, nn_precision=None, keep_slots=False, **kw):
+def make_problem(controller='naive', cost='ext', N=None, nn_precision=None, keep_slots=False, precision=None, **kw):
     params, md = params_model(**kw)
-    prob, keep = build_problem(params, controller, cost=cost, N=N, model=md, nn_precision=nn_precision)
+    prob, keep = build_problem(params, controller, cost=cost, N=N, model=md, nn_precision=nn_precision, precision=precision)
     prob.qp_keep_slots = int(keep_slots)
     prob._keep = keep
     return prob, params, md

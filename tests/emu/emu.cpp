@@ -53,23 +53,23 @@ namespace {
 struct HostStage {
   int ln, nfb, lazy, nb = 2;
   int nbuf() const { return nb; }
-  std::vector<qs_fac> mem;
-  struct Copy { qs_fac* dst; const qs_fac* src; size_t n; };
+  std::vector<qs_real> mem;
+  struct Copy { qs_real* dst; const qs_real* src; size_t n; };
   std::vector<Copy> pend[2];
-  HostStage(int lane_, int nfb_, int lazy_) : ln(lane_), nfb(nfb_), lazy(lazy_), mem((size_t)2 * nfb_ * TL, (qs_fac)0) {}
+  HostStage(int lane_, int nfb_, int lazy_) : ln(lane_), nfb(nfb_), lazy(lazy_), mem((size_t)2 * nfb_ * TL, (qs_real)0) {}
   int lane() const { return ln; }
   bool any(bool v) const { return v; }
   void sync() const {}
-  qs_fac* buf(int b) { return mem.data() + (size_t)b * nfb * TL + ln; }
+  qs_real* buf(int b) { return mem.data() + (size_t)b * nfb * TL + ln; }
   void fetch_begin(int, int) {}
-  void fetch(int b, int dst_field, const qs_fac* gblock, int src_field, int nfields) {
+  void fetch(int b, int dst_field, const qs_real* gblock, int src_field, int nfields) {
     Copy c{mem.data() + ((size_t)b * nfb + dst_field) * TL, gblock + (size_t)src_field * TL, (size_t)nfields * TL};
     if (dst_field + nfields > nfb) { fprintf(stderr, "emu: staging overflow\n"); abort(); }
-    if (lazy) pend[b].push_back(c); else std::memcpy(c.dst, c.src, c.n * sizeof(qs_fac));
+    if (lazy) pend[b].push_back(c); else std::memcpy(c.dst, c.src, c.n * sizeof(qs_real));
   }
-  void wait(int b) { for (auto& c : pend[b]) std::memcpy(c.dst, c.src, c.n * sizeof(qs_fac)); pend[b].clear(); }
+  void wait(int b) { for (auto& c : pend[b]) std::memcpy(c.dst, c.src, c.n * sizeof(qs_real)); pend[b].clear(); }
   void publish() const {}
-  void prefetch(const qs_fac*, int, int) const {}
+  void prefetch(const qs_real*, int, int) const {}
 };
 
 struct HostBackend {
@@ -148,8 +148,7 @@ extern "C" int emu_qp_solve(const smpc_problem_t* P, int B, const double* rec, c
                             int32_t* qp_iter, int32_t* qp_status, double* qp_res, int* n_redo_total) {
   const int N = P->N, T = (B + TL - 1) / TL;
   const size_t S = (size_t)T * (N + 1) * TL;
-  std::vector<qs_real> vrec(S * REC, (qs_real)0), st(S * NIT, (qs_real)0), st2(S * NS2, (qs_real)0), prod(S * NPROD, (qs_real)0);
-  std::vector<qs_fac> sb(S * NSB, (qs_fac)0);
+  std::vector<qs_real> vrec(S * REC, (qs_real)0), st(S * NIT, (qs_real)0), st2(S * NS2, (qs_real)0), prod(S * NPROD, (qs_real)0), sb(S * NSB, (qs_real)0);
   std::vector<double> it0(S * NIT, 0.0), it1(S * NIT, 0.0), res(S * NRES, 0.0), stp(S * NSTP, 0.0), pd((size_t)T * NPD * TL, 0.0);
   std::vector<int32_t> pi32((size_t)T * NPI * TL, 0);
   for (int b = 0; b < B; ++b)
@@ -207,8 +206,7 @@ extern "C" int emu_qp_solve1(const smpc_problem_t* P, const double* rec, const d
                              int32_t* qp_iter, int32_t* qp_status, double* qp_res) {
   struct Ws {
     int N = -1;
-    std::vector<qs_real> vrec, st, st2, prod;
-    std::vector<qs_fac> sb;
+    std::vector<qs_real> vrec, st, st2, prod, sb;
     std::vector<double> it0, it1, res, stp, pd, psm;
     std::vector<int32_t> pi32;
   };
@@ -218,7 +216,7 @@ extern "C" int emu_qp_solve1(const smpc_problem_t* P, const double* rec, const d
   if (w.N != N) {
     w.N = N;
     w.vrec.assign(S * REC, (qs_real)0); w.it0.assign(S * NIT, 0.0); w.it1.assign(S * NIT, 0.0); w.st.assign(S * NIT, (qs_real)0); w.st2.assign(S * NS2, (qs_real)0);
-    w.sb.assign(S * NSB, (qs_fac)0); w.prod.assign(S * NPROD, (qs_real)0); w.res.assign(S * NRES, 0.0); w.stp.assign(S * NSTP, 0.0);
+    w.sb.assign(S * NSB, (qs_real)0); w.prod.assign(S * NPROD, (qs_real)0); w.res.assign(S * NRES, 0.0); w.stp.assign(S * NSTP, 0.0);
     w.pd.assign((size_t)NPD * TL, 0.0); w.pi32.assign((size_t)NPI * TL, 0); w.psm.assign(65 * TL, 0.0);
   }
   for (int k = 0; k <= N; ++k)

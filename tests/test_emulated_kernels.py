@@ -154,3 +154,34 @@ def test_run_ahead_and_compaction_do_not_change_results(emu, controller):
         on = act == 1
         assert np.array_equal(e['xt'][on], base['xt'][on]) and np.array_equal(e['ut'][on], base['ut'][on]), (depth, compact)
         assert np.isnan(e['xt'][~on]).all()                       # masked problems stay untouched
+
+
+@pytest.mark.parametrize('controller,cost', [('st', 'ext'), ('htwa', 'ext'), ('naive', 'ext'), ('receding', 'ext'), ('constraint_everywhere', 'ext'),
+                                             ('backup', 'zero'), ('zerovel', 'ext')])
+def test_fp32_storage_flavour_against_the_fp64_oracle(controller, cost):
+    """smpc_problem_t::precision = SMPC_PREC_F32 (qp_split.cuh with QS_REAL = float: stage records, search directions, condensed matrices
+    and Riccati factors stored in fp32, iterate and arithmetic fp64; tolerances 1e-5 / 1e-6 and the stall test of qs_ctl), compiled for the
+    host: same accept / fail status as the fp64 oracle with its fp64 tolerances, trajectories within the 1e-3 relative of BASELINE.json's
+    fp32 mode, and no run-away iteration (the fp32 search direction bottoms the residuals out; the stall test ends the solve there)."""
+    from tests.emu import kernel_source_oracle
+    N, B = 45, 48
+    prob64, params, md = make_problem(controller, cost=cost, N=N)
+    prob32, _, _ = make_problem(controller, cost=cost, N=N, precision='f32')
+    assert prob32.precision == 1 and prob32.qp_tol_stat == 1e-5 and prob64.qp_tol_stat == 1e-6
+    x0 = start_states(B, seed=31, vel=0.5)
+    xg, ug = rollout_guess(x0, N, params.dt, seed=32)
+    o = Oracle(prob64, B, 0)
+    e = kernel_source_oracle(prob32, B, 0, f32=True)
+    for h in (o, e):
+        h.set_guess(xg, ug)
+        if controller == 'receding':
+            h.set_state(abi.STATE_R, np.full(B, 7, dtype=np.int32))
+    st_o, st_e = o.rti_solve(x0 + 1e-3), e.rti_solve(x0 + 1e-3)
+    assert np.array_equal(st_o, st_e)
+    ok = st_o == 0
+    assert ok.any()
+    (xo, uo), (xe, ue) = o.get_temp(), e.get_temp()
+    assert np.abs(xo - xe)[ok].max() <= 1e-3 * max(1.0, np.abs(xo).max())
+    assert np.abs(uo - ue)[ok].max() <= 1e-3 * max(1.0, np.abs(uo).max())
+    it_o, it_e = o.get_state(abi.STATE_QP_ITER), e.get_state(abi.STATE_QP_ITER)
+    assert it_e[ok].max() <= it_o[ok].max() + 6, (it_e.max(), it_o.max())

@@ -1,0 +1,104 @@
+"""smpc_problem_t::precision = SMPC_PREC_F32 on the GPU: the fp32-storage flavour of the QP solver (csrc/qp_f32.cu = csrc/qp.cu with
+QS_REAL = float).  BASELINE.json north_star, fp32 mode: trajectories within 1e-3 relative of the fp64 reference path, identical
+status codes on the test set; the kernel forms of the flavour agree bit for bit like those of the fp64 flavour."""
+import os
+
+import numpy as np
+import pytest
+
+from safe_mpc_b200 import abi
+from tests.common import make_problem, start_states, rollout_guess, cfg0_initial_states, cfg0_plants, sqp_warm_start, run_closed_loop, outcome_sets
+
+pytestmark = pytest.mark.gpu
+
+RTOL32 = 1e-3
+
+
+@pytest.mark.parametrize('controller,cost,N', [('st', 'ext', 45), ('htwa', 'ext', 45), ('naive', 'ext', 45), ('receding', 'ext', 45),
+                                               ('constraint_everywhere', 'ext', 30), ('backup', 'zero', 45), ('zerovel', 'ext', 45),
+                                               ('real_receding', 'ext', 20)])
+def test_rti_solve_fp32_storage_against_the_fp64_oracle(controller, cost, N):
+    from safe_mpc_b200.engine import Engine
+    from oracle.oracle import Oracle
+    B = 160
+    prob64, params, md = make_problem(controller, cost=cost, N=N)
+    prob32, _, _ = make_problem(controller, cost=cost, N=N, precision='f32')
+    x0 = start_states(B, seed=31, vel=0.5)
+    xg, ug = rollout_guess(x0, N, params.dt, seed=32)
+    eng, orc = Engine(prob32, B, 0), Oracle(prob64, B, 0)
+    for e in (eng, orc):
+        e.set_guess(xg, ug)
+        if controller in ('receding', 'real_receding'):
+            e.set_state(abi.STATE_R, np.full(B, min(7, N - 1), dtype=np.int32))
+    st_g, st_o = eng.rti_solve(x0 + 1e-3), orc.rti_solve(x0 + 1e-3)
+    np.testing.assert_array_equal(st_g, st_o)
+    ok = st_o == 0
+    (xt_g, ut_g), (xt_o, ut_o) = eng.get_temp(), orc.get_temp()
+    ex = np.abs(xt_g - xt_o)[ok].max() / max(1.0, np.abs(xt_o).max())
+    eu = np.abs(ut_g - ut_o)[ok].max() / max(1.0, np.abs(ut_o).max())
+    it_g, it_o = eng.get_state(abi.STATE_QP_ITER), orc.get_state(abi.STATE_QP_ITER)
+    print(f'\n{controller}: rel err x {ex:.1e} u {eu:.1e}; IPM iterations fp32-storage {it_g.mean():.1f} (max {it_g.max()}) fp64 oracle {it_o.mean():.1f} (max {it_o.max()})')
+    assert ex <= RTOL32 and eu <= RTOL32
+    assert it_g[ok].max() <= it_o[ok].max() + 6
+    # the stage records are the fp64 ones rounded to fp32
+    lin_g, lin_o = eng.get_lin(), orc.get_lin()
+    assert (np.abs(lin_g - lin_o) / np.maximum(1.0, np.abs(lin_o))).max() <= 1e-6
+
+
+@pytest.mark.parametrize('controller', ['st', 'receding'])
+def test_fp32_kernel_forms_agree_bitwise(controller):
+    """cooperative / thread-per-stage prep, lane-per-problem / warp-per-problem / two-warp Riccati sweeps, compaction of the slots: the fp32
+    flavour keeps the property of the fp64 one that a problem's result does not depend on which form served it."""
+    from safe_mpc_b200.engine import Engine
+    Bc, Nc = 1280, 16
+
+    def solve(env):
+        old = {k: os.environ.get(k) for k in env}
+        os.environ.update(env)
+        try:
+            prob, params, md = make_problem(controller, N=Nc, precision='f32')
+            eng = Engine(prob, Bc, 0)
+        finally:
+            for k, v in old.items():
+                os.environ.pop(k, None) if v is None else os.environ.__setitem__(k, v)
+        x0 = start_states(Bc, seed=23, vel=0.5)
+        x0[::3, 5:] *= 4.0
+        xg, ug = rollout_guess(x0, Nc, params.dt, seed=24, scale=1.0)
+        eng.set_guess(xg, ug)
+        st = eng.rti_solve(x0)
+        xt, ut = eng.get_temp()
+        it = eng.get_state(abi.STATE_QP_ITER)
+        eng.close()
+        return st, xt, ut, it
+
+    base = solve({'SMPC_QP_TAIL': '0', 'SMPC_QP_PREP': 'thread', 'SMPC_QP_RIC1': 'single', 'SMPC_QP_COMPACT': '0'})
+    for env in ({'SMPC_QP_TAIL': '100000', 'SMPC_QP_COMPACT': '0'}, {'SMPC_QP_TAIL': '0', 'SMPC_QP_COMPACT': '0'}, {'SMPC_QP_DEPTH': '2'}, {}):
+        other = solve(env)
+        for i in range(4):
+            assert np.array_equal(base[i], other[i]), (env, i)
+
+
+def test_closed_loop_fp32_storage_outcomes():
+    """configs[0]-style closed loop (100 Halton initial states, N = 45, ST controller, 300 steps) in fp32-storage mode against the fp64
+    engine: the outcome codes agree for (nearly) every problem and the trajectories stay within 1e-3 relative over the first 50 steps."""
+    from safe_mpc_b200.engine import Engine, Sim
+    B, N, steps = 100, 45, 300
+    prob64, params, md = make_problem('st', N=N)
+    prob32, _, _ = make_problem('st', N=N, precision='f32')
+    b64, _, _ = make_problem('backup', cost='zero', N=params.back_hor)
+    b32, _, _ = make_problem('backup', cost='zero', N=params.back_hor, precision='f32')
+    eng = Engine(prob64, B, 0)
+    x0 = cfg0_initial_states(eng, md, params, B, 'halton')
+    pin, tn = cfg0_plants(md, params, B, 0.0, 0.0)
+    xg, ug = sqp_warm_start(eng, x0, N, 10)
+    eng.close()
+    r64 = run_closed_loop(Engine, Sim, prob64, b64, x0, xg, ug, pin, tn, steps)
+    r32 = run_closed_loop(Engine, Sim, prob32, b32, x0, xg, ug, pin, tn, steps)
+    same = r64['outcome'] == r32['outcome']
+    x64, x32 = np.nan_to_num(r64['x']), np.nan_to_num(r32['x'])
+    err = np.abs(x64 - x32).max(axis=2) / max(1.0, np.abs(x64).max())
+    print(f'\nfp64 {outcome_sets(r64["outcome"])} fp32-storage {outcome_sets(r32["outcome"])}; identical outcome codes {int(same.sum())} of {B}; '
+          f'max rel trajectory difference over 50 steps {err[:, :51].max():.1e}, over {steps} steps median {np.median(err.max(axis=1)):.1e}; '
+          f'IPM iterations fp64 {r64["counters"]["ipm_iterations"]} fp32-storage {r32["counters"]["ipm_iterations"]}')
+    assert same.mean() >= 0.95
+    assert err[:, :51].max() <= RTOL32

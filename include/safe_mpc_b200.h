@@ -246,7 +246,8 @@ int smpc_get_qp_residuals(smpc_handle_t* h, double* res5, int32_t mem);
  * `backup` is a handle created with controller = SMPC_CTRL_BACKUP and N = back_hor (mpc.py:54-73),
  * same batch.  One smpc_sim_step advances every live problem by one control step: abort following /
  * PD hold / controller.step, backup solve on abort, plant step, bounds and collision checks.
- * No host synchronisation inside. */
+ * Asynchronous towards the caller (nothing is copied back), but not free of host synchronisation: the QP solver reads one pair of
+ * counters per interior-point iteration (csrc/qp.cu) unless the batch is small enough for the solo kernel. */
 int smpc_sim_create(smpc_handle_t* main_ctrl, smpc_handle_t* backup, int32_t n_steps, smpc_sim_t** out);
 void smpc_sim_destroy(smpc_sim_t* s);
 int smpc_sim_reset(smpc_sim_t* s, const double* x_init, int32_t mem);
@@ -271,9 +272,10 @@ int smpc_get_times(smpc_handle_t* h, double* out7);
 /* per-kernel timing of the QP solver (the split interior-point kernels of csrc/qp.cu), CUDA events on the streams the
  * kernels are launched on.  smpc_set_profiling(h, 1) makes every following solve record one event pair per kernel (and
  * synchronise at its end); smpc_get_profile returns, for the last solve, the summed duration [ms] and the launch count per
- * kernel kind (index = SMPC_PROF_*), the span of the whole solve [ms] and the IPM iterations of the slowest problem. */
+ * kernel kind (index = SMPC_PROF_*), the span of the whole solve [ms] and the IPM iterations the host sequenced (those of the slowest
+ * problem; iterations that SMPC_PROF_SOLO -- one launch that runs whole iterations on the device -- performed are not counted). */
 enum { SMPC_PROF_INIT = 0, SMPC_PROF_PREP = 1, SMPC_PROF_CTL = 2, SMPC_PROF_RIC1 = 3, SMPC_PROF_STEP0 = 4, SMPC_PROF_RIC2 = 5,
-       SMPC_PROF_STEP1 = 6, SMPC_PROF_RED = 7, SMPC_PROF_COMPACT = 8, SMPC_PROF_STEP2 = 9, SMPC_PROF_FINAL = 10, SMPC_PROF_N = 11 };
+       SMPC_PROF_STEP1 = 6, SMPC_PROF_RED = 7, SMPC_PROF_COMPACT = 8, SMPC_PROF_STEP2 = 9, SMPC_PROF_FINAL = 10, SMPC_PROF_SOLO = 11, SMPC_PROF_N = 12 };
 int smpc_set_profiling(smpc_handle_t* h, int32_t enable);
 int smpc_get_profile(smpc_handle_t* h, double* ms /*[SMPC_PROF_N]*/, int32_t* count /*[SMPC_PROF_N]*/, double* span_ms, int32_t* iterations);
 /* number of kernels this handle has launched so far (bench.py "gpu_launches") */

@@ -855,14 +855,9 @@ __device__ __forceinline__ void rt_park(double* S, const double (&r)[RT_NR], int
   }
 }
 
-__global__ void __launch_bounds__(32 * RT_WARPS) qs_ric1t_kernel(const smpc_problem_t* __restrict__ dP, QsBufs q) {
-  extern __shared__ __align__(16) double rt_sm[];
-  const smpc_problem_t& P = *dP;
-  const int N = q.N, tile = blockIdx.x / (32 / RT_WARPS), wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int pl = (blockIdx.x % (32 / RT_WARPS)) * RT_WARPS + wi;          // problem (lane of the tile) this warp serves
-  const int32_t* pi = q.pi + qs_pb(tile, NPI, pl);
-  if (!QF(pi, J_ACT)) return;
-  double* S = rt_sm + (size_t)wi * RT_PER_WARP;             // staged fields, index = field - first field of the range
+// one warp, one problem: tile / pl = slot of the problem, S = RT_PER_WARP doubles of shared memory of this warp
+__device__ __forceinline__ void rt_ric1(const smpc_problem_t& P, const QsBufs& q, int tile, int pl, int lane, double* S) {
+  const int N = q.N;
   double* Pb = S + RT_PB;                                    // [2][65]: P (55) and p (10) of stage k + 1 / k
   double* TX = S + RT_TX;                                    // [75] multipliers, then D [5], then exchange [12]
   double* DD = TX + 75;
@@ -1035,18 +1030,21 @@ __global__ void __launch_bounds__(32 * RT_WARPS) qs_ric1t_kernel(const smpc_prob
   }
 }
 
+__global__ void __launch_bounds__(32 * RT_WARPS) qs_ric1t_kernel(const smpc_problem_t* __restrict__ dP, QsBufs q) {
+  extern __shared__ __align__(16) double rt_sm[];
+  const int tile = blockIdx.x / (32 / RT_WARPS), wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pl = (blockIdx.x % (32 / RT_WARPS)) * RT_WARPS + wi;          // problem (lane of the tile) this warp serves
+  if (!QF(q.pi + qs_pb(tile, NPI, pl), J_ACT)) return;
+  rt_ric1(*dP, q, tile, pl, lane, rt_sm + (size_t)wi * RT_PER_WARP);
+}
+
 // ric2 for the tail: one warp per problem, lanes 0-15 carry the corrector direction, lanes 16-31 the centering direction
 // (row / entry index = lane & 15).  Expressions and summation order of qs_ric2.
-__global__ void __launch_bounds__(32 * RT_WARPS) qs_ric2t_kernel(const smpc_problem_t* __restrict__ dP, QsBufs q) {
-  extern __shared__ __align__(16) double rt_sm[];
-  const smpc_problem_t& P = *dP;
-  const int N = q.N, tile = blockIdx.x / (32 / RT_WARPS), wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int pl = (blockIdx.x % (32 / RT_WARPS)) * RT_WARPS + wi;
+__device__ __forceinline__ void rt_ric2(const smpc_problem_t& P, const QsBufs& q, int tile, int pl, int lane, double* S) {
+  const int N = q.N;
   const int32_t* pi = q.pi + qs_pb(tile, NPI, pl);
-  if (!QF(pi, J_ACT)) return;
   const int v = lane >> 4, i = lane & 15;                   // direction, row
   const unsigned hb = lane & 16;                             // first lane of this half warp
-  double* S = rt_sm + (size_t)wi * RT_PER_WARP;
   double* YV = S + RT_PB;                                    // [2][10] y, then pn
   double* PN = YV + 20;                                      // [2][10]
   double* DXV = PN + 20;                                     // [2][10]
@@ -1193,6 +1191,85 @@ __global__ void __launch_bounds__(32 * RT_WARPS) qs_ric2t_kernel(const smpc_prob
   }
 }
 
+__global__ void __launch_bounds__(32 * RT_WARPS) qs_ric2t_kernel(const smpc_problem_t* __restrict__ dP, QsBufs q) {
+  extern __shared__ __align__(16) double rt_sm[];
+  const int tile = blockIdx.x / (32 / RT_WARPS), wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pl = (blockIdx.x % (32 / RT_WARPS)) * RT_WARPS + wi;
+  if (!QF(q.pi + qs_pb(tile, NPI, pl), J_ACT)) return;
+  rt_ric2(*dP, q, tile, pl, lane, rt_sm + (size_t)wi * RT_PER_WARP);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Solo kernel: one CTA per problem runs WHOLE interior-point iterations on the device until its problem has finished -- no
+// launch per phase, no counter read-back, nobody waits for anybody else.  Used (a) for the tail of a solve, once at most
+// `solo_max` problems of a tile group still iterate (a problem that runs into qp_max_iter used to hold the batch for ~190
+// iterations of ~9 launches each), and (b) from the first iteration on for small batches (configs[0]: 100 problems, less than one
+// problem per SM), where a solve is nothing but latency.  The phases are the functions of qp_split.cuh and the warp-per-problem
+// sweeps above, on the same arrays (a problem's working set, ~340 KB, lives in L2), separated by CTA barriers: thread k serves
+// stage k in the stage-parallel phases, warp 0 runs the sweeps, thread 0 the per-problem control logic.  Same functions, same
+// operands: results are bit-identical to the multi-kernel path, so a problem's result does not depend on who served it.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int SOLO_THREADS = 64;
+constexpr size_t SOLO_SMEM = sizeof(double) * ((SOLO_THREADS / 32) * PREP_SCRATCH * TL + RT_PER_WARP) + 16;
+
+__global__ void __launch_bounds__(SOLO_THREADS) qs_solo_kernel(const smpc_problem_t* __restrict__ dP, QsBufs q, int kk0, int32_t* status, int32_t* qp_iter,
+                                                               int32_t* qp_status, double* qp_res) {
+  extern __shared__ __align__(16) double so_sm[];
+  __shared__ int s_on, s_redo;
+  const smpc_problem_t& P = *dP;
+  const int N = q.N, tile = blockIdx.x / TL, pl = blockIdx.x % TL, tid = threadIdx.x, lane = tid & 31, wi = tid >> 5;
+  int32_t* pi = q.pi + qs_pb(tile, NPI, pl);
+  if (!QF(pi, J_ACT)) return;                                // (the whole CTA: same slot)
+  double* jsm = so_sm + (size_t)wi * PREP_SCRATCH * TL + lane;
+  double* S = so_sm + (size_t)(SOLO_THREADS / 32) * PREP_SCRATCH * TL;
+#ifdef QS_SOLO_TIMING
+  long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t0 = clock64(), t1;
+  int nit = 0;
+#define SOLO_T(i) { t1 = clock64(); tph[i] += t1 - t0; t0 = t1; }
+#else
+#define SOLO_T(i)
+#endif
+  for (int kk = kk0;; ++kk) {
+    if (tid == 0) s_on = qs_ctl(P, q, tile, pl, kk, status, qp_iter, qp_status, qp_res) ? 1 : 0;
+    __syncthreads();
+    SOLO_T(0)
+    if (!s_on) break;
+    if (wi == 0) rt_ric1(P, q, tile, pl, lane, S);
+    __syncthreads();
+    SOLO_T(1)
+    for (int k = tid; k <= N; k += SOLO_THREADS) qs_step(P, q, tile, pl, k, kk, 0);
+    __syncthreads();
+    SOLO_T(2)
+    if (wi == 0) rt_ric2(P, q, tile, pl, lane, S);
+    __syncthreads();
+    SOLO_T(3)
+    for (int k = tid; k <= N; k += SOLO_THREADS) qs_step(P, q, tile, pl, k, kk, 1);
+    __syncthreads();
+    SOLO_T(4)
+    if (tid == 0) { qs_red(P, q, tile, pl, false); s_redo = QF(pi, J_REDO); }
+    __syncthreads();
+    SOLO_T(5)
+    if (s_redo) {
+      for (int k = tid; k <= N; k += SOLO_THREADS) qs_step(P, q, tile, pl, k, kk, 2);
+      __syncthreads();
+      if (tid == 0) qs_red(P, q, tile, pl, true);
+      __syncthreads();
+    }
+    SOLO_T(6)
+    for (int k = tid; k <= N; k += SOLO_THREADS) qs_prep<false>(P, q, tile, pl, k, kk + 1, jsm);
+    __syncthreads();
+    SOLO_T(7)
+#ifdef QS_SOLO_TIMING
+    ++nit;
+#endif
+  }
+#ifdef QS_SOLO_TIMING
+  if (tid == 0 && blockIdx.x < 2 && nit > 0)
+    printf("SOLO slot %d its %d cycles/it: ctl %lld ric1 %lld step0 %lld ric2 %lld step1 %lld red %lld redo %lld prep %lld\n", blockIdx.x, nit, tph[0] / nit,
+           tph[1] / nit, tph[2] / nit, tph[3] / nit, tph[4] / nit, tph[5] / nit, tph[6] / nit, tph[7] / nit);
+#endif
+}
+
 __global__ void __launch_bounds__(32) qs_ric2_kernel(const smpc_problem_t* __restrict__ dP, QsBufs q) {
   extern __shared__ __align__(128) double smem[];
   TmaStage w;
@@ -1292,6 +1369,10 @@ struct QpSolver {
   int* n_moves = nullptr;
   cudaEvent_t ev_in = nullptr;  // inputs (records, x0) are ready on the caller's stream
   int last_iters = 0;
+  int solo_max = 384;           // a solve of at most this many problems per tile group is run by the solo kernel (one CTA per problem, whole iterations on
+                                // the device, one launch per solve; SMPC_QP_SOLO; 0: never)
+  bool solo_tail = false;       // ... and so is the tail of a larger solve once that few problems are left (SMPC_QP_SOLO_TAIL=1).  Off: measured on B200
+                                // (profiles/r02_solo.md) a solo iteration takes 0.42 ms against 0.23 ms for a tail iteration of the multi-kernel path
   int tail_max = 384;           // a tile group with at most this many problems still iterating is served by the warp-per-problem sweeps (0: never)
   bool split_ric1 = true;       // two warps per tile in the factorising Riccati sweep (SMPC_QP_RIC1=single selects the one-warp form)
   bool coop_prep = true;        // kk >= 1: four-warp cooperative prep with TMA-staged inputs (SMPC_QP_PREP=thread selects the thread-per-stage form)
@@ -1346,6 +1427,9 @@ QpSolver* qp_create(int B, int N, int iter_max, bool keep_slots, cudaStream_t st
   if (e == cudaSuccess) e = cudaFuncSetAttribute(qs_ric1t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RT_SMEM);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(qs_ric2t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RT_SMEM);
   if (const char* te = getenv("SMPC_QP_TAIL")) s->tail_max = atoi(te);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(qs_solo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLO_SMEM);
+  if (const char* se = getenv("SMPC_QP_SOLO")) s->solo_max = atoi(se);
+  if (const char* se = getenv("SMPC_QP_SOLO_TAIL")) s->solo_tail = atoi(se) != 0;
   if (const char* de = getenv("SMPC_QP_DEPTH")) s->depth = atoi(de);
   if (s->depth < 0) s->depth = 0;
   if (s->depth > RING - 2) s->depth = RING - 2;
@@ -1431,7 +1515,8 @@ void qp_get_profile(const QpSolver* s, double* ms, int32_t* n, double* span_ms) 
 namespace {
 static int prof_slot(const char* n) {
   static const char* names[SMPC_PROF_N] = {"qs_init_kernel", "qs_prep_kernel", "qs_ctl_kernel", "qs_ric1_kernel", "qs_step_kernel<0>", "qs_ric2_kernel",
-                                           "qs_step_kernel<1>", "qs_red_kernel", "qs_compact" /* final + plan + move of a compaction */, "qs_step_kernel<2>", "qs_final_kernel"};
+                                           "qs_step_kernel<1>", "qs_red_kernel", "qs_compact" /* final + plan + move of a compaction */, "qs_step_kernel<2>", "qs_final_kernel",
+                                           "qs_solo_kernel"};
   for (int i = 0; i < SMPC_PROF_N; ++i) if (names[i] && !strcmp(names[i], n)) return i;
   return 0;
 }
@@ -1525,6 +1610,18 @@ struct DeviceBackend {
     else if (mode == 1) { cudaStream_t stm_ = st(false); tr0("qs_step_kernel<1>", stm_); qs_step_kernel<1><<<sp_grid(), 32 * SP_WARPS, 0, stm_>>>(dP, g->q, tl(), kk); tr1(stm_); }
     else { cudaStream_t stm_ = st(false); tr0("qs_step_kernel<2>", stm_); qs_step_kernel<2><<<sp_grid(), 32 * SP_WARPS, 0, stm_>>>(dP, g->q, tl(), kk); tr1(stm_); }
     count();
+  }
+  // hand the rest of the solve (from the control phase of iteration kk on) to the solo kernel when few enough problems are left
+  bool solo(int kk) {
+    const int left = n_active_last < g->in_use ? n_active_last : g->in_use;
+    if (s->solo_max <= 0 || left > s->solo_max || (kk > 0 && !s->solo_tail)) return false;
+    kk_last = kk;
+    cudaStream_t stm_ = st(false);
+    tr0("qs_solo_kernel", stm_);
+    qs_solo_kernel<<<tl() * TL, SOLO_THREADS, SOLO_SMEM, stm_>>>(dP, g->q, kk, status, qp_iter, qp_status, qp_res);
+    tr1(stm_);
+    count();
+    return true;
   }
   // results of the problems that have finished and not been written yet; all slots of the group (empty ones are skipped)
   void final() { { cudaStream_t stm_ = st(false); tr0("qs_final_kernel", stm_); qs_final_kernel<<<sp_grid_all(), 32 * SP_WARPS, 0, stm_>>>(g->q, g->T, s->B, act, status, xt, ut); tr1(stm_); } count(); }

@@ -1329,7 +1329,11 @@ struct QsLoop {
     if (depth > 0) { bk.step(kk, 2); bk.red(true); }
     bk.request_counters(kk);
   }
-  void start() { bk.init(); bk.prep(0); issue(); }
+  void start() {
+    bk.init(); bk.prep(0);
+    if (bk.solo(0)) { bk.final(); done = true; return; }      // small batch: the backend runs the whole solve on its own
+    issue();
+  }
   void advance() {
     int n_active = 0, n_redo = 0;
     if (depth == 0) {
@@ -1347,6 +1351,7 @@ struct QsLoop {
     bk.compact(kk);              // (the backend decides; a no-op for most iterations)
     ++kk;
     bk.prep(kk);
+    if (bk.solo(kk)) { bk.final(); done = true; return; }     // few problems left: the backend finishes the solve on its own (qp.cu: solo kernel)
     issue();
   }
 };

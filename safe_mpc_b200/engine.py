@@ -89,7 +89,7 @@ class Engine(EngineBase):
         return int(self.lib.smpc_stream(self.h) or 0)
 
     PROF_NAMES = ['qs_init', 'qs_prep', 'qs_ctl', 'qs_ric1', 'qs_step0', 'qs_ric2', 'qs_step1', 'qs_red', 'qs_compact',
-                  'qs_step2_centering', 'qs_final']
+                  'qs_step2_centering', 'qs_final', 'qs_solo']
 
     def set_profiling(self, on: bool):
         self._call('set_profiling', C.c_int32(int(on)))

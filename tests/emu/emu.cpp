@@ -122,6 +122,7 @@ struct HostBackend {
     }
     if (nm) { ++n_compactions; n_moves += nm; }
   }
+  bool solo(int) { return false; }
   void red(bool after) { each_problem([&](int t, int l) { qs_red(P, q, t, l, after); }); }
   int redo_total = 0;
   void request_counters(int) {}

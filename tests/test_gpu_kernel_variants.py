@@ -16,6 +16,7 @@ B, N = 160, 30
 
 def _solve(controller, env):
     from safe_mpc_b200.engine import Engine
+    env = {'SMPC_QP_SOLO': '0', **env}     # (a batch this small would be served by the solo kernel alone: off unless the test asks for it)
     old = {k: os.environ.get(k) for k in env}
     os.environ.update(env)
     try:
@@ -81,6 +82,7 @@ def test_host_loop_depth_and_compaction_agree_bitwise(controller):
     Bc, Nc = 1280, 16
 
     def solve(env):
+        env = {'SMPC_QP_SOLO': '0', **env}
         old = {k: os.environ.get(k) for k in env}
         os.environ.update(env)
         try:
@@ -103,7 +105,21 @@ def test_host_loop_depth_and_compaction_agree_bitwise(controller):
 
     base = solve({'SMPC_QP_DEPTH': '0', 'SMPC_QP_COMPACT': '0'})       # one host round trip per iteration, no compaction
     assert len(set(base[3].tolist())) >= 6
-    for env in ({'SMPC_QP_DEPTH': '3', 'SMPC_QP_COMPACT': '0'}, {'SMPC_QP_DEPTH': '0', 'SMPC_QP_COMPACT': '1'}, {}):
+    # ... and neither may the solo kernel (one CTA per problem, whole iterations on the device) that takes over the tail of a solve
+    for env in ({'SMPC_QP_DEPTH': '3', 'SMPC_QP_COMPACT': '0'}, {'SMPC_QP_DEPTH': '0', 'SMPC_QP_COMPACT': '1'}, {},
+                {'SMPC_QP_SOLO': '384', 'SMPC_QP_SOLO_TAIL': '1'}, {'SMPC_QP_SOLO': '200', 'SMPC_QP_SOLO_TAIL': '1', 'SMPC_QP_COMPACT': '0'},
+                {'SMPC_QP_SOLO': '100000'}):
         other = solve(env)
         for i in range(4):
             assert np.array_equal(base[i], other[i]), (env, i)
+
+
+@pytest.mark.parametrize('controller', ['st', 'receding', 'htwa', 'naive'])
+def test_solo_kernel_agrees_bitwise(controller):
+    """qs_solo_kernel (one CTA per problem, all phases of every interior-point iteration in one launch): from the first iteration on
+    (what a batch of this size gets by default), or taking over once at most 60 problems are left -- same bits as the multi-kernel path."""
+    multi = _solve(controller, {'SMPC_QP_SOLO': '0'})
+    for env in ({'SMPC_QP_SOLO': '384'}, {'SMPC_QP_SOLO': '60', 'SMPC_QP_SOLO_TAIL': '1'}, {'SMPC_QP_SOLO': '60', 'SMPC_QP_SOLO_TAIL': '1', 'SMPC_QP_TAIL': '0'}):
+        solo = _solve(controller, env)
+        for i in range(4):
+            assert np.array_equal(multi[i], solo[i]), (env, i)

@@ -53,6 +53,7 @@ def test_fp32_kernel_forms_agree_bitwise(controller):
     Bc, Nc = 1280, 16
 
     def solve(env):
+        env = {'SMPC_QP_SOLO': '0', **env}
         old = {k: os.environ.get(k) for k in env}
         os.environ.update(env)
         try:

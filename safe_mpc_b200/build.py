@@ -13,7 +13,7 @@ from concurrent.futures import ThreadPoolExecutor
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'csrc')
 LIB = os.path.join(CSRC, 'libsafe_mpc_b200.so')
 SOURCES = ['api.cu', 'kernels.cu', 'qp.cu', 'qp_f32.cu', 'mlp_tc.cu', 'mlp_tc2.cu', 'peaks.cu']
-HEADERS = ['engine.cuh', 'qp_split.cuh', 'dev_model.cuh', 'mlp_tc_common.cuh', os.path.join('..', '..', 'include', 'safe_mpc_b200.h')]
+HEADERS = ['engine.cuh', 'qp_split.cuh', 'qp_tail.cuh', 'dev_model.cuh', 'mlp_tc_common.cuh', os.path.join('..', '..', 'include', 'safe_mpc_b200.h')]
 NVCC_FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-Xcompiler', '-fPIC',
               '-Xptxas', '-v']
 

@@ -791,7 +791,7 @@ __global__ void __launch_bounds__(64) qs_ric1x_kernel(const smpc_problem_t* __re
     if (k < N) {
 #pragma unroll
       for (int i = 0; i < 5; ++i) {
-        double ws = QF(sb, F_T + i * 5 + i) * QF(sb, F_LP + i);
+        double ws = (double)QF(sb, F_T + i * 5 + i) * (double)QF(sb, F_LP + i);   // (operands widened first: fp32-storage flavour)
 #pragma unroll
         for (int r = 0; r < 10; ++r) ws += QF(sb, F_T + (5 + r) * 5 + i) * dx[r];
         du[i] = -ws;
@@ -821,382 +821,27 @@ __global__ void __launch_bounds__(64) qs_ric1x_kernel(const smpc_problem_t* __re
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Tail kernels: one WARP per problem.  The lane-per-problem sweeps above take the same time for 1 or 10 000 active problems
-// (46 dependent stages of a ~2 000-instruction stream); in the last iterations of a solve a handful of problems are left -- and
-// a problem that runs into qp_max_iter holds the whole batch for hundreds of iterations.  When few problems iterate the host
-// switches to these kernels: the lanes of a warp own the rows / entries of ONE problem, so the dependent chain of a stage is
-// ~150 instructions instead of ~2 000.  Every entry is computed with the expressions and the summation order of qs_ric1 /
-// qs_ric2 (qp_split.cuh), so a problem gets bit-identical results whichever kernel serves it.  One CTA per tile, warp w =
-// problem w of the tile; warps of finished problems exit at once.  The accesses of a warp are 8-byte reads 256 B apart (the
-// layout is made for the lane-per-problem kernels) -- irrelevant for the few hundred problems these kernels are used for.
+// Tail kernels: one WARP per problem (the sweeps themselves: qp_tail.cuh).  One CTA serves RT_WARPS problems of a tile; warps of
+// finished problems exit at once.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int RT_S = 184;                      // staged fields of one stage (largest range: ric2 forward, 180)
-constexpr int RT_PB = RT_S;                    // P / p double buffer [2][65] (ric1) or pn, dx vectors (ric2)
-constexpr int RT_TX = RT_PB + 130;             // pan rows [15][5], D [5], exchange [12]
-constexpr int RT_PER_WARP = RT_TX + 75 + 5 + 12 + 4;
-constexpr int RT_WARPS = 16;                   // warps (problems) per CTA: two CTAs per tile, 128 registers per thread
-constexpr size_t RT_SMEM = sizeof(double) * RT_PER_WARP * RT_WARPS;
-
-// fields [f0, f0 + nf) of one stage of one problem: issued one stage ahead into registers (RT_NR per lane), parked in shared
-// memory when their stage starts, so that the global round trip of stage k - 1 runs under the arithmetic of stage k
-constexpr int RT_NR = 6;
-__device__ __forceinline__ void rt_issue(double (&r)[RT_NR], const qs_real* gblock_lane, int f0, int nf, int lane) {
-#pragma unroll
-  for (int u = 0; u < RT_NR; ++u) {
-    const int f = lane + 32 * u;
-    r[u] = f < nf ? gblock_lane[(size_t)(f0 + f) * TL] : 0.0;
-  }
-}
-__device__ __forceinline__ void rt_park(double* S, const double (&r)[RT_NR], int nf, int lane) {
-#pragma unroll
-  for (int u = 0; u < RT_NR; ++u) {
-    const int f = lane + 32 * u;
-    if (f < nf) S[f] = r[u];
-  }
-}
-
-// one warp, one problem: tile / pl = slot of the problem, S = RT_PER_WARP doubles of shared memory of this warp
-__device__ __forceinline__ void rt_ric1(const smpc_problem_t& P, const QsBufs& q, int tile, int pl, int lane, double* S) {
-  const int N = q.N;
-  double* Pb = S + RT_PB;                                    // [2][65]: P (55) and p (10) of stage k + 1 / k
-  double* TX = S + RT_TX;                                    // [75] multipliers, then D [5], then exchange [12]
-  double* DD = TX + 75;
-  double* X = DD + 5;
-  double* pd = q.pd + qs_pb(tile, NPD, pl);
-  const double dt = P.dt, a2 = 0.5 * P.dt * P.dt;
-  const qs_real* gsb = q.sb + qs_blk(tile, N, 0, NSB, pl);   // stage blocks, lane offset of this problem applied
-  const size_t sstride = (size_t)NSB * TL;
-  int cur = 0;                                               // Pb[cur] = (P_{k+1}, p_{k+1})
-  double rr[RT_NR];
-  rt_issue(rr, gsb + (size_t)N * sstride, B_M, B_LP - B_M, lane);
-
-  for (int k = N; k >= 0; --k) {
-    const double* pc = Pb + cur * 65;
-    double* pn_ = Pb + (cur ^ 1) * 65;
-    auto Pn = [&](int idx) { return pc[idx]; };
-    rt_park(S, rr, B_LP - B_M, lane);                                      // M GA RB at S[field]
-    if (k > 0) rt_issue(rr, gsb + (size_t)(k - 1) * sstride, B_M, B_LP - B_M, lane);
-    __syncwarp();
-    qs_real* fac = q.sb + qs_blk(tile, N, k, NSB, pl);
-    // y = P rb + p  (lanes 0-9)
-    if (k < N && lane < 10) {
-      double s_ = 0.0;
-#pragma unroll
-      for (int j = 0; j < 10; ++j) s_ += Pn(trs(lane, j)) * S[H_RB + j];
-      QF(fac, F_WV + lane) = s_;
-      X[lane] = s_ + pc[55 + lane];
-    }
-    __syncwarp();
-    // gradient and panel row of lane i < 15
-    double g = 0.0, pan[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-    if (lane < 15) {
-      g = S[H_GA + lane];
-      if (k < N) {
-        if (lane < 5) g += a2 * X[lane] + dt * X[5 + lane];
-        else if (lane < 10) g += X[lane - 5];
-        else g += dt * X[lane - 10] + X[lane - 5];
-      } else if (lane < 5) g = 0.0;
-#pragma unroll
-      for (int j = 0; j < 5; ++j)
-        if (j <= lane) pan[j] = S[H_M + tri(lane, j)] + (k < N ? qs_y(lane, j, dt, a2, Pn) : 0.0);
-    }
-    __syncwarp();                                                          // X (y) consumed
-    // LDL' elimination of the control columns: lane i owns row i
-    double dd[5];
-#pragma unroll
-    for (int j = 0; j < 5; ++j) {
-      if (lane >= j && lane <= 4) X[lane] = pan[j];                        // column j of the rows j..4, not yet scaled
-      if (lane == j) X[8] = g;
-      __syncwarp();
-      const double d = X[j];
-      const double invd = d > 0.0 ? qs_rcp(d) : 0.0;
-      dd[j] = d > 0.0 ? d : 0.0;
-      if (lane > j && lane < 15) {
-        const double t = pan[j] * invd;
-        g -= t * X[8];
-#pragma unroll
-        for (int c = j + 1; c < 5; ++c)
-          if (c <= lane) pan[c] -= t * X[c];
-        pan[j] = t;
-      }
-      if (lane == j) pan[j] = invd;
-      __syncwarp();
-    }
-    if (lane < 15) {
-#pragma unroll
-      for (int j = 0; j < 5; ++j)
-        if (j <= lane) { TX[lane * 5 + j] = pan[j]; QF(fac, F_T + lane * 5 + j) = pan[j]; }
-      QF(fac, F_LP + lane) = g;
-      if (lane >= 5) pn_[55 + lane - 5] = g;                               // p_k
-    }
-    if (lane < 5) DD[lane] = dd[lane];
-    __syncwarp();
-    // P_k = trailing block - T_x D T_x': entry e = tri(r, s_) of the state block, two entries per lane
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int e = lane + 32 * h;
-      if (e < 55) {
-        int r = 0;
-        while (tri(r + 1, 0) <= e) ++r;
-        const int c_ = e - tri(r, 0);
-        const int i = 5 + r, c = 5 + c_;
-        double v = S[H_M + tri(i, c)] + (k < N ? qs_y(i, c, dt, a2, Pn) : 0.0);
-#pragma unroll
-        for (int j = 0; j < 5; ++j) v -= (TX[i * 5 + j] * DD[j]) * TX[c * 5 + j];
-        pn_[e] = v;
-        QF(fac, F_P + e) = v;
-      }
-    }
-    __syncwarp();
-    cur ^= 1;
-  }
-  // stage 0: factorise P_0 (kept for ric2) and solve P_0 dx_0 = -p_0   (one lane; once per sweep)
-  double* DX = X;                                                          // [10]
-  if (lane == 0) {
-    const double* p0 = Pb + cur * 65;
-    double m[10][10], gg[10], dx[10];
-#pragma unroll
-    for (int i = 0; i < 10; ++i) {
-      gg[i] = p0[55 + i];
-#pragma unroll
-      for (int c = 0; c <= i; ++c) m[i][c] = p0[tri(i, c)];
-    }
-#pragma unroll
-    for (int j = 0; j < 10; ++j) {
-      const double d = m[j][j];
-      const double invd = d > 0.0 ? qs_rcp(d) : 0.0;
-      m[j][j] = invd;
-#pragma unroll
-      for (int i = 9; i > j; --i) {
-        const double t = m[i][j] * invd;
-        gg[i] -= t * gg[j];
-#pragma unroll
-        for (int c = j + 1; c <= i; ++c) m[i][c] -= t * m[c][j];
-        m[i][j] = t;
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < 10; ++i)
-#pragma unroll
-      for (int c = 0; c <= i; ++c) QF(pd, D_T0 + tri(i, c)) = m[i][c];
-#pragma unroll
-    for (int i = 9; i >= 0; --i) {
-      double acc = m[i][i] * gg[i];
-#pragma unroll
-      for (int c = i + 1; c < 10; ++c) acc += m[c][i] * dx[c];
-      dx[i] = m[i][i] > 0.0 ? -acc : 0.0;
-    }
-#pragma unroll
-    for (int i = 0; i < 10; ++i) DX[i] = dx[i];
-  }
-  __threadfence_block();
-  __syncwarp();
-  // forward substitution (affine direction): lanes 0-4 own du, lanes 0-9 own dx
-  double* ZZ = TX;                                                         // [15] dz of the running stage
-  double* DU = TX + 16;                                                    // [5]
-  rt_issue(rr, gsb, B_RB, B_WV - B_RB, lane);
-  for (int k = 0; k <= N; ++k) {
-    rt_park(S, rr, B_WV - B_RB, lane);                                      // RB LP T at S[field - B_RB]
-    if (k < N) rt_issue(rr, gsb + (size_t)(k + 1) * sstride, B_RB, B_WV - B_RB, lane);
-    __syncwarp();
-    const double* sb = S - B_RB;
-    double du = 0.0;
-    if (k < N && lane < 5) {
-      double ws = sb[F_T + lane * 5 + lane] * sb[F_LP + lane];
-#pragma unroll
-      for (int r = 0; r < 10; ++r) ws += sb[F_T + (5 + r) * 5 + lane] * DX[r];
-      du = -ws;
-    }
-    if (k < N) {
-      // du[i] -= T[c][i] du[c] for c = 4 .. 1, i < c (the order of qs_ric1)
-#pragma unroll
-      for (int c = 4; c >= 1; --c) {
-        const double duc = __shfl_sync(0xffffffffu, du, c);
-        if (lane < c) du -= sb[F_T + c * 5 + lane] * duc;
-      }
-    }
-    if (lane < 5) { ZZ[lane] = du; DU[lane] = du; }
-    if (lane < 10) ZZ[5 + lane] = DX[lane];
-    __syncwarp();
-    double nx = 0.0;
-    if (k < N && lane < 10) {
-      if (lane < 5) nx = DX[lane] + dt * DX[5 + lane] + a2 * DU[lane] + sb[H_RB + lane];
-      else nx = DX[lane] + dt * DU[lane - 5] + sb[H_RB + lane];
-    }
-    if (lane < 15) QF(q.st + qs_blk(tile, N, k, NIT, pl), I_Z + lane) = ZZ[lane];
-    __syncwarp();
-    if (k < N && lane < 10) DX[lane] = nx;
-    __syncwarp();
-  }
-}
+#include "qp_tail.cuh"
 
 __global__ void __launch_bounds__(32 * RT_WARPS) qs_ric1t_kernel(const smpc_problem_t* __restrict__ dP, QsBufs q) {
-  extern __shared__ __align__(16) double rt_sm[];
+  extern __shared__ __align__(16) unsigned char rt_sm[];
   const int tile = blockIdx.x / (32 / RT_WARPS), wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pl = (blockIdx.x % (32 / RT_WARPS)) * RT_WARPS + wi;          // problem (lane of the tile) this warp serves
   if (!QF(q.pi + qs_pb(tile, NPI, pl), J_ACT)) return;
-  rt_ric1(*dP, q, tile, pl, lane, rt_sm + (size_t)wi * RT_PER_WARP);
-}
-
-// ric2 for the tail: one warp per problem, lanes 0-15 carry the corrector direction, lanes 16-31 the centering direction
-// (row / entry index = lane & 15).  Expressions and summation order of qs_ric2.
-__device__ __forceinline__ void rt_ric2(const smpc_problem_t& P, const QsBufs& q, int tile, int pl, int lane, double* S) {
-  const int N = q.N;
-  const int32_t* pi = q.pi + qs_pb(tile, NPI, pl);
-  const int v = lane >> 4, i = lane & 15;                   // direction, row
-  const unsigned hb = lane & 16;                             // first lane of this half warp
-  double* YV = S + RT_PB;                                    // [2][10] y, then pn
-  double* PN = YV + 20;                                      // [2][10]
-  double* DXV = PN + 20;                                     // [2][10]
-  double* DUV = DXV + 20;                                    // [2][5]
-  double* T0 = DUV + 10;                                     // [55] factor of P_0
-  double* pd = q.pd + qs_pb(tile, NPD, pl);
-  const double dt = P.dt, a2 = 0.5 * P.dt * P.dt;
-  const qs_real* gsb = q.sb + qs_blk(tile, N, 0, NSB, pl);
-  const size_t sstride = (size_t)NSB * TL;
-  const int n1 = B_P - B_GA, n2 = NSB - B_V1;
-
-  // ---- sigma from the affine step statistics (sums over the stages in stage order, like qs_reduce_step) ----
-  double sigmu;
-  {
-    double* RS = S;                                          // [3][N + 1]
-    for (int k = lane; k <= N; k += 32) {
-      const double* stp = q.stp + qs_blk(tile, N, k, NSTP, pl);
-      RS[k] = QF(stp, S_ALPHA); RS[(N + 1) + k] = QF(stp, S_LIN); RS[2 * (N + 1) + k] = QF(stp, S_QUAD);
-    }
-    __syncwarp();
-    double sm_ = 0.0;
-    if (lane == 0) {
-      double alpha = 1.0, s_lin = 0.0, s_quad = 0.0;
-      for (int k = 0; k <= N; ++k) { alpha = fmin(alpha, RS[k]); s_lin += RS[(N + 1) + k]; s_quad += RS[2 * (N + 1) + k]; }
-      const double mu = QF(pd, D_MU);
-      const double mu_aff = mu + (alpha * s_lin + alpha * alpha * s_quad) / QF(pi, J_NC);
-      double sigma = mu_aff / mu; sigma = sigma * sigma * sigma;
-      sm_ = sigma * mu;
-      QF(pd, D_MUAFF) = mu_aff; QF(pd, D_SIGMU) = sm_;
-    }
-    sigmu = __shfl_sync(0xffffffffu, sm_, 0);
-    __syncwarp();
-  }
-  if (i < 10) { PN[v * 10 + i] = 0.0; DXV[v * 10 + i] = 0.0; }
-  for (int e = lane; e < 55; e += 32) T0[e] = QF(pd, D_T0 + e);
-  double rr[RT_NR];
-  // backward stage fields: [B_GA, B_P) at S[f - B_GA], [B_V1, NSB) at S[n1 + f - B_V1]
-  auto issue_b = [&](int k) {
-    const qs_real* blk = gsb + (size_t)k * sstride;
-#pragma unroll
-    for (int u = 0; u < RT_NR; ++u) {
-      const int f = lane + 32 * u;
-      rr[u] = f < n1 ? blk[(size_t)(B_GA + f) * TL] : (f < n1 + n2 ? blk[(size_t)(B_V1 + f - n1) * TL] : 0.0);
-    }
-  };
-  issue_b(N);
-  for (int k = N; k >= 0; --k) {
-    rt_park(S, rr, n1 + n2, lane);
-    if (k > 0) issue_b(k - 1);
-    __syncwarp();
-    const double* sb = S - B_GA;                              // sb[f] valid for B_GA <= f < B_P
-    const double* vv = S + n1 - B_V1;                         // vv[f] valid for B_V1 <= f < NSB
-    qs_real* fac = q.sb + qs_blk(tile, N, k, NSB, pl);
-    if (k < N && i < 10) YV[v * 10 + i] = sb[F_WV + i] + PN[v * 10 + i];
-    __syncwarp();
-    double g = 0.0;
-    if (i < 15) {
-      const double ga = sb[H_GA + i], s2 = sigmu * vv[V_2 + i];
-      g = v == 0 ? ga + vv[V_1 + i] - s2 : ga + 0.0 - s2;
-      if (k < N) {
-        const double* y = YV + v * 10;
-        if (i < 5) g += a2 * y[i] + dt * y[5 + i];
-        else if (i < 10) g += y[i - 5];
-        else g += dt * y[i - 10] + y[i - 5];
-      } else if (i < 5) g = 0.0;
-    }
-#pragma unroll
-    for (int j = 0; j < 5; ++j) {
-      const double gj = __shfl_sync(0xffffffffu, g, hb | j);
-      if (i > j && i < 15) g -= sb[F_T + i * 5 + j] * gj;
-    }
-    if (i < 15) QF(fac, (v == 0 ? F_LP : F_LP2) + i) = g;
-    __syncwarp();                                             // y consumed by every lane
-    if (i >= 5 && i < 15) PN[v * 10 + i - 5] = g;
-    __syncwarp();
-  }
-  // stage 0: P_0 dx_0 = -p_0 with the factor kept by ric1 (one lane per direction)
-  if (i == 0) {
-    double pn[10], dx[10];
-#pragma unroll
-    for (int r = 0; r < 10; ++r) pn[r] = PN[v * 10 + r];
-#pragma unroll
-    for (int j = 0; j < 10; ++j)
-#pragma unroll
-      for (int r = j + 1; r < 10; ++r) pn[r] -= T0[tri(r, j)] * pn[j];
-#pragma unroll
-    for (int r = 9; r >= 0; --r) {
-      const double invd = T0[tri(r, r)];
-      double acc = invd * pn[r];
-#pragma unroll
-      for (int c = r + 1; c < 10; ++c) acc += T0[tri(c, r)] * dx[c];
-      dx[r] = invd > 0.0 ? -acc : 0.0;
-    }
-#pragma unroll
-    for (int r = 0; r < 10; ++r) DXV[v * 10 + r] = dx[r];
-  }
-  __syncwarp();
-  // forward: stages fetch RB LP T WV P LP2 = [B_RB, B_V1) at S[f - B_RB]
-  rt_issue(rr, gsb, B_RB, B_V1 - B_RB, lane);
-  for (int k = 0; k <= N; ++k) {
-    rt_park(S, rr, B_V1 - B_RB, lane);
-    if (k < N) rt_issue(rr, gsb + (size_t)(k + 1) * sstride, B_RB, B_V1 - B_RB, lane);
-    __syncwarp();
-    const double* sb = S - B_RB;
-    const double* dx = DXV + v * 10;
-    const int lp = v == 0 ? F_LP : F_LP2;
-    qs_real* sto = v == 0 ? q.st + qs_blk(tile, N, k, NIT, pl) : q.st2 + qs_blk(tile, N, k, NS2, pl);
-    // multiplier step of the link k-1 -> k:  dpi = P_k dx_k + p_k
-    if (i < 10) {
-      double s_ = 0.0;
-      if (k > 0) {
-        s_ = sb[lp + 5 + i];
-#pragma unroll
-        for (int j = 0; j < 10; ++j) s_ += sb[F_P + trs(i, j)] * dx[j];
-      }
-      QF(sto, I_PIM + i) = s_;
-    }
-    double du = 0.0;
-    if (k < N && i < 5) {
-      double ws = sb[F_T + i * 5 + i] * sb[lp + i];
-#pragma unroll
-      for (int r = 0; r < 10; ++r) ws += sb[F_T + (5 + r) * 5 + i] * dx[r];
-      du = -ws;
-    }
-    if (k < N) {
-#pragma unroll
-      for (int c = 4; c >= 1; --c) {
-        const double duc = __shfl_sync(0xffffffffu, du, hb | c);
-        if (i < c) du -= sb[F_T + c * 5 + i] * duc;
-      }
-    }
-    if (i < 5) { DUV[v * 5 + i] = du; QF(sto, I_Z + i) = du; }
-    if (i < 10) QF(sto, I_Z + 5 + i) = dx[i];
-    __syncwarp();
-    double nx = 0.0;
-    if (k < N && i < 10) {
-      const double* duv = DUV + v * 5;
-      if (i < 5) nx = dx[i] + dt * dx[5 + i] + a2 * duv[i] + sb[H_RB + i];
-      else nx = dx[i] + dt * duv[i - 5] + sb[H_RB + i];
-    }
-    __syncwarp();
-    if (k < N && i < 10) DXV[v * 10 + i] = nx;
-    __syncwarp();
-  }
+  double* W = reinterpret_cast<double*>(rt_sm + (size_t)wi * RT_WARP_BYTES);
+  rt_ric1(*dP, q, tile, pl, lane, W, reinterpret_cast<qs_real*>(W + RT_WORK));
 }
 
 __global__ void __launch_bounds__(32 * RT_WARPS) qs_ric2t_kernel(const smpc_problem_t* __restrict__ dP, QsBufs q) {
-  extern __shared__ __align__(16) double rt_sm[];
+  extern __shared__ __align__(16) unsigned char rt_sm[];
   const int tile = blockIdx.x / (32 / RT_WARPS), wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pl = (blockIdx.x % (32 / RT_WARPS)) * RT_WARPS + wi;
   if (!QF(q.pi + qs_pb(tile, NPI, pl), J_ACT)) return;
-  rt_ric2(*dP, q, tile, pl, lane, rt_sm + (size_t)wi * RT_PER_WARP);
+  double* W = reinterpret_cast<double*>(rt_sm + (size_t)wi * RT_WARP_BYTES);
+  rt_ric2(*dP, q, tile, pl, lane, W, reinterpret_cast<qs_real*>(W + RT_WORK));
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1210,7 +855,7 @@ __global__ void __launch_bounds__(32 * RT_WARPS) qs_ric2t_kernel(const smpc_prob
 // operands: results are bit-identical to the multi-kernel path, so a problem's result does not depend on who served it.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int SOLO_THREADS = 64;
-constexpr size_t SOLO_SMEM = sizeof(double) * ((SOLO_THREADS / 32) * PREP_SCRATCH * TL + RT_PER_WARP) + 16;
+constexpr size_t SOLO_SMEM = sizeof(double) * (SOLO_THREADS / 32) * PREP_SCRATCH * TL + RT_WARP_BYTES + 16;
 
 __global__ void __launch_bounds__(SOLO_THREADS) qs_solo_kernel(const smpc_problem_t* __restrict__ dP, QsBufs q, int kk0, int32_t* status, int32_t* qp_iter,
                                                                int32_t* qp_status, double* qp_res) {
@@ -1221,7 +866,8 @@ __global__ void __launch_bounds__(SOLO_THREADS) qs_solo_kernel(const smpc_proble
   int32_t* pi = q.pi + qs_pb(tile, NPI, pl);
   if (!QF(pi, J_ACT)) return;                                // (the whole CTA: same slot)
   double* jsm = so_sm + (size_t)wi * PREP_SCRATCH * TL + lane;
-  double* S = so_sm + (size_t)(SOLO_THREADS / 32) * PREP_SCRATCH * TL;
+  double* W = so_sm + (size_t)(SOLO_THREADS / 32) * PREP_SCRATCH * TL;
+  qs_real* ring = reinterpret_cast<qs_real*>(W + RT_WORK);
 #ifdef QS_SOLO_TIMING
   long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t0 = clock64(), t1;
   int nit = 0;
@@ -1234,13 +880,13 @@ __global__ void __launch_bounds__(SOLO_THREADS) qs_solo_kernel(const smpc_proble
     __syncthreads();
     SOLO_T(0)
     if (!s_on) break;
-    if (wi == 0) rt_ric1(P, q, tile, pl, lane, S);
+    if (wi == 0) rt_ric1(P, q, tile, pl, lane, W, ring);
     __syncthreads();
     SOLO_T(1)
     for (int k = tid; k <= N; k += SOLO_THREADS) qs_step(P, q, tile, pl, k, kk, 0);
     __syncthreads();
     SOLO_T(2)
-    if (wi == 0) rt_ric2(P, q, tile, pl, lane, S);
+    if (wi == 0) rt_ric2(P, q, tile, pl, lane, W, ring);
     __syncthreads();
     SOLO_T(3)
     for (int k = tid; k <= N; k += SOLO_THREADS) qs_step(P, q, tile, pl, k, kk, 1);
@@ -1374,6 +1020,7 @@ struct QpSolver {
   bool solo_tail = false;       // ... and so is the tail of a larger solve once that few problems are left (SMPC_QP_SOLO_TAIL=1).  Off: measured on B200
                                 // (profiles/r02_solo.md) a solo iteration takes 0.42 ms against 0.23 ms for a tail iteration of the multi-kernel path
   int tail_max = 384;           // a tile group with at most this many problems still iterating is served by the warp-per-problem sweeps (0: never)
+  int tail_which = 3;           // development: bit 0 / 1 = the factorising / the vector sweep may use the warp-per-problem form (SMPC_QP_TAIL_WHICH)
   bool split_ric1 = true;       // two warps per tile in the factorising Riccati sweep (SMPC_QP_RIC1=single selects the one-warp form)
   bool coop_prep = true;        // kk >= 1: four-warp cooperative prep with TMA-staged inputs (SMPC_QP_PREP=thread selects the thread-per-stage form)
   bool profile = false;         // record one event pair per kernel of the next solves (smpc_set_profiling)
@@ -1427,6 +1074,7 @@ QpSolver* qp_create(int B, int N, int iter_max, bool keep_slots, cudaStream_t st
   if (e == cudaSuccess) e = cudaFuncSetAttribute(qs_ric1t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RT_SMEM);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(qs_ric2t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RT_SMEM);
   if (const char* te = getenv("SMPC_QP_TAIL")) s->tail_max = atoi(te);
+  if (const char* te = getenv("SMPC_QP_TAIL_WHICH")) s->tail_which = atoi(te);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(qs_solo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLO_SMEM);
   if (const char* se = getenv("SMPC_QP_SOLO")) s->solo_max = atoi(se);
   if (const char* se = getenv("SMPC_QP_SOLO_TAIL")) s->solo_tail = atoi(se) != 0;
@@ -1588,7 +1236,7 @@ struct DeviceBackend {
     {
       cudaStream_t stm_ = st(true);
       tr0("qs_ric1_kernel", stm_);
-      if (n_active_last <= s->tail_max) qs_ric1t_kernel<<<tl() * (32 / RT_WARPS), 32 * RT_WARPS, RT_SMEM, stm_>>>(dP, g->q);
+      if (n_active_last <= s->tail_max && (s->tail_which & 1)) qs_ric1t_kernel<<<tl() * (32 / RT_WARPS), 32 * RT_WARPS, RT_SMEM, stm_>>>(dP, g->q);
       else if (s->split_ric1) qs_ric1x_kernel<<<tl(), 64, RIC1X_SMEM, stm_>>>(dP, g->q);
       else qs_ric1_kernel<<<tl(), 32, RIC1_SMEM, stm_>>>(dP, g->q);
       tr1(stm_);
@@ -1599,7 +1247,7 @@ struct DeviceBackend {
     {
       cudaStream_t stm_ = st(true);
       tr0("qs_ric2_kernel", stm_);
-      if (n_active_last <= s->tail_max) qs_ric2t_kernel<<<tl() * (32 / RT_WARPS), 32 * RT_WARPS, RT_SMEM, stm_>>>(dP, g->q);
+      if (n_active_last <= s->tail_max && (s->tail_which & 2)) qs_ric2t_kernel<<<tl() * (32 / RT_WARPS), 32 * RT_WARPS, RT_SMEM, stm_>>>(dP, g->q);
       else qs_ric2_kernel<<<tl(), 32, RIC2_SMEM, stm_>>>(dP, g->q);
       tr1(stm_);
     }

@@ -836,7 +836,7 @@ SMPC_HD void qs_ric1(const smpc_problem_t& P, const QsBufs& q, int tile, W& w, d
     if (k < N) {
 #pragma unroll
       for (int i = 0; i < 5; ++i) {
-        double ws = QF(sb, F_T + i * 5 + i) * QF(sb, F_LP + i);
+        double ws = (double)QF(sb, F_T + i * 5 + i) * (double)QF(sb, F_LP + i);   // (operands widened first: fp32-storage flavour)
 #pragma unroll
         for (int r = 0; r < 10; ++r) ws += QF(sb, F_T + (5 + r) * 5 + i) * dx[r];
         du[i] = -ws;

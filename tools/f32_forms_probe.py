@@ -33,6 +33,8 @@ for controller in ('st',):
     for env in ({'SMPC_QP_TAIL': '0', 'SMPC_QP_PREP': 'thread', 'SMPC_QP_COMPACT': '0'},               # two-warp ric1
                 {'SMPC_QP_TAIL': '0', 'SMPC_QP_RIC1': 'single', 'SMPC_QP_COMPACT': '0'},              # cooperative prep
                 {'SMPC_QP_TAIL': '100000', 'SMPC_QP_PREP': 'thread', 'SMPC_QP_COMPACT': '0'},         # warp-per-problem sweeps
+                {'SMPC_QP_TAIL': '100000', 'SMPC_QP_TAIL_WHICH': '1', 'SMPC_QP_PREP': 'thread', 'SMPC_QP_RIC1': 'single', 'SMPC_QP_COMPACT': '0'},
+                {'SMPC_QP_TAIL': '100000', 'SMPC_QP_TAIL_WHICH': '2', 'SMPC_QP_PREP': 'thread', 'SMPC_QP_RIC1': 'single', 'SMPC_QP_COMPACT': '0'},
                 {'SMPC_QP_TAIL': '0', 'SMPC_QP_PREP': 'thread', 'SMPC_QP_RIC1': 'single', 'SMPC_QP_COMPACT': '1'},
                 {'SMPC_QP_SOLO': '100000', 'SMPC_QP_COMPACT': '0'}):
         o = solve(controller, env)

@@ -199,6 +199,15 @@ int smpc_set_plant_inertial(smpc_handle_t* h, const double* inertial, int32_t me
 /* additive torque noise drawn by the host with default_rng(seed=i) (mpc.py:126, env_model.py:196), [B][NU] */
 int smpc_set_torque_noise(smpc_handle_t* h, const double* tau_noise, int32_t mem);
 
+/* --- stage parameters of the cost: the end-effector reference per stage ---
+ * The reference sets p = [cost.traj[:, current_step + i], alpha, gate] on every stage of every solve (controller.py:153-156); for the
+ * reach costs cost.traj is ee_ref repeated (cost_definition.py:29-31,67,89), for the tracking costs a time-indexed path (Tracking8*,
+ * TrackingMovingCircle*, cost_definition.py:102-288).  traj[n][3] is that array (one row per control step, shared by the batch like
+ * the reference's cost object); stage k of problem b is linearised around traj[min(current_step[b] + k, n - 1)], current_step being
+ * the per-problem counter that smpc_controller_step advances and smpc_reset_controller clears.  n = 0: back to the constant
+ * smpc_problem_t::ee_ref.  (alpha and the gate are per handle / per problem state: smpc_problem_t::alpha, SMPC_STATE_R.) */
+int smpc_set_ee_trajectory(smpc_handle_t* h, const double* traj, int32_t n, int32_t mem);
+
 /* --- warm start (controller.py:195-200,390-393) --- */
 int smpc_set_guess(smpc_handle_t* h, const double* xg, const double* ug, int32_t mem);
 int smpc_get_guess(smpc_handle_t* h, double* xg, double* ug, int32_t mem);

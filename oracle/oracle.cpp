@@ -60,6 +60,7 @@ struct orc_handle {
   double probe_eps = 0.0;
   std::vector<int32_t> probe_flips;
   std::vector<double> xg, ug, xt, ut, lin, plant_inertial, tau_noise, x_viable;
+  std::vector<double> ee_traj;   // [n][3] end-effector reference per control step (cost.traj of the reference); empty: P.ee_ref
   std::vector<double> qp_z, qp_pi, qp_lam, qp_t, qp_res;
   std::vector<int32_t> fails, r, status, qp_iter, qp_status, cur_step, cand;
   std::vector<Workspace> ws;   // one per thread
@@ -123,7 +124,8 @@ bool stage_has_nn(const orc_problem_t& P, int k) {
 }
 
 // One stage of the linearisation -> stage record (layout in include/safe_mpc_b200.h)
-void linearize_stage(const orc_handle& h, int k, const double* x, const double* u, const double* xnext, bool gate_on, double* rec) {
+// ee_ref: p[0:3] of this stage = cost.traj[:, current_step + k] (controller.py:153-156)
+void linearize_stage(const orc_handle& h, int k, const double* x, const double* u, const double* xnext, bool gate_on, const double* ee_ref, double* rec) {
   const orc_problem_t& P = h.P;
   const int N = P.N;
   const bool term = (k == N);
@@ -140,7 +142,7 @@ void linearize_stage(const orc_handle& h, int k, const double* x, const double* 
     for (int i = 0; i < NQ; ++i) qd[i] = Dual2<NQ>::var(q[i], i);
     fk_points<Dual2<NQ>>(P, qd, pts);
     Dual2<NQ> c(0.0);
-    for (int d = 0; d < 3; ++d) { Dual2<NQ> e = pts[0][d] - P.ee_ref[d]; c = c + e * e; }
+    for (int d = 0; d < 3; ++d) { Dual2<NQ> e = pts[0][d] - ee_ref[d]; c = c + e * e; }
     c = c * P.q_weight;
     for (int i = 0; i < NQ; ++i) rec[SMPC_REC_G + NU + i] = s * c.g[i];
     int o = 0;
@@ -152,7 +154,7 @@ void linearize_stage(const orc_handle& h, int k, const double* x, const double* 
     fk_points<Dual<NQ>>(P, qd, pts);
     for (int i = 0; i < NQ; ++i) {
       double g = 0.0;
-      for (int d = 0; d < 3; ++d) g += pts[0][d].d[i] * (pts[0][d].v - P.ee_ref[d]);
+      for (int d = 0; d < 3; ++d) g += pts[0][d].d[i] * (pts[0][d].v - ee_ref[d]);
       rec[SMPC_REC_G + NU + i] = s * P.q_weight * g;
     }
     int o = 0;
@@ -297,7 +299,12 @@ int rti_solve_one(orc_handle& h, int b, const double* x0, Workspace& W) {
   QpIpm& qp = *W.qp;
   for (int k = 0; k <= N; ++k) {
     double* rec = lin + (size_t)k * REC;
-    linearize_stage(h, k, xg + k * NX, k < N ? ug + k * NU : nullptr, k < N ? xg + (k + 1) * NX : nullptr, gate_on(h, b, k), rec);
+    const double* eer = P.ee_ref;
+    if (!h.ee_traj.empty()) {
+      const int n = (int)(h.ee_traj.size() / 3), c = h.cur_step[b] + k;
+      eer = &h.ee_traj[3 * (size_t)(c < n - 1 ? c : n - 1)];
+    }
+    linearize_stage(h, k, xg + k * NX, k < N ? ug + k * NU : nullptr, k < N ? xg + (k + 1) * NX : nullptr, gate_on(h, b, k), eer, rec);
     double lo[NX], hi[NX];
     stage_box(h, b, k, x0, lo, hi);
     assemble_stage(P, k, rec, lo, hi, qp.stages()[k]);
@@ -612,6 +619,11 @@ int orc_get_probe_flips(orc_handle_t* h, int32_t* out) {
 }
 
 int orc_set_plant_inertial(orc_handle_t* h, const double* v) { std::copy(v, v + h->plant_inertial.size(), h->plant_inertial.begin()); return SMPC_OK; }
+int orc_set_ee_trajectory(orc_handle_t* h, const double* traj, int32_t n) {
+  if (n < 0 || (n > 0 && !traj)) return SMPC_ERR_ARG;
+  h->ee_traj.assign(traj, traj + 3 * (size_t)n);
+  return SMPC_OK;
+}
 int orc_set_torque_noise(orc_handle_t* h, const double* v) { std::copy(v, v + h->tau_noise.size(), h->tau_noise.begin()); return SMPC_OK; }
 int orc_set_guess(orc_handle_t* h, const double* xg, const double* ug) {
   std::copy(xg, xg + h->xg.size(), h->xg.begin());

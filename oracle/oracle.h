@@ -59,6 +59,8 @@ int orc_get_probe_flips(orc_handle_t* h, int32_t* out);
 
 int orc_set_plant_inertial(orc_handle_t* h, const double* inertial);
 int orc_set_torque_noise(orc_handle_t* h, const double* tau_noise);
+/* cost.traj of the reference (controller.py:153-156, cost_definition.py:29-31,102-288): see smpc_set_ee_trajectory */
+int orc_set_ee_trajectory(orc_handle_t* h, const double* traj, int32_t n);
 int orc_set_guess(orc_handle_t* h, const double* xg, const double* ug);
 int orc_get_guess(orc_handle_t* h, double* xg, double* ug);
 int orc_get_temp(orc_handle_t* h, double* x_temp, double* u_temp);

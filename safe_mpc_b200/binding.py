@@ -109,6 +109,18 @@ class EngineBase:
         p, m, k = self._in(noise, np.float64, (self.B, abi.NU))
         self._call('set_torque_noise', p, mem=m)
 
+    def set_ee_trajectory(self, traj):
+        """cost.traj of the reference (controller.py:153-156): traj [n, 3], one end-effector reference per control step; None or an
+        empty array restores the constant ee_ref of the problem struct"""
+        if traj is None or len(traj) == 0:
+            args = [_P(0), C.c_int32(0)]
+            m = abi.HOST
+        else:
+            n = int(len(traj))
+            p_, m, k = self._in(traj, np.float64, (n, 3))
+            args = [p_, C.c_int32(n)]
+        self._call('set_ee_trajectory', *args, mem=m)
+
     def set_guess(self, xg, ug):
         px, mx, kx = self._in(xg, np.float64, (self.B, self.N + 1, abi.NX))
         pu, mu, ku = self._in(ug, np.float64, (self.B, self.N, abi.NU))

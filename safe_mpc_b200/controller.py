@@ -43,9 +43,17 @@ class AbstractController:
         self.ocp_solver._keepalive = (prob, keep)
         self.ocp_solver.set_plant_inertial(self.model.plant_inertial)
         self.ocp_solver.set_torque_noise(self.model.torque_noise)
+        self._upload_trajectory()
         self.build_flag = True
         if self._pending_guess is not None:
             self.setGuess(*self._pending_guess)
+
+    def _upload_trajectory(self):
+        """The stage parameters p[0:3] of the reference: cost.traj[:, current_step + i] on stage i of every solve (controller.py:153-156).
+        A tracking cost hands its whole path to the engine, which indexes it with the per-problem step counter; the reach costs keep
+        the constant ee_ref of the problem struct."""
+        if self.cost is not None and getattr(self.cost, 'tracking', False):
+            self.ocp_solver.set_ee_trajectory(np.ascontiguousarray(self.cost.traj.T))
 
     def resetHorizon(self, N):
         """controller.py:203-214.  The horizon is a creation parameter of an engine handle: changing it re-creates the handle."""
@@ -53,9 +61,14 @@ class AbstractController:
         if N != self.N or not self.build_flag:
             self.N = N
             self.model.params.N = N
+            if self.cost is not None:
+                self.cost.update_trajectory()                # controller.py:214
             if self.build_flag:
                 self.ocp_solver.close()
                 self.build_controller()
+        elif self.cost is not None and getattr(self.cost, 'tracking', False):
+            self.cost.update_trajectory()
+            self._upload_trajectory()
 
     def _solver(self):
         if not self.build_flag:

@@ -24,6 +24,8 @@ struct smpc_handle {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   int64_t launches = 0;
+  double* ee_traj = nullptr;        // [n_traj][3] end-effector reference per control step (smpc_set_ee_trajectory); n_traj = 0: P.ee_ref
+  int n_traj = 0;
   std::string err;
   std::vector<void*> allocs;
   // network
@@ -155,7 +157,7 @@ int solve_pipeline(smpc_handle* h, const double* x0_dev, const uint8_t* act) {
     const int mode = h->P.nn_rows == SMPC_NN_TERMINAL ? ROWS_TERMINAL : (h->P.nn_rows == SMPC_NN_EVERYWHERE ? ROWS_ALL : (h->P.nn_rows == SMPC_NN_PARALLEL ? ROWS_CAND : ROWS_RECEDING));
     run_mlp(h, B, N, mode, 0, h->xg, act, nullptr, h->nn11, true);
   }
-  launch_linearize(c, h->dP, B, N, h->xg, h->ug, h->P.nn_rows == SMPC_NN_PARALLEL ? h->cand : h->r, act, h->nn11, QPCALL(h, qp_rec), h->qpf != nullptr);
+  launch_linearize(c, h->dP, B, N, h->xg, h->ug, h->P.nn_rows == SMPC_NN_PARALLEL ? h->cand : h->r, act, h->nn11, h->ee_traj, h->n_traj, h->cur_step, QPCALL(h, qp_rec), h->qpf != nullptr);
   if (h->timed) cudaEventRecord(h->ev[1], h->stream);
   cudaError_t qe = h->qpf ? f32::launch_qp_solve(c, h->dP, h->qpf, x0_dev, h->r, act, h->xt, h->ut, h->status, h->qp_iter, h->qp_status, h->qp_res)
                           : f64::launch_qp_solve(c, h->dP, h->qp, x0_dev, h->r, act, h->xt, h->ut, h->status, h->qp_iter, h->qp_status, h->qp_res);
@@ -241,6 +243,7 @@ int smpc_create(const smpc_problem_t* prob, int32_t batch, int32_t device, smpc_
   CKC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   for (auto& ev : h->ev) CKC(cudaEventCreate(&ev));
   CKC(mlp_prepare());
+  CKC(linearize_prepare());
   // network weights: original + transposed copies of the two square layers
   if (prob->nn_weights) {
     const size_t np = SMPC_NN_NPARAM, sq = (size_t)SMPC_HID * SMPC_HID;
@@ -350,6 +353,7 @@ void smpc_destroy(smpc_handle_t* h) {
   f64::qp_destroy(h->qp);
   f32::qp_destroy(h->qpf);
   if (h->stage) cudaFree(h->stage);
+  if (h->ee_traj) cudaFree(h->ee_traj);
   for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -357,6 +361,22 @@ void smpc_destroy(smpc_handle_t* h) {
 
 int smpc_set_plant_inertial(smpc_handle_t* h, const double* v, int32_t mem) { return copy_in(h, h->plant_inertial, v, sizeof(double) * h->B * NQ * 10, mem); }
 int smpc_set_torque_noise(smpc_handle_t* h, const double* v, int32_t mem) { return copy_in(h, h->tau_noise, v, sizeof(double) * h->B * NU, mem); }
+
+int smpc_set_ee_trajectory(smpc_handle_t* h, const double* traj, int32_t n, int32_t mem) {
+  if (!h) return SMPC_ERR_ARG;
+  if (n < 0 || (n > 0 && !traj)) return fail(h, SMPC_ERR_ARG, "smpc_set_ee_trajectory: n < 0 or missing array");
+  if (cudaSetDevice(h->device) != cudaSuccess) return fail(h, SMPC_ERR_CUDA, "cudaSetDevice", cudaGetLastError());
+  cudaStreamSynchronize(h->stream);                         // no solve may still read the array that is replaced
+  if (h->ee_traj) { cudaFree(h->ee_traj); h->ee_traj = nullptr; }
+  h->n_traj = 0;
+  if (n == 0) return SMPC_OK;
+  cudaError_t e = cudaMalloc((void**)&h->ee_traj, sizeof(double) * 3 * (size_t)n);
+  if (e != cudaSuccess) return fail(h, SMPC_ERR_CUDA, "smpc_set_ee_trajectory: cudaMalloc", e);
+  const int rc = copy_in(h, h->ee_traj, traj, sizeof(double) * 3 * (size_t)n, mem);
+  if (rc) return rc;
+  h->n_traj = n;
+  return SMPC_OK;
+}
 
 int smpc_set_guess(smpc_handle_t* h, const double* xg, const double* ug, int32_t mem) {
   int rc = copy_in(h, h->xg, xg, sizeof(double) * h->B * (h->N + 1) * NX, mem);

@@ -79,38 +79,87 @@ SMPC_HD V3 inertia_mul(const double* I10, V3 w) {   // I10 = m, c[3], Ixx,Iyy,Iz
 }
 
 // ------------------------------------------------------------------------------------------------ RNEA
+// Results of the nominal pass that the tangent passes read.  Two homes: thread-private (`Rnea`: registers / local memory -- host
+// emulation, plant kernel, thread-per-stage linearisation) or shared memory (`RneaSm`: field f of this lane at p[32 f] -- cooperative
+// linearisation kernel, where several warps read the state of the same 32 problems and index it with run-time joint numbers).
 struct Rnea {
   M3 R[NQ];                 // parent <- body
   V3 w[NQ], wd[NQ], vd[NQ]; // body angular velocity / acceleration, linear acceleration of the frame origin
   V3 f[NQ], n[NQ];          // accumulated wrench transmitted through joint i, body frame i
 };
+SMPC_HD M3 get_R(const Rnea& S, int i) { return S.R[i]; }
+SMPC_HD V3 get_w(const Rnea& S, int i) { return S.w[i]; }
+SMPC_HD V3 get_wd(const Rnea& S, int i) { return S.wd[i]; }
+SMPC_HD V3 get_vd(const Rnea& S, int i) { return S.vd[i]; }
+SMPC_HD V3 get_f(const Rnea& S, int i) { return S.f[i]; }
+SMPC_HD V3 get_n(const Rnea& S, int i) { return S.n[i]; }
+SMPC_HD void set_R(Rnea& S, int i, const M3& r) { S.R[i] = r; }
+SMPC_HD void set_w(Rnea& S, int i, V3 a) { S.w[i] = a; }
+SMPC_HD void set_wd(Rnea& S, int i, V3 a) { S.wd[i] = a; }
+SMPC_HD void set_vd(Rnea& S, int i, V3 a) { S.vd[i] = a; }
+SMPC_HD void set_f(Rnea& S, int i, V3 a) { S.f[i] = a; }
+SMPC_HD void set_n(Rnea& S, int i, V3 a) { S.n[i] = a; }
+
+enum { SM_LANES = 32 };
+enum { RS_R = 0, RS_W = 9 * NQ, RS_WD = RS_W + 3 * NQ, RS_VD = RS_WD + 3 * NQ, RS_F = RS_VD + 3 * NQ, RS_N = RS_F + 3 * NQ, RS_SIZE = RS_N + 3 * NQ };
+struct RneaSm {
+  double* p;                // shared memory, lane offset applied
+};
+SMPC_HD V3 sm_ld3(const double* p, int f) { return v3(p[(f)*SM_LANES], p[(f + 1) * SM_LANES], p[(f + 2) * SM_LANES]); }
+SMPC_HD void sm_st3(double* p, int f, V3 a) { p[(f)*SM_LANES] = a.x; p[(f + 1) * SM_LANES] = a.y; p[(f + 2) * SM_LANES] = a.z; }
+SMPC_HD M3 sm_ld9(const double* p, int f) {
+  M3 r;
+#pragma unroll
+  for (int e = 0; e < 9; ++e) r.m[e] = p[(f + e) * SM_LANES];
+  return r;
+}
+SMPC_HD void sm_st9(double* p, int f, const M3& r) {
+#pragma unroll
+  for (int e = 0; e < 9; ++e) p[(f + e) * SM_LANES] = r.m[e];
+}
+SMPC_HD M3 get_R(const RneaSm& S, int i) { return sm_ld9(S.p, RS_R + 9 * i); }
+SMPC_HD V3 get_w(const RneaSm& S, int i) { return sm_ld3(S.p, RS_W + 3 * i); }
+SMPC_HD V3 get_wd(const RneaSm& S, int i) { return sm_ld3(S.p, RS_WD + 3 * i); }
+SMPC_HD V3 get_vd(const RneaSm& S, int i) { return sm_ld3(S.p, RS_VD + 3 * i); }
+SMPC_HD V3 get_f(const RneaSm& S, int i) { return sm_ld3(S.p, RS_F + 3 * i); }
+SMPC_HD V3 get_n(const RneaSm& S, int i) { return sm_ld3(S.p, RS_N + 3 * i); }
+SMPC_HD void set_R(RneaSm& S, int i, const M3& r) { sm_st9(S.p, RS_R + 9 * i, r); }
+SMPC_HD void set_w(RneaSm& S, int i, V3 a) { sm_st3(S.p, RS_W + 3 * i, a); }
+SMPC_HD void set_wd(RneaSm& S, int i, V3 a) { sm_st3(S.p, RS_WD + 3 * i, a); }
+SMPC_HD void set_vd(RneaSm& S, int i, V3 a) { sm_st3(S.p, RS_VD + 3 * i, a); }
+SMPC_HD void set_f(RneaSm& S, int i, V3 a) { sm_st3(S.p, RS_F + 3 * i, a); }
+SMPC_HD void set_n(RneaSm& S, int i, V3 a) { sm_st3(S.p, RS_N + 3 * i, a); }
 
 // tau = M(q) a + h(q, v) of the chain with inertial parameters `I` ([NQ][10]); fills `S` for the tangent passes
+template <class RS>
 SMPC_HD void rnea(const smpc_problem_t& P, const double (*I)[10], const double* q, const double* v, const double* a,
-                  Rnea& S, double* tau) {
+                  RS& S, double* tau) {
   V3 w = v3(0, 0, 0), wd = v3(0, 0, 0), vd = v3(-P.gravity[0], -P.gravity[1], -P.gravity[2]);
 #pragma unroll
   for (int i = 0; i < NQ; ++i) {
-    S.R[i] = joint_rot(P, i, q[i]);
+    const M3 Ri = joint_rot(P, i, q[i]);
+    set_R(S, i, Ri);
     const V3 ax = v3(P.joint_axis[i]), p = v3(P.joint_p[i]);
     const V3 acc = vd + cross(wd, p) + cross(w, cross(w, p));
-    vd = mulT(S.R[i], acc);
+    vd = mulT(Ri, acc);
     const V3 av = v[i] * ax;
-    w = mulT(S.R[i], w) + av;
-    wd = mulT(S.R[i], wd) + a[i] * ax + cross(w, av);
-    S.w[i] = w; S.wd[i] = wd; S.vd[i] = vd;
+    w = mulT(Ri, w) + av;
+    wd = mulT(Ri, wd) + a[i] * ax + cross(w, av);
+    set_w(S, i, w); set_wd(S, i, wd); set_vd(S, i, vd);
     const V3 c = v3(&I[i][1]);
     const V3 F = I[i][0] * (vd + cross(wd, c) + cross(w, cross(w, c)));
     const V3 Nn = inertia_mul(I[i], wd) + cross(w, inertia_mul(I[i], w)) + cross(c, F);
-    S.f[i] = F; S.n[i] = Nn;
+    set_f(S, i, F); set_n(S, i, Nn);
   }
 #pragma unroll
   for (int i = NQ - 1; i >= 0; --i) {
-    tau[i] = dot(v3(P.joint_axis[i]), S.n[i]);
+    const V3 ni = get_n(S, i);
+    tau[i] = dot(v3(P.joint_axis[i]), ni);
     if (i > 0) {
-      const V3 fp = mul(S.R[i], S.f[i]);
-      S.f[i - 1] = S.f[i - 1] + fp;
-      S.n[i - 1] = S.n[i - 1] + mul(S.R[i], S.n[i]) + cross(v3(P.joint_p[i]), fp);
+      const M3 Ri = get_R(S, i);
+      const V3 fp = mul(Ri, get_f(S, i));
+      set_f(S, i - 1, get_f(S, i - 1) + fp);
+      set_n(S, i - 1, get_n(S, i - 1) + mul(Ri, ni) + cross(v3(P.joint_p[i]), fp));
     }
   }
 }
@@ -118,19 +167,20 @@ SMPC_HD void rnea(const smpc_problem_t& P, const double (*I)[10], const double* 
 enum { TAN_Q = 0, TAN_V = 1, TAN_U = 2 };
 
 // d tau / d (q_j | v_j | u_j) given the nominal pass `S` (v: joint velocities, u: joint accelerations)
-template <int MODE>
-SMPC_HD void rnea_tangent(const smpc_problem_t& P, const double (*I)[10], const Rnea& S, const double* v, const double* u,
+template <int MODE, class RS>
+SMPC_HD void rnea_tangent(const smpc_problem_t& P, const double (*I)[10], const RS& S, const double* v, const double* u,
                           int j, double* dtau) {
   V3 dF[NQ], dN[NQ];
   V3 dw, dwd, dvd;
   const V3 aj = v3(P.joint_axis[j]);
   if (MODE == TAN_Q) {
-    dw = cross(S.w[j], aj);
-    const V3 rwd = S.wd[j] - u[j] * aj - cross(S.w[j], v[j] * aj);   // R_j^T wd_{j-1}
+    const V3 wj = get_w(S, j);
+    dw = cross(wj, aj);
+    const V3 rwd = get_wd(S, j) - u[j] * aj - cross(wj, v[j] * aj);   // R_j^T wd_{j-1}
     dwd = cross(rwd, aj) + cross(dw, v[j] * aj);
-    dvd = cross(S.vd[j], aj);
+    dvd = cross(get_vd(S, j), aj);
   } else if (MODE == TAN_V) {
-    dw = aj; dwd = cross(S.w[j], aj); dvd = v3(0, 0, 0);
+    dw = aj; dwd = cross(get_w(S, j), aj); dvd = v3(0, 0, 0);
   } else {
     dw = v3(0, 0, 0); dwd = aj; dvd = v3(0, 0, 0);
   }
@@ -139,15 +189,16 @@ SMPC_HD void rnea_tangent(const smpc_problem_t& P, const double (*I)[10], const 
     if (i < j) { dF[i] = v3(0, 0, 0); dN[i] = v3(0, 0, 0); continue; }
     if (i > j) {
       const V3 p = v3(P.joint_p[i]);
-      const V3 wp = S.w[i - 1];
+      const V3 wp = get_w(S, i - 1);
+      const M3 Ri = get_R(S, i);
       V3 t = dvd + cross(dwd, p);
       if (MODE != TAN_U) t = t + cross(dw, cross(wp, p)) + cross(wp, cross(dw, p));
-      dvd = mulT(S.R[i], t);
-      dwd = mulT(S.R[i], dwd);
-      if (MODE != TAN_U) { dw = mulT(S.R[i], dw); dwd = dwd + cross(dw, v[i] * v3(P.joint_axis[i])); }
+      dvd = mulT(Ri, t);
+      dwd = mulT(Ri, dwd);
+      if (MODE != TAN_U) { dw = mulT(Ri, dw); dwd = dwd + cross(dw, v[i] * v3(P.joint_axis[i])); }
     }
     const V3 c = v3(&I[i][1]);
-    const V3 w = S.w[i];
+    const V3 w = get_w(S, i);
     V3 t = dvd + cross(dwd, c);
     if (MODE != TAN_U) t = t + cross(dw, cross(w, c)) + cross(w, cross(dw, c));
     dF[i] = I[i][0] * t;
@@ -163,11 +214,12 @@ SMPC_HD void rnea_tangent(const smpc_problem_t& P, const double (*I)[10], const 
     if (i > 0) {
       if (MODE == TAN_Q && i == j) {
         // nominal accumulated wrench of body j is S.f[j], S.n[j]
-        fi = fi + cross(aj, S.f[j]);
-        ni = ni + cross(aj, S.n[j]);
+        fi = fi + cross(aj, get_f(S, j));
+        ni = ni + cross(aj, get_n(S, j));
       }
-      cf = mul(S.R[i], fi);
-      cn = mul(S.R[i], ni) + cross(v3(P.joint_p[i]), cf);
+      const M3 Ri = get_R(S, i);
+      cf = mul(Ri, fi);
+      cn = mul(Ri, ni) + cross(v3(P.joint_p[i]), cf);
     }
   }
 }
@@ -178,8 +230,19 @@ struct Fk {
   V3 o[NQ];       // body-frame origins (= joint origins) in the world
   V3 z[NQ];       // joint axes in the world
 };
+enum { FK_RW = 0, FK_O = 9 * NQ, FK_Z = FK_O + 3 * NQ, FK_SIZE = FK_Z + 3 * NQ };
+struct FkSm {
+  double* p;      // shared memory, lane offset applied (same layout convention as RneaSm)
+};
+SMPC_HD V3 get_o(const Fk& K, int i) { return K.o[i]; }
+SMPC_HD V3 get_z(const Fk& K, int i) { return K.z[i]; }
+SMPC_HD void set_fk(Fk& K, int i, const M3& Rc, V3 oc, V3 z) { K.Rw[i] = Rc; K.o[i] = oc; K.z[i] = z; }
+SMPC_HD V3 get_o(const FkSm& K, int i) { return sm_ld3(K.p, FK_O + 3 * i); }
+SMPC_HD V3 get_z(const FkSm& K, int i) { return sm_ld3(K.p, FK_Z + 3 * i); }
+SMPC_HD void set_fk(FkSm& K, int i, const M3& Rc, V3 oc, V3 z) { sm_st9(K.p, FK_RW + 9 * i, Rc); sm_st3(K.p, FK_O + 3 * i, oc); sm_st3(K.p, FK_Z + 3 * i, z); }
 
-SMPC_HD void fk(const smpc_problem_t& P, const double* q, Fk& K) {
+template <class KS>
+SMPC_HD void fk(const smpc_problem_t& P, const double* q, KS& K) {
   M3 Rc;
   Rc.m[0] = 1; Rc.m[1] = 0; Rc.m[2] = 0; Rc.m[3] = 0; Rc.m[4] = 1; Rc.m[5] = 0; Rc.m[6] = 0; Rc.m[7] = 0; Rc.m[8] = 1;
   V3 oc = v3(0, 0, 0);
@@ -187,10 +250,12 @@ SMPC_HD void fk(const smpc_problem_t& P, const double* q, Fk& K) {
   for (int i = 0; i < NQ; ++i) {
     oc = oc + mul(Rc, v3(P.joint_p[i]));
     Rc = matmul(Rc, joint_rot(P, i, q[i]));
-    K.Rw[i] = Rc; K.o[i] = oc; K.z[i] = mul(Rc, v3(P.joint_axis[i]));
+    set_fk(K, i, Rc, oc, mul(Rc, v3(P.joint_axis[i])));
   }
 }
 
+// world position of point p: thread-private state is selected with compile-time indices (a run-time index would send the whole
+// struct to local memory), the shared-memory state is addressed directly
 SMPC_HD V3 point_world(const smpc_problem_t& P, const Fk& K, int p) {
   const int b = P.point_body[p];
   const V3 l = v3(P.point_local[p]);
@@ -200,12 +265,19 @@ SMPC_HD V3 point_world(const smpc_problem_t& P, const Fk& K, int p) {
   for (int i = 0; i < NQ; ++i) if (i == b) r = K.o[i] + mul(K.Rw[i], l);
   return r;
 }
+SMPC_HD V3 point_world(const smpc_problem_t& P, const FkSm& K, int p) {
+  const int b = P.point_body[p];
+  const V3 l = v3(P.point_local[p]);
+  if (b < 0) return l;
+  return get_o(K, b) + mul(sm_ld9(K.p, FK_RW + 9 * b), l);
+}
 
 // J[:, j] = z_j x (Pw - o_j) for j <= body, else 0
-SMPC_HD void point_jacobian(const smpc_problem_t& P, const Fk& K, int p, V3 Pw, V3* J) {
+template <class KS>
+SMPC_HD void point_jacobian(const smpc_problem_t& P, const KS& K, int p, V3 Pw, V3* J) {
   const int b = P.point_body[p];
 #pragma unroll
-  for (int j = 0; j < NQ; ++j) J[j] = (j <= b) ? cross(K.z[j], Pw - K.o[j]) : v3(0, 0, 0);
+  for (int j = 0; j < NQ; ++j) J[j] = (j <= b) ? cross(get_z(K, j), Pw - get_o(K, j)) : v3(0, 0, 0);
 }
 
 // --------------------------------------------------------------------------- capsule segment distance
@@ -329,38 +401,31 @@ SMPC_HD bool collision_free(const smpc_problem_t& P, const double* x) {         
 // one stage of the linearisation -> stage record (viability row value/gradient are supplied by the MLP kernel);
 // `rs` = stride between consecutive record fields (32 in the device layout [tile][stage][field][32 problems])
 // R: element type of the record array (double, or float for the fp32-storage flavour of the QP solver: values are rounded on store)
-template <class R>
-SMPC_HD void linearize_stage(const smpc_problem_t& P, int k, const double* x, const double* u, const double* xnext,
-                             bool has_nn, bool gate_on, const double* nn11, R* rec, int rs = 1) {
-  const int N = P.N;
-  const bool term = (k == N);
+// The pieces below are shared by the thread-per-stage form (linearize_stage: host emulation, SMPC_LIN=thread) and the cooperative
+// kernel (kernels.cu: linearize_coop_kernel), which runs them on different warps of a CTA.
+// -- cost rows: gradient, exact Hessian of the end-effector term (cost_definition.py:83-100), control weight, LM scalars
+// ee_ref: end-effector reference of this stage (smpc_problem_t::ee_ref, or a row of the trajectory of smpc_set_ee_trajectory)
+template <class R, class KS>
+SMPC_HD void lin_cost(const smpc_problem_t& P, int k, const KS& K, const double* u, const double* ee_ref, R* rec, int rs) {
+  const bool term = (k == P.N);
   const double s = term ? 1.0 : P.dt;
-  for (int i = 0; i < REC; ++i) rec[(size_t)rs * (i)] = 0.0;
-#pragma unroll
-  for (int i = 0; i < NX; ++i) rec[(size_t)rs * (SMPC_REC_X + i)] = x[i];
-  if (!term)
-#pragma unroll
-    for (int i = 0; i < NU; ++i) rec[(size_t)rs * (SMPC_REC_U + i)] = u[i];
-  const double* q = x;
-  const double* v = x + NQ;
-  Fk K;
-  fk(P, q, K);
-  // ---- cost ----
   double hu = 0.0;
   if (P.cost_type != SMPC_COST_ZERO) {
     const V3 Pw = point_world(P, K, 0);
     V3 J[NQ];
     point_jacobian(P, K, 0, Pw, J);
-    const V3 e = Pw - v3(P.ee_ref);
+    const V3 e = Pw - v3(ee_ref);
     const bool ext = P.cost_type == SMPC_COST_EXT;
     const double wq = (ext ? 2.0 : 1.0) * P.q_weight * s;
     const int be = P.point_body[0];
     int o = 0;
+#pragma unroll
     for (int i = 0; i < NQ; ++i) {
       rec[(size_t)rs * (SMPC_REC_G + NU + i)] = wq * dot(J[i], e);
+#pragma unroll
       for (int j = 0; j <= i; ++j) {
         double h = dot(J[i], J[j]);
-        if (ext && i <= be) h += dot(e, cross(K.z[j], cross(K.z[i], Pw - K.o[i])));   // j <= i: d2P/dq_j dq_i
+        if (ext && i <= be) h += dot(e, cross(get_z(K, j), cross(get_z(K, i), Pw - get_o(K, i))));   // j <= i: d2P/dq_j dq_i
         rec[(size_t)rs * (SMPC_REC_HQQ + o++)] = wq * h;
       }
     }
@@ -375,37 +440,41 @@ SMPC_HD void linearize_stage(const smpc_problem_t& P, int k, const double* x, co
   rec[(size_t)rs * (SMPC_REC_HU)] = term ? 0.0 : hu + lmk;
   rec[(size_t)rs * (SMPC_REC_HV)] = lmk;
   rec[(size_t)rs * (SMPC_REC_HQ)] = lmk;
-  // ---- torque rows ----
-  if (!term) {
-    Rnea S;
-    double tau[NQ], d[NQ];
-    rnea(P, P.inertial, q, v, u, S, tau);
+}
+// -- column `col` (0..14: u_j, q_j, v_j) of the torque Jacobian
+template <int MODE, class R, class RS>
+SMPC_HD void lin_tau_col(const smpc_problem_t& P, const RS& S, const double* v, const double* u, int j, R* rec, int rs) {
+  double d[NQ];
+  rnea_tangent<MODE>(P, P.inertial, S, v, u, j, d);
+  const int col = MODE == TAN_U ? j : (MODE == TAN_Q ? NU + j : NU + NQ + j);
 #pragma unroll
-    for (int i = 0; i < NU; ++i) rec[(size_t)rs * (SMPC_REC_TAU + i)] = tau[i];
-    for (int j = 0; j < NQ; ++j) {
-      rnea_tangent<TAN_U>(P, P.inertial, S, v, u, j, d);
-      for (int i = 0; i < NU; ++i) rec[(size_t)rs * (SMPC_REC_JTAU + i * 15 + j)] = d[i];
-      rnea_tangent<TAN_Q>(P, P.inertial, S, v, u, j, d);
-      for (int i = 0; i < NU; ++i) rec[(size_t)rs * (SMPC_REC_JTAU + i * 15 + NU + j)] = d[i];
-      rnea_tangent<TAN_V>(P, P.inertial, S, v, u, j, d);
-      for (int i = 0; i < NU; ++i) rec[(size_t)rs * (SMPC_REC_JTAU + i * 15 + NU + NQ + j)] = d[i];
-    }
+  for (int i = 0; i < NU; ++i) rec[(size_t)rs * (SMPC_REC_JTAU + i * 15 + col)] = d[i];
+}
+// -- capsule pair p: squared distance and its gradient
+template <class R, class KS>
+SMPC_HD void lin_pair(const smpc_problem_t& P, const KS& K, int p, R* rec, int rs) {
+  const V3 A = point_world(P, K, P.pair_pa[p]), Bp = point_world(P, K, P.pair_pb[p]);
+  V3 gA, gB, JA[NQ], JB[NQ];
+  const double d = segment_dist_grad(A, Bp, v3(P.pair_C[p]), v3(P.pair_D[p]), &gA, &gB);
+  point_jacobian(P, K, P.pair_pa[p], A, JA);
+  point_jacobian(P, K, P.pair_pb[p], Bp, JB);
+  rec[(size_t)rs * (SMPC_REC_DIST + p)] = d;
+#pragma unroll
+  for (int j = 0; j < NQ; ++j) rec[(size_t)rs * (SMPC_REC_JDIST + p * NQ + j)] = dot(gA, JA[j]) + dot(gB, JB[j]);
+}
+// -- guess, row counts, viability row, dynamics offset
+template <class R>
+SMPC_HD void lin_misc(const smpc_problem_t& P, int k, const double* x, const double* u, const double* xnext, bool has_nn, bool gate_on,
+                      const double* nn11, R* rec, int rs) {
+  const bool term = (k == P.N);
+#pragma unroll
+  for (int i = 0; i < NX; ++i) rec[(size_t)rs * (SMPC_REC_X + i)] = x[i];
+  if (!term) {
+#pragma unroll
+    for (int i = 0; i < NU; ++i) rec[(size_t)rs * (SMPC_REC_U + i)] = u[i];
     rec[(size_t)rs * (SMPC_REC_NTAU)] = NU;
   }
-  // ---- capsule rows ----
-  if (k > 0 || P.stage0_collision_rows) {
-    for (int p = 0; p < NPAIR; ++p) {
-      const V3 A = point_world(P, K, P.pair_pa[p]), Bp = point_world(P, K, P.pair_pb[p]);
-      V3 gA, gB, JA[NQ], JB[NQ];
-      const double d = segment_dist_grad(A, Bp, v3(P.pair_C[p]), v3(P.pair_D[p]), &gA, &gB);
-      point_jacobian(P, K, P.pair_pa[p], A, JA);
-      point_jacobian(P, K, P.pair_pb[p], Bp, JB);
-      rec[(size_t)rs * (SMPC_REC_DIST + p)] = d;
-      for (int j = 0; j < NQ; ++j) rec[(size_t)rs * (SMPC_REC_JDIST + p * NQ + j)] = dot(gA, JA[j]) + dot(gB, JB[j]);
-    }
-    rec[(size_t)rs * (SMPC_REC_NDIST)] = NPAIR;
-  }
-  // ---- viability row ----
+  if (k > 0 || P.stage0_collision_rows) rec[(size_t)rs * (SMPC_REC_NDIST)] = NPAIR;
   rec[(size_t)rs * (SMPC_REC_SOFT)] = -1.0;
   if (has_nn) {
     rec[(size_t)rs * (SMPC_REC_NNROW)] = 1.0;
@@ -418,13 +487,42 @@ SMPC_HD void linearize_stage(const smpc_problem_t& P, int k, const double* x, co
     }
     if (term && P.nn_terminal_soft) rec[(size_t)rs * (SMPC_REC_SOFT)] = P.slack_penalty_e;
   }
-  // ---- dynamics offset ----
   if (!term) {
     double xn[NX];
     f_disc(P.dt, x, u, xn);
 #pragma unroll
     for (int i = 0; i < NX; ++i) rec[(size_t)rs * (SMPC_REC_B + i)] = xn[i] - xnext[i];
   }
+}
+
+template <class R>
+SMPC_HD void linearize_stage(const smpc_problem_t& P, int k, const double* x, const double* u, const double* xnext,
+                             bool has_nn, bool gate_on, const double* nn11, R* rec, int rs = 1, const double* ee_ref = nullptr) {
+  const int N = P.N;
+  const bool term = (k == N);
+  for (int i = 0; i < REC; ++i) rec[(size_t)rs * (i)] = 0.0;
+  const double* q = x;
+  const double* v = x + NQ;
+  Fk K;
+  fk(P, q, K);
+  lin_cost(P, k, K, u, ee_ref ? ee_ref : P.ee_ref, rec, rs);
+  // ---- torque rows ----
+  if (!term) {
+    Rnea S;
+    double tau[NQ];
+    rnea(P, P.inertial, q, v, u, S, tau);
+#pragma unroll
+    for (int i = 0; i < NU; ++i) rec[(size_t)rs * (SMPC_REC_TAU + i)] = tau[i];
+    for (int j = 0; j < NQ; ++j) {
+      lin_tau_col<TAN_U>(P, S, v, u, j, rec, rs);
+      lin_tau_col<TAN_Q>(P, S, v, u, j, rec, rs);
+      lin_tau_col<TAN_V>(P, S, v, u, j, rec, rs);
+    }
+  }
+  // ---- capsule rows ----
+  if (k > 0 || P.stage0_collision_rows)
+    for (int p = 0; p < NPAIR; ++p) lin_pair(P, K, p, rec, rs);
+  lin_misc(P, k, x, u, xnext, has_nn, gate_on, nn11, rec, rs);
 }
 
 SMPC_HD bool stage_has_nn(const smpc_problem_t& P, int k) {

@@ -51,6 +51,7 @@ struct LaunchCtx {
 
 // kernels.cu
 cudaError_t mlp_prepare();
+cudaError_t linearize_prepare();
 void launch_prep(const LaunchCtx& c, const smpc_problem_t* dP, int B, int N, double* xg, const double* ug, const uint8_t* act, bool correct);
 void launch_mlp(const LaunchCtx& c, const smpc_problem_t* dP, const MlpWeights& w, int B, int N, int rows_mode, int n_flat,
                 const double* xsrc, const int32_t* r, const uint8_t* act, const uint8_t* need, double* out11, bool want_grad);
@@ -68,7 +69,8 @@ void launch_mlp_tc2(const LaunchCtx& c, const smpc_problem_t* dP, const MlpTcWei
                     const double* xsrc, const int32_t* r, const uint8_t* act, const uint8_t* need, double* out11, bool want_grad);
 // lin: tile-interleaved record array of the QP solver, double or (lin_f32) float
 void launch_linearize(const LaunchCtx& c, const smpc_problem_t* dP, int B, int N, const double* xg, const double* ug,
-                      const int32_t* r, const uint8_t* act, const double* nn11, void* lin, bool lin_f32);
+                      const int32_t* r, const uint8_t* act, const double* nn11, const double* traj, int n_traj, const int32_t* cur_step,
+                      void* lin, bool lin_f32);
 void launch_ctrl_post1(const LaunchCtx& c, const smpc_problem_t* dP, int B, int N, const uint8_t* act, const double* xg, const double* ug,
                        const double* xt, int32_t* status, int32_t* fails, int32_t* r, double* x_viable, uint8_t* need_scan,
                        uint8_t* abort_flag, double* u_out);

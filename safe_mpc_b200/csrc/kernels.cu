@@ -1,5 +1,8 @@
 // Kernels around the QP: warm-start correction, viability network, stage linearisation, controller state machines,
 // plant step and the closed-loop bookkeeping.  Reference semantics are cited per kernel.
+#include <cstdlib>
+#include <cstring>
+
 #include "engine.cuh"
 
 namespace smpc {
@@ -182,10 +185,14 @@ void launch_mlp(const LaunchCtx& c, const smpc_problem_t* dP, const MlpWeights& 
 // ----------------------------------------------------------------------------------------------------------------
 // Linearisation of every (problem, stage): one thread each (dev_model.cuh: linearize_stage)
 // ----------------------------------------------------------------------------------------------------------------
+#ifndef LIN_MINB
+#define LIN_MINB 1
+#endif
 template <class R>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, LIN_MINB)
 linearize_kernel(const smpc_problem_t* __restrict__ dP, int B, int N, const double* __restrict__ xg, const double* __restrict__ ug,
-                 const int32_t* __restrict__ r, const uint8_t* __restrict__ act, const double* __restrict__ nn11, R* lin) {
+                 const int32_t* __restrict__ r, const uint8_t* __restrict__ act, const double* __restrict__ nn11, const double* __restrict__ traj,
+                 int n_traj, const int32_t* __restrict__ cur_step, R* lin) {
   // records are written tile-interleaved, [tile][stage][field][lane] (qp_split.cuh): thread = lane of warp (tile, stage),
   // so every field store of a warp is one contiguous 256-byte segment
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -206,13 +213,128 @@ linearize_kernel(const smpc_problem_t* __restrict__ dP, int B, int N, const doub
   if (P.nn_rows == SMPC_NN_RECEDING && k < N) gate = (k == r[b]);      // controller.py:452-469
   if (P.nn_rows == SMPC_NN_PARALLEL) gate = (k == r[b]);               // controller.py:578-588 (r = candidate node of this solve)
   R* rec = lin + qs_blk(tile, N, k, REC, lane);
-  linearize_stage(P, k, x, u, xn, has_nn, gate, nn11 + ((size_t)b * (N + 1) + k) * NN_OUT, rec, TL);
+  const double* eer = n_traj > 0 ? traj + 3 * (size_t)min(cur_step[b] + k, n_traj - 1) : nullptr;     // controller.py:153-156
+  linearize_stage(P, k, x, u, xn, has_nn, gate, nn11 + ((size_t)b * (N + 1) + k) * NN_OUT, rec, TL, eer);
+}
+// ----------------------------------------------------------------------------------------------------------------
+// Linearisation, cooperative form: one CTA of eight warps per (tile of 32 problems, stage); lane = problem in every warp.
+// The thread-per-stage form above keeps the state of the nominal passes (RNEA: 120 doubles, kinematics: 75) per thread and
+// indexes it with run-time joint numbers: 255 registers, a 2 KB stack frame, 1.8 GB written per launch for 0.7 GB of records,
+// FP64 pipe 36 % busy (profiles/r02_linearize_flops.md).  Here that state lives in shared memory, [field][lane], written once
+// by the two nominal passes and read by everybody:
+//   phase A   warp 0: recursive Newton-Euler pass (tau, body velocities / accelerations / wrenches)     warp 1: forward kinematics
+//             warps 2-7: zero the record block (fields nobody writes must read 0)
+//   phase B   the 15 columns of d tau / d(u, q, v) (one tangent recursion each), the 6 capsule pairs, the cost block and the
+//             remaining rows are 23 independent items, dealt to the eight warps by estimated cost (longest first)
+// Every item is the very function the thread-per-stage form calls (dev_model.cuh: lin_*), on the same operands.
+// ----------------------------------------------------------------------------------------------------------------
+constexpr int LC_WARPS = 8;
+enum { LC_X = 0, LC_U = NX, LC_XN = NX + NU, LC_S = 2 * NX + NU, LC_K = LC_S + RS_SIZE, LC_FIELDS = LC_K + FK_SIZE };
+constexpr size_t LC_SMEM = sizeof(double) * LC_FIELDS * TL;
+// items: 0-4 d/du_j, 5-9 d/dq_j, 10-14 d/dv_j, 15-20 capsule pair, 21 cost block, 22 remaining rows; -1 = none
+__constant__ int8_t lc_items[LC_WARPS][4] = {{5, 16, -1, -1}, {10, 17, -1, -1}, {6, 3, 9, -1}, {11, 15, 20, -1},
+                                             {21, 2, 14, -1}, {7, 8, 18, -1},   {12, 13, 19, -1}, {0, 1, 4, 22}};
+
+#ifndef LC_MINB
+#define LC_MINB 2                // resident CTAs per SM the register allocation is sized for
+#endif
+template <class R>
+__global__ void __launch_bounds__(32 * LC_WARPS, LC_MINB)
+linearize_coop_kernel(const smpc_problem_t* __restrict__ dP, int B, int N, const double* __restrict__ xg, const double* __restrict__ ug,
+                      const int32_t* __restrict__ r, const uint8_t* __restrict__ act, const double* __restrict__ nn11, const double* __restrict__ traj,
+                      int n_traj, const int32_t* __restrict__ cur_step, R* lin) {
+  extern __shared__ __align__(16) double lc_sm[];
+  const smpc_problem_t& P = *dP;
+  const int tile = blockIdx.x / (N + 1), k = blockIdx.x % (N + 1);
+  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+  const int b = tile * TL + lane;
+  const bool on = b < B && (!act || act[b]);
+  if (!__any_sync(0xffffffffu, on)) return;                  // (the eight warps serve the same 32 problems: same answer)
+  const bool term = (k == N);
+  // guess of this stage (x, u) and state of the next one, staged once for all warps
+  for (int e = threadIdx.x; e < LC_S * TL; e += 32 * LC_WARPS) {
+    const int l = e & 31, f = e >> 5, bb = tile * TL + l;
+    double v = 0.0;
+    if (bb < B) {
+      if (f < LC_U) v = xg[((size_t)bb * (N + 1) + k) * NX + f];
+      else if (f < LC_XN) v = term ? 0.0 : ug[((size_t)bb * N + k) * NU + (f - LC_U)];
+      else v = term ? 0.0 : xg[((size_t)bb * (N + 1) + k + 1) * NX + (f - LC_XN)];
+    }
+    lc_sm[e] = v;
+  }
+  __syncthreads();
+  double x[NX], u[NU];
+#pragma unroll
+  for (int i = 0; i < NX; ++i) x[i] = lc_sm[(LC_X + i) * TL + lane];
+#pragma unroll
+  for (int i = 0; i < NU; ++i) u[i] = lc_sm[(LC_U + i) * TL + lane];
+  RneaSm S{lc_sm + (size_t)LC_S * TL + lane};
+  FkSm K{lc_sm + (size_t)LC_K * TL + lane};
+  R* rec = lin + qs_blk(tile, N, k, REC, lane);
+  double tau[NQ];
+  if (wi == 0) {
+    if (!term) rnea(P, P.inertial, x, x + NQ, u, S, tau);
+  } else if (wi == 1) {
+    fk(P, x, K);
+  } else if (on) {
+    for (int f = wi - 2; f < REC; f += LC_WARPS - 2) rec[(size_t)f * TL] = 0.0;
+  }
+  __syncthreads();
+  if (!on) return;
+  if (wi == 0 && !term) {
+#pragma unroll
+    for (int i = 0; i < NU; ++i) rec[(size_t)TL * (SMPC_REC_TAU + i)] = tau[i];
+  }
+  for (int s_ = 0; s_ < 4; ++s_) {
+    const int item = lc_items[wi][s_];
+    if (item < 0) break;
+    if (item < 15) {
+      if (term) continue;
+      const int j = item % 5;
+      if (item < 5) lin_tau_col<TAN_U>(P, S, x + NQ, u, j, rec, TL);
+      else if (item < 10) lin_tau_col<TAN_Q>(P, S, x + NQ, u, j, rec, TL);
+      else lin_tau_col<TAN_V>(P, S, x + NQ, u, j, rec, TL);
+    } else if (item < 21) {
+      if (k > 0 || P.stage0_collision_rows) lin_pair(P, K, item - 15, rec, TL);
+    } else if (item == 21) {
+      lin_cost(P, k, K, u, n_traj > 0 ? traj + 3 * (size_t)min(cur_step[b] + k, n_traj - 1) : P.ee_ref, rec, TL);
+    } else {
+      double xn[NX];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) xn[i] = lc_sm[(LC_XN + i) * TL + lane];
+      const bool has_nn = stage_has_nn(P, k);
+      bool gate = true;
+      if (P.nn_rows == SMPC_NN_RECEDING && k < N) gate = (k == r[b]);      // controller.py:452-469
+      if (P.nn_rows == SMPC_NN_PARALLEL) gate = (k == r[b]);               // controller.py:578-588 (r = candidate node of this solve)
+      lin_misc(P, k, x, u, xn, has_nn, gate, nn11 + ((size_t)b * (N + 1) + k) * NN_OUT, rec, TL);
+    }
+  }
+}
+
+// Which form runs: the thread-per-stage one.  The cooperative kernel gives the same bits but is slower on B200 (1.39 ms against 0.84 ms
+// for 460 000 stages: its warps run eight different unrolled instruction streams and stall on instruction fetch and on the barrier
+// behind the two nominal passes, profiles/r02_linearize.md); SMPC_LIN=coop selects it (read at every launch: a getenv per solve is noise).
+static bool lin_thread_form() {
+  const char* e = getenv("SMPC_LIN");
+  return !(e && !strcmp(e, "coop"));
+}
+cudaError_t linearize_prepare() {
+  cudaError_t e = cudaFuncSetAttribute(linearize_coop_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LC_SMEM);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(linearize_coop_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LC_SMEM);
+  return e;
 }
 void launch_linearize(const LaunchCtx& c, const smpc_problem_t* dP, int B, int N, const double* xg, const double* ug, const int32_t* r,
-                      const uint8_t* act, const double* nn11, void* lin, bool lin_f32) {
-  const int n = ((B + TL - 1) / TL) * (N + 1) * TL;
-  if (lin_f32) linearize_kernel<float><<<GRID1D(n, 128), 128, 0, c.stream>>>(dP, B, N, xg, ug, r, act, nn11, static_cast<float*>(lin));
-  else linearize_kernel<double><<<GRID1D(n, 128), 128, 0, c.stream>>>(dP, B, N, xg, ug, r, act, nn11, static_cast<double*>(lin));
+                      const uint8_t* act, const double* nn11, const double* traj, int n_traj, const int32_t* cur_step, void* lin, bool lin_f32) {
+  const int tiles = (B + TL - 1) / TL;
+  if (lin_thread_form()) {
+    const int n = tiles * (N + 1) * TL;
+    if (lin_f32) linearize_kernel<float><<<GRID1D(n, 128), 128, 0, c.stream>>>(dP, B, N, xg, ug, r, act, nn11, traj, n_traj, cur_step, static_cast<float*>(lin));
+    else linearize_kernel<double><<<GRID1D(n, 128), 128, 0, c.stream>>>(dP, B, N, xg, ug, r, act, nn11, traj, n_traj, cur_step, static_cast<double*>(lin));
+  } else {
+    const int grid = tiles * (N + 1);
+    if (lin_f32) linearize_coop_kernel<float><<<grid, 32 * LC_WARPS, LC_SMEM, c.stream>>>(dP, B, N, xg, ug, r, act, nn11, traj, n_traj, cur_step, static_cast<float*>(lin));
+    else linearize_coop_kernel<double><<<grid, 32 * LC_WARPS, LC_SMEM, c.stream>>>(dP, B, N, xg, ug, r, act, nn11, traj, n_traj, cur_step, static_cast<double*>(lin));
+  }
   ++*c.launches;
 }
 

@@ -23,6 +23,15 @@ int emu_linearize(const smpc_problem_t* P, int n, const int* k, const double* x,
   return 0;
 }
 
+// the same with a per-item end-effector reference (smpc_set_ee_trajectory: row current_step + k of the trajectory), ee_ref [n][3]
+int emu_linearize_ref(const smpc_problem_t* P, int n, const int* k, const double* x, const double* u, const double* xnext,
+                      const int* gate, const double* nn11, const double* ee_ref, double* rec) {
+  for (int i = 0; i < n; ++i)
+    linearize_stage(*P, k[i], x + i * NX, u + i * NU, xnext + i * NX, stage_has_nn(*P, k[i]), gate[i] != 0, nn11 + i * 11, rec + (size_t)i * REC, 1,
+                    ee_ref + (size_t)i * 3);
+  return 0;
+}
+
 int emu_plant_step(const smpc_problem_t* P, int n, const double* inertial, const double* noise, const double* x, const double* u,
                    double* xn, double* a) {
   for (int i = 0; i < n; ++i)

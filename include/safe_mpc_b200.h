@@ -291,6 +291,11 @@ int smpc_get_profile(smpc_handle_t* h, double* ms /*[SMPC_PROF_N]*/, int32_t* co
 int64_t smpc_launch_count(const smpc_handle_t* h);
 /* the CUDA stream the handle launches on (cudaStream_t as void*) */
 void* smpc_stream(smpc_handle_t* h);
+/* make the handle launch on the caller's stream (cudaStream_t as void*; it must belong to the handle's device and outlive the
+ * handle or the next smpc_set_stream) -- what a per-call cudaStream_t argument would do, set once instead of
+ * passed to every function.  NULL: back to a private non-blocking stream.  Returns after the work queued so far has finished.
+ * The legacy default stream is not supported (the QP solver orders its internal streams with events against this one). */
+int smpc_set_stream(smpc_handle_t* h, void* stream);
 int smpc_sync(smpc_handle_t* h);
 
 /* --- measured machine peaks for the roofline of bench.py (the dynamics / QP kernels are charged to the

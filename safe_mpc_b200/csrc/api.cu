@@ -22,6 +22,7 @@ struct smpc_handle {
   smpc_problem_t* dP = nullptr;
   int B = 0, N = 0, device = 0;
   cudaStream_t stream = nullptr;
+  bool own_stream = true;           // false: the caller's stream (smpc_set_stream), never destroyed here
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   int64_t launches = 0;
   double* ee_traj = nullptr;        // [n_traj][3] end-effector reference per control step (smpc_set_ee_trajectory); n_traj = 0: P.ee_ref
@@ -68,6 +69,8 @@ struct smpc_sim {
   SimDev d;
   int j = 0;
   int32_t* outcome_tmp = nullptr;
+  unsigned long long* h_requests = nullptr;   // pinned: backup requests so far (SimDev::counters[4])
+  unsigned long long requests_seen = 0;
   std::vector<void*> allocs;        // device buffers of this closed loop (freed by smpc_sim_destroy)
   int device = 0;
 };
@@ -355,7 +358,7 @@ void smpc_destroy(smpc_handle_t* h) {
   if (h->stage) cudaFree(h->stage);
   if (h->ee_traj) cudaFree(h->ee_traj);
   for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
-  if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
   delete h;
 }
 
@@ -580,6 +583,15 @@ int smpc_get_times(smpc_handle_t* h, double* out7) {
 }
 int64_t smpc_launch_count(const smpc_handle_t* h) { return h->launches; }
 void* smpc_stream(smpc_handle_t* h) { return (void*)h->stream; }
+int smpc_set_stream(smpc_handle_t* h, void* stream) {
+  if (!h) return SMPC_ERR_ARG;
+  if (cudaSetDevice(h->device) != cudaSuccess) return fail(h, SMPC_ERR_CUDA, "cudaSetDevice", cudaGetLastError());
+  CK(h, cudaStreamSynchronize(h->stream));                  // everything queued so far is finished before the stream changes
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  if (stream) { h->stream = (cudaStream_t)stream; h->own_stream = false; }
+  else { h->own_stream = true; CK(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); }
+  return SMPC_OK;
+}
 int smpc_sync(smpc_handle_t* h) { CK(h, cudaStreamSynchronize(h->stream)); return check_launch(h, "sync"); }
 
 // ------------------------------------------------------------------------------------------------ closed loop
@@ -603,7 +615,8 @@ int smpc_sim_create(smpc_handle_t* c, smpc_handle_t* bk, int32_t n_steps, smpc_s
   CKS(dalloc(c, &d.mode, (size_t)B)); CKS(dalloc(c, &d.ja, (size_t)B)); CKS(dalloc(c, &d.outcome, (size_t)B));
   CKS(dalloc(c, &d.need_ctrl, (size_t)B)); CKS(dalloc(c, &d.need_backup, (size_t)B)); CKS(dalloc(c, &d.abort_flag, (size_t)B));
   CKS(dalloc(c, &d.live, (size_t)B));
-  CKS(dalloc(c, &d.counters, (size_t)4));
+  CKS(dalloc(c, &d.counters, (size_t)5));
+  CKS(cudaMallocHost((void**)&s->h_requests, sizeof(unsigned long long)));
   CKS(dalloc(c, &s->outcome_tmp, (size_t)B));
 #undef CKS
   s->allocs.assign(c->allocs.begin() + n_before, c->allocs.end());
@@ -616,6 +629,7 @@ void smpc_sim_destroy(smpc_sim_t* s) {
   cudaSetDevice(s->device);
   cudaDeviceSynchronize();          // (the handles may already be gone: do not touch them)
   for (void* p : s->allocs) cudaFree(p);
+  if (s->h_requests) cudaFreeHost(s->h_requests);
   delete s;
 }
 
@@ -629,7 +643,8 @@ int smpc_sim_reset(smpc_sim_t* s, const double* x_init, int32_t mem) {
   launch_fill_f64(lc, d.ulog, (size_t)B * d.n_steps * NU, nan);
   launch_fill_f64(lc, d.xv_first, (size_t)B * NX, nan);
   launch_fill_i32(lc, d.mode, B, 0); launch_fill_i32(lc, d.ja, B, 0); launch_fill_i32(lc, d.outcome, B, 0);
-  CK(c, cudaMemsetAsync(d.counters, 0, 4 * sizeof(unsigned long long), c->stream));
+  CK(c, cudaMemsetAsync(d.counters, 0, 5 * sizeof(unsigned long long), c->stream));
+  s->requests_seen = 0;
   int rc = copy_in(c, d.x, x_init, sizeof(double) * B * NX, mem); if (rc) return rc;
   CK(c, cudaMemcpy2DAsync(d.xlog, sizeof(double) * (d.n_steps + 1) * NX, d.x, sizeof(double) * NX, sizeof(double) * NX, B, cudaMemcpyDeviceToDevice, c->stream));
   s->j = 0;
@@ -651,7 +666,14 @@ int smpc_sim_step(smpc_sim_t* s) {
   c->times_pending = 2;
   if (!rc) {
     launch_sim_mid(lc, d, c->x_viable, bk->xg, bk->ug, c->qp_iter);
-    rc = solve_pipeline(bk, c->x_viable, d.need_backup);     // safe_ocp.solve(x_viable), one RTI (mpc.py:177)
+    // the backup OCP is solved only in a step in which some problem aborted (mpc.py:168-177): one 8-byte read-back decides, instead of
+    // an empty linearisation + QP launch sequence in every step (the host has waited for the main solve's counters anyway)
+    CK(c, cudaMemcpyAsync(s->h_requests, d.counters + 4, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    if (*s->h_requests != s->requests_seen) {
+      s->requests_seen = *s->h_requests;
+      rc = solve_pipeline(bk, c->x_viable, d.need_backup);   // safe_ocp.solve(x_viable), one RTI (mpc.py:177)
+    }
   }
   if (!rc) {
     launch_sim_post(lc, d, c->dP, s->j, bk->status, bk->xt, bk->ut, c->plant_inertial, c->tau_noise, bk->qp_iter);

@@ -99,7 +99,7 @@ struct SimDev {
   double *x, *xlog, *ulog, *x_abort, *u_abort, *xv_first, *u_ctrl, *u;
   int32_t *mode, *ja, *outcome;
   uint8_t *need_ctrl, *need_backup, *abort_flag, *live;
-  unsigned long long* counters;   // [4]
+  unsigned long long* counters;   // [5]: RTI solves, backup solves, plant steps, IPM iterations; [4] = backup requests so far (host: skip the empty backup solve)
 };
 void launch_sim_pre(const LaunchCtx& c, const SimDev& s, const smpc_problem_t* dP, int j);
 void launch_sim_mid(const LaunchCtx& c, const SimDev& s, const double* x_viable, double* bk_xg, double* bk_ug, const int32_t* qp_iter_main);

@@ -653,6 +653,7 @@ __global__ void sim_mid_kernel(SimDev s, const double* __restrict__ x_viable, do
     for (int k = 0; k <= Nb; ++k) for (int i = 0; i < NX; ++i) xg[k * NX + i] = xv[i];
     for (int i = 0; i < Nb * NU; ++i) ug[i] = 0.0;
     s.need_backup[b] = 1;
+    atomicAdd(&s.counters[4], 1ull);
   }
 }
 void launch_sim_mid(const LaunchCtx& c, const SimDev& s, const double* x_viable, double* bk_xg, double* bk_ug, const int32_t* qp_iter_main) {

@@ -37,6 +37,7 @@ def load_library():
         lib.smpc_launch_count.argtypes = [C.c_void_p]
         lib.smpc_stream.restype = C.c_void_p
         lib.smpc_stream.argtypes = [C.c_void_p]
+        lib.smpc_set_stream.argtypes = [C.c_void_p, C.c_void_p]
         _LIB = lib
     return _LIB
 
@@ -87,6 +88,13 @@ class Engine(EngineBase):
 
     def stream(self) -> int:
         return int(self.lib.smpc_stream(self.h) or 0)
+
+    def set_stream(self, stream):
+        """Launch on the caller's CUDA stream (a torch.cuda.Stream, a raw cudaStream_t as int, or None = private stream)."""
+        raw = 0 if stream is None else int(getattr(stream, 'cuda_stream', stream))
+        self._user_stream = stream                            # keep a torch stream object alive
+        self._ext = None
+        self._check(self.lib.smpc_set_stream(self.h, C.c_void_p(raw)), 'set_stream')
 
     PROF_NAMES = ['qs_init', 'qs_prep', 'qs_ctl', 'qs_ric1', 'qs_step0', 'qs_ric2', 'qs_step1', 'qs_red', 'qs_compact',
                   'qs_step2_centering', 'qs_final', 'qs_solo']

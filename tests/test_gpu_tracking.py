@@ -118,3 +118,32 @@ def test_tracking_cost_through_the_controller_classes():
         x, _ = model.integrate(x, u)
     assert np.array_equal(controller.ocp_solver.get_state(abi.STATE_STATUS), plain.get_state(abi.STATE_STATUS))
     plain.close(); const.close()
+
+
+def test_caller_stream():
+    """smpc_set_stream: the handle launches on the caller's stream; same results, and back to a private stream with NULL"""
+    import torch
+    from safe_mpc_b200.engine import Engine
+    B, N = 640, 20
+    prob, params, md = make_problem('st', N=N)
+    x0 = start_states(B, seed=81, vel=0.3)
+    xg, ug = rollout_guess(x0, N, params.dt, seed=82, scale=1.0)
+    eng = Engine(prob, B, 0)
+    eng.set_guess(xg, ug); st0 = eng.rti_solve(x0); xt0, ut0 = eng.get_temp()
+    own = eng.stream()
+    s = torch.cuda.Stream()
+    eng.set_stream(s)
+    assert eng.stream() == s.cuda_stream != own
+    with torch.cuda.stream(s):
+        xd = torch.tensor(x0, device='cuda')
+        eng.set_guess(torch.tensor(xg, device='cuda'), torch.tensor(ug, device='cuda'))
+        st1 = eng.rti_solve(xd)
+        xt1, ut1 = eng.get_temp(like=xd)
+    s.synchronize()
+    assert np.array_equal(st0, st1.cpu().numpy() if hasattr(st1, 'cpu') else st1)
+    assert np.array_equal(xt0, xt1.cpu().numpy()) and np.array_equal(ut0, ut1.cpu().numpy())
+    eng.set_stream(None)
+    assert eng.stream() not in (0, s.cuda_stream)
+    eng.set_guess(xg, ug); st2 = eng.rti_solve(x0); xt2, _ = eng.get_temp()
+    assert np.array_equal(st0, st2) and np.array_equal(xt0, xt2)
+    eng.close()

@@ -123,6 +123,7 @@ def test_controller_steps_closed_loop(controller):
         _close(xgg[m], xgo[m], RTOL, f'x_guess step {step}'); _close(ugg[m], ugo[m], RTOL, f'u_guess step {step}')
         x_g, _ = eng.plant_step(x_g, u_g); x_o, _ = orc.plant_step(x_o, u_o)
         _close(x_g[m], x_o[m], RTOL, f'x step {step}')
+    print(f'\n{controller}: {int(keep.sum())} of {B} problems compared over all 12 steps ({B - int(keep.sum())} dropped at an ill-conditioned QP)')
     assert keep.sum() >= B // 2, f'only {keep.sum()} of {B} problems stayed well-posed'
     _close(eng.get_x_viable()[keep], orc.get_x_viable()[keep], RTOL, 'x_viable')
 

@@ -591,7 +591,13 @@ constexpr size_t R1X_BYTES = R1X_STG_BYTES + sizeof(double) * (65 + R1X_XF) * TL
 static_assert(sizeof(qs_real) * (R1X_FWD1 + R1X_FWD) * TL <= R1X_BYTES, "forward buffers");
 constexpr size_t RIC1X_SMEM = R1X_BYTES + 32;
 
-__device__ __forceinline__ void r1x_bar() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
+// named barrier of the two warps of a tile.  The warps reach it from different code paths and, inside a warp, lanes may arrive from a
+// data-dependent branch (a non-positive pivot, an inactive lane): the warp reconverges first and the barrier is the non-aligned form
+// (bar.sync = barrier.sync.aligned is undefined for a diverged warp; compute-sanitizer synccheck flagged it, gpurun_out/r2c17)
+__device__ __forceinline__ void r1x_bar() {
+  __syncwarp();
+  asm volatile("barrier.sync 1, 64;" ::: "memory");
+}
 __device__ __forceinline__ void r1x_fetch(qs_real* dst, const qs_real* src, int nfields, uint64_t* bar) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"((uint32_t)(nfields * TL * sizeof(qs_real))) : "memory");
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),

@@ -983,7 +983,10 @@ __global__ void dump_qp_kernel(const smpc_problem_t* __restrict__ dP, QsBufs q, 
 
 // ------------------------------------------------------------------------------------------------ solver object
 #ifndef QS_GROUPS
-#define QS_GROUPS 3              // tile groups solved concurrently on their own streams (see QsLoop)
+#define QS_GROUPS 1              // tile groups solved concurrently on their own streams (see QsLoop).  Round 1 ran three (the latency-bound sweeps of one
+                                 // group under the streaming kernels of the others: +3 %); since the slots are compacted between iterations and every
+                                 // kernel runs at 0.6-0.95 of the HBM peak on the full batch, one group is faster: cfg[1] 60.25 -> 59.38 ms per step, cfg[2]
+                                 // HTWA 33.45 -> 32.29 ms (three runs each, gpurun_out/r2tune, r2tune2); SMPC_QP_GROUPS=n brings the groups back
 #endif
 constexpr int MAX_GROUPS = 8;
 constexpr int RING = 8;          // counter read-backs in flight per group (run-ahead depth + 2 at most)
@@ -1038,6 +1041,7 @@ struct QpSolver {
                                 // (step<2>, red) and gains nothing while three tile groups already cover the round trip
   bool compact = true;          // pack the problems still iterating into the leading slots between iterations (SMPC_QP_COMPACT=0: never)
   int compact_min_tiles = 32;   // ... for groups of at least this many tiles
+  double compact_at = 0.85;     // ... once the active count has fallen to this fraction of the slots in use (SMPC_QP_COMPACT_AT)
   bool compacted = false;       // the last solve reused slots: per-slot dumps (smpc_get_lin / smpc_get_qp) are not available for it
   int n_compactions = 0;        // of the last solve
   bool trace_print = false;     // SMPC_QP_TRACE=1
@@ -1088,6 +1092,7 @@ QpSolver* qp_create(int B, int N, int iter_max, bool keep_slots, cudaStream_t st
   if (s->depth < 0) s->depth = 0;
   if (s->depth > RING - 2) s->depth = RING - 2;
   if (const char* ce = getenv("SMPC_QP_COMPACT")) s->compact = atoi(ce) != 0;
+  if (const char* ce = getenv("SMPC_QP_COMPACT_AT")) { const double v = atof(ce); if (v > 0.1 && v < 1.0) s->compact_at = v; }
   if (keep_slots) s->compact = false;
   s->trace_print = getenv("SMPC_QP_TRACE") != nullptr;
   if (e == cudaSuccess) e = cudaFuncSetAttribute(qs_ric2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RIC2_SMEM);
@@ -1286,7 +1291,7 @@ struct DeviceBackend {
   void compact(int kk) {
     if (!s->compact || g->T < s->compact_min_tiles) return;
     const int na = n_active_last;
-    if (na > g->in_use || g->in_use - na < TL || (double)na > 0.85 * g->in_use) return;
+    if (na > g->in_use || g->in_use - na < TL || (double)na > s->compact_at * g->in_use) return;
     // in the tail (warp-per-problem sweeps, a handful of tiles) one compaction at its start is enough: a further one costs more
     // (three launches, ~0.1 ms) than the few tiles it would save
     if (na <= s->tail_max && g->in_use <= 2 * s->tail_max) return;

@@ -186,7 +186,7 @@ def run_engine(a):
     main.set_plant_inertial(pin)
     warm_guess(main, x0, N, a.sqp_iters)
     guess0 = [np.array(v, copy=True) for v in main.get_guess()]     # the e2e arm replays the same closed loop from the same warm start
-    total_steps = a.warmup + a.steps
+    total_steps = a.warmup + a.steps + 2 * a.probe_steps        # (the roofline probe continues the same closed loop)
     sim = Sim(main, bk, total_steps)
     sim.reset(x0)
     stream = torch.cuda.ExternalStream(main.stream(), device=dev)
@@ -209,33 +209,41 @@ def run_engine(a):
     solves = (c1['rti_solves'] - c0['rti_solves']) + (c1['backup_solves'] - c0['backup_solves'])
     ipm = c1['ipm_iterations'] - c0['ipm_iterations']
 
-    # ---- the QP solve timed alone, with one CUDA-event pair per kernel on the stream it is launched on (roofline) ----
-    # (a second handle with a single tile group, so that no two kernels of the solve overlap while they are timed)
-    os.environ['SMPC_QP_GROUPS'] = '1'
-    probe, _bk, _ = make_handles(Engine, params, md, a.controller, B, local_rank)
-    os.environ.pop('SMPC_QP_GROUPS')
-    probe.set_guess(*main.get_guess())
+    # ---- per-kernel times of the QP solves of further closed-loop steps (roofline) ----
+    # The same closed loop simply continues after the timed region: first a few steps that only read the acados-style time fields of
+    # the step (time_qp, time_lin), then a few steps with one CUDA-event pair around every kernel on the stream it is launched on
+    # (smpc_set_profiling; the solver runs a single tile group, so no two kernels of a solve overlap while they are timed).  The
+    # event pairs cost launch gaps, so these steps are outside the timed region; what is summed is kernel durations only.
     xs = torch.tensor(x0, device=dev)
-    probe.rti_solve(xs); probe.sync()
-    probe.set_profiling(True)
-    profs = []
-    for _ in range(3):
-        probe.rti_solve(xs); probe.sync()
-        profs.append((probe.profile(), probe.times()))
-    probe.set_profiling(False)
-    qp_iter_probe = probe.get_state(abi.STATE_QP_ITER)
-    probe.close(); _bk.close()
-    main.rti_solve(xs); main.sync()
     tq = []
-    for _ in range(3):
-        main.rti_solve(xs); main.sync()
+    for _ in range(a.probe_steps):
+        sim.step(); main.sync()
         tq.append(main.times())
-    (kern, span_ms, it_max), tms = profs[-1]
+    kern = {}
+    span_ms, it_max = 0.0, 0
+    cp0 = sim.counters()
+    main.set_profiling(True)
+    tq_prof = []
+    for _ in range(a.probe_steps):
+        sim.step(); main.sync()
+        k1, sp1, itm1 = main.profile()
+        for k, (ms_k, n_k) in k1.items():
+            o = kern.get(k, (0.0, 0))
+            kern[k] = (o[0] + ms_k, o[1] + n_k)
+        span_ms += sp1; it_max = max(it_max, itm1)
+        tq_prof.append(main.times())
+    main.set_profiling(False)
+    cp1 = sim.counters()
+    probe_solves = cp1['rti_solves'] - cp0['rti_solves']
+    probe_ipm = cp1['ipm_iterations'] - cp0['ipm_iterations']
+    # a problem takes part in the launches kk = 0 .. iter of its solve
+    probe_visits = float(probe_ipm + probe_solves) * (N + 1)
     qp_ms = float(np.median([t['time_qp'] for t in tq]) * 1e3)
-    qp_ms_1group = float(np.median([p[1]['time_qp'] for p in profs]) * 1e3)
+    qp_ms_1group = float(np.median([t['time_qp'] for t in tq_prof]) * 1e3)
     lin_ms = float(np.median([t['time_lin'] for t in tq]) * 1e3)
-    it_qp = float(main.get_state(abi.STATE_QP_ITER).mean())
-    it_sum = float(main.get_state(abi.STATE_QP_ITER).sum())
+    it_qp = probe_ipm / max(1, probe_solves)
+    it_sum = float(probe_ipm) / a.probe_steps                                     # IPM iterations of one batched solve
+    kern = {k: (v[0] / a.probe_steps, v[1] / a.probe_steps) for k, v in kern.items()}   # -> per solve
     kern_total = sum(v[0] for v in kern.values())
 
     # ---- the linearisation kernel alone: a handle without viability rows (time_lin = linearize_kernel only), same B and N ----
@@ -317,14 +325,18 @@ def run_engine(a):
         'qs_step1': (122, 292, 0.0),
         'qs_step2_centering': (122, 301, 0.0),
     }
+    # the solo kernel (one CTA per problem, whole IPM iterations in one launch: small batches) runs every phase above on the same arrays
+    UNITS['qs_solo'] = tuple(sum(u[i] for k, u in UNITS.items() if k != 'qs_step2_centering') for i in range(3))
     UNITS = {k: ((d * 8 + v * sb) / 8.0, fl) for k, (d, v, fl) in UNITS.items()}    # -> (fp64-equivalents per visit, flop)
-    visits = float((qp_iter_probe + 1).sum()) * (N + 1)
+    visits = probe_visits / a.probe_steps                                       # (problem, stage) visits of one batched solve
     table = {}
     for k, (dbl, flop) in UNITS.items():
         ms_k, n_k = kern[k]
         if n_k == 0 or ms_k <= 0:
             continue
         v = visits if k != 'qs_step2_centering' else None     # (only the problems that switch direction: not tracked per launch)
+        if k == 'qs_prep' and kern.get('qs_solo', (0, 0))[1] > 0 and kern.get('qs_ric1', (0, 0))[1] == 0:
+            v = float(probe_solves) / a.probe_steps * (N + 1)   # solo path: only the cold-start prep is a launch of its own
         row = {'ms_per_solve': round(ms_k, 3), 'launches': n_k, 'share_of_qp_solve': ms_k / max(kern_total, 1e-9)}
         if v is not None:
             row.update({'hbm_gbs': v * dbl * 8 / (ms_k * 1e-3) / 1e9, 'hbm_frac': v * dbl * 8 / (ms_k * 1e-3) / 1e9 / hbm_peak,
@@ -333,11 +345,11 @@ def run_engine(a):
         table[k] = row
     dom = max((k for k in table if 'hbm_gbs' in table[k]), key=lambda k: table[k]['ms_per_solve'])
     dname = {'qs_prep': 'qs_prep_coop_kernel / qs_prep_kernel', 'qs_ric1': 'qs_ric1x_kernel / qs_ric1t_kernel', 'qs_ric2': 'qs_ric2_kernel / qs_ric2t_kernel',
-             'qs_step0': 'qs_step_kernel<0>', 'qs_step1': 'qs_step_kernel<1>'}[dom]
+             'qs_step0': 'qs_step_kernel<0>', 'qs_step1': 'qs_step_kernel<1>', 'qs_solo': 'qs_solo_kernel'}[dom]
     d = table[dom]
     traffic = {'qs_prep': 2.42e9, 'qs_ric1': 1.47e9, 'qs_ric2': 1.31e9}.get(dom) if (B, N) == (10000, 45) else None
     # bytes the whole solve moves per problem against what is algorithmically necessary (~11 KB per problem and RTI iteration)
-    moved = sum(table[k]['bytes_per_visit'] for k in table if 'bytes_per_visit' in table[k]) * visits / B
+    moved = sum(table[k]['bytes_per_visit'] for k in table if 'bytes_per_visit' in table[k] and not (k == 'qs_prep' and 'qs_solo' in table)) * visits / B
     necessary = ((N + 1) * abi.NX + N * abi.NU) * 8 * 2 + 200
     flops_solve = 0.48e6 * (N + 1) / 46.0 * it_sum                              # 0.48 MFLOP per IPM iteration at N = 45
     value = solves_all / (ms_max * 1e-3)
@@ -354,7 +366,9 @@ def run_engine(a):
                                           'warm start in / out + x0 + status that SURVEY 8(d) calls algorithmically necessary: the solver state '
                                           '(~340 KB per problem) does not fit on chip for the ~1 500 problems the sequential Riccati recursion needs in flight, '
                                           'so every IPM iteration re-streams it (DESIGN.md section 3.2)'},
-                'note': 'bytes and time are summed over every launch of the family in one solve; a launch only touches the problems still iterating'}
+                'note': 'bytes and time are summed over every launch of the family in the solves of the probe steps; a launch only touches the problems still iterating'
+                        + ('; the solo kernel serves a batch smaller than the machine out of L2 (working set below the L2 size): it is bound by the latency of one '
+                           'problem\'s dependent chain, the HBM basis is reported for completeness only' if dom == 'qs_solo' else '')}
     # linearisation kernel against the FP64 pipe (flop per stage from the executed-instruction tally)
     roof_dyn = None
     if lin_probe:
@@ -385,8 +399,9 @@ def run_engine(a):
         'peaks': {'hbm_gbs': hbm_peak, 'fp64_tflops': fp64_peak, 'fp32_tflops': fp32_peak, 'fp64_source': fp64_src},
         'qp_solve': {'ms': qp_ms, 'ms_single_tile_group': qp_ms_1group, 'linearize_ms': lin_ms, 'ipm_iterations_mean': it_qp, 'ipm_iterations_max': it_max,
                      'algorithmic_fp64_tflops': flops_solve / (qp_ms * 1e-3) / 1e12, 'algorithmic_fp64_frac': flops_solve / (qp_ms * 1e-3) / 1e12 / fp64_peak,
-                     'kernel_ms': {k: round(v[0], 3) for k, v in kern.items()}, 'kernel_launches': {k: v[1] for k, v in kern.items()},
-                     'kernel_ms_note': 'per-kernel sums of one solve timed with a single tile group (no overlap between kernels)'},
+                     'kernel_ms': {k: round(v[0], 3) for k, v in kern.items()}, 'kernel_launches': {k: round(v[1], 1) for k, v in kern.items()},
+                     'kernel_ms_note': f'per-kernel sums per solve, averaged over the solves of {a.probe_steps} further closed-loop steps timed with one '
+                                       'CUDA-event pair per kernel (single tile group: no overlap between kernels)'},
         'outcome': D.outcome_counts(outcome),
     }
     if mlp:
@@ -483,6 +498,7 @@ def main():
     ap.add_argument('--ref-problems', type=int, default=256, dest='ref_problems')
     ap.add_argument('--cpu-problems', type=int, default=256, dest='cpu_problems')
     ap.add_argument('--cpu-steps', type=int, default=8, dest='cpu_steps')
+    ap.add_argument('--probe-steps', type=int, default=5, dest='probe_steps', help='closed-loop steps after the timed region that are timed kernel by kernel')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-mlp', action='store_true', dest='no_mlp')

@@ -491,17 +491,41 @@ __global__ void __launch_bounds__(CP_THREADS) qs_compact_plan_kernel(QsBufs q, i
   if (tid == 0) *n_moves = n - apn;
 }
 
-constexpr int CM_THREADS = 128, CM_SPLIT = 4;
+// move: lane = move.  The plan pairs the movers (active slots beyond the boundary, in slot order) with the holes below it (in slot
+// order), so 32 consecutive moves read from one or two source tiles and write into a few destination tiles: a warp instruction that
+// copies one field of 32 moves touches a handful of 256-byte rows with most of their sectors in use (the first form had one thread per
+// field of ONE move: every access in a row of its own, 8 useful bytes per 32-byte sector on both sides -- 1.0 -> ~0.3 ms per compaction
+// of a cfg[1] solve).  CTA = four warps that take the fields of one stage of 32 moves round-robin; grid = (32-move groups, stages).
+constexpr int CM_THREADS = 128;
 __global__ void __launch_bounds__(CM_THREADS) qs_compact_move_kernel(QsBufs q, const int32_t* __restrict__ mv, int mv_half, const int* __restrict__ n_moves, int kk) {
-  const int i = blockIdx.x;
-  if (i >= *n_moves) return;
+  const int nm = *n_moves;
+  if ((int)blockIdx.x * 32 >= nm) return;
+  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;
+  if (i >= nm) return;
   const int src = mv[i], dst = mv[mv_half + i];
-  for (int k = blockIdx.y; k <= q.N; k += CM_SPLIT)
-    for (int f = threadIdx.x; f < CMP_FIELDS; f += CM_THREADS) qs_compact_move_field(q, src, dst, k, kk, f);
-  if (blockIdx.y == 0) {
-    __syncthreads();
-    if (threadIdx.x == 0) qs_compact_move_scalars(q, src, dst);
+  const int N = q.N, k = blockIdx.y;
+  const int ts = src / TL, ls = src % TL, td = dst / TL, ld = dst % TL;
+  {
+    const qs_real* a = q.rec + qs_blk(ts, N, k, REC, ls);
+    qs_real* b = const_cast<qs_real*>(q.rec) + qs_blk(td, N, k, REC, ld);
+#pragma unroll 8
+    for (int f = wi; f < REC; f += CM_THREADS / 32) QF(b, f) = QF(a, f);
   }
+  {
+    const double* a = q.it[kk & 1] + qs_blk(ts, N, k, NIT, ls);
+    double* b = q.it[kk & 1] + qs_blk(td, N, k, NIT, ld);
+#pragma unroll 8
+    for (int f = wi; f < NIT; f += CM_THREADS / 32) QF(b, f) = QF(a, f);
+  }
+  {
+    const qs_real* a = q.st + qs_blk(ts, N, k, NIT, ls);
+    qs_real* b = q.st + qs_blk(td, N, k, NIT, ld);
+#pragma unroll 8
+    for (int f = wi; f < NIT; f += CM_THREADS / 32) QF(b, f) = QF(a, f);
+  }
+  static_assert(CMP_FIELDS == REC + 2 * NIT, "fields of a move (qs_compact_move_field)");
+  if (k == 0 && wi == 0) qs_compact_move_scalars(q, src, dst);
 }
 
 
@@ -1300,8 +1324,8 @@ struct DeviceBackend {
     const int tl_before = tl();
     qs_final_kernel<<<(tl_before * (s->N + 1) + SP_WARPS - 1) / SP_WARPS, 32 * SP_WARPS, 0, stm_>>>(g->q, tl_before, s->B, act, status, xt, ut);
     qs_compact_plan_kernel<<<1, CP_THREADS, 0, stm_>>>(g->q, tl_before, g->mv, g->mv_half, g->n_moves);
-    const int grid_x = g->in_use / 2 + 1;          // movers = min(active beyond the boundary, holes below it) <= half of the slots in use
-    qs_compact_move_kernel<<<dim3(grid_x, CM_SPLIT), CM_THREADS, 0, stm_>>>(g->q, g->mv, g->mv_half, g->n_moves, kk);
+    const int grid_x = (g->in_use / 2) / 32 + 1;   // movers = min(active beyond the boundary, holes below it) <= half of the slots in use; 32 per CTA
+    qs_compact_move_kernel<<<dim3(grid_x, s->N + 1), CM_THREADS, 0, stm_>>>(g->q, g->mv, g->mv_half, g->n_moves, kk);
     tr1(stm_);
     count(3);
     g->in_use = na;

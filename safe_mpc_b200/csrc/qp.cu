@@ -955,14 +955,32 @@ __global__ void __launch_bounds__(32) qs_ric2_kernel(const smpc_problem_t* __res
   qs_ric2(*dP, q, blockIdx.x, w);
 }
 
-__global__ void __launch_bounds__(32) qs_red_kernel(const smpc_problem_t* __restrict__ dP, QsBufs q, int kk, int after_redo, int* counters) {
+// redo_list: the slots (of this group) whose problem fell back to the centering direction, tile by tile in arrival order of the tiles
+__global__ void __launch_bounds__(32) qs_red_kernel(const smpc_problem_t* __restrict__ dP, QsBufs q, int kk, int after_redo, int* counters, int32_t* redo_list) {
   qs_red(*dP, q, blockIdx.x, threadIdx.x, after_redo != 0);
   if (!after_redo) {
     const int32_t* pi = q.pi + qs_pb(blockIdx.x, NPI, threadIdx.x);
     const bool redo = QF(pi, J_ACT) && QF(pi, J_REDO);
     const unsigned m = __ballot_sync(0xffffffffu, redo);
-    if (threadIdx.x == 0 && m) atomicAdd(&counters[2 * kk + 1], __popc(m));
+    int base = 0;
+    if (threadIdx.x == 0 && m) base = atomicAdd(&counters[2 * kk + 1], __popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (redo) redo_list[base + __popc(m & ((1u << threadIdx.x) - 1u))] = blockIdx.x * TL + threadIdx.x;
   }
+}
+
+// The switch to the centering direction for FEW flagged problems: one CTA per list entry, thread = stage (qs_step mode 2), then thread 0
+// takes the step length of the new direction (qs_red, second call) -- the same two functions as the launches qs_step_kernel<2> + qs_red_kernel
+// they replace, on the same operands (bit-identical), but the work is proportional to the number of flagged PROBLEMS: the tile form runs a
+// whole warp for every (tile, stage) that holds at least one flagged lane, i.e. nearly all of them once 5 % of the problems are flagged.
+constexpr int RL_THREADS = 64;
+__global__ void __launch_bounds__(RL_THREADS) qs_redo_list_kernel(const smpc_problem_t* __restrict__ dP, QsBufs q, int kk, const int32_t* __restrict__ redo_list,
+                                                                  const int* __restrict__ n_list) {
+  if ((int)blockIdx.x >= *n_list) return;
+  const int slot = redo_list[blockIdx.x], tile = slot / TL, pl = slot % TL;
+  for (int k = threadIdx.x; k <= q.N; k += RL_THREADS) qs_step(*dP, q, tile, pl, k, kk, 2);
+  __syncthreads();
+  if (threadIdx.x == 0) qs_red(*dP, q, tile, pl, true);
 }
 
 // stage records, tile-interleaved -> caller layout [B][N+1][REC] (smpc_get_lin)
@@ -1032,6 +1050,7 @@ struct QpGroup {
   int32_t* mv = nullptr;        // compaction: [2][mv_half] source / destination slots
   int mv_half = 0;
   int* n_moves = nullptr;       // device
+  int32_t* redo_list = nullptr; // [32 T] slots flagged for the centering direction in the current iteration (qs_red_kernel)
   int in_use = 0;               // slots that may still hold an iterating problem (32 T at the start of a solve, less after a compaction)
   int tiles() const { return (in_use + TL - 1) / TL; }
 };
@@ -1046,6 +1065,10 @@ struct QpSolver {
   int* h_counters = nullptr;
   int32_t* mv = nullptr;        // compaction plans of the groups
   int* n_moves = nullptr;
+  int32_t* redo_list = nullptr;
+  int redo_list_max = -1;       // the centering switch runs one CTA per flagged problem when at most this many are flagged (-1: an eighth of the slots in
+                                // use; 0: never; SMPC_QP_REDO_LIST).  Measured on cfg[1] (gpurun_out/r2c25, 3 runs each): never 57.8 ms per step, 1/8 57.5,
+                                // 1/4 57.9, 1/2 58.8 -- the list kernel (254 registers, lane-strided accesses) only pays for a few hundred problems
   cudaEvent_t ev_in = nullptr;  // inputs (records, x0) are ready on the caller's stream
   int last_iters = 0;
   int solo_max = 384;           // a solve of at most this many problems per tile group is run by the solo kernel (one CTA per problem, whole iterations on
@@ -1098,6 +1121,8 @@ QpSolver* qp_create(int B, int N, int iter_max, bool keep_slots, cudaStream_t st
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_in, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaMalloc((void**)&s->mv, sizeof(int32_t) * ((size_t)s->T * TL + 2 * MAX_GROUPS));
   if (e == cudaSuccess) e = cudaMalloc((void**)&s->n_moves, sizeof(int) * MAX_GROUPS);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&s->redo_list, sizeof(int32_t) * (size_t)s->T * TL);
+  if (const char* pe = getenv("SMPC_QP_REDO_LIST")) s->redo_list_max = atoi(pe);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(qs_prep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PREP_SMEM);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(qs_prep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PREP_SMEM);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(qs_prep_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PC_SMEM);
@@ -1160,6 +1185,7 @@ QpSolver* qp_create(int B, int N, int iter_max, bool keep_slots, cudaStream_t st
     gr.mv_half = gr.T * TL / 2 + 1;
     gr.mv = s->mv + mv_off; mv_off += 2 * (size_t)gr.mv_half;
     gr.n_moves = s->n_moves + g;
+    gr.redo_list = s->redo_list + (size_t)t0 * TL;
     gr.in_use = gr.T * TL;
   }
   *err = cudaSuccess;
@@ -1182,6 +1208,7 @@ void qp_destroy(QpSolver* s) {
   if (s->h_counters) cudaFreeHost(s->h_counters);
   if (s->mv) cudaFree(s->mv);
   if (s->n_moves) cudaFree(s->n_moves);
+  if (s->redo_list) cudaFree(s->redo_list);
   delete s;
 }
 
@@ -1214,6 +1241,8 @@ struct DeviceBackend {
   double *xt, *ut; int32_t *status, *qp_iter, *qp_status; double* qp_res;
   int kk_last = 0;
   int n_active_last = 1 << 30;  // problems still iterating after the newest control kernel the host has seen
+  int n_redo_last = -1, n_redo_kk = -1;   // problems flagged for the centering direction in iteration n_redo_kk (the counters the host read last)
+  bool red_done = false;        // the list form of the centering switch has already taken the step length: the next red(true) is a no-op
   cudaError_t err = cudaSuccess;
   bool on_hi = false;
   bool trace_on() const { return s->profile || s->trace_print; }
@@ -1291,7 +1320,17 @@ struct DeviceBackend {
   void step(int kk, int mode) {
     if (mode == 0) { cudaStream_t stm_ = st(false); tr0("qs_step_kernel<0>", stm_); qs_step_kernel<0><<<sp_grid(), 32 * SP_WARPS, 0, stm_>>>(dP, g->q, tl(), kk); tr1(stm_); }
     else if (mode == 1) { cudaStream_t stm_ = st(false); tr0("qs_step_kernel<1>", stm_); qs_step_kernel<1><<<sp_grid(), 32 * SP_WARPS, 0, stm_>>>(dP, g->q, tl(), kk); tr1(stm_); }
-    else { cudaStream_t stm_ = st(false); tr0("qs_step_kernel<2>", stm_); qs_step_kernel<2><<<sp_grid(), 32 * SP_WARPS, 0, stm_>>>(dP, g->q, tl(), kk); tr1(stm_); }
+    else {
+      cudaStream_t stm_ = st(false);
+      tr0("qs_step_kernel<2>", stm_);
+      // (the host knows the number of flagged problems only when it has waited for the counters of THIS iteration: depth 0)
+      const int lim = s->redo_list_max < 0 ? g->in_use / 8 : s->redo_list_max;
+      if (n_redo_kk == kk && n_redo_last > 0 && n_redo_last <= lim) {
+        qs_redo_list_kernel<<<n_redo_last, RL_THREADS, 0, stm_>>>(dP, g->q, kk, g->redo_list, g->counters + 2 * kk + 1);
+        red_done = true;
+      } else qs_step_kernel<2><<<sp_grid(), 32 * SP_WARPS, 0, stm_>>>(dP, g->q, tl(), kk);
+      tr1(stm_);
+    }
     count();
   }
   // hand the rest of the solve (from the control phase of iteration kk on) to the solo kernel when few enough problems are left
@@ -1308,7 +1347,11 @@ struct DeviceBackend {
   }
   // results of the problems that have finished and not been written yet; all slots of the group (empty ones are skipped)
   void final() { { cudaStream_t stm_ = st(false); tr0("qs_final_kernel", stm_); qs_final_kernel<<<sp_grid_all(), 32 * SP_WARPS, 0, stm_>>>(g->q, g->T, s->B, act, status, xt, ut); tr1(stm_); } count(); }
-  void red(bool after) { { cudaStream_t stm_ = st(false); tr0("qs_red_kernel", stm_); qs_red_kernel<<<tl(), 32, 0, stm_>>>(dP, g->q, kk_last, after ? 1 : 0, g->counters); tr1(stm_); } count(); }
+  void red(bool after) {
+    if (after && red_done) { red_done = false; return; }
+    { cudaStream_t stm_ = st(false); tr0("qs_red_kernel", stm_); qs_red_kernel<<<tl(), 32, 0, stm_>>>(dP, g->q, kk_last, after ? 1 : 0, g->counters, g->redo_list); tr1(stm_); }
+    count();
+  }
   // Compaction between iteration kk and kk + 1 (qp_split.cuh: qs_compact_*), decided on the newest active count the host has seen --
   // an upper bound of the current one, the counts never grow: when it has fallen to 85 % of the slots in use (and by at least a
   // tile), the problems still iterating are packed into the leading slots and every later launch covers only those tiles.
@@ -1352,6 +1395,7 @@ struct DeviceBackend {
     if (e != cudaSuccess) { err = e; na = 0; nr = 0; return true; }     // stop iterating; the caller reports the error
     na = g->h_counters[2 * slot]; nr = g->h_counters[2 * slot + 1];
     n_active_last = na;
+    n_redo_last = nr; n_redo_kk = kk;
     if (s->trace_print) fprintf(stderr, "QPCOUNT g=%d kk=%d active=%d redo=%d in_use=%d\n", gi(), kk, na, nr, g->in_use);
     return true;
   }

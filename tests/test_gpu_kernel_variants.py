@@ -106,7 +106,9 @@ def test_host_loop_depth_and_compaction_agree_bitwise(controller):
     base = solve({'SMPC_QP_DEPTH': '0', 'SMPC_QP_COMPACT': '0'})       # one host round trip per iteration, no compaction
     assert len(set(base[3].tolist())) >= 6
     # ... and neither may the solo kernel (one CTA per problem, whole iterations on the device) that takes over the tail of a solve
+    # ... nor the form of the switch to the centering direction (one CTA per flagged problem when few are flagged, else a pass over the tiles)
     for env in ({'SMPC_QP_DEPTH': '3', 'SMPC_QP_COMPACT': '0'}, {'SMPC_QP_DEPTH': '0', 'SMPC_QP_COMPACT': '1'}, {},
+                {'SMPC_QP_REDO_LIST': '0'}, {'SMPC_QP_REDO_LIST': '100000'}, {'SMPC_QP_REDO_LIST': '100000', 'SMPC_QP_COMPACT': '0'},
                 {'SMPC_QP_SOLO': '384', 'SMPC_QP_SOLO_TAIL': '1'}, {'SMPC_QP_SOLO': '200', 'SMPC_QP_SOLO_TAIL': '1', 'SMPC_QP_COMPACT': '0'},
                 {'SMPC_QP_SOLO': '100000'}):
         other = solve(env)

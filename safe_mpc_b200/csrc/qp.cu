@@ -430,7 +430,7 @@ __global__ void __launch_bounds__(32 * SP_WARPS, QS_SP_MINB) qs_step_kernel(cons
 
 __global__ void __launch_bounds__(32) qs_ctl_kernel(const smpc_problem_t* __restrict__ dP, QsBufs q, int kk, int32_t* status, int32_t* qp_iter,
                                                      int32_t* qp_status, double* qp_res, int* counters) {
-  const bool on = qs_ctl(*dP, q, blockIdx.x, threadIdx.x, kk, status, qp_iter, qp_status, qp_res);
+  const bool on = qs_ctl<16>(*dP, q, blockIdx.x, threadIdx.x, kk, status, qp_iter, qp_status, qp_res);
   const unsigned m = __ballot_sync(0xffffffffu, on);
   if (threadIdx.x == 0 && m) atomicAdd(&counters[2 * kk], __popc(m));
 }

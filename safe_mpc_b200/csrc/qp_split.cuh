@@ -499,6 +499,9 @@ SMPC_HD void qs_prep(const smpc_problem_t& P, const QsBufs& q, int tile, int lan
 // ctl: residual norms of the new iterate, exit tests (same control flow as the oracle's QpIpm::solve), result.
 // thread = problem.  Returns true when the problem stays active.
 // ================================================================================================================
+// CH: stages whose residuals are loaded together (the per-tile kernel uses 16: qs_ctl 1.05 -> 0.69 ms per cfg[1] solve; 0 = plain loop: the solo
+// kernel, whose thread 0 runs this between the phases of a 255-register kernel, and the host emulation).  Same accumulation order either way.
+template <int CH = 0>
 SMPC_HD bool qs_ctl(const smpc_problem_t& P, const QsBufs& q, int tile, int lane, int kk_in, int32_t* status, int32_t* qp_iter,
                     int32_t* qp_status, double* qp_res) {
   const int N = q.N;
@@ -507,11 +510,35 @@ SMPC_HD bool qs_ctl(const smpc_problem_t& P, const QsBufs& q, int tile, int lane
   double* pd = q.pd + qs_pb(tile, NPD, lane);
   int kk = kk_in;
   double ng = 0.0, nb = 0.0, nd = 0.0, nm = 0.0, mu = 0.0, chk = 0.0, cnt = 0.0;
+  if constexpr (CH == 0) {
 #pragma unroll 8
-  for (int k = 0; k <= N; ++k) {
-    const double* res = q.res + qs_blk(tile, N, k, NRES, lane);
-    ng = fmax(ng, QF(res, R_NG)); nb = fmax(nb, QF(res, R_NB)); nd = fmax(nd, QF(res, R_ND)); nm = fmax(nm, QF(res, R_NM));
-    mu += QF(res, R_MU); chk += QF(res, R_CHK); cnt += QF(res, R_CNT);
+    for (int k = 0; k <= N; ++k) {
+      const double* res = q.res + qs_blk(tile, N, k, NRES, lane);
+      ng = fmax(ng, QF(res, R_NG)); nb = fmax(nb, QF(res, R_NB)); nd = fmax(nd, QF(res, R_ND)); nm = fmax(nm, QF(res, R_NM));
+      mu += QF(res, R_MU); chk += QF(res, R_CHK); cnt += QF(res, R_CNT);
+    }
+  } else {
+    // One warp per tile and a loop over the stages: the launch lasts as long as the load round trips of one thread, so the loop runs in
+    // chunks of CH stages -- all loads of a chunk first (112 in flight for CH = 16), then the accumulation in stage order.
+    constexpr int C = CH > 0 ? CH : 1;
+    for (int k0 = 0; k0 <= N; k0 += C) {
+      double v[C][7];
+#pragma unroll
+      for (int j = 0; j < C; ++j) {
+        if (k0 + j <= N) {
+          const double* res = q.res + qs_blk(tile, N, k0 + j, NRES, lane);
+          v[j][0] = QF(res, R_NG); v[j][1] = QF(res, R_NB); v[j][2] = QF(res, R_ND); v[j][3] = QF(res, R_NM);
+          v[j][4] = QF(res, R_MU); v[j][5] = QF(res, R_CHK); v[j][6] = QF(res, R_CNT);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < C; ++j) {
+        if (k0 + j <= N) {
+          ng = fmax(ng, v[j][0]); nb = fmax(nb, v[j][1]); nd = fmax(nd, v[j][2]); nm = fmax(nm, v[j][3]);
+          mu += v[j][4]; chk += v[j][5]; cnt += v[j][6];
+        }
+      }
+    }
   }
   if (kk == 0) QF(pi, J_NC) = (int)(cnt + 0.5);
   const int nc = QF(pi, J_NC);

@@ -29,6 +29,10 @@ constexpr int SP_WARPS = 4;      // warps per CTA of the stage-parallel kernels
 #ifndef QS_PREP_MINB
 #define QS_PREP_MINB 4
 #endif
+#ifndef QS_PC_ROLL
+#define QS_PC_ROLL 1             // unroll factor of the row loops of the cooperative prep kernel (1 = rolled)
+#endif
+constexpr int PC_ROLL = QS_PC_ROLL;
 #ifndef QS_SP_MINB
 #define QS_SP_MINB 3             // resident CTAs per SM the register allocation of prep / step is sized for
 #endif
@@ -235,14 +239,16 @@ __global__ void __launch_bounds__(32 * PC_WARPS, 2) qs_prep_coop_kernel(const sm
 #pragma unroll
       for (int j = 0; j < 10; ++j) QF(ito, I_PIM + j) = pimv[j];
     }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { double lo, hi; box(j, lo, hi); hard_row(j, z[5 + j], lo, hi); }
+    // (row loops are ROLLED, QS_PC_ROLL: the kernel is 111 KB of straight-line SASS run once per CTA by four warps at four different program
+    // counters, and the instruction fetch was its largest stall -- ncu: no_instruction 3.7 of 11 cycles per issue, L1.5 I-cache 32 KB)
+#pragma unroll PC_ROLL
+    for (int j = 0; j < 4; ++j) { double lo, hi; box(j, lo, hi); hard_row(j, QF(s_it, I_Z + 5 + j) + a * QF(s_st, I_Z + 5 + j), lo, hi); }
   } else if (wi == 1) {
-#pragma unroll
-    for (int j = 4; j < 10; ++j) { double lo, hi; box(j, lo, hi); hard_row(j, z[5 + j], lo, hi); }
+#pragma unroll PC_ROLL
+    for (int j = 4; j < 10; ++j) { double lo, hi; box(j, lo, hi); hard_row(j, QF(s_it, I_Z + 5 + j) + a * QF(s_st, I_Z + 5 + j), lo, hi); }
   } else if (wi == 2) {
     if (F.tau) {
-#pragma unroll
+#pragma unroll PC_ROLL
       for (int r = 0; r < 5; ++r) {
         double az = 0.0;
 #pragma unroll
@@ -253,7 +259,7 @@ __global__ void __launch_bounds__(32 * PC_WARPS, 2) qs_prep_coop_kernel(const sm
     }
   } else {
     if (F.dist) {
-#pragma unroll
+#pragma unroll PC_ROLL
       for (int p = 0; p < 6; ++p) {
         double az = 0.0;
 #pragma unroll
@@ -323,7 +329,7 @@ __global__ void __launch_bounds__(32 * PC_WARPS, 2) qs_prep_coop_kernel(const sm
 #pragma unroll
     for (int j = 0; j < 10; ++j) { rg[5 + j] += QF(s_it, I_LAM + j); gd[5 + j] += QF(s_it, I_LAM + QNR + j); }
     if (F.tau) {
-#pragma unroll
+#pragma unroll PC_ROLL
       for (int r = 0; r < 5; ++r) {
         const double nu = QF(s_it, I_LAM + 10 + r), gam = QF(s_it, I_LAM + QNR + 10 + r);
 #pragma unroll
@@ -331,7 +337,7 @@ __global__ void __launch_bounds__(32 * PC_WARPS, 2) qs_prep_coop_kernel(const sm
       }
     }
     if (F.dist) {
-#pragma unroll
+#pragma unroll PC_ROLL
       for (int p = 0; p < 6; ++p) {
         const double nu = QF(s_it, I_LAM + 15 + p), gam = QF(s_it, I_LAM + QNR + 15 + p);
 #pragma unroll
@@ -367,6 +373,8 @@ __global__ void __launch_bounds__(32 * PC_WARPS, 2) qs_prep_coop_kernel(const sm
     // ---- merge: rows of the condensed stage matrix H + reg + C' Gam C (warp 1: rows 0-8, 2: 9-11, 3: 12-14) ----
     const double hu = (k == N) ? 1.0 : QF(rs, SMPC_REC_HU) + reg;
     const double hq = QF(rs, SMPC_REC_HQ) + reg, hv = QF(rs, SMPC_REC_HV) + reg;
+    // (the row loops of this phase stay unrolled: it runs after the CTA barrier, on the critical path of the work item, and rolled it loses
+    // the overlap between the rows -- prep 13.4 -> 14.1 ms per cfg[1] solve, gpurun_out/r2c32)
     double Gg[12];
 #pragma unroll
     for (int r = 0; r < 12; ++r) {

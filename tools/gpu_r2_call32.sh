@@ -1,0 +1,19 @@
+#!/bin/bash
+# cooperative prep: constraint-row loops of the merge phase rolled too
+cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
+O=gpurun_out/r2c32; mkdir -p $O
+timeout 900 python -m pytest tests/test_gpu_kernel_variants.py tests/test_gpu_precision_f32.py -x -q -m gpu > $O/tests.log 2>&1; echo "tests rc=$?" >> $O/summary.txt
+run() { tag=$1; shift; for i in 1 2 3; do env "$@" timeout 600 python bench.py --steps 30 --warmup 3 --no-mlp --no-cpu --no-e2e $EXTRA > $O/${tag}_$i.json 2> $O/${tag}_$i.err; done; }
+run new X=1
+run prev SMPC_LIB=$PWD/build/variants/libprev.so
+cat $O/summary.txt; tail -3 $O/tests.log
+python - <<'PY'
+import json,glob,collections
+r=collections.defaultdict(list)
+for f in sorted(glob.glob('gpurun_out/r2c32/*.json')):
+    try: d=json.load(open(f))
+    except Exception: continue
+    k=d.get('qp_solve',{}).get('kernel_ms',{})
+    r[f.split('/')[-1].rsplit('_',1)[0]].append((d['ms_per_step'], d['p50_step_ms'], d['p99_step_ms'], k.get('qs_prep'), d['roofline_kernels']['qs_prep']['hbm_frac']))
+for k,v in r.items(): print(k, ' '.join('%.2f/%.2f/%.1f[prep %s ms, %.3f]'%t for t in v))
+PY

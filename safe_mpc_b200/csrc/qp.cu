@@ -29,6 +29,9 @@ constexpr int SP_WARPS = 4;      // warps per CTA of the stage-parallel kernels
 #ifndef QS_PREP_MINB
 #define QS_PREP_MINB 4
 #endif
+#ifndef QS_PC_SBND
+#define QS_PC_SBND 1             // cooperative prep: row bounds of the stage in shared memory (prep 13.6 -> 13.0 ms per cfg[1] solve, gpurun_out/r2c34)
+#endif
 #ifndef QS_PC_ROLL
 #define QS_PC_ROLL 1             // unroll factor of the row loops of the cooperative prep kernel (1 = rolled)
 #endif
@@ -75,7 +78,7 @@ constexpr int PC_NPART = 6;                               // residual-norm parti
 // staged: previous iterate (fp64), stage record and step (storage type); the fp32 flavour keeps the fp64 partials of the warps in an array of
 // their own (the fp64 flavour parks them in consumed slots of the staged step, as before: two CTAs of 107.5 KB per SM)
 constexpr size_t PC_SMEM = sizeof(double) * NIT * TL + sizeof(qs_real) * (PC_NREC + NIT) * TL +
-                           (sizeof(qs_real) == 8 ? 0 : sizeof(double) * PC_WARPS * PC_NPART * TL) + 16;
+                           (sizeof(qs_real) == 8 ? 0 : sizeof(double) * PC_WARPS * PC_NPART * TL) + 16 + sizeof(double) * 36;
 static_assert(PC_REC0 + PC_NREC > SMPC_REC_HQ && PC_REC0 + PC_NREC <= SMPC_REC, "staged record range");
 
 __device__ __forceinline__ void pc_row_out(double* s_it, int sl, double nu, double gam, double G) {
@@ -111,6 +114,22 @@ __global__ void __launch_bounds__(32 * PC_WARPS, 2) qs_prep_coop_kernel(const sm
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sm_st)),
                  "l"(g_st_blk), "r"(nb_st), "r"(smem_u32(bar)) : "memory");
   }
+  // (tried: issuing the staging before the activity flags are read, so that the two round trips overlap -- 0.3 ms per step slower)
+  const StageFlags F = qs_flags(P, k);
+  // bounds of the rows of this stage -> shared memory: the row loops are rolled, and a bound read from the problem block in global memory
+  // with a run-time row index would put a load round trip into every iteration (ncu source page: 6.6 % of the samples on those DADDs)
+  double* sbnd = reinterpret_cast<double*>(bar + 2);        // [0,10) box lower, [10,20) box upper, [20,25) [25,30) torque, [30,36) capsule lower
+  if (QS_PC_SBND && threadIdx.x < 36) {
+    const int t = threadIdx.x;
+    const bool rr = P.controller == SMPC_CTRL_REAL_RECEDING;
+    double v;
+    if (t < 10) v = k == N ? P.lbx_e[t] : (rr ? P.x_min[t] : P.lbx[t]);
+    else if (t < 20) v = k == N ? P.ubx_e[t - 10] : (rr ? P.x_max[t - 10] : P.ubx[t - 10]);
+    else if (t < 25) v = P.tau_min[t - 20];
+    else if (t < 30) v = P.tau_max[t - 25];
+    else v = P.pair_lo_ocp[t - 30];
+    sbnd[t] = v;
+  }
   // lane views: field f of the record at rs[f * TL] (valid for PC_REC0 <= f < PC_REC0 + PC_NREC)
   const qs_real* rs = sm_rec - (size_t)PC_REC0 * TL + lane;
   double* s_it = sm_it + lane;
@@ -130,7 +149,6 @@ __global__ void __launch_bounds__(32 * PC_WARPS, 2) qs_prep_coop_kernel(const sm
   const int rrec = QF(pi, J_R);
   double* ito = q.it[kk & 1] + qs_blk(tile, N, k, NIT, lane);
   qs_real* hc = q.sb + qs_blk(tile, N, k, NHC, lane);
-  const StageFlags F = qs_flags(P, k);
   const double lam_min = 1e-16, t_min = 1e-16, reg = P.qp_reg_prim;
   const double dt = P.dt, a2 = 0.5 * P.dt * P.dt;
 
@@ -169,11 +187,16 @@ __global__ void __launch_bounds__(32 * PC_WARPS, 2) qs_prep_coop_kernel(const sm
   auto box = [&](int j, double& lo, double& hi) {
     const double xk = QF(rs, SMPC_REC_X + j);
     if (k == 0) { lo = QF(pd, D_X0 + j) - xk; hi = lo; }
+    else if (k < N && P.controller == SMPC_CTRL_REAL_RECEDING && k == rrec) {
+      const double c = QF(q.rec + qs_blk(tile, N, k + 1, REC, lane), SMPC_REC_X + j); lo = c - 1e-3 - xk; hi = c + 1e-3 - xk;
+    }
+#if QS_PC_SBND
+    else { lo = sbnd[j] - xk; hi = sbnd[10 + j] - xk; }
+#else
     else if (k == N) { lo = P.lbx_e[j] - xk; hi = P.ubx_e[j] - xk; }
-    else if (P.controller == SMPC_CTRL_REAL_RECEDING) {
-      if (k == rrec) { const double c = QF(q.rec + qs_blk(tile, N, k + 1, REC, lane), SMPC_REC_X + j); lo = c - 1e-3 - xk; hi = c + 1e-3 - xk; }
-      else { lo = P.x_min[j] - xk; hi = P.x_max[j] - xk; }
-    } else { lo = P.lbx[j] - xk; hi = P.ubx[j] - xk; }
+    else if (P.controller == SMPC_CTRL_REAL_RECEDING) { lo = P.x_min[j] - xk; hi = P.x_max[j] - xk; }
+    else { lo = P.lbx[j] - xk; hi = P.ubx[j] - xk; }
+#endif
   };
   QsNorms nr;
   nr.ng = nr.nb = nr.nd = nr.nm = nr.mu = nr.chk = 0.0; nr.cnt = 0;
@@ -254,7 +277,11 @@ __global__ void __launch_bounds__(32 * PC_WARPS, 2) qs_prep_coop_kernel(const sm
 #pragma unroll
         for (int c = 0; c < 15; ++c) az += QF(rs, SMPC_REC_JTAU + r * 15 + c) * z[c];
         const double v = QF(rs, SMPC_REC_TAU + r);
+#if QS_PC_SBND
+        hard_row(10 + r, az, sbnd[20 + r] - v, sbnd[25 + r] - v);
+#else
         hard_row(10 + r, az, P.tau_min[r] - v, P.tau_max[r] - v);
+#endif
       }
     }
   } else {
@@ -265,7 +292,11 @@ __global__ void __launch_bounds__(32 * PC_WARPS, 2) qs_prep_coop_kernel(const sm
 #pragma unroll
         for (int c = 0; c < 5; ++c) az += QF(rs, SMPC_REC_JDIST + p * 5 + c) * z[5 + c];
         const double v = QF(rs, SMPC_REC_DIST + p);
+#if QS_PC_SBND
+        hard_row(15 + p, az, sbnd[30 + p] - v, P.pair_hi - v);
+#else
         hard_row(15 + p, az, P.pair_lo_ocp[p] - v, P.pair_hi - v);
+#endif
       }
     }
     if (F.nn) {

@@ -1,5 +1,5 @@
 #!/bin/bash
-# cooperative prep: constraint-row loops of the merge phase rolled too
+# cooperative prep variants: bitwise tests + A/B against libprev.so (the build before the rolled loops)
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 O=gpurun_out/r2c32; mkdir -p $O
 timeout 900 python -m pytest tests/test_gpu_kernel_variants.py tests/test_gpu_precision_f32.py -x -q -m gpu > $O/tests.log 2>&1; echo "tests rc=$?" >> $O/summary.txt

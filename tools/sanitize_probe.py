@@ -35,3 +35,7 @@ run({'SMPC_QP_SOLO': '384'}, precision='f32')
 run({'SMPC_QP_SOLO': '20', 'SMPC_QP_SOLO_TAIL': '1', 'SMPC_QP_TAIL': '40'}, B=130)
 run({'SMPC_QP_SOLO': '384'}, controller='constraint_everywhere', nn_precision='tf32x3')
 run({'SMPC_QP_SOLO': '384', 'SMPC_MLP_TC': 'pair'}, controller='receding', nn_precision='tf32x3')
+# round 2, later additions: slot compaction with the lane = move kernel (40 tiles, problems of very different iteration counts), the
+# centering switch per flagged problem (list form forced / never), cooperative prep with rolled row loops and bounds in shared memory
+run({'SMPC_QP_SOLO': '0', 'SMPC_QP_REDO_LIST': '100000'}, B=1280, N=10)
+run({'SMPC_QP_SOLO': '0', 'SMPC_QP_REDO_LIST': '0', 'SMPC_QP_TAIL': '0'}, controller='real_receding', B=1280, N=10)

@@ -37,7 +37,9 @@ constexpr int SP_WARPS = 4;      // warps per CTA of the stage-parallel kernels
 #endif
 constexpr int PC_ROLL = QS_PC_ROLL;
 #ifndef QS_SP_MINB
-#define QS_SP_MINB 3             // resident CTAs per SM the register allocation of prep / step is sized for
+#define QS_SP_MINB 2             // resident CTAs per SM the register allocation of the step kernels is sized for.  2 = 255 registers, no spills, 8 warps
+                                 // per SM: cfg[1] 55.0 -> 53.4 ms per step against 3 (168 registers, spills between the load phases; 4: 59.9 ms) with one
+                                 // tile group (gpurun_out/r2c43); round 1 had measured 3 as the best with three concurrent tile groups
 #endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

@@ -22,7 +22,10 @@ inline namespace QS_FLAVOUR {
 
 namespace {
 
-constexpr int SP_WARPS = 4;      // warps per CTA of the stage-parallel kernels
+#ifndef QS_SP_WARPS
+#define QS_SP_WARPS 2            // (2 / 4 / 8 warps per CTA at the same 8 warps per SM: cfg[1] 53.2 / 53.5 / 54.0 ms per step, gpurun_out/r2c46)
+#endif
+constexpr int SP_WARPS = QS_SP_WARPS;   // warps per CTA of the stage-parallel kernels
 #ifndef QS_RIC_NBUF
 #define QS_RIC_NBUF 1            // staging buffers of the Riccati sweeps (1: more resident warps per SM, no fetch overlap)
 #endif
@@ -37,9 +40,9 @@ constexpr int SP_WARPS = 4;      // warps per CTA of the stage-parallel kernels
 #endif
 constexpr int PC_ROLL = QS_PC_ROLL;
 #ifndef QS_SP_MINB
-#define QS_SP_MINB 2             // resident CTAs per SM the register allocation of the step kernels is sized for.  2 = 255 registers, no spills, 8 warps
-                                 // per SM: cfg[1] 55.0 -> 53.4 ms per step against 3 (168 registers, spills between the load phases; 4: 59.9 ms) with one
-                                 // tile group (gpurun_out/r2c43); round 1 had measured 3 as the best with three concurrent tile groups
+#define QS_SP_MINB 4             // resident CTAs (of SP_WARPS = 2 warps) per SM the register allocation of the step kernels is sized for: 255 registers, no spills, 8 warps
+                                 // per SM.  Measured with four warps per CTA and one tile group (gpurun_out/r2c43): 8 warps per SM 53.4 ms per cfg[1] step, 12 warps
+                                 // (168 registers, spills between the load phases: the round-1 setting, found with three concurrent tile groups) 55.0 ms, 16 warps 59.9 ms
 #endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

@@ -347,14 +347,19 @@ def run_engine(a):
     dname = {'qs_prep': 'qs_prep_coop_kernel / qs_prep_kernel', 'qs_ric1': 'qs_ric1x_kernel / qs_ric1t_kernel', 'qs_ric2': 'qs_ric2_kernel / qs_ric2t_kernel',
              'qs_step0': 'qs_step_kernel<0>', 'qs_step1': 'qs_step_kernel<1>', 'qs_solo': 'qs_solo_kernel'}[dom]
     d = table[dom]
-    traffic = {'qs_prep': 2.42e9, 'qs_ric1': 1.47e9, 'qs_ric2': 1.31e9}.get(dom) if (B, N) == (10000, 45) else None
+    # ncu --set full captures of the round-2 kernels, one all-active launch each (dram__bytes_read.sum + dram__bytes_write.sum)
+    ncu_traffic = {'qs_prep': (1.549120e9 + 0.930624e9, 'profiles/r02_prep_coop_rolled_raw.csv'),
+                   'qs_ric1': (0.876355e9 + 0.582946e9, 'profiles/r02_ric1x_raw.csv'),
+                   'qs_ric2': (1.219103e9 + 0.277923e9, 'profiles/r02_ric2_raw.csv')}
+    traffic, traffic_file = ncu_traffic.get(dom, (None, None)) if (B, N) == (10000, 45) else (None, None)
     # bytes the whole solve moves per problem against what is algorithmically necessary (~11 KB per problem and RTI iteration)
     moved = sum(table[k]['bytes_per_visit'] for k in table if 'bytes_per_visit' in table[k] and not (k == 'qs_prep' and 'qs_solo' in table)) * visits / B
     necessary = ((N + 1) * abi.NX + N * abi.NU) * 8 * 2 + 200
     flops_solve = 0.48e6 * (N + 1) / 46.0 * it_sum                              # 0.48 MFLOP per IPM iteration at N = 45
     value = solves_all / (ms_max * 1e-3)
     roofline = {'kernel': dname, 'bound': 'hbm', 'achieved': d['hbm_gbs'], 'peak': hbm_peak, 'unit': 'GB/s', 'frac': d['hbm_frac'],
-                'traffic': traffic, 'traffic_source': 'ncu dram__bytes_read+write of one all-active launch, profiles/r01_qp_v7.md (B=10000, N=45 only)',
+                'traffic': traffic, 'traffic_source': 'ncu dram__bytes_read+write of one all-active launch (313 tiles x %d stages), %s (B=10000, N=45 only)' % (N + 1, traffic_file),
+                'traffic_algorithmic_all_active': d['bytes_per_visit'] * 313 * 32 * (N + 1) if traffic else None,
                 'peak_source': peak_src, 'selection': 'the QP kernel family with the largest summed duration in one solve (kernel_ms below)',
                 'algorithmic_bytes_per_launch': d['bytes_per_visit'] * visits / max(1, d['launches']), 'launch_ms': d['ms_per_solve'] / max(1, d['launches']),
                 'launches_per_solve': d['launches'], 'share_of_qp_solve': d['share_of_qp_solve'],

@@ -232,6 +232,13 @@ int smpc_plant_step(smpc_handle_t* h, const double* x, const double* u,
 /* --- pieces exposed for parity tests and for the host-side mirror of AdamModel --- */
 /* tau_fun(x,u) (env_model.py:80-83), n rows */
 int smpc_tau(smpc_handle_t* h, int32_t n, const double* x, const double* u, double* tau, int32_t mem);
+/* Torque-input dynamics with sensitivities -- extension row (f)4 of SURVEY.md section 8 (north_star: "RNEA/ABA inside an explicit RK4
+   integrator that emits state/control sensitivities"); the reference has no counterpart call: its OCP dynamics are the constant
+   double integrator f_fun (env_model.py:58-71).  x' = [v; M(q)^-1 (tau - h(q, v))] with the reference's mass_matrix_fun /
+   bias_force_fun (env_model.py:42-43) on the controller model; one explicit RK4 step of length dt for n rows:
+   x_next [n][10], A = d x_next / d x [n][10][10], B = d x_next / d tau [n][10][5] (row-major; A and / or B may be NULL). */
+int smpc_rk4_sens(smpc_handle_t* h, int32_t n, const double* x, const double* tau, double dt,
+                  double* x_next, double* A, double* B, int32_t mem);
 /* ee_fun(x) (env_model.py:91-95) [n][3] and the 6 collision-constraint values (env_model.py:263-271) [n][6] */
 int smpc_kinematics(smpc_handle_t* h, int32_t n, const double* x, double* ee, double* dist, int32_t mem);
 /* nn_func_x(x): c(x) with the handle's alpha (safe_set.py:100-102) and its gradient [n][NX] (grad may be NULL) */

@@ -546,6 +546,48 @@ void mass_bias(const orc_problem_t& P, const double inertial[][10], const double
   }
 }
 
+// Torque-input dynamics x' = [v; M(q)^-1 (tau - h(q, v))] on the controller model, one explicit RK4 step, sensitivities by
+// forward-mode AD (Dual<15>: 10 state + 5 torque directions) of the plain restatement -- independent of the hand-derived
+// inverse-dynamics tangents the CUDA path uses.  Extension row (f)4 of SURVEY.md section 8: the reference has no torque-input
+// transcription (env_model.py:58-71 is the double integrator); M and h are its mass_matrix_fun / bias_force_fun (env_model.py:42-43).
+template <class T>
+void forward_dynamics(const orc_problem_t& P, const T* x, const T* tau, T* a) {
+  T zero[NQ], g0[NQ], bias[NQ], M[NQ * NQ], L[NQ * NQ], y[NQ];
+  for (int i = 0; i < NQ; ++i) zero[i] = T(0.0);
+  rnea<T>(P, P.inertial, x, x + NQ, zero, bias);
+  rnea<T>(P, P.inertial, x, zero, zero, g0);
+  for (int j = 0; j < NQ; ++j) {
+    T e[NQ], col[NQ];
+    for (int i = 0; i < NQ; ++i) e[i] = T(i == j ? 1.0 : 0.0);
+    rnea<T>(P, P.inertial, x, zero, e, col);
+    for (int i = 0; i < NQ; ++i) M[i * NQ + j] = col[i] - g0[i];
+  }
+  for (int i = 0; i < NQ * NQ; ++i) L[i] = T(0.0);
+  for (int j = 0; j < NQ; ++j) {
+    T d = M[j * NQ + j];
+    for (int k = 0; k < j; ++k) d = d - L[j * NQ + k] * L[j * NQ + k];
+    L[j * NQ + j] = sqrt(d);
+    for (int i = j + 1; i < NQ; ++i) {
+      T s = M[i * NQ + j];
+      for (int k = 0; k < j; ++k) s = s - L[i * NQ + k] * L[j * NQ + k];
+      L[i * NQ + j] = s / L[j * NQ + j];
+    }
+  }
+  for (int i = 0; i < NQ; ++i) { T s = tau[i] - bias[i]; for (int k = 0; k < i; ++k) s = s - L[i * NQ + k] * y[k]; y[i] = s / L[i * NQ + i]; }
+  for (int i = NQ - 1; i >= 0; --i) { T s = y[i]; for (int k = i + 1; k < NQ; ++k) s = s - L[k * NQ + i] * a[k]; a[i] = s / L[i * NQ + i]; }
+}
+template <class T>
+void rk4_step(const orc_problem_t& P, double dt, const T* x, const T* tau, T* xn) {
+  T k[4][NX], xi[NX], a[NQ];
+  const double c[4] = {0.0, 0.5, 0.5, 1.0};
+  for (int s = 0; s < 4; ++s) {
+    for (int i = 0; i < NX; ++i) xi[i] = s == 0 ? x[i] : x[i] + k[s - 1][i] * (c[s] * dt);
+    forward_dynamics<T>(P, xi, tau, a);
+    for (int i = 0; i < NQ; ++i) { k[s][i] = xi[NQ + i]; k[s][NQ + i] = a[i]; }
+  }
+  for (int i = 0; i < NX; ++i) xn[i] = x[i] + (k[0][i] + k[1][i] * 2.0 + k[2][i] * 2.0 + k[3][i]) * (dt / 6.0);
+}
+
 // AdamModel.integrate (env_model.py:192-206)
 void plant_step_one(const orc_handle& h, int b, const double* x, const double* u, double* xn, double* a) {
   const orc_problem_t& P = h.P;
@@ -692,6 +734,21 @@ int orc_plant_step(orc_handle_t* h, const double* x, const double* u, double* xn
 
 int orc_tau(orc_handle_t* h, int32_t n, const double* x, const double* u, double* tau) {
   for (int i = 0; i < n; ++i) rnea<double>(h->P, h->P.inertial, x + (size_t)i * NX, x + (size_t)i * NX + NQ, u + (size_t)i * NU, tau + (size_t)i * NU);
+  return SMPC_OK;
+}
+int orc_rk4_sens(orc_handle_t* h, int32_t n, const double* x, const double* tau, double dt, double* xn, double* A, double* B) {
+  using D = orc::Dual<NX + NU>;
+  parallel_for(n, h->threads, [&](int i, int) {
+    D xd[NX], td[NU], out[NX];
+    for (int j = 0; j < NX; ++j) xd[j] = D::var(x[(size_t)i * NX + j], j);
+    for (int j = 0; j < NU; ++j) td[j] = D::var(tau[(size_t)i * NU + j], NX + j);
+    rk4_step<D>(h->P, dt, xd, td, out);
+    for (int r = 0; r < NX; ++r) {
+      xn[(size_t)i * NX + r] = out[r].v;
+      if (A) for (int j = 0; j < NX; ++j) A[((size_t)i * NX + r) * NX + j] = out[r].d[j];
+      if (B) for (int j = 0; j < NU; ++j) B[((size_t)i * NX + r) * NU + j] = out[r].d[NX + j];
+    }
+  });
   return SMPC_OK;
 }
 int orc_kinematics(orc_handle_t* h, int32_t n, const double* x, double* ee, double* dist) {

@@ -72,6 +72,8 @@ int orc_controller_step_scripted(orc_handle_t* h, const double* x, const int32_t
                                  uint8_t* abort_flag);
 int orc_plant_step(orc_handle_t* h, const double* x, const double* u, double* x_next, double* a_applied);
 int orc_tau(orc_handle_t* h, int32_t n, const double* x, const double* u, double* tau);
+/* torque-input RK4 step with sensitivities (forward-mode AD); counterpart of smpc_rk4_sens */
+int orc_rk4_sens(orc_handle_t* h, int32_t n, const double* x, const double* tau, double dt, double* x_next, double* A, double* B);
 int orc_kinematics(orc_handle_t* h, int32_t n, const double* x, double* ee, double* dist);
 int orc_nn_constraint(orc_handle_t* h, int32_t n, const double* x, double* c, double* grad);
 int orc_get_lin(orc_handle_t* h, double* lin);

@@ -178,6 +178,21 @@ class EngineBase:
         self._call('tau', C.c_int32(n), px, pu, po, mem=self._mem(mx, mu))
         return out
 
+    def rk4_sens(self, x, tau, dt, sens=True):
+        """torque-input dynamics x' = [v; M(q)^-1 (tau - h(q, v))], one explicit RK4 step -> (x_next [n, 10], A [n, 10, 10], B [n, 10, 5])
+        with A = d x_next / d x, B = d x_next / d tau; sens=False: x_next only"""
+        n = len(x)
+        px, mx, kx = self._in(x, np.float64, (n, abi.NX))
+        pt, mt, kt = self._in(tau, np.float64, (n, abi.NU))
+        xn, pn, _ = self._out((n, abi.NX), np.float64, x)
+        if sens:
+            A, pa, _ = self._out((n, abi.NX, abi.NX), np.float64, x)
+            Bm, pb, _ = self._out((n, abi.NX, abi.NU), np.float64, x)
+        else:
+            A = Bm = None; pa = pb = _P(0)
+        self._call('rk4_sens', C.c_int32(n), px, pt, C.c_double(dt), pn, pa, pb, mem=self._mem(mx, mt))
+        return (xn, A, Bm) if sens else xn
+
     def kinematics(self, x):
         n = len(x)
         px, mx, kx = self._in(x, np.float64, (n, abi.NX))

@@ -473,6 +473,25 @@ int smpc_tau(smpc_handle_t* h, int32_t n, const double* x, const double* u, doub
   return copy_out(h, tau, s + bx + bu, bu, mem);
 }
 
+int smpc_rk4_sens(smpc_handle_t* h, int32_t n, const double* x, const double* tau, double dt, double* x_next, double* A, double* B, int32_t mem) {
+  if (n <= 0) return SMPC_OK;
+  if (!x || !tau || !x_next || !(dt > 0.0)) return fail(h, SMPC_ERR_ARG, "rk4_sens: x, tau, x_next must be given and dt > 0");
+  const size_t bx = sizeof(double) * n * NX, bu = sizeof(double) * n * NU, ba = A ? bx * NX : 0, bb = B ? bx * NU : 0;
+  if (mem == SMPC_DEVICE) { launch_rk4_sens(h->ctx(), h->dP, n, dt, x, tau, x_next, A, B); return check_launch(h, "rk4_sens"); }
+  int rc = stage_reserve(h, 2 * bx + bu + ba + bb); if (rc) return rc;
+  char* s = (char*)h->stage;
+  double *dx = (double*)s, *dt_ = (double*)(s + bx), *dn = (double*)(s + bx + bu), *dA = A ? (double*)(s + 2 * bx + bu) : nullptr,
+         *dB = B ? (double*)(s + 2 * bx + bu + ba) : nullptr;
+  rc = copy_in(h, dx, x, bx, mem); if (rc) return rc;
+  rc = copy_in(h, dt_, tau, bu, mem); if (rc) return rc;
+  launch_rk4_sens(h->ctx(), h->dP, n, dt, dx, dt_, dn, dA, dB);
+  rc = check_launch(h, "rk4_sens"); if (rc) return rc;
+  rc = copy_out(h, x_next, dn, bx, mem); if (rc) return rc;
+  if (A) { rc = copy_out(h, A, dA, ba, mem); if (rc) return rc; }
+  if (B) { rc = copy_out(h, B, dB, bb, mem); if (rc) return rc; }
+  return SMPC_OK;
+}
+
 int smpc_kinematics(smpc_handle_t* h, int32_t n, const double* x, double* ee, double* dist, int32_t mem) {
   if (n <= 0) return SMPC_OK;
   const size_t bx = sizeof(double) * n * NX, be = sizeof(double) * n * 3, bd = sizeof(double) * n * NPAIR;

@@ -571,4 +571,100 @@ SMPC_HD void plant_step(const smpc_problem_t& P, const double (*Iplant)[10], con
   f_disc(P.dt, x, a, xn);
 }
 
+// ------------------------------------------------------------------------ torque-input dynamics with sensitivities
+// Extension row (f)4 of SURVEY.md section 8 (north_star: "RNEA/ABA inside an explicit RK4 integrator that emits state/control
+// sensitivities").  The reference's OCP dynamics are the constant double integrator (env_model.py:58-71); its torque model
+// tau = M(q) u + h(q, v) (env_model.py:42-43,80-83) is inverted here, on the controller model:
+//     x' = f(x, tau) = [ v ; a ],   a = M(q)^-1 (tau - h(q, v))
+// First derivatives from the identity  d ID / d(q, v) + M d a / d(q, v) = 0  at a = FD(q, v, tau)  (the inverse-dynamics tangents
+// are the ones the linearisation already uses: rnea_tangent):
+//     da/dtau = M^-1,   da/dq = -M^-1 dID/dq |_(q, v, a),   da/dv = -M^-1 dID/dv |_(q, v, a)
+// All matrices row-major 5x5.
+SMPC_HD void chol5(const double* M, double* L) {
+  for (int i = 0; i < NQ * NQ; ++i) L[i] = 0.0;
+  for (int j = 0; j < NQ; ++j) {
+    double d = M[j * NQ + j];
+    for (int k = 0; k < j; ++k) d -= L[j * NQ + k] * L[j * NQ + k];
+    L[j * NQ + j] = sqrt(d);
+    for (int i = j + 1; i < NQ; ++i) {
+      double s = M[i * NQ + j];
+      for (int k = 0; k < j; ++k) s -= L[i * NQ + k] * L[j * NQ + k];
+      L[i * NQ + j] = s / L[j * NQ + j];
+    }
+  }
+}
+SMPC_HD void chol5_solve(const double* L, const double* b, double* y) {
+  double t[NQ];
+  for (int i = 0; i < NQ; ++i) { double s = b[i]; for (int k = 0; k < i; ++k) s -= L[i * NQ + k] * t[k]; t[i] = s / L[i * NQ + i]; }
+  for (int i = NQ - 1; i >= 0; --i) { double s = t[i]; for (int k = i + 1; k < NQ; ++k) s -= L[k * NQ + i] * y[k]; y[i] = s / L[i * NQ + i]; }
+}
+
+SMPC_HD void fd_sens(const smpc_problem_t& P, const double (*I)[10], const double* x, const double* tau, double* a, double* Aq,
+                     double* Av, double* Mi) {
+  Rnea S;
+  double M[NQ * NQ], L[NQ * NQ], h[NQ], d[NQ], y[NQ];
+  const double zero[NQ] = {0, 0, 0, 0, 0};
+  rnea(P, I, x, x + NQ, zero, S, h);
+  for (int j = 0; j < NQ; ++j) {
+    rnea_tangent<TAN_U>(P, I, S, x + NQ, zero, j, d);
+    for (int i = 0; i < NQ; ++i) M[i * NQ + j] = d[i];
+  }
+  chol5(M, L);
+  for (int i = 0; i < NQ; ++i) d[i] = tau[i] - h[i];
+  chol5_solve(L, d, a);
+  rnea(P, I, x, x + NQ, a, S, h);                      // nominal pass at the solved acceleration (h: scratch, = tau)
+  for (int j = 0; j < NQ; ++j) {
+    rnea_tangent<TAN_Q>(P, I, S, x + NQ, a, j, d);
+    chol5_solve(L, d, y);
+    for (int i = 0; i < NQ; ++i) Aq[i * NQ + j] = -y[i];
+    rnea_tangent<TAN_V>(P, I, S, x + NQ, a, j, d);
+    chol5_solve(L, d, y);
+    for (int i = 0; i < NQ; ++i) Av[i * NQ + j] = -y[i];
+    for (int i = 0; i < NQ; ++i) d[i] = i == j ? 1.0 : 0.0;
+    chol5_solve(L, d, y);
+    for (int i = 0; i < NQ; ++i) Mi[i * NQ + j] = y[i];
+  }
+}
+
+// One explicit RK4 step of length dt of x' = f(x, tau) with the discrete-time sensitivities
+//     A = d x_next / d x  [10][10],   B = d x_next / d tau  [10][5]      (row-major)
+// propagated through the four stages: with S_i = d x_i / d(x, tau) = [I 0] + c_i dt dK_{i-1} (c = 0, 1/2, 1/2, 1) the stage slope
+// K_i = f(x_i, tau) has  dK_i = [ S_i(v rows) ; Aq_i S_i(q rows) + Av_i S_i(v rows) + [0 | Minv_i] ],  and
+//     [A B] = [I 0] + dt/6 (dK_1 + 2 dK_2 + 2 dK_3 + dK_4)       AB: [10][15] row-major, columns 0-9 = A, 10-14 = B.
+SMPC_HD void rk4_sens(const smpc_problem_t& P, const double (*I)[10], double dt, const double* x, const double* tau, double* xn,
+                      double* AB) {
+  constexpr int NC = NX + NU;                           // sensitivity columns: x (10), tau (5)
+  double dK[NX * NC], K[NX], ka[NX], xi[NX];
+  double a[NQ], Aq[NQ * NQ], Av[NQ * NQ], Mi[NQ * NQ];
+  for (int i = 0; i < NX * NC; ++i) { dK[i] = 0.0; AB[i] = 0.0; }
+  for (int i = 0; i < NX; ++i) { K[i] = 0.0; ka[i] = 0.0; }
+  for (int st = 0; st < 4; ++st) {
+    const double c = st == 0 ? 0.0 : (st == 3 ? 1.0 : 0.5), wgt = (st == 0 || st == 3) ? 1.0 : 2.0;
+    for (int i = 0; i < NX; ++i) xi[i] = x[i] + c * dt * K[i];
+    fd_sens(P, I, xi, tau, a, Aq, Av, Mi);
+    for (int i = 0; i < NQ; ++i) { K[i] = xi[NQ + i]; K[NQ + i] = a[i]; }
+    for (int i = 0; i < NX; ++i) ka[i] += wgt * K[i];
+    for (int j = 0; j < NC; ++j) {                      // column j of dK_{st-1} -> column j of S -> column j of dK_st, in place
+      double Sc[NX];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) Sc[i] = (i == j ? 1.0 : 0.0) + c * dt * dK[i * NC + j];
+#pragma unroll
+      for (int i = 0; i < NQ; ++i) {
+        double s = j >= NX ? Mi[i * NQ + (j - NX)] : 0.0;
+#pragma unroll
+        for (int k = 0; k < NQ; ++k) s += Aq[i * NQ + k] * Sc[k] + Av[i * NQ + k] * Sc[NQ + k];
+        dK[i * NC + j] = Sc[NQ + i];
+        dK[(NQ + i) * NC + j] = s;
+        AB[i * NC + j] += wgt * Sc[NQ + i];
+        AB[(NQ + i) * NC + j] += wgt * s;
+      }
+    }
+  }
+  const double w6 = dt / 6.0;
+  for (int i = 0; i < NX; ++i) {
+    xn[i] = x[i] + w6 * ka[i];
+    for (int j = 0; j < NC; ++j) AB[i * NC + j] = (i == j ? 1.0 : 0.0) + w6 * AB[i * NC + j];
+  }
+}
+
 }  // namespace smpc

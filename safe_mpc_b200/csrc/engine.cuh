@@ -88,6 +88,7 @@ void launch_par_post(const LaunchCtx& c, const smpc_problem_t* dP, int B, int N,
 void launch_plant(const LaunchCtx& c, const smpc_problem_t* dP, int B, const double* inertial, const double* noise, const double* x,
                   const double* u, const uint8_t* act, double* xn, double* a);
 void launch_tau(const LaunchCtx& c, const smpc_problem_t* dP, int n, const double* x, const double* u, double* tau);
+void launch_rk4_sens(const LaunchCtx& c, const smpc_problem_t* dP, int n, double dt, const double* x, const double* tau, double* xn, double* A, double* B);
 void launch_kin(const LaunchCtx& c, const smpc_problem_t* dP, int n, const double* x, double* ee, double* dist);
 void launch_fill_i32(const LaunchCtx& c, int32_t* p, int n, int32_t v);
 void launch_fill_f64(const LaunchCtx& c, double* p, size_t n, double v);

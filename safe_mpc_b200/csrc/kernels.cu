@@ -567,6 +567,38 @@ void launch_tau(const LaunchCtx& c, const smpc_problem_t* dP, int n, const doubl
   tau_kernel<<<GRID1D(n, 64), 64, 0, c.stream>>>(dP, n, x, u, tau);
   ++*c.launches;
 }
+// Torque-input dynamics, one explicit RK4 step with sensitivities (dev_model.cuh: rk4_sens).  thread = row.
+// The row's state / torque are read and its 160 outputs written with the caller's row-major layout: a warp's stores of one output
+// field are strided by the row size, so the results are first collected in shared memory and written out by the whole CTA in
+// consecutive addresses (one coalesced pass per output array).
+constexpr int RK4_THREADS = 32, RK4_NC = NX + NU;          // (static shared memory: 32 x 151 doubles = 38.7 KB)
+__global__ void __launch_bounds__(RK4_THREADS) rk4_sens_kernel(const smpc_problem_t* __restrict__ dP, int n, double dt, const double* __restrict__ x,
+                                                              const double* __restrict__ tau, double* xn, double* A, double* B) {
+  __shared__ double so[RK4_THREADS * (NX * RK4_NC + 1)];      // [A B] of every row of the CTA, one padding word per row against bank conflicts
+  const int i0 = blockIdx.x * RK4_THREADS, i = i0 + threadIdx.x, rows = min(RK4_THREADS, n - i0);
+  double* AB = so + threadIdx.x * (NX * RK4_NC + 1);
+  double xo[NX];
+  if (i < n) {
+    double xx[NX], tt[NU];
+    for (int q = 0; q < NX; ++q) xx[q] = x[(size_t)i * NX + q];
+    for (int q = 0; q < NU; ++q) tt[q] = tau[(size_t)i * NU + q];
+    rk4_sens(*dP, dP->inertial, dt, xx, tt, xo, AB);
+    for (int q = 0; q < NX; ++q) xn[(size_t)i * NX + q] = xo[q];
+  }
+  __syncthreads();
+  if (A) for (int e = threadIdx.x; e < rows * NX * NX; e += RK4_THREADS) {
+    const int r = e / (NX * NX), q = e % (NX * NX);
+    A[(size_t)i0 * NX * NX + e] = so[r * (NX * RK4_NC + 1) + (q / NX) * RK4_NC + q % NX];
+  }
+  if (B) for (int e = threadIdx.x; e < rows * NX * NU; e += RK4_THREADS) {
+    const int r = e / (NX * NU), q = e % (NX * NU);
+    B[(size_t)i0 * NX * NU + e] = so[r * (NX * RK4_NC + 1) + (q / NU) * RK4_NC + NX + q % NU];
+  }
+}
+void launch_rk4_sens(const LaunchCtx& c, const smpc_problem_t* dP, int n, double dt, const double* x, const double* tau, double* xn, double* A, double* B) {
+  rk4_sens_kernel<<<GRID1D(n, RK4_THREADS), RK4_THREADS, 0, c.stream>>>(dP, n, dt, x, tau, xn, A, B);
+  ++*c.launches;
+}
 __global__ void kin_kernel(const smpc_problem_t* __restrict__ dP, int n, const double* __restrict__ x, double* ee, double* dist) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;

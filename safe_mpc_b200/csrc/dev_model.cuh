@@ -599,6 +599,7 @@ SMPC_HD void chol5_solve(const double* L, const double* b, double* y) {
   for (int i = NQ - 1; i >= 0; --i) { double s = t[i]; for (int k = i + 1; k < NQ; ++k) s -= L[k * NQ + i] * y[k]; y[i] = s / L[i * NQ + i]; }
 }
 
+template <bool SENS>
 SMPC_HD void fd_sens(const smpc_problem_t& P, const double (*I)[10], const double* x, const double* tau, double* a, double* Aq,
                      double* Av, double* Mi) {
   Rnea S;
@@ -612,6 +613,7 @@ SMPC_HD void fd_sens(const smpc_problem_t& P, const double (*I)[10], const doubl
   chol5(M, L);
   for (int i = 0; i < NQ; ++i) d[i] = tau[i] - h[i];
   chol5_solve(L, d, a);
+  if (!SENS) return;
   rnea(P, I, x, x + NQ, a, S, h);                      // nominal pass at the solved acceleration (h: scratch, = tau)
   for (int j = 0; j < NQ; ++j) {
     rnea_tangent<TAN_Q>(P, I, S, x + NQ, a, j, d);
@@ -630,40 +632,51 @@ SMPC_HD void fd_sens(const smpc_problem_t& P, const double (*I)[10], const doubl
 //     A = d x_next / d x  [10][10],   B = d x_next / d tau  [10][5]      (row-major)
 // propagated through the four stages: with S_i = d x_i / d(x, tau) = [I 0] + c_i dt dK_{i-1} (c = 0, 1/2, 1/2, 1) the stage slope
 // K_i = f(x_i, tau) has  dK_i = [ S_i(v rows) ; Aq_i S_i(q rows) + Av_i S_i(v rows) + [0 | Minv_i] ],  and
-//     [A B] = [I 0] + dt/6 (dK_1 + 2 dK_2 + 2 dK_3 + dK_4)       AB: [10][15] row-major, columns 0-9 = A, 10-14 = B.
+//     [A B] = [I 0] + dt/6 (dK_1 + 2 dK_2 + 2 dK_3 + dK_4).   SENS = false: x_next only (no tangent passes).
+template <bool SENS>
 SMPC_HD void rk4_sens(const smpc_problem_t& P, const double (*I)[10], double dt, const double* x, const double* tau, double* xn,
-                      double* AB) {
+                      double* A, double* B) {
   constexpr int NC = NX + NU;                           // sensitivity columns: x (10), tau (5)
-  double dK[NX * NC], K[NX], ka[NX], xi[NX];
-  double a[NQ], Aq[NQ * NQ], Av[NQ * NQ], Mi[NQ * NQ];
-  for (int i = 0; i < NX * NC; ++i) { dK[i] = 0.0; AB[i] = 0.0; }
+  double dK[SENS ? NX * NC : 1], K[NX], ka[NX], xi[NX];
+  double a[NQ], Aq[SENS ? NQ * NQ : 1], Av[SENS ? NQ * NQ : 1], Mi[SENS ? NQ * NQ : 1];
+  if (SENS) {
+    for (int i = 0; i < NX * NC; ++i) dK[i] = 0.0;
+    for (int i = 0; i < NX * NX; ++i) A[i] = 0.0;
+    for (int i = 0; i < NX * NU; ++i) B[i] = 0.0;
+  }
   for (int i = 0; i < NX; ++i) { K[i] = 0.0; ka[i] = 0.0; }
   for (int st = 0; st < 4; ++st) {
     const double c = st == 0 ? 0.0 : (st == 3 ? 1.0 : 0.5), wgt = (st == 0 || st == 3) ? 1.0 : 2.0;
     for (int i = 0; i < NX; ++i) xi[i] = x[i] + c * dt * K[i];
-    fd_sens(P, I, xi, tau, a, Aq, Av, Mi);
+    fd_sens<SENS>(P, I, xi, tau, a, Aq, Av, Mi);
     for (int i = 0; i < NQ; ++i) { K[i] = xi[NQ + i]; K[NQ + i] = a[i]; }
     for (int i = 0; i < NX; ++i) ka[i] += wgt * K[i];
-    for (int j = 0; j < NC; ++j) {                      // column j of dK_{st-1} -> column j of S -> column j of dK_st, in place
-      double Sc[NX];
+    if (SENS)
+      for (int j = 0; j < NC; ++j) {                    // column j of dK_{st-1} -> column j of S -> column j of dK_st, in place
+        double Sc[NX];
 #pragma unroll
-      for (int i = 0; i < NX; ++i) Sc[i] = (i == j ? 1.0 : 0.0) + c * dt * dK[i * NC + j];
+        for (int i = 0; i < NX; ++i) Sc[i] = (i == j ? 1.0 : 0.0) + c * dt * dK[i * NC + j];
+        double* out = j < NX ? A + j : B + (j - NX);    // accumulated column j of [A B]
+        const int ld = j < NX ? NX : NU;
 #pragma unroll
-      for (int i = 0; i < NQ; ++i) {
-        double s = j >= NX ? Mi[i * NQ + (j - NX)] : 0.0;
+        for (int i = 0; i < NQ; ++i) {
+          double s = j >= NX ? Mi[i * NQ + (j - NX)] : 0.0;
 #pragma unroll
-        for (int k = 0; k < NQ; ++k) s += Aq[i * NQ + k] * Sc[k] + Av[i * NQ + k] * Sc[NQ + k];
-        dK[i * NC + j] = Sc[NQ + i];
-        dK[(NQ + i) * NC + j] = s;
-        AB[i * NC + j] += wgt * Sc[NQ + i];
-        AB[(NQ + i) * NC + j] += wgt * s;
+          for (int k = 0; k < NQ; ++k) s += Aq[i * NQ + k] * Sc[k] + Av[i * NQ + k] * Sc[NQ + k];
+          dK[i * NC + j] = Sc[NQ + i];
+          dK[(NQ + i) * NC + j] = s;
+          out[i * ld] += wgt * Sc[NQ + i];
+          out[(NQ + i) * ld] += wgt * s;
+        }
       }
-    }
   }
   const double w6 = dt / 6.0;
   for (int i = 0; i < NX; ++i) {
     xn[i] = x[i] + w6 * ka[i];
-    for (int j = 0; j < NC; ++j) AB[i * NC + j] = (i == j ? 1.0 : 0.0) + w6 * AB[i * NC + j];
+    if (SENS) {
+      for (int j = 0; j < NX; ++j) A[i * NX + j] = (i == j ? 1.0 : 0.0) + w6 * A[i * NX + j];
+      for (int j = 0; j < NU; ++j) B[i * NU + j] = w6 * B[i * NU + j];
+    }
   }
 }
 

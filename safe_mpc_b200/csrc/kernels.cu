@@ -571,32 +571,34 @@ void launch_tau(const LaunchCtx& c, const smpc_problem_t* dP, int n, const doubl
 // The row's state / torque are read and its 160 outputs written with the caller's row-major layout: a warp's stores of one output
 // field are strided by the row size, so the results are first collected in shared memory and written out by the whole CTA in
 // consecutive addresses (one coalesced pass per output array).
-constexpr int RK4_THREADS = 32, RK4_NC = NX + NU;          // (static shared memory: 32 x 151 doubles = 38.7 KB)
+constexpr int RK4_THREADS = 32;          // static shared memory: 32 x 101 doubles = 25.9 KB -> 8 CTAs (8 warps, the 255-register limit) per SM
+template <bool SENS>
 __global__ void __launch_bounds__(RK4_THREADS) rk4_sens_kernel(const smpc_problem_t* __restrict__ dP, int n, double dt, const double* __restrict__ x,
                                                               const double* __restrict__ tau, double* xn, double* A, double* B) {
-  __shared__ double so[RK4_THREADS * (NX * RK4_NC + 1)];      // [A B] of every row of the CTA, one padding word per row against bank conflicts
+  constexpr int LDS = NX * NX + 1;                            // A of one row + one padding word against bank conflicts
+  __shared__ double so[SENS ? RK4_THREADS * LDS : 1];
   const int i0 = blockIdx.x * RK4_THREADS, i = i0 + threadIdx.x, rows = min(RK4_THREADS, n - i0);
-  double* AB = so + threadIdx.x * (NX * RK4_NC + 1);
-  double xo[NX];
+  double xo[NX], Bo[SENS ? NX * NU : 1];
   if (i < n) {
     double xx[NX], tt[NU];
     for (int q = 0; q < NX; ++q) xx[q] = x[(size_t)i * NX + q];
     for (int q = 0; q < NU; ++q) tt[q] = tau[(size_t)i * NU + q];
-    rk4_sens(*dP, dP->inertial, dt, xx, tt, xo, AB);
+    rk4_sens<SENS>(*dP, dP->inertial, dt, xx, tt, xo, SENS ? so + threadIdx.x * LDS : nullptr, Bo);
     for (int q = 0; q < NX; ++q) xn[(size_t)i * NX + q] = xo[q];
   }
+  if (!SENS) return;
   __syncthreads();
-  if (A) for (int e = threadIdx.x; e < rows * NX * NX; e += RK4_THREADS) {
-    const int r = e / (NX * NX), q = e % (NX * NX);
-    A[(size_t)i0 * NX * NX + e] = so[r * (NX * RK4_NC + 1) + (q / NX) * RK4_NC + q % NX];
-  }
-  if (B) for (int e = threadIdx.x; e < rows * NX * NU; e += RK4_THREADS) {
-    const int r = e / (NX * NU), q = e % (NX * NU);
-    B[(size_t)i0 * NX * NU + e] = so[r * (NX * RK4_NC + 1) + (q / NU) * RK4_NC + NX + q % NU];
+  if (A) for (int e = threadIdx.x; e < rows * NX * NX; e += RK4_THREADS) A[(size_t)i0 * NX * NX + e] = so[(e / (NX * NX)) * LDS + e % (NX * NX)];
+  if (B) {
+    __syncthreads();
+    if (i < n) for (int q = 0; q < NX * NU; ++q) so[threadIdx.x * LDS + q] = Bo[q];
+    __syncthreads();
+    for (int e = threadIdx.x; e < rows * NX * NU; e += RK4_THREADS) B[(size_t)i0 * NX * NU + e] = so[(e / (NX * NU)) * LDS + e % (NX * NU)];
   }
 }
 void launch_rk4_sens(const LaunchCtx& c, const smpc_problem_t* dP, int n, double dt, const double* x, const double* tau, double* xn, double* A, double* B) {
-  rk4_sens_kernel<<<GRID1D(n, RK4_THREADS), RK4_THREADS, 0, c.stream>>>(dP, n, dt, x, tau, xn, A, B);
+  if (A || B) rk4_sens_kernel<true><<<GRID1D(n, RK4_THREADS), RK4_THREADS, 0, c.stream>>>(dP, n, dt, x, tau, xn, A, B);
+  else rk4_sens_kernel<false><<<GRID1D(n, RK4_THREADS), RK4_THREADS, 0, c.stream>>>(dP, n, dt, x, tau, xn, A, B);
   ++*c.launches;
 }
 __global__ void kin_kernel(const smpc_problem_t* __restrict__ dP, int n, const double* __restrict__ x, double* ee, double* dist) {

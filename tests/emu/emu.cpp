@@ -41,12 +41,8 @@ int emu_plant_step(const smpc_problem_t* P, int n, const double* inertial, const
 
 int emu_rk4_sens(const smpc_problem_t* P, int n, const double* x, const double* tau, double dt, double* xn, double* A, double* B) {
   for (int i = 0; i < n; ++i) {
-    double AB[NX * (NX + NU)];
-    rk4_sens(*P, P->inertial, dt, x + i * NX, tau + i * NU, xn + i * NX, AB);
-    for (int r = 0; r < NX; ++r) {
-      for (int c = 0; c < NX; ++c) A[((size_t)i * NX + r) * NX + c] = AB[r * (NX + NU) + c];
-      for (int c = 0; c < NU; ++c) B[((size_t)i * NX + r) * NU + c] = AB[r * (NX + NU) + NX + c];
-    }
+    if (A && B) rk4_sens<true>(*P, P->inertial, dt, x + i * NX, tau + i * NU, xn + i * NX, A + (size_t)i * NX * NX, B + (size_t)i * NX * NU);
+    else rk4_sens<false>(*P, P->inertial, dt, x + i * NX, tau + i * NU, xn + i * NX, nullptr, nullptr);
   }
   return 0;
 }

@@ -29,8 +29,8 @@ def test_rk4_sens_matches_oracle():
         xg, Ag, Bg = eng.rk4_sens(x, tau, dt)
         xo, Ao, Bo = orc.rk4_sens(x, tau, dt)
         assert _rel(xg, xo) < 1e-10 and _rel(Ag, Ao) < 1e-10 and _rel(Bg, Bo) < 1e-10
-    # value-only call writes the same x_next
-    np.testing.assert_array_equal(eng.rk4_sens(x, tau, 0.02, sens=False), xg)
+    # the value-only kernel (no tangent passes) gives the same x_next
+    assert _rel(eng.rk4_sens(x, tau, 0.02, sens=False), xg) < 1e-13
 
 
 def test_rk4_sens_device_buffers_and_errors():

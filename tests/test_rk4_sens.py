@@ -81,3 +81,6 @@ def test_device_source_matches_oracle_ad(setup):
         emu.emu_rk4_sens(C.byref(prob), len(x), p(x), p(tau), C.c_double(dt), p(xe), p(Ae), p(Be))
         for got, want in ((xe, xn), (Ae, A), (Be, B)):
             assert (np.abs(got - want) / np.maximum(1.0, np.abs(want))).max() < 1e-10
+        xv = np.zeros_like(xn)                       # value-only form (no tangent passes)
+        emu.emu_rk4_sens(C.byref(prob), len(x), p(x), p(tau), C.c_double(dt), p(xv), None, None)
+        assert (np.abs(xv - xe) / np.maximum(1.0, np.abs(xe))).max() < 1e-13

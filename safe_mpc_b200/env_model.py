@@ -129,6 +129,12 @@ class AdamModel:
         plant, double-integrator update.  -> (x_next [B, nx], applied acceleration [B, nu])."""
         return self.engine().plant_step(self._rows(x), self._rows(u))
 
+    def integrate_torque_rk4(self, x, tau, dt=None, sens=True):
+        """Extension (no reference counterpart): rows of states / joint torques through one explicit RK4
+        step of x' = [v; M(q)^-1 (tau - h(q, v))] on the controller model -> (x_next, A = d x_next / d x, B = d x_next / d tau),
+        or x_next alone with sens=False (smpc_rk4_sens)."""
+        return self.engine().rk4_sens(self._rows(x), self._rows(tau), float(self.params.dt if dt is None else dt), sens=sens)
+
     # ---- perturbed plants / noise (env_model.py:321-331, utils.py:126-171) -----------------------------------------
     def update_randomized_dynamics(self, inertial=None, noise_percent=None, seed=0, controller_name=None):
         """Per-problem plant parameters [B, nq, 10].  The reference reloads ``z1_randomized<name>.urdf`` per test; here the

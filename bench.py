@@ -290,8 +290,10 @@ def run_engine(a):
 
     # ---- the viability network kernels timed alone on the row count of configs[2] (a row per problem and stage) ----
     mlp = None
+    rk4 = None
     if rank == 0 and not a.no_mlp:
         mlp = time_mlp(params, md, B * N, local_rank, dev)
+        rk4 = time_rk4(params, md, B * (N + 1), local_rank, dev)
 
     # ---- aggregate over ranks ----
     vec = [ms, solves, ipm, l1 - l0, (e2e['seconds'] if e2e else 0.0), (e2e['solves'] if e2e else 0.0)]
@@ -419,6 +421,9 @@ def run_engine(a):
         mlp['tensor_peak_tf32_tflops'] = tpeak
         mlp['tf32x3']['frac_of_tensor_peak'] = mlp['tf32x3']['executed_tf32_tflops'] / tpeak
         line['viability_network'] = mlp
+    if rk4:
+        rk4['fp64_frac'] = rk4['fp64_tflops'] / fp64_peak
+        line['torque_input_rk4'] = rk4
     if e2e:
         e2e_s = max(v[4] for v in allv)
         line['e2e'] = {'value': sum(v[5] for v in allv) / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': e2e['h2d'], 'd2h_bytes_per_step': e2e['d2h'],
@@ -429,6 +434,39 @@ def run_engine(a):
         line['cpu_baseline'] = {'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': 'port', 'sample': r['sample'],
                                 'ipm_iterations_per_solve': r['ipm_per_solve']}
     print(json.dumps(line), flush=True)
+
+
+def time_rk4(params, md, n_rows, device_index, dev):
+    """Extension kernel of SURVEY 8(f)4, not on the closed-loop path: one torque-input RK4 step with sensitivities (smpc_rk4_sens) for a
+    row per (problem, stage), buffers resident in HBM."""
+    import torch
+    from safe_mpc_b200.engine import Engine
+    rng = np.random.default_rng(9)
+    mid, half = 0.5 * (md.x_min + md.x_max), 0.5 * (md.x_max - md.x_min)
+    x = mid + 0.8 * half * rng.uniform(-1, 1, (n_rows, abi.NX))
+    x[:, abi.NQ:] *= 0.6
+    xd = torch.tensor(x, device=dev); td = torch.tensor(rng.uniform(-8, 8, (n_rows, abi.NU)), device=dev)
+    prob, keep = build_problem(params, 'naive', cost='ext', model=md)
+    eng = Engine(prob, 64, device_index)
+    stream = torch.cuda.ExternalStream(eng.stream(), device=dev)
+    out = {'kernel': 'rk4_sens_kernel', 'rows': n_rows, 'flop_per_row': 81657,
+           'flop_source': 'executed FP64 instructions under ncu (2 DFMA + DADD + DMUL per row): profiles/r02_rk4_sens.md',
+           'note': 'extension beyond the reference formulation (SURVEY 8(f)4), not part of the timed closed loop'}
+    for sens in (True, False):
+        eng.rk4_sens(xd, td, params.dt, sens=sens); eng.sync()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+        ev[0].record(stream)
+        for i in range(5):
+            eng.rk4_sens(xd, td, params.dt, sens=sens)
+            ev[i + 1].record(stream)
+        eng.sync(); torch.cuda.synchronize()
+        ms = float(np.median([ev[i].elapsed_time(ev[i + 1]) for i in range(5)]))
+        if sens:
+            out.update({'ms': ms, 'rows_per_s': n_rows / (ms * 1e-3), 'fp64_tflops': n_rows * 81657 / (ms * 1e-3) / 1e12})
+        else:
+            out['ms_value_only'] = ms
+    eng.close()
+    return out
 
 
 def time_mlp(params, md, n_rows, device_index, dev):

@@ -46,5 +46,24 @@ def main():
         print(name, 'status', status.tolist(), 'iters', it.tolist(), '->', out)
 
 
+def main_rk4():
+    """tests/golden/rk4_sens.npz: the torque-input RK4 step with sensitivities (extension row (f)4) of the oracle's forward-mode AD."""
+    from tests.common import random_states
+    prob, params, md = make_problem('st')
+    o = Oracle(prob, 4, 1)
+    x = random_states(md, 48, seed=201, vel_scale=0.6)
+    tau = np.random.default_rng(202).uniform(-8, 8, (48, 5))
+    dts = np.array([params.dt, 0.02])
+    res = [o.rk4_sens(x, tau, float(dt)) for dt in dts]
+    out = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'rk4_sens.npz')
+    np.savez_compressed(out, x=x, tau=tau, dt=dts, x_next=np.array([r[0] for r in res]), A=np.array([r[1] for r in res]),
+                        B=np.array([r[2] for r in res]))
+    print('rk4_sens ->', out)
+
+
 if __name__ == '__main__':
-    main()
+    if 'rk4' in sys.argv[1:]:
+        main_rk4()
+    else:
+        main()
+        main_rk4()

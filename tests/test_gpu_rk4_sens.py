@@ -68,3 +68,13 @@ def test_rk4_sens_full_size_property():
     idx = rng.choice(n, 2000, replace=False)
     xo, Ao, Bo = orc.rk4_sens(x[idx], tau[idx], dt)
     assert _rel(xn[idx], xo) < 1e-10 and _rel(A[idx], Ao) < 1e-10 and _rel(B[idx], Bo) < 1e-10
+
+
+def test_rk4_sens_matches_the_golden_vectors():
+    """tests/golden/rk4_sens.npz (oracle forward-mode AD, tests/golden/make_golden.py rk4)"""
+    import os
+    eng, orc, params, md = _pair()
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'rk4_sens.npz'))
+    for i, dt in enumerate(g['dt']):
+        xn, A, B = eng.rk4_sens(g['x'], g['tau'], float(dt))
+        assert _rel(xn, g['x_next'][i]) < 1e-10 and _rel(A, g['A'][i]) < 1e-10 and _rel(B, g['B'][i]) < 1e-10

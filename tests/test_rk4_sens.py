@@ -84,3 +84,25 @@ def test_device_source_matches_oracle_ad(setup):
         xv = np.zeros_like(xn)                       # value-only form (no tangent passes)
         emu.emu_rk4_sens(C.byref(prob), len(x), p(x), p(tau), C.c_double(dt), p(xv), None, None)
         assert (np.abs(xv - xe) / np.maximum(1.0, np.abs(xe))).max() < 1e-13
+
+
+def _golden():
+    import os
+    return np.load(os.path.join(os.path.dirname(__file__), 'golden', 'rk4_sens.npz'))
+
+
+def test_oracle_and_device_source_reproduce_the_golden_vectors(setup):
+    """tests/golden/rk4_sens.npz (tests/golden/make_golden.py rk4): regression pin of the oracle, fixture of the kernel source"""
+    from tests.emu import load
+    emu = load()
+    prob, params, md, o = setup
+    g = _golden()
+    x, tau = g['x'], g['tau']
+    p = lambda a: C.c_void_p(a.ctypes.data)
+    for i, dt in enumerate(g['dt']):
+        xn, A, B = o.rk4_sens(x, tau, float(dt))
+        xe = np.zeros_like(xn); Ae = np.zeros_like(A); Be = np.zeros_like(B)
+        emu.emu_rk4_sens(C.byref(prob), len(x), p(x), p(tau), C.c_double(float(dt)), p(xe), p(Ae), p(Be))
+        for got, emu_got, want in ((xn, xe, g['x_next'][i]), (A, Ae, g['A'][i]), (B, Be, g['B'][i])):
+            assert (np.abs(got - want) / np.maximum(1.0, np.abs(want))).max() < 1e-12
+            assert (np.abs(emu_got - want) / np.maximum(1.0, np.abs(want))).max() < 1e-10
